@@ -1,0 +1,198 @@
+/*
+ * wfm_b200.h — C-ABI of the B200 waveform sampling engine (libwfmb200.so).
+ *
+ * The reference (feihoo87/waveforms 2.2.3) has no FFI for this path: the seam
+ * is Python-level.  Each entry point below names the reference call it
+ * replaces (paths relative to /root/reference):
+ *
+ *   wfm_program_create   – the walk over (bounds, seq) that
+ *                          waveforms/_waveform.pyx:155-169 (calc_parts) does
+ *                          per call; here the piecewise program is uploaded
+ *                          once as a flat IR and reused.
+ *   wfm_sample           – Waveform.sample / Waveform.__call__ /
+ *                          WaveVStack.__call__  (waveforms/waveform.py:173-207,
+ *                          :529-563, :679-693) = np.arange + calc_parts +
+ *                          _calc/_apply + basis functions
+ *                          (_waveform.pyx:130-152, :290-371;
+ *                          multy_drag.py:158-232) + np.clip + _fill_parts.
+ *   wfm_sample_host      – same, with HOST output buffers (device->host copy
+ *                          inside the call): the end-to-end path.
+ *   wfm_sosfilt          – scipy.signal.sosfilt call sites
+ *                          waveforms/waveform.py:200-203, :249 and
+ *                          scipy.signal.lfilter in distortion.py:321.
+ *   wfm_fft_filter       – np.fft.fft / ifft in distortion.py:208-221
+ *                          (reflection, correct_reflection) and
+ *                          scipy.signal.fftconvolve in distortion.py:329-333.
+ *
+ * Conventions: plain C structs of pointers and counts; every function returns
+ * 0 on success or a negative WFM_E* code (no exceptions cross the ABI), and
+ * wfm_last_error() returns a thread-local message.  Device output buffers are
+ * caller-owned (the library never frees them).  Calls are asynchronous with
+ * respect to `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ * stream) unless the name ends in _host.  One program lives on one device;
+ * multi-GPU callers create one program per device holding that device's shard
+ * of the channels (no collective is involved anywhere on this path).
+ */
+#ifndef WFM_B200_H
+#define WFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFM_ABI_VERSION 1
+
+/* error codes */
+#define WFM_OK            0
+#define WFM_EINVAL       -1  /* malformed IR / bad argument            */
+#define WFM_ECUDA        -2  /* CUDA runtime error (see last_error)    */
+#define WFM_ENOMEM       -3
+#define WFM_EUNSUPPORTED -4  /* basis id or mode not implemented       */
+
+/* basis-function ids — identical to the reference's registration order
+ * (_waveform.pyx:374-388; multy_drag.py:177, :214) */
+enum {
+  WFM_LINEAR = 1, WFM_GAUSSIAN = 2, WFM_ERF = 3, WFM_COS = 4, WFM_SINC = 5,
+  WFM_EXP = 6, WFM_INTERP = 7, WFM_LINEARCHIRP = 8, WFM_EXPONENTIALCHIRP = 9,
+  WFM_HYPERBOLICCHIRP = 10, WFM_COSH = 11, WFM_SINH = 12, WFM_DRAG = 13,
+  WFM_MOLLIFIER = 14, WFM_D_GAUSSIAN = 15, WFM_DRAG_SIN = 16,
+  WFM_DRAG_SINX = 17,
+  /* lowering-only ops (never appear in Waveform objects) */
+  WFM_COS_ROT = 32  /* cos(w(x-shift)) derived from an earlier COS factor of
+                       the same segment with equal w by an exact-difference
+                       rotation; see DESIGN.md §K1 */
+};
+
+/* WfmWave.flags */
+#define WFM_WAVE_EXPLICIT_X     0x1u  /* x read from the x array at x_off     */
+#define WFM_WAVE_LAST_OVERRIDE  0x2u  /* x[n-1] = x_last (np.linspace endpoint) */
+#define WFM_WAVE_CLIP           0x4u  /* np.clip(v, clip_lo, clip_hi) on non-zero segments */
+#define WFM_WAVE_PRESHIFT       0x8u  /* x' = x - pre_shift (WaveVStack.shift) */
+#define WFM_WAVE_COMPLEX        0x10u /* channel has complex amplitudes        */
+
+/* one output channel (a Waveform, or a whole WaveVStack) — 96 bytes */
+typedef struct WfmWave {
+  double   t0;        /* affine grid: x[j] = t0 + j*delta (multiply, then add; never fused) */
+  double   delta;
+  double   x_last;
+  double   clip_lo, clip_hi;
+  double   pre_shift;
+  double   offset;    /* accumulator start (WaveVStack.offset), 0 otherwise */
+  int64_t  n;         /* number of samples */
+  int64_t  out_off;   /* index of this channel's first sample in the output buffer */
+  int64_t  x_off;     /* index of its first abscissa in the explicit-x buffer */
+  int32_t  seg_begin; /* first row in the segment table */
+  int32_t  n_seg;     /* rows; the last one has bound +inf */
+  uint32_t flags;
+  uint32_t reserved;
+} WfmWave;
+
+/* per segment: where its distinct factors and its terms start; row n_segs
+ * closes the table — 8 bytes */
+typedef struct WfmSegPtr {
+  int32_t fac;
+  int32_t term;
+} WfmSegPtr;
+
+/* one distinct basis-function evaluation f(x - shift, args) — 32 bytes */
+typedef struct WfmFactor {
+  int32_t func;     /* WFM_* id */
+  int32_t arg_off;  /* first extra argument in the f64 argument pool */
+  double  shift;
+  double  a0, a1;   /* the first two scalar arguments, inline */
+} WfmFactor;
+
+/* WfmTerm.flags */
+#define WFM_TERM_GROUP_END 0x1u /* last term of a stack member: fold the group sum into the channel accumulator */
+
+/* amp * prod(refs) — 32 bytes */
+typedef struct WfmTerm {
+  double   amp_re, amp_im;
+  int32_t  ref_begin;
+  int32_t  n_ref;
+  uint32_t flags;
+  uint32_t reserved;
+} WfmTerm;
+
+/* WfmRef.kind */
+#define WFM_POW_ONE  0   /* exponent == 1: multiply by the factor value        */
+#define WFM_POW_INT  1   /* small integer exponent: repeated multiplication    */
+#define WFM_POW_GEN  2   /* pow(value, expo)                                   */
+
+/* factor-slot ^ exponent — 16 bytes */
+typedef struct WfmRef {
+  double  expo;
+  int32_t slot;   /* index into the segment's factor list */
+  int32_t kind;
+} WfmRef;
+
+/* host-side view of a lowered batch; all pointers are HOST pointers */
+typedef struct WfmProgramDesc {
+  int64_t n_waves;   const WfmWave*   waves;
+  int64_t n_segs;    const double*    seg_bound; /* [n_segs] upper bounds        */
+                     const WfmSegPtr* seg_ptr;   /* [n_segs + 1]                 */
+  int64_t n_facs;    const WfmFactor* facs;
+  int64_t n_terms;   const WfmTerm*   terms;
+  int64_t n_refs;    const WfmRef*    refs;
+  int64_t n_args;    const double*    args;      /* f64 argument / table pool    */
+  int64_t n_x;       const double*    x;         /* explicit abscissae (may be NULL) */
+} WfmProgramDesc;
+
+typedef struct WfmProgram* wfm_program_t;
+
+/* output element types */
+#define WFM_F64 0
+#define WFM_F32 1
+#define WFM_C128 2  /* interleaved (re, im) doubles */
+
+typedef struct WfmLaunch {
+  int64_t first_wave;  /* channels [first_wave, first_wave + n_wave) */
+  int64_t n_wave;      /* 0 = all from first_wave                    */
+  int32_t dtype;       /* WFM_F64 | WFM_F32 | WFM_C128               */
+  int32_t accumulate;  /* 0: out = value; 1: out += value            */
+  void*   out;         /* DEVICE pointer (wfm_sample) / HOST pointer (wfm_sample_host) */
+  int64_t out_elems;   /* capacity of out, in elements of dtype      */
+} WfmLaunch;
+
+int  wfm_abi_version(void);
+const char* wfm_last_error(void);
+int  wfm_device_count(void);
+
+int  wfm_program_create(const WfmProgramDesc* host_ir, int device, wfm_program_t* out);
+int  wfm_program_destroy(wfm_program_t prog);
+int64_t wfm_program_total_samples(wfm_program_t prog);
+/* number of kernel launches issued through this program so far */
+int64_t wfm_program_launch_count(wfm_program_t prog);
+
+int  wfm_sample(wfm_program_t prog, const WfmLaunch* launch, void* stream);
+int  wfm_sample_host(wfm_program_t prog, const WfmLaunch* launch);
+
+/* Cascaded biquads, direct form II transposed, exactly scipy.signal.sosfilt:
+ *   y = b0*x + z0;  z0 = b1*x - a1*y + z1;  z1 = b2*x - a2*y
+ * on `n_sig` independent signals of `n` samples each, signal s starting at
+ * x + s*stride (DEVICE pointers, f64; y may alias x).  `sos` is HOST
+ * [n_sections][6] (b0 b1 b2 a0 a1 a2, a0 == 1).  `initial` is subtracted
+ * before and added after filtering (waveform.py:199-203).  `zi` / `zf` are HOST
+ * [n_sig][n_sections][2] initial / final states (either may be NULL: zero
+ * initial state / final state not returned). */
+int  wfm_sosfilt(const double* sos, int32_t n_sections, double initial,
+                 const double* x, double* y, int64_t n_sig, int64_t n,
+                 int64_t stride, const double* zi, double* zf, void* stream);
+
+/* y = real(ifft(fft(x) * H)) per signal, H given on the np.fft.fftfreq grid as
+ * HOST interleaved complex [n]; arbitrary n.  x, y DEVICE f64 (may alias). */
+int  wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n,
+                    int64_t stride, const double* H, void* stream);
+
+/* plain complex DFT of n_sig signals (DEVICE interleaved complex128, in
+ * place), forward (sign = -1) or inverse with 1/n scaling (sign = +1) —
+ * np.fft.fft / np.fft.ifft. */
+int  wfm_fft_c2c(double* data, int64_t n_sig, int64_t n, int64_t stride,
+                 int32_t sign, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFM_B200_H */

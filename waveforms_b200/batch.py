@@ -1,0 +1,95 @@
+"""Batched sampling: many channels, one kernel launch per GPU.
+
+``sample_batch`` is what an upstream scheduler calls instead of looping
+``Waveform.sample()`` over channels (the reference has no batched entry point;
+its closest container is ``WaveVStack``, waveform.py:638).  Channels are
+independent, so multi-GPU execution is a partition of the channel list — one
+program and one output buffer per device, no collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+from .lowering import lower
+
+
+def channel_grid(w, sample_rate=None):
+    """(Channel, Grid) of a Waveform/WaveVStack exactly as ``sample()`` would
+    evaluate it (waveform.py:173-190)."""
+    rate = w.sample_rate if sample_rate is None else sample_rate
+    if w.start is None or w.stop is None or rate is None:
+        raise ValueError(
+            f'Waveform is not initialized. {w.start=}, {w.stop=}, sample_rate={rate}'
+        )
+    return w._channel(), engine.arange_grid(w.start, w.stop, 1 / rate)
+
+
+def shard_ranges(weights, n_shards):
+    """Contiguous ranges of channels with balanced total weight (samples)."""
+    weights = np.asarray(weights, dtype=np.float64)
+    csum = np.concatenate([[0.0], np.cumsum(weights)])
+    total = csum[-1]
+    cuts = [0]
+    for s in range(1, n_shards):
+        cuts.append(int(np.searchsorted(csum, total * s / n_shards)))
+    cuts.append(len(weights))
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, len(weights)))
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(n_shards)]
+
+
+class BatchResult:
+    """Device-resident result of ``sample_batch``: one flat tensor per device
+    plus the per-channel (device, offset, length) table."""
+
+    def __init__(self, tensors, table, dtype):
+        self.tensors = tensors
+        self.table = table
+        self.dtype = dtype
+
+    def __len__(self):
+        return len(self.table)
+
+    def channel(self, i):
+        dev, off, n = self.table[i]
+        return self.tensors[dev][off:off + n]
+
+    def numpy(self):
+        host = [t.cpu().numpy() for t in self.tensors]
+        return [host[dev][off:off + n] for dev, off, n in self.table]
+
+
+def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
+                 filters='own'):
+    """Sample every waveform in ``waveforms`` on its own start/stop/sample_rate
+    grid.  ``dtype``: np.float64 (reference parity, 1e-12) or np.float32
+    (fp32 output, 1e-6).  ``devices``: list of CUDA device indices to shard the
+    channels over (default: the current device).  Returns a ``BatchResult``
+    whose tensors stay on the GPUs.
+
+    ``filters='own'`` applies each waveform's ``.filters`` (sample-time IIR,
+    waveform.py:193-203) on the device; ``None`` skips them."""
+    import torch
+    engine.require_gpu()
+    items = [channel_grid(w, sample_rate) for w in waveforms]
+    if devices is None:
+        devices = [torch.cuda.current_device()]
+    code = {np.dtype(np.float64): engine.WFM_F64,
+            np.dtype(np.float32): engine.WFM_F32,
+            np.dtype(np.complex128): engine.WFM_C128}[np.dtype(dtype)]
+    ranges = shard_ranges([g.n for _, g in items], len(devices))
+    tensors, table = [], []
+    for slot, (dev, (lo, hi)) in enumerate(zip(devices, ranges)):
+        batch = lower(items[lo:hi])
+        with torch.cuda.device(dev):
+            prog = engine.Program(batch, dev)
+            out = prog.sample_device(dtype=code)
+            if filters == 'own':
+                from .dsp import apply_channel_filters
+                apply_channel_filters(out, batch, waveforms[lo:hi])
+            prog.close()
+        tensors.append(out)
+        for k in range(hi - lo):
+            table.append((slot, int(batch.waves['out_off'][k]),
+                          int(batch.waves['n'][k])))
+    return BatchResult(tensors, table, dtype)

@@ -1,0 +1,61 @@
+"""Build libwfmb200.so in-tree with nvcc for sm_100a (no torch, no JIT cache).
+
+    python -m waveforms_b200.csrc.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / 'libwfmb200.so'
+SOURCES = ['wfm_api.cu', 'wfm_sample.cu', 'wfm_iir.cu', 'wfm_fft.cu']
+HEADERS = ['wfm_internal.h', 'wfm_basis.cuh', 'wfm_multidrag.cuh',
+           '../../include/wfm_b200.h']
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
+    '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',
+    # parity: never contract a*b+c behind our back (explicit fma() only)
+    '-fmad=false',
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    return 'nvcc'
+
+
+def stale():
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [HERE / s for s in SOURCES] + [HERE / h for h in HEADERS]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    objs = []
+    for src in SOURCES:
+        obj = HERE / (Path(src).stem + '.o')
+        cmd = [nvcc_path(), *NVCC_FLAGS, '-c', str(HERE / src), '-o', str(obj)]
+        if verbose:
+            cmd.insert(1, '-Xptxas')
+            cmd.insert(2, '-v')
+            print(' '.join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        objs.append(str(obj))
+    cmd = [nvcc_path(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
+           '-o', str(LIB), *objs]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == '__main__':
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    print(path)

@@ -1,0 +1,295 @@
+// wfm_api.cu — extern "C" boundary of libwfmb200.so (see include/wfm_b200.h).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "wfm_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define WFM_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(WFM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+cudaError_t upload(const T* host, int64_t n, const T** dev) {
+  *dev = nullptr;
+  // always allocate at least one element so kernels never see a null table
+  size_t bytes = sizeof(T) * (size_t)std::max<int64_t>(n, 1);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    e = cudaMemcpy(p, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p); return e; }
+  } else {
+    cudaMemset(p, 0, bytes);
+  }
+  *dev = static_cast<const T*>(p);
+  return cudaSuccess;
+}
+
+bool known_func(int f) { return (f >= WFM_LINEAR && f <= WFM_DRAG_SINX) || f == WFM_COS_ROT; }
+
+}  // namespace
+
+struct WfmProgram {
+  int device = 0;
+  wfm::DevProgram dev{};
+  std::vector<WfmWave> waves;  // host copy (tile lists, output sizing)
+  wfm::TileDesc* d_tiles = nullptr;
+  std::vector<int64_t> tile_prefix;  // tiles before channel w
+  int64_t n_tiles = 0;
+  int64_t total_samples = 0;  // extent of the output buffer in samples
+  int64_t launches = 0;
+  void* d_stage = nullptr;  // device staging buffer for wfm_sample_host
+  size_t stage_bytes = 0;
+  bool any_complex = false;
+
+  ~WfmProgram() {
+    DeviceGuard g(device);
+    cudaFree((void*)dev.waves);
+    cudaFree((void*)dev.seg_bound);
+    cudaFree((void*)dev.seg_ptr);
+    cudaFree((void*)dev.facs);
+    cudaFree((void*)dev.terms);
+    cudaFree((void*)dev.refs);
+    cudaFree((void*)dev.args);
+    cudaFree((void*)dev.x);
+    cudaFree(d_tiles);
+    cudaFree(d_stage);
+  }
+};
+
+static int validate(const WfmProgramDesc* d) {
+  if (!d) return fail(WFM_EINVAL, "null program descriptor");
+  if (d->n_waves < 0 || d->n_segs < 0 || d->n_facs < 0 || d->n_terms < 0 || d->n_refs < 0 || d->n_args < 0 || d->n_x < 0)
+    return fail(WFM_EINVAL, "negative table size");
+  if (d->n_segs > INT32_MAX - 1 || d->n_facs > INT32_MAX || d->n_terms > INT32_MAX || d->n_refs > INT32_MAX ||
+      d->n_args > INT32_MAX)
+    return fail(WFM_EINVAL, "table too large for 32-bit indices");
+  if ((d->n_waves && !d->waves) || (d->n_segs && (!d->seg_bound || !d->seg_ptr)) || (d->n_facs && !d->facs) ||
+      (d->n_terms && !d->terms) || (d->n_refs && !d->refs) || (d->n_args && !d->args) || (d->n_x && !d->x))
+    return fail(WFM_EINVAL, "null table pointer with non-zero size");
+  // segment table
+  for (int64_t s = 0; s < d->n_segs; ++s) {
+    const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
+    if (a.fac < 0 || a.term < 0 || b.fac < a.fac || b.term < a.term)
+      return fail(WFM_EINVAL, "segment %lld: pointer table not monotone", (long long)s);
+  }
+  if (d->n_segs) {
+    const WfmSegPtr e = d->seg_ptr[d->n_segs];
+    if (e.fac != d->n_facs || e.term != d->n_terms)
+      return fail(WFM_EINVAL, "segment pointer table does not close (%d/%lld factors, %d/%lld terms)", e.fac,
+                  (long long)d->n_facs, e.term, (long long)d->n_terms);
+  }
+  for (int64_t k = 0; k < d->n_facs; ++k) {
+    const WfmFactor& f = d->facs[k];
+    if (!known_func(f.func)) return fail(WFM_EUNSUPPORTED, "factor %lld: unknown basis id %d", (long long)k, f.func);
+    if (f.arg_off < 0 || f.arg_off > d->n_args)
+      return fail(WFM_EINVAL, "factor %lld: argument offset out of range", (long long)k);
+    if (f.func == WFM_INTERP) {
+      if (f.arg_off + 2 > d->n_args) return fail(WFM_EINVAL, "factor %lld: INTERP header out of range", (long long)k);
+      double n = d->args[f.arg_off];
+      if (!(n >= 1) || f.arg_off + 2 + (int64_t)n > d->n_args)
+        return fail(WFM_EINVAL, "factor %lld: INTERP table out of range", (long long)k);
+    }
+  }
+  // terms and refs, segment by segment (slot indices are segment-relative)
+  for (int64_t s = 0; s < d->n_segs; ++s) {
+    const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
+    const int nf = b.fac - a.fac;
+    for (int t = a.term; t < b.term; ++t) {
+      const WfmTerm& tm = d->terms[t];
+      if (tm.n_ref < 0 || tm.ref_begin < 0 || (int64_t)tm.ref_begin + tm.n_ref > d->n_refs)
+        return fail(WFM_EINVAL, "term %d: reference range out of bounds", t);
+      for (int r = tm.ref_begin; r < tm.ref_begin + tm.n_ref; ++r) {
+        const WfmRef& rf = d->refs[r];
+        if (rf.slot < 0 || rf.slot >= nf) return fail(WFM_EINVAL, "ref %d: slot %d outside segment (%d factors)", r, rf.slot, nf);
+        if (rf.kind < WFM_POW_ONE || rf.kind > WFM_POW_GEN) return fail(WFM_EINVAL, "ref %d: bad exponent kind", r);
+      }
+    }
+    if (b.term > a.term && !(d->terms[b.term - 1].flags & WFM_TERM_GROUP_END))
+      return fail(WFM_EINVAL, "segment %lld: last term does not close its group", (long long)s);
+  }
+  for (int64_t w = 0; w < d->n_waves; ++w) {
+    const WfmWave& wv = d->waves[w];
+    if (wv.n < 0 || wv.out_off < 0) return fail(WFM_EINVAL, "channel %lld: negative extent", (long long)w);
+    if (wv.n_seg < 1 || wv.seg_begin < 0 || (int64_t)wv.seg_begin + wv.n_seg > d->n_segs)
+      return fail(WFM_EINVAL, "channel %lld: segment range out of bounds", (long long)w);
+    if (!(d->seg_bound[wv.seg_begin + wv.n_seg - 1] == INFINITY))
+      return fail(WFM_EINVAL, "channel %lld: last bound must be +inf", (long long)w);
+    if ((wv.flags & WFM_WAVE_EXPLICIT_X) && (wv.x_off < 0 || wv.x_off + wv.n > d->n_x))
+      return fail(WFM_EINVAL, "channel %lld: explicit abscissae out of range", (long long)w);
+    if (wv.out_off % 4) return fail(WFM_EINVAL, "channel %lld: out_off must be a multiple of 4 (16-byte stores)", (long long)w);
+  }
+  return WFM_OK;
+}
+
+extern "C" {
+
+int wfm_abi_version(void) { return WFM_ABI_VERSION; }
+
+const char* wfm_last_error(void) { return g_err; }
+
+int wfm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) {
+  if (!out) return fail(WFM_EINVAL, "null output handle");
+  *out = nullptr;
+  int rc = validate(d);
+  if (rc != WFM_OK) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(WFM_ECUDA, "cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+  WfmProgram* p = new (std::nothrow) WfmProgram();
+  if (!p) return fail(WFM_ENOMEM, "out of host memory");
+  p->device = device;
+  p->waves.assign(d->waves, d->waves + d->n_waves);
+
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto host, int64_t n, auto dev) {
+    if (e == cudaSuccess) e = upload(host, n, dev);
+  };
+  up(d->waves, d->n_waves, &p->dev.waves);
+  up(d->seg_bound, d->n_segs, &p->dev.seg_bound);
+  up(d->seg_ptr, d->n_segs ? d->n_segs + 1 : 0, &p->dev.seg_ptr);
+  up(d->facs, d->n_facs, &p->dev.facs);
+  up(d->terms, d->n_terms, &p->dev.terms);
+  up(d->refs, d->n_refs, &p->dev.refs);
+  up(d->args, d->n_args, &p->dev.args);
+  up(d->x, d->n_x, &p->dev.x);
+
+  // tile list: kTileSamples consecutive samples of one channel per CTA
+  std::vector<wfm::TileDesc> tiles;
+  p->tile_prefix.resize(d->n_waves + 1);
+  int64_t total = 0;
+  for (int64_t w = 0; w < d->n_waves; ++w) {
+    p->tile_prefix[w] = (int64_t)tiles.size();
+    const WfmWave& wv = d->waves[w];
+    for (int64_t j = 0; j < wv.n; j += wfm::kTileSamples) tiles.push_back({j, (int32_t)w, 0});
+    total = std::max(total, wv.out_off + wv.n);
+    if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
+  }
+  p->tile_prefix[d->n_waves] = (int64_t)tiles.size();
+  p->n_tiles = (int64_t)tiles.size();
+  p->total_samples = total;
+  if (e == cudaSuccess) {
+    const wfm::TileDesc* dt = nullptr;
+    e = upload(tiles.data(), (int64_t)tiles.size(), &dt);
+    p->d_tiles = const_cast<wfm::TileDesc*>(dt);
+  }
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return WFM_OK;
+}
+
+int wfm_program_destroy(wfm_program_t prog) {
+  delete prog;
+  return WFM_OK;
+}
+
+int64_t wfm_program_total_samples(wfm_program_t prog) { return prog ? prog->total_samples : -1; }
+
+int64_t wfm_program_launch_count(wfm_program_t prog) { return prog ? prog->launches : -1; }
+
+static int check_launch(wfm_program_t prog, const WfmLaunch* l, int64_t* first, int64_t* count, int64_t* need) {
+  if (!prog || !l) return fail(WFM_EINVAL, "null program or launch");
+  const int64_t nw = (int64_t)prog->waves.size();
+  *first = l->first_wave;
+  *count = l->n_wave == 0 ? nw - l->first_wave : l->n_wave;
+  if (*first < 0 || *count < 0 || *first + *count > nw) return fail(WFM_EINVAL, "channel range out of bounds");
+  if (l->dtype != WFM_F64 && l->dtype != WFM_F32 && l->dtype != WFM_C128) return fail(WFM_EINVAL, "bad dtype");
+  if (prog->any_complex && l->dtype != WFM_C128)
+    for (int64_t w = *first; w < *first + *count; ++w)
+      if (prog->waves[w].flags & WFM_WAVE_COMPLEX)
+        return fail(WFM_EINVAL, "channel %lld has complex amplitudes: request WFM_C128 output", (long long)w);
+  int64_t ext = 0;
+  for (int64_t w = *first; w < *first + *count; ++w) ext = std::max(ext, prog->waves[w].out_off + prog->waves[w].n);
+  *need = ext;
+  if (!l->out && ext > 0) return fail(WFM_EINVAL, "null output buffer");
+  if (l->out_elems < ext) return fail(WFM_EINVAL, "output buffer too small: %lld < %lld", (long long)l->out_elems, (long long)ext);
+  return WFM_OK;
+}
+
+int wfm_sample(wfm_program_t prog, const WfmLaunch* l, void* stream) {
+  int64_t first, count, need;
+  int rc = check_launch(prog, l, &first, &count, &need);
+  if (rc != WFM_OK) return rc;
+  if ((uintptr_t)l->out % 16) return fail(WFM_EINVAL, "output buffer must be 16-byte aligned");
+  DeviceGuard g(prog->device);
+  const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles + t0, t1 - t0, l->dtype, l->accumulate, l->out,
+                              (cudaStream_t)stream));
+  if (t1 > t0) prog->launches += 1;
+  return WFM_OK;
+}
+
+int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
+  int64_t first, count, need;
+  int rc = check_launch(prog, l, &first, &count, &need);
+  if (rc != WFM_OK) return rc;
+  if (l->accumulate) return fail(WFM_EUNSUPPORTED, "accumulate is not available with host buffers");
+  DeviceGuard g(prog->device);
+  const size_t esz = l->dtype == WFM_F64 ? 8 : (l->dtype == WFM_F32 ? 4 : 16);
+  // only the extent actually covered by the requested channels is staged/copied
+  int64_t lo = INT64_MAX;
+  for (int64_t w = first; w < first + count; ++w) lo = std::min(lo, prog->waves[w].out_off);
+  if (count == 0 || need == 0) return WFM_OK;
+  const size_t bytes = (size_t)need * esz;
+  if (prog->stage_bytes < bytes) {
+    cudaFree(prog->d_stage);
+    prog->d_stage = nullptr;
+    prog->stage_bytes = 0;
+    WFM_CUDA(cudaMalloc(&prog->d_stage, bytes));
+    prog->stage_bytes = bytes;
+  }
+  // padding between channels is never written by the kernel: keep it defined
+  WFM_CUDA(cudaMemsetAsync((char*)prog->d_stage + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, 0));
+  const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles + t0, t1 - t0, l->dtype, 0, prog->d_stage, 0));
+  if (t1 > t0) prog->launches += 1;
+  WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->d_stage + (size_t)lo * esz,
+                           (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, 0));
+  WFM_CUDA(cudaStreamSynchronize(0));
+  return WFM_OK;
+}
+
+}  // extern "C"

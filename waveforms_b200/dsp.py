@@ -1,0 +1,69 @@
+"""Device DSP helpers behind the sample-time IIR hook and ``distortion``:
+thin Python over ``wfm_sosfilt`` / ``wfm_fft_filter`` (csrc/wfm_iir.cu,
+csrc/wfm_fft.cu).  No SciPy filtering happens here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import engine
+from .lowering import lower
+
+
+def _stream(torch, device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None):
+    """In-place-capable cascaded biquad filter on a CUDA f64 tensor ``x`` of
+    shape (n,) or (n_sig, n) (row stride = x.stride(0)).  Returns (y, zf)."""
+    import torch
+    lib = engine.require_gpu()
+    sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64)).reshape(-1, 6)
+    x2 = x if x.dim() == 2 else x.unsqueeze(0)
+    assert x2.dtype == torch.float64 and x2.stride(1) == 1
+    n_sig, n = x2.shape
+    y = x2 if out is None else (out if out.dim() == 2 else out.unsqueeze(0))
+    nsec = sos.shape[0]
+    zi_arr = None
+    if zi is not None:
+        zi_arr = np.ascontiguousarray(
+            np.broadcast_to(np.asarray(zi, dtype=np.float64),
+                            (n_sig, nsec, 2)))
+    zf = np.zeros((n_sig, nsec, 2)) if want_zf else None
+    rc = lib.wfm_sosfilt(sos.ctypes.data, nsec, float(initial or 0.0),
+                         x2.data_ptr(), y.data_ptr(), n_sig, n, x2.stride(0),
+                         zi_arr.ctypes.data if zi_arr is not None else None,
+                         zf.ctypes.data if zf is not None else None,
+                         _stream(torch, x.device))
+    engine._check(rc)
+    if zf is not None:
+        torch.cuda.current_stream(x.device).synchronize()
+    return (y if x.dim() == 2 else y[0]), zf
+
+
+def sample_and_filter(chan, grid, sos, initial, zi):
+    """Waveform.sample with ``filters=(sos, initial)``: K1 then K2 on the
+    device, one device->host copy of the filtered result."""
+    batch = lower([(chan, grid)])
+    prog = engine.Program(batch)
+    try:
+        dev = prog.sample_device(dtype=engine.WFM_F64)
+        sig = dev[:grid.n]
+        _, zf = sosfilt_device(sos, sig, initial=initial or 0.0, zi=zi,
+                               want_zf=zi is not None)
+        host = sig.cpu().numpy()
+    finally:
+        prog.close()
+    return host, (zf[0] if zf is not None else None)
+
+
+def apply_channel_filters(out, batch, waveforms):
+    """Apply each waveform's own ``.filters`` to its slice of ``out``."""
+    for k, w in enumerate(waveforms):
+        if w.filters is None:
+            continue
+        sos, initial = w.filters
+        off, n = int(batch.waves['out_off'][k]), int(batch.waves['n'][k])
+        sosfilt_device(sos, out[off:off + n], initial=initial or 0.0)

@@ -1,0 +1,294 @@
+"""ctypes binding of libwfmb200.so and the host-side sampling entry points.
+
+PyTorch is used for device-buffer ownership and streams only; every sample is
+computed by the hand-written CUDA kernels behind the C-ABI
+(include/wfm_b200.h).  There is no CPU path: if the library or a GPU is missing
+these functions raise ``EngineUnavailable``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from pathlib import Path
+
+import numpy as np
+
+from . import _algebra as A
+from .lowering import (FACTOR_DT, REF_DT, SEGPTR_DT, TERM_DT, WAVE_DT, Channel,
+                       Grid, LoweredBatch, lower)
+
+_LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libwfmb200.so'
+
+WFM_F64, WFM_F32, WFM_C128 = 0, 1, 2
+_NP_DTYPE = {WFM_F64: np.float64, WFM_F32: np.float32, WFM_C128: np.complex128}
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _ProgramDesc(C.Structure):
+    _fields_ = [('n_waves', C.c_int64), ('waves', C.c_void_p),
+                ('n_segs', C.c_int64), ('seg_bound', C.c_void_p),
+                ('seg_ptr', C.c_void_p), ('n_facs', C.c_int64),
+                ('facs', C.c_void_p), ('n_terms', C.c_int64),
+                ('terms', C.c_void_p), ('n_refs', C.c_int64),
+                ('refs', C.c_void_p), ('n_args', C.c_int64),
+                ('args', C.c_void_p), ('n_x', C.c_int64), ('x', C.c_void_p)]
+
+
+class _Launch(C.Structure):
+    _fields_ = [('first_wave', C.c_int64), ('n_wave', C.c_int64),
+                ('dtype', C.c_int32), ('accumulate', C.c_int32),
+                ('out', C.c_void_p), ('out_elems', C.c_int64)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+EXPORTS = [
+    'wfm_abi_version', 'wfm_last_error', 'wfm_device_count',
+    'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
+    'wfm_program_launch_count', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
+    'wfm_fft_filter', 'wfm_fft_c2c'
+]
+
+
+def load_library():
+    """dlopen libwfmb200.so (built in-tree by ``csrc/build.py``).  Loading does
+    not need a GPU; computing does."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not _LIB_PATH.exists():
+            raise EngineUnavailable(
+                f'{_LIB_PATH} is missing: build it with '
+                '`python -m waveforms_b200.csrc.build` (nvcc, sm_100a). '
+                'waveforms_b200 has no CPU fallback.')
+        lib = C.CDLL(str(_LIB_PATH))
+        lib.wfm_last_error.restype = C.c_char_p
+        lib.wfm_program_create.argtypes = [
+            C.POINTER(_ProgramDesc), C.c_int,
+            C.POINTER(C.c_void_p)
+        ]
+        lib.wfm_program_destroy.argtypes = [C.c_void_p]
+        lib.wfm_program_total_samples.argtypes = [C.c_void_p]
+        lib.wfm_program_total_samples.restype = C.c_int64
+        lib.wfm_program_launch_count.argtypes = [C.c_void_p]
+        lib.wfm_program_launch_count.restype = C.c_int64
+        lib.wfm_sample.argtypes = [C.c_void_p, C.POINTER(_Launch), C.c_void_p]
+        lib.wfm_sample_host.argtypes = [C.c_void_p, C.POINTER(_Launch)]
+        lib.wfm_sosfilt.argtypes = [
+            C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+            C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+            C.c_void_p
+        ]
+        lib.wfm_fft_filter.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p
+        ]
+        lib.wfm_fft_c2c.argtypes = [
+            C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p
+        ]
+        if lib.wfm_abi_version() != 1:
+            raise EngineUnavailable('libwfmb200.so ABI version mismatch')
+        _lib = lib
+        return lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load_library().wfm_last_error().decode(errors='replace')
+        raise EngineError(f'libwfmb200 error {rc}: {msg}')
+
+
+def require_gpu():
+    lib = load_library()
+    if lib.wfm_device_count() < 1:
+        raise EngineUnavailable(
+            'no CUDA device visible: waveforms_b200 samples on the GPU only '
+            '(no CPU fallback)')
+    return lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def check_function_lib(function_lib):
+    """The reference lets callers swap the basis-function table per call
+    (waveform.py:539-540).  The device implements ids 1..17 natively; any other
+    table cannot be honoured."""
+    if function_lib is None or function_lib is A._baseFunc:
+        return
+    from .lowering import UnsupportedBasis
+    raise UnsupportedBasis(
+        'function_lib= with user callables is not supported: basis functions '
+        'are evaluated by the CUDA kernel (ids 1..17)')
+
+
+# -- grids -------------------------------------------------------------------
+def arange_grid(start, stop, step) -> Grid:
+    """np.arange(start, stop, step) for floats: length ceil((stop-start)/step),
+    x[j] = start + j*((start+step)-start)  (NumPy's fill loop)."""
+    start, stop, step = float(start), float(stop), float(step)
+    n = max(int(math.ceil((stop - start) / step)), 0)
+    return Grid(n=n, t0=start, delta=(start + step) - start)
+
+
+def linspace_grid(start, stop, num, endpoint=True) -> Grid:
+    """np.linspace: x[j] = j*step + start, last sample forced to ``stop`` when
+    endpoint=True."""
+    start, stop, num = float(start), float(stop), int(num)
+    div = (num - 1) if endpoint else num
+    step = (stop - start) / div if div > 0 else 0.0
+    return Grid(n=num, t0=start, delta=step,
+                x_last=stop if (endpoint and num > 1) else None)
+
+
+def explicit_grid(x) -> Grid:
+    arr = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).reshape(-1)
+    return Grid(n=arr.size, x=arr)
+
+
+# -- program -----------------------------------------------------------------
+class Program:
+    """A lowered batch resident on one GPU."""
+
+    def __init__(self, batch: LoweredBatch, device: int | None = None):
+        lib = require_gpu()
+        torch = _torch()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self.batch = batch
+        self._lib = lib
+        d = _ProgramDesc()
+        keep = []
+
+        def ptr(a):
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            return a.ctypes.data if a.size else None
+
+        d.n_waves, d.waves = len(batch.waves), ptr(batch.waves)
+        d.n_segs, d.seg_bound = len(batch.seg_bound), ptr(batch.seg_bound)
+        d.seg_ptr = ptr(batch.seg_ptr)
+        d.n_facs, d.facs = len(batch.facs), ptr(batch.facs)
+        d.n_terms, d.terms = len(batch.terms), ptr(batch.terms)
+        d.n_refs, d.refs = len(batch.refs), ptr(batch.refs)
+        d.n_args, d.args = len(batch.args), ptr(batch.args)
+        d.n_x, d.x = len(batch.x), ptr(batch.x)
+        h = C.c_void_p()
+        _check(lib.wfm_program_create(C.byref(d), self.device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.wfm_program_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def total_samples(self):
+        return self.batch.total_samples
+
+    @property
+    def launch_count(self):
+        return int(self._lib.wfm_program_launch_count(self._h))
+
+    def default_dtype(self):
+        return WFM_C128 if self.batch.any_complex else WFM_F64
+
+    def sample_device(self, dtype=None, out=None, accumulate=False,
+                      first_wave=0, n_wave=0, stream=None):
+        """Launch K1; returns a torch tensor on ``self.device`` holding the
+        whole batch back to back (channel w at ``waves['out_off'][w]``)."""
+        torch = _torch()
+        if dtype is None:
+            dtype = self.default_dtype()
+        tdt = {WFM_F64: torch.float64, WFM_F32: torch.float32,
+               WFM_C128: torch.complex128}[dtype]
+        if out is None:
+            alloc = torch.zeros if accumulate else torch.empty
+            out = alloc(self.total_samples, dtype=tdt,
+                        device=f'cuda:{self.device}')
+        assert out.dtype == tdt and out.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        l = _Launch(first_wave, n_wave, dtype, int(bool(accumulate)),
+                    out.data_ptr(), out.numel())
+        _check(self._lib.wfm_sample(self._h, C.byref(l), C.c_void_p(stream)))
+        return out
+
+    def sample_host(self, dtype=None, out=None, first_wave=0, n_wave=0):
+        """End-to-end: kernel + device->host copy into a NumPy buffer through
+        ``wfm_sample_host``."""
+        if dtype is None:
+            dtype = self.default_dtype()
+        if out is None:
+            out = np.empty(self.total_samples, dtype=_NP_DTYPE[dtype])
+        assert out.dtype == _NP_DTYPE[dtype] and out.flags.c_contiguous
+        l = _Launch(first_wave, n_wave, dtype, 0, out.ctypes.data, out.size)
+        _check(self._lib.wfm_sample_host(self._h, C.byref(l)))
+        return out
+
+
+# -- single-channel helpers used by Waveform.__call__/sample -------------------
+def _run_one(chan: Channel, grid: Grid, want_complex=None):
+    batch = lower([(chan, grid)])
+    prog = Program(batch)
+    try:
+        dtype = prog.default_dtype()
+        res = prog.sample_host(dtype=dtype)
+    finally:
+        prog.close()
+    return res[:grid.n]
+
+
+def sample_one(chan: Channel, grid: Grid, out=None, accumulate=False,
+               zero_out=False, sos=None, initial=None, zi=None,
+               return_zf=False):
+    """One channel, NumPy in / NumPy out (the drop-in ``Waveform.sample`` /
+    ``__call__`` path).  ``sos`` applies the sample-time IIR
+    (waveform.py:193-203) on the device."""
+    if sos is None:
+        sig = _run_one(chan, grid)
+        zf = None
+    else:
+        from .dsp import sample_and_filter
+        sig, zf = sample_and_filter(chan, grid, sos, initial, zi)
+    if out is not None:
+        if not accumulate:
+            out *= 0
+        out[:grid.n] += sig
+        sig = out
+    if return_zf:
+        return sig, zf
+    return sig
+
+
+def sample_parts(chan: Channel, grid: Grid):
+    """``frag=True``: list of (start, stop, values) for the non-zero segments
+    (calc_parts' return value, _waveform.pyx:155-169).  Values come from the
+    device; the index ranges are host bookkeeping on the abscissae."""
+    (bounds, seq), = chan.members
+    xs = grid.materialize()
+    sig = _run_one(chan, grid)
+    edges = np.searchsorted(xs, bounds)
+    parts = []
+    start = 0
+    for k, stop in enumerate(edges):
+        stop = int(stop)
+        if start < stop and seq[k] != A.ZERO:
+            parts.append((start, stop, sig[start:stop]))
+        start = stop
+    return parts

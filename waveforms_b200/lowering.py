@@ -1,0 +1,390 @@
+"""Lower symbolic piecewise waveforms to the flat batched device IR.
+
+Input: a list of (Channel, Grid).  A Channel is one output array: a plain
+``Waveform`` (one member, optional clip) or a ``WaveVStack`` (many members,
+offset, pre-shift).  Output: ``LoweredBatch`` — NumPy structured arrays laid out
+exactly as the C structs in include/wfm_b200.h, ready to hand to
+``wfm_program_create``.
+
+What the lowering fixes (all of it is host work the reference redoes on every
+call inside calc_parts/_calc, /root/reference/waveforms/_waveform.pyx:130-169):
+
+* per segment, the list of DISTINCT factors (the reference memoises factor
+  values per segment by the factor tuple, :135-147) and per term the
+  (slot, exponent) references into that list;
+* for a stack, the union of the members' bounds, so one binary search per
+  sample replaces one np.searchsorted per member (waveform.py:690-692); terms
+  keep member order and carry a group-end flag so the device accumulates
+  ``offset + sum_members(sum_terms)`` in the reference's order;
+* every sample-independent scalar a basis function computes from its Python
+  arguments (e.g. ``2*pi*(freq+delta)`` in DRAG, hermite / mollifier
+  polynomial coefficients, the multi-DRAG matrices), evaluated here with the
+  same Python expression order as the reference so the rounded constants are
+  identical.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _algebra as A
+
+WAVE_DT = np.dtype([('t0', '<f8'), ('delta', '<f8'), ('x_last', '<f8'),
+                    ('clip_lo', '<f8'), ('clip_hi', '<f8'),
+                    ('pre_shift', '<f8'), ('offset', '<f8'), ('n', '<i8'),
+                    ('out_off', '<i8'), ('x_off', '<i8'), ('seg_begin', '<i4'),
+                    ('n_seg', '<i4'), ('flags', '<u4'), ('reserved', '<u4')])
+SEGPTR_DT = np.dtype([('fac', '<i4'), ('term', '<i4')])
+FACTOR_DT = np.dtype([('func', '<i4'), ('arg_off', '<i4'), ('shift', '<f8'),
+                      ('a0', '<f8'), ('a1', '<f8')])
+TERM_DT = np.dtype([('amp_re', '<f8'), ('amp_im', '<f8'), ('ref_begin', '<i4'),
+                    ('n_ref', '<i4'), ('flags', '<u4'), ('reserved', '<u4')])
+REF_DT = np.dtype([('expo', '<f8'), ('slot', '<i4'), ('kind', '<i4')])
+assert WAVE_DT.itemsize == 96 and FACTOR_DT.itemsize == 32
+assert TERM_DT.itemsize == 32 and REF_DT.itemsize == 16
+
+WAVE_EXPLICIT_X = 0x1
+WAVE_LAST_OVERRIDE = 0x2
+WAVE_CLIP = 0x4
+WAVE_PRESHIFT = 0x8
+WAVE_COMPLEX = 0x10
+TERM_GROUP_END = 0x1
+POW_ONE, POW_INT, POW_GEN = 0, 1, 2
+MAX_INT_POW = 64
+
+DRAG_SIN_ID = 16
+DRAG_SINX_ID = 17
+
+
+class UnsupportedBasis(NotImplementedError):
+    """Raised for basis functions the device cannot evaluate (user-registered
+    Python callables: ``function()``, ``registerBaseFunc``, ``function_lib=``).
+    There is deliberately no CPU fallback."""
+
+
+@dataclass
+class Grid:
+    """Sample abscissae.  affine: x[j] = t0 + j*delta (unfused), optionally with
+    the last sample forced to ``x_last`` (np.linspace endpoint=True); explicit:
+    user array."""
+    n: int
+    t0: float = 0.0
+    delta: float = 0.0
+    x_last: float | None = None
+    x: np.ndarray | None = None
+
+    def materialize(self) -> np.ndarray:
+        """Host copy of the abscissae (host bookkeeping such as ``frag=True``
+        index ranges; never used to compute sample values)."""
+        if self.x is not None:
+            return self.x
+        xs = self.t0 + np.arange(self.n, dtype=np.float64) * self.delta
+        if self.x_last is not None and self.n > 0:
+            xs[-1] = self.x_last
+        return xs
+
+
+@dataclass
+class Channel:
+    members: list
+    clip: tuple | None = None
+    offset: float = 0
+    pre_shift: float = 0
+    _lowered: object = field(default=None, repr=False, compare=False)
+
+
+@dataclass
+class LoweredBatch:
+    waves: np.ndarray
+    seg_bound: np.ndarray
+    seg_ptr: np.ndarray
+    facs: np.ndarray
+    terms: np.ndarray
+    refs: np.ndarray
+    args: np.ndarray
+    x: np.ndarray
+    total_samples: int
+    any_complex: bool
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.waves, self.seg_bound, self.seg_ptr,
+                                      self.facs, self.terms, self.refs,
+                                      self.args, self.x))
+
+
+# ---------------------------------------------------------------------------
+# per-function argument packing.  Each packer returns (a0, a1, pool_list);
+# the device readers are in csrc/wfm_basis.cuh (same order).
+# ---------------------------------------------------------------------------
+def _pack_none(args):
+    return 0.0, 0.0, ()
+
+
+def _pack_one(args):
+    v, = args
+    return float(v), 0.0, ()
+
+
+def _pack_interp(args):
+    start, stop, points = args
+    pts = np.asarray(points, dtype=np.float64).reshape(-1)
+    n = len(pts)
+    if n == 0:
+        raise ValueError('INTERP needs at least one point')
+    # np.linspace(start, stop, n): step = (stop-start)/(n-1); xp[j]=j*step+start
+    step = (stop - start) / (n - 1) if n > 1 else 0.0
+    return float(start), float(stop), (float(n), float(step), *pts.tolist())
+
+
+def _pack_linearchirp(args):
+    f0, f1, T, phi0 = args
+    return float(f0), float(phi0), (float((f1 - f0) / (2 * T)), float(2 * np.pi))
+
+
+def _pack_expchirp(args):
+    f0, alpha, phi0 = args
+    return float(alpha), float(phi0), (float(2 * math.pi * f0), )
+
+
+def _pack_hypchirp(args):
+    f0, k, phi0 = args
+    return float(k), float(phi0), (float(2 * np.pi * f0 / k), )
+
+
+def _pack_drag(args):
+    t0, freq, width, delta, block_freq, phase = args
+    o = np.pi / width
+    k1 = 2 * np.pi * (freq + delta)
+    k2 = 2 * np.pi * delta * t0 + phase
+    if block_freq is None or block_freq - delta == 0:
+        return float(t0), float(o), (float(k1), float(k2), 0.0, 0.0, 0.0)
+    b = 1 / np.pi / 2 / (block_freq - delta)
+    return float(t0), float(o), (float(k1), float(k2), 1.0, float(-b * o),
+                                 float(2 * o))
+
+
+def _mollifier_poly(d):
+    p = np.poly1d([-2, 0])
+    for n in range(1, d):
+        p = np.poly1d([1, 0, -2, 0, 1]) * p.deriv() + np.poly1d(
+            [-4 * n, 0, 4 * n - 2, 0]) * p
+    return p
+
+
+def _pack_mollifier(args):
+    r, d = args
+    d = int(d)
+    if d == 0:
+        return float(r), 0.0, ()
+    coeffs = [float(c) for c in _mollifier_poly(d).coeffs]
+    return float(r), float(d), (float(r**d), float(len(coeffs)), *coeffs)
+
+
+def _pack_dgaussian(args):
+    s, n = args
+    n = int(n)
+    return float(s), float(n), (float((-1)**n / s**n), )
+
+
+PACKERS = {
+    A.LINEAR: _pack_none,
+    A.GAUSSIAN: _pack_one,
+    A.ERF: _pack_one,
+    A.COS: _pack_one,
+    A.SINC: _pack_one,
+    A.EXP: _pack_one,
+    A.INTERP: _pack_interp,
+    A.LINEARCHIRP: _pack_linearchirp,
+    A.EXPONENTIALCHIRP: _pack_expchirp,
+    A.HYPERBOLICCHIRP: _pack_hypchirp,
+    A.COSH: _pack_one,
+    A.SINH: _pack_one,
+    A.DRAG: _pack_drag,
+    A.MOLLIFIER: _pack_mollifier,
+    A.D_GAUSSIAN: _pack_dgaussian,
+}
+
+
+def register_packer(type_id, packer):
+    """Used by multy_drag.py for ids 16/17."""
+    PACKERS[type_id] = packer
+
+
+class _Pools:
+    """Growing flat arrays shared by all channels of a batch."""
+
+    def __init__(self):
+        self.bound, self.segfac, self.segterm = [], [], []
+        self.fac, self.term, self.ref = [], [], []
+        self.args = []
+        self._arg_cache = {}
+        self.n_fac = self.n_term = self.n_ref = 0
+
+    def arg_block(self, key, values):
+        off = self._arg_cache.get(key)
+        if off is None:
+            off = len(self.args)
+            self.args.extend(values)
+            self._arg_cache[key] = off
+        return off
+
+
+def _pack_factor(pools, factor):
+    type_id = factor[0]
+    packer = PACKERS.get(type_id)
+    if packer is None:
+        raise UnsupportedBasis(
+            f'basis function id {type_id} ({A._baseFunc.get(type_id)!r}) has no '
+            'device implementation; user-registered Python callables cannot '
+            'be sampled by waveforms_b200')
+    a0, a1, pool = packer(factor[1:-1])
+    arg_off = pools.arg_block((type_id, factor[1:-1]), pool) if pool else 0
+    return (type_id, arg_off, float(factor[-1]), a0, a1)
+
+
+def _ref_kind(n):
+    if n == 1:
+        return POW_ONE
+    if isinstance(n, (int, np.integer)) or (isinstance(n, float)
+                                             and n == int(n)):
+        if 0 < abs(int(n)) <= MAX_INT_POW:
+            return POW_INT
+    return POW_GEN
+
+
+def _lower_segment(pools, groups):
+    """groups: list of expressions (one per stack member active here, in member
+    order).  Appends the segment's factors / terms / refs to the pools.
+    Returns True if any amplitude is complex."""
+    slots = {}
+    cplx = False
+    for expr in groups:
+        terms, amps = expr
+        last = len(amps) - 1
+        for k, ((factors, exponents), amp) in enumerate(zip(terms, amps)):
+            ref_begin = pools.n_ref
+            for f, n in zip(factors, exponents):
+                slot = slots.get(f)
+                if slot is None:
+                    slot = len(slots)
+                    slots[f] = slot
+                    pools.fac.append(_pack_factor(pools, f))
+                    pools.n_fac += 1
+                pools.ref.append((float(n), slot, _ref_kind(n)))
+                pools.n_ref += 1
+            if isinstance(amp, complex) or isinstance(amp, np.complexfloating):
+                re, im = float(amp.real), float(amp.imag)
+                cplx = cplx or im != 0.0
+            else:
+                re, im = float(amp), 0.0
+            pools.term.append((re, im, ref_begin, pools.n_ref - ref_begin,
+                               TERM_GROUP_END if k == last else 0, 0))
+            pools.n_term += 1
+    return cplx
+
+
+def _merge_members(members):
+    """Union the members' bounds.  Returns (bounds, per-segment list of member
+    expressions that are non-zero there, in member order)."""
+    if len(members) == 1:
+        bounds, seq = members[0]
+        return list(bounds), [[] if s == A.ZERO else [s] for s in seq]
+    edges = set()
+    for bounds, _ in members:
+        edges.update(bounds)
+    edges.discard(math.inf)
+    merged = sorted(edges)
+    merged.append(math.inf)
+    marr = np.asarray(merged, dtype=np.float64)
+    active = [[] for _ in merged]
+    for bounds, seq in members:
+        lo = 0  # merged index where the member's current segment starts
+        for b, s in zip(bounds, seq):
+            hi = int(np.searchsorted(marr, b, side='left')) + 1 if b != math.inf \
+                else len(merged)
+            if s != A.ZERO:
+                for k in range(lo, hi):
+                    active[k].append(s)
+            lo = hi
+    return merged, active
+
+
+def _lower_channel(pools, chan):
+    bounds, active = _merge_members(chan.members)
+    seg_begin = len(pools.bound)
+    cplx = False
+    for b, groups in zip(bounds, active):
+        pools.bound.append(float(b))
+        pools.segfac.append(pools.n_fac)
+        pools.segterm.append(pools.n_term)
+        if groups:
+            cplx = _lower_segment(pools, groups) or cplx
+    return seg_begin, len(bounds), cplx
+
+
+def lower(items) -> LoweredBatch:
+    """items: iterable of (Channel, Grid).  Output offsets are assigned
+    back-to-back, each channel's start padded to a multiple of 2 samples so
+    16-byte vector stores stay aligned."""
+    pools = _Pools()
+    items = list(items)
+    waves = np.zeros(len(items), dtype=WAVE_DT)
+    xs = []
+    x_off = 0
+    out_off = 0
+    any_complex = False
+    for i, (chan, grid) in enumerate(items):
+        seg_begin, n_seg, cplx = _lower_channel(pools, chan)
+        any_complex = any_complex or cplx
+        w = waves[i]
+        flags = 0
+        if grid.x is not None:
+            flags |= WAVE_EXPLICIT_X
+            w['x_off'] = x_off
+            arr = np.ascontiguousarray(grid.x, dtype=np.float64).reshape(-1)
+            xs.append(arr)
+            x_off += len(arr)
+        else:
+            w['t0'], w['delta'] = grid.t0, grid.delta
+            if grid.x_last is not None:
+                flags |= WAVE_LAST_OVERRIDE
+                w['x_last'] = grid.x_last
+        if chan.clip is not None and (chan.clip[0] != -math.inf
+                                      or chan.clip[1] != math.inf):
+            flags |= WAVE_CLIP
+            w['clip_lo'], w['clip_hi'] = chan.clip
+        if chan.pre_shift != 0:
+            flags |= WAVE_PRESHIFT
+            w['pre_shift'] = chan.pre_shift
+        if cplx:
+            flags |= WAVE_COMPLEX
+        off = chan.offset
+        w['offset'] = off.real if isinstance(off, complex) else off
+        w['n'] = grid.n
+        w['out_off'] = out_off
+        w['seg_begin'] = seg_begin
+        w['n_seg'] = n_seg
+        w['flags'] = flags
+        out_off += (grid.n + 3) & ~3
+    n_segs = len(pools.bound)
+    seg_ptr = np.zeros(n_segs + 1, dtype=SEGPTR_DT)
+    seg_ptr['fac'][:n_segs] = pools.segfac
+    seg_ptr['term'][:n_segs] = pools.segterm
+    seg_ptr['fac'][n_segs] = pools.n_fac
+    seg_ptr['term'][n_segs] = pools.n_term
+    return LoweredBatch(
+        waves=waves,
+        seg_bound=np.asarray(pools.bound, dtype=np.float64),
+        seg_ptr=seg_ptr,
+        facs=np.array(pools.fac, dtype=FACTOR_DT) if pools.fac else np.zeros(
+            0, FACTOR_DT),
+        terms=np.array(pools.term, dtype=TERM_DT) if pools.term else np.zeros(
+            0, TERM_DT),
+        refs=np.array(pools.ref, dtype=REF_DT) if pools.ref else np.zeros(
+            0, REF_DT),
+        args=np.asarray(pools.args, dtype=np.float64),
+        x=np.concatenate(xs) if xs else np.zeros(0, np.float64),
+        total_samples=out_off,
+        any_complex=any_complex)
