@@ -63,10 +63,10 @@ def _tokenize(text):
                 f"Syntax error at line 1, column {pos}: token recognition "
                 f"error at: '{text[pos:pos + 1]}'")
         kind = m.lastgroup
-        value = m.group(kind)
+        value, col = m.group(kind), m.start(kind)
         if kind == 'ID' and value in _CONSTANTS:
             kind = 'CONSTANT'
-        tokens.append((kind, value, m.start(kind)))
+        tokens.append((kind, value, col))
         pos = m.end()
     tokens.append(('EOF', '<EOF>', end))
     return tokens
