@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — batched Waveform.sample throughput (GSa/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the 20-qubit XY+Z control
+frame — 40 channels x 100 us at 2 GSa/s (200 000 samples each), XY = 250
+DRAG-mixed cosPulse/gaussian pulses per channel, Z = 100 erf-edged squares — as a
+batch of FRAMES frames per GPU (one frame is 64 MB of output, far below L2 and
+launch latency; a scheduler submits many).  One step = one pass of the sampling
+hot path over that batch: FRAMES x 40 x 200 000 fp64 samples per GPU per step.
+The step's output (FRAMES x 64 MB) is larger than L2, so no L2 flush is needed
+between iterations.
+
+One JSON line on stdout (rank 0):
+  value    whole-job GSa/s, IR resident in HBM, CUDA events, max over ranks
+  e2e      the same through the C-ABI with HOST buffers: wfm_program_create
+           (IR host->device) + wfm_sample_host (kernel + device->host copy of
+           every sample into pinned memory) + destroy, per step
+  roofline algorithmic bytes (8 B/sample, write-only) / K1 time vs
+           the measured HBM bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's compiled evaluator (oracle/_ref) or the oracle
+           port timed on this host on a bounded sample (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests' / 'golden'))
+
+CHANNELS = 40
+T_END = 100e-6
+RATE = 2e9
+N_SAMP = 200000
+XY_PULSES = 250
+Z_PULSES = 100
+WORKLOAD = ('cfg2: 20-qubit XY+Z control frame, 40 ch x 100 us @ 2 GSa/s, '
+            'cosPulse/gaussian DRAG + erf-edged Z, fp64')
+
+
+def b200_namespace():
+    import types
+    import waveforms_b200 as wf
+    from waveforms_b200.waveform import WaveVStack
+    ns = types.SimpleNamespace(**{k: getattr(wf, k) for k in dir(wf) if not k.startswith('_')})
+    ns.WaveVStack = WaveVStack
+    return ns
+
+
+def build_frame(ns, seed=20260002):
+    """One frame = 20 XY + 20 Z channels as Waveform/WaveVStack objects built
+    through the drop-in API."""
+    import cases
+    rng = np.random.default_rng(seed)
+    chans = []
+    for q in range(CHANNELS // 2):
+        w, _ = cases.xy_channel(ns, rng, XY_PULSES, 400e-9, T_END, RATE)
+        chans.append(w)
+    for q in range(CHANNELS // 2):
+        w, _ = cases.z_channel(ns, rng, Z_PULSES, T_END, RATE)
+        chans.append(w)
+    return chans
+
+
+def clock_sampler(stop_evt, out, device_index):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    try:
+        p = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                              '-i', str(device_index), '-lms', '100'],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop_evt.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarize_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in lines:
+        f = [x.strip() for x in ln.split(',')]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(names, f[3:7]):
+            if v.lower().startswith('active'):
+                reasons.add(name)
+    if not sm:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+    return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+            'samples': len(sm)}
+
+
+def measured_peak():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def recorded_traffic():
+    p = ROOT / 'profiles' / 'k1_traffic.json'
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return None
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's evaluator (oracle/_ref) or the oracle port
+# ---------------------------------------------------------------------------
+_CPU_CHANS = None
+_CPU_CALC = None
+
+
+def _cpu_init(use_ref):
+    global _CPU_CALC
+    import warnings
+    warnings.simplefilter('ignore')
+    _CPU_CALC = None
+    if use_ref:
+        from oracle.build_ref import load
+        ref = load()
+        if ref is not None:
+            def calc(bounds, seq, x, lo=-np.inf, hi=np.inf, _r=ref):
+                return _r.calc_parts(bounds, seq, x, _r._baseFunc, lo, hi)
+            _CPU_CALC = calc
+
+
+def _cpu_sample(idx):
+    from oracle import wfm_oracle as O
+    kind, payload = _CPU_CHANS[idx]
+    x = O.sample_grid(0, T_END, RATE)
+    kw = {} if _CPU_CALC is None else {'calc': _CPU_CALC}
+    if kind == 'stack':
+        y = O.stack_call(payload, x, 0, 0, **kw)
+    else:
+        y = O.waveform_call(payload[0], payload[1], x, **kw)
+    return len(y)
+
+
+def cpu_payload(chans):
+    out = []
+    for w in chans:
+        if hasattr(w, 'wlist'):
+            out.append(('stack', list(w.wlist)))
+        else:
+            out.append(('waveform', (w.bounds, w.seq)))
+    return out
+
+
+def run_cpu(chans, steps, warmup, procs):
+    """Times `steps` passes over the given channels with `procs` worker
+    processes (fork; objects inherited, not pickled)."""
+    global _CPU_CHANS
+    import multiprocessing as mp
+    from oracle.build_ref import load
+    kind = 'reference' if load() is not None else 'port'
+    _CPU_CHANS = cpu_payload(chans)
+    idx = list(range(len(_CPU_CHANS)))
+    if procs <= 1:
+        _cpu_init(kind == 'reference')
+        for _ in range(warmup):
+            [_cpu_sample(i) for i in idx]
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(steps):
+            n += sum(_cpu_sample(i) for i in idx)
+        dt = time.perf_counter() - t0
+    else:
+        ctx = mp.get_context('fork')
+        with ctx.Pool(procs, initializer=_cpu_init, initargs=(kind == 'reference', )) as pool:
+            for _ in range(warmup):
+                pool.map(_cpu_sample, idx, chunksize=1)
+            t0 = time.perf_counter()
+            n = 0
+            for _ in range(steps):
+                n += sum(pool.map(_cpu_sample, idx, chunksize=1))
+            dt = time.perf_counter() - t0
+    return n, dt, kind
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--frames', type=int, default=64, help='frames per GPU per step')
+    ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    ns = b200_namespace()
+
+    config = {'workload': WORKLOAD, 'channels_per_frame': CHANNELS, 'samples_per_channel': N_SAMP,
+              'frames_per_gpu': args.frames, 'xy_pulses_per_channel': XY_PULSES, 'z_pulses_per_channel': Z_PULSES,
+              'l2': 'step output (frames x 64 MB) exceeds L2; no flush needed', 'sharding': f'dp{world} by frame'}
+
+    # ------------------------------------------------------------------ CPU arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        chans = build_frame(ns)
+        procs = os.cpu_count() or 1
+        n, dt, kind = run_cpu(chans, args.steps, args.warmup, procs)
+        gsa = n / dt / 1e9
+        line = {'impl': 'reference', 'metric': 'Waveform.sample GSa/s (batched)', 'value': gsa, 'unit': 'GSa/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': dict(config, frames_per_gpu=1, note='one step = ONE frame (40 channels) on the host cores'),
+                'cpu_baseline': {'value': gsa, 'unit': 'GSa/s', 'cores': procs, 'kind': kind,
+                                 'sample': 'one full frame (40 ch x 200k samples) per step, process pool over channels'},
+                'e2e': {'value': gsa, 'unit': 'GSa/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    from waveforms_b200 import engine
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower, replicate
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    t_b0 = time.perf_counter()
+    chans = build_frame(ns, seed=20260002)
+    t_build = time.perf_counter() - t_b0
+    t_l0 = time.perf_counter()
+    frame = lower([channel_grid(w) for w in chans])
+    t_lower = time.perf_counter() - t_l0
+    rng = np.random.default_rng(1000 + rank)
+    batch = replicate(frame, args.frames, amp_scale=rng.uniform(0.5, 1.0, args.frames))
+    samples_per_step = int(batch.waves['n'].sum())
+    code = engine.WFM_F64 if args.dtype == 'f64' else engine.WFM_F32
+    esz = 8 if args.dtype == 'f64' else 4
+    tdt = torch.float64 if args.dtype == 'f64' else torch.float32
+
+    prog = engine.Program(batch, local_rank)
+    out = torch.empty(batch.total_samples, dtype=tdt, device=f'cuda:{local_rank}')
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        prog.sample_device(dtype=code, out=out)
+    barrier()
+    clock_lines, stop_evt = [], threading.Event()
+    sampler = threading.Thread(target=clock_sampler, args=(stop_evt, clock_lines, local_rank), daemon=True)
+    sampler.start()
+    time.sleep(0.35)
+    launches0 = prog.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        prog.sample_device(dtype=code, out=out)
+        ev[k + 1].record(stream)
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    launches = prog.launch_count - launches0
+    # keep the sampler alive through the e2e leg as well, then summarise the timed region only
+    n_kernel_clock = len(clock_lines)
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=f'cuda:{local_rank}')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = samples_per_step * world * args.steps / (total_ms_max * 1e-3) / 1e9
+
+    # ---- e2e: C-ABI with host buffers (IR upload + kernel + D2H every step)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(batch.total_samples, dtype=tdt, pin_memory=True)
+        host_np = host.numpy()
+        prog.close()
+        del out
+        torch.cuda.empty_cache()
+        e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            p2 = engine.Program(batch, local_rank)
+            p2.sample_host(dtype=code, out=host_np)
+            p2.close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            p2 = engine.Program(batch, local_rank)
+            p2.sample_host(dtype=code, out=host_np)
+            p2.close()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=f'cuda:{local_rank}')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {'value': samples_per_step * world * e_steps / dt / 1e9, 'unit': 'GSa/s',
+               'h2d_bytes_per_step': int(batch.nbytes()), 'd2h_bytes_per_step': int(batch.total_samples * esz),
+               'steps': e_steps, 'ms_per_step': dt / e_steps * 1e3,
+               'path': 'wfm_program_create(host IR) + wfm_sample_host(pinned host out) + wfm_program_destroy'}
+        checksum = float(host_np[:N_SAMP].sum())
+    else:
+        prog.close()
+        checksum = None
+    stop_evt.set()
+    sampler.join(timeout=3)
+    clocks = summarize_clocks(clock_lines[:max(n_kernel_clock, 1)] if n_kernel_clock else clock_lines)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    k1_ms = float(np.mean(per_launch_ms))
+    achieved = samples_per_step * esz / (k1_ms * 1e-3) / 1e9
+    traffic = recorded_traffic()
+    roofline = {'bound': 'hbm', 'kernel': 'wfm::sample_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': samples_per_step * esz, 'launch_ms': k1_ms,
+                'traffic': traffic['dram_bytes_per_launch'] if traffic else None,
+                'traffic_source': traffic.get('source') if traffic else None}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        # bounded sample: 2 XY + 2 Z channels, single core
+        sub = [chans[0], chans[1], chans[CHANNELS // 2], chans[CHANNELS // 2 + 1]]
+        n, dt, kind = run_cpu(sub, steps=2, warmup=1, procs=1)
+        cpu = {'value': n / dt / 1e9, 'unit': 'GSa/s', 'cores': 1, 'kind': kind,
+               'sample': '2 XY + 2 Z channels of the frame (4 x 200k samples), 2 passes, 1 process'}
+
+    line = {'metric': 'Waveform.sample GSa/s (batched)', 'value': value, 'unit': 'GSa/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+            'data': 'synthetic', 'config': config, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': roofline, 'cpu_baseline': cpu,
+            'host': {'frame_build_s': t_build, 'frame_lower_s': t_lower, 'ir_bytes': int(batch.nbytes()),
+                     'checksum_ch0': checksum}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

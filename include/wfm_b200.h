@@ -173,13 +173,23 @@ int  wfm_sample_host(wfm_program_t prog, const WfmLaunch* launch);
  *   y = b0*x + z0;  z0 = b1*x - a1*y + z1;  z1 = b2*x - a2*y
  * on `n_sig` independent signals of `n` samples each, signal s starting at
  * x + s*stride (DEVICE pointers, f64; y may alias x).  `sos` is HOST
- * [n_sections][6] (b0 b1 b2 a0 a1 a2, a0 == 1).  `initial` is subtracted
+ * [n_sections][6] (b0 b1 b2 a0 a1 a2), n_sections <= 8.  `initial` is subtracted
  * before and added after filtering (waveform.py:199-203).  `zi` / `zf` are HOST
  * [n_sig][n_sections][2] initial / final states (either may be NULL: zero
- * initial state / final state not returned). */
+ * initial state / final state not returned; a non-NULL zf makes the call
+ * synchronous).
+ *   WFM_IIR_EXACT  one thread per signal, sequential in time: bit-identical to
+ *                  scipy (parallelism = n_sig).
+ *   WFM_IIR_SCAN   block-parallel associative scan over time (one CTA per
+ *                  signal, 4096-sample tiles): the throughput path; equals the
+ *                  sequential result up to the filter's own rounding-noise gain
+ *                  (see DESIGN.md, K2). */
+#define WFM_IIR_EXACT 0
+#define WFM_IIR_SCAN  1
 int  wfm_sosfilt(const double* sos, int32_t n_sections, double initial,
                  const double* x, double* y, int64_t n_sig, int64_t n,
-                 int64_t stride, const double* zi, double* zf, void* stream);
+                 int64_t stride, const double* zi, double* zf, int32_t mode,
+                 void* stream);
 
 /* y = real(ifft(fft(x) * H)) per signal, H given on the np.fft.fftfreq grid as
  * HOST interleaved complex [n]; arbitrary n.  x, y DEVICE f64 (may alias). */

@@ -1,0 +1,146 @@
+"""GPU parity of the DSP kernels (K2 IIR; K3 FFT lives in test_gpu_fft.py)
+against scipy — the third-party implementation the reference calls — and the
+golden vectors produced by the reference's distortion.py."""
+import numpy as np
+import pytest
+from scipy.signal import butter, lfilter, lfiltic, sosfilt, tf2sos
+
+from helpers import FP64_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+EXP_DECAY_SOS = np.array([[0.99015614, -1.97372497, 0.98357705, 1., -1.99346203, 0.99347026]])
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('n', [1, 7, 16, 4095, 4096, 4097, 20000])
+@pytest.mark.parametrize('nsec', [1, 2, 3])
+def test_sosfilt_exact_is_bit_identical(n, nsec):
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(n * 10 + nsec)
+    sos = tf2sos(*butter(2 * nsec, 0.05 + 0.1 * nsec))
+    x = rng.standard_normal((3, n))
+    y, _ = sosfilt_device(sos, _dev(x), mode='exact')
+    assert np.array_equal(y.cpu().numpy(), sosfilt(sos, x, axis=-1))
+
+
+def test_sosfilt_exact_exp_decay_golden(dsp_golden):
+    from waveforms_b200.dsp import sosfilt_device
+    g = dsp_golden
+    y, _ = sosfilt_device(g['exp_decay_sos'], _dev(g['sig']), mode='exact')
+    assert np.array_equal(y.cpu().numpy(), g['sosfilt'])
+
+
+def test_sosfilt_state_streaming():
+    """zi/zf round trip == one-shot (waveform.py:222-249 chunked mode)."""
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(3)
+    sos = tf2sos(*butter(3, 0.1))
+    x = rng.standard_normal(10000)
+    want = sosfilt(sos, x)
+    for mode in ('exact', 'scan'):
+        zi = np.zeros((sos.shape[0], 2))
+        got = []
+        for a in range(0, 10000, 3000):
+            y, zf = sosfilt_device(sos, _dev(x[a:a + 3000]), zi=zi, want_zf=True, mode=mode)
+            zi = zf[0]
+            got.append(y.cpu().numpy())
+        got = np.concatenate(got)
+        if mode == 'exact':
+            assert np.array_equal(got, want)
+        else:
+            assert rel_err(got, want) <= FP64_TOL
+
+
+@pytest.mark.parametrize('n', [5, 4096, 4097, 50000])
+def test_sosfilt_scan_well_conditioned(n):
+    """Butterworth sections (poles well inside the unit circle): the scan equals
+    the sequential result to 1e-12."""
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(n)
+    sos = tf2sos(*butter(4, 0.2))
+    x = rng.standard_normal((2, n))
+    y, _ = sosfilt_device(sos, _dev(x), mode='scan')
+    assert rel_err(y.cpu().numpy(), sosfilt(sos, x, axis=-1)) <= FP64_TOL
+
+
+def test_sosfilt_scan_exp_decay_is_as_accurate_as_scipy():
+    """Poles at 0.9952/0.9983: scipy's own sequential rounding noise is ~3e-12
+    (DESIGN.md K2).  The scan must (a) stay within 1e-11 of scipy and (b) be no
+    further from the extended-precision answer than scipy itself is."""
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(11)
+    n = 60000
+    x = np.zeros(n)
+    for _ in range(12):
+        a, b = sorted(rng.integers(0, n, 2))
+        x[a:b] += rng.uniform(-0.5, 0.5)
+    ref = sosfilt(EXP_DECAY_SOS, x)
+    y, _ = sosfilt_device(EXP_DECAY_SOS, _dev(x), mode='scan')
+    y = y.cpu().numpy()
+    assert rel_err(y, ref) <= 1e-11
+    b0, b1, b2, _, a1, a2 = (np.longdouble(v) for v in EXP_DECAY_SOS[0])
+    z0 = z1 = np.longdouble(0)
+    exact = np.empty(n, dtype=np.longdouble)
+    for i, xv in enumerate(x.astype(np.longdouble)):
+        yv = b0 * xv + z0
+        z0 = b1 * xv - a1 * yv + z1
+        z1 = b2 * xv - a2 * yv
+        exact[i] = yv
+    err_scan = float(np.max(np.abs(y - exact)))
+    err_scipy = float(np.max(np.abs(ref - exact)))
+    assert err_scan <= 2.0 * err_scipy + 1e-15
+
+
+def test_sosfilt_initial_offset():
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(5)
+    sos = tf2sos(*butter(2, 0.1))
+    x = rng.standard_normal(5000) + 0.3
+    y, _ = sosfilt_device(sos, _dev(x), initial=0.3, mode='exact')
+    assert np.array_equal(y.cpu().numpy(), sosfilt(sos, x - 0.3) + 0.3)
+
+
+def test_reference_filter_tests(ns):
+    """/root/reference/tests/test_waveform.py:169-194 and
+    tests/test_wavevstack.py:113-137, through the CUDA path."""
+    from waveforms_b200 import Waveform, WaveVStack
+    sample_rate = 1000
+    b, a = butter(3, 4.0, 'lowpass', fs=sample_rate)
+    zi = lfiltic(b, a, [0])
+    t = np.linspace(-1, 1, 2000, endpoint=False)
+
+    wav = ns.step(0)
+    wav.sample_rate, wav.start, wav.stop = sample_rate, -1, 1
+    wav.filters = (tf2sos(b, a), 0)
+    points = lfilter(b, a, np.heaviside(t, 1), zi=zi)[0]
+    assert np.allclose(wav.sample(), points)
+    assert np.allclose(Waveform.fromlist(wav.tolist()).sample(), points)
+    assert np.allclose(Waveform.fromtree(wav.totree()).sample(), points)
+
+    st = WaveVStack([ns.step(0) << 0.5, -ns.step(0)])
+    st.sample_rate, st.start, st.stop = sample_rate, -1, 1
+    st.filters = (tf2sos(b, a), 0)
+    points = lfilter(b, a, np.heaviside(t + 0.5, 1) - np.heaviside(t, 1), zi=zi)[0]
+    assert np.allclose(st.sample(), points, atol=1e-6)
+    assert np.allclose(WaveVStack.fromlist(st.tolist()).sample(), points, atol=1e-6)
+
+
+def test_chunked_sampling_matches_reference_semantics(ns):
+    """_sample_iter (waveform.py:209-257): per-chunk linspace grids, IIR state
+    carried across chunks."""
+    from oracle import wfm_oracle as O
+    sos = tf2sos(*butter(2, 0.05))
+    w = 0.7 * ns.gaussian(2e-6) >> 3e-6
+    w.start, w.stop, w.sample_rate = 0.0, 6e-6, 1e9
+    w.filters = (sos, 0)
+    chunks = list(w.sample(chunk_size=2500))
+    assert [len(c) for c in chunks] == [2500, 2500, 1000]
+    xs = np.concatenate([np.linspace(a, min(a + 2.5e-6, 6e-6), k, endpoint=False)
+                         for a, k in ((0.0, 2500), (2.5e-6, 2500), (5e-6, 1000))])
+    want = sosfilt(sos, O.waveform_call(w.bounds, w.seq, xs))
+    assert rel_err(np.concatenate(chunks), want) <= FP64_TOL

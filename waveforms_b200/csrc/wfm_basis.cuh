@@ -14,13 +14,9 @@
 #pragma once
 #include <math_constants.h>
 #include "../../include/wfm_b200.h"
+#include "wfm_math.cuh"
 
 namespace wfm {
-
-__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
 
 constexpr double kPi = 3.141592653589793;       // numpy.pi
 constexpr double kTwoPi = 6.283185307179586;    // 2 * numpy.pi
@@ -57,7 +53,7 @@ __device__ __forceinline__ double f_sinc(double t, double bw) {
 __device__ __forceinline__ double interp_xp(int j, int n, double step, double start, double stop) {
   return (j == n - 1 && n > 1) ? stop : add(mul((double)j, step), start);
 }
-__device__ double f_interp(double t, double start, double stop, const double* __restrict__ pool) {
+__device__ inline double f_interp(double t, double start, double stop, const double* __restrict__ pool) {
   const int n = (int)pool[0];
   const double step = pool[1];
   const double* fp = pool + 2;
@@ -97,7 +93,7 @@ __device__ __forceinline__ double f_drag(double t, double t0, double o, const do
 }
 
 // _waveform.pyx:359-371.  a0 = r, a1 = d; pool (d > 0): [r**d, ncoef, coefs...]
-__device__ double f_mollifier(double t, double r, double dd, const double* __restrict__ pool) {
+__device__ inline double f_mollifier(double t, double r, double dd, const double* __restrict__ pool) {
   double u = dvd(t, r);
   double au = fabs(u);
   double q = sub(mul(au, au), 1.0);
@@ -118,7 +114,7 @@ __device__ double f_mollifier(double t, double r, double dd, const double* __res
 // scipy.special.hermite(n)(x) dispatches to eval_hermite: the three-term
 // recurrence of He_n at sqrt(2)*x, scaled by 2**(n/2).  a0 = s, a1 = n,
 // pool: [c = (-1)**n / s**n]
-__device__ double f_dgaussian(double t, double s, double nn, const double* __restrict__ pool) {
+__device__ inline double f_dgaussian(double t, double s, double nn, const double* __restrict__ pool) {
   const int n = (int)nn;
   double u = dvd(t, s);
   double h;
@@ -144,7 +140,7 @@ __device__ double f_dgaussian(double t, double s, double nn, const double* __res
 
 // multi-notch DRAG envelopes, ids 16/17 (multy_drag.py:30-174); see
 // wfm_multidrag.cuh
-__device__ double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx);
+__device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx);
 
 __device__ __forceinline__ double eval_factor(const WfmFactor& f, double x, const double* __restrict__ args) {
   const double t = sub(x, f.shift);

@@ -27,7 +27,7 @@ __device__ __forceinline__ double polyval_rows(const double* __restrict__ c, int
   return y;
 }
 
-__device__ double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx) {
+__device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx) {
   const double t0 = f.a0, o = f.a1;
   const double tm1 = pool[2], tm2 = pool[3], plateau = pool[4];
   const int m = (int)pool[5];

@@ -15,9 +15,17 @@ def _stream(torch, device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None):
+IIR_EXACT, IIR_SCAN = 0, 1
+_IIR_MODES = {'exact': IIR_EXACT, 'scan': IIR_SCAN}
+
+
+def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None,
+                   mode='exact'):
     """In-place-capable cascaded biquad filter on a CUDA f64 tensor ``x`` of
-    shape (n,) or (n_sig, n) (row stride = x.stride(0)).  Returns (y, zf)."""
+    shape (n,) or (n_sig, n) (row stride = x.stride(0)).  Returns (y, zf).
+
+    mode='exact': sequential-in-time kernel, bit-identical to
+    scipy.signal.sosfilt; mode='scan': block-parallel associative scan."""
     import torch
     lib = engine.require_gpu()
     sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64)).reshape(-1, 6)
@@ -36,7 +44,7 @@ def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None):
                          x2.data_ptr(), y.data_ptr(), n_sig, n, x2.stride(0),
                          zi_arr.ctypes.data if zi_arr is not None else None,
                          zf.ctypes.data if zf is not None else None,
-                         _stream(torch, x.device))
+                         _IIR_MODES[mode], _stream(torch, x.device))
     engine._check(rc)
     if zf is not None:
         torch.cuda.current_stream(x.device).synchronize()

@@ -87,7 +87,7 @@ def load_library():
         lib.wfm_sosfilt.argtypes = [
             C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
             C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
-            C.c_void_p
+            C.c_int32, C.c_void_p
         ]
         lib.wfm_fft_filter.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,

@@ -388,3 +388,41 @@ def lower(items) -> LoweredBatch:
         x=np.concatenate(xs) if xs else np.zeros(0, np.float64),
         total_samples=out_off,
         any_complex=any_complex)
+
+
+def replicate(batch: LoweredBatch, copies: int, amp_scale=None) -> LoweredBatch:
+    """``copies`` independent copies of a lowered batch laid out back to back
+    (every table duplicated, indices rebased) — how a scheduler's batch of
+    identical-shape frames looks.  ``amp_scale[c]`` (optional) multiplies all
+    amplitudes of copy c so the copies produce distinct outputs."""
+    R = int(copies)
+    nw, ns = len(batch.waves), len(batch.seg_bound)
+    nf, nt, nr = len(batch.facs), len(batch.terms), len(batch.refs)
+    waves = np.tile(batch.waves, R)
+    rep = np.repeat(np.arange(R), nw)
+    waves['out_off'] += rep * batch.total_samples
+    waves['seg_begin'] += (rep * ns).astype(np.int32)
+    waves['x_off'] += rep * len(batch.x)
+    seg_ptr = np.zeros(R * ns + 1, dtype=SEGPTR_DT)
+    body = np.tile(batch.seg_ptr[:ns], R)
+    rs = np.repeat(np.arange(R), ns)
+    body['fac'] += (rs * nf).astype(np.int32)
+    body['term'] += (rs * nt).astype(np.int32)
+    seg_ptr[:R * ns] = body
+    seg_ptr['fac'][R * ns] = R * nf
+    seg_ptr['term'][R * ns] = R * nt
+    terms = np.tile(batch.terms, R)
+    rt = np.repeat(np.arange(R), nt)
+    terms['ref_begin'] += (rt * nr).astype(np.int32)
+    if amp_scale is not None:
+        sc = np.asarray(amp_scale, dtype=np.float64)[rt]
+        terms['amp_re'] *= sc
+        terms['amp_im'] *= sc
+    facs = np.tile(batch.facs, R)
+    facs['arg_off'] += (np.repeat(np.arange(R), nf) * len(batch.args)).astype(np.int32)
+    return LoweredBatch(waves=waves, seg_bound=np.tile(batch.seg_bound, R),
+                        seg_ptr=seg_ptr, facs=facs, terms=terms,
+                        refs=np.tile(batch.refs, R),
+                        args=np.tile(batch.args, R), x=np.tile(batch.x, R),
+                        total_samples=batch.total_samples * R,
+                        any_complex=batch.any_complex)
