@@ -191,6 +191,14 @@ int  wfm_sosfilt(const double* sos, int32_t n_sections, double initial,
                  int64_t stride, const double* zi, double* zf, int32_t mode,
                  void* stream);
 
+/* scipy.signal.lfilter(b, a, x, zi=zi) — one direct-form-II-transposed section of
+ * order max(nb, na) - 1 <= 16 (distortion.py:321, the polynomial products built by
+ * combine_filters).  One thread per signal, sequential in time, bit-identical to
+ * scipy.  b, a, zi, zf are HOST arrays (zi/zf: [n_sig][order], may be NULL). */
+int  wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na,
+                 const double* x, double* y, int64_t n_sig, int64_t n,
+                 int64_t stride, const double* zi, double* zf, void* stream);
+
 /* y = real(ifft(fft(x) * H)) per signal, H given on the np.fft.fftfreq grid as
  * HOST interleaved complex [n]; arbitrary n.  x, y DEVICE f64 (may alias). */
 int  wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n,

@@ -1,0 +1,104 @@
+"""GPU parity of K3 (shared-memory Stockham FFT, four-step, Bluestein) against
+numpy.fft — the third-party implementation the reference calls — and of the
+distortion apply functions against golden vectors from the reference's
+distortion.py (its parity is unpinned by the reference's own tests)."""
+import numpy as np
+import pytest
+
+from helpers import FP64_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# 7-smooth single-level, radix mixes, two-level (four-step), non-smooth (Bluestein)
+LENGTHS = [1, 2, 3, 4, 5, 7, 8, 12, 30, 64, 100, 243, 625, 640, 1000, 1024, 2401, 4096, 6000, 6144,
+           8192, 10000, 16384, 40000, 400000, 1 << 20,
+           11, 13, 97, 997, 1215 * 11, 6151, 20011]
+
+
+@pytest.mark.parametrize('n', LENGTHS)
+def test_c2c_matches_numpy(n):
+    import torch
+    from waveforms_b200.dsp import fft_c2c_device
+    rng = np.random.default_rng(n)
+    nsig = 3 if n <= 40000 else 1
+    z = rng.standard_normal((nsig, n)) + 1j * rng.standard_normal((nsig, n))
+    want_f, want_i = np.fft.fft(z, axis=-1), np.fft.ifft(z, axis=-1)
+    got_f = fft_c2c_device(torch.from_numpy(z.copy()).cuda()).cpu().numpy()
+    got_i = fft_c2c_device(torch.from_numpy(z.copy()).cuda(), inverse=True).cpu().numpy()
+    assert rel_err(got_f, want_f) <= FP64_TOL
+    assert rel_err(got_i, want_i) <= FP64_TOL
+
+
+@pytest.mark.parametrize('n', [1, 5, 64, 1000, 4000, 6144, 6145, 10000, 400000, 997, 12347])
+def test_fft_filter_matches_numpy(n):
+    import torch
+    from waveforms_b200.dsp import fft_filter_device
+    rng = np.random.default_rng(n + 1)
+    nsig = 4 if n <= 10000 else 2
+    x = rng.standard_normal((nsig, n))
+    H = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    want = np.fft.ifft(np.fft.fft(x, axis=-1) * H, axis=-1).real
+    got = fft_filter_device(torch.from_numpy(x).cuda(), H).cpu().numpy()
+    assert rel_err(got, want) <= FP64_TOL
+
+
+def test_reflection_golden(dsp_golden):
+    from waveforms_b200 import distortion as D
+    g = dsp_golden
+    sig, fs = g['sig'], g['fs']
+    assert rel_err(D.reflection(sig, 0.05, 13.3e-9, fs), g['reflection']) <= FP64_TOL
+    assert rel_err(D.correct_reflection(sig, 0.05, 13.3e-9, fs), g['correct_reflection']) <= FP64_TOL
+    for m in (997, 1000, 1215, 2048, 3125):
+        s, want = g[f'correct_reflection_{m}']
+        assert rel_err(D.correct_reflection(s, 0.07, 11.1e-9, fs), want) <= FP64_TOL
+
+
+def test_reflection_roundtrip_full_size():
+    """config-4 size (400 000 = 2^7 5^5): correct_reflection(reflection(x)) == x."""
+    import torch
+    from waveforms_b200 import distortion as D
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.standard_normal((2, 400000))).cuda()
+    y = D.correct_reflection(D.reflection(x, 0.05, 13.3e-9, 2e9), 0.05, 13.3e-9, 2e9)
+    assert float((y - x).abs().max()) <= 1e-12 * float(x.abs().max())
+
+
+def test_design_functions_golden(dsp_golden):
+    from waveforms_b200 import distortion as D
+    g = dsp_golden
+    fs = g['fs']
+    assert np.array_equal(D.exp_decay_filter([-0.03, 0.02], [0.1e-6, 0.3e-6], fs, inv=True, output='sos'),
+                          g['exp_decay_sos'])
+    b, a = D.exp_decay_filter([-0.03, 0.02], [0.1e-6, 0.3e-6], fs)
+    assert np.array_equal(b, g['exp_decay_ba'][0]) and np.array_equal(a, g['exp_decay_ba'][1])
+    z, p, k = D.exp_decay_filter(0.05, 0.2e-6, fs, output='zpk')
+    assert np.array_equal(z, g['exp_decay_zpk'][0]) and np.array_equal(p, g['exp_decay_zpk'][1]) and k == g['exp_decay_zpk'][2]
+    assert np.array_equal(D.zDistortKernel(1 / fs, [(0.1e-6, -0.03), (0.3e-6, 0.02)]), g['zDistortKernel'])
+    assert np.array_equal(D.shift(g['sig'], 3.3e-9, 1 / fs), g['shift'])
+    assert D.high_pass_filter(1e-6, fs) == g['high_pass']
+
+
+def test_distort_and_predistort_golden(dsp_golden):
+    from waveforms_b200 import distortion as D
+    g = dsp_golden
+    sig, fs = g['sig'], g['fs']
+    params = [(-0.03, 0.1e-6), (0.02, 0.3e-6)]
+    # lfilter path: the sequential kernel is bit-faithful to scipy
+    assert np.array_equal(D.distort(sig, params, fs), g['distort'])
+    assert np.array_equal(D.distort(sig + 0.2, params, fs, initial=0.2), g['distort_initial'])
+    filters = [D.exp_decay_filter(a, tau, fs) for a, tau in params]
+    y, zf = D.predistort(sig, filters=filters, return_zf=True)
+    assert np.array_equal(y, g['predistort_zf'][0]) and np.array_equal(zf, g['predistort_zf'][1])
+    # kernel convolution (FFT): 1e-12 relative
+    ker = g['zDistortKernel']
+    assert rel_err(D.predistort(sig, ker=ker), g['predistort_ker']) <= FP64_TOL
+    assert rel_err(D.predistort(sig, filters=filters, ker=ker), g['predistort_both']) <= FP64_TOL
+
+
+def test_correct_reflection_symbolic(ns):
+    """Waveform input stays symbolic (distortion.py:216-217)."""
+    from waveforms_b200 import distortion as D
+    w = ns.square(1e-6, edge=5e-9) >> 2e-6
+    c = D.correct_reflection(w, 0.05, 13.3e-9)
+    want = 1 / (1 - 0.05) * w - 0.05 / (1 - 0.05) * (w >> 13.3e-9)
+    assert c.bounds == want.bounds and c.seq == want.seq

@@ -17,9 +17,13 @@ HEADERS = ['wfm_internal.h', 'wfm_basis.cuh', 'wfm_math.cuh', 'wfm_multidrag.cuh
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
     '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2',
-    # parity: never contract a*b+c behind our back (explicit fma() only)
-    '-fmad=false',
 ]
+# parity-critical translation units never contract a*b+c behind our back
+# (explicit fma() only); the FFT is free to fuse
+PER_SOURCE_FLAGS = {
+    'wfm_sample.cu': ['-fmad=false'],
+    'wfm_iir.cu': ['-fmad=false'],
+}
 
 
 def nvcc_path():
@@ -43,7 +47,8 @@ def build(force=False, verbose=False):
     objs = []
     for src in SOURCES:
         obj = HERE / (Path(src).stem + '.o')
-        cmd = [nvcc_path(), *NVCC_FLAGS, '-c', str(HERE / src), '-o', str(obj)]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []), '-c',
+               str(HERE / src), '-o', str(obj)]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')

@@ -201,7 +201,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   for (int64_t w = 0; w < d->n_waves; ++w) {
     p->tile_prefix[w] = (int64_t)tiles.size();
     const WfmWave& wv = d->waves[w];
-    for (int64_t j = 0; j < wv.n; j += wfm::kTileSamples) tiles.push_back({j, (int32_t)w, 0});
+    for (int64_t j = 0; j < wv.n; j += wfm::kTileSamples) tiles.push_back({j, (int32_t)w, 0, 0, 0});
     total = std::max(total, wv.out_off + wv.n);
     if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
   }
@@ -213,6 +213,9 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     e = upload(tiles.data(), (int64_t)tiles.size(), &dt);
     p->d_tiles = const_cast<wfm::TileDesc*>(dt);
   }
+  // device pre-pass: every tile learns the segment range it spans
+  if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, p->d_tiles, p->n_tiles, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   if (e != cudaSuccess) {
     delete p;
     return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));

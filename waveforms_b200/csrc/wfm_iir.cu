@@ -264,6 +264,54 @@ __global__ void __launch_bounds__(kIirThreads) sosfilt_scan_kernel(IirParams P, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// lfilter: single high-order section, scipy.signal.lfilter's DF2T loop
+// (scipy/signal/_lfilter.c.src): y = z[0] + b[0]*x;
+// z[k] = (z[k+1] + x*b[k+1]) - y*a[k+1];  z[M-1] = x*b[M] - y*a[M].
+// One thread per signal, sequential in time, bit-faithful (note the different
+// association from sosfilt's (b1*x - a1*y) + z1).
+// ---------------------------------------------------------------------------
+constexpr int kMaxOrder = 16;
+struct LfilterParams {
+  int order;  // M = max(len(a), len(b)) - 1
+  double b[kMaxOrder + 1];
+  double a[kMaxOrder + 1];
+};
+
+__global__ void __launch_bounds__(128) lfilter_exact_kernel(LfilterParams P, const double* __restrict__ x, double* y,
+                                                             int64_t n_sig, int64_t n, int64_t stride,
+                                                             const double* __restrict__ zi, double* __restrict__ zf) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sig) return;
+  const int M = P.order;
+  double z[kMaxOrder];
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k) z[k] = (zi && k < M) ? zi[s * M + k] : 0.0;
+  const double* __restrict__ xs = x + s * stride;
+  double* ys = y + s * stride;
+  for (int64_t j = 0; j < n; ++j) {
+    const double xv = xs[j];
+    double yv;
+    if (M == 0) {
+      yv = mul(P.b[0], xv);
+    } else {
+      yv = add(z[0], mul(P.b[0], xv));
+#pragma unroll
+      for (int k = 0; k < kMaxOrder - 1; ++k)
+        if (k < M - 1) z[k] = sub(add(z[k + 1], mul(xv, P.b[k + 1])), mul(yv, P.a[k + 1]));
+#pragma unroll
+      for (int k = 0; k < kMaxOrder; ++k)
+        if (k == M - 1) z[k] = sub(mul(xv, P.b[M]), mul(yv, P.a[M]));
+    }
+    ys[j] = yv;
+  }
+  if (zf) {
+#pragma unroll
+    for (int k = 0; k < kMaxOrder; ++k)
+      if (k < M) zf[s * M + k] = z[k];
+  }
+}
+
 // host: 2x2 matrix powers in long double
 struct M2 {
   long double a, b, c, d;
@@ -353,5 +401,41 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
   if (e == cudaSuccess && zf) e = cudaMemcpyAsync(zf, d_zf, state_bytes, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && (d_zi || d_zf || d_tab)) e = cudaStreamSynchronize(st);  // before freeing scratch
   cleanup();
+  return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
+}
+
+extern "C" int wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na, const double* x, double* y,
+                           int64_t n_sig, int64_t n, int64_t stride, const double* zi, double* zf, void* stream) {
+  using namespace wfm;
+  if (!b || !a || nb < 1 || na < 1 || a[0] == 0.0 || n_sig < 0 || n < 0 || (n_sig > 1 && stride < n)) return WFM_EINVAL;
+  const int M = std::max(nb, na) - 1;
+  if (M > kMaxOrder) return WFM_EUNSUPPORTED;
+  if (n_sig == 0) return WFM_OK;
+  if (!x || !y) return WFM_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  LfilterParams P{};
+  P.order = M;
+  for (int k = 0; k <= M; ++k) {  // scipy normalises both polynomials by a[0]
+    P.b[k] = k < nb ? b[k] / a[0] : 0.0;
+    P.a[k] = k < na ? a[k] / a[0] : 0.0;
+  }
+  const size_t state_bytes = sizeof(double) * (size_t)std::max(M, 1) * (size_t)n_sig;
+  double *d_zi = nullptr, *d_zf = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (zi && M > 0) {
+    e = cudaMalloc(&d_zi, state_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, sizeof(double) * M * n_sig, cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess && zf && M > 0) e = cudaMalloc(&d_zf, state_bytes);
+  if (e == cudaSuccess) {
+    const int threads = 128;
+    lfilter_exact_kernel<<<(unsigned)((n_sig + threads - 1) / threads), threads, 0, st>>>(P, x, y, n_sig, n, stride,
+                                                                                        d_zi, d_zf);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && d_zf) e = cudaMemcpyAsync(zf, d_zf, sizeof(double) * M * n_sig, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && (d_zi || d_zf)) e = cudaStreamSynchronize(st);
+  cudaFree(d_zi);
+  cudaFree(d_zf);
   return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
 }

@@ -25,8 +25,12 @@ struct DevProgram {
 struct TileDesc {
   int64_t j0;
   int32_t wave;
+  int32_t seg_lo;  // channel-relative segment of the tile's first abscissa  } filled on the device by
+  int32_t seg_hi;  // ... and of its last one                                } prepare_tiles_kernel
   int32_t reserved;
 };
+
+cudaError_t launch_prepare_tiles(const DevProgram& P, TileDesc* tiles, int64_t n_tiles, cudaStream_t stream);
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t n_tiles, int dtype, int accumulate,
                           void* out, cudaStream_t stream);

@@ -6,21 +6,30 @@
 // (/root/reference/waveforms/waveform.py:173-207, :529-563, :679-693;
 //  /root/reference/waveforms/_waveform.pyx:130-169).
 //
-// Work decomposition: the output of the batch is cut into tiles of
-// kTileSamples consecutive samples of ONE channel; one CTA per tile.
-//   1. warps 0/1 locate the segments of the tile's first / last abscissa with
-//      a 32-ary ballot search over the channel's bounds (global, L2-resident);
-//   2. the CTA stages that slice of the segment table (bounds + factor/term
-//      pointers) in shared memory;
-//   3. every thread owns 16 bytes of output per row (2 fp64 / 4 fp32 samples),
-//      finds its segment by binary search in shared memory, interprets the
-//      segment's factor list / term list, and issues one 16-byte streaming
-//      store.  A warp-row therefore writes 512 contiguous bytes.
-// Tiles that lie inside a single segment skip the search; tiles inside a zero
-// segment degenerate to pure stores (the HBM-write-bound case).
+// Work decomposition: the output of the batch is cut into tiles of kTileSamples
+// consecutive samples of ONE channel; one CTA (256 threads) per tile.
 //
-// Bounds are HBM-resident f64, the output is write-once: stores use
-// st.global.cs (evict-first) so they do not displace the IR in L2.
+//  0. (once per program, prepare_tiles_kernel) every tile learns the segments of
+//     its first and last abscissa: one thread per tile, binary search over the
+//     channel's bounds.
+//  1. The CTA turns the tile's slice of the bound table into INTEGER sample
+//     positions: thread k finds the first sample of the tile whose abscissa is
+//     >= bound k — a division for the guess, then exact comparisons against the
+//     rounded grid value x[j] = t0 + j*delta, so ownership is bit-identical to
+//     np.searchsorted on the reference's grid.  Positions and the segments'
+//     factor/term pointers live in shared memory.
+//  2. A warp owns chunks of 32*V consecutive samples (V = 2 fp64 / 4 fp32 per
+//     thread = one 16-byte store per thread, 512 contiguous bytes per warp).
+//     The chunk's first segment comes from a per-chunk table (one LDS).  A chunk
+//     that lies inside one segment is warp-uniform: an empty (zero) segment
+//     costs a store and nothing else — no abscissa, no search; a non-empty one
+//     runs the segment program without divergence.  Mixed chunks let every lane
+//     advance from the chunk's first segment.
+//  3. The segment program (distinct factors, then terms referencing factor
+//     slots) is interpreted for the thread's V samples at once.
+//
+// Output is write-once: stores use st.global.cs (evict-first) so they do not
+// displace the IR in L2.  Algorithmic traffic: 8 B (4 B) per sample, write-only.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "wfm_basis.cuh"
@@ -30,8 +39,9 @@
 namespace wfm {
 
 constexpr int kThreads = 256;
-constexpr int kStageSegs = 1024;  // segment-table rows staged per tile (8 KB bounds + 8 KB ptrs)
+constexpr int kStageSegs = 1024;  // segment rows staged per tile
 constexpr int kMaxSlots = 12;     // distinct factor values cached per segment evaluation
+constexpr int kMaxChunks = kTileSamples / 64;
 
 template <typename T> struct OutVec;
 template <> struct OutVec<double> { static constexpr int N = 2; };
@@ -68,84 +78,164 @@ __device__ __forceinline__ double abscissa(const WfmWave& w, const double* __res
   return x;
 }
 
-// Number of bounds <= x among b[0..n) (b sorted, b[n-1] = +inf): the index of
-// the segment that owns x, i.e. np.searchsorted(bounds, x, side='right').
-// Executed by one full warp; 32 pivots per round.
-__device__ int warp_segment_search(const double* __restrict__ b, int n, double x, int lane) {
-  int lo = 0, hi = n - 1;  // answer in [lo, hi]
-  while (hi > lo) {
-    int width = hi - lo;
-    int stride = (width + 31) / 32;
-    int idx = min(lo + (lane + 1) * stride - 1, hi);
-    bool le = (idx < hi) ? (__ldg(b + idx) <= x) : false;  // b[hi] > x is known
-    unsigned m = __ballot_sync(0xffffffffu, le);
-    int c = __popc(m);  // bounds are sorted, so `le` is a prefix
-    int new_lo = (c == 0) ? lo : min(lo + c * stride - 1, hi) + 1;
-    int new_hi = (c == 32) ? hi : min(lo + (c + 1) * stride - 1, hi);
-    lo = min(new_lo, hi);
-    hi = max(new_hi, lo);
+// number of bounds <= x among b[0..n) (b sorted, b[n-1] = +inf): the segment that
+// owns x == np.searchsorted(bounds, x, side='right')
+__device__ __forceinline__ int owning_segment(const double* __restrict__ b, int n, double x) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(b + mid) <= x) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
+// ---- pre-pass: segment range of every tile (one thread per tile) --------------------
+__global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, int64_t n_tiles) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  TileDesc td = tiles[t];
+  const WfmWave w = P.waves[td.wave];
+  const int64_t last = min(td.j0 + (int64_t)kTileSamples, w.n) - 1;
+  const double* b = P.seg_bound + w.seg_begin;
+  td.seg_lo = owning_segment(b, w.n_seg, abscissa(w, P.x, td.j0));
+  td.seg_hi = max(td.seg_lo, owning_segment(b, w.n_seg, abscissa(w, P.x, last)));
+  tiles[t] = td;
+}
+
+// first sample jj in [0, cnt] of the tile with abscissa >= bound (cnt if none)
+__device__ int first_sample_at_or_after(const WfmWave& w, const double* __restrict__ xs, int64_t j0, int cnt,
+                                        double bound) {
+  if (!(w.flags & WFM_WAVE_EXPLICIT_X) && w.delta > 0.0) {
+    double b = bound;
+    if (w.flags & WFM_WAVE_PRESHIFT) b = b + w.pre_shift;
+    double g = ceil((b - w.t0) / w.delta) - (double)j0;
+    int jj = g <= 0.0 ? 0 : (g >= (double)cnt ? cnt : (int)g);
+    // exact fix-up against the rounded grid (monotone in j)
+    while (jj > 0 && abscissa(w, xs, j0 + jj - 1) >= bound) --jj;
+    while (jj < cnt && abscissa(w, xs, j0 + jj) < bound) ++jj;
+    return jj;
+  }
+  int lo = 0, hi = cnt;  // generic: binary search over the tile's abscissae
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (abscissa(w, xs, j0 + mid) < bound) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int V>
 struct Acc {
-  double re, im;
+  double re[V];
+  double im[V];
 };
 
-// Evaluate one segment's program at abscissa x.
-template <bool kComplex>
-__device__ __forceinline__ Acc eval_segment(const DevProgram& P, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1,
-                                            double x) {
-  Acc total{w.offset, 0.0};
+// basis function on V samples at once; the hot ids are unrolled over V so the
+// independent evaluations interleave, the rest fall back to the scalar code
+template <int V>
+__device__ __forceinline__ void eval_factor_v(const WfmFactor& f, const double (&x)[V], const double* __restrict__ args,
+                                              double (&out)[V]) {
+  switch (f.func) {
+    case WFM_COS:
+#pragma unroll
+      for (int e = 0; e < V; ++e) out[e] = cos(mul(f.a0, sub(x[e], f.shift)));
+      break;
+    case WFM_GAUSSIAN:
+#pragma unroll
+      for (int e = 0; e < V; ++e) out[e] = f_gaussian(sub(x[e], f.shift), f.a0);
+      break;
+    case WFM_ERF:
+#pragma unroll
+      for (int e = 0; e < V; ++e) out[e] = erf(dvd(sub(x[e], f.shift), f.a0));
+      break;
+    case WFM_LINEAR:
+#pragma unroll
+      for (int e = 0; e < V; ++e) out[e] = sub(x[e], f.shift);
+      break;
+    default:
+#pragma unroll 1
+      for (int e = 0; e < V; ++e) out[e] = eval_factor(f, x[e], args);
+      break;
+  }
+}
+
+// Evaluate one segment's program at V abscissae.
+template <int V, bool kComplex>
+__device__ __forceinline__ void eval_segment(const DevProgram& P, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1,
+                                             const double (&x)[V], Acc<V>& total) {
+#pragma unroll
+  for (int e = 0; e < V; ++e) { total.re[e] = w.offset; total.im[e] = 0.0; }
   const int nt = p1.term - p0.term;
-  if (nt == 0) return total;  // zero segment: untouched by clip (calc_parts skips it)
+  if (nt == 0) return;  // zero segment: untouched by clip (calc_parts skips it)
   const int nf = p1.fac - p0.fac;
-  double vals[kMaxSlots];
+  double vals[kMaxSlots][V];
   const WfmFactor* __restrict__ facs = P.facs + p0.fac;
 #pragma unroll 1
-  for (int k = 0; k < nf && k < kMaxSlots; ++k) vals[k] = eval_factor(facs[k], x, P.args);
+  for (int k = 0; k < nf && k < kMaxSlots; ++k) eval_factor_v<V>(facs[k], x, P.args, vals[k]);
 
-  double g_re = 0.0, g_im = 0.0;
+  double g_re[V], g_im[V];
   bool g_first = true;
 #pragma unroll 1
   for (int it = 0; it < nt; ++it) {
     const WfmTerm tm = P.terms[p0.term + it];
-    double prod = 1.0;
+    double prod[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) prod[e] = 1.0;
     bool p_first = true;
 #pragma unroll 1
     for (int r = 0; r < tm.n_ref; ++r) {
       const WfmRef ref = P.refs[tm.ref_begin + r];
-      double v = (ref.slot < kMaxSlots) ? vals[ref.slot] : eval_factor(facs[ref.slot], x, P.args);
-      if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
-      else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
-      prod = p_first ? v : mul(prod, v);  // 1 * v == v
+      double v[V];
+      if (ref.slot < kMaxSlots) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = vals[ref.slot][e];
+      } else {
+        eval_factor_v<V>(facs[ref.slot], x, P.args, v);
+      }
+      if (ref.kind == WFM_POW_INT) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = pow_small_int(v[e], (int)ref.expo);
+      } else if (ref.kind == WFM_POW_GEN) {
+#pragma unroll 1
+        for (int e = 0; e < V; ++e) v[e] = pow(v[e], ref.expo);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) prod[e] = p_first ? v[e] : mul(prod[e], v[e]);  // 1 * v == v
       p_first = false;
     }
-    const double t_re = mul(tm.amp_re, prod);
-    g_re = g_first ? t_re : add(g_re, t_re);  // 0 + a == a
-    if (kComplex) {
-      const double t_im = mul(tm.amp_im, prod);
-      g_im = g_first ? t_im : add(g_im, t_im);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const double t_re = mul(tm.amp_re, prod[e]);
+      g_re[e] = g_first ? t_re : add(g_re[e], t_re);  // 0 + a == a
+      if (kComplex) {
+        const double t_im = mul(tm.amp_im, prod[e]);
+        g_im[e] = g_first ? t_im : add(g_im[e], t_im);
+      }
     }
     g_first = false;
     if (tm.flags & WFM_TERM_GROUP_END) {
-      total.re = add(total.re, g_re);
-      if (kComplex) total.im = add(total.im, g_im);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        total.re[e] = add(total.re[e], g_re[e]);
+        if (kComplex) total.im[e] = add(total.im[e], g_im[e]);
+      }
       g_first = true;
     }
   }
-  if (w.flags & WFM_WAVE_CLIP) total.re = fmin(fmax(total.re, w.clip_lo), w.clip_hi);
-  return total;
+  if (w.flags & WFM_WAVE_CLIP) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) total.re[e] = fmin(fmax(total.re[e], w.clip_lo), w.clip_hi);
+  }
 }
 
 template <typename OutT, bool kAccumulate>
 __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const TileDesc* __restrict__ tiles,
                                                           OutT* __restrict__ out) {
   constexpr int V = OutVec<OutT>::N;
-  constexpr int kRowSamples = kThreads * V;
-  __shared__ double s_bound[kStageSegs];
+  constexpr int kChunk = 32 * V;                      // samples per warp-chunk
+  constexpr int kChunks = kTileSamples / kChunk;      // chunks per tile
+  __shared__ int s_start[kStageSegs + 1];             // first tile-sample of staged segment k
   __shared__ WfmSegPtr s_ptr[kStageSegs + 1];
-  __shared__ int s_range[2];
+  __shared__ int s_chunk_seg[kMaxChunks];
 
   const TileDesc td = tiles[blockIdx.x];
   const WfmWave w = P.waves[td.wave];
@@ -154,65 +244,113 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp < 2) {
-    const int64_t j = warp == 0 ? j0 : j0 + cnt - 1;
-    const int s = warp_segment_search(gb, w.n_seg, abscissa(w, P.x, j), lane);
-    if (lane == 0) s_range[warp] = s;
-  }
-  __syncthreads();
-  const int seg_lo = s_range[0];
-  const int nb = s_range[1] - seg_lo + 1;  // abscissae are non-decreasing => >= 1
-  const bool staged = nb <= kStageSegs;
-  if (staged) {
-    for (int k = threadIdx.x; k < nb; k += kThreads) s_bound[k] = gb[seg_lo + k];
-    for (int k = threadIdx.x; k <= nb; k += kThreads) s_ptr[k] = gp[seg_lo + k];
-  }
-  __syncthreads();
-
+  const int seg_lo = td.seg_lo;
+  const int nb = td.seg_hi - seg_lo + 1;
   OutT* __restrict__ dst = out + w.out_off + j0;
-  const bool tile_zero = nb == 1 && s_ptr[0].term == s_ptr[1].term && w.offset == 0.0;
 
-  for (int base = threadIdx.x * V; base < cnt; base += kRowSamples) {
-    double v[V];
-    if (tile_zero) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) v[e] = 0.0;
-    } else {
-      int seg = 0;  // relative to seg_lo
-#pragma unroll
+  if (nb > kStageSegs) {
+    // pathological density (> 1024 segments in one tile): per-sample search in global memory
+    for (int base = threadIdx.x * V; base < cnt; base += kThreads * V) {
+      double v[V];
+      int seg = seg_lo;
+#pragma unroll 1
       for (int e = 0; e < V; ++e) {
-        const int jj = base + e;
-        if (jj >= cnt) { v[e] = 0.0; continue; }
-        const double x = abscissa(w, P.x, j0 + jj);
-        WfmSegPtr p0, p1;
-        if (staged) {
-          if (e == 0) {
-            int lo = 0, hi = nb - 1;  // first k with s_bound[k] > x
-            while (lo < hi) {
-              int mid = (lo + hi) >> 1;
-              if (s_bound[mid] <= x) lo = mid + 1; else hi = mid;
-            }
-            seg = lo;
-          } else {
-            while (seg < nb - 1 && s_bound[seg] <= x) ++seg;
-          }
-          p0 = s_ptr[seg];
-          p1 = s_ptr[seg + 1];
-        } else {
-          int lo = (e == 0) ? 0 : seg, hi = nb - 1;
-          while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(gb + seg_lo + mid) <= x) lo = mid + 1; else hi = mid;
-          }
-          seg = lo;
-          p0 = gp[seg_lo + seg];
-          p1 = gp[seg_lo + seg + 1];
-        }
-        v[e] = eval_segment<false>(P, w, p0, p1, x).re;
+        v[e] = 0.0;
+        if (base + e >= cnt) continue;
+        double x1[1] = {abscissa(w, P.x, j0 + base + e)};
+        while (seg < td.seg_hi && __ldg(gb + seg) <= x1[0]) ++seg;
+        Acc<1> a;
+        eval_segment<1, false>(P, w, gp[seg], gp[seg + 1], x1, a);
+        v[e] = a.re[0];
+      }
+      for (int e = 0; e < V && base + e < cnt; ++e)
+        dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
+    }
+    return;
+  }
+
+  // ---- stage the tile's segment slice: sample positions + program pointers ----------
+  for (int k = threadIdx.x; k <= nb; k += kThreads) {
+    s_ptr[k] = gp[seg_lo + k];
+    int pos;
+    if (k == 0) pos = 0;
+    else if (k == nb) pos = cnt;
+    else pos = first_sample_at_or_after(w, P.x, j0, cnt, gb[seg_lo + k - 1]);
+    s_start[k] = pos;
+  }
+  __syncthreads();
+  if (threadIdx.x < kChunks) {
+    // staged segment that owns the first sample of chunk c: last k with s_start[k] <= c*kChunk
+    const int jj = threadIdx.x * kChunk;
+    int lo = 0, hi = nb - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_start[mid] <= jj) lo = mid; else hi = mid - 1;
+    }
+    s_chunk_seg[threadIdx.x] = lo;
+  }
+  __syncthreads();
+
+  for (int c = warp; c * kChunk < cnt; c += kThreads / 32) {
+    const int cbeg = c * kChunk;
+    const int cend = min(cbeg + kChunk, cnt);
+    const int base = cbeg + lane * V;
+    const int k0 = s_chunk_seg[c];
+    const bool uniform = s_start[k0 + 1] >= cend;  // whole chunk inside staged segment k0
+    double v[V];
+    bool done = false;
+    if (uniform) {
+      const WfmSegPtr p0 = s_ptr[k0], p1 = s_ptr[k0 + 1];
+      if (p0.term == p1.term) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = w.offset;  // empty segment: no abscissa needed
+        done = true;
+      } else if (base + V <= cend) {
+        double x[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) x[e] = abscissa(w, P.x, j0 + base + e);
+        Acc<V> a;
+        eval_segment<V, false>(P, w, p0, p1, x, a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = a.re[e];
+        done = true;
       }
     }
-    if (base + V <= cnt) {
+    if (!done) {
+      int k = k0;
+      // lanes advance from the chunk's first segment to their own
+      while (k < nb - 1 && s_start[k + 1] <= base) ++k;
+      if (base + V <= cend && s_start[k + 1] >= base + V) {
+        const WfmSegPtr p0 = s_ptr[k], p1 = s_ptr[k + 1];
+        if (p0.term == p1.term) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[e] = w.offset;
+        } else {
+          double x[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) x[e] = abscissa(w, P.x, j0 + base + e);
+          Acc<V> a;
+          eval_segment<V, false>(P, w, p0, p1, x, a);
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[e] = a.re[e];
+        }
+      } else {
+        // a bound falls between this thread's samples (or the tile ends): one by one
+#pragma unroll 1
+        for (int e = 0; e < V; ++e) {
+          v[e] = 0.0;
+          if (base + e >= cend) continue;
+          while (k < nb - 1 && s_start[k + 1] <= base + e) ++k;
+          const WfmSegPtr p0 = s_ptr[k], p1 = s_ptr[k + 1];
+          if (p0.term == p1.term) { v[e] = w.offset; continue; }
+          double x1[1] = {abscissa(w, P.x, j0 + base + e)};
+          Acc<1> a;
+          eval_segment<1, false>(P, w, p0, p1, x1, a);
+          v[e] = a.re[0];
+        }
+      }
+    }
+    if (base + V <= cend) {
       if (kAccumulate) {
         double old[V];
         load_vec(dst + base, old);
@@ -221,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
       }
       store_vec(dst + base, v);
     } else {
-      for (int e = 0; e < V && base + e < cnt; ++e)
+      for (int e = 0; e < V && base + e < cend; ++e)
         dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
     }
   }
@@ -238,23 +376,32 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   double2* __restrict__ dst = out + w.out_off + j0;
-  int seg = 0;
+  int seg = td.seg_lo;
   for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
-    const double x = abscissa(w, P.x, j0 + jj);
-    int lo = seg, hi = w.n_seg - 1;
+    double x1[1] = {abscissa(w, P.x, j0 + jj)};
+    int lo = seg, hi = td.seg_hi;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (__ldg(gb + mid) <= x) lo = mid + 1; else hi = mid;
+      if (__ldg(gb + mid) <= x1[0]) lo = mid + 1; else hi = mid;
     }
     seg = lo;
-    Acc a = eval_segment<true>(P, w, gp[seg], gp[seg + 1], x);
+    Acc<1> a;
+    eval_segment<1, true>(P, w, gp[seg], gp[seg + 1], x1, a);
+    double re = a.re[0], im = a.im[0];
     if (kAccumulate) {
       double2 o = dst[jj];
-      a.re = add(o.x, a.re);
-      a.im = add(o.y, a.im);
+      re = add(o.x, re);
+      im = add(o.y, im);
     }
-    dst[jj] = make_double2(a.re, a.im);
+    dst[jj] = make_double2(re, im);
   }
+}
+
+cudaError_t launch_prepare_tiles(const DevProgram& P, TileDesc* tiles, int64_t n_tiles, cudaStream_t stream) {
+  if (n_tiles == 0) return cudaSuccess;
+  const int threads = 128;
+  prepare_tiles_kernel<<<(unsigned)((n_tiles + threads - 1) / threads), threads, 0, stream>>>(P, tiles, n_tiles);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t n_tiles, int dtype, int accumulate,

@@ -1,0 +1,271 @@
+"""Flux-line predistortion — drop-in for /root/reference/waveforms/distortion.py.
+
+Filter DESIGN stays on the host (tiny polynomial / root-finding work, SciPy as
+in the reference): ``exp_decay_filter``, ``high_pass_filter``,
+``combine_filters``, ``factor_filter``, ``stable_filter``, ``reflection_filter``,
+``zDistortKernel``.  Filter APPLICATION to sampled signals runs on the GPU:
+
+    predistort / distort  lfilter  -> wfm_lfilter (bit-faithful DF2T, K2)
+                          kernel convolution -> wfm_fft_filter (K3)
+    reflection / correct_reflection          -> wfm_fft_filter (K3)
+
+Signals may be NumPy arrays (copied to the current CUDA device and back, like
+any other call of this package) or CUDA torch tensors of shape (n,) or
+(n_sig, n), which are processed as a batch and stay on the device.
+"""
+from __future__ import annotations
+
+import warnings
+from itertools import zip_longest
+from typing import Sequence
+
+import numpy as np
+from scipy.signal import lfiltic, tf2zpk, zpk2sos, zpk2tf
+
+from . import dsp
+
+
+def _to_device(sig):
+    """(tensor, was_numpy)"""
+    import torch
+    if isinstance(sig, torch.Tensor):
+        return sig.to(dtype=torch.float64).contiguous().clone(), False
+    arr = np.ascontiguousarray(np.asarray(sig, dtype=np.float64))
+    return torch.from_numpy(arr).cuda(), True
+
+
+def _from_device(t, was_numpy):
+    return t.cpu().numpy() if was_numpy else t
+
+
+def shift(signal: np.ndarray, delay: float, dt: float) -> np.ndarray:
+    """delay a signal (reference distortion.py:12-39; host, three-tap
+    interpolation + integer shift — not on the GPU path)."""
+    points = int(delay // dt)
+    delta = delay / dt - points
+    if delta > 0:
+        signal = np.convolve(signal, np.array([0, 1 - delta, delta]),
+                             mode='same')
+    if points == 0:
+        return signal
+    ret = np.zeros_like(signal)
+    if points < 0:
+        ret[:points] = signal[-points:]
+    else:
+        ret[points:] = signal[:-points]
+    return ret
+
+
+def extractKernel(sig_in, sig_out, sample_rate, bw=None, skip=0):
+    """Calibration helper (reference distortion.py:42-48), host."""
+    from scipy.fftpack import fft, ifft, ifftshift
+    corr = fft(sig_in) / fft(sig_out)
+    ker = np.real(ifftshift(ifft(corr)))
+    if bw is not None and bw < 0.5 * sample_rate:
+        k = np.exp(-0.5 * np.linspace(-3.0, 3.0, int(2 * sample_rate / bw))**2)
+        ker = np.convolve(ker, k / k.sum(), mode='same')
+    return ker[int(skip):len(ker) - int(skip)]
+
+
+def zDistortKernel(dt: float, params: Sequence[tuple]) -> np.ndarray:
+    """reference distortion.py:51-60 (design: a ~2k-point host transform)."""
+    from scipy.fftpack import fftfreq, ifft, ifftshift
+    t = 3 * np.asarray(params)[:, 0].max()
+    omega = 2 * np.pi * fftfreq(int(t / dt) + 1, dt)
+    H = 1
+    for tau, A in params:
+        H += (1j * A * omega * tau) / (1j * omega * tau + 1)
+    return ifftshift(ifft(1 / H)).real
+
+
+def high_pass_filter(tau, sample_rate):
+    k = 2.0 * tau * sample_rate
+    return [k / (1 + k), -k / (1 + k)], [1.0, (1 - k) / (1 + k)]
+
+
+def exp_decay_filter_old(amp, tau, sample_rate):
+    """reference distortion.py:73-99"""
+    alpha = 1 - np.exp(-1 / (abs(sample_rate * tau) * (1 + amp)))
+    if amp >= 0:
+        k = amp / (1 + amp - alpha)
+        a = [(1 - k + k * alpha), -(1 - k) * (1 - alpha)]
+    else:
+        k = -amp / (1 + amp) / (1 - alpha)
+        a = [(1 + k - k * alpha), -(1 + k) * (1 - alpha)]
+    b = [1 / a[0], -(1 - alpha) / a[0]]
+    return b, [1, a[1] / a[0]]
+
+
+def exp_decay_filter(amp, tau, sample_rate, inv: bool = False, output='ba'):
+    """Multi-exponential step-response filter
+    out(t) = u(t) (1 - sum_i A_i exp(-t/tau_i)); reference distortion.py:102-185.
+    output: 'ba' | 'sos' | 'zpk'."""
+    if isinstance(amp, (int, float, complex)):
+        amp, tau = [amp], [tau]
+    numerator, denominator = np.poly1d([0.0]), np.poly1d([1.0])
+    for i, (A, t) in enumerate(zip(amp, tau)):
+        denominator = denominator * np.poly1d([1, -1 / t])
+        term = np.poly1d([-A, 0.0])
+        for j, t_ in enumerate(tau):
+            if j != i:
+                term = term * np.poly1d([1, -1 / t_])
+        numerator = numerator + term
+    numerator = numerator + denominator
+
+    z = np.exp(-numerator.roots / sample_rate)
+    p = np.exp(-1 / (np.asarray(tau) * sample_rate))
+    if inv:
+        z, p = p, z
+    p = p[np.abs(p) < 1]  # drop unstable poles
+    k = (np.prod(1 - p) / np.prod(1 - z)).real
+    if output == 'sos':
+        return zpk2sos(z, p, k)
+    if output == 'ba':
+        return zpk2tf(z, p, k)
+    if output == 'zpk':
+        return z, p, k
+    raise ValueError(f"Invalid output type: {output}")
+
+
+def reflection_filter(f, A, tau):
+    """H(f) = (1 - A) / (1 - A exp(-2 pi i f tau)); reference :188-205."""
+    return (1 - A) / (1 - A * np.exp(-2j * np.pi * f * tau))
+
+
+def reflection(sig, A, tau, sample_rate):
+    """ifft(fft(sig) * H).real on the GPU (reference :208-210)."""
+    dev, was_np = _to_device(sig)
+    freq = np.fft.fftfreq(dev.shape[-1], 1 / sample_rate)
+    out = dsp.fft_filter_device(dev, reflection_filter(freq, A, tau), out=dev)
+    return _from_device(out, was_np)
+
+
+def correct_reflection(sig, A, tau, sample_rate=None):
+    """Waveform -> symbolic inverse (sig/(1-A) - A/(1-A) (sig >> tau));
+    sampled signal -> ifft(fft(sig) / H).real on the GPU (reference :213-223)."""
+    from .waveform import Waveform
+    if isinstance(sig, Waveform):
+        return 1 / (1 - A) * sig - A / (1 - A) * (sig >> tau)
+    if sample_rate is None:
+        raise ValueError('sample_rate is not given')
+    dev, was_np = _to_device(sig)
+    freq = np.fft.fftfreq(dev.shape[-1], 1 / sample_rate)
+    out = dsp.fft_filter_device(dev, 1 / reflection_filter(freq, A, tau),
+                                out=dev)
+    return _from_device(out, was_np)
+
+
+def combine_filters(filters):
+    """Polynomial product of (b, a) pairs (reference :226-244)."""
+    b, a = np.poly1d([1.0]), np.poly1d([1.0])
+    for b_, a_ in filters:
+        b = b * np.poly1d(b_)
+        a = a * np.poly1d(a_)
+    return b.coeffs, a.coeffs
+
+
+def factor_filter(b, a):
+    """Split into first-order sections (reference :247-266)."""
+    b, a = np.poly1d(b), np.poly1d(a)
+    p, q = a.roots, b.roots
+    b_amp = (b[0] / a[0])**(1 / max(len(q), len(p)))
+    return [([b_amp, -b_amp * b_], [1, -a_])
+            for a_, b_ in zip_longest(p, q, fillvalue=0)]
+
+
+def stable_filter(exp_decay_filters: list, sample_rate: float):
+    """reference :269-286 (including its (a, b) unpacking order)."""
+    filters = []
+    for amp, tau in exp_decay_filters:
+        a, b = exp_decay_filter(amp, tau, sample_rate)
+        filters.append((b, a))
+    b, a = combine_filters(filters)
+    z, p, k = tf2zpk(b, a)
+    return bool(np.all(np.abs(p) < 1))
+
+
+def _centered_kernel_response(ker, n):
+    """Frequency response of the zero-padded linear convolution the reference
+    performs with fftconvolve over a 3n-padded signal and then slices
+    [n + K//2 : 2n + K//2] (reference :329-333): on a length-L circular grid
+    (L >= n + K - 1) that is the kernel advanced by K//2 samples."""
+    K = len(ker)
+    L = dsp_next_fast_len(n + K - 1)
+    h = np.zeros(L)
+    h[:K] = ker
+    h = np.roll(h, -(K // 2))
+    return np.fft.fft(h), L
+
+
+def dsp_next_fast_len(m):
+    """Smallest 7-smooth length >= m (the device FFT's radix set)."""
+    def smooth(v):
+        for r in (2, 3, 5, 7):
+            while v % r == 0:
+                v //= r
+        return v == 1
+    while not smooth(m):
+        m += 1
+    return m
+
+
+def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
+               initial_x=None, initial_y=None, zi=None, return_zf: bool = False):
+    """IIR predistortion (lfilter with lfiltic initial state) followed by an
+    optional centred kernel convolution; reference :289-337."""
+    import torch
+    dev, was_np = _to_device(sig)
+    zf = None
+    if filters is not None:
+        b, a = combine_filters(filters)
+        z, p, k = tf2zpk(b, a)
+        if not np.all(np.abs(p) < 1):
+            warnings.warn('Warning: filter is unstable')
+        if zi is None:
+            if initial_x is None:
+                initial_x = np.full((len(b) - 1, ), initial)
+            else:
+                initial_x = np.asarray(initial_x)[:len(b) - 1]
+            if initial_y is None:
+                initial_y = np.full((len(a) - 1, ), initial)
+            else:
+                initial_y = np.asarray(initial_y)[:len(a) - 1]
+            zi = lfiltic(b, a, initial_y, initial_x)
+        dev, zf = dsp.lfilter_device(b, a, dev, zi=zi, want_zf=True)
+        if zf is not None and dev.dim() == 1:
+            zf = zf[0]
+    if ker is not None:
+        ker = np.asarray(ker, dtype=np.float64)
+        n = dev.shape[-1]
+        Hk, L = _centered_kernel_response(ker, n)
+        pad = torch.zeros(dev.shape[:-1] + (L, ), dtype=torch.float64,
+                          device=dev.device)
+        pad[..., :n] = dev
+        dev = dsp.fft_filter_device(pad, Hk, out=pad)[..., :n].contiguous()
+    out = _from_device(dev, was_np)
+    return (out, zf) if return_zf else out
+
+
+def distort(points, params, sample_rate, initial=0.0):
+    """reference :340-346"""
+    filters = []
+    for amp, tau in np.asarray(params).reshape(-1, 2):
+        b, a = exp_decay_filter(amp, abs(tau), sample_rate)
+        filters.append((b, a))
+    return predistort(points, filters, initial=initial)
+
+
+def phase_curve(t, params, df_dphi, pulse_width, start, wav, sample_rate):
+    """Calibration fitting helper (reference :349-366): samples ``wav`` and
+    distorts it on the GPU, the boxcar integration and interpolation stay host."""
+    lim = max(np.max(np.abs(t)), 20e-6)
+    num = round(2 * lim * sample_rate)
+    tlist = np.arange(num) / sample_rate - lim
+    points = wav(tlist)
+    pulse_points = round(pulse_width * sample_rate)
+    start_points = round((start + pulse_width) * sample_rate) - 1
+    ker = np.hstack([np.ones(pulse_points) / sample_rate,
+                     np.zeros(start_points)])
+    points = np.convolve(2 * np.pi * df_dphi *
+                         distort(points, params, sample_rate), ker, mode='same')
+    return np.interp(t, tlist, points)

@@ -75,3 +75,59 @@ def apply_channel_filters(out, batch, waveforms):
         sos, initial = w.filters
         off, n = int(batch.waves['out_off'][k]), int(batch.waves['n'][k])
         sosfilt_device(sos, out[off:off + n], initial=initial or 0.0)
+
+
+def lfilter_device(b, a, x, zi=None, want_zf=False):
+    """scipy.signal.lfilter(b, a, x, zi=zi) on a CUDA f64 tensor (n,) or
+    (n_sig, n), in place; bit-identical sequential kernel.  Returns (y, zf)."""
+    import torch
+    lib = engine.require_gpu()
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1))
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    order = max(len(a), len(b)) - 1
+    x2 = x if x.dim() == 2 else x.unsqueeze(0)
+    assert x2.dtype == torch.float64 and x2.stride(1) == 1
+    n_sig, n = x2.shape
+    zi_arr = None
+    if zi is not None and order > 0:
+        zi_arr = np.ascontiguousarray(
+            np.broadcast_to(np.asarray(zi, dtype=np.float64), (n_sig, order)))
+    zf = np.zeros((n_sig, max(order, 0))) if want_zf else None
+    rc = lib.wfm_lfilter(b.ctypes.data, len(b), a.ctypes.data, len(a),
+                         x2.data_ptr(), x2.data_ptr(), n_sig, n, x2.stride(0),
+                         zi_arr.ctypes.data if zi_arr is not None else None,
+                         zf.ctypes.data if zf is not None and order > 0 else None,
+                         _stream(torch, x.device))
+    engine._check(rc)
+    return x, zf
+
+
+def fft_filter_device(x, H, out=None):
+    """real(ifft(fft(x) * H)) on a CUDA f64 tensor (n,) or (n_sig, n);
+    ``H`` is a host complex array on the np.fft.fftfreq grid."""
+    import torch
+    lib = engine.require_gpu()
+    x2 = x if x.dim() == 2 else x.unsqueeze(0)
+    assert x2.dtype == torch.float64 and x2.stride(1) == 1
+    n_sig, n = x2.shape
+    H = np.ascontiguousarray(np.asarray(H, dtype=np.complex128).reshape(-1))
+    assert H.size == n
+    y = torch.empty_like(x2) if out is None else (out if out.dim() == 2 else out.unsqueeze(0))
+    rc = lib.wfm_fft_filter(x2.data_ptr(), y.data_ptr(), n_sig, n, x2.stride(0),
+                            H.ctypes.data, _stream(torch, x.device))
+    engine._check(rc)
+    return y if x.dim() == 2 else y[0]
+
+
+def fft_c2c_device(z, inverse=False):
+    """np.fft.fft / np.fft.ifft of a CUDA complex128 tensor (n,) or (n_sig, n),
+    in place."""
+    import torch
+    lib = engine.require_gpu()
+    z2 = z if z.dim() == 2 else z.unsqueeze(0)
+    assert z2.dtype == torch.complex128 and z2.stride(1) == 1
+    n_sig, n = z2.shape
+    rc = lib.wfm_fft_c2c(z2.data_ptr(), n_sig, n, z2.stride(0),
+                         1 if inverse else -1, _stream(torch, z.device))
+    engine._check(rc)
+    return z

@@ -55,7 +55,7 @@ EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
-    'wfm_fft_filter', 'wfm_fft_c2c'
+    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c'
 ]
 
 
@@ -88,6 +88,11 @@ def load_library():
             C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
             C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
             C.c_int32, C.c_void_p
+        ]
+        lib.wfm_lfilter.argtypes = [
+            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+            C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+            C.c_void_p, C.c_void_p
         ]
         lib.wfm_fft_filter.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
