@@ -140,6 +140,11 @@ static int validate(const WfmProgramDesc* d) {
     if (b.term > a.term && !(d->terms[b.term - 1].flags & WFM_TERM_GROUP_END))
       return fail(WFM_EINVAL, "segment %lld: last term does not close its group", (long long)s);
   }
+  // the sampling kernel stages a tile's references as ONE contiguous slice: they
+  // must be packed in term order
+  for (int64_t t = 0; t + 1 < d->n_terms; ++t)
+    if (d->terms[t + 1].ref_begin != d->terms[t].ref_begin + d->terms[t].n_ref)
+      return fail(WFM_EINVAL, "term %lld: references must be packed in term order", (long long)(t + 1));
   for (int64_t w = 0; w < d->n_waves; ++w) {
     const WfmWave& wv = d->waves[w];
     if (wv.n < 0 || wv.out_off < 0) return fail(WFM_EINVAL, "channel %lld: negative extent", (long long)w);

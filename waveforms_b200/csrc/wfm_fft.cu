@@ -199,12 +199,13 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
 }
 
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
-// FWD: real x[N2*n1 + n2] -> FFT over n1 -> * W_n^(n2 k1) -> scratch[k1*N2 + n2]
-// INV: scratch[k1*N2 + n2] * conj W -> IFFT over k1 -> real(...)/n -> y[N2*n1 + n2]
-template <bool kFwd, bool kRealIO>
+// element (r, n2) of the [N1][N2] view; the inter-pass twiddle W_n^(sgn * r * n2) is
+// applied after the transform (first pass of a forward-structured transform) or
+// before it (last pass of the fused filter, undoing the forward pass)
+template <bool kTwAfter, bool kRealIn, bool kRealOut>
 __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, int N2, int C, const void* __restrict__ in,
                                                                void* __restrict__ out, int64_t in_stride,
-                                                               int64_t out_stride, double scale) {
+                                                               int64_t out_stride, double sgn, double scale) {
   const int N1 = P.L;
   const int64_t n = (int64_t)N1 * N2;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
@@ -212,18 +213,17 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, int N2
   const int c0 = blockIdx.x * C;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
-  const double sgn = kFwd ? -1.0 : 1.0;
   for (int e = threadIdx.x; e < N1 * C; e += blockDim.x) {
     const int c = e % C, r = e / C;
     double2 v = make_double2(0.0, 0.0);
     if (c < cw) {
       const int64_t idx = (int64_t)r * N2 + c0 + c;
-      if (kFwd && kRealIO) {
+      if (kRealIn) {
         v.x = static_cast<const double*>(in)[sig * in_stride + idx];
       } else {
         v = static_cast<const double2*>(in)[sig * in_stride + idx];
-        if (!kFwd) v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, +1.0));
       }
+      if (!kTwAfter) v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, sgn));
     }
     a[e] = v;
   }
@@ -234,14 +234,9 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, int N2
     if (c >= cw) continue;
     const int64_t idx = (int64_t)r * N2 + c0 + c;
     double2 v = f[e];
-    if (kFwd) {
-      v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, -1.0));
-      static_cast<double2*>(out)[sig * out_stride + idx] = v;
-    } else if (kRealIO) {
-      static_cast<double*>(out)[sig * out_stride + idx] = v.x * scale;
-    } else {
-      static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
-    }
+    if (kTwAfter) v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, sgn));
+    if (kRealOut) static_cast<double*>(out)[sig * out_stride + idx] = v.x * scale;
+    else static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
   }
 }
 
@@ -459,17 +454,8 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   const int C1 = tile_width(N1, 8), C2 = tile_width(N2, 4);
   const size_t smem1 = 2 * sizeof(double2) * (size_t)N1 * C1, smem2 = 2 * sizeof(double2) * (size_t)N2 * C2;
   dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
-  if (sgn < 0) {
-    if ((e = set_smem(fft_cols_kernel<true, false>, smem1)) != cudaSuccess) goto done;
-    // forward twiddle is applied after the column transform
-    fft_cols_kernel<true, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, data, scratch, stride, n, 1.0);
-  } else {
-    // inverse: same four-step with conjugate roots; the conj twiddle of the
-    // forward-structured inverse is applied between the passes, which for the
-    // decimation used here means AFTER the column pass as well
-    if ((e = set_smem(fft_cols_kernel<true, false>, smem1)) != cudaSuccess) goto done;
-    fft_cols_kernel<true, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, data, scratch, stride, n, 1.0);
-  }
+  if ((e = set_smem(fft_cols_kernel<true, false, false>, smem1)) != cudaSuccess) goto done;
+  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, data, scratch, stride, n, sgn, 1.0);
   if ((e = cudaGetLastError()) != cudaSuccess) goto done;
   if ((e = set_smem(fft_rows_kernel<false>, smem2)) != cudaSuccess) goto done;
   fft_rows_kernel<false><<<g2, kFftThreads, smem2, st>>>(P2, N1, C2, scratch, data, n, stride, nullptr, sgn, scale);
@@ -484,10 +470,6 @@ static cudaError_t c2c_any(double2* data, int64_t n_sig, int64_t n, int64_t stri
                            cudaStream_t st) {
   if (n <= 1) return cudaSuccess;
   if (is_smooth(n) && (n <= kMaxPoints || [&] { int a, b; return split_two_level(n, &a, &b); }())) {
-    if (sgn > 0) {
-      // inverse through the forward machinery: ifft(x) = conj(fft(conj(x)))/n is
-      // avoided; the kernels take the sign directly
-    }
     return c2c_smooth(data, n_sig, n, stride, sgn, scale, st);
   }
   const int64_t M = next_smooth(2 * n - 1);
@@ -566,13 +548,14 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
     const int C1 = tile_width(N1, 8), C2 = tile_width(N2, 4);
     const size_t smem1 = 2 * sizeof(double2) * (size_t)N1 * C1, smem2 = 2 * sizeof(double2) * (size_t)N2 * C2;
     dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
-    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true>, smem1);
-    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, true>, smem1);
+    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
+    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
     if (e == cudaSuccess) {
-      fft_cols_kernel<true, true><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, x, scratch, stride, n, 1.0);
+      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, x, scratch, stride, n, -1.0, 1.0);
       fft_rows_kernel<true><<<g2, kFftThreads, smem2, st>>>(P2, N1, C2, scratch, nullptr, n, 0, dH, -1.0, 1.0);
-      fft_cols_kernel<false, true><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, scratch, y, n, stride, 1.0 / (double)n);
+      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, scratch, y, n, stride, +1.0,
+                                                                          1.0 / (double)n);
       e = cudaGetLastError();
     }
     if (scratch) cudaFreeAsync(scratch, st);

@@ -12,21 +12,25 @@
 //  0. (once per program, prepare_tiles_kernel) every tile learns the segments of
 //     its first and last abscissa: one thread per tile, binary search over the
 //     channel's bounds.
-//  1. The CTA turns the tile's slice of the bound table into INTEGER sample
-//     positions: thread k finds the first sample of the tile whose abscissa is
-//     >= bound k — a division for the guess, then exact comparisons against the
+//  1. Prologue.  Thread k turns bound k of the tile's slice of the segment table
+//     into an INTEGER sample position: the first sample whose abscissa is >= the
+//     bound — a division for the guess, then exact comparisons against the
 //     rounded grid value x[j] = t0 + j*delta, so ownership is bit-identical to
-//     np.searchsorted on the reference's grid.  Positions and the segments'
-//     factor/term pointers live in shared memory.
-//  2. A warp owns chunks of 32*V consecutive samples (V = 2 fp64 / 4 fp32 per
-//     thread = one 16-byte store per thread, 512 contiguous bytes per warp).
-//     The chunk's first segment comes from a per-chunk table (one LDS).  A chunk
-//     that lies inside one segment is warp-uniform: an empty (zero) segment
-//     costs a store and nothing else — no abscissa, no search; a non-empty one
-//     runs the segment program without divergence.  Mixed chunks let every lane
-//     advance from the chunk's first segment.
-//  3. The segment program (distinct factors, then terms referencing factor
-//     slots) is interpreted for the thread's V samples at once.
+//     np.searchsorted on the reference's grid.  It also classifies the segment:
+//     FLAT (no basis factor: zero, or a constant evaluated once here) or ACTIVE.
+//     Meanwhile one thread starts a TMA bulk copy (cp.async.bulk + mbarrier) of
+//     the tile's slice of the factor / term / reference tables into shared
+//     memory.
+//  2. Phase 1 — stores.  A warp owns chunks of 32*V consecutive samples (V = 2
+//     fp64 / 4 fp32 per thread = one 16-byte store per thread, 512 contiguous
+//     bytes per warp).  Every sample of a FLAT segment is written here; no
+//     abscissa is computed.  This is the HBM-write-bound part.
+//  3. Phase 2 — compute.  The ACTIVE samples of the tile are enumerated through
+//     a prefix sum over the segments and dealt round-robin to all 256 threads, so
+//     a tile with one 40-sample pulse keeps 40 lanes of 2 warps busy once instead
+//     of serialising inside one warp, and a dense tile keeps every lane busy.
+//     Each thread interprets its sample's segment program (distinct factors,
+//     then terms referencing factor slots) out of shared memory.
 //
 // Output is write-once: stores use st.global.cs (evict-first) so they do not
 // displace the IR in L2.  Algorithmic traffic: 8 B (4 B) per sample, write-only.
@@ -39,9 +43,10 @@
 namespace wfm {
 
 constexpr int kThreads = 256;
-constexpr int kStageSegs = 1024;  // segment rows staged per tile
+constexpr int kStageSegs = 512;   // segment rows staged per tile
 constexpr int kMaxSlots = 12;     // distinct factor values cached per segment evaluation
 constexpr int kMaxChunks = kTileSamples / 64;
+constexpr int kIrBytes = 24576;   // shared-memory budget for the tile's factor/term/ref slice
 
 template <typename T> struct OutVec;
 template <> struct OutVec<double> { static constexpr int N = 2; };
@@ -55,6 +60,12 @@ __device__ __forceinline__ void store_vec(float* p, const double (&v)[4]) {
                "f"((float)v[2]), "f"((float)v[3])
                : "memory");
 }
+__device__ __forceinline__ void store_one(double* p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void store_one(float* p, double v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"((float)v) : "memory");
+}
 __device__ __forceinline__ void load_vec(const double* p, double (&v)[2]) {
   double2 t = *reinterpret_cast<const double2*>(p);
   v[0] = t.x; v[1] = t.y;
@@ -62,6 +73,39 @@ __device__ __forceinline__ void load_vec(const double* p, double (&v)[2]) {
 __device__ __forceinline__ void load_vec(const float* p, double (&v)[4]) {
   float4 t = *reinterpret_cast<const float4*>(p);
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+// ---- mbarrier + TMA bulk copy (global -> shared) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// size and both addresses must be multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // abscissa of sample j of channel w: x[j] = t0 + j*delta — a multiply and an add,
@@ -123,108 +167,59 @@ __device__ int first_sample_at_or_after(const WfmWave& w, const double* __restri
   return lo;
 }
 
-template <int V>
-struct Acc {
-  double re[V];
-  double im[V];
+// where the interpreter reads the program from: global tables, or the tile's
+// slice staged in shared memory (pointers pre-biased so global indices work)
+struct IrView {
+  const WfmFactor* facs;
+  const WfmTerm* terms;
+  const WfmRef* refs;
+  const double* args;
 };
 
-// basis function on V samples at once; the hot ids are unrolled over V so the
-// independent evaluations interleave, the rest fall back to the scalar code
-template <int V>
-__device__ __forceinline__ void eval_factor_v(const WfmFactor& f, const double (&x)[V], const double* __restrict__ args,
-                                              double (&out)[V]) {
-  switch (f.func) {
-    case WFM_COS:
-#pragma unroll
-      for (int e = 0; e < V; ++e) out[e] = cos(mul(f.a0, sub(x[e], f.shift)));
-      break;
-    case WFM_GAUSSIAN:
-#pragma unroll
-      for (int e = 0; e < V; ++e) out[e] = f_gaussian(sub(x[e], f.shift), f.a0);
-      break;
-    case WFM_ERF:
-#pragma unroll
-      for (int e = 0; e < V; ++e) out[e] = erf(dvd(sub(x[e], f.shift), f.a0));
-      break;
-    case WFM_LINEAR:
-#pragma unroll
-      for (int e = 0; e < V; ++e) out[e] = sub(x[e], f.shift);
-      break;
-    default:
-#pragma unroll 1
-      for (int e = 0; e < V; ++e) out[e] = eval_factor(f, x[e], args);
-      break;
-  }
-}
-
-// Evaluate one segment's program at V abscissae.
-template <int V, bool kComplex>
-__device__ __forceinline__ void eval_segment(const DevProgram& P, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1,
-                                             const double (&x)[V], Acc<V>& total) {
-#pragma unroll
-  for (int e = 0; e < V; ++e) { total.re[e] = w.offset; total.im[e] = 0.0; }
+// Evaluate one segment's program at one abscissa.
+template <bool kComplex>
+__device__ __forceinline__ void eval_segment(const IrView& ir, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1, double x,
+                                             double& out_re, double& out_im) {
+  out_re = w.offset;
+  out_im = 0.0;
   const int nt = p1.term - p0.term;
   if (nt == 0) return;  // zero segment: untouched by clip (calc_parts skips it)
   const int nf = p1.fac - p0.fac;
-  double vals[kMaxSlots][V];
-  const WfmFactor* __restrict__ facs = P.facs + p0.fac;
+  double vals[kMaxSlots];
+  const WfmFactor* facs = ir.facs + p0.fac;
 #pragma unroll 1
-  for (int k = 0; k < nf && k < kMaxSlots; ++k) eval_factor_v<V>(facs[k], x, P.args, vals[k]);
+  for (int k = 0; k < nf && k < kMaxSlots; ++k) vals[k] = eval_factor(facs[k], x, ir.args);
 
-  double g_re[V], g_im[V];
+  double g_re = 0.0, g_im = 0.0;
   bool g_first = true;
 #pragma unroll 1
   for (int it = 0; it < nt; ++it) {
-    const WfmTerm tm = P.terms[p0.term + it];
-    double prod[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) prod[e] = 1.0;
+    const WfmTerm tm = ir.terms[p0.term + it];
+    double prod = 1.0;
     bool p_first = true;
 #pragma unroll 1
     for (int r = 0; r < tm.n_ref; ++r) {
-      const WfmRef ref = P.refs[tm.ref_begin + r];
-      double v[V];
-      if (ref.slot < kMaxSlots) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = vals[ref.slot][e];
-      } else {
-        eval_factor_v<V>(facs[ref.slot], x, P.args, v);
-      }
-      if (ref.kind == WFM_POW_INT) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = pow_small_int(v[e], (int)ref.expo);
-      } else if (ref.kind == WFM_POW_GEN) {
-#pragma unroll 1
-        for (int e = 0; e < V; ++e) v[e] = pow(v[e], ref.expo);
-      }
-#pragma unroll
-      for (int e = 0; e < V; ++e) prod[e] = p_first ? v[e] : mul(prod[e], v[e]);  // 1 * v == v
+      const WfmRef ref = ir.refs[tm.ref_begin + r];
+      double v = (ref.slot < kMaxSlots) ? vals[ref.slot] : eval_factor(facs[ref.slot], x, ir.args);
+      if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
+      else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
+      prod = p_first ? v : mul(prod, v);  // 1 * v == v
       p_first = false;
     }
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const double t_re = mul(tm.amp_re, prod[e]);
-      g_re[e] = g_first ? t_re : add(g_re[e], t_re);  // 0 + a == a
-      if (kComplex) {
-        const double t_im = mul(tm.amp_im, prod[e]);
-        g_im[e] = g_first ? t_im : add(g_im[e], t_im);
-      }
+    const double t_re = mul(tm.amp_re, prod);
+    g_re = g_first ? t_re : add(g_re, t_re);  // 0 + a == a
+    if (kComplex) {
+      const double t_im = mul(tm.amp_im, prod);
+      g_im = g_first ? t_im : add(g_im, t_im);
     }
     g_first = false;
     if (tm.flags & WFM_TERM_GROUP_END) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        total.re[e] = add(total.re[e], g_re[e]);
-        if (kComplex) total.im[e] = add(total.im[e], g_im[e]);
-      }
+      out_re = add(out_re, g_re);
+      if (kComplex) out_im = add(out_im, g_im);
       g_first = true;
     }
   }
-  if (w.flags & WFM_WAVE_CLIP) {
-#pragma unroll
-    for (int e = 0; e < V; ++e) total.re[e] = fmin(fmax(total.re[e], w.clip_lo), w.clip_hi);
-  }
+  if (w.flags & WFM_WAVE_CLIP) out_re = fmin(fmax(out_re, w.clip_lo), w.clip_hi);
 }
 
 template <typename OutT, bool kAccumulate>
@@ -233,9 +228,15 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   constexpr int V = OutVec<OutT>::N;
   constexpr int kChunk = 32 * V;                      // samples per warp-chunk
   constexpr int kChunks = kTileSamples / kChunk;      // chunks per tile
-  __shared__ int s_start[kStageSegs + 1];             // first tile-sample of staged segment k
+  __shared__ __align__(16) unsigned char s_ir[kIrBytes];
   __shared__ WfmSegPtr s_ptr[kStageSegs + 1];
+  __shared__ double s_val[kStageSegs];                // value of a FLAT segment
+  __shared__ int s_start[kStageSegs + 1];             // first tile-sample of staged segment k
+  __shared__ int s_act[kStageSegs + 1];               // active samples before staged segment k
   __shared__ int s_chunk_seg[kMaxChunks];
+  __shared__ unsigned char s_active[kStageSegs];
+  __shared__ uint64_t s_bar;
+  __shared__ int s_staged;
 
   const TileDesc td = tiles[blockIdx.x];
   const WfmWave w = P.waves[td.wave];
@@ -247,110 +248,138 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   const int seg_lo = td.seg_lo;
   const int nb = td.seg_hi - seg_lo + 1;
   OutT* __restrict__ dst = out + w.out_off + j0;
+  IrView ir{P.facs, P.terms, P.refs, P.args};
 
   if (nb > kStageSegs) {
-    // pathological density (> 1024 segments in one tile): per-sample search in global memory
-    for (int base = threadIdx.x * V; base < cnt; base += kThreads * V) {
-      double v[V];
-      int seg = seg_lo;
-#pragma unroll 1
-      for (int e = 0; e < V; ++e) {
-        v[e] = 0.0;
-        if (base + e >= cnt) continue;
-        double x1[1] = {abscissa(w, P.x, j0 + base + e)};
-        while (seg < td.seg_hi && __ldg(gb + seg) <= x1[0]) ++seg;
-        Acc<1> a;
-        eval_segment<1, false>(P, w, gp[seg], gp[seg + 1], x1, a);
-        v[e] = a.re[0];
+    // pathological density (> 512 segments in one tile): per-sample search in global memory
+    for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
+      const double x = abscissa(w, P.x, j0 + jj);
+      int lo = seg_lo, hi = td.seg_hi;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(gb + mid) <= x) lo = mid + 1; else hi = mid;
       }
-      for (int e = 0; e < V && base + e < cnt; ++e)
-        dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
+      double re, im;
+      eval_segment<false>(ir, w, gp[lo], gp[lo + 1], x, re, im);
+      dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
     }
     return;
   }
 
-  // ---- stage the tile's segment slice: sample positions + program pointers ----------
+  // ---- prologue ------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // slice of the factor / term / ref tables this tile can touch
+    const WfmSegPtr a = gp[seg_lo], b = gp[seg_lo + nb];
+    const int nf = b.fac - a.fac, nt = b.term - a.term;
+    int r0 = 0, nr = 0;
+    if (nt > 0) {
+      r0 = P.terms[a.term].ref_begin;
+      const WfmTerm last = P.terms[b.term - 1];
+      nr = last.ref_begin + last.n_ref - r0;
+    }
+    const uint32_t bf = (uint32_t)nf * sizeof(WfmFactor), bt = (uint32_t)nt * sizeof(WfmTerm),
+                   br = (uint32_t)nr * sizeof(WfmRef);
+    const bool stage = (nf > 0) && (bf + bt + br <= (uint32_t)kIrBytes);
+    s_staged = stage ? 1 : 0;
+    if (stage) {
+      mbar_expect_tx(&s_bar, bf + bt + br);
+      bulk_g2s(s_ir, P.facs + a.fac, bf, &s_bar);
+      bulk_g2s(s_ir + bf, P.terms + a.term, bt, &s_bar);
+      if (br) bulk_g2s(s_ir + bf + bt, P.refs + r0, br, &s_bar);
+    }
+  }
   for (int k = threadIdx.x; k <= nb; k += kThreads) {
-    s_ptr[k] = gp[seg_lo + k];
+    const WfmSegPtr p0 = gp[seg_lo + k];
+    s_ptr[k] = p0;
     int pos;
     if (k == 0) pos = 0;
     else if (k == nb) pos = cnt;
     else pos = first_sample_at_or_after(w, P.x, j0, cnt, gb[seg_lo + k - 1]);
     s_start[k] = pos;
+    if (k < nb) {
+      const WfmSegPtr p1 = gp[seg_lo + k + 1];
+      const bool active = p1.fac > p0.fac;
+      s_active[k] = active ? 1 : 0;
+      double re = w.offset, im;
+      if (!active && p1.term > p0.term) eval_segment<false>(ir, w, p0, p1, 0.0, re, im);  // constant segment
+      s_val[k] = re;
+    }
   }
   __syncthreads();
-  if (threadIdx.x < kChunks) {
+  if (warp == 0) {
+    // exclusive prefix of active sample counts over the staged segments
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+      const int k = b0 + lane;
+      int c = (k < nb && s_active[k]) ? (s_start[k + 1] - s_start[k]) : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (k < nb) s_act[k] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_act[nb] = carry;
+  } else if (threadIdx.x - 32 < kChunks) {
     // staged segment that owns the first sample of chunk c: last k with s_start[k] <= c*kChunk
-    const int jj = threadIdx.x * kChunk;
+    const int c = threadIdx.x - 32;
+    const int jj = c * kChunk;
     int lo = 0, hi = nb - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_start[mid] <= jj) lo = mid; else hi = mid - 1;
     }
-    s_chunk_seg[threadIdx.x] = lo;
+    s_chunk_seg[c] = lo;
   }
   __syncthreads();
 
+  // ---- phase 1: every sample of a FLAT segment (store-bound, no abscissae) ------------
   for (int c = warp; c * kChunk < cnt; c += kThreads / 32) {
     const int cbeg = c * kChunk;
     const int cend = min(cbeg + kChunk, cnt);
     const int base = cbeg + lane * V;
     const int k0 = s_chunk_seg[c];
-    const bool uniform = s_start[k0 + 1] >= cend;  // whole chunk inside staged segment k0
     double v[V];
-    bool done = false;
-    if (uniform) {
-      const WfmSegPtr p0 = s_ptr[k0], p1 = s_ptr[k0 + 1];
-      if (p0.term == p1.term) {
+    if (s_start[k0 + 1] >= cend) {  // whole chunk inside staged segment k0
+      if (s_active[k0]) continue;
+      const double val = s_val[k0];
 #pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = w.offset;  // empty segment: no abscissa needed
-        done = true;
-      } else if (base + V <= cend) {
-        double x[V];
+      for (int e = 0; e < V; ++e) v[e] = val;
+      if (base + V <= cend) {
+        if (kAccumulate) {
+          double old[V];
+          load_vec(dst + base, old);
 #pragma unroll
-        for (int e = 0; e < V; ++e) x[e] = abscissa(w, P.x, j0 + base + e);
-        Acc<V> a;
-        eval_segment<V, false>(P, w, p0, p1, x, a);
-#pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = a.re[e];
-        done = true;
-      }
-    }
-    if (!done) {
-      int k = k0;
-      // lanes advance from the chunk's first segment to their own
-      while (k < nb - 1 && s_start[k + 1] <= base) ++k;
-      if (base + V <= cend && s_start[k + 1] >= base + V) {
-        const WfmSegPtr p0 = s_ptr[k], p1 = s_ptr[k + 1];
-        if (p0.term == p1.term) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) v[e] = w.offset;
-        } else {
-          double x[V];
-#pragma unroll
-          for (int e = 0; e < V; ++e) x[e] = abscissa(w, P.x, j0 + base + e);
-          Acc<V> a;
-          eval_segment<V, false>(P, w, p0, p1, x, a);
-#pragma unroll
-          for (int e = 0; e < V; ++e) v[e] = a.re[e];
+          for (int e = 0; e < V; ++e) v[e] = add(old[e], v[e]);
         }
+        store_vec(dst + base, v);
       } else {
-        // a bound falls between this thread's samples (or the tile ends): one by one
-#pragma unroll 1
-        for (int e = 0; e < V; ++e) {
-          v[e] = 0.0;
-          if (base + e >= cend) continue;
-          while (k < nb - 1 && s_start[k + 1] <= base + e) ++k;
-          const WfmSegPtr p0 = s_ptr[k], p1 = s_ptr[k + 1];
-          if (p0.term == p1.term) { v[e] = w.offset; continue; }
-          double x1[1] = {abscissa(w, P.x, j0 + base + e)};
-          Acc<1> a;
-          eval_segment<1, false>(P, w, p0, p1, x1, a);
-          v[e] = a.re[0];
-        }
+        for (int e = 0; e < V && base + e < cend; ++e)
+          dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
       }
+      continue;
     }
-    if (base + V <= cend) {
+    // a bound falls inside the chunk: lanes advance from the chunk's first segment
+    int k = k0;
+    bool flat[V];
+    bool all_flat = base + V <= cend;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const int jj = base + e;
+      flat[e] = false;
+      v[e] = 0.0;
+      if (jj < cend) {
+        while (k < nb - 1 && s_start[k + 1] <= jj) ++k;
+        flat[e] = !s_active[k];
+        v[e] = s_val[k];
+      }
+      all_flat = all_flat && flat[e];
+    }
+    if (all_flat) {
       if (kAccumulate) {
         double old[V];
         load_vec(dst + base, old);
@@ -359,9 +388,42 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
       }
       store_vec(dst + base, v);
     } else {
-      for (int e = 0; e < V && base + e < cend; ++e)
-        dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        if (flat[e]) {
+          if (kAccumulate) dst[base + e] = (OutT)add((double)dst[base + e], v[e]);
+          else store_one(dst + base + e, v[e]);
+        }
     }
+  }
+
+  // ---- phase 2: the tile's ACTIVE samples, dealt evenly to all threads ------------------
+  const int n_active = s_act[nb];
+  if (s_staged) mbar_wait(&s_bar, 0);  // also guarantees no copy is in flight when the CTA retires
+  if (n_active == 0) return;
+  if (s_staged) {
+    const WfmSegPtr a = s_ptr[0];
+    const int nf = s_ptr[nb].fac - a.fac, nt = s_ptr[nb].term - a.term;
+    const WfmFactor* sf = reinterpret_cast<const WfmFactor*>(s_ir);
+    const WfmTerm* st = reinterpret_cast<const WfmTerm*>(s_ir + (size_t)nf * sizeof(WfmFactor));
+    const WfmRef* sr = reinterpret_cast<const WfmRef*>(s_ir + (size_t)nf * sizeof(WfmFactor) + (size_t)nt * sizeof(WfmTerm));
+    const int r0 = nt > 0 ? st[0].ref_begin : 0;
+    ir.facs = sf - a.fac;
+    ir.terms = st - a.term;
+    ir.refs = sr - r0;
+  }
+  for (int i = threadIdx.x; i < n_active; i += kThreads) {
+    int lo = 0, hi = nb - 1;  // last k with s_act[k] <= i: the active segment holding sample i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_act[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const int jj = s_start[lo] + (i - s_act[lo]);
+    const double x = abscissa(w, P.x, j0 + jj);
+    double re, im;
+    eval_segment<false>(ir, w, s_ptr[lo], s_ptr[lo + 1], x, re, im);
+    if (kAccumulate) dst[jj] = (OutT)add((double)dst[jj], re);
+    else store_one(dst + jj, re);
   }
 }
 
@@ -376,18 +438,18 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   double2* __restrict__ dst = out + w.out_off + j0;
+  const IrView ir{P.facs, P.terms, P.refs, P.args};
   int seg = td.seg_lo;
   for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
-    double x1[1] = {abscissa(w, P.x, j0 + jj)};
+    const double x = abscissa(w, P.x, j0 + jj);
     int lo = seg, hi = td.seg_hi;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (__ldg(gb + mid) <= x1[0]) lo = mid + 1; else hi = mid;
+      if (__ldg(gb + mid) <= x) lo = mid + 1; else hi = mid;
     }
     seg = lo;
-    Acc<1> a;
-    eval_segment<1, true>(P, w, gp[seg], gp[seg + 1], x1, a);
-    double re = a.re[0], im = a.im[0];
+    double re, im;
+    eval_segment<true>(ir, w, gp[seg], gp[seg + 1], x, re, im);
     if (kAccumulate) {
       double2 o = dst[jj];
       re = add(o.x, re);
