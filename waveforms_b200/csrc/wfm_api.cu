@@ -199,14 +199,26 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   up(d->args, d->n_args, &p->dev.args);
   up(d->x, d->n_x, &p->dev.x);
 
-  // tile list: kTileSamples consecutive samples of one channel per CTA
+  // tile size from the segment density of the batch
+  {
+    int64_t samples = 0;
+    for (int64_t w = 0; w < d->n_waves; ++w) samples += d->waves[w].n;
+    const double segs_per_4k = samples > 0 ? (double)d->n_segs * 4096.0 / (double)samples : 0.0;
+    int ts = wfm::kMaxTileSamples;
+    if (segs_per_4k > 24.0) ts = 8192;
+    if (segs_per_4k > 64.0) ts = 4096;
+    if (segs_per_4k > 160.0) ts = wfm::kMinTileSamples;
+    p->dev.tile_samples = ts;
+  }
+  const int64_t tile_samples = p->dev.tile_samples;
+  // tile list: tile_samples consecutive samples of one channel per CTA
   std::vector<wfm::TileDesc> tiles;
   p->tile_prefix.resize(d->n_waves + 1);
   int64_t total = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
     p->tile_prefix[w] = (int64_t)tiles.size();
     const WfmWave& wv = d->waves[w];
-    for (int64_t j = 0; j < wv.n; j += wfm::kTileSamples) tiles.push_back({j, (int32_t)w, 0, 0, 0});
+    for (int64_t j = 0; j < wv.n; j += tile_samples) tiles.push_back({j, (int32_t)w, 0, 0, 0, 0, 0, 0, 0, 0, 0});
     total = std::max(total, wv.out_off + wv.n);
     if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
   }

@@ -6,8 +6,9 @@
 // (/root/reference/waveforms/waveform.py:173-207, :529-563, :679-693;
 //  /root/reference/waveforms/_waveform.pyx:130-169).
 //
-// Work decomposition: the output of the batch is cut into tiles of kTileSamples
-// consecutive samples of ONE channel; one CTA (256 threads) per tile.
+// Work decomposition: the output of the batch is cut into tiles of tile_samples
+// (2048..16384, chosen per program from its segment density) consecutive samples
+// of ONE channel; one CTA (256 threads) per tile.
 //
 //  0. (once per program, prepare_tiles_kernel) every tile learns the segments of
 //     its first and last abscissa: one thread per tile, binary search over the
@@ -43,9 +44,9 @@
 namespace wfm {
 
 constexpr int kThreads = 256;
-constexpr int kStageSegs = 512;   // segment rows staged per tile
+constexpr int kStageSegs = 1024;  // segment rows staged per tile
 constexpr int kMaxSlots = 12;     // distinct factor values cached per segment evaluation
-constexpr int kMaxChunks = kTileSamples / 64;
+constexpr int kMaxChunks = kMaxTileSamples / 64;
 constexpr int kIrBytes = 24576;   // shared-memory budget for the tile's factor/term/ref slice
 
 template <typename T> struct OutVec;
@@ -139,10 +140,22 @@ __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles,
   if (t >= n_tiles) return;
   TileDesc td = tiles[t];
   const WfmWave w = P.waves[td.wave];
-  const int64_t last = min(td.j0 + (int64_t)kTileSamples, w.n) - 1;
+  const int64_t last = min(td.j0 + (int64_t)P.tile_samples, w.n) - 1;
   const double* b = P.seg_bound + w.seg_begin;
   td.seg_lo = owning_segment(b, w.n_seg, abscissa(w, P.x, td.j0));
   td.seg_hi = max(td.seg_lo, owning_segment(b, w.n_seg, abscissa(w, P.x, last)));
+  const WfmSegPtr a = P.seg_ptr[w.seg_begin + td.seg_lo], e = P.seg_ptr[w.seg_begin + td.seg_hi + 1];
+  td.fac0 = a.fac;
+  td.n_fac = e.fac - a.fac;
+  td.term0 = a.term;
+  td.n_term = e.term - a.term;
+  td.ref0 = 0;
+  td.n_ref = 0;
+  if (td.n_term > 0) {
+    td.ref0 = P.terms[a.term].ref_begin;
+    const WfmTerm lt = P.terms[e.term - 1];
+    td.n_ref = lt.ref_begin + lt.n_ref - td.ref0;
+  }
   tiles[t] = td;
 }
 
@@ -227,21 +240,20 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
                                                           OutT* __restrict__ out) {
   constexpr int V = OutVec<OutT>::N;
   constexpr int kChunk = 32 * V;                      // samples per warp-chunk
-  constexpr int kChunks = kTileSamples / kChunk;      // chunks per tile
   __shared__ __align__(16) unsigned char s_ir[kIrBytes];
   __shared__ WfmSegPtr s_ptr[kStageSegs + 1];
   __shared__ double s_val[kStageSegs];                // value of a FLAT segment
-  __shared__ int s_start[kStageSegs + 1];             // first tile-sample of staged segment k
-  __shared__ int s_act[kStageSegs + 1];               // active samples before staged segment k
+  __shared__ uint16_t s_start[kStageSegs + 1];        // first tile-sample of staged segment k (<= 16384)
+  __shared__ uint16_t s_act[kStageSegs + 1];          // active samples before staged segment k
   __shared__ int s_chunk_seg[kMaxChunks];
   __shared__ unsigned char s_active[kStageSegs];
   __shared__ uint64_t s_bar;
-  __shared__ int s_staged;
 
   const TileDesc td = tiles[blockIdx.x];
   const WfmWave w = P.waves[td.wave];
   const int64_t j0 = td.j0;
-  const int cnt = (int)min((int64_t)kTileSamples, w.n - j0);
+  const int cnt = (int)min((int64_t)P.tile_samples, w.n - j0);
+  const int n_chunks = (cnt + kChunk - 1) / kChunk;
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   IrView ir{P.facs, P.terms, P.refs, P.args};
 
   if (nb > kStageSegs) {
-    // pathological density (> 512 segments in one tile): per-sample search in global memory
+    // pathological density (> 1024 segments in one tile): per-sample search in global memory
     for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
       const double x = abscissa(w, P.x, j0 + jj);
       int lo = seg_lo, hi = td.seg_hi;
@@ -267,28 +279,17 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   }
 
   // ---- prologue ------------------------------------------------------------------------
-  if (threadIdx.x == 0) {
+  const uint32_t bf = (uint32_t)td.n_fac * sizeof(WfmFactor), bt = (uint32_t)td.n_term * sizeof(WfmTerm),
+                 br = (uint32_t)td.n_ref * sizeof(WfmRef);
+  const bool staged = td.n_fac > 0 && bf + bt + br <= (uint32_t)kIrBytes;
+  if (threadIdx.x == 0 && staged) {
+    // the tile's slice of the factor / term / ref tables: one TMA bulk copy each
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // slice of the factor / term / ref tables this tile can touch
-    const WfmSegPtr a = gp[seg_lo], b = gp[seg_lo + nb];
-    const int nf = b.fac - a.fac, nt = b.term - a.term;
-    int r0 = 0, nr = 0;
-    if (nt > 0) {
-      r0 = P.terms[a.term].ref_begin;
-      const WfmTerm last = P.terms[b.term - 1];
-      nr = last.ref_begin + last.n_ref - r0;
-    }
-    const uint32_t bf = (uint32_t)nf * sizeof(WfmFactor), bt = (uint32_t)nt * sizeof(WfmTerm),
-                   br = (uint32_t)nr * sizeof(WfmRef);
-    const bool stage = (nf > 0) && (bf + bt + br <= (uint32_t)kIrBytes);
-    s_staged = stage ? 1 : 0;
-    if (stage) {
-      mbar_expect_tx(&s_bar, bf + bt + br);
-      bulk_g2s(s_ir, P.facs + a.fac, bf, &s_bar);
-      bulk_g2s(s_ir + bf, P.terms + a.term, bt, &s_bar);
-      if (br) bulk_g2s(s_ir + bf + bt, P.refs + r0, br, &s_bar);
-    }
+    mbar_expect_tx(&s_bar, bf + bt + br);
+    bulk_g2s(s_ir, P.facs + td.fac0, bf, &s_bar);
+    bulk_g2s(s_ir + bf, P.terms + td.term0, bt, &s_bar);
+    if (br) bulk_g2s(s_ir + bf + bt, P.refs + td.ref0, br, &s_bar);
   }
   for (int k = threadIdx.x; k <= nb; k += kThreads) {
     const WfmSegPtr p0 = gp[seg_lo + k];
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
     if (k == 0) pos = 0;
     else if (k == nb) pos = cnt;
     else pos = first_sample_at_or_after(w, P.x, j0, cnt, gb[seg_lo + k - 1]);
-    s_start[k] = pos;
+    s_start[k] = (uint16_t)pos;
     if (k < nb) {
       const WfmSegPtr p1 = gp[seg_lo + k + 1];
       const bool active = p1.fac > p0.fac;
@@ -313,43 +314,104 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
     int carry = 0;
     for (int b0 = 0; b0 < nb; b0 += 32) {
       const int k = b0 + lane;
-      int c = (k < nb && s_active[k]) ? (s_start[k + 1] - s_start[k]) : 0;
+      int c = (k < nb && s_active[k]) ? ((int)s_start[k + 1] - (int)s_start[k]) : 0;
       int incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
       }
-      if (k < nb) s_act[k] = carry + incl - c;
+      if (k < nb) s_act[k] = (uint16_t)(carry + incl - c);
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) s_act[nb] = carry;
-  } else if (threadIdx.x - 32 < kChunks) {
+    if (lane == 0) s_act[nb] = (uint16_t)carry;
+  } else {
     // staged segment that owns the first sample of chunk c: last k with s_start[k] <= c*kChunk
-    const int c = threadIdx.x - 32;
-    const int jj = c * kChunk;
-    int lo = 0, hi = nb - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_start[mid] <= jj) lo = mid; else hi = mid - 1;
+    for (int c = threadIdx.x - 32; c < n_chunks; c += kThreads - 32) {
+      const int jj = c * kChunk;
+      int lo = 0, hi = nb - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_start[mid] <= jj) lo = mid; else hi = mid - 1;
+      }
+      s_chunk_seg[c] = lo;
     }
-    s_chunk_seg[c] = lo;
   }
   __syncthreads();
 
   // ---- phase 1: every sample of a FLAT segment (store-bound, no abscissae) ------------
-  for (int c = warp; c * kChunk < cnt; c += kThreads / 32) {
-    const int cbeg = c * kChunk;
-    const int cend = min(cbeg + kChunk, cnt);
-    const int base = cbeg + lane * V;
-    const int k0 = s_chunk_seg[c];
-    double v[V];
-    if (s_start[k0 + 1] >= cend) {  // whole chunk inside staged segment k0
-      if (s_active[k0]) continue;
-      const double val = s_val[k0];
+  constexpr int kSuper = 4;  // chunks handled per warp iteration
+  for (int sc = warp * kSuper; sc < n_chunks; sc += (kThreads / 32) * kSuper) {
+    const int sbeg = sc * kChunk;
+    const int send = min(sbeg + kSuper * kChunk, cnt);
+    const int ks = s_chunk_seg[sc];
+    if (s_start[ks + 1] >= send) {
+      // the whole super-chunk lies inside staged segment ks
+      if (s_active[ks]) continue;
+      const double val = s_val[ks];
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] = val;
-      if (base + V <= cend) {
+      for (int q = 0; q < kSuper; ++q) {
+        const int base = sbeg + q * kChunk + lane * V;
+        double v[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = val;
+        if (base + V <= send) {
+          if (kAccumulate) {
+            double old[V];
+            load_vec(dst + base, old);
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = add(old[e], v[e]);
+          }
+          store_vec(dst + base, v);
+        } else {
+          for (int e = 0; e < V && base + e < send; ++e)
+            dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
+        }
+      }
+      continue;
+    }
+    for (int c = sc; c < sc + kSuper && c < n_chunks; ++c) {
+      const int cbeg = c * kChunk;
+      const int cend = min(cbeg + kChunk, cnt);
+      const int base = cbeg + lane * V;
+      const int k0 = s_chunk_seg[c];
+      double v[V];
+      if (s_start[k0 + 1] >= cend) {  // whole chunk inside staged segment k0
+        if (s_active[k0]) continue;
+        const double val = s_val[k0];
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = val;
+        if (base + V <= cend) {
+          if (kAccumulate) {
+            double old[V];
+            load_vec(dst + base, old);
+#pragma unroll
+            for (int e = 0; e < V; ++e) v[e] = add(old[e], v[e]);
+          }
+          store_vec(dst + base, v);
+        } else {
+          for (int e = 0; e < V && base + e < cend; ++e)
+            dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
+        }
+        continue;
+      }
+      // a bound falls inside the chunk: lanes advance from the chunk's first segment
+      int k = k0;
+      bool flat[V];
+      bool all_flat = base + V <= cend;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int jj = base + e;
+        flat[e] = false;
+        v[e] = 0.0;
+        if (jj < cend) {
+          while (k < nb - 1 && s_start[k + 1] <= jj) ++k;
+          flat[e] = !s_active[k];
+          v[e] = s_val[k];
+        }
+        all_flat = all_flat && flat[e];
+      }
+      if (all_flat) {
         if (kAccumulate) {
           double old[V];
           load_vec(dst + base, old);
@@ -358,59 +420,24 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
         }
         store_vec(dst + base, v);
       } else {
-        for (int e = 0; e < V && base + e < cend; ++e)
-          dst[base + e] = kAccumulate ? (OutT)add((double)dst[base + e], v[e]) : (OutT)v[e];
-      }
-      continue;
-    }
-    // a bound falls inside the chunk: lanes advance from the chunk's first segment
-    int k = k0;
-    bool flat[V];
-    bool all_flat = base + V <= cend;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const int jj = base + e;
-      flat[e] = false;
-      v[e] = 0.0;
-      if (jj < cend) {
-        while (k < nb - 1 && s_start[k + 1] <= jj) ++k;
-        flat[e] = !s_active[k];
-        v[e] = s_val[k];
+        for (int e = 0; e < V; ++e)
+          if (flat[e]) {
+            if (kAccumulate) dst[base + e] = (OutT)add((double)dst[base + e], v[e]);
+            else store_one(dst + base + e, v[e]);
+          }
       }
-      all_flat = all_flat && flat[e];
-    }
-    if (all_flat) {
-      if (kAccumulate) {
-        double old[V];
-        load_vec(dst + base, old);
-#pragma unroll
-        for (int e = 0; e < V; ++e) v[e] = add(old[e], v[e]);
-      }
-      store_vec(dst + base, v);
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e)
-        if (flat[e]) {
-          if (kAccumulate) dst[base + e] = (OutT)add((double)dst[base + e], v[e]);
-          else store_one(dst + base + e, v[e]);
-        }
     }
   }
 
   // ---- phase 2: the tile's ACTIVE samples, dealt evenly to all threads ------------------
   const int n_active = s_act[nb];
-  if (s_staged) mbar_wait(&s_bar, 0);  // also guarantees no copy is in flight when the CTA retires
+  if (staged) mbar_wait(&s_bar, 0);  // also guarantees no copy is in flight when the CTA retires
   if (n_active == 0) return;
-  if (s_staged) {
-    const WfmSegPtr a = s_ptr[0];
-    const int nf = s_ptr[nb].fac - a.fac, nt = s_ptr[nb].term - a.term;
-    const WfmFactor* sf = reinterpret_cast<const WfmFactor*>(s_ir);
-    const WfmTerm* st = reinterpret_cast<const WfmTerm*>(s_ir + (size_t)nf * sizeof(WfmFactor));
-    const WfmRef* sr = reinterpret_cast<const WfmRef*>(s_ir + (size_t)nf * sizeof(WfmFactor) + (size_t)nt * sizeof(WfmTerm));
-    const int r0 = nt > 0 ? st[0].ref_begin : 0;
-    ir.facs = sf - a.fac;
-    ir.terms = st - a.term;
-    ir.refs = sr - r0;
+  if (staged) {
+    ir.facs = reinterpret_cast<const WfmFactor*>(s_ir) - td.fac0;
+    ir.terms = reinterpret_cast<const WfmTerm*>(s_ir + bf) - td.term0;
+    ir.refs = reinterpret_cast<const WfmRef*>(s_ir + bf + bt) - td.ref0;
   }
   for (int i = threadIdx.x; i < n_active; i += kThreads) {
     int lo = 0, hi = nb - 1;  // last k with s_act[k] <= i: the active segment holding sample i
@@ -418,7 +445,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
       const int mid = (lo + hi + 1) >> 1;
       if (s_act[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    const int jj = s_start[lo] + (i - s_act[lo]);
+    const int jj = (int)s_start[lo] + (i - (int)s_act[lo]);
     const double x = abscissa(w, P.x, j0 + jj);
     double re, im;
     eval_segment<false>(ir, w, s_ptr[lo], s_ptr[lo + 1], x, re, im);
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
   const TileDesc td = tiles[blockIdx.x];
   const WfmWave w = P.waves[td.wave];
   const int64_t j0 = td.j0;
-  const int cnt = (int)min((int64_t)kTileSamples, w.n - j0);
+  const int cnt = (int)min((int64_t)P.tile_samples, w.n - j0);
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   double2* __restrict__ dst = out + w.out_off + j0;
