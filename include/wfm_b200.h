@@ -59,10 +59,15 @@ enum {
   WFM_HYPERBOLICCHIRP = 10, WFM_COSH = 11, WFM_SINH = 12, WFM_DRAG = 13,
   WFM_MOLLIFIER = 14, WFM_D_GAUSSIAN = 15, WFM_DRAG_SIN = 16,
   WFM_DRAG_SINX = 17,
-  /* lowering-only ops (never appear in Waveform objects) */
-  WFM_COS_ROT = 32  /* cos(w(x-shift)) derived from an earlier COS factor of
-                       the same segment with equal w by an exact-difference
-                       rotation; see DESIGN.md §K1 */
+  /* lowering-only ops (never appear in Waveform objects); DESIGN.md, K1:
+   * several COS factors of one segment that share w are evaluated as ONE sincos
+   * plus rotations by the exactly measured argument difference */
+  WFM_COS_SINCOS = 32, /* slot k <- cos(w(x-shift)), slot k+1 <- sin(...); the
+                          next factor row must be WFM_NOP (it owns slot k+1) */
+  WFM_NOP = 33,        /* placeholder row for the sine slot */
+  WFM_COS_ROT = 34     /* cos(w(x-shift)) from the WFM_COS_SINCOS row of equal w;
+                          pool: [base_slot, base_shift, D, cos D, sin D] with
+                          D ~ w*(base_shift - shift) */
 };
 
 /* WfmWave.flags */

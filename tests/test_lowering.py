@@ -16,10 +16,19 @@ def test_readme_channel_structure():
     b = lower_one(I, engine.arange_grid(-1e-6, 9e-6, 1e-9))
     assert b.waves['n'][0] == 10000 and b.waves['n_seg'][0] == 3
     assert b.seg_bound.tolist() == [-1e-08, 1e-08, np.inf]
-    # active segment: 5 terms whose 8 factor references share 5 DISTINCT cos factors (memoised per factor tuple)
+    # active segment: 5 terms whose 8 factor references share 5 DISTINCT cos factors (the
+    # reference memoises per factor tuple).  Two frequencies -> 2 COS_SINCOS rows (+ their
+    # NOP sine rows) and 3 COS_ROT rows.
     assert b.seg_ptr['term'].tolist() == [0, 0, 5, 5]
-    assert b.seg_ptr["fac"].tolist() == [0, 0, 5, 5] and len(b.refs) == 8
-    assert (b.facs['func'] == 4).all()
+    assert b.seg_ptr["fac"].tolist() == [0, 0, 7, 7] and len(b.refs) == 8
+    assert b.facs['func'].tolist() == [L.COS_SINCOS, L.NOP, L.COS_SINCOS, L.NOP, L.COS_ROT, L.COS_ROT, L.COS_ROT]
+    for row in b.facs[4:]:
+        base = int(b.args[row['arg_off']])
+        assert b.facs[base]['func'] == L.COS_SINCOS and b.facs[base]['a0'] == row['a0']
+        D = b.args[row['arg_off'] + 2]
+        assert D == row['a0'] * (b.args[row['arg_off'] + 1] - row['shift'])
+        assert b.args[row['arg_off'] + 3] == np.cos(D) and b.args[row['arg_off'] + 4] == np.sin(D)
+    assert not set(b.refs['slot'].tolist()) & {1, 3}          # nothing refers to a sine slot
     assert b.terms['flags'].tolist() == [0, 0, 0, 0, L.TERM_GROUP_END]
     assert not b.any_complex
 

@@ -57,7 +57,7 @@ cudaError_t upload(const T* host, int64_t n, const T** dev) {
   return cudaSuccess;
 }
 
-bool known_func(int f) { return (f >= WFM_LINEAR && f <= WFM_DRAG_SINX) || f == WFM_COS_ROT; }
+bool known_func(int f) { return (f >= WFM_LINEAR && f <= WFM_DRAG_SINX) || (f >= WFM_COS_SINCOS && f <= WFM_COS_ROT); }
 
 }  // namespace
 
@@ -81,6 +81,7 @@ struct WfmProgram {
     cudaFree((void*)dev.seg_ptr);
     cudaFree((void*)dev.facs);
     cudaFree((void*)dev.terms);
+    cudaFree((void*)dev.cterms);
     cudaFree((void*)dev.refs);
     cudaFree((void*)dev.args);
     cudaFree((void*)dev.x);
@@ -127,6 +128,23 @@ static int validate(const WfmProgramDesc* d) {
   for (int64_t s = 0; s < d->n_segs; ++s) {
     const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
     const int nf = b.fac - a.fac;
+    for (int k = 0; k < nf; ++k) {
+      const WfmFactor& f = d->facs[a.fac + k];
+      if (f.func == WFM_COS_SINCOS) {
+        if (k + 1 >= nf || k + 1 >= wfm::kMaxSlots || d->facs[a.fac + k + 1].func != WFM_NOP)
+          return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it inside the value cache", (long long)s, k);
+      } else if (f.func == WFM_NOP) {
+        if (k == 0 || d->facs[a.fac + k - 1].func != WFM_COS_SINCOS)
+          return fail(WFM_EINVAL, "segment %lld: stray NOP row %d", (long long)s, k);
+      } else if (f.func == WFM_COS_ROT) {
+        if (f.arg_off + 5 > d->n_args) return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: pool out of range", (long long)s, k);
+        const double bs = d->args[f.arg_off];
+        const int base = (int)bs;
+        if (!(bs >= 0) || base >= k || k >= wfm::kMaxSlots || d->facs[a.fac + base].func != WFM_COS_SINCOS ||
+            d->facs[a.fac + base].a0 != f.a0)
+          return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: bad base row", (long long)s, k);
+      }
+    }
     for (int t = a.term; t < b.term; ++t) {
       const WfmTerm& tm = d->terms[t];
       if (tm.n_ref < 0 || tm.ref_begin < 0 || (int64_t)tm.ref_begin + tm.n_ref > d->n_refs)
@@ -134,6 +152,7 @@ static int validate(const WfmProgramDesc* d) {
       for (int r = tm.ref_begin; r < tm.ref_begin + tm.n_ref; ++r) {
         const WfmRef& rf = d->refs[r];
         if (rf.slot < 0 || rf.slot >= nf) return fail(WFM_EINVAL, "ref %d: slot %d outside segment (%d factors)", r, rf.slot, nf);
+        if (d->facs[a.fac + rf.slot].func == WFM_NOP) return fail(WFM_EINVAL, "ref %d: refers to a NOP row", r);
         if (rf.kind < WFM_POW_ONE || rf.kind > WFM_POW_GEN) return fail(WFM_EINVAL, "ref %d: bad exponent kind", r);
       }
     }
@@ -195,6 +214,25 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   up(d->seg_ptr, d->n_segs ? d->n_segs + 1 : 0, &p->dev.seg_ptr);
   up(d->facs, d->n_facs, &p->dev.facs);
   up(d->terms, d->n_terms, &p->dev.terms);
+  {
+    std::vector<wfm::CTerm> ct((size_t)d->n_terms);
+    for (int64_t t = 0; t < d->n_terms; ++t) {
+      const WfmTerm& tm = d->terms[t];
+      wfm::CTerm c{};
+      c.amp = tm.amp_re;
+      c.flags = (tm.flags & WFM_TERM_GROUP_END) ? wfm::kCTermGroupEnd : 0;
+      bool ext = tm.n_ref > 6;
+      for (int r = 0; r < tm.n_ref && !ext; ++r) {
+        const WfmRef& rf = d->refs[tm.ref_begin + r];
+        if (rf.kind != WFM_POW_ONE || rf.slot >= wfm::kMaxSlots) ext = true;
+        else c.slot[r] = (uint8_t)rf.slot;
+      }
+      if (ext) c.flags |= wfm::kCTermExt;
+      c.n_ref = ext ? 0 : (uint8_t)tm.n_ref;
+      ct[(size_t)t] = c;
+    }
+    up(ct.data(), d->n_terms, &p->dev.cterms);
+  }
   up(d->refs, d->n_refs, &p->dev.refs);
   up(d->args, d->n_args, &p->dev.args);
   up(d->x, d->n_x, &p->dev.x);

@@ -12,6 +12,20 @@ namespace wfm {
 constexpr int kMinTileSamples = 2048;
 constexpr int kMaxTileSamples = 16384;
 
+// Compact term built at upload from WfmTerm + WfmRef: amplitude and up to six
+// factor slots with exponent 1 in ONE 16-byte record (one load per term in the
+// interpreter).  Terms that do not fit (more refs, an exponent != 1, a slot
+// beyond the value cache) carry kCTermExt and are read from the ABI tables.
+struct CTerm {
+  double amp;
+  uint8_t n_ref;
+  uint8_t flags;
+  uint8_t slot[6];
+};
+static_assert(sizeof(CTerm) == 16, "CTerm layout");
+constexpr uint8_t kCTermGroupEnd = 1, kCTermExt = 2;
+constexpr int kMaxSlots = 12;  // distinct factor values cached per segment evaluation
+
 // device-resident copy of a lowered batch (all DEVICE pointers)
 struct DevProgram {
   const WfmWave* waves;
@@ -19,6 +33,7 @@ struct DevProgram {
   const WfmSegPtr* seg_ptr;
   const WfmFactor* facs;
   const WfmTerm* terms;
+  const CTerm* cterms;  // parallel to terms
   const WfmRef* refs;
   const double* args;
   const double* x;

@@ -45,7 +45,6 @@ namespace wfm {
 
 constexpr int kThreads = 256;
 constexpr int kStageSegs = 1024;  // segment rows staged per tile
-constexpr int kMaxSlots = 12;     // distinct factor values cached per segment evaluation
 constexpr int kMaxChunks = kMaxTileSamples / 64;
 constexpr int kIrBytes = 24576;   // shared-memory budget for the tile's factor/term/ref slice
 
@@ -184,51 +183,122 @@ __device__ int first_sample_at_or_after(const WfmWave& w, const double* __restri
 // slice staged in shared memory (pointers pre-biased so global indices work)
 struct IrView {
   const WfmFactor* facs;
-  const WfmTerm* terms;
+  const CTerm* cterms;  // compact terms (real-valued kernels)
+  const WfmTerm* terms; // ABI terms / refs: global only (extended terms, complex kernel)
   const WfmRef* refs;
   const double* args;
 };
 
-// Evaluate one segment's program at one abscissa.
-template <bool kComplex>
-__device__ __forceinline__ void eval_segment(const IrView& ir, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1, double x,
-                                             double& out_re, double& out_im) {
+// distinct factor values of one segment -> vals[0 .. min(nf, kMaxSlots))
+__device__ __forceinline__ void eval_factors(const WfmFactor* facs, int nf, double x, const double* __restrict__ args,
+                                             double (&vals)[kMaxSlots]) {
+#pragma unroll 1
+  for (int k = 0; k < nf && k < kMaxSlots; ++k) {
+    const WfmFactor f = facs[k];
+    if (f.func == WFM_COS_SINCOS) {
+      // one range reduction serves every COS factor of this frequency
+      double s, c;
+      sincos(mul(f.a0, sub(x, f.shift)), &s, &c);
+      vals[k] = c;
+      vals[k + 1] = s;  // row k+1 is the NOP placeholder (validated at upload)
+      ++k;
+    } else if (f.func == WFM_COS_ROT) {
+      // cos(a_t) with a_t = w*(x - shift) rounded exactly as the reference rounds
+      // it, obtained from the base row's (cos, sin)(a_b):  a_t = a_b + D + eps with
+      // D a host constant (cos D, sin D tabulated) and eps = (a_t - a_b) - D the
+      // MEASURED residual (|eps| ~ ulp(a)), expanded to second order.
+      const double* __restrict__ p = args + f.arg_off;
+      const int base = (int)p[0];
+      const double a_t = mul(f.a0, sub(x, f.shift));
+      const double a_b = mul(f.a0, sub(x, p[1]));
+      const double eps = sub(sub(a_t, a_b), p[2]);
+      const double cb = vals[base], sb = vals[base + 1];
+      const double C = fma(cb, p[3], -(sb * p[4]));
+      const double S = fma(sb, p[3], cb * p[4]);
+      vals[k] = fma(-0.5 * eps * eps, C, fma(-eps, S, C));
+    } else {
+      vals[k] = eval_factor(f, x, args);
+    }
+  }
+}
+
+// product of the referenced factor powers of an ABI term (general path)
+__device__ __forceinline__ double term_product(const IrView& ir, const WfmFactor* facs, const WfmTerm& tm, double x,
+                                               const double (&vals)[kMaxSlots]) {
+  double prod = 1.0;
+  bool first = true;
+#pragma unroll 1
+  for (int r = 0; r < tm.n_ref; ++r) {
+    const WfmRef ref = ir.refs[tm.ref_begin + r];
+    double v = (ref.slot < kMaxSlots) ? vals[ref.slot] : eval_factor(facs[ref.slot], x, ir.args);
+    if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
+    else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
+    prod = first ? v : mul(prod, v);  // 1 * v == v
+    first = false;
+  }
+  return prod;
+}
+
+// Evaluate one segment's program at one abscissa (real-valued channels; compact terms).
+__device__ __forceinline__ double eval_segment_real(const IrView& ir, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1,
+                                                    double x) {
+  double total = w.offset;
+  const int nt = p1.term - p0.term;
+  if (nt == 0) return total;  // zero segment: untouched by clip (calc_parts skips it)
+  double vals[kMaxSlots];
+  const WfmFactor* facs = ir.facs + p0.fac;
+  eval_factors(facs, p1.fac - p0.fac, x, ir.args, vals);
+  double g = 0.0;
+  bool g_first = true;
+#pragma unroll 1
+  for (int it = 0; it < nt; ++it) {
+    const CTerm ct = ir.cterms[p0.term + it];
+    double prod;
+    if (ct.flags & kCTermExt) {
+      prod = term_product(ir, facs, ir.terms[p0.term + it], x, vals);
+    } else {
+      prod = 1.0;
+#pragma unroll 1
+      for (int r = 0; r < ct.n_ref; ++r) {
+        const double v = vals[ct.slot[r]];
+        prod = r == 0 ? v : mul(prod, v);
+      }
+    }
+    const double t = mul(ct.amp, prod);
+    g = g_first ? t : add(g, t);  // 0 + a == a
+    g_first = false;
+    if (ct.flags & kCTermGroupEnd) {
+      total = add(total, g);
+      g_first = true;
+    }
+  }
+  if (w.flags & WFM_WAVE_CLIP) total = fmin(fmax(total, w.clip_lo), w.clip_hi);
+  return total;
+}
+
+// complex amplitudes (WFM_C128 output): ABI terms from global memory
+__device__ __forceinline__ void eval_segment_cplx(const IrView& ir, const WfmWave& w, WfmSegPtr p0, WfmSegPtr p1,
+                                                  double x, double& out_re, double& out_im) {
   out_re = w.offset;
   out_im = 0.0;
   const int nt = p1.term - p0.term;
-  if (nt == 0) return;  // zero segment: untouched by clip (calc_parts skips it)
-  const int nf = p1.fac - p0.fac;
+  if (nt == 0) return;
   double vals[kMaxSlots];
   const WfmFactor* facs = ir.facs + p0.fac;
-#pragma unroll 1
-  for (int k = 0; k < nf && k < kMaxSlots; ++k) vals[k] = eval_factor(facs[k], x, ir.args);
-
+  eval_factors(facs, p1.fac - p0.fac, x, ir.args, vals);
   double g_re = 0.0, g_im = 0.0;
   bool g_first = true;
 #pragma unroll 1
   for (int it = 0; it < nt; ++it) {
     const WfmTerm tm = ir.terms[p0.term + it];
-    double prod = 1.0;
-    bool p_first = true;
-#pragma unroll 1
-    for (int r = 0; r < tm.n_ref; ++r) {
-      const WfmRef ref = ir.refs[tm.ref_begin + r];
-      double v = (ref.slot < kMaxSlots) ? vals[ref.slot] : eval_factor(facs[ref.slot], x, ir.args);
-      if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
-      else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
-      prod = p_first ? v : mul(prod, v);  // 1 * v == v
-      p_first = false;
-    }
-    const double t_re = mul(tm.amp_re, prod);
-    g_re = g_first ? t_re : add(g_re, t_re);  // 0 + a == a
-    if (kComplex) {
-      const double t_im = mul(tm.amp_im, prod);
-      g_im = g_first ? t_im : add(g_im, t_im);
-    }
+    const double prod = term_product(ir, facs, tm, x, vals);
+    const double t_re = mul(tm.amp_re, prod), t_im = mul(tm.amp_im, prod);
+    g_re = g_first ? t_re : add(g_re, t_re);
+    g_im = g_first ? t_im : add(g_im, t_im);
     g_first = false;
     if (tm.flags & WFM_TERM_GROUP_END) {
       out_re = add(out_re, g_re);
-      if (kComplex) out_im = add(out_im, g_im);
+      out_im = add(out_im, g_im);
       g_first = true;
     }
   }
@@ -260,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   const int seg_lo = td.seg_lo;
   const int nb = td.seg_hi - seg_lo + 1;
   OutT* __restrict__ dst = out + w.out_off + j0;
-  IrView ir{P.facs, P.terms, P.refs, P.args};
+  IrView ir{P.facs, P.cterms, P.terms, P.refs, P.args};
 
   if (nb > kStageSegs) {
     // pathological density (> 1024 segments in one tile): per-sample search in global memory
@@ -271,25 +341,22 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
         const int mid = (lo + hi) >> 1;
         if (__ldg(gb + mid) <= x) lo = mid + 1; else hi = mid;
       }
-      double re, im;
-      eval_segment<false>(ir, w, gp[lo], gp[lo + 1], x, re, im);
+      const double re = eval_segment_real(ir, w, gp[lo], gp[lo + 1], x);
       dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
     }
     return;
   }
 
   // ---- prologue ------------------------------------------------------------------------
-  const uint32_t bf = (uint32_t)td.n_fac * sizeof(WfmFactor), bt = (uint32_t)td.n_term * sizeof(WfmTerm),
-                 br = (uint32_t)td.n_ref * sizeof(WfmRef);
-  const bool staged = td.n_fac > 0 && bf + bt + br <= (uint32_t)kIrBytes;
+  const uint32_t bf = (uint32_t)td.n_fac * sizeof(WfmFactor), bt = (uint32_t)td.n_term * sizeof(CTerm);
+  const bool staged = td.n_fac > 0 && bf + bt <= (uint32_t)kIrBytes;
   if (threadIdx.x == 0 && staged) {
-    // the tile's slice of the factor / term / ref tables: one TMA bulk copy each
+    // the tile's slice of the factor and compact-term tables: one TMA bulk copy each
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&s_bar, bf + bt + br);
+    mbar_expect_tx(&s_bar, bf + bt);
     bulk_g2s(s_ir, P.facs + td.fac0, bf, &s_bar);
-    bulk_g2s(s_ir + bf, P.terms + td.term0, bt, &s_bar);
-    if (br) bulk_g2s(s_ir + bf + bt, P.refs + td.ref0, br, &s_bar);
+    bulk_g2s(s_ir + bf, P.cterms + td.term0, bt, &s_bar);
   }
   for (int k = threadIdx.x; k <= nb; k += kThreads) {
     const WfmSegPtr p0 = gp[seg_lo + k];
@@ -303,8 +370,8 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
       const WfmSegPtr p1 = gp[seg_lo + k + 1];
       const bool active = p1.fac > p0.fac;
       s_active[k] = active ? 1 : 0;
-      double re = w.offset, im;
-      if (!active && p1.term > p0.term) eval_segment<false>(ir, w, p0, p1, 0.0, re, im);  // constant segment
+      double re = w.offset;
+      if (!active && p1.term > p0.term) re = eval_segment_real(ir, w, p0, p1, 0.0);  // constant segment
       s_val[k] = re;
     }
   }
@@ -436,8 +503,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
   if (n_active == 0) return;
   if (staged) {
     ir.facs = reinterpret_cast<const WfmFactor*>(s_ir) - td.fac0;
-    ir.terms = reinterpret_cast<const WfmTerm*>(s_ir + bf) - td.term0;
-    ir.refs = reinterpret_cast<const WfmRef*>(s_ir + bf + bt) - td.ref0;
+    ir.cterms = reinterpret_cast<const CTerm*>(s_ir + bf) - td.term0;
   }
   for (int i = threadIdx.x; i < n_active; i += kThreads) {
     int lo = 0, hi = nb - 1;  // last k with s_act[k] <= i: the active segment holding sample i
@@ -447,8 +513,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(DevProgram P, const Ti
     }
     const int jj = (int)s_start[lo] + (i - (int)s_act[lo]);
     const double x = abscissa(w, P.x, j0 + jj);
-    double re, im;
-    eval_segment<false>(ir, w, s_ptr[lo], s_ptr[lo + 1], x, re, im);
+    const double re = eval_segment_real(ir, w, s_ptr[lo], s_ptr[lo + 1], x);
     if (kAccumulate) dst[jj] = (OutT)add((double)dst[jj], re);
     else store_one(dst + jj, re);
   }
@@ -465,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
   const double* __restrict__ gb = P.seg_bound + w.seg_begin;
   const WfmSegPtr* __restrict__ gp = P.seg_ptr + w.seg_begin;
   double2* __restrict__ dst = out + w.out_off + j0;
-  const IrView ir{P.facs, P.terms, P.refs, P.args};
+  const IrView ir{P.facs, P.cterms, P.terms, P.refs, P.args};
   int seg = td.seg_lo;
   for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
     const double x = abscissa(w, P.x, j0 + jj);
@@ -476,7 +541,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
     }
     seg = lo;
     double re, im;
-    eval_segment<true>(ir, w, gp[seg], gp[seg + 1], x, re, im);
+    eval_segment_cplx(ir, w, gp[seg], gp[seg + 1], x, re, im);
     if (kAccumulate) {
       double2 o = dst[jj];
       re = add(o.x, re);

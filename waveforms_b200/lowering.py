@@ -25,6 +25,7 @@ call inside calc_parts/_calc, /root/reference/waveforms/_waveform.pyx:130-169):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -254,11 +255,75 @@ def _ref_kind(n):
     return POW_GEN
 
 
+COS_SINCOS, NOP, COS_ROT = 32, 33, 34
+MAX_SLOTS = 12  # csrc/wfm_sample.cu kMaxSlots: factor values cached per evaluation
+USE_ROTATION = os.environ.get('WFM_NO_ROT', '') == ''
+
+
+def _plan_slots(order):
+    """Assign factor-table rows (= value slots) to the distinct factors of one
+    segment.  COS factors sharing w become one COS_SINCOS row (+ a NOP row for
+    the sine) and COS_ROT rows.  Returns (rows, slot_of) where rows is a list of
+    ('plain', f) | ('sincos', f) | ('nop',) | ('rot', f, base_slot, base_f)."""
+    groups = {}
+    if USE_ROTATION:
+        for f in order:
+            if f[0] == A.COS:
+                groups.setdefault(f[1], []).append(f)
+    rows, slot_of, base_of = [], {}, {}
+    for f in order:
+        members = groups.get(f[1]) if f[0] == A.COS else None
+        if members and len(members) > 1:
+            if f is members[0] or f == members[0]:
+                if len(rows) + 2 <= MAX_SLOTS:
+                    slot_of[f] = len(rows)
+                    base_of[f[1]] = (len(rows), f)
+                    rows.append(('sincos', f))
+                    rows.append(('nop', ))
+                    continue
+            elif f[1] in base_of and len(rows) < MAX_SLOTS:
+                slot_of[f] = len(rows)
+                rows.append(('rot', f, *base_of[f[1]]))
+                continue
+        slot_of[f] = len(rows)
+        rows.append(('plain', f))
+    return rows, slot_of
+
+
+def _emit_rows(pools, rows):
+    for row in rows:
+        kind = row[0]
+        if kind == 'plain':
+            pools.fac.append(_pack_factor(pools, row[1]))
+        elif kind == 'sincos':
+            f = row[1]
+            pools.fac.append((COS_SINCOS, 0, float(f[-1]), float(f[1]), 0.0))
+        elif kind == 'nop':
+            pools.fac.append((NOP, 0, 0.0, 0.0, 0.0))
+        else:
+            _, f, base_slot, base_f = row
+            w, s_t, s_b = f[1], f[-1], base_f[-1]
+            delta = float(w * (s_b - s_t))
+            off = pools.arg_block(('rot', w, s_t, s_b, base_slot),
+                                  (float(base_slot), float(s_b), delta,
+                                   math.cos(delta), math.sin(delta)))
+            pools.fac.append((COS_ROT, off, float(s_t), float(w), 0.0))
+        pools.n_fac += 1
+
+
 def _lower_segment(pools, groups):
     """groups: list of expressions (one per stack member active here, in member
     order).  Appends the segment's factors / terms / refs to the pools.
     Returns True if any amplitude is complex."""
-    slots = {}
+    order, seen = [], set()
+    for expr in groups:
+        for factors, _ in expr[0]:
+            for f in factors:
+                if f not in seen:
+                    seen.add(f)
+                    order.append(f)
+    rows, slot_of = _plan_slots(order)
+    _emit_rows(pools, rows)
     cplx = False
     for expr in groups:
         terms, amps = expr
@@ -266,13 +331,7 @@ def _lower_segment(pools, groups):
         for k, ((factors, exponents), amp) in enumerate(zip(terms, amps)):
             ref_begin = pools.n_ref
             for f, n in zip(factors, exponents):
-                slot = slots.get(f)
-                if slot is None:
-                    slot = len(slots)
-                    slots[f] = slot
-                    pools.fac.append(_pack_factor(pools, f))
-                    pools.n_fac += 1
-                pools.ref.append((float(n), slot, _ref_kind(n)))
+                pools.ref.append((float(n), slot_of[f], _ref_kind(n)))
                 pools.n_ref += 1
             if isinstance(amp, complex) or isinstance(amp, np.complexfloating):
                 re, im = float(amp.real), float(amp.imag)
