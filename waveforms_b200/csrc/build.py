@@ -41,14 +41,17 @@ def stale():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """``defines``/``out``: experiment builds (e.g. -DWFM_K1_MIN_BLOCKS=2 into
+    another file name, selected at run time with WFM_LIB=<path>)."""
+    lib = LIB if out is None else Path(out)
+    if out is None and not force and not stale():
         return LIB
     objs = []
     for src in SOURCES:
-        obj = HERE / (Path(src).stem + '.o')
-        cmd = [nvcc_path(), *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []), '-c',
-               str(HERE / src), '-o', str(obj)]
+        obj = HERE / (Path(src).stem + ('' if out is None else '.' + lib.stem) + '.o')
+        cmd = [nvcc_path(), *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []),
+               *[f'-D{d}' for d in defines], '-c', str(HERE / src), '-o', str(obj)]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')
@@ -56,11 +59,14 @@ def build(force=False, verbose=False):
         subprocess.run(cmd, check=True)
         objs.append(str(obj))
     cmd = [nvcc_path(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
-           '-o', str(LIB), *objs]
+           '-o', str(lib), *objs]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv,
+                 defines=defs, out=outs[0] if outs else None)
     print(path)

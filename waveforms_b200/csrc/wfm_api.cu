@@ -82,9 +82,13 @@ struct WfmProgram {
     cudaFree((void*)dev.facs);
     cudaFree((void*)dev.terms);
     cudaFree((void*)dev.cterms);
+    cudaFree((void*)dev.dfacs);
     cudaFree((void*)dev.refs);
     cudaFree((void*)dev.args);
     cudaFree((void*)dev.x);
+    cudaFree((void*)dev.seg_start);
+    cudaFree((void*)dev.seg_val);
+    cudaFree((void*)dev.seg_wave);
     cudaFree(d_tiles);
     cudaFree(d_stage);
   }
@@ -167,6 +171,7 @@ static int validate(const WfmProgramDesc* d) {
   for (int64_t w = 0; w < d->n_waves; ++w) {
     const WfmWave& wv = d->waves[w];
     if (wv.n < 0 || wv.out_off < 0) return fail(WFM_EINVAL, "channel %lld: negative extent", (long long)w);
+    if (wv.n >= INT32_MAX) return fail(WFM_EINVAL, "channel %lld: more than 2^31-2 samples", (long long)w);
     if (wv.n_seg < 1 || wv.seg_begin < 0 || (int64_t)wv.seg_begin + wv.n_seg > d->n_segs)
       return fail(WFM_EINVAL, "channel %lld: segment range out of bounds", (long long)w);
     if (!(d->seg_bound[wv.seg_begin + wv.n_seg - 1] == INFINITY))
@@ -214,38 +219,50 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   up(d->seg_ptr, d->n_segs ? d->n_segs + 1 : 0, &p->dev.seg_ptr);
   up(d->facs, d->n_facs, &p->dev.facs);
   up(d->terms, d->n_terms, &p->dev.terms);
-  {
-    std::vector<wfm::CTerm> ct((size_t)d->n_terms);
-    for (int64_t t = 0; t < d->n_terms; ++t) {
-      const WfmTerm& tm = d->terms[t];
-      wfm::CTerm c{};
-      c.amp = tm.amp_re;
-      c.flags = (tm.flags & WFM_TERM_GROUP_END) ? wfm::kCTermGroupEnd : 0;
-      bool ext = tm.n_ref > 6;
-      for (int r = 0; r < tm.n_ref && !ext; ++r) {
-        const WfmRef& rf = d->refs[tm.ref_begin + r];
-        if (rf.kind != WFM_POW_ONE || rf.slot >= wfm::kMaxSlots) ext = true;
-        else c.slot[r] = (uint8_t)rf.slot;
-      }
-      if (ext) c.flags |= wfm::kCTermExt;
-      c.n_ref = ext ? 0 : (uint8_t)tm.n_ref;
-      ct[(size_t)t] = c;
-    }
-    up(ct.data(), d->n_terms, &p->dev.cterms);
-  }
   up(d->refs, d->n_refs, &p->dev.refs);
   up(d->args, d->n_args, &p->dev.args);
   up(d->x, d->n_x, &p->dev.x);
 
-  // tile size from the segment density of the batch
+  // owning channel of every segment row (pre-pass only) and the widest segment
+  int max_rows = 0;
+  {
+    std::vector<int32_t> seg_wave((size_t)d->n_segs, 0);
+    for (int64_t w = 0; w < d->n_waves; ++w) {
+      const WfmWave& wv = d->waves[w];
+      std::fill(seg_wave.begin() + wv.seg_begin, seg_wave.begin() + wv.seg_begin + wv.n_seg, (int32_t)w);
+    }
+    for (int64_t sg = 0; sg < d->n_segs; ++sg)
+      max_rows = std::max(max_rows, (int)(d->seg_ptr[sg + 1].fac - d->seg_ptr[sg].fac));
+    up(seg_wave.data(), d->n_segs, &p->dev.seg_wave);
+  }
+  p->dev.n_slots = std::max(1, std::min(max_rows, wfm::kMaxSlots));
+  int32_t* d_seg_start = nullptr;
+  double* d_seg_val = nullptr;
+  wfm::DFactor* d_dfacs = nullptr;
+  wfm::CTerm* d_cterms = nullptr;
+  int* d_max_ir = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&d_seg_start, sizeof(int32_t) * (size_t)std::max<int64_t>(d->n_segs, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_seg_val, sizeof(double) * (size_t)std::max<int64_t>(d->n_segs, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_dfacs, sizeof(wfm::DFactor) * (size_t)std::max<int64_t>(d->n_facs, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cterms, sizeof(wfm::CTerm) * (size_t)std::max<int64_t>(d->n_terms, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_max_ir, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d_max_ir, 0, sizeof(int));
+  p->dev.seg_start = d_seg_start;
+  p->dev.seg_val = d_seg_val;
+  p->dev.dfacs = d_dfacs;
+  p->dev.cterms = d_cterms;
+
+  // tile size: the tile's segment rows must fit the staging tables (256 rows) with
+  // margin and its slice of the device tables a third of the shared-memory budget
+  // on average (tiles are denser than average where pulses cluster)
   {
     int64_t samples = 0;
     for (int64_t w = 0; w < d->n_waves; ++w) samples += d->waves[w].n;
-    const double segs_per_4k = samples > 0 ? (double)d->n_segs * 4096.0 / (double)samples : 0.0;
+    const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
+    const double segs = (double)d->n_segs * per_sample;
+    const double ir = ((double)d->n_facs * sizeof(wfm::DFactor) + (double)d->n_terms * sizeof(wfm::CTerm)) * per_sample;
     int ts = wfm::kMaxTileSamples;
-    if (segs_per_4k > 24.0) ts = 8192;
-    if (segs_per_4k > 64.0) ts = 4096;
-    if (segs_per_4k > 160.0) ts = wfm::kMinTileSamples;
+    while (ts > wfm::kMinTileSamples && (segs * ts > 128.0 || ir * ts > wfm::kMaxIrBytes / 3.0)) ts >>= 1;
     p->dev.tile_samples = ts;
   }
   const int64_t tile_samples = p->dev.tile_samples;
@@ -256,7 +273,8 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   for (int64_t w = 0; w < d->n_waves; ++w) {
     p->tile_prefix[w] = (int64_t)tiles.size();
     const WfmWave& wv = d->waves[w];
-    for (int64_t j = 0; j < wv.n; j += tile_samples) tiles.push_back({j, (int32_t)w, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+    for (int64_t j = 0; j < wv.n; j += tile_samples)
+      tiles.push_back({j, wv.out_off + j, (int32_t)w, (int32_t)std::min<int64_t>(tile_samples, wv.n - j), 0, 0, 0, 0, 0, 0});
     total = std::max(total, wv.out_off + wv.n);
     if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
   }
@@ -268,13 +286,20 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     e = upload(tiles.data(), (int64_t)tiles.size(), &dt);
     p->d_tiles = const_cast<wfm::TileDesc*>(dt);
   }
-  // device pre-pass: every tile learns the segment range it spans
-  if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, p->d_tiles, p->n_tiles, 0);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  // device pre-pass: segment start positions and flat values, then every tile's segment range
+  int max_ir = 0;
+  if (e == cudaSuccess)
+    e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_segs, d->n_facs, d->n_terms, p->n_tiles}, d_seg_start,
+                            d_seg_val, d_dfacs, d_cterms, p->d_tiles, d_max_ir, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(&max_ir, d_max_ir, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_max_ir);
   if (e != cudaSuccess) {
     delete p;
     return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));
   }
+  // shared memory for a tile's table slice: what the largest tile needs, capped (tiles
+  // beyond the cap take the kernel's global-memory fallback path)
+  p->dev.ir_bytes = std::min((max_ir + 15) & ~15, wfm::kMaxIrBytes);
   *out = p;
   return WFM_OK;
 }

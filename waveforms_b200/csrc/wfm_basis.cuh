@@ -45,7 +45,7 @@ __device__ __forceinline__ double f_gaussian(double t, double s) {
 __device__ __forceinline__ double f_sinc(double t, double bw) {
   double u = mul(bw, t);
   double y = mul(kPi, u == 0.0 ? 1.0e-20 : u);
-  return dvd(sin(y), y);
+  return dvd(sin_cw(y), y);
 }
 
 // _waveform.pyx:319-320  np.interp(t, np.linspace(start, stop, n), points)
@@ -82,13 +82,13 @@ __device__ inline double f_interp(double t, double start, double stop, const dou
 // pool: [k1 = 2pi(freq+delta), k2 = 2pi*delta*t0 + phase, has_y, c3 = -b*o, o2 = 2*o]
 __device__ __forceinline__ double f_drag(double t, double t0, double o, const double* __restrict__ pool) {
   double dt = sub(t, t0);
-  double s1 = sin(mul(o, dt));
+  double s1 = sin_cw(mul(o, dt));
   double ox = mul(s1, s1);
   double wt = sub(mul(pool[0], t), pool[1]);
   double sw, cw;
-  sincos(wt, &sw, &cw);
+  sincos_cw(wt, &sw, &cw);
   if (pool[2] == 0.0) return mul(ox, cw);
-  double oy = mul(pool[3], sin(mul(pool[4], dt)));
+  double oy = mul(pool[3], sin_cw(mul(pool[4], dt)));
   return add(mul(ox, cw), mul(oy, sw));
 }
 
@@ -140,15 +140,25 @@ __device__ inline double f_dgaussian(double t, double s, double nn, const double
 
 // multi-notch DRAG envelopes, ids 16/17 (multy_drag.py:30-174); see
 // wfm_multidrag.cuh
-__device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx);
+__device__ inline double f_drag_sin(double t, double t0, double o, const double* __restrict__ pool, bool sinx);
 
-__device__ __forceinline__ double eval_factor(const WfmFactor& f, double x, const double* __restrict__ args) {
+// one basis-function row: func id, shift, the two inline scalars, offset of its
+// block in the argument pool (WfmFactor / DFactor carry exactly these)
+struct FacArgs {
+  int func;
+  int arg_off;
+  double shift, a0, a1;
+};
+
+// every basis function; out of line (one copy per kernel): the sampling kernel
+// inlines the hot ones itself (eval_factors in wfm_sample.cu)
+static __device__ __noinline__ double eval_factor(const FacArgs& f, double x, const double* __restrict__ args) {
   const double t = sub(x, f.shift);
   switch (f.func) {
     case WFM_LINEAR: return t;
     case WFM_GAUSSIAN: return f_gaussian(t, f.a0);
     case WFM_ERF: return erf(dvd(t, f.a0));
-    case WFM_COS: return cos(mul(f.a0, t));
+    case WFM_COS: return cos_cw(mul(f.a0, t));
     case WFM_SINC: return f_sinc(t, f.a0);
     case WFM_EXP: return exp(mul(f.a0, t));
     case WFM_INTERP: return f_interp(t, f.a0, f.a1, args + f.arg_off);
@@ -156,26 +166,26 @@ __device__ __forceinline__ double eval_factor(const WfmFactor& f, double x, cons
       // sin(phi0 + 2pi*((f1-f0)/(2T)*t**2 + f0*t)); a0 = f0, a1 = phi0, pool [c, 2pi]
       const double* p = args + f.arg_off;
       double inner = add(mul(p[0], mul(t, t)), mul(f.a0, t));
-      return sin(add(f.a1, mul(p[1], inner)));
+      return sin_cw(add(f.a1, mul(p[1], inner)));
     }
     case WFM_EXPONENTIALCHIRP: {
       // sin(phi0 + 2pi*f0*(exp(alpha*t)-1)/alpha); a0 = alpha, a1 = phi0, pool [2pi*f0]
       const double* p = args + f.arg_off;
       double g = sub(exp(mul(f.a0, t)), 1.0);
-      return sin(add(f.a1, dvd(mul(p[0], g), f.a0)));
+      return sin_cw(add(f.a1, dvd(mul(p[0], g), f.a0)));
     }
     case WFM_HYPERBOLICCHIRP: {
       // sin(phi0 + 2pi*f0/k*log(1+k*t)); a0 = k, a1 = phi0, pool [2pi*f0/k]
       const double* p = args + f.arg_off;
-      return sin(add(f.a1, mul(p[0], log(add(1.0, mul(f.a0, t))))));
+      return sin_cw(add(f.a1, mul(p[0], log(add(1.0, mul(f.a0, t))))));
     }
     case WFM_COSH: return cosh(mul(f.a0, t));
     case WFM_SINH: return sinh(mul(f.a0, t));
     case WFM_DRAG: return f_drag(t, f.a0, f.a1, args + f.arg_off);
     case WFM_MOLLIFIER: return f_mollifier(t, f.a0, f.a1, args + f.arg_off);
     case WFM_D_GAUSSIAN: return f_dgaussian(t, f.a0, f.a1, args + f.arg_off);
-    case WFM_DRAG_SIN: return f_drag_sin(t, f, args + f.arg_off, false);
-    case WFM_DRAG_SINX: return f_drag_sin(t, f, args + f.arg_off, true);
+    case WFM_DRAG_SIN: return f_drag_sin(t, f.a0, f.a1, args + f.arg_off, false);
+    case WFM_DRAG_SINX: return f_drag_sin(t, f.a0, f.a1, args + f.arg_off, true);
     default: return CUDART_NAN;
   }
 }

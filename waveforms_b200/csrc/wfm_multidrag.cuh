@@ -27,8 +27,7 @@ __device__ __forceinline__ double polyval_rows(const double* __restrict__ c, int
   return y;
 }
 
-__device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* __restrict__ pool, bool sinx) {
-  const double t0 = f.a0, o = f.a1;
+__device__ inline double f_drag_sin(double t, double t0, double o, const double* __restrict__ pool, bool sinx) {
   const double tm1 = pool[2], tm2 = pool[3], plateau = pool[4];
   const int m = (int)pool[5];
   const double* __restrict__ gx = pool + 8;
@@ -70,7 +69,7 @@ __device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* 
     } else {
       const double arg = (t >= tm2) ? mul(o, sub(dt, plateau)) : mul(o, dt);
       double S, Cc;
-      sincos(arg, &S, &Cc);
+      sincos_cw(arg, &S, &Cc);
       double sp = 1.0;
       for (int p = 0; p <= m; ++p) {
         const double basis = (p & 1) ? mul(sp, Cc) : sp;
@@ -82,7 +81,7 @@ __device__ inline double f_drag_sin(double t, const WfmFactor& f, const double* 
   }
   const double wt = sub(mul(pool[0], t), pool[1]);
   double sw, cw;
-  sincos(wt, &sw, &cw);
+  sincos_cw(wt, &sw, &cw);
   return add(mul(ox, cw), mul(oy, sw));
 }
 

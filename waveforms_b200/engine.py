@@ -18,7 +18,11 @@ from . import _algebra as A
 from .lowering import (FACTOR_DT, REF_DT, SEGPTR_DT, TERM_DT, WAVE_DT, Channel,
                        Grid, LoweredBatch, lower)
 
-_LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libwfmb200.so'
+import os
+
+# WFM_LIB selects another build of the same library (kernel-tuning experiments)
+_LIB_PATH = Path(os.environ.get('WFM_LIB') or
+                 Path(__file__).resolve().parent / 'csrc' / 'libwfmb200.so')
 
 WFM_F64, WFM_F32, WFM_C128 = 0, 1, 2
 _NP_DTYPE = {WFM_F64: np.float64, WFM_F32: np.float32, WFM_C128: np.complex128}
