@@ -89,6 +89,8 @@ struct WfmProgram {
     cudaFree((void*)dev.seg_start);
     cudaFree((void*)dev.seg_val);
     cudaFree((void*)dev.seg_wave);
+    cudaFree((void*)dev.pkt_off);
+    cudaFree((void*)dev.packets);
     cudaFree(d_tiles);
     cudaFree(d_stage);
   }
@@ -235,38 +237,42 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
       max_rows = std::max(max_rows, (int)(d->seg_ptr[sg + 1].fac - d->seg_ptr[sg].fac));
     up(seg_wave.data(), d->n_segs, &p->dev.seg_wave);
   }
-  p->dev.n_slots = std::max(1, std::min(max_rows, wfm::kMaxSlots));
+  p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
   int32_t* d_seg_start = nullptr;
   double* d_seg_val = nullptr;
   wfm::DFactor* d_dfacs = nullptr;
   wfm::CTerm* d_cterms = nullptr;
-  int* d_max_ir = nullptr;
   if (e == cudaSuccess) e = cudaMalloc(&d_seg_start, sizeof(int32_t) * (size_t)std::max<int64_t>(d->n_segs, 1));
   if (e == cudaSuccess) e = cudaMalloc(&d_seg_val, sizeof(double) * (size_t)std::max<int64_t>(d->n_segs, 1));
   if (e == cudaSuccess) e = cudaMalloc(&d_dfacs, sizeof(wfm::DFactor) * (size_t)std::max<int64_t>(d->n_facs, 1));
   if (e == cudaSuccess) e = cudaMalloc(&d_cterms, sizeof(wfm::CTerm) * (size_t)std::max<int64_t>(d->n_terms, 1));
-  if (e == cudaSuccess) e = cudaMalloc(&d_max_ir, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(d_max_ir, 0, sizeof(int));
   p->dev.seg_start = d_seg_start;
   p->dev.seg_val = d_seg_val;
   p->dev.dfacs = d_dfacs;
   p->dev.cterms = d_cterms;
 
-  // tile size: the tile's segment rows must fit the staging tables (256 rows) with
-  // margin and its slice of the device tables a third of the shared-memory budget
-  // on average (tiles are denser than average where pulses cluster)
+  // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample),
+  // the value slots and two packet buffers (the tile's rows of the device tables,
+  // double-buffered).  Take the largest tile (a multiple of 128 samples) whose AVERAGE
+  // packet leaves a 4x margin in a packet buffer for tiles where pulses cluster; a tile
+  // whose packet still does not fit takes the kernel's cold path.
   {
     int64_t samples = 0;
     for (int64_t w = 0; w < d->n_waves; ++w) samples += d->waves[w].n;
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
-    const double segs = (double)d->n_segs * per_sample;
-    const double ir = ((double)d->n_facs * sizeof(wfm::DFactor) + (double)d->n_terms * sizeof(wfm::CTerm)) * per_sample;
-    int ts = wfm::kMaxTileSamples;
-    while (ts > wfm::kMinTileSamples && (segs * ts > 128.0 || ir * ts > wfm::kMaxIrBytes / 3.0)) ts >>= 1;
+    const double ir = ((double)d->n_facs * sizeof(wfm::DFactor) + (double)d->n_terms * sizeof(wfm::CTerm) +
+                       (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
+    const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
+    int ts = wfm::kMaxTileSamples, cap = 0;
+    for (;; ts -= 128) {
+      cap = ((wfm::kWarpSliceBytes - fixed - ts * 8) / 2) & ~15;
+      if (ts <= wfm::kMinTileSamples || (cap >= 256 && 64.0 + 4.0 * ir * ts <= cap)) break;
+    }
     p->dev.tile_samples = ts;
+    p->dev.pkt_cap = std::max(cap, 64);
   }
   const int64_t tile_samples = p->dev.tile_samples;
-  // tile list: tile_samples consecutive samples of one channel per CTA
+  // tile list: tile_samples consecutive samples of one channel per tile
   std::vector<wfm::TileDesc> tiles;
   p->tile_prefix.resize(d->n_waves + 1);
   int64_t total = 0;
@@ -281,25 +287,42 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->tile_prefix[d->n_waves] = (int64_t)tiles.size();
   p->n_tiles = (int64_t)tiles.size();
   p->total_samples = total;
+  if (e == cudaSuccess && p->n_tiles >= INT32_MAX) {
+    const long long nt = (long long)p->n_tiles;
+    delete p;
+    return fail(WFM_EINVAL, "too many tiles (%lld)", nt);
+  }
   if (e == cudaSuccess) {
     const wfm::TileDesc* dt = nullptr;
     e = upload(tiles.data(), (int64_t)tiles.size(), &dt);
     p->d_tiles = const_cast<wfm::TileDesc*>(dt);
   }
-  // device pre-pass: segment start positions and flat values, then every tile's segment range
-  int max_ir = 0;
+  // device pre-pass 1: segment start positions and flat values, device table formats,
+  // every tile's segment range and packet size; then the packet offsets (exclusive scan)
+  uint32_t *d_pkt_size = nullptr, *d_pkt_off = nullptr, *d_scratch = nullptr;
+  const size_t nt1 = (size_t)p->n_tiles + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&d_pkt_size, sizeof(uint32_t) * nt1);
+  if (e == cudaSuccess) e = cudaMalloc(&d_pkt_off, sizeof(uint32_t) * nt1);
+  if (e == cudaSuccess) e = cudaMalloc(&d_scratch, sizeof(uint32_t) * (nt1 / 4096 + 2));
+  p->dev.pkt_off = d_pkt_off;
   if (e == cudaSuccess)
     e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_segs, d->n_facs, d->n_terms, p->n_tiles}, d_seg_start,
-                            d_seg_val, d_dfacs, d_cterms, p->d_tiles, d_max_ir, 0);
-  if (e == cudaSuccess) e = cudaMemcpy(&max_ir, d_max_ir, sizeof(int), cudaMemcpyDeviceToHost);
-  cudaFree(d_max_ir);
+                            d_seg_val, d_dfacs, d_cterms, p->d_tiles, d_pkt_size, 0);
+  if (e == cudaSuccess) e = wfm::launch_scan(d_pkt_size, d_pkt_off, d_scratch, p->n_tiles, 0);
+  uint32_t total16 = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&total16, d_pkt_off + p->n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  // pass 2: the packets themselves
+  unsigned char* d_packets = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&d_packets, std::max<size_t>((size_t)total16 * 16, 16));
+  p->dev.packets = d_packets;
+  if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, p->n_tiles, d_packets, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  cudaFree(d_pkt_size);
+  cudaFree(d_scratch);
   if (e != cudaSuccess) {
     delete p;
     return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));
   }
-  // shared memory for a tile's table slice: what the largest tile needs, capped (tiles
-  // beyond the cap take the kernel's global-memory fallback path)
-  p->dev.ir_bytes = std::min((max_ir + 15) & ~15, wfm::kMaxIrBytes);
   *out = p;
   return WFM_OK;
 }
@@ -339,7 +362,7 @@ int wfm_sample(wfm_program_t prog, const WfmLaunch* l, void* stream) {
   if ((uintptr_t)l->out % 16) return fail(WFM_EINVAL, "output buffer must be 16-byte aligned");
   DeviceGuard g(prog->device);
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles + t0, t1 - t0, l->dtype, l->accumulate, l->out,
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, l->accumulate, l->out,
                               (cudaStream_t)stream));
   if (t1 > t0) prog->launches += 1;
   return WFM_OK;
@@ -367,7 +390,7 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   // padding between channels is never written by the kernel: keep it defined
   WFM_CUDA(cudaMemsetAsync((char*)prog->d_stage + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, 0));
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles + t0, t1 - t0, l->dtype, 0, prog->d_stage, 0));
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->d_stage, 0));
   if (t1 > t0) prog->launches += 1;
   WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->d_stage + (size_t)lo * esz,
                            (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, 0));

@@ -85,8 +85,8 @@ __device__ __forceinline__ double f_drag(double t, double t0, double o, const do
   double s1 = sin_cw(mul(o, dt));
   double ox = mul(s1, s1);
   double wt = sub(mul(pool[0], t), pool[1]);
-  double sw, cw;
-  sincos_cw(wt, &sw, &cw);
+  const SinCos sc = sincos_cw(wt);
+  const double sw = sc.s, cw = sc.c;
   if (pool[2] == 0.0) return mul(ox, cw);
   double oy = mul(pool[3], sin_cw(mul(pool[4], dt)));
   return add(mul(ox, cw), mul(oy, sw));

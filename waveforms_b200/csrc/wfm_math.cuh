@@ -19,51 +19,74 @@ __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, 
 // argument has a relative error of ~2^-53 even next to a multiple of pi/2.
 // Kernels: the fdlibm minimax polynomials on [-pi/4, pi/4].  Measured against
 // mpmath over +-1e9 (incl. neighbours of k*pi/2): relative error < 2 * 2^-53.
-static __device__ __noinline__ void sincos_huge(double a, double* sn, double* cs) { sincos(a, sn, cs); }
+// The coefficients sit in constant memory so that every FMA takes its constant
+// as a c[bank][offset] operand instead of two moves into registers.
+static __constant__ double kTrig[16] = {
+    0.6366197723675814,        // 0: 2/pi
+    1.5707963267948966,        // 1: pi/2 HI
+    6.123233995736766e-17,     // 2: pi/2 MID
+    -1.4973849048591698e-33,   // 3: pi/2 LO
+    1.58969099521155010221e-10,   // 4: S6
+    -2.50507602534068634195e-08,  // 5: S5
+    2.75573137070700676789e-06,   // 6: S4
+    -1.98412698298579493134e-04,  // 7: S3
+    8.33333333332248946124e-03,   // 8: S2
+    -1.66666666666666324348e-01,  // 9: S1
+    -1.13596475577881948265e-11,  // 10: C6
+    2.08757232129817482790e-09,   // 11: C5
+    -2.75573143513906633035e-07,  // 12: C4
+    2.48015872894767294178e-05,   // 13: C3
+    -1.38888888888741095749e-03,  // 14: C2
+    4.16666666666666019037e-02,   // 15: C1
+};
 
-__device__ __forceinline__ void sincos_cw(double a, double* sn, double* cs) {
-  if (!(fabs(a) <= 1073741824.0)) {  // also NaN / inf: CUDA's Payne-Hanek path, out of line
-    sincos_huge(a, sn, cs);
-    return;
-  }
-  const double q = rint(a * 0.6366197723675814);
-  double r = fma(-q, 1.5707963267948966, a);
-  r = fma(-q, 6.123233995736766e-17, r);
-  r = fma(-q, -1.4973849048591698e-33, r);
+struct SinCos {
+  double s, c;
+};
+
+static __device__ __noinline__ SinCos sincos_huge(double a) {  // CUDA's Payne-Hanek path, out of line
+  SinCos r;
+  sincos(a, &r.s, &r.c);
+  return r;
+}
+
+__device__ __forceinline__ SinCos sincos_cw(double a) {
+  if (!(fabs(a) <= 1073741824.0)) return sincos_huge(a);  // also NaN / inf
+  const double q = rint(a * kTrig[0]);
+  double r = fma(-q, kTrig[1], a);
+  r = fma(-q, kTrig[2], r);
+  r = fma(-q, kTrig[3], r);
   const double z = r * r;
-  double ps = 1.58969099521155010221e-10;
-  ps = fma(ps, z, -2.50507602534068634195e-08);
-  ps = fma(ps, z, 2.75573137070700676789e-06);
-  ps = fma(ps, z, -1.98412698298579493134e-04);
-  ps = fma(ps, z, 8.33333333332248946124e-03);
-  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double ps = kTrig[4];
+  ps = fma(ps, z, kTrig[5]);
+  ps = fma(ps, z, kTrig[6]);
+  ps = fma(ps, z, kTrig[7]);
+  ps = fma(ps, z, kTrig[8]);
+  ps = fma(ps, z, kTrig[9]);
   const double s = fma(r * z, ps, r);
-  double pc = -1.13596475577881948265e-11;
-  pc = fma(pc, z, 2.08757232129817482790e-09);
-  pc = fma(pc, z, -2.75573143513906633035e-07);
-  pc = fma(pc, z, 2.48015872894767294178e-05);
-  pc = fma(pc, z, -1.38888888888741095749e-03);
-  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double pc = kTrig[10];
+  pc = fma(pc, z, kTrig[11]);
+  pc = fma(pc, z, kTrig[12]);
+  pc = fma(pc, z, kTrig[13]);
+  pc = fma(pc, z, kTrig[14]);
+  pc = fma(pc, z, kTrig[15]);
   const double hz = 0.5 * z;
   const double w = 1.0 - hz;
   const double c = w + (((1.0 - w) - hz) + z * z * pc);
   const int n = (int)q;
-  const double ss = (n & 1) ? c : s;
-  const double cc = (n & 1) ? s : c;
-  *sn = (n & 2) ? -ss : ss;
-  *cs = ((n + 1) & 2) ? -cc : cc;
+  // quadrant: swap for odd n, then flip signs through the sign bit
+  const bool odd = n & 1;
+  const double ss = odd ? c : s;
+  const double cc = odd ? s : c;
+  const unsigned long long sbit = (unsigned long long)(n & 2) << 62;
+  const unsigned long long cbit = (unsigned long long)((n + 1) & 2) << 62;
+  SinCos o;
+  o.s = __longlong_as_double(__double_as_longlong(ss) ^ sbit);
+  o.c = __longlong_as_double(__double_as_longlong(cc) ^ cbit);
+  return o;
 }
 
-__device__ __forceinline__ double sin_cw(double a) {
-  double s, c;
-  sincos_cw(a, &s, &c);
-  return s;
-}
-
-__device__ __forceinline__ double cos_cw(double a) {
-  double s, c;
-  sincos_cw(a, &s, &c);
-  return c;
-}
+__device__ __forceinline__ double sin_cw(double a) { return sincos_cw(a).s; }
+__device__ __forceinline__ double cos_cw(double a) { return sincos_cw(a).c; }
 
 }  // namespace wfm

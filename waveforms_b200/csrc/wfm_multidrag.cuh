@@ -68,8 +68,8 @@ __device__ inline double f_drag_sin(double t, double t0, double o, const double*
       oy = pool[7];
     } else {
       const double arg = (t >= tm2) ? mul(o, sub(dt, plateau)) : mul(o, dt);
-      double S, Cc;
-      sincos_cw(arg, &S, &Cc);
+      const SinCos sa = sincos_cw(arg);
+      const double S = sa.s, Cc = sa.c;
       double sp = 1.0;
       for (int p = 0; p <= m; ++p) {
         const double basis = (p & 1) ? mul(sp, Cc) : sp;
@@ -80,8 +80,8 @@ __device__ inline double f_drag_sin(double t, double t0, double o, const double*
     }
   }
   const double wt = sub(mul(pool[0], t), pool[1]);
-  double sw, cw;
-  sincos_cw(wt, &sw, &cw);
+  const SinCos sc = sincos_cw(wt);
+  const double sw = sc.s, cw = sc.c;
   return add(mul(ox, cw), mul(oy, sw));
 }
 

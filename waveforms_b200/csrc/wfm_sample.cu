@@ -17,45 +17,45 @@
 //   * every tile (tile_samples consecutive samples of one channel) learns the
 //     segment range it spans and its slice of the factor / term tables.
 //
-// Per launch, one CTA (256 threads) per tile; the tile is ASSEMBLED IN SHARED
-// MEMORY and leaves the SM as ONE TMA bulk store (cp.async.bulk shared->global):
-//   1. Prologue.  One thread starts a TMA bulk load (cp.async.bulk + mbarrier) of
-//      the tile's slice of the factor / compact-term tables; every thread copies
-//      one row of the segment tables (start position, flat value, pointers).
-//   2. Flat fill.  The whole shared tile is first filled with the channel's
-//      zero-segment value (16-byte shared stores, no table look-ups, overlapping the
-//      table loads); warp 1 then compacts the list of flat segments whose value
-//      differs (constant plateaus) and those runs are rewritten one warp per run.
-//      No abscissa is computed for flat samples.
+// Per launch: a PERSISTENT grid (CTAs per SM x 148) of 8-warp CTAs in which every
+// WARP is autonomous.  A warp owns a private slice of shared memory (output tile,
+// factor-value slots, table slice, segment rows, one mbarrier) and loops over
+// tiles (warp w of the grid takes tiles w, w+G, ...); there is NO block-level
+// barrier anywhere, so a warp stalled on a table load or a long pulse never
+// idles its neighbours.  The tile is ASSEMBLED IN SHARED MEMORY and leaves the
+// SM as ONE TMA bulk store (cp.async.bulk shared->global):
+//   1. Prologue.  Lane 0 starts a TMA bulk load (cp.async.bulk + mbarrier) of
+//      the tile's slice of the factor / compact-term tables; the lanes copy the
+//      tile's segment rows (start position, flat value, pointers); the NEXT tile's
+//      descriptor is prefetched.
+//   2. Flat fill.  After the previous tile's bulk store has finished reading the
+//      buffer, the whole tile is filled with the channel's zero-segment value
+//      (16-byte shared stores, no table look-ups); a ballot compacts the list of
+//      flat segments whose value differs (constant plateaus) and those runs are
+//      rewritten.  No abscissa is computed for flat samples.
 //   3. Active samples.  The ACTIVE samples of the tile are enumerated through a
-//      prefix sum over the segments and dealt round-robin to all 256 threads, so
-//      a tile with one 40-sample pulse keeps 40 lanes busy once and a dense tile
-//      keeps every lane busy.  Each thread interprets its sample's segment
-//      program (distinct factors into per-thread value slots in shared memory,
-//      then terms referencing the slots) and writes the sample into the tile.
-//   4. Store.  fence.proxy.async, barrier, one elected thread issues the bulk
-//      store of the whole tile with an L2 evict-first policy (the output is
-//      write-once; it must not displace the IR).  HBM sees full lines only, no
-//      LSU store instructions are spent on the output, and the store drains
-//      while the other resident CTAs of the SM compute.
+//      warp prefix sum over the segment rows and dealt round-robin to the 32
+//      lanes.  Each lane interprets its sample's segment program (distinct
+//      factors into per-lane value slots in shared memory, then terms referencing
+//      the slots) and writes the sample into the tile.
+//   4. Store.  fence.proxy.async, __syncwarp, lane 0 issues the bulk store of the
+//      whole tile with an L2 evict-first policy (the output is write-once; it must
+//      not displace the IR).  HBM sees full lines only, no LSU store instructions
+//      are spent on the output, and the store drains while the warp is already in
+//      the prologue of its next tile.
 //
 // Algorithmic traffic: 8 B (4 B) per sample, write-only.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "wfm_basis.cuh"
 #include "wfm_multidrag.cuh"
 #include "wfm_internal.h"
 
 namespace wfm {
 
-#ifndef WFM_K1_THREADS
-#define WFM_K1_THREADS 256
-#endif
-constexpr int kThreads = WFM_K1_THREADS;
-#ifndef WFM_K1_MIN_BLOCKS
-#define WFM_K1_MIN_BLOCKS 3  // resident CTAs per SM the register allocation is sized for
-#endif
-constexpr int kStageSegs = 256;  // segment rows staged per tile
+constexpr int kThreads = 256;  // 8 autonomous warps per CTA
+constexpr int kWarpsPerCta = kThreads / 32;
 
 template <typename T> struct OutVec;
 template <> struct OutVec<double> { static constexpr int N = 2; };
@@ -161,60 +161,66 @@ struct WaveEval {
   uint32_t flags;
 };
 
-// per-thread cache of the distinct factor values of one segment evaluation
-struct LocalSlots {  // registers / local memory: fallback and complex kernels
-  double v[kMaxSlots];
-  __device__ __forceinline__ double get(int k) const { return v[k]; }
-  __device__ __forceinline__ void set(int k, double x) { v[k] = x; }
+// per-lane cache of the distinct factor values of one segment evaluation.  PHYSICAL
+// slot 0 holds the constant 1.0; the value of factor row k lives in physical slot k+1.
+struct LocalSlots {  // registers / local memory: cold path and complex kernel
+  double v[kMaxSlots + 1];
+  __device__ __forceinline__ LocalSlots() { v[0] = 1.0; }
+  __device__ __forceinline__ double phys(int k) const { return v[k]; }
+  __device__ __forceinline__ void setp(int k, double x) { v[k] = x; }
 };
-struct SmemSlots {  // shared memory, slot-major: slot k of thread t at p[k*kThreads] (conflict-free)
+struct SmemSlots {  // the warp's shared slice, slot-major: physical slot k of lane l at p[k*32] (conflict-free)
   double* p;
-  __device__ __forceinline__ double get(int k) const { return p[k * kThreads]; }
-  __device__ __forceinline__ void set(int k, double x) const { p[k * kThreads] = x; }
+  __device__ __forceinline__ double phys(int k) const { return p[k * 32]; }
+  __device__ __forceinline__ void setp(int k, double x) const { p[k * 32] = x; }
 };
 
-__device__ __forceinline__ FacArgs fac_args(const DFactor& f) { return FacArgs{f.func, f.aux, f.shift, f.a0, f.a1}; }
+__device__ __forceinline__ FacArgs fac_args(const DFactor& f) {
+  return FacArgs{f.func & 0xffff, f.aux, f.shift, f.a0, f.a1};
+}
 
-// distinct factor values of one segment -> slots [0 .. min(nf, kMaxSlots));
-// facs = the segment's first row (shared memory when the tile's slice is staged)
+// factor rows of one segment -> value slots.  Every row names its destination
+// (physical) slot, so packets can drop the NOP placeholder rows; facs = the
+// segment's first row (shared memory when the tile's packet is staged).
 template <typename Slots>
-__device__ __forceinline__ void eval_factors(const DFactor* __restrict__ facs, int nf, double x,
+__device__ __forceinline__ void eval_factors(const DFactor* __restrict__ facs, int n_rows, double x,
                                              const double* __restrict__ args, Slots& vals) {
 #pragma unroll 1
-  for (int k = 0; k < nf && k < kMaxSlots; ++k) {
-    const int func = facs[k].func;
-    const double shift = facs[k].shift, a0 = facs[k].a0;
-    if (func == WFM_COS_SINCOS) {
-      // one range reduction serves every COS factor of this frequency
-      double s, c;
-      sincos_cw(mul(a0, sub(x, shift)), &s, &c);
-      vals.set(k, c);
-      vals.set(k + 1, s);  // row k+1 is the NOP placeholder (validated at upload)
-      ++k;
-    } else if (func == WFM_COS_ROT) {
+  for (int k = 0; k < n_rows; ++k) {
+    const uint32_t fo = (uint32_t)facs[k].func;
+    const int op = (fo >> 16) & 0xff;
+    const int dest = fo >> 24;
+    const double a0 = facs[k].a0;
+    const double t = sub(x, facs[k].shift);
+    if (op == OP_ROT) {
       // cos(a_t) with a_t = w*(x - shift) rounded exactly as the reference rounds
       // it, obtained from the base row's (cos, sin)(a_b):  a_t = a_b + D + eps with
       // D a host constant (cos D, sin D tabulated) and eps = (a_t - a_b) - D the
       // MEASURED residual (|eps| ~ ulp(a)), expanded to second order.
-      const int base = facs[k].aux;
+      const int base = facs[k].aux;  // physical slot of the base row's cosine
       const double bshift = facs[k].p[0], D = facs[k].p[1], cD = facs[k].p[2], sD = facs[k].p[3];
-      const double a_t = mul(a0, sub(x, shift));
+      const double a_t = mul(a0, t);
       const double a_b = mul(a0, sub(x, bshift));
       const double eps = sub(sub(a_t, a_b), D);
-      const double cb = vals.get(base), sb = vals.get(base + 1);
+      const double cb = vals.phys(base), sb = vals.phys(base + 1);
       const double C = fma(cb, cD, -(sb * sD));
       const double S = fma(sb, cD, cb * sD);
-      vals.set(k, fma(-0.5 * eps * eps, C, fma(-eps, S, C)));
-    } else if (func == WFM_COS) {
-      vals.set(k, cos_cw(mul(a0, sub(x, shift))));
-    } else if (func == WFM_LINEAR) {
-      vals.set(k, sub(x, shift));
-    } else if (func == WFM_GAUSSIAN) {
-      vals.set(k, f_gaussian(sub(x, shift), a0));
-    } else if (func == WFM_ERF) {
-      vals.set(k, erf(dvd(sub(x, shift), a0)));
-    } else {
-      vals.set(k, eval_factor(fac_args(facs[k]), x, args));
+      vals.setp(dest, fma(-0.5 * eps * eps, C, fma(-eps, S, C)));
+    } else if (op == OP_SINCOS) {
+      // one range reduction serves every COS factor of this frequency
+      const SinCos sc = sincos_cw(mul(a0, t));
+      vals.setp(dest, sc.c);
+      vals.setp(dest + 1, sc.s);
+    } else if (op == OP_COS) {
+      vals.setp(dest, cos_cw(mul(a0, t)));
+    } else if (op == OP_LINEAR) {
+      vals.setp(dest, t);
+    } else if (op == OP_GAUSSIAN) {
+      vals.setp(dest, f_gaussian(t, a0));
+    } else if (op == OP_ERF) {
+      vals.setp(dest, erf(dvd(t, a0)));
+    } else if (op != OP_NOP) {
+      vals.setp(dest, eval_factor(fac_args(facs[k]), x, args));
     }
   }
 }
@@ -222,63 +228,53 @@ __device__ __forceinline__ void eval_factors(const DFactor* __restrict__ facs, i
 // product of the referenced factor powers of an ABI term (general path); gfac = the
 // segment's first row in the GLOBAL factor table
 template <typename Slots>
-__device__ __forceinline__ double term_product(const IrGlobal& g, int gfac, const WfmTerm& tm, double x,
-                                               const Slots& vals) {
+__device__ __noinline__ double term_product(const IrGlobal& g, int gfac, const WfmTerm& tm, double x,
+                                            const Slots& vals) {
   double prod = 1.0;
-  bool first = true;
 #pragma unroll 1
   for (int r = 0; r < tm.n_ref; ++r) {
     const WfmRef ref = g.refs[tm.ref_begin + r];
-    double v = (ref.slot < kMaxSlots) ? vals.get(ref.slot) : eval_factor(fac_args(g.dfacs[gfac + ref.slot]), x, g.args);
+    double v = (ref.slot < kMaxSlots) ? vals.phys(ref.slot + 1) : eval_factor(fac_args(g.dfacs[gfac + ref.slot]), x, g.args);
     if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
     else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
-    prod = first ? v : mul(prod, v);  // 1 * v == v
-    first = false;
+    prod = mul(prod, v);  // the reference's product starts from 1; 1 * v is exact
   }
   return prod;
 }
 
+static __device__ __noinline__ double clip_value(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
 // Evaluate one segment's program at one abscissa (real-valued channels; compact terms).
 // facs / cterms point at the segment's first rows (shared or global memory);
 // gfac / gterm are the same rows' indices in the global tables.
+// Order of operations = the reference's (_waveform.pyx:134-152, waveform.py:690-692):
+// every term is amp * (((1 * f1) * f2) * ...), a member's terms are summed left to
+// right starting from 0, the member sums are added to the accumulator (offset).
 template <typename Slots>
 __device__ __forceinline__ double eval_segment_real(const DFactor* __restrict__ facs, const CTerm* __restrict__ cterms,
                                                     int nf, int nt, const IrGlobal& g, int gfac, int gterm,
                                                     const WaveEval& w, double x, Slots& vals) {
   double total = w.offset;
   if (nt == 0) return total;  // zero segment: untouched by clip (calc_parts skips it)
-  eval_factors(facs, nf, x, g.args, vals);
+  eval_factors(facs, nf, x, g.args, vals);  // global rows: nf <= kMaxSlots (the caller clamps)
   double grp = 0.0;
-  bool g_first = true;
 #pragma unroll 1
   for (int it = 0; it < nt; ++it) {
     const double amp = cterms[it].amp;
-    const uint64_t pk = cterms[it].packed;
-    const uint32_t flags = (uint32_t)(pk >> 8) & 0xffu;
+    const uint32_t pk = (uint32_t)cterms[it].packed;
     double prod;
-    if (flags & kCTermExt) {
+    if (pk & kCTermExt) {
       prod = term_product(g, gfac, g.terms[gterm + it], x, vals);
     } else {
-      const int n_ref = (int)(pk & 0xffu);
-      uint32_t slots_lo = (uint32_t)(pk >> 16), slots_hi = (uint32_t)(pk >> 48);
-      prod = 1.0;
-#pragma unroll 1
-      for (int r = 0; r < n_ref; ++r) {
-        const double v = vals.get((int)(slots_lo & 0xffu));
-        slots_lo = (slots_lo >> 8) | (slots_hi << 24);
-        slots_hi >>= 8;
-        prod = r == 0 ? v : mul(prod, v);
-      }
+      prod = mul(mul(vals.phys((pk >> 8) & 0xffu), vals.phys((pk >> 16) & 0xffu)), vals.phys(pk >> 24));
     }
-    const double t = mul(amp, prod);
-    grp = g_first ? t : add(grp, t);  // 0 + a == a
-    g_first = false;
-    if (flags & kCTermGroupEnd) {
+    grp = add(grp, mul(amp, prod));
+    if (pk & kCTermGroupEnd) {
       total = add(total, grp);
-      g_first = true;
+      grp = 0.0;
     }
   }
-  if (w.flags & WFM_WAVE_CLIP) total = fmin(fmax(total, w.clip_lo), w.clip_hi);
+  if (w.flags & WFM_WAVE_CLIP) total = clip_value(total, w.clip_lo, w.clip_hi);
   return total;
 }
 
@@ -290,21 +286,18 @@ __device__ __forceinline__ void eval_segment_cplx(const IrGlobal& g, const WaveE
   const int nt = p1.term - p0.term;
   if (nt == 0) return;
   LocalSlots vals;
-  eval_factors(g.dfacs + p0.fac, p1.fac - p0.fac, x, g.args, vals);
+  eval_factors(g.dfacs + p0.fac, min(p1.fac - p0.fac, kMaxSlots), x, g.args, vals);
   double g_re = 0.0, g_im = 0.0;
-  bool g_first = true;
 #pragma unroll 1
   for (int it = 0; it < nt; ++it) {
     const WfmTerm tm = g.terms[p0.term + it];
     const double prod = term_product(g, p0.fac, tm, x, vals);
-    const double t_re = mul(tm.amp_re, prod), t_im = mul(tm.amp_im, prod);
-    g_re = g_first ? t_re : add(g_re, t_re);
-    g_im = g_first ? t_im : add(g_im, t_im);
-    g_first = false;
+    g_re = add(g_re, mul(tm.amp_re, prod));
+    g_im = add(g_im, mul(tm.amp_im, prod));
     if (tm.flags & WFM_TERM_GROUP_END) {
       out_re = add(out_re, g_re);
       out_im = add(out_im, g_im);
-      g_first = true;
+      g_re = g_im = 0.0;
     }
   }
   if (w.flags & WFM_WAVE_CLIP) out_re = fmin(fmax(out_re, w.clip_lo), w.clip_hi);
@@ -322,18 +315,14 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
   const WfmSegPtr p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1];
   double val = w.offset;
   if (p1.fac == p0.fac && p1.term > p0.term) {
-    // constant segment: offset + sum over stack members of (sum of their constant terms)
+    // constant segment: offset + sum over stack members of (0 + sum of their constant terms)
     double grp = 0.0;
-    bool g_first = true;
     for (int t = p0.term; t < p1.term; ++t) {
       const WfmTerm tm = P.terms[t];
-      double c = tm.amp_re;
-      if (tm.n_ref > 0) c = CUDART_NAN;  // cannot happen: a term with factors makes the segment active
-      grp = g_first ? c : add(grp, c);
-      g_first = false;
+      grp = add(grp, tm.n_ref > 0 ? CUDART_NAN : tm.amp_re);  // a term with factors would make the segment active
       if (tm.flags & WFM_TERM_GROUP_END) {
         val = add(val, grp);
-        g_first = true;
+        grp = 0.0;
       }
     }
     if (w.flags & WFM_WAVE_CLIP) val = fmin(fmax(val, w.clip_lo), w.clip_hi);
@@ -342,12 +331,34 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
 }
 
 // one thread per factor row: the 64-byte device row
-__global__ void prepare_factors_kernel(DevProgram P, DFactor* __restrict__ dfacs, int64_t n_facs) {
+__global__ void prepare_factors_kernel(DevProgram P, DFactor* __restrict__ dfacs, int64_t n_facs, int64_t n_segs) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_facs) return;
   const WfmFactor f = P.facs[k];
+  int op = OP_GENERIC;
+  switch (f.func) {
+    case WFM_COS_ROT: op = OP_ROT; break;
+    case WFM_COS_SINCOS: op = OP_SINCOS; break;
+    case WFM_NOP: op = OP_NOP; break;
+    case WFM_COS: op = OP_COS; break;
+    case WFM_LINEAR: op = OP_LINEAR; break;
+    case WFM_GAUSSIAN: op = OP_GAUSSIAN; break;
+    case WFM_ERF: op = OP_ERF; break;
+    default: break;
+  }
+  // destination (physical) value slot = row within its segment + 1; found from the
+  // segment table by binary search over seg_ptr (rows of one segment are contiguous)
+  int lo = 0, hi = (int)n_segs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int64_t)P.seg_ptr[mid].fac <= k) lo = mid; else hi = mid - 1;
+  }
+  while (lo + 1 < (int)n_segs && P.seg_ptr[lo + 1].fac <= k) ++lo;  // skip factor-less segments sharing the offset
+  const int row = (int)(k - P.seg_ptr[lo].fac);
+  if (row >= kMaxSlots) op = OP_NOP;  // beyond the value cache: evaluated on demand by extended terms
+  const int dest = row < kMaxSlots ? row + 1 : 0;
   DFactor d;
-  d.func = f.func;
+  d.func = f.func | (op << 16) | (dest << 24);
   d.aux = f.arg_off;
   d.shift = f.shift;
   d.a0 = f.a0;
@@ -355,7 +366,7 @@ __global__ void prepare_factors_kernel(DevProgram P, DFactor* __restrict__ dfacs
   d.p[0] = d.p[1] = d.p[2] = d.p[3] = 0.0;
   if (f.func == WFM_COS_ROT) {
     const double* __restrict__ p = P.args + f.arg_off;  // [base_slot, base_shift, D, cos D, sin D]
-    d.aux = (int)p[0];
+    d.aux = (int)p[0] + 1;  // physical slot of the base row's cosine
     d.p[0] = p[1];
     d.p[1] = p[2];
     d.p[2] = p[3];
@@ -370,20 +381,18 @@ __global__ void prepare_terms_kernel(DevProgram P, CTerm* __restrict__ cterms, i
   if (t >= n_terms) return;
   const WfmTerm tm = P.terms[t];
   uint64_t packed = 0;
-  bool ext = tm.n_ref > 6;
+  bool ext = tm.n_ref > 3;
   for (int r = 0; r < tm.n_ref && !ext; ++r) {
     const WfmRef rf = P.refs[tm.ref_begin + r];
     if (rf.kind != WFM_POW_ONE || rf.slot >= kMaxSlots) ext = true;
-    else packed |= (uint64_t)(uint32_t)rf.slot << (16 + 8 * r);
+    else packed |= (uint64_t)(uint32_t)(rf.slot + 1) << (8 + 8 * r);  // physical slot; 0 = the constant 1.0
   }
   uint32_t flags = (tm.flags & WFM_TERM_GROUP_END) ? kCTermGroupEnd : 0u;
   if (ext) {
     flags |= kCTermExt;
     packed = 0;
-  } else {
-    packed |= (uint64_t)(uint32_t)tm.n_ref;
   }
-  packed |= (uint64_t)flags << 8;
+  packed |= flags;
   cterms[t] = CTerm{tm.amp_re, packed};
 }
 
@@ -397,9 +406,57 @@ __device__ __forceinline__ int owning_segment(const int32_t* __restrict__ start,
   return lo;
 }
 
-// one thread per tile: the segment rows it spans and its slice of the tables
+// what a tile's packet holds (shared by the measuring and the filling pass)
+struct TileLayout {
+  int n_arows, n_patch, n_fac, n_term, n_active;
+  bool cold;
+  __device__ __forceinline__ int bytes() const {
+    if (cold) return (int)sizeof(PacketHeader);
+    return (int)sizeof(PacketHeader) + (n_arows ? (n_arows + 1) * (int)sizeof(ARow) : 0) + n_patch * (int)sizeof(PatchRow) +
+           n_fac * (int)sizeof(DFactor) + n_term * (int)sizeof(CTerm);
+  }
+};
+
+// tile-relative [a, b) of segment k (channel-relative row) clipped to the tile
+__device__ __forceinline__ void seg_span(const int32_t* __restrict__ st, int n_seg, int64_t n, int k, int64_t j0, int cnt,
+                                         int& a, int& b) {
+  const int64_t lo = st[k], hi = (k + 1 < n_seg) ? (int64_t)st[k + 1] : n;
+  a = (int)(max(lo, j0) - j0);
+  b = (int)(min(hi, j0 + cnt) - j0);
+}
+
+// rows of a segment the packet carries: no NOP placeholders, nothing beyond the value cache
+__device__ __forceinline__ int packet_rows(const DFactor* __restrict__ dfacs, WfmSegPtr p0, WfmSegPtr p1) {
+  int n = 0;
+  for (int r = p0.fac; r < p1.fac; ++r) n += (((uint32_t)dfacs[r].func >> 16) & 0xff) != OP_NOP;
+  return n;
+}
+
+__device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, const WfmWave& w) {
+  TileLayout L{0, 0, 0, 0, 0, false};
+  const int32_t* __restrict__ st = P.seg_start + w.seg_begin;
+  const int k0 = td.seg0 - w.seg_begin;
+  for (int k = k0; k < k0 + td.nb; ++k) {
+    int a, b;
+    seg_span(st, w.n_seg, w.n, k, td.j0, td.cnt, a, b);
+    if (b <= a) continue;
+    const WfmSegPtr p0 = P.seg_ptr[w.seg_begin + k], p1 = P.seg_ptr[w.seg_begin + k + 1];
+    if (p1.fac > p0.fac) {
+      L.n_arows += 1;
+      L.n_fac += packet_rows(P.dfacs, p0, p1);
+      L.n_term += p1.term - p0.term;
+      L.n_active += b - a;
+    } else if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) {
+      L.n_patch += 1;
+    }
+  }
+  L.cold = L.bytes() > P.pkt_cap;
+  return L;
+}
+
+// one thread per tile: the segment rows it spans, its slice of the tables, its packet size
 __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, int64_t n_tiles,
-                                     int* __restrict__ max_ir_bytes) {
+                                     uint32_t* __restrict__ pkt_size) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
   TileDesc td = tiles[t];
@@ -415,12 +472,153 @@ __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles,
   td.term0 = a.term;
   td.n_term = e.term - a.term;
   tiles[t] = td;
-  if (td.n_fac > 0 && td.nb <= kStageSegs)
-    atomicMax(max_ir_bytes, td.n_fac * (int)sizeof(DFactor) + td.n_term * (int)sizeof(CTerm));
+  pkt_size[t] = (uint32_t)(measure_tile(P, td, w).bytes() / 16);
+}
+
+// ---- exclusive scan of the packet sizes (three small kernels) -----------------------------
+constexpr int kScanBlock = 256, kScanItems = 16, kScanTile = kScanBlock * kScanItems;  // 4096 per block
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[kScanBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += u;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  uint32_t before = 0, all = 0;
+  for (int k = 0; k < kScanBlock / 32; ++k) {
+    if (k < wid) before += warp_sums[k];
+    all += warp_sums[k];
+  }
+  __syncthreads();
+  *total = all;
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ sums,
+                                                                 int64_t n) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v = 0;
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) v += in[base + i];
+  uint32_t total;
+  block_exclusive_scan(v, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place; sums[n_blocks] = grand total
+__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint32_t* __restrict__ sums, int64_t n_blocks) {
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < n_blocks; b0 += kScanBlock) {
+    const int64_t i = b0 + threadIdx.x;
+    const uint32_t v = i < n_blocks ? sums[i] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < n_blocks) sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[n_blocks] = carry;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ sums,
+                                                                uint32_t* __restrict__ out, int64_t n, int64_t n_blocks) {
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t item[kScanItems];
+  uint32_t v = 0;
+  for (int i = 0; i < kScanItems; ++i) {
+    item[i] = base + i < n ? in[base + i] : 0;
+    v += item[i];
+  }
+  uint32_t total;
+  uint32_t run = sums[blockIdx.x] + block_exclusive_scan(v, &total);
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += item[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[n_blocks];
+}
+
+// ---- pass 2: one warp per tile writes its packet --------------------------------------------
+__global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const TileDesc* __restrict__ tiles,
+                                                           int64_t n_tiles, unsigned char* __restrict__ packets) {
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= n_tiles) return;
+  const TileDesc td = tiles[t];
+  const WfmWave w = P.waves[td.wave];
+  const TileLayout L = measure_tile(P, td, w);  // every lane, identical result
+  unsigned char* pk = packets + (size_t)P.pkt_off[t] * 16;
+  ARow* arows = reinterpret_cast<ARow*>(pk + sizeof(PacketHeader));
+  PatchRow* patches = reinterpret_cast<PatchRow*>(arows + (L.n_arows ? L.n_arows + 1 : 0));
+  DFactor* facs = reinterpret_cast<DFactor*>(patches + L.n_patch);
+  CTerm* cterms = reinterpret_cast<CTerm*>(facs + L.n_fac);
+  if (lane == 0) {
+    PacketHeader h;
+    h.out0 = td.out0;
+    h.j0 = td.j0;
+    h.base = w.offset;
+    h.t0 = w.t0;
+    h.delta = w.delta;
+    h.wave = td.wave;
+    h.flags = w.flags | (L.cold ? kPacketCold : 0u);
+    h.cnt = (uint16_t)td.cnt;
+    h.n_arows = L.cold ? 0 : (uint16_t)L.n_arows;
+    h.n_patch = L.cold ? 0 : (uint16_t)L.n_patch;
+    h.n_active = L.cold ? 0 : (uint16_t)L.n_active;
+    h.n_fac = L.cold ? 0 : (uint16_t)L.n_fac;
+    h.n_term = L.cold ? 0 : (uint16_t)L.n_term;
+    h.reserved = 0;
+    *reinterpret_cast<PacketHeader*>(pk) = h;
+  }
+  if (L.cold) return;
+  // rows: one sequential walk over the tile's segments (lane 0), table rows copied by all lanes
+  const int32_t* __restrict__ st = P.seg_start + w.seg_begin;
+  const int k0 = td.seg0 - w.seg_begin;
+  int ia = 0, ip = 0, fac_rel = 0, term_rel = 0, first = 0;
+  for (int k = k0; k < k0 + td.nb; ++k) {
+    int a, b;
+    seg_span(st, w.n_seg, w.n, k, td.j0, td.cnt, a, b);
+    if (b <= a) continue;
+    const WfmSegPtr p0 = P.seg_ptr[w.seg_begin + k], p1 = P.seg_ptr[w.seg_begin + k + 1];
+    if (p1.fac > p0.fac) {
+      if (lane == 0)
+        arows[ia] = ARow{(uint16_t)a, (uint16_t)first, (uint16_t)fac_rel, (uint16_t)term_rel, p0.fac, p0.term};
+      // factor rows without the NOP placeholders (order kept), 16 bytes per lane and step
+      int kept = 0;
+      for (int r = p0.fac; r < p1.fac; ++r) {
+        if ((((uint32_t)P.dfacs[r].func >> 16) & 0xff) == OP_NOP) continue;
+        if (lane < 4)
+          reinterpret_cast<uint4*>(facs + fac_rel + kept)[lane] = reinterpret_cast<const uint4*>(P.dfacs + r)[lane];
+        ++kept;
+      }
+      for (int q = lane; q < p1.term - p0.term; q += 32)
+        reinterpret_cast<uint4*>(cterms + term_rel)[q] = reinterpret_cast<const uint4*>(P.cterms + p0.term)[q];
+      ia += 1;
+      fac_rel += kept;
+      term_rel += p1.term - p0.term;
+      first += b - a;
+    } else {
+      const double v = P.seg_val[w.seg_begin + k];
+      if (__double_as_longlong(v) != __double_as_longlong(w.offset)) {
+        if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 0u, v};
+        ip += 1;
+      }
+    }
+  }
+  if (lane == 0 && L.n_arows)
+    arows[ia] = ARow{(uint16_t)td.cnt, (uint16_t)first, (uint16_t)fac_rel, (uint16_t)term_rel, 0, 0};  // sentinel
 }
 
 // ---- the sampling kernel ------------------------------------------------------------------
-// [a, b) of the shared tile <- val, executed by one warp
+// [a, b) of the warp's shared tile <- val
 template <typename OutT>
 __device__ __forceinline__ void fill_run(OutT* __restrict__ s_out, int a, int b, double val, int lane) {
   constexpr int V = OutVec<OutT>::N;
@@ -435,175 +633,186 @@ __device__ __forceinline__ void fill_run(OutT* __restrict__ s_out, int a, int b,
   for (int p = a_al + lane * V; p < b_al; p += 32 * V) fill_vec(s_out + p, val);
 }
 
+// per-warp shared-memory slice (dynamic shared memory; all sub-arrays 16-byte aligned):
+//   [out: tile_samples x OutT][slots: n_slots x 32 x f64][packet buffer 0][packet buffer 1][2 mbarriers]
+__host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int pkt_cap, size_t esz) {
+  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * 32 * 8 + 2 * (size_t)pkt_cap + 16;
+  return (b + 127) & ~(size_t)127;
+}
+
+// the cold path of a tile (its packet would not fit the warp's buffers): per-sample
+// search, tables in global memory, direct stores
+template <typename OutT, bool kAccumulate>
+__device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDesc& td, OutT* __restrict__ dst, int lane) {
+  const WfmWave w = P.waves[td.wave];
+  const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
+  const IrGlobal g{P.dfacs, P.terms, P.refs, P.args};
+  const int32_t* __restrict__ st = P.seg_start + td.seg0;
+  const WfmSegPtr* __restrict__ gp = P.seg_ptr + td.seg0;
+  for (int jj = lane; jj < td.cnt; jj += 32) {
+    int lo = 0, hi = td.nb - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
+    }
+    const WfmSegPtr p0 = gp[lo], p1 = gp[lo + 1];
+    LocalSlots vals;
+    const double re = eval_segment_real(P.dfacs + p0.fac, P.cterms + p0.term, min(p1.fac - p0.fac, kMaxSlots),
+                                        p1.term - p0.term, g, p0.fac, p0.term, we, abscissa(w, P.x, td.j0 + jj), vals);
+    dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
+  }
+}
+
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
 template <typename OutT, bool kAccumulate>
-__global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS) sample_kernel(DevProgram P, const TileDesc* __restrict__ tiles,
-                                                          OutT* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
+    sample_kernel(DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end, OutT* __restrict__ out) {
   constexpr int V = OutVec<OutT>::N;
-  // dynamic: [tile: tile_samples x OutT][value slots: n_slots x 256 x f64][IR slice: ir_bytes]
-  OutT* s_out = reinterpret_cast<OutT*>(k1_smem);
-  double* s_slots = reinterpret_cast<double*>(k1_smem + (size_t)P.tile_samples * sizeof(OutT));
-  unsigned char* s_ir = reinterpret_cast<unsigned char*>(s_slots + (size_t)P.n_slots * kThreads);
-  __shared__ WfmSegPtr s_ptr[kStageSegs + 1];
-  __shared__ double s_val[kStageSegs];           // value of a FLAT segment
-  __shared__ uint16_t s_start[kStageSegs + 1];   // first tile-sample of staged segment k
-  __shared__ uint16_t s_act[kStageSegs + 1];     // active samples before staged segment k
-  __shared__ uint16_t s_patch[kStageSegs];       // flat, non-empty segments whose value differs from the base fill
-  __shared__ int s_npatch;
-  __shared__ WfmWave s_wave;
-  __shared__ uint64_t s_bar;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  // this warp's private slice
+  unsigned char* slice = k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, sizeof(OutT));
+  OutT* s_out = reinterpret_cast<OutT*>(slice);
+  double* s_slots = reinterpret_cast<double*>(slice + (size_t)P.tile_samples * sizeof(OutT));
+  unsigned char* s_pkt = reinterpret_cast<unsigned char*>(s_slots + (size_t)P.n_slots * 32);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
 
-  const TileDesc td = tiles[blockIdx.x];
-  const int cnt = td.cnt;
-  const int nb = td.nb;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  OutT* __restrict__ dst = out + td.out0;
   const IrGlobal g{P.dfacs, P.terms, P.refs, P.args};
+  SmemSlots vals{s_slots + lane};
+  const int n_warps = gridDim.x * kWarpsPerCta;
+  int t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
+  if (t >= tile_end) return;
 
-  const uint32_t bf = (uint32_t)td.n_fac * sizeof(DFactor), bt = (uint32_t)td.n_term * sizeof(CTerm);
-  if (nb > kStageSegs || (td.n_fac > 0 && bf + bt > (uint32_t)P.ir_bytes)) {
-    // pathological density (> 256 segment rows, or a table slice beyond the shared-memory
-    // budget, in one tile): per-sample search, tables in global memory, direct stores
-    const WfmWave w = P.waves[td.wave];
-    const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
-    const int32_t* __restrict__ st = P.seg_start + td.seg0;
-    const WfmSegPtr* __restrict__ gp = P.seg_ptr + td.seg0;
-    for (int jj = threadIdx.x; jj < cnt; jj += kThreads) {
-      int lo = 0, hi = nb - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
-      }
-      const WfmSegPtr p0 = gp[lo], p1 = gp[lo + 1];
-      LocalSlots vals;
-      const double re = eval_segment_real(P.dfacs + p0.fac, P.cterms + p0.term, p1.fac - p0.fac, p1.term - p0.term, g,
-                                          p0.fac, p0.term, we, abscissa(w, P.x, td.j0 + jj), vals);
-      dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
-    }
-    return;
-  }
-
-  // ---- prologue ------------------------------------------------------------------------
-  const bool staged = td.n_fac > 0;
-  if (threadIdx.x == 0 && staged) {
-    // the tile's slice of the factor and compact-term tables: one TMA bulk copy each
-    mbar_init(&s_bar, 1);
+  if (lane == 0) {
+    mbar_init(s_bar, 1);
+    mbar_init(s_bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&s_bar, bf + bt);
-    bulk_g2s(s_ir, P.dfacs + td.fac0, bf, &s_bar);
-    bulk_g2s(s_ir + bf, P.cterms + td.term0, bt, &s_bar);
   }
-  const double base = P.waves[td.wave].offset;  // value of every zero segment
+  s_slots[lane] = 1.0;  // physical slot 0: the unit a missing term reference multiplies by
+  __syncwarp();
+
+  // packet of the first tile -> buffer 0; offsets of the second tile -> registers
+  uint32_t off_next = 0, end_next = 0;  // packet of tile t + n_warps, 16-byte units
   {
-    // segment rows of the tile (nothing here depends on the channel record)
-    const int32_t* __restrict__ gs = P.seg_start + td.seg0;
-    const double* __restrict__ gv = P.seg_val + td.seg0;
-    const WfmSegPtr* __restrict__ gp = P.seg_ptr + td.seg0;
-    for (int k = threadIdx.x; k <= nb; k += kThreads) {
-      s_ptr[k] = gp[k];
-      int pos;
-      if (k == 0) pos = 0;
-      else if (k == nb) pos = cnt;
-      else pos = (int)min((int64_t)cnt, max((int64_t)0, (int64_t)gs[k] - td.j0));
-      s_start[k] = (uint16_t)pos;
-      if (k < nb) s_val[k] = gv[k];
+    const uint32_t o0 = P.pkt_off[t], o1 = P.pkt_off[t + 1];
+    if (lane == 0) {
+      mbar_expect_tx(s_bar, (o1 - o0) * 16u);
+      bulk_g2s(s_pkt, P.packets + (size_t)o0 * 16, (o1 - o0) * 16u, s_bar);
     }
-    if (threadIdx.x >= kThreads - (int)(sizeof(WfmWave) / 8)) {
-      const int q = threadIdx.x - (kThreads - (int)(sizeof(WfmWave) / 8));
-      reinterpret_cast<uint64_t*>(&s_wave)[q] = reinterpret_cast<const uint64_t*>(P.waves + td.wave)[q];
+    if (t + n_warps < tile_end) {
+      off_next = P.pkt_off[t + n_warps];
+      end_next = P.pkt_off[t + n_warps + 1];
     }
   }
-  // base fill: the whole tile <- the zero-segment value; flat segments with another
-  // value and the active samples overwrite it below
-  {
-    const int n_fill = (cnt + V - 1) & ~(V - 1);  // the tile buffer is a multiple of V
+  uint32_t phases = 0;         // bit b: parity to wait for on buffer b
+  int buf = 0;
+  bool store_pending = false;  // lane 0: a bulk store may still be reading s_out
+
 #pragma unroll 1
-    for (int p = threadIdx.x * V; p < n_fill; p += kThreads * V) fill_vec(s_out + p, base);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // exclusive prefix of ACTIVE sample counts over the staged segments
-    int carry = 0;
-    for (int b0 = 0; b0 < nb; b0 += 32) {
-      const int k = b0 + lane;
-      int c = 0;
-      if (k < nb && s_ptr[k + 1].fac > s_ptr[k].fac) c = (int)s_start[k + 1] - (int)s_start[k];
-      int incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+  for (; t < tile_end; t += n_warps) {
+    const unsigned char* pk = s_pkt + (size_t)buf * P.pkt_cap;
+    // prefetch: the next tile's packet into the other buffer (its previous tile is done:
+    // every lane passed the __syncwarp that ends an iteration), the offsets of the tile after
+    if (t + n_warps < tile_end) {
+      if (lane == 0) {
+        mbar_expect_tx(s_bar + (buf ^ 1), (end_next - off_next) * 16u);
+        bulk_g2s(s_pkt + (size_t)(buf ^ 1) * P.pkt_cap, P.packets + (size_t)off_next * 16, (end_next - off_next) * 16u,
+                 s_bar + (buf ^ 1));
       }
-      if (k < nb) s_act[k] = (uint16_t)(carry + incl - c);
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (t + 2 * n_warps < tile_end) {
+        off_next = P.pkt_off[t + 2 * n_warps];
+        end_next = P.pkt_off[t + 2 * n_warps + 1];
+      }
     }
-    if (lane == 0) s_act[nb] = (uint16_t)carry;
-  } else if (warp == 1) {
-    // compacted list of the flat segments the base fill did not already serve
-    int n = 0;
-    for (int b0 = 0; b0 < nb; b0 += 32) {
-      const int k = b0 + lane;
-      bool need = false;
-      if (k < nb && s_start[k + 1] > s_start[k] && s_ptr[k + 1].fac == s_ptr[k].fac)
-        need = __double_as_longlong(s_val[k]) != __double_as_longlong(base);
-      const unsigned m = __ballot_sync(0xffffffffu, need);
-      if (need) s_patch[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
-      n += __popc(m);
-    }
-    if (lane == 0) s_npatch = n;
-  }
-  __syncthreads();
+    mbar_wait(s_bar + buf, (phases >> buf) & 1u);
+    phases ^= 1u << buf;
 
-  // ---- flat segments with their own value: one warp per run ------------------------------
-  {
-    const int n_patch = s_npatch;
-    for (int i = warp; i < n_patch; i += kThreads / 32) {
-      const int k = s_patch[i];
-      fill_run(s_out, (int)s_start[k], (int)s_start[k + 1], s_val[k], lane);
-    }
-  }
+    const PacketHeader* __restrict__ h = reinterpret_cast<const PacketHeader*>(pk);
+    const int cnt = h->cnt;
+    const uint32_t flags = h->flags;
+    const int n_arows = h->n_arows, n_patch = h->n_patch, n_active = h->n_active;
+    const double base = h->base;
+    OutT* __restrict__ dst = out + h->out0;
 
-  // ---- the tile's ACTIVE samples, dealt evenly to all threads ------------------------------
-  const int n_active = s_act[nb];
-  if (staged) mbar_wait(&s_bar, 0);  // also guarantees no copy is in flight when the CTA retires
-  if (n_active > 0) {
-    const WaveEval we{s_wave.offset, s_wave.clip_lo, s_wave.clip_hi, s_wave.flags};
-    const uint32_t wflags = s_wave.flags;
-    const double t0 = s_wave.t0, delta = s_wave.delta;
-    const bool plain_grid = !(wflags & (WFM_WAVE_EXPLICIT_X | WFM_WAVE_LAST_OVERRIDE | WFM_WAVE_PRESHIFT));
-    SmemSlots vals{s_slots + threadIdx.x};
-    const DFactor* __restrict__ sf = reinterpret_cast<const DFactor*>(s_ir);
-    const CTerm* __restrict__ sc = reinterpret_cast<const CTerm*>(s_ir + bf);
+    if (flags & kPacketCold) {
+      sample_tile_cold<OutT, kAccumulate>(P, tiles[t], dst, lane);
+      __syncwarp();
+      buf ^= 1;
+      continue;
+    }
+
+    // the previous tile's bulk store must have finished READING the tile buffer
+    if (lane == 0 && store_pending) bulk_wait_read_all();
+    __syncwarp();
+
+    // base fill: the whole tile <- the zero-segment value; flat segments with another
+    // value and the active samples overwrite it below
+    {
+      const int n_fill = (cnt + V - 1) & ~(V - 1);  // the tile buffer is a multiple of V
+      int p = lane * V;
 #pragma unroll 1
-    for (int i = threadIdx.x; i < n_active; i += kThreads) {
-      int lo = 0, hi = nb - 1;  // last k with s_act[k] <= i: the active segment holding sample i
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_act[mid] <= i) lo = mid; else hi = mid - 1;
+      for (; p + 3 * 32 * V < n_fill; p += 4 * 32 * V) {
+        fill_vec(s_out + p, base);
+        fill_vec(s_out + p + 32 * V, base);
+        fill_vec(s_out + p + 2 * 32 * V, base);
+        fill_vec(s_out + p + 3 * 32 * V, base);
       }
-      const int jj = (int)s_start[lo] + (i - (int)s_act[lo]);
-      const double x = plain_grid ? add(t0, mul((double)(td.j0 + jj), delta)) : abscissa(s_wave, P.x, td.j0 + jj);
-      const WfmSegPtr p0 = s_ptr[lo], p1 = s_ptr[lo + 1];
-      s_out[jj] = (OutT)eval_segment_real(sf + (p0.fac - td.fac0), sc + (p0.term - td.term0), p1.fac - p0.fac,
-                                          p1.term - p0.term, g, p0.fac, p0.term, we, x, vals);
+#pragma unroll 1
+      for (; p < n_fill; p += 32 * V) fill_vec(s_out + p, base);
     }
-  }
+    __syncwarp();
 
-  // ---- store ---------------------------------------------------------------------------------
-  if (kAccumulate) {
-    // out += tile (Waveform.__call__(..., accumulate=True)): read-modify-write epilogue
-    __syncthreads();
-    for (int p = threadIdx.x; p < cnt; p += kThreads) dst[p] = (OutT)add((double)dst[p], (double)s_out[p]);
-    return;
+    const ARow* __restrict__ arows = reinterpret_cast<const ARow*>(pk + sizeof(PacketHeader));
+    const PatchRow* __restrict__ patches = reinterpret_cast<const PatchRow*>(arows + (n_arows ? n_arows + 1 : 0));
+    // ---- flat segments with their own value ----------------------------------------------
+    for (int i = 0; i < n_patch; ++i) fill_run(s_out, (int)patches[i].a, (int)patches[i].b, patches[i].val, lane);
+
+    // ---- the tile's ACTIVE samples, dealt round-robin to the lanes ------------------------
+    if (n_active > 0) {
+      const DFactor* __restrict__ sf = reinterpret_cast<const DFactor*>(patches + n_patch);
+      const CTerm* __restrict__ sc = reinterpret_cast<const CTerm*>(sf + h->n_fac);
+      WaveEval we{base, 0.0, 0.0, flags};
+      if (flags & WFM_WAVE_CLIP) {
+        we.clip_lo = P.waves[h->wave].clip_lo;
+        we.clip_hi = P.waves[h->wave].clip_hi;
+      }
+      const double t0 = h->t0, delta = h->delta;
+      const int64_t j0 = h->j0;
+      const bool plain_grid = !(flags & (WFM_WAVE_EXPLICIT_X | WFM_WAVE_LAST_OVERRIDE | WFM_WAVE_PRESHIFT));
+      int lo = 0;
+#pragma unroll 1
+      for (int i = lane; i < n_active; i += 32) {
+        while ((int)arows[lo + 1].first <= i) ++lo;  // the active segment holding sample i (i grows monotonically)
+        const ARow r0 = arows[lo];
+        const int fac_end = arows[lo + 1].fac_rel, term_end = arows[lo + 1].term_rel;
+        const int jj = (int)r0.start + (i - (int)r0.first);
+        const double x = plain_grid ? add(t0, mul((double)(j0 + jj), delta)) : abscissa(P.waves[h->wave], P.x, j0 + jj);
+        s_out[jj] = (OutT)eval_segment_real(sf + r0.fac_rel, sc + r0.term_rel, fac_end - (int)r0.fac_rel,
+                                            term_end - (int)r0.term_rel, g, r0.gfac, r0.gterm, we, x, vals);
+      }
+    }
+
+    // ---- store ---------------------------------------------------------------------------
+    if (kAccumulate) {
+      // out += tile (Waveform.__call__(..., accumulate=True)): read-modify-write epilogue
+      __syncwarp();
+      for (int p = lane; p < cnt; p += 32) dst[p] = (OutT)add((double)dst[p], (double)s_out[p]);
+    } else {
+      // the whole tile as one TMA bulk copy
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int n_bulk = cnt & ~(V - 1);  // 16-byte multiple; the ragged tail goes out as scalars
+      if (lane == 0 && n_bulk > 0) {
+        bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT));
+        store_pending = true;
+      }
+      if (n_bulk + lane < cnt) dst[n_bulk + lane] = s_out[n_bulk + lane];
+    }
+    __syncwarp();  // all reads of the packet and of the tail of s_out are done
+    buf ^= 1;
   }
-  // the whole tile as one TMA bulk copy
-  fence_proxy_async_smem();
-  __syncthreads();
-  const int n_bulk = cnt & ~(V - 1);  // 16-byte multiple; the ragged tail goes out as scalars
-  if (threadIdx.x == 0 && n_bulk > 0) bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT));
-  if (n_bulk + (int)threadIdx.x < cnt) dst[n_bulk + threadIdx.x] = s_out[n_bulk + threadIdx.x];
-  if (threadIdx.x == 0) bulk_wait_read_all();  // shared memory must outlive the copy's reads
+  if (lane == 0 && store_pending) bulk_wait_read_all();  // shared memory must outlive the copy's reads
 }
 
 // complex128 output: interleaved (re, im); one sample per thread per row.
@@ -636,39 +845,69 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
 }
 
 cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, int32_t* seg_start, double* seg_val,
-                           DFactor* dfacs, CTerm* cterms, TileDesc* tiles, int* max_ir_bytes, cudaStream_t stream) {
+                           DFactor* dfacs, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size, cudaStream_t stream) {
   const int threads = 128;
   auto blocks = [&](int64_t items) { return (unsigned)((items + threads - 1) / threads); };
   if (n.n_segs > 0) prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, seg_start, seg_val, n.n_segs);
-  if (n.n_facs > 0) prepare_factors_kernel<<<blocks(n.n_facs), threads, 0, stream>>>(P, dfacs, n.n_facs);
+  if (n.n_facs > 0) prepare_factors_kernel<<<blocks(n.n_facs), threads, 0, stream>>>(P, dfacs, n.n_facs, n.n_segs);
   if (n.n_terms > 0) prepare_terms_kernel<<<blocks(n.n_terms), threads, 0, stream>>>(P, cterms, n.n_terms);
-  if (n.n_tiles > 0) prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, tiles, n.n_tiles, max_ir_bytes);
+  if (n.n_tiles > 0) prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, tiles, n.n_tiles, pkt_size);
   return cudaGetLastError();
 }
 
-size_t sample_smem_bytes(const DevProgram& P, int dtype) {
-  const size_t esz = dtype == WFM_F32 ? 4 : 8;
-  return (size_t)P.tile_samples * esz + (size_t)P.n_slots * kThreads * sizeof(double) + (size_t)P.ir_bytes;
+cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* scratch, int64_t n, cudaStream_t stream) {
+  const int64_t n_blocks = (n + kScanTile - 1) / kScanTile;
+  if (n_blocks == 0) return cudaMemsetAsync(pkt_off, 0, sizeof(uint32_t), stream);
+  scan_reduce_kernel<<<(unsigned)n_blocks, kScanBlock, 0, stream>>>(pkt_size, scratch, n);
+  scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(scratch, n_blocks);
+  scan_apply_kernel<<<(unsigned)n_blocks, kScanBlock, 0, stream>>>(pkt_size, scratch, pkt_off, n, n_blocks);
+  return cudaGetLastError();
 }
 
-cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t n_tiles, int dtype, int accumulate,
-                          void* out, cudaStream_t stream) {
+cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int64_t n_tiles, unsigned char* packets,
+                                cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
-  dim3 grid((unsigned)n_tiles), block(kThreads);
+  fill_packets_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, stream>>>(P, tiles, n_tiles, packets);
+  return cudaGetLastError();
+}
+
+int warp_fixed_bytes(int n_slots) { return n_slots * 32 * 8 + 16 + 128; }
+
+size_t sample_smem_bytes(const DevProgram& P, int dtype) {
+  return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
+}
+
+template <typename OutT, bool kAcc>
+static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                                     int dtype, void* out, cudaStream_t stream) {
+  auto k = sample_kernel<OutT, kAcc>;
   const size_t smem = sample_smem_bytes(P, dtype);
-  cudaError_t e = cudaSuccess;
-  if (dtype == WFM_F64) {
-    auto k = accumulate ? sample_kernel<double, true> : sample_kernel<double, false>;
-    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k<<<grid, block, smem, stream>>>(P, tiles, (double*)out);
-  } else if (dtype == WFM_F32) {
-    auto k = accumulate ? sample_kernel<float, true> : sample_kernel<float, false>;
-    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-    k<<<grid, block, smem, stream>>>(P, tiles, (float*)out);
-  } else {
-    if (accumulate) sample_kernel_c128<true><<<grid, block, 0, stream>>>(P, tiles, (double2*)out);
-    else sample_kernel_c128<false><<<grid, block, 0, stream>>>(P, tiles, (double2*)out);
-  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per_sm = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem)) != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  const int64_t want = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);
+  k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
+                          int accumulate, void* out, cudaStream_t stream) {
+  if (n_tiles == 0) return cudaSuccess;
+  if (tile_begin + n_tiles > INT32_MAX) return cudaErrorInvalidValue;
+  if (dtype == WFM_F64)
+    return accumulate ? launch_persistent<double, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+                      : launch_persistent<double, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  if (dtype == WFM_F32)
+    return accumulate ? launch_persistent<float, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+                      : launch_persistent<float, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  dim3 grid((unsigned)n_tiles), block(kThreads);
+  if (accumulate) sample_kernel_c128<true><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
+  else sample_kernel_c128<false><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
   return cudaGetLastError();
 }
 
