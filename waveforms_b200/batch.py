@@ -93,3 +93,39 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
             table.append((slot, int(batch.waves['out_off'][k]),
                           int(batch.waves['n'][k])))
     return BatchResult(tensors, table, dtype)
+
+
+def rank_shard(weights, rank=None, world=None):
+    """The contiguous channel range ``(lo, hi)`` this process owns when the job
+    runs as one process per GPU (torchrun): RANK / WORLD_SIZE from the
+    environment unless given.  Every rank computes the same partition from the
+    same weights, so no exchange is needed to agree on it."""
+    import os
+    rank = int(os.environ.get('RANK', '0')) if rank is None else int(rank)
+    world = int(os.environ.get('WORLD_SIZE', '1')) if world is None else int(world)
+    if not 0 <= rank < world:
+        raise ValueError(f'rank {rank} outside world of {world}')
+    return shard_ranges(weights, world)[rank]
+
+
+def lower_rank_shard(waveforms, rank=None, world=None, sample_rate=None):
+    """Host half of the one-process-per-GPU path: lower only this rank's shard.
+    Returns ``(lo, hi, LoweredBatch)``; ``sample_batch_rank`` runs it."""
+    items = [channel_grid(w, sample_rate) for w in waveforms]
+    lo, hi = rank_shard([g.n for _, g in items], rank, world)
+    return lo, hi, lower(items[lo:hi])
+
+
+def sample_batch_rank(waveforms, rank=None, world=None, sample_rate=None,
+                      dtype=np.float64, device=None, filters='own'):
+    """One process per GPU: sample this rank's shard of ``waveforms`` on
+    ``device`` (default: LOCAL_RANK).  Returns ``(lo, hi, BatchResult)`` with the
+    result's channel ``i`` = ``waveforms[lo + i]``.  No collective is issued."""
+    import os
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    lo, hi = rank_shard([channel_grid(w, sample_rate)[1].n for w in waveforms],
+                        rank, world)
+    res = sample_batch(waveforms[lo:hi], sample_rate=sample_rate, dtype=dtype,
+                       devices=[device], filters=filters)
+    return lo, hi, res
