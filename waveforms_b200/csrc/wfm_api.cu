@@ -82,7 +82,8 @@ struct WfmProgram {
     cudaFree((void*)dev.facs);
     cudaFree((void*)dev.terms);
     cudaFree((void*)dev.cterms);
-    cudaFree((void*)dev.dfacs);
+    cudaFree((void*)dev.seg_plan);
+    cudaFree((void*)dev.row_slot);
     cudaFree((void*)dev.refs);
     cudaFree((void*)dev.args);
     cudaFree((void*)dev.x);
@@ -137,8 +138,8 @@ static int validate(const WfmProgramDesc* d) {
     for (int k = 0; k < nf; ++k) {
       const WfmFactor& f = d->facs[a.fac + k];
       if (f.func == WFM_COS_SINCOS) {
-        if (k + 1 >= nf || k + 1 >= wfm::kMaxSlots || d->facs[a.fac + k + 1].func != WFM_NOP)
-          return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it inside the value cache", (long long)s, k);
+        if (k + 1 >= nf || d->facs[a.fac + k + 1].func != WFM_NOP)
+          return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it", (long long)s, k);
       } else if (f.func == WFM_NOP) {
         if (k == 0 || d->facs[a.fac + k - 1].func != WFM_COS_SINCOS)
           return fail(WFM_EINVAL, "segment %lld: stray NOP row %d", (long long)s, k);
@@ -146,7 +147,7 @@ static int validate(const WfmProgramDesc* d) {
         if (f.arg_off + 5 > d->n_args) return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: pool out of range", (long long)s, k);
         const double bs = d->args[f.arg_off];
         const int base = (int)bs;
-        if (!(bs >= 0) || base >= k || k >= wfm::kMaxSlots || d->facs[a.fac + base].func != WFM_COS_SINCOS ||
+        if (!(bs >= 0) || base >= k || d->facs[a.fac + base].func != WFM_COS_SINCOS ||
             d->facs[a.fac + base].a0 != f.a0)
           return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: bad base row", (long long)s, k);
       }
@@ -240,15 +241,18 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
   int32_t* d_seg_start = nullptr;
   double* d_seg_val = nullptr;
-  wfm::DFactor* d_dfacs = nullptr;
+  wfm::SegPlan* d_seg_plan = nullptr;
+  uint8_t* d_row_slot = nullptr;
   wfm::CTerm* d_cterms = nullptr;
   if (e == cudaSuccess) e = cudaMalloc(&d_seg_start, sizeof(int32_t) * (size_t)std::max<int64_t>(d->n_segs, 1));
   if (e == cudaSuccess) e = cudaMalloc(&d_seg_val, sizeof(double) * (size_t)std::max<int64_t>(d->n_segs, 1));
-  if (e == cudaSuccess) e = cudaMalloc(&d_dfacs, sizeof(wfm::DFactor) * (size_t)std::max<int64_t>(d->n_facs, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_seg_plan, sizeof(wfm::SegPlan) * (size_t)std::max<int64_t>(d->n_segs, 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_row_slot, (size_t)std::max<int64_t>(d->n_facs, 16));
   if (e == cudaSuccess) e = cudaMalloc(&d_cterms, sizeof(wfm::CTerm) * (size_t)std::max<int64_t>(d->n_terms, 1));
   p->dev.seg_start = d_seg_start;
   p->dev.seg_val = d_seg_val;
-  p->dev.dfacs = d_dfacs;
+  p->dev.seg_plan = d_seg_plan;
+  p->dev.row_slot = d_row_slot;
   p->dev.cterms = d_cterms;
 
   // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample),
@@ -260,8 +264,8 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     int64_t samples = 0;
     for (int64_t w = 0; w < d->n_waves; ++w) samples += d->waves[w].n;
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
-    const double ir = ((double)d->n_facs * sizeof(wfm::DFactor) + (double)d->n_terms * sizeof(wfm::CTerm) +
-                       (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
+    const double ir = ((double)d->n_facs * 40.0 /* SRow 16, RRow 64, GRow 32; NOP rows vanish */ +
+                       (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
     const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
     int ts = wfm::kMaxTileSamples, cap = 0;
     for (;; ts -= 128) {
@@ -280,7 +284,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     p->tile_prefix[w] = (int64_t)tiles.size();
     const WfmWave& wv = d->waves[w];
     for (int64_t j = 0; j < wv.n; j += tile_samples)
-      tiles.push_back({j, wv.out_off + j, (int32_t)w, (int32_t)std::min<int64_t>(tile_samples, wv.n - j), 0, 0, 0, 0, 0, 0});
+      tiles.push_back({j, wv.out_off + j, (int32_t)w, (int32_t)std::min<int64_t>(tile_samples, wv.n - j), 0, 0});
     total = std::max(total, wv.out_off + wv.n);
     if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
   }
@@ -307,7 +311,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->dev.pkt_off = d_pkt_off;
   if (e == cudaSuccess)
     e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_segs, d->n_facs, d->n_terms, p->n_tiles}, d_seg_start,
-                            d_seg_val, d_dfacs, d_cterms, p->d_tiles, d_pkt_size, 0);
+                            d_seg_val, d_seg_plan, d_row_slot, d_cterms, p->d_tiles, d_pkt_size, 0);
   if (e == cudaSuccess) e = wfm::launch_scan(d_pkt_size, d_pkt_off, d_scratch, p->n_tiles, 0);
   uint32_t total16 = 0;
   if (e == cudaSuccess) e = cudaMemcpy(&total16, d_pkt_off + p->n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost);

@@ -9,58 +9,89 @@ namespace wfm {
 // samples per tile of the sampling kernel.  A tile is assembled by ONE WARP in its
 // private slice of shared memory (tile_samples x 8 B) and stored with one TMA bulk
 // copy.  Chosen per program from the table density: dense programs take smaller
-// tiles so that the tile's segment rows (<= kStageSegs) and its slice of the
-// factor / term tables fit the warp's slice.
+// tiles so that the tile's packet fits the warp's slice.
 #ifndef WFM_K1_MIN_BLOCKS
 #define WFM_K1_MIN_BLOCKS 2  // resident 8-warp CTAs per SM the kernel is sized for
 #endif
 #ifndef WFM_K1_MAX_TILE
 #define WFM_K1_MAX_TILE 1024
 #endif
+// samples one lane evaluates together (a UNIT: consecutive samples of one active
+// segment).  Two independent dependency chains per lane hide the fp64 latencies the
+// interpreter is bound by at 16 warps per SM, and the row decoding is paid once per
+// unit instead of once per sample.
+#ifndef WFM_K1_UNIT
+#define WFM_K1_UNIT 2
+#endif
+constexpr int kUnit = WFM_K1_UNIT;
 constexpr int kMinTileSamples = 128;
 constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
 // shared memory per warp: 8 * WFM_K1_MIN_BLOCKS warps share the SM's 227 KB (1 KB per CTA is reserved)
 constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024) / 8) & ~127;
 
-// Compact term built on the device at upload from WfmTerm + WfmRef: amplitude and up
-// to three factor slots with exponent 1 in ONE 16-byte record (one load per term in
-// the interpreter).  packed: bits 0..7 flags, 8..15 / 16..23 / 24..31 PHYSICAL value
-// slots of the three references; a missing reference points at physical slot 0, which
-// always holds 1.0 (x * 1.0 is exact), so the product needs no loop and no branch.
-// Terms that do not fit (more refs, an exponent != 1, a slot beyond the value cache)
-// carry kCTermExt and are read from the ABI tables.
+// Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of kUnit
+// doubles in the warp's shared slice, slot-major (slot k of lane l at byte
+// k * kSlotStride + l * 8 * kUnit: conflict-free).  Slot 0 always holds 1.0.
+constexpr int kMaxSlots = 12;
+constexpr int kSlotStride = 32 * 8 * kUnit;  // bytes between consecutive slots
+
+// ---- the device program of ONE active segment (built on the device at upload) ------------
+// The ABI factor rows of a segment are regrouped BY CLASS so that the interpreter runs
+// three tight loops and decodes no opcode on the hot rows:
+//   SRow[n_sc]   WFM_COS_SINCOS: slots 1+2i (cos) and 2+2i (sin)       <- sincos(w * (x - shift))
+//   RRow[n_rot]  WFM_COS_ROT   : slot 1+2 n_sc+j   <- cos(w * (x - shift)) by rotation of its base
+//   GRow[n_gen]  everything else: slot 1+2 n_sc+n_rot+k  (switch on the basis id)
+//   CTerm[n_term]
+// WFM_NOP rows (the sine placeholders of the ABI) vanish.
+struct SRow {
+  double shift, w;
+};
+static_assert(sizeof(SRow) == 16, "SRow layout");
+
+struct RRow {
+  double shift, w;
+  double bshift;     // shift of the base WFM_COS_SINCOS row
+  double D, cD, sD;  // D ~ w * (bshift - shift) and its cosine / sine (host constants)
+  uint32_t base_off; // byte offset of the base row's cosine slot (its sine follows at + kSlotStride)
+  uint32_t pad0;
+  double pad1;
+};
+static_assert(sizeof(RRow) == 64, "RRow layout");
+
+struct GRow {
+  int32_t func;     // WFM_* basis id
+  int32_t arg_off;  // its block in the argument pool (global memory)
+  double shift, a0, a1;
+};
+static_assert(sizeof(GRow) == 32, "GRow layout");
+
+// amp * v[o0] * v[o1] * v[o2]: up to three exponent-1 references as BYTE offsets of
+// their value slots; a missing reference points at slot 0 (1.0; x * 1.0 is exact),
+// so the product needs no loop and no branch.  Terms that do not fit (more
+// references, an exponent != 1) carry kCTermExt and are read from the ABI tables.
 struct CTerm {
   double amp;
-  uint64_t packed;
+  uint16_t o0, o1, o2;
+  uint16_t flags;
 };
 static_assert(sizeof(CTerm) == 16, "CTerm layout");
 constexpr uint32_t kCTermGroupEnd = 1, kCTermExt = 2;
-constexpr int kMaxSlots = 12;  // distinct factor values cached per segment evaluation (physical slots 1..12)
 
-// interpreter op of a factor row (upper 16 bits of DFactor::func), hottest first
-enum : int { OP_ROT = 0, OP_SINCOS = 1, OP_NOP = 2, OP_COS = 3, OP_LINEAR = 4, OP_GAUSSIAN = 5, OP_ERF = 6, OP_GENERIC = 7 };
-
-// Device factor row built at upload from WfmFactor (+ its argument-pool block for
-// the rotation rows): everything the hot basis functions need in ONE 64-byte row
-// that is staged in shared memory with the tile.
-//   WFM_COS_ROT: aux = base slot, p = {base_shift, D, cos D, sin D}
-//   others     : aux = arg_off (argument pool stays in global memory)
-// func = WFM_* id | OP_* << 16
-struct DFactor {
-  int32_t func;
-  int32_t aux;
-  double shift;
-  double a0, a1;
-  double p[4];
+// per segment, parallel to the ABI segment table
+struct SegPlan {
+  uint8_t n_sc, n_rot, n_gen, flags;
+  uint16_t n_term;
+  uint16_t blk16;  // bytes / 16 of its rows + terms in a packet (0 for a wide segment)
 };
-static_assert(sizeof(DFactor) == 64, "DFactor layout");
-
+static_assert(sizeof(SegPlan) == 8, "SegPlan layout");
+// more value slots / terms than the hot path holds: evaluated row by row from the ABI tables
+constexpr uint32_t kSegWide = 1;
 
 // ---- tile packets: the device IR the sampling kernel executes ------------------------------
 // Built once per program on the device.  A packet is everything ONE tile needs,
 // contiguous in global memory (16-byte aligned, size a multiple of 16) so that a
 // warp brings it into shared memory with ONE TMA bulk copy:
-//   PacketHeader | ARow[n_arows + 1] | PatchRow[n_patch] | DFactor[n_fac] | CTerm[n_term]
+//   PacketHeader | ARow[n_arows + 1] | PatchRow[n_patch] | per active segment: SRow.. RRow.. GRow.. CTerm..
 // Zero segments do not appear at all: the kernel fills the tile with `base` first.
 struct PacketHeader {
   int64_t out0;   // index of the tile's first sample in the output buffer
@@ -72,22 +103,20 @@ struct PacketHeader {
   uint16_t cnt;      // samples in the tile
   uint16_t n_arows;  // active segments intersecting the tile
   uint16_t n_patch;  // flat segments whose value differs from `base`
-  uint16_t n_active; // active samples
-  uint16_t n_fac;    // factor rows in the packet
-  uint16_t n_term;   // compact terms in the packet
-  uint32_t reserved;
+  uint16_t n_units;  // units (kUnit consecutive samples of one active segment) in the tile
+  uint32_t reserved[2];
 };
 static_assert(sizeof(PacketHeader) == 64, "PacketHeader layout");
 constexpr uint32_t kPacketCold = 0x80000000u;  // header only: the tile takes the global-table path
 
 // one ACTIVE segment of the tile; row n_arows is a sentinel closing the ranges
 struct ARow {
-  uint16_t start;     // first tile-sample of the segment
-  uint16_t first;     // active samples of the tile before this segment
-  uint16_t fac_rel;   // its first factor row within the packet
-  uint16_t term_rel;  // its first compact term within the packet
-  int32_t gfac;       // the same rows in the global tables (extended terms only)
-  int32_t gterm;
+  uint16_t start;  // first tile-sample of the segment
+  uint16_t first;  // units of the tile before this segment
+  uint16_t rel;    // bits 0..11: offset / 16 of its rows within the packet; bits 12..15: SegPlan flags
+  uint16_t len;    // its samples inside the tile
+  uint8_t n_sc, n_rot, n_gen, n_term;
+  int32_t gseg;    // absolute segment row (extended terms, wide segments)
 };
 static_assert(sizeof(ARow) == 16, "ARow layout");
 
@@ -104,46 +133,46 @@ struct DevProgram {
   const WfmWave* waves;
   const double* seg_bound;
   const WfmSegPtr* seg_ptr;
-  const WfmFactor* facs;   // ABI rows (pre-pass only)
+  const WfmFactor* facs;   // ABI rows
   const WfmTerm* terms;
   const WfmRef* refs;
   const double* args;
   const double* x;
   // built on the device once per program (prepare kernels):
-  const DFactor* dfacs;      // parallel to facs
+  const SegPlan* seg_plan;   // [n_segs]
+  const uint8_t* row_slot;   // [n_facs] value slot of every ABI factor row (0 for WFM_NOP rows)
   const CTerm* cterms;       // parallel to terms
   const int32_t* seg_start;  // [n_segs] first sample (channel-relative) owned by the segment
   const double* seg_val;     // [n_segs] value of a FLAT segment (offset + constant terms, clipped)
   const int32_t* seg_wave;   // [n_segs] owning channel (host-built; pre-pass only)
   const uint32_t* pkt_off;       // [n_tiles + 1] packet offsets in 16-byte units
   const unsigned char* packets;  // the tile packets
-  int tile_samples;  // kMinTileSamples .. kMaxTileSamples, power of two
-  int n_slots;       // PHYSICAL value slots per lane in shared memory: 1 (the constant 1.0) + max rows per segment
+  int tile_samples;  // kMinTileSamples .. kMaxTileSamples, multiple of 128
+  int n_slots;       // value slots per lane in shared memory: 1 (the constant 1.0) + max rows per segment
   int pkt_cap;       // bytes of ONE packet buffer in a warp's shared slice (two buffers per warp)
 };
 
-// one CTA's work item: up to DevProgram::tile_samples consecutive samples of channel `wave`
+// one warp's work item: up to DevProgram::tile_samples consecutive samples of channel `wave`
 struct TileDesc {
   int64_t j0;    // first sample of the tile in its channel
   int64_t out0;  // index of that sample in the output buffer
   int32_t wave;
   int32_t cnt;   // samples in the tile
   // filled on the device by prepare_tiles_kernel (once per program):
-  int32_t seg0;           // ABSOLUTE segment row that owns the tile's first sample
-  int32_t nb;             // segment rows the tile spans
-  int32_t fac0, n_fac;    // slice of the factor table the tile can touch
-  int32_t term0, n_term;  // ... of the term table
+  int32_t seg0;  // ABSOLUTE segment row that owns the tile's first sample
+  int32_t nb;    // segment rows the tile spans
 };
-static_assert(sizeof(TileDesc) == 48, "TileDesc layout");
+static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
 struct PrepareCounts {
   int64_t n_segs, n_facs, n_terms, n_tiles;
 };
 
-// pass 1: segment start positions, flat values, device factor rows, compact terms,
+// pass 1: segment start positions, flat values, segment plans, slot map, compact terms,
 // every tile's segment range and packet size (16-byte units) -> pkt_size[n_tiles]
 cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, int32_t* seg_start, double* seg_val,
-                           DFactor* dfacs, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size, cudaStream_t stream);
+                           SegPlan* seg_plan, uint8_t* row_slot, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size,
+                           cudaStream_t stream);
 // exclusive scan: pkt_size[n] -> pkt_off[n + 1] (pkt_off[n] = total); scratch holds ceil(n / 4096) + 1 words
 cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* scratch, int64_t n, cudaStream_t stream);
 // pass 2: write the packets

@@ -89,4 +89,60 @@ __device__ __forceinline__ SinCos sincos_cw(double a) {
 __device__ __forceinline__ double sin_cw(double a) { return sincos_cw(a).s; }
 __device__ __forceinline__ double cos_cw(double a) { return sincos_cw(a).c; }
 
+// N independent arguments at once: the same arithmetic per element (bit-identical to
+// sincos_cw), written element-wise so that the N dependency chains interleave.
+template <int N>
+__device__ __forceinline__ void sincos_cw_n(const double (&a)[N], double (&s_out)[N], double (&c_out)[N]) {
+  bool fast = true;
+#pragma unroll
+  for (int u = 0; u < N; ++u) fast = fast && (fabs(a[u]) <= 1073741824.0);
+  if (!fast) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      const SinCos r = sincos_cw(a[u]);
+      s_out[u] = r.s;
+      c_out[u] = r.c;
+    }
+    return;
+  }
+  double q[N], r[N], z[N], ps[N], pc[N];
+#pragma unroll
+  for (int u = 0; u < N; ++u) q[u] = rint(a[u] * kTrig[0]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) r[u] = fma(-q[u], kTrig[1], a[u]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) r[u] = fma(-q[u], kTrig[2], r[u]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) r[u] = fma(-q[u], kTrig[3], r[u]);
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    z[u] = r[u] * r[u];
+    ps[u] = kTrig[4];
+    pc[u] = kTrig[10];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+      ps[u] = fma(ps[u], z[u], kTrig[5 + k]);
+      pc[u] = fma(pc[u], z[u], kTrig[11 + k]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < N; ++u) {
+    const double s = fma(r[u] * z[u], ps[u], r[u]);
+    const double hz = 0.5 * z[u];
+    const double w = 1.0 - hz;
+    const double c = w + (((1.0 - w) - hz) + z[u] * z[u] * pc[u]);
+    const int n = (int)q[u];
+    const bool odd = n & 1;
+    const double ss = odd ? c : s;
+    const double cc = odd ? s : c;
+    const unsigned long long sbit = (unsigned long long)(n & 2) << 62;
+    const unsigned long long cbit = (unsigned long long)((n + 1) & 2) << 62;
+    s_out[u] = __longlong_as_double(__double_as_longlong(ss) ^ sbit);
+    c_out[u] = __longlong_as_double(__double_as_longlong(cc) ^ cbit);
+  }
+}
+
 }  // namespace wfm

@@ -6,38 +6,36 @@
 // (/root/reference/waveforms/waveform.py:173-207, :529-563, :679-693;
 //  /root/reference/waveforms/_waveform.pyx:130-169).
 //
-// Once per program (prepare_segments_kernel / prepare_tiles_kernel):
+// Once per program (prepare_segments_kernel / prepare_tiles_kernel / fill_packets_kernel):
 //   * every segment learns the INTEGER sample position where it starts: the first
 //     sample whose abscissa is >= its lower bound — a division for the guess,
 //     then exact comparisons against the rounded grid value x[j] = t0 + j*delta,
 //     so ownership is bit-identical to np.searchsorted on the reference's grid;
 //   * every FLAT segment (no basis factor: zero, or a constant) gets its value;
-//   * the ABI factor / term rows are rewritten into the device formats (64-byte
-//     factor rows carrying their rotation constants, 16-byte compact terms);
-//   * every tile (tile_samples consecutive samples of one channel) learns the
-//     segment range it spans and its slice of the factor / term tables.
+//   * every ACTIVE segment gets its device program: the ABI factor rows regrouped by
+//     class (sincos rows, rotation rows, generic rows; wfm_internal.h) with their
+//     value slots assigned in that order, and its terms as 16-byte compact records
+//     holding the byte offsets of the slots they multiply;
+//   * every tile (tile_samples consecutive samples of one channel) gets ONE packet
+//     with everything it needs.
 //
 // Per launch: a PERSISTENT grid (CTAs per SM x 148) of 8-warp CTAs in which every
 // WARP is autonomous.  A warp owns a private slice of shared memory (output tile,
-// factor-value slots, table slice, segment rows, one mbarrier) and loops over
-// tiles (warp w of the grid takes tiles w, w+G, ...); there is NO block-level
-// barrier anywhere, so a warp stalled on a table load or a long pulse never
-// idles its neighbours.  The tile is ASSEMBLED IN SHARED MEMORY and leaves the
-// SM as ONE TMA bulk store (cp.async.bulk shared->global):
-//   1. Prologue.  Lane 0 starts a TMA bulk load (cp.async.bulk + mbarrier) of
-//      the tile's slice of the factor / compact-term tables; the lanes copy the
-//      tile's segment rows (start position, flat value, pointers); the NEXT tile's
-//      descriptor is prefetched.
+// value slots, two packet buffers, two mbarriers) and loops over tiles (warp w of
+// the grid takes tiles w, w+G, ...); there is NO block-level barrier anywhere, so a
+// warp stalled on a packet load or a long pulse never idles its neighbours.  The
+// tile is ASSEMBLED IN SHARED MEMORY and leaves the SM as ONE TMA bulk store:
+//   1. Prologue.  Lane 0 starts the TMA bulk load (cp.async.bulk + mbarrier) of the
+//      NEXT tile's packet into the other packet buffer, then the warp waits for
+//      this tile's packet (requested one tile ago).
 //   2. Flat fill.  After the previous tile's bulk store has finished reading the
 //      buffer, the whole tile is filled with the channel's zero-segment value
-//      (16-byte shared stores, no table look-ups); a ballot compacts the list of
-//      flat segments whose value differs (constant plateaus) and those runs are
-//      rewritten.  No abscissa is computed for flat samples.
-//   3. Active samples.  The ACTIVE samples of the tile are enumerated through a
-//      warp prefix sum over the segment rows and dealt round-robin to the 32
-//      lanes.  Each lane interprets its sample's segment program (distinct
-//      factors into per-lane value slots in shared memory, then terms referencing
-//      the slots) and writes the sample into the tile.
+//      (16-byte shared stores, no table look-ups); the constant plateaus listed in
+//      the packet are rewritten.  No abscissa is computed for flat samples.
+//   3. Active samples.  The tile's active samples are grouped into UNITS (kUnit
+//      consecutive samples of one segment) that are dealt round-robin to the lanes.
+//      A lane interprets the segment program once per unit — the kUnit samples run
+//      as independent dependency chains — and writes the values into the tile.
 //   4. Store.  fence.proxy.async, __syncwarp, lane 0 issues the bulk store of the
 //      whole tile with an L2 evict-first policy (the output is write-once; it must
 //      not displace the IR).  HBM sees full lines only, no LSU store instructions
@@ -146,152 +144,70 @@ __device__ int first_sample_at_or_after(const WfmWave& w, const double* __restri
   return lo;
 }
 
-// global tables the interpreter may fall back to (extended terms, rows beyond the
-// value cache, argument pool of the cold basis functions)
-struct IrGlobal {
-  const DFactor* dfacs;
-  const WfmTerm* terms;
-  const WfmRef* refs;
-  const double* args;
-};
-
 // the few channel fields a sample evaluation needs
 struct WaveEval {
   double offset, clip_lo, clip_hi;
   uint32_t flags;
 };
 
-// per-lane cache of the distinct factor values of one segment evaluation.  PHYSICAL
-// slot 0 holds the constant 1.0; the value of factor row k lives in physical slot k+1.
-struct LocalSlots {  // registers / local memory: cold path and complex kernel
-  double v[kMaxSlots + 1];
-  __device__ __forceinline__ LocalSlots() { v[0] = 1.0; }
-  __device__ __forceinline__ double phys(int k) const { return v[k]; }
-  __device__ __forceinline__ void setp(int k, double x) { v[k] = x; }
+// kUnit values of one lane
+struct Val {
+  double v[kUnit];
 };
-struct SmemSlots {  // the warp's shared slice, slot-major: physical slot k of lane l at p[k*32] (conflict-free)
-  double* p;
-  __device__ __forceinline__ double phys(int k) const { return p[k * 32]; }
-  __device__ __forceinline__ void setp(int k, double x) const { p[k * 32] = x; }
-};
-
-__device__ __forceinline__ FacArgs fac_args(const DFactor& f) {
-  return FacArgs{f.func & 0xffff, f.aux, f.shift, f.a0, f.a1};
-}
-
-// factor rows of one segment -> value slots.  Every row names its destination
-// (physical) slot, so packets can drop the NOP placeholder rows; facs = the
-// segment's first row (shared memory when the tile's packet is staged).
-template <typename Slots>
-__device__ __forceinline__ void eval_factors(const DFactor* __restrict__ facs, int n_rows, double x,
-                                             const double* __restrict__ args, Slots& vals) {
-#pragma unroll 1
-  for (int k = 0; k < n_rows; ++k) {
-    const uint32_t fo = (uint32_t)facs[k].func;
-    const int op = (fo >> 16) & 0xff;
-    const int dest = fo >> 24;
-    const double a0 = facs[k].a0;
-    const double t = sub(x, facs[k].shift);
-    if (op == OP_ROT) {
-      // cos(a_t) with a_t = w*(x - shift) rounded exactly as the reference rounds
-      // it, obtained from the base row's (cos, sin)(a_b):  a_t = a_b + D + eps with
-      // D a host constant (cos D, sin D tabulated) and eps = (a_t - a_b) - D the
-      // MEASURED residual (|eps| ~ ulp(a)), expanded to second order.
-      const int base = facs[k].aux;  // physical slot of the base row's cosine
-      const double bshift = facs[k].p[0], D = facs[k].p[1], cD = facs[k].p[2], sD = facs[k].p[3];
-      const double a_t = mul(a0, t);
-      const double a_b = mul(a0, sub(x, bshift));
-      const double eps = sub(sub(a_t, a_b), D);
-      const double cb = vals.phys(base), sb = vals.phys(base + 1);
-      const double C = fma(cb, cD, -(sb * sD));
-      const double S = fma(sb, cD, cb * sD);
-      vals.setp(dest, fma(-0.5 * eps * eps, C, fma(-eps, S, C)));
-    } else if (op == OP_SINCOS) {
-      // one range reduction serves every COS factor of this frequency
-      const SinCos sc = sincos_cw(mul(a0, t));
-      vals.setp(dest, sc.c);
-      vals.setp(dest + 1, sc.s);
-    } else if (op == OP_COS) {
-      vals.setp(dest, cos_cw(mul(a0, t)));
-    } else if (op == OP_LINEAR) {
-      vals.setp(dest, t);
-    } else if (op == OP_GAUSSIAN) {
-      vals.setp(dest, f_gaussian(t, a0));
-    } else if (op == OP_ERF) {
-      vals.setp(dest, erf(dvd(t, a0)));
-    } else if (op != OP_NOP) {
-      vals.setp(dest, eval_factor(fac_args(facs[k]), x, args));
-    }
+__device__ __forceinline__ Val ld_slot(const unsigned char* p) {
+  Val r;
+  if constexpr (kUnit == 2) {
+    const double2 d = *reinterpret_cast<const double2*>(p);
+    r.v[0] = d.x;
+    r.v[1] = d.y;
+  } else {
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) r.v[u] = reinterpret_cast<const double*>(p)[u];
   }
+  return r;
 }
-
-// product of the referenced factor powers of an ABI term (general path); gfac = the
-// segment's first row in the GLOBAL factor table
-template <typename Slots>
-__device__ __noinline__ double term_product(const IrGlobal& g, int gfac, const WfmTerm& tm, double x,
-                                            const Slots& vals) {
-  double prod = 1.0;
-#pragma unroll 1
-  for (int r = 0; r < tm.n_ref; ++r) {
-    const WfmRef ref = g.refs[tm.ref_begin + r];
-    double v = (ref.slot < kMaxSlots) ? vals.phys(ref.slot + 1) : eval_factor(fac_args(g.dfacs[gfac + ref.slot]), x, g.args);
-    if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
-    else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
-    prod = mul(prod, v);  // the reference's product starts from 1; 1 * v is exact
+__device__ __forceinline__ void st_slot(unsigned char* p, const Val& r) {
+  if constexpr (kUnit == 2) {
+    *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) reinterpret_cast<double*>(p)[u] = r.v[u];
   }
-  return prod;
 }
 
 static __device__ __noinline__ double clip_value(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-// Evaluate one segment's program at one abscissa (real-valued channels; compact terms).
-// facs / cterms point at the segment's first rows (shared or global memory);
-// gfac / gterm are the same rows' indices in the global tables.
-// Order of operations = the reference's (_waveform.pyx:134-152, waveform.py:690-692):
-// every term is amp * (((1 * f1) * f2) * ...), a member's terms are summed left to
-// right starting from 0, the member sums are added to the accumulator (offset).
-template <typename Slots>
-__device__ __forceinline__ double eval_segment_real(const DFactor* __restrict__ facs, const CTerm* __restrict__ cterms,
-                                                    int nf, int nt, const IrGlobal& g, int gfac, int gterm,
-                                                    const WaveEval& w, double x, Slots& vals) {
-  double total = w.offset;
-  if (nt == 0) return total;  // zero segment: untouched by clip (calc_parts skips it)
-  eval_factors(facs, nf, x, g.args, vals);  // global rows: nf <= kMaxSlots (the caller clamps)
-  double grp = 0.0;
-#pragma unroll 1
-  for (int it = 0; it < nt; ++it) {
-    const double amp = cterms[it].amp;
-    const uint32_t pk = (uint32_t)cterms[it].packed;
-    double prod;
-    if (pk & kCTermExt) {
-      prod = term_product(g, gfac, g.terms[gterm + it], x, vals);
-    } else {
-      prod = mul(mul(vals.phys((pk >> 8) & 0xffu), vals.phys((pk >> 16) & 0xffu)), vals.phys(pk >> 24));
-    }
-    grp = add(grp, mul(amp, prod));
-    if (pk & kCTermGroupEnd) {
-      total = add(total, grp);
-      grp = 0.0;
-    }
-  }
-  if (w.flags & WFM_WAVE_CLIP) total = clip_value(total, w.clip_lo, w.clip_hi);
-  return total;
+// ---- the slow evaluator: ABI tables in global memory, no value cache -----------------------
+// Used by cold tiles (packet larger than a buffer), wide segments (more value slots or
+// terms than the hot path holds) and the complex128 kernel.  A WFM_COS_SINCOS /
+// WFM_COS_ROT row IS cos(w * (x - shift)) (the lowering only regrouped equal-w cosines).
+static __device__ __noinline__ double eval_row_direct(const WfmFactor& f, double x, const double* __restrict__ args) {
+  if (f.func == WFM_COS_SINCOS || f.func == WFM_COS_ROT || f.func == WFM_COS) return cos_cw(mul(f.a0, sub(x, f.shift)));
+  return eval_factor(FacArgs{f.func, f.arg_off, f.shift, f.a0, f.a1}, x, args);
 }
 
-// complex amplitudes (WFM_C128 output): ABI terms from global memory
-__device__ __forceinline__ void eval_segment_cplx(const IrGlobal& g, const WaveEval& w, WfmSegPtr p0, WfmSegPtr p1,
-                                                  double x, double& out_re, double& out_im) {
+// Order of operations = the reference's (_waveform.pyx:134-152, waveform.py:690-692):
+// every term is amp * (((1 * f1^n1) * f2^n2) * ...), a member's terms are summed left to
+// right starting from 0, the member sums are added to the accumulator (offset).
+static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int seg, const WaveEval& w, double x,
+                                                      double& out_re, double& out_im) {
+  const WfmSegPtr p0 = P.seg_ptr[seg], p1 = P.seg_ptr[seg + 1];
   out_re = w.offset;
   out_im = 0.0;
-  const int nt = p1.term - p0.term;
-  if (nt == 0) return;
-  LocalSlots vals;
-  eval_factors(g.dfacs + p0.fac, min(p1.fac - p0.fac, kMaxSlots), x, g.args, vals);
+  if (p1.term == p0.term) return;  // zero segment: untouched by clip (calc_parts skips it)
   double g_re = 0.0, g_im = 0.0;
 #pragma unroll 1
-  for (int it = 0; it < nt; ++it) {
-    const WfmTerm tm = g.terms[p0.term + it];
-    const double prod = term_product(g, p0.fac, tm, x, vals);
+  for (int t = p0.term; t < p1.term; ++t) {
+    const WfmTerm tm = P.terms[t];
+    double prod = 1.0;
+#pragma unroll 1
+    for (int r = 0; r < tm.n_ref; ++r) {
+      const WfmRef ref = P.refs[tm.ref_begin + r];
+      double v = eval_row_direct(P.facs[p0.fac + ref.slot], x, P.args);
+      if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
+      else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
+      prod = mul(prod, v);  // the reference's product starts from 1; 1 * v is exact
+    }
     g_re = add(g_re, mul(tm.amp_re, prod));
     g_im = add(g_im, mul(tm.amp_im, prod));
     if (tm.flags & WFM_TERM_GROUP_END) {
@@ -300,21 +216,153 @@ __device__ __forceinline__ void eval_segment_cplx(const IrGlobal& g, const WaveE
       g_re = g_im = 0.0;
     }
   }
-  if (w.flags & WFM_WAVE_CLIP) out_re = fmin(fmax(out_re, w.clip_lo), w.clip_hi);
+  if (w.flags & WFM_WAVE_CLIP) out_re = clip_value(out_re, w.clip_lo, w.clip_hi);
+}
+
+// product of an extended term (more than three references or an exponent != 1) from the
+// ABI tables; the factor values are the ones already sitting in the lane's value slots
+static __device__ __noinline__ double term_product_ext(const DevProgram& P, int seg, int it, const unsigned char* sl, int u) {
+  const WfmSegPtr p0 = P.seg_ptr[seg];
+  const WfmTerm tm = P.terms[p0.term + it];
+  double prod = 1.0;
+#pragma unroll 1
+  for (int r = 0; r < tm.n_ref; ++r) {
+    const WfmRef ref = P.refs[tm.ref_begin + r];
+    const int slot = P.row_slot[p0.fac + ref.slot];
+    double v = reinterpret_cast<const double*>(sl + slot * kSlotStride)[u];
+    if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
+    else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
+    prod = mul(prod, v);
+  }
+  return prod;
+}
+
+// ---- the hot evaluator: one UNIT (kUnit samples of one active segment) per call -------------
+// blk: the segment's rows in the staged packet (SRow.. RRow.. GRow.. CTerm..); sl: this
+// lane's value slots (slot k at sl + k * kSlotStride, slot 0 holds 1.0).
+__device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
+                                         bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
+                                         const double (&x)[kUnit], unsigned char* __restrict__ sl) {
+  unsigned char* dst = sl + kSlotStride;  // slot 1
+  // -- one range reduction + both polynomials per frequency
+  const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(blk);
+#pragma unroll 1
+  for (int i = 0; i < n_sc; ++i) {
+    const double shift = sr[i].shift, wv = sr[i].w;
+    double a[kUnit];
+    Val s, c;
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) a[u] = mul(wv, sub(x[u], shift));
+    sincos_cw_n<kUnit>(a, s.v, c.v);
+    st_slot(dst, c);
+    st_slot(dst + kSlotStride, s);
+    dst += 2 * kSlotStride;
+  }
+  // -- further cosines of a frequency already reduced: cos(a_t), a_t = w*(x - shift) rounded
+  // exactly as the reference rounds it, from the base row's (cos, sin)(a_b): a_t = a_b + D + eps
+  // with D a host constant (cos D, sin D tabulated) and eps = (a_t - a_b) - D the MEASURED
+  // residual (|eps| ~ ulp(a)), expanded to second order
+  const RRow* __restrict__ rr = reinterpret_cast<const RRow*>(sr + n_sc);
+#pragma unroll 1
+  for (int j = 0; j < n_rot; ++j) {
+    const double shift = rr[j].shift, wv = rr[j].w, bshift = rr[j].bshift;
+    const double D = rr[j].D, cD = rr[j].cD, sD = rr[j].sD;
+    const unsigned char* bp = sl + rr[j].base_off;
+    const Val cb = ld_slot(bp), sb = ld_slot(bp + kSlotStride);
+    Val r;
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) {
+      const double a_t = mul(wv, sub(x[u], shift));
+      const double a_b = mul(wv, sub(x[u], bshift));
+      const double eps = sub(sub(a_t, a_b), D);
+      const double C = fma(cb.v[u], cD, -(sb.v[u] * sD));
+      const double S = fma(sb.v[u], cD, cb.v[u] * sD);
+      r.v[u] = fma(-0.5 * eps * eps, C, fma(-eps, S, C));
+    }
+    st_slot(dst, r);
+    dst += kSlotStride;
+  }
+  // -- every other basis function
+  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(rr + n_rot);
+#pragma unroll 1
+  for (int k = 0; k < n_gen; ++k) {
+    const int func = gr[k].func;
+    const double shift = gr[k].shift, a0 = gr[k].a0;
+    Val r;
+    if (func == WFM_COS) {
+      double a[kUnit], s[kUnit];
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) a[u] = mul(a0, sub(x[u], shift));
+      sincos_cw_n<kUnit>(a, s, r.v);
+    } else if (func == WFM_LINEAR) {
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) r.v[u] = sub(x[u], shift);
+    } else if (func == WFM_GAUSSIAN) {
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) r.v[u] = f_gaussian(sub(x[u], shift), a0);
+    } else if (func == WFM_ERF) {
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) r.v[u] = erf(dvd(sub(x[u], shift), a0));
+    } else {
+      const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
+#pragma unroll 1
+      for (int u = 0; u < kUnit; ++u) r.v[u] = eval_factor(fa, x[u], P.args);
+    }
+    st_slot(dst, r);
+    dst += kSlotStride;
+  }
+  // -- terms
+  const uint4* __restrict__ ct = reinterpret_cast<const uint4*>(gr + n_gen);
+  Val total, grp;
+#pragma unroll
+  for (int u = 0; u < kUnit; ++u) {
+    total.v[u] = w.offset;
+    grp.v[u] = 0.0;
+  }
+#pragma unroll 1
+  for (int it = 0; it < n_term; ++it) {
+    const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags
+    const double amp = __hiloint2double((int)c.y, (int)c.x);
+    Val prod;
+    if (has_ext && (c.w >> 16) & kCTermExt) {
+#pragma unroll 1
+      for (int u = 0; u < kUnit; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
+    } else {
+      const Val f0 = ld_slot(sl + (c.z & 0xffffu)), f1 = ld_slot(sl + (c.z >> 16)), f2 = ld_slot(sl + (c.w & 0xffffu));
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) prod.v[u] = mul(mul(f0.v[u], f1.v[u]), f2.v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) grp.v[u] = add(grp.v[u], mul(amp, prod.v[u]));
+    if ((c.w >> 16) & kCTermGroupEnd) {
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) {
+        total.v[u] = add(total.v[u], grp.v[u]);
+        grp.v[u] = 0.0;
+      }
+    }
+  }
+  if (w.flags & WFM_WAVE_CLIP) {
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) total.v[u] = clip_value(total.v[u], w.clip_lo, w.clip_hi);
+  }
+  return total;
 }
 
 // ---- pre-pass (once per program) ----------------------------------------------------------
-// one thread per segment: start position, value of a flat segment
+// one thread per segment: start position, value of a flat segment, plan of an active one
 __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_start, double* __restrict__ seg_val,
-                                        int64_t n_segs) {
+                                        SegPlan* __restrict__ seg_plan, uint8_t* __restrict__ row_slot,
+                                        CTerm* __restrict__ cterms, int64_t n_segs) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_segs) return;
   const WfmWave w = P.waves[P.seg_wave[s]];
   const int k = (int)(s - w.seg_begin);
   seg_start[s] = k == 0 ? 0 : first_sample_at_or_after(w, P.x, (int)w.n, P.seg_bound[s - 1]);
   const WfmSegPtr p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1];
+  const int nf = p1.fac - p0.fac, nt = p1.term - p0.term;
   double val = w.offset;
-  if (p1.fac == p0.fac && p1.term > p0.term) {
+  if (nf == 0 && nt > 0) {
     // constant segment: offset + sum over stack members of (0 + sum of their constant terms)
     double grp = 0.0;
     for (int t = p0.term; t < p1.term; ++t) {
@@ -328,72 +376,51 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
     if (w.flags & WFM_WAVE_CLIP) val = fmin(fmax(val, w.clip_lo), w.clip_hi);
   }
   seg_val[s] = val;
-}
 
-// one thread per factor row: the 64-byte device row
-__global__ void prepare_factors_kernel(DevProgram P, DFactor* __restrict__ dfacs, int64_t n_facs, int64_t n_segs) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_facs) return;
-  const WfmFactor f = P.facs[k];
-  int op = OP_GENERIC;
-  switch (f.func) {
-    case WFM_COS_ROT: op = OP_ROT; break;
-    case WFM_COS_SINCOS: op = OP_SINCOS; break;
-    case WFM_NOP: op = OP_NOP; break;
-    case WFM_COS: op = OP_COS; break;
-    case WFM_LINEAR: op = OP_LINEAR; break;
-    case WFM_GAUSSIAN: op = OP_GAUSSIAN; break;
-    case WFM_ERF: op = OP_ERF; break;
-    default: break;
+  // plan: rows by class, value slots in class order
+  int n_sc = 0, n_rot = 0, n_gen = 0;
+  for (int r = 0; r < nf; ++r) {
+    const int f = P.facs[p0.fac + r].func;
+    if (f == WFM_COS_SINCOS) ++n_sc;
+    else if (f == WFM_COS_ROT) ++n_rot;
+    else if (f != WFM_NOP) ++n_gen;
   }
-  // destination (physical) value slot = row within its segment + 1; found from the
-  // segment table by binary search over seg_ptr (rows of one segment are contiguous)
-  int lo = 0, hi = (int)n_segs - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if ((int64_t)P.seg_ptr[mid].fac <= k) lo = mid; else hi = mid - 1;
+  const bool wide = 2 * n_sc + n_rot + n_gen > kMaxSlots || nt > 255;
+  int i_sc = 0, i_rot = 0, i_gen = 0;
+  for (int r = 0; r < nf; ++r) {
+    const int f = P.facs[p0.fac + r].func;
+    int slot = 0;
+    if (!wide) {
+      if (f == WFM_COS_SINCOS) slot = 1 + 2 * i_sc++;
+      else if (f == WFM_COS_ROT) slot = 1 + 2 * n_sc + i_rot++;
+      else if (f != WFM_NOP) slot = 1 + 2 * n_sc + n_rot + i_gen++;
+    }
+    row_slot[p0.fac + r] = (uint8_t)slot;
   }
-  while (lo + 1 < (int)n_segs && P.seg_ptr[lo + 1].fac <= k) ++lo;  // skip factor-less segments sharing the offset
-  const int row = (int)(k - P.seg_ptr[lo].fac);
-  if (row >= kMaxSlots) op = OP_NOP;  // beyond the value cache: evaluated on demand by extended terms
-  const int dest = row < kMaxSlots ? row + 1 : 0;
-  DFactor d;
-  d.func = f.func | (op << 16) | (dest << 24);
-  d.aux = f.arg_off;
-  d.shift = f.shift;
-  d.a0 = f.a0;
-  d.a1 = f.a1;
-  d.p[0] = d.p[1] = d.p[2] = d.p[3] = 0.0;
-  if (f.func == WFM_COS_ROT) {
-    const double* __restrict__ p = P.args + f.arg_off;  // [base_slot, base_shift, D, cos D, sin D]
-    d.aux = (int)p[0] + 1;  // physical slot of the base row's cosine
-    d.p[0] = p[1];
-    d.p[1] = p[2];
-    d.p[2] = p[3];
-    d.p[3] = p[4];
+  for (int t = 0; t < nt; ++t) {
+    const WfmTerm tm = P.terms[p0.term + t];
+    bool ext = tm.n_ref > 3;
+    uint16_t o[3] = {0, 0, 0};
+    for (int r = 0; r < tm.n_ref && !ext; ++r) {
+      const WfmRef rf = P.refs[tm.ref_begin + r];
+      if (rf.kind != WFM_POW_ONE) ext = true;
+      else o[r] = (uint16_t)(row_slot[p0.fac + rf.slot] * kSlotStride);
+    }
+    uint16_t flags = (tm.flags & WFM_TERM_GROUP_END) ? kCTermGroupEnd : 0u;
+    if (ext) {
+      flags |= kCTermExt;
+      o[0] = o[1] = o[2] = 0;
+    }
+    cterms[p0.term + t] = CTerm{tm.amp_re, o[0], o[1], o[2], flags};
   }
-  dfacs[k] = d;
-}
-
-// one thread per term: the 16-byte compact term
-__global__ void prepare_terms_kernel(DevProgram P, CTerm* __restrict__ cterms, int64_t n_terms) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_terms) return;
-  const WfmTerm tm = P.terms[t];
-  uint64_t packed = 0;
-  bool ext = tm.n_ref > 3;
-  for (int r = 0; r < tm.n_ref && !ext; ++r) {
-    const WfmRef rf = P.refs[tm.ref_begin + r];
-    if (rf.kind != WFM_POW_ONE || rf.slot >= kMaxSlots) ext = true;
-    else packed |= (uint64_t)(uint32_t)(rf.slot + 1) << (8 + 8 * r);  // physical slot; 0 = the constant 1.0
-  }
-  uint32_t flags = (tm.flags & WFM_TERM_GROUP_END) ? kCTermGroupEnd : 0u;
-  if (ext) {
-    flags |= kCTermExt;
-    packed = 0;
-  }
-  packed |= flags;
-  cterms[t] = CTerm{tm.amp_re, packed};
+  SegPlan pl;
+  pl.n_sc = (uint8_t)min(n_sc, 255);
+  pl.n_rot = (uint8_t)min(n_rot, 255);
+  pl.n_gen = (uint8_t)min(n_gen, 255);
+  pl.flags = wide ? kSegWide : 0u;
+  pl.n_term = (uint16_t)min(nt, 65535);
+  pl.blk16 = wide ? 0 : (uint16_t)((n_sc * sizeof(SRow) + n_rot * sizeof(RRow) + n_gen * sizeof(GRow) + nt * sizeof(CTerm)) / 16);
+  seg_plan[s] = pl;
 }
 
 // last segment k in [0, n) with start[k] <= j (start[0] == 0)
@@ -408,12 +435,12 @@ __device__ __forceinline__ int owning_segment(const int32_t* __restrict__ start,
 
 // what a tile's packet holds (shared by the measuring and the filling pass)
 struct TileLayout {
-  int n_arows, n_patch, n_fac, n_term, n_active;
+  int n_arows, n_patch, n_units, blk16;
   bool cold;
   __device__ __forceinline__ int bytes() const {
     if (cold) return (int)sizeof(PacketHeader);
     return (int)sizeof(PacketHeader) + (n_arows ? (n_arows + 1) * (int)sizeof(ARow) : 0) + n_patch * (int)sizeof(PatchRow) +
-           n_fac * (int)sizeof(DFactor) + n_term * (int)sizeof(CTerm);
+           blk16 * 16;
   }
 };
 
@@ -425,15 +452,8 @@ __device__ __forceinline__ void seg_span(const int32_t* __restrict__ st, int n_s
   b = (int)(min(hi, j0 + cnt) - j0);
 }
 
-// rows of a segment the packet carries: no NOP placeholders, nothing beyond the value cache
-__device__ __forceinline__ int packet_rows(const DFactor* __restrict__ dfacs, WfmSegPtr p0, WfmSegPtr p1) {
-  int n = 0;
-  for (int r = p0.fac; r < p1.fac; ++r) n += (((uint32_t)dfacs[r].func >> 16) & 0xff) != OP_NOP;
-  return n;
-}
-
 __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, const WfmWave& w) {
-  TileLayout L{0, 0, 0, 0, 0, false};
+  TileLayout L{0, 0, 0, 0, false};
   const int32_t* __restrict__ st = P.seg_start + w.seg_begin;
   const int k0 = td.seg0 - w.seg_begin;
   for (int k = k0; k < k0 + td.nb; ++k) {
@@ -443,18 +463,18 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
     const WfmSegPtr p0 = P.seg_ptr[w.seg_begin + k], p1 = P.seg_ptr[w.seg_begin + k + 1];
     if (p1.fac > p0.fac) {
       L.n_arows += 1;
-      L.n_fac += packet_rows(P.dfacs, p0, p1);
-      L.n_term += p1.term - p0.term;
-      L.n_active += b - a;
+      L.blk16 += P.seg_plan[w.seg_begin + k].blk16;
+      L.n_units += (b - a + kUnit - 1) / kUnit;
     } else if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) {
       L.n_patch += 1;
     }
   }
-  L.cold = L.bytes() > P.pkt_cap;
+  // ARow::rel addresses 16-byte units with 12 bits
+  L.cold = L.bytes() > P.pkt_cap || L.bytes() >= 4096 * 16;
   return L;
 }
 
-// one thread per tile: the segment rows it spans, its slice of the tables, its packet size
+// one thread per tile: the segment rows it spans, its packet size
 __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, int64_t n_tiles,
                                      uint32_t* __restrict__ pkt_size) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,11 +486,6 @@ __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles,
   const int hi = max(lo, owning_segment(st, w.n_seg, td.j0 + td.cnt - 1));
   td.seg0 = w.seg_begin + lo;
   td.nb = hi - lo + 1;
-  const WfmSegPtr a = P.seg_ptr[w.seg_begin + lo], e = P.seg_ptr[w.seg_begin + hi + 1];
-  td.fac0 = a.fac;
-  td.n_fac = e.fac - a.fac;
-  td.term0 = a.term;
-  td.n_term = e.term - a.term;
   tiles[t] = td;
   pkt_size[t] = (uint32_t)(measure_tile(P, td, w).bytes() / 16);
 }
@@ -558,8 +573,7 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
   unsigned char* pk = packets + (size_t)P.pkt_off[t] * 16;
   ARow* arows = reinterpret_cast<ARow*>(pk + sizeof(PacketHeader));
   PatchRow* patches = reinterpret_cast<PatchRow*>(arows + (L.n_arows ? L.n_arows + 1 : 0));
-  DFactor* facs = reinterpret_cast<DFactor*>(patches + L.n_patch);
-  CTerm* cterms = reinterpret_cast<CTerm*>(facs + L.n_fac);
+  unsigned char* blocks = reinterpret_cast<unsigned char*>(patches + L.n_patch);
   if (lane == 0) {
     PacketHeader h;
     h.out0 = td.out0;
@@ -572,49 +586,76 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
     h.cnt = (uint16_t)td.cnt;
     h.n_arows = L.cold ? 0 : (uint16_t)L.n_arows;
     h.n_patch = L.cold ? 0 : (uint16_t)L.n_patch;
-    h.n_active = L.cold ? 0 : (uint16_t)L.n_active;
-    h.n_fac = L.cold ? 0 : (uint16_t)L.n_fac;
-    h.n_term = L.cold ? 0 : (uint16_t)L.n_term;
-    h.reserved = 0;
+    h.n_units = L.cold ? 0 : (uint16_t)L.n_units;
+    h.reserved[0] = h.reserved[1] = 0;
     *reinterpret_cast<PacketHeader*>(pk) = h;
   }
   if (L.cold) return;
-  // rows: one sequential walk over the tile's segments (lane 0), table rows copied by all lanes
+  // one sequential walk over the tile's segments (identical in every lane); the rows of a
+  // segment are written by the lanes in parallel
   const int32_t* __restrict__ st = P.seg_start + w.seg_begin;
   const int k0 = td.seg0 - w.seg_begin;
-  int ia = 0, ip = 0, fac_rel = 0, term_rel = 0, first = 0;
+  int ia = 0, ip = 0, first = 0;
+  unsigned char* blk = blocks;
   for (int k = k0; k < k0 + td.nb; ++k) {
     int a, b;
     seg_span(st, w.n_seg, w.n, k, td.j0, td.cnt, a, b);
     if (b <= a) continue;
-    const WfmSegPtr p0 = P.seg_ptr[w.seg_begin + k], p1 = P.seg_ptr[w.seg_begin + k + 1];
+    const int seg = w.seg_begin + k;
+    const WfmSegPtr p0 = P.seg_ptr[seg], p1 = P.seg_ptr[seg + 1];
     if (p1.fac > p0.fac) {
-      if (lane == 0)
-        arows[ia] = ARow{(uint16_t)a, (uint16_t)first, (uint16_t)fac_rel, (uint16_t)term_rel, p0.fac, p0.term};
-      // factor rows without the NOP placeholders (order kept), 16 bytes per lane and step
-      int kept = 0;
-      for (int r = p0.fac; r < p1.fac; ++r) {
-        if ((((uint32_t)P.dfacs[r].func >> 16) & 0xff) == OP_NOP) continue;
-        if (lane < 4)
-          reinterpret_cast<uint4*>(facs + fac_rel + kept)[lane] = reinterpret_cast<const uint4*>(P.dfacs + r)[lane];
-        ++kept;
+      const SegPlan pl = P.seg_plan[seg];
+      if (lane == 0) {
+        ARow r;
+        r.start = (uint16_t)a;
+        r.first = (uint16_t)first;
+        r.rel = (uint16_t)(((blk - pk) / 16) | ((uint32_t)pl.flags << 12));
+        r.len = (uint16_t)(b - a);
+        r.n_sc = pl.n_sc;
+        r.n_rot = pl.n_rot;
+        r.n_gen = pl.n_gen;
+        r.n_term = (uint8_t)pl.n_term;
+        r.gseg = seg;
+        arows[ia] = r;
       }
-      for (int q = lane; q < p1.term - p0.term; q += 32)
-        reinterpret_cast<uint4*>(cterms + term_rel)[q] = reinterpret_cast<const uint4*>(P.cterms + p0.term)[q];
+      if (!(pl.flags & kSegWide)) {
+        SRow* sr = reinterpret_cast<SRow*>(blk);
+        RRow* rr = reinterpret_cast<RRow*>(sr + pl.n_sc);
+        GRow* gr = reinterpret_cast<GRow*>(rr + pl.n_rot);
+        CTerm* ct = reinterpret_cast<CTerm*>(gr + pl.n_gen);
+        for (int r = lane; r < p1.fac - p0.fac; r += 32) {
+          const WfmFactor f = P.facs[p0.fac + r];
+          const int slot = P.row_slot[p0.fac + r];
+          if (f.func == WFM_COS_SINCOS) {
+            sr[(slot - 1) / 2] = SRow{f.shift, f.a0};
+          } else if (f.func == WFM_COS_ROT) {
+            const double* __restrict__ p = P.args + f.arg_off;  // [base_row, base_shift, D, cos D, sin D]
+            const int base_slot = P.row_slot[p0.fac + (int)p[0]];
+            rr[slot - 1 - 2 * pl.n_sc] = RRow{f.shift, f.a0, p[1], p[2], p[3], p[4], (uint32_t)(base_slot * kSlotStride), 0u, 0.0};
+          } else if (f.func != WFM_NOP) {
+            gr[slot - 1 - 2 * pl.n_sc - pl.n_rot] = GRow{f.func, f.arg_off, f.shift, f.a0, f.a1};
+          }
+        }
+        for (int q = lane; q < p1.term - p0.term; q += 32)
+          reinterpret_cast<uint4*>(ct)[q] = reinterpret_cast<const uint4*>(P.cterms + p0.term)[q];
+        blk += (size_t)pl.blk16 * 16;
+      }
       ia += 1;
-      fac_rel += kept;
-      term_rel += p1.term - p0.term;
-      first += b - a;
+      first += (b - a + kUnit - 1) / kUnit;
     } else {
-      const double v = P.seg_val[w.seg_begin + k];
+      const double v = P.seg_val[seg];
       if (__double_as_longlong(v) != __double_as_longlong(w.offset)) {
         if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 0u, v};
         ip += 1;
       }
     }
   }
-  if (lane == 0 && L.n_arows)
-    arows[ia] = ARow{(uint16_t)td.cnt, (uint16_t)first, (uint16_t)fac_rel, (uint16_t)term_rel, 0, 0};  // sentinel
+  if (lane == 0 && L.n_arows) {
+    ARow r{};
+    r.start = (uint16_t)td.cnt;
+    r.first = (uint16_t)first;
+    arows[ia] = r;  // sentinel
+  }
 }
 
 // ---- the sampling kernel ------------------------------------------------------------------
@@ -634,9 +675,9 @@ __device__ __forceinline__ void fill_run(OutT* __restrict__ s_out, int a, int b,
 }
 
 // per-warp shared-memory slice (dynamic shared memory; all sub-arrays 16-byte aligned):
-//   [out: tile_samples x OutT][slots: n_slots x 32 x f64][packet buffer 0][packet buffer 1][2 mbarriers]
+//   [out: tile_samples x OutT][slots: n_slots x kSlotStride][packet buffer 0][packet buffer 1][2 mbarriers]
 __host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int pkt_cap, size_t esz) {
-  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * 32 * 8 + 2 * (size_t)pkt_cap + 16;
+  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * kSlotStride + 2 * (size_t)pkt_cap + 16;
   return (b + 127) & ~(size_t)127;
 }
 
@@ -646,19 +687,15 @@ template <typename OutT, bool kAccumulate>
 __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDesc& td, OutT* __restrict__ dst, int lane) {
   const WfmWave w = P.waves[td.wave];
   const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
-  const IrGlobal g{P.dfacs, P.terms, P.refs, P.args};
   const int32_t* __restrict__ st = P.seg_start + td.seg0;
-  const WfmSegPtr* __restrict__ gp = P.seg_ptr + td.seg0;
   for (int jj = lane; jj < td.cnt; jj += 32) {
     int lo = 0, hi = td.nb - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
     }
-    const WfmSegPtr p0 = gp[lo], p1 = gp[lo + 1];
-    LocalSlots vals;
-    const double re = eval_segment_real(P.dfacs + p0.fac, P.cterms + p0.term, min(p1.fac - p0.fac, kMaxSlots),
-                                        p1.term - p0.term, g, p0.fac, p0.term, we, abscissa(w, P.x, td.j0 + jj), vals);
+    double re, im;
+    eval_segment_slow(P, td.seg0 + lo, we, abscissa(w, P.x, td.j0 + jj), re, im);
     dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
   }
 }
@@ -667,19 +704,19 @@ extern __shared__ __align__(128) unsigned char k1_smem[];
 
 template <typename OutT, bool kAccumulate>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
-    sample_kernel(DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end, OutT* __restrict__ out) {
+    sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
+                  OutT* __restrict__ out) {
   constexpr int V = OutVec<OutT>::N;
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   // this warp's private slice
   unsigned char* slice = k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, sizeof(OutT));
   OutT* s_out = reinterpret_cast<OutT*>(slice);
-  double* s_slots = reinterpret_cast<double*>(slice + (size_t)P.tile_samples * sizeof(OutT));
-  unsigned char* s_pkt = reinterpret_cast<unsigned char*>(s_slots + (size_t)P.n_slots * 32);
+  unsigned char* s_slots = slice + (size_t)P.tile_samples * sizeof(OutT);
+  unsigned char* s_pkt = s_slots + (size_t)P.n_slots * kSlotStride;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
+  unsigned char* sl = s_slots + lane * 8 * kUnit;  // this lane's value slots
 
-  const IrGlobal g{P.dfacs, P.terms, P.refs, P.args};
-  SmemSlots vals{s_slots + lane};
   const int n_warps = gridDim.x * kWarpsPerCta;
   int t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
   if (t >= tile_end) return;
@@ -689,7 +726,12 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     mbar_init(s_bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  s_slots[lane] = 1.0;  // physical slot 0: the unit a missing term reference multiplies by
+  {
+    Val one;  // slot 0: the unit a missing term reference multiplies by
+#pragma unroll
+    for (int u = 0; u < kUnit; ++u) one.v[u] = 1.0;
+    st_slot(sl, one);
+  }
   __syncwarp();
 
   // packet of the first tile -> buffer 0; offsets of the second tile -> registers
@@ -731,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     const PacketHeader* __restrict__ h = reinterpret_cast<const PacketHeader*>(pk);
     const int cnt = h->cnt;
     const uint32_t flags = h->flags;
-    const int n_arows = h->n_arows, n_patch = h->n_patch, n_active = h->n_active;
+    const int n_arows = h->n_arows, n_patch = h->n_patch, n_units = h->n_units;
     const double base = h->base;
     OutT* __restrict__ dst = out + h->out0;
 
@@ -750,16 +792,14 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     // value and the active samples overwrite it below
     {
       const int n_fill = (cnt + V - 1) & ~(V - 1);  // the tile buffer is a multiple of V
-      int p = lane * V;
+      if (__double_as_longlong(base) == 0) {
+        // +0.0, the usual case: 16-byte stores of the zero register
+#pragma unroll 4
+        for (int p = lane * V; p < n_fill; p += 32 * V) *reinterpret_cast<uint4*>(s_out + p) = make_uint4(0u, 0u, 0u, 0u);
+      } else {
 #pragma unroll 1
-      for (; p + 3 * 32 * V < n_fill; p += 4 * 32 * V) {
-        fill_vec(s_out + p, base);
-        fill_vec(s_out + p + 32 * V, base);
-        fill_vec(s_out + p + 2 * 32 * V, base);
-        fill_vec(s_out + p + 3 * 32 * V, base);
+        for (int p = lane * V; p < n_fill; p += 32 * V) fill_vec(s_out + p, base);
       }
-#pragma unroll 1
-      for (; p < n_fill; p += 32 * V) fill_vec(s_out + p, base);
     }
     __syncwarp();
 
@@ -768,10 +808,8 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     // ---- flat segments with their own value ----------------------------------------------
     for (int i = 0; i < n_patch; ++i) fill_run(s_out, (int)patches[i].a, (int)patches[i].b, patches[i].val, lane);
 
-    // ---- the tile's ACTIVE samples, dealt round-robin to the lanes ------------------------
-    if (n_active > 0) {
-      const DFactor* __restrict__ sf = reinterpret_cast<const DFactor*>(patches + n_patch);
-      const CTerm* __restrict__ sc = reinterpret_cast<const CTerm*>(sf + h->n_fac);
+    // ---- the tile's ACTIVE samples: units dealt round-robin to the lanes -------------------
+    if (n_units > 0) {
       WaveEval we{base, 0.0, 0.0, flags};
       if (flags & WFM_WAVE_CLIP) {
         we.clip_lo = P.waves[h->wave].clip_lo;
@@ -782,14 +820,37 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       const bool plain_grid = !(flags & (WFM_WAVE_EXPLICIT_X | WFM_WAVE_LAST_OVERRIDE | WFM_WAVE_PRESHIFT));
       int lo = 0;
 #pragma unroll 1
-      for (int i = lane; i < n_active; i += 32) {
-        while ((int)arows[lo + 1].first <= i) ++lo;  // the active segment holding sample i (i grows monotonically)
-        const ARow r0 = arows[lo];
-        const int fac_end = arows[lo + 1].fac_rel, term_end = arows[lo + 1].term_rel;
-        const int jj = (int)r0.start + (i - (int)r0.first);
-        const double x = plain_grid ? add(t0, mul((double)(j0 + jj), delta)) : abscissa(P.waves[h->wave], P.x, j0 + jj);
-        s_out[jj] = (OutT)eval_segment_real(sf + r0.fac_rel, sc + r0.term_rel, fac_end - (int)r0.fac_rel,
-                                            term_end - (int)r0.term_rel, g, r0.gfac, r0.gterm, we, x, vals);
+      for (int i = lane; i < n_units; i += 32) {
+        while ((int)arows[lo + 1].first <= i) ++lo;  // the active segment holding unit i (i grows monotonically)
+        const uint4 rw = reinterpret_cast<const uint4*>(arows)[lo];  // ARow: start first | rel len | n_sc n_rot n_gen n_term | gseg
+        const int start = rw.x & 0xffffu, first = rw.x >> 16, rel = rw.y & 0xfffu, len = rw.y >> 16;
+        const uint32_t sflags = (rw.y >> 12) & 0xfu;
+        const int jj = start + (i - first) * kUnit;
+        const int n_valid = min(kUnit, start + len - jj);
+        double x[kUnit];
+        if (plain_grid) {
+          // the tile's sample index fits 32 bits (channels hold < 2^31 samples)
+          const int jg = (int)j0 + jj;
+#pragma unroll
+          for (int u = 0; u < kUnit; ++u) x[u] = add(t0, mul((double)(jg + u), delta));
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < kUnit; ++u) x[u] = abscissa(P.waves[h->wave], P.x, j0 + min(jj + u, cnt - 1));
+        }
+        Val r;
+        if (sflags & kSegWide) {
+#pragma unroll 1
+          for (int u = 0; u < kUnit; ++u) {
+            double im;
+            eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
+          }
+        } else {
+          r = eval_unit(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                        (int)rw.w, we, x, sl);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnit; ++u)
+          if (u < n_valid) s_out[jj + u] = (OutT)r.v[u];
       }
     }
 
@@ -815,17 +876,15 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   if (lane == 0 && store_pending) bulk_wait_read_all();  // shared memory must outlive the copy's reads
 }
 
-// complex128 output: interleaved (re, im); one sample per thread per row.
+// complex128 output: interleaved (re, im); one sample per thread per row, ABI tables.
 template <bool kAccumulate>
-__global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, const TileDesc* __restrict__ tiles,
-                                                               double2* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads) sample_kernel_c128(const __grid_constant__ DevProgram P,
+                                                               const TileDesc* __restrict__ tiles, double2* __restrict__ out) {
   const TileDesc td = tiles[blockIdx.x];
   const WfmWave w = P.waves[td.wave];
   const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
   const int32_t* __restrict__ st = P.seg_start + td.seg0;
-  const WfmSegPtr* __restrict__ gp = P.seg_ptr + td.seg0;
   double2* __restrict__ dst = out + td.out0;
-  const IrGlobal g{P.dfacs, P.terms, P.refs, P.args};
   for (int jj = threadIdx.x; jj < td.cnt; jj += kThreads) {
     const double x = abscissa(w, P.x, td.j0 + jj);
     int lo = 0, hi = td.nb - 1;
@@ -834,7 +893,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
       if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
     }
     double re, im;
-    eval_segment_cplx(g, we, gp[lo], gp[lo + 1], x, re, im);
+    eval_segment_slow(P, td.seg0 + lo, we, x, re, im);
     if (kAccumulate) {
       double2 o = dst[jj];
       re = add(o.x, re);
@@ -845,12 +904,12 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(DevProgram P, con
 }
 
 cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, int32_t* seg_start, double* seg_val,
-                           DFactor* dfacs, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size, cudaStream_t stream) {
+                           SegPlan* seg_plan, uint8_t* row_slot, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size,
+                           cudaStream_t stream) {
   const int threads = 128;
   auto blocks = [&](int64_t items) { return (unsigned)((items + threads - 1) / threads); };
-  if (n.n_segs > 0) prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, seg_start, seg_val, n.n_segs);
-  if (n.n_facs > 0) prepare_factors_kernel<<<blocks(n.n_facs), threads, 0, stream>>>(P, dfacs, n.n_facs, n.n_segs);
-  if (n.n_terms > 0) prepare_terms_kernel<<<blocks(n.n_terms), threads, 0, stream>>>(P, cterms, n.n_terms);
+  if (n.n_segs > 0)
+    prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, seg_start, seg_val, seg_plan, row_slot, cterms, n.n_segs);
   if (n.n_tiles > 0) prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, tiles, n.n_tiles, pkt_size);
   return cudaGetLastError();
 }
@@ -871,7 +930,7 @@ cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int6
   return cudaGetLastError();
 }
 
-int warp_fixed_bytes(int n_slots) { return n_slots * 32 * 8 + 16 + 128; }
+int warp_fixed_bytes(int n_slots) { return n_slots * kSlotStride + 16 + 128; }
 
 size_t sample_smem_bytes(const DevProgram& P, int dtype) {
   return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
