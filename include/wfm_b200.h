@@ -164,7 +164,13 @@ typedef struct WfmLaunch {
 int  wfm_abi_version(void);
 const char* wfm_last_error(void);
 int  wfm_device_count(void);
+int  wfm_trim(void);
 
+/* Uploads the flat IR and runs the device pre-pass.  The host tables may live in
+ * pageable or in pinned memory (cudaHostAlloc / torch pin_memory): pinned tables copy
+ * at link speed.  Device memory comes from a per-device cache inside the library that
+ * wfm_program_destroy returns it to (no cudaMalloc / cudaFree in a scheduler's steady
+ * state); wfm_trim() hands the cached blocks back to the driver. */
 int  wfm_program_create(const WfmProgramDesc* host_ir, int device, wfm_program_t* out);
 int  wfm_program_destroy(wfm_program_t prog);
 int64_t wfm_program_total_samples(wfm_program_t prog);

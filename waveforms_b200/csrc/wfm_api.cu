@@ -9,9 +9,30 @@
 #include <vector>
 #include "wfm_internal.h"
 
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <thread>
+
 namespace {
 
 thread_local char g_err[512] = "";
+
+// WFM_TIMING=1: stage times of the host-side entry points on stderr
+struct StageTimer {
+  bool on;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(const char* w) : on(std::getenv("WFM_TIMING") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* stage) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[wfm] %s: %-22s %8.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -39,65 +60,121 @@ struct DeviceGuard {
   }
 };
 
-template <typename T>
-cudaError_t upload(const T* host, int64_t n, const T** dev) {
-  *dev = nullptr;
-  // always allocate at least one element so kernels never see a null table
-  size_t bytes = sizeof(T) * (size_t)std::max<int64_t>(n, 1);
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) return e;
-  if (n > 0) {
-    e = cudaMemcpy(p, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(p); return e; }
-  } else {
-    cudaMemset(p, 0, bytes);
-  }
-  *dev = static_cast<const T*>(p);
-  return cudaSuccess;
-}
-
 bool known_func(int f) { return (f >= WFM_LINEAR && f <= WFM_DRAG_SINX) || (f >= WFM_COS_SINCOS && f <= WFM_COS_ROT); }
 
 }  // namespace
 
+// ---- per-device cache of device allocations ------------------------------------------------
+// wfm_program_create / wfm_sample_host / wfm_program_destroy run once per batch in a
+// scheduler's steady state; cudaMalloc / cudaFree cost milliseconds each and cudaFree
+// synchronises the device, so freed blocks are kept and reused (best fit, at most 2x the
+// request).  wfm_trim() returns them to the driver.
+namespace pool {
+struct Block {
+  void* p;
+  size_t bytes;
+};
+constexpr int kMaxDevices = 64;
+std::mutex mu;
+std::vector<Block> cache[kMaxDevices];
+
+size_t round_up(size_t bytes) {
+  const size_t g = bytes >= (size_t(1) << 20) ? (size_t(1) << 20) : 4096;  // 1 MiB granules for large blocks
+  return (std::max<size_t>(bytes, 1) + g - 1) / g * g;
+}
+
+void trim_device(int dev) {
+  for (const Block& b : cache[dev]) cudaFree(b.p);
+  cache[dev].clear();
+}
+
+// the current device must be `dev`
+cudaError_t alloc(int dev, size_t bytes, Block* out) {
+  bytes = round_up(bytes);
+  if (dev >= 0 && dev < kMaxDevices) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto& c = cache[dev];
+    int best = -1;
+    for (int i = 0; i < (int)c.size(); ++i)
+      if (c[i].bytes >= bytes && c[i].bytes <= 2 * bytes && (best < 0 || c[i].bytes < c[best].bytes)) best = i;
+    if (best >= 0) {
+      *out = c[best];
+      c.erase(c.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation && dev >= 0 && dev < kMaxDevices) {
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      trim_device(dev);
+    }
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) return e;
+  *out = Block{p, bytes};
+  return cudaSuccess;
+}
+
+void release(int dev, const Block& b) {
+  if (!b.p) return;
+  if (dev < 0 || dev >= kMaxDevices) {
+    cudaFree(b.p);
+    return;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[dev].push_back(b);
+}
+}  // namespace pool
+
 struct WfmProgram {
   int device = 0;
   wfm::DevProgram dev{};
-  std::vector<WfmWave> waves;  // host copy (tile lists, output sizing)
+  std::vector<WfmWave> waves;  // host copy (output sizing, channel ranges)
+  pool::Block arena{nullptr, 0};    // every table of the program
+  pool::Block packets{nullptr, 0};  // the tile packets (sized by the device pre-pass)
+  pool::Block stage{nullptr, 0};    // device staging buffer of wfm_sample_host
   wfm::TileDesc* d_tiles = nullptr;
   std::vector<int64_t> tile_prefix;  // tiles before channel w
   int64_t n_tiles = 0;
   int64_t total_samples = 0;  // extent of the output buffer in samples
   int64_t launches = 0;
-  void* d_stage = nullptr;  // device staging buffer for wfm_sample_host
-  size_t stage_bytes = 0;
   bool any_complex = false;
 
   ~WfmProgram() {
     DeviceGuard g(device);
-    cudaFree((void*)dev.waves);
-    cudaFree((void*)dev.seg_bound);
-    cudaFree((void*)dev.seg_ptr);
-    cudaFree((void*)dev.facs);
-    cudaFree((void*)dev.terms);
-    cudaFree((void*)dev.cterms);
-    cudaFree((void*)dev.seg_plan);
-    cudaFree((void*)dev.row_slot);
-    cudaFree((void*)dev.refs);
-    cudaFree((void*)dev.args);
-    cudaFree((void*)dev.x);
-    cudaFree((void*)dev.seg_start);
-    cudaFree((void*)dev.seg_val);
-    cudaFree((void*)dev.seg_wave);
-    cudaFree((void*)dev.pkt_off);
-    cudaFree((void*)dev.packets);
-    cudaFree(d_tiles);
-    cudaFree(d_stage);
+    // kernels launched through this program (on any stream) may still read the tables;
+    // cudaFree used to wait for them implicitly
+    cudaDeviceSynchronize();
+    pool::release(device, arena);
+    pool::release(device, packets);
+    pool::release(device, stage);
   }
 };
 
-static int validate(const WfmProgramDesc* d) {
+// run fn(lo, hi) over [0, n) on up to 8 host threads; returns the first non-zero result
+template <typename F>
+static int parallel_ranges(int64_t n, F fn) {
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int nt = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), std::max<int64_t>(n / 65536, 1));
+  if (nt <= 1) return fn((int64_t)0, n);
+  std::vector<int> rc(nt, 0);
+  std::vector<std::string> msg(nt);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      rc[t] = fn(n * t / nt, n * (t + 1) / nt);
+      if (rc[t] != 0) msg[t] = g_err;  // g_err is thread-local: carry the message to the caller's thread
+    });
+  for (auto& x : th) x.join();
+  for (int t = 0; t < nt; ++t)
+    if (rc[t] != 0) return fail(rc[t], "%s", msg[t].c_str());
+  return 0;
+}
+
+static int validate(const WfmProgramDesc* d, int* max_rows_out) {
   if (!d) return fail(WFM_EINVAL, "null program descriptor");
   if (d->n_waves < 0 || d->n_segs < 0 || d->n_facs < 0 || d->n_terms < 0 || d->n_refs < 0 || d->n_args < 0 || d->n_x < 0)
     return fail(WFM_EINVAL, "negative table size");
@@ -107,70 +184,78 @@ static int validate(const WfmProgramDesc* d) {
   if ((d->n_waves && !d->waves) || (d->n_segs && (!d->seg_bound || !d->seg_ptr)) || (d->n_facs && !d->facs) ||
       (d->n_terms && !d->terms) || (d->n_refs && !d->refs) || (d->n_args && !d->args) || (d->n_x && !d->x))
     return fail(WFM_EINVAL, "null table pointer with non-zero size");
-  // segment table
-  for (int64_t s = 0; s < d->n_segs; ++s) {
-    const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
-    if (a.fac < 0 || a.term < 0 || b.fac < a.fac || b.term < a.term)
-      return fail(WFM_EINVAL, "segment %lld: pointer table not monotone", (long long)s);
-  }
   if (d->n_segs) {
     const WfmSegPtr e = d->seg_ptr[d->n_segs];
     if (e.fac != d->n_facs || e.term != d->n_terms)
       return fail(WFM_EINVAL, "segment pointer table does not close (%d/%lld factors, %d/%lld terms)", e.fac,
                   (long long)d->n_facs, e.term, (long long)d->n_terms);
   }
-  for (int64_t k = 0; k < d->n_facs; ++k) {
-    const WfmFactor& f = d->facs[k];
-    if (!known_func(f.func)) return fail(WFM_EUNSUPPORTED, "factor %lld: unknown basis id %d", (long long)k, f.func);
-    if (f.arg_off < 0 || f.arg_off > d->n_args)
-      return fail(WFM_EINVAL, "factor %lld: argument offset out of range", (long long)k);
-    if (f.func == WFM_INTERP) {
-      if (f.arg_off + 2 > d->n_args) return fail(WFM_EINVAL, "factor %lld: INTERP header out of range", (long long)k);
-      double n = d->args[f.arg_off];
-      if (!(n >= 1) || f.arg_off + 2 + (int64_t)n > d->n_args)
-        return fail(WFM_EINVAL, "factor %lld: INTERP table out of range", (long long)k);
-    }
-  }
-  // terms and refs, segment by segment (slot indices are segment-relative)
-  for (int64_t s = 0; s < d->n_segs; ++s) {
-    const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
-    const int nf = b.fac - a.fac;
-    for (int k = 0; k < nf; ++k) {
-      const WfmFactor& f = d->facs[a.fac + k];
-      if (f.func == WFM_COS_SINCOS) {
-        if (k + 1 >= nf || d->facs[a.fac + k + 1].func != WFM_NOP)
-          return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it", (long long)s, k);
-      } else if (f.func == WFM_NOP) {
-        if (k == 0 || d->facs[a.fac + k - 1].func != WFM_COS_SINCOS)
-          return fail(WFM_EINVAL, "segment %lld: stray NOP row %d", (long long)s, k);
-      } else if (f.func == WFM_COS_ROT) {
-        if (f.arg_off + 5 > d->n_args) return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: pool out of range", (long long)s, k);
-        const double bs = d->args[f.arg_off];
-        const int base = (int)bs;
-        if (!(bs >= 0) || base >= k || d->facs[a.fac + base].func != WFM_COS_SINCOS ||
-            d->facs[a.fac + base].a0 != f.a0)
-          return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: bad base row", (long long)s, k);
+  int rc = parallel_ranges(d->n_facs, [&](int64_t lo, int64_t hi) {
+    for (int64_t k = lo; k < hi; ++k) {
+      const WfmFactor& f = d->facs[k];
+      if (!known_func(f.func)) return fail(WFM_EUNSUPPORTED, "factor %lld: unknown basis id %d", (long long)k, f.func);
+      if (f.arg_off < 0 || f.arg_off > d->n_args)
+        return fail(WFM_EINVAL, "factor %lld: argument offset out of range", (long long)k);
+      if (f.func == WFM_INTERP) {
+        if (f.arg_off + 2 > d->n_args) return fail(WFM_EINVAL, "factor %lld: INTERP header out of range", (long long)k);
+        double n = d->args[f.arg_off];
+        if (!(n >= 1) || f.arg_off + 2 + (int64_t)n > d->n_args)
+          return fail(WFM_EINVAL, "factor %lld: INTERP table out of range", (long long)k);
       }
     }
-    for (int t = a.term; t < b.term; ++t) {
-      const WfmTerm& tm = d->terms[t];
-      if (tm.n_ref < 0 || tm.ref_begin < 0 || (int64_t)tm.ref_begin + tm.n_ref > d->n_refs)
-        return fail(WFM_EINVAL, "term %d: reference range out of bounds", t);
-      for (int r = tm.ref_begin; r < tm.ref_begin + tm.n_ref; ++r) {
-        const WfmRef& rf = d->refs[r];
-        if (rf.slot < 0 || rf.slot >= nf) return fail(WFM_EINVAL, "ref %d: slot %d outside segment (%d factors)", r, rf.slot, nf);
-        if (d->facs[a.fac + rf.slot].func == WFM_NOP) return fail(WFM_EINVAL, "ref %d: refers to a NOP row", r);
-        if (rf.kind < WFM_POW_ONE || rf.kind > WFM_POW_GEN) return fail(WFM_EINVAL, "ref %d: bad exponent kind", r);
+    return 0;
+  });
+  if (rc != WFM_OK) return rc;
+  // segment table, terms and refs, segment by segment (slot indices are segment-relative)
+  std::atomic<int> max_rows{0};
+  rc = parallel_ranges(d->n_segs, [&](int64_t lo, int64_t hi) {
+    int local_max = 0;
+    for (int64_t s = lo; s < hi; ++s) {
+      const WfmSegPtr a = d->seg_ptr[s], b = d->seg_ptr[s + 1];
+      if (a.fac < 0 || a.term < 0 || b.fac < a.fac || b.term < a.term || b.fac > d->n_facs || b.term > d->n_terms)
+        return fail(WFM_EINVAL, "segment %lld: pointer table not monotone", (long long)s);
+      const int nf = b.fac - a.fac;
+      local_max = std::max(local_max, nf);
+      for (int k = 0; k < nf; ++k) {
+        const WfmFactor& f = d->facs[a.fac + k];
+        if (f.func == WFM_COS_SINCOS) {
+          if (k + 1 >= nf || d->facs[a.fac + k + 1].func != WFM_NOP)
+            return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it", (long long)s, k);
+        } else if (f.func == WFM_NOP) {
+          if (k == 0 || d->facs[a.fac + k - 1].func != WFM_COS_SINCOS)
+            return fail(WFM_EINVAL, "segment %lld: stray NOP row %d", (long long)s, k);
+        } else if (f.func == WFM_COS_ROT) {
+          if (f.arg_off + 5 > d->n_args) return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: pool out of range", (long long)s, k);
+          const double bs = d->args[f.arg_off];
+          const int base = (int)bs;
+          if (!(bs >= 0) || base >= k || d->facs[a.fac + base].func != WFM_COS_SINCOS || d->facs[a.fac + base].a0 != f.a0)
+            return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: bad base row", (long long)s, k);
+        }
       }
+      for (int t = a.term; t < b.term; ++t) {
+        const WfmTerm& tm = d->terms[t];
+        if (tm.n_ref < 0 || tm.ref_begin < 0 || (int64_t)tm.ref_begin + tm.n_ref > d->n_refs)
+          return fail(WFM_EINVAL, "term %d: reference range out of bounds", t);
+        // the sampling kernel walks a segment's references as ONE contiguous slice: packed in term order
+        if (t + 1 < d->n_terms && d->terms[t + 1].ref_begin != tm.ref_begin + tm.n_ref)
+          return fail(WFM_EINVAL, "term %d: references must be packed in term order", t + 1);
+        for (int r = tm.ref_begin; r < tm.ref_begin + tm.n_ref; ++r) {
+          const WfmRef& rf = d->refs[r];
+          if (rf.slot < 0 || rf.slot >= nf) return fail(WFM_EINVAL, "ref %d: slot %d outside segment (%d factors)", r, rf.slot, nf);
+          if (d->facs[a.fac + rf.slot].func == WFM_NOP) return fail(WFM_EINVAL, "ref %d: refers to a NOP row", r);
+          if (rf.kind < WFM_POW_ONE || rf.kind > WFM_POW_GEN) return fail(WFM_EINVAL, "ref %d: bad exponent kind", r);
+        }
+      }
+      if (b.term > a.term && !(d->terms[b.term - 1].flags & WFM_TERM_GROUP_END))
+        return fail(WFM_EINVAL, "segment %lld: last term does not close its group", (long long)s);
     }
-    if (b.term > a.term && !(d->terms[b.term - 1].flags & WFM_TERM_GROUP_END))
-      return fail(WFM_EINVAL, "segment %lld: last term does not close its group", (long long)s);
-  }
-  // the sampling kernel stages a tile's references as ONE contiguous slice: they
-  // must be packed in term order
-  for (int64_t t = 0; t + 1 < d->n_terms; ++t)
-    if (d->terms[t + 1].ref_begin != d->terms[t].ref_begin + d->terms[t].n_ref)
-      return fail(WFM_EINVAL, "term %lld: references must be packed in term order", (long long)(t + 1));
+    int cur = max_rows.load();
+    while (local_max > cur && !max_rows.compare_exchange_weak(cur, local_max)) {
+    }
+    return 0;
+  });
+  if (rc != WFM_OK) return rc;
+  *max_rows_out = max_rows.load();
   for (int64_t w = 0; w < d->n_waves; ++w) {
     const WfmWave& wv = d->waves[w];
     if (wv.n < 0 || wv.out_off < 0) return fail(WFM_EINVAL, "channel %lld: negative extent", (long long)w);
@@ -201,68 +286,47 @@ int wfm_device_count(void) {
   return n;
 }
 
+int wfm_trim(void) {
+  std::lock_guard<std::mutex> lk(pool::mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int dev = 0; dev < pool::kMaxDevices; ++dev) {
+    if (pool::cache[dev].empty()) continue;
+    if (cudaSetDevice(dev) == cudaSuccess) pool::trim_device(dev);
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  cudaGetLastError();
+  return WFM_OK;
+}
+
 int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) {
   if (!out) return fail(WFM_EINVAL, "null output handle");
   *out = nullptr;
-  int rc = validate(d);
+  StageTimer tm("program_create");
+  int max_rows = 0;
+  int rc = validate(d, &max_rows);
   if (rc != WFM_OK) return rc;
+  tm.lap("validate");
   DeviceGuard g(device);
   if (!g.ok) return fail(WFM_ECUDA, "cannot select CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
   WfmProgram* p = new (std::nothrow) WfmProgram();
   if (!p) return fail(WFM_ENOMEM, "out of host memory");
   p->device = device;
   p->waves.assign(d->waves, d->waves + d->n_waves);
-
-  cudaError_t e = cudaSuccess;
-  auto up = [&](auto host, int64_t n, auto dev) {
-    if (e == cudaSuccess) e = upload(host, n, dev);
-  };
-  up(d->waves, d->n_waves, &p->dev.waves);
-  up(d->seg_bound, d->n_segs, &p->dev.seg_bound);
-  up(d->seg_ptr, d->n_segs ? d->n_segs + 1 : 0, &p->dev.seg_ptr);
-  up(d->facs, d->n_facs, &p->dev.facs);
-  up(d->terms, d->n_terms, &p->dev.terms);
-  up(d->refs, d->n_refs, &p->dev.refs);
-  up(d->args, d->n_args, &p->dev.args);
-  up(d->x, d->n_x, &p->dev.x);
-
-  // owning channel of every segment row (pre-pass only) and the widest segment
-  int max_rows = 0;
-  {
-    std::vector<int32_t> seg_wave((size_t)d->n_segs, 0);
-    for (int64_t w = 0; w < d->n_waves; ++w) {
-      const WfmWave& wv = d->waves[w];
-      std::fill(seg_wave.begin() + wv.seg_begin, seg_wave.begin() + wv.seg_begin + wv.n_seg, (int32_t)w);
-    }
-    for (int64_t sg = 0; sg < d->n_segs; ++sg)
-      max_rows = std::max(max_rows, (int)(d->seg_ptr[sg + 1].fac - d->seg_ptr[sg].fac));
-    up(seg_wave.data(), d->n_segs, &p->dev.seg_wave);
-  }
   p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
-  int32_t* d_seg_start = nullptr;
-  double* d_seg_val = nullptr;
-  wfm::SegPlan* d_seg_plan = nullptr;
-  uint8_t* d_row_slot = nullptr;
-  wfm::CTerm* d_cterms = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc(&d_seg_start, sizeof(int32_t) * (size_t)std::max<int64_t>(d->n_segs, 1));
-  if (e == cudaSuccess) e = cudaMalloc(&d_seg_val, sizeof(double) * (size_t)std::max<int64_t>(d->n_segs, 1));
-  if (e == cudaSuccess) e = cudaMalloc(&d_seg_plan, sizeof(wfm::SegPlan) * (size_t)std::max<int64_t>(d->n_segs, 1));
-  if (e == cudaSuccess) e = cudaMalloc(&d_row_slot, (size_t)std::max<int64_t>(d->n_facs, 16));
-  if (e == cudaSuccess) e = cudaMalloc(&d_cterms, sizeof(wfm::CTerm) * (size_t)std::max<int64_t>(d->n_terms, 1));
-  p->dev.seg_start = d_seg_start;
-  p->dev.seg_val = d_seg_val;
-  p->dev.seg_plan = d_seg_plan;
-  p->dev.row_slot = d_row_slot;
-  p->dev.cterms = d_cterms;
 
   // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample),
-  // the value slots and two packet buffers (the tile's rows of the device tables,
-  // double-buffered).  Take the largest tile (a multiple of 128 samples) whose AVERAGE
-  // packet leaves a 4x margin in a packet buffer for tiles where pulses cluster; a tile
-  // whose packet still does not fit takes the kernel's cold path.
+  // the value slots and two packet buffers (double-buffered).  Take the largest tile (a
+  // multiple of 128 samples) whose AVERAGE packet leaves a 4x margin in a packet buffer
+  // for tiles where pulses cluster; a tile whose packet still does not fit takes the
+  // kernel's cold path.
+  int64_t samples = 0, total = 0;
+  for (int64_t w = 0; w < d->n_waves; ++w) {
+    samples += d->waves[w].n;
+    total = std::max(total, d->waves[w].out_off + d->waves[w].n);
+    if (d->waves[w].flags & WFM_WAVE_COMPLEX) p->any_complex = true;
+  }
   {
-    int64_t samples = 0;
-    for (int64_t w = 0; w < d->n_waves; ++w) samples += d->waves[w].n;
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
     const double ir = ((double)d->n_facs * 40.0 /* SRow 16, RRow 64, GRow 32; NOP rows vanish */ +
                        (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
@@ -276,53 +340,98 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     p->dev.pkt_cap = std::max(cap, 64);
   }
   const int64_t tile_samples = p->dev.tile_samples;
-  // tile list: tile_samples consecutive samples of one channel per tile
-  std::vector<wfm::TileDesc> tiles;
+  // tiles: tile_samples consecutive samples of one channel; only the per-channel prefix is
+  // built here, the tile rows are generated on the device
   p->tile_prefix.resize(d->n_waves + 1);
-  int64_t total = 0;
+  int64_t n_tiles = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
-    p->tile_prefix[w] = (int64_t)tiles.size();
-    const WfmWave& wv = d->waves[w];
-    for (int64_t j = 0; j < wv.n; j += tile_samples)
-      tiles.push_back({j, wv.out_off + j, (int32_t)w, (int32_t)std::min<int64_t>(tile_samples, wv.n - j), 0, 0});
-    total = std::max(total, wv.out_off + wv.n);
-    if (wv.flags & WFM_WAVE_COMPLEX) p->any_complex = true;
+    p->tile_prefix[w] = n_tiles;
+    n_tiles += (d->waves[w].n + tile_samples - 1) / tile_samples;
   }
-  p->tile_prefix[d->n_waves] = (int64_t)tiles.size();
-  p->n_tiles = (int64_t)tiles.size();
+  p->tile_prefix[d->n_waves] = n_tiles;
+  p->n_tiles = n_tiles;
   p->total_samples = total;
-  if (e == cudaSuccess && p->n_tiles >= INT32_MAX) {
-    const long long nt = (long long)p->n_tiles;
+  if (n_tiles >= INT32_MAX) {
     delete p;
-    return fail(WFM_EINVAL, "too many tiles (%lld)", nt);
+    return fail(WFM_EINVAL, "too many tiles (%lld)", (long long)n_tiles);
   }
-  if (e == cudaSuccess) {
-    const wfm::TileDesc* dt = nullptr;
-    e = upload(tiles.data(), (int64_t)tiles.size(), &dt);
-    p->d_tiles = const_cast<wfm::TileDesc*>(dt);
+
+  // ONE arena for every table (ABI tables + the tables the pre-pass derives), 256-byte aligned slots
+  size_t arena_bytes = 0;
+  auto reserve = [&](size_t bytes) {
+    const size_t off = arena_bytes;
+    arena_bytes += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    return off;
+  };
+  const size_t nt1 = (size_t)n_tiles + 1;
+  const size_t o_waves = reserve(sizeof(WfmWave) * d->n_waves), o_bound = reserve(sizeof(double) * d->n_segs),
+               o_segptr = reserve(sizeof(WfmSegPtr) * (d->n_segs + 1)), o_facs = reserve(sizeof(WfmFactor) * d->n_facs),
+               o_terms = reserve(sizeof(WfmTerm) * d->n_terms), o_refs = reserve(sizeof(WfmRef) * d->n_refs),
+               o_args = reserve(sizeof(double) * d->n_args), o_x = reserve(sizeof(double) * d->n_x),
+               o_segwave = reserve(sizeof(int32_t) * d->n_segs), o_segstart = reserve(sizeof(int32_t) * d->n_segs),
+               o_segval = reserve(sizeof(double) * d->n_segs), o_plan = reserve(sizeof(wfm::SegPlan) * d->n_segs),
+               o_rowslot = reserve((size_t)d->n_facs), o_cterms = reserve(sizeof(wfm::CTerm) * d->n_terms),
+               o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_tiles = reserve(sizeof(wfm::TileDesc) * n_tiles),
+               o_pktsize = reserve(sizeof(uint32_t) * nt1), o_pktoff = reserve(sizeof(uint32_t) * nt1),
+               o_scratch = reserve(sizeof(uint32_t) * (nt1 / 4096 + 2));
+  cudaError_t e = pool::alloc(device, arena_bytes, &p->arena);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(e == cudaErrorMemoryAllocation ? WFM_ENOMEM : WFM_ECUDA, "allocating %zu bytes for the program failed: %s",
+                arena_bytes, cudaGetErrorString(e));
   }
-  // device pre-pass 1: segment start positions and flat values, device table formats,
-  // every tile's segment range and packet size; then the packet offsets (exclusive scan)
-  uint32_t *d_pkt_size = nullptr, *d_pkt_off = nullptr, *d_scratch = nullptr;
-  const size_t nt1 = (size_t)p->n_tiles + 1;
-  if (e == cudaSuccess) e = cudaMalloc(&d_pkt_size, sizeof(uint32_t) * nt1);
-  if (e == cudaSuccess) e = cudaMalloc(&d_pkt_off, sizeof(uint32_t) * nt1);
-  if (e == cudaSuccess) e = cudaMalloc(&d_scratch, sizeof(uint32_t) * (nt1 / 4096 + 2));
-  p->dev.pkt_off = d_pkt_off;
+  char* base = (char*)p->arena.p;
+  auto up = [&](size_t off, const void* host, size_t bytes) {
+    // pinned host tables (cudaHostAlloc / torch pin_memory) copy at link speed; pageable ones are staged by the driver
+    if (e == cudaSuccess && bytes > 0) e = cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, 0);
+  };
+  up(o_waves, d->waves, sizeof(WfmWave) * d->n_waves);
+  up(o_bound, d->seg_bound, sizeof(double) * d->n_segs);
+  up(o_segptr, d->seg_ptr, d->n_segs ? sizeof(WfmSegPtr) * (d->n_segs + 1) : 0);
+  up(o_facs, d->facs, sizeof(WfmFactor) * d->n_facs);
+  up(o_terms, d->terms, sizeof(WfmTerm) * d->n_terms);
+  up(o_refs, d->refs, sizeof(WfmRef) * d->n_refs);
+  up(o_args, d->args, sizeof(double) * d->n_args);
+  up(o_x, d->x, sizeof(double) * d->n_x);
+  up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
+  p->dev.waves = (const WfmWave*)(base + o_waves);
+  p->dev.seg_bound = (const double*)(base + o_bound);
+  p->dev.seg_ptr = (const WfmSegPtr*)(base + o_segptr);
+  p->dev.facs = (const WfmFactor*)(base + o_facs);
+  p->dev.terms = (const WfmTerm*)(base + o_terms);
+  p->dev.refs = (const WfmRef*)(base + o_refs);
+  p->dev.args = (const double*)(base + o_args);
+  p->dev.x = (const double*)(base + o_x);
+  p->dev.seg_wave = (const int32_t*)(base + o_segwave);
+  p->dev.seg_start = (const int32_t*)(base + o_segstart);
+  p->dev.seg_val = (const double*)(base + o_segval);
+  p->dev.seg_plan = (const wfm::SegPlan*)(base + o_plan);
+  p->dev.row_slot = (const uint8_t*)(base + o_rowslot);
+  p->dev.cterms = (const wfm::CTerm*)(base + o_cterms);
+  p->dev.pkt_off = (const uint32_t*)(base + o_pktoff);
+  p->d_tiles = (wfm::TileDesc*)(base + o_tiles);
+  tm.lap("arena + uploads");
+
+  // device pre-pass 1: owning channel of every segment, segment start positions and flat
+  // values, segment plans, the tile rows with their packet sizes; then the packet offsets
+  wfm::PrepareBuffers pb{(int32_t*)(base + o_segwave), (int32_t*)(base + o_segstart), (double*)(base + o_segval),
+                         (wfm::SegPlan*)(base + o_plan), (uint8_t*)(base + o_rowslot), (wfm::CTerm*)(base + o_cterms),
+                         p->d_tiles, (const int64_t*)(base + o_prefix), (uint32_t*)(base + o_pktsize)};
   if (e == cudaSuccess)
-    e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_segs, d->n_facs, d->n_terms, p->n_tiles}, d_seg_start,
-                            d_seg_val, d_seg_plan, d_row_slot, d_cterms, p->d_tiles, d_pkt_size, 0);
-  if (e == cudaSuccess) e = wfm::launch_scan(d_pkt_size, d_pkt_off, d_scratch, p->n_tiles, 0);
+    e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_waves, d->n_segs, d->n_facs, d->n_terms, n_tiles}, pb, 0);
+  if (e == cudaSuccess)
+    e = wfm::launch_scan((uint32_t*)(base + o_pktsize), (uint32_t*)(base + o_pktoff), (uint32_t*)(base + o_scratch), n_tiles, 0);
   uint32_t total16 = 0;
-  if (e == cudaSuccess) e = cudaMemcpy(&total16, d_pkt_off + p->n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost);
-  // pass 2: the packets themselves
-  unsigned char* d_packets = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc(&d_packets, std::max<size_t>((size_t)total16 * 16, 16));
-  p->dev.packets = d_packets;
-  if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, p->n_tiles, d_packets, 0);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&total16, (uint32_t*)(base + o_pktoff) + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
   if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  cudaFree(d_pkt_size);
-  cudaFree(d_scratch);
+  tm.lap("device pre-pass 1");
+  // pass 2: the packets themselves
+  if (e == cudaSuccess) e = pool::alloc(device, std::max<size_t>((size_t)total16 * 16, 16), &p->packets);
+  p->dev.packets = (const unsigned char*)p->packets.p;
+  if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, n_tiles, (unsigned char*)p->packets.p, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  tm.lap("device pre-pass 2");
   if (e != cudaSuccess) {
     delete p;
     return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));
@@ -332,7 +441,9 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
 }
 
 int wfm_program_destroy(wfm_program_t prog) {
+  StageTimer tm("program_destroy");
   delete prog;
+  tm.lap("release");
   return WFM_OK;
 }
 
@@ -377,6 +488,7 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   int rc = check_launch(prog, l, &first, &count, &need);
   if (rc != WFM_OK) return rc;
   if (l->accumulate) return fail(WFM_EUNSUPPORTED, "accumulate is not available with host buffers");
+  StageTimer tm("sample_host");
   DeviceGuard g(prog->device);
   const size_t esz = l->dtype == WFM_F64 ? 8 : (l->dtype == WFM_F32 ? 4 : 16);
   // only the extent actually covered by the requested channels is staged/copied
@@ -384,21 +496,22 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   for (int64_t w = first; w < first + count; ++w) lo = std::min(lo, prog->waves[w].out_off);
   if (count == 0 || need == 0) return WFM_OK;
   const size_t bytes = (size_t)need * esz;
-  if (prog->stage_bytes < bytes) {
-    cudaFree(prog->d_stage);
-    prog->d_stage = nullptr;
-    prog->stage_bytes = 0;
-    WFM_CUDA(cudaMalloc(&prog->d_stage, bytes));
-    prog->stage_bytes = bytes;
+  if (prog->stage.bytes < bytes) {
+    pool::release(prog->device, prog->stage);
+    prog->stage = pool::Block{nullptr, 0};
+    cudaError_t ea = pool::alloc(prog->device, bytes, &prog->stage);
+    if (ea != cudaSuccess) return fail(WFM_ENOMEM, "allocating the %zu-byte staging buffer failed: %s", bytes, cudaGetErrorString(ea));
   }
+  tm.lap("stage alloc");
   // padding between channels is never written by the kernel: keep it defined
-  WFM_CUDA(cudaMemsetAsync((char*)prog->d_stage + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, 0));
+  WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, 0));
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->d_stage, 0));
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->stage.p, 0));
   if (t1 > t0) prog->launches += 1;
-  WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->d_stage + (size_t)lo * esz,
+  WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->stage.p + (size_t)lo * esz,
                            (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, 0));
   WFM_CUDA(cudaStreamSynchronize(0));
+  tm.lap("memset+kernel+D2H");
   return WFM_OK;
 }
 

@@ -165,14 +165,26 @@ struct TileDesc {
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
 struct PrepareCounts {
-  int64_t n_segs, n_facs, n_terms, n_tiles;
+  int64_t n_waves, n_segs, n_facs, n_terms, n_tiles;
 };
 
-// pass 1: segment start positions, flat values, segment plans, slot map, compact terms,
-// every tile's segment range and packet size (16-byte units) -> pkt_size[n_tiles]
-cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, int32_t* seg_start, double* seg_val,
-                           SegPlan* seg_plan, uint8_t* row_slot, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size,
-                           cudaStream_t stream);
+// tables the pre-pass writes (device pointers into the program's arena)
+struct PrepareBuffers {
+  int32_t* seg_wave;
+  int32_t* seg_start;
+  double* seg_val;
+  SegPlan* seg_plan;
+  uint8_t* row_slot;
+  CTerm* cterms;
+  TileDesc* tiles;
+  const int64_t* tile_prefix;  // [n_waves + 1] tiles before channel w (host-built)
+  uint32_t* pkt_size;          // [n_tiles + 1]
+};
+
+// pass 1: owning channel of every segment, segment start positions, flat values, segment
+// plans, slot map, compact terms, the tile rows with their segment range and packet size
+// (16-byte units) -> pkt_size[n_tiles]
+cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream);
 // exclusive scan: pkt_size[n] -> pkt_off[n + 1] (pkt_off[n] = total); scratch holds ceil(n / 4096) + 1 words
 cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* scratch, int64_t n, cudaStream_t stream);
 // pass 2: write the packets

@@ -350,6 +350,14 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
 }
 
 // ---- pre-pass (once per program) ----------------------------------------------------------
+// one warp per channel: the owning channel of each of its segment rows
+__global__ void mark_seg_wave_kernel(DevProgram P, int32_t* __restrict__ seg_wave, int64_t n_waves) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_waves) return;
+  const int seg_begin = P.waves[w].seg_begin, n_seg = P.waves[w].n_seg;
+  for (int k = threadIdx.x & 31; k < n_seg; k += 32) seg_wave[seg_begin + k] = (int32_t)w;
+}
+
 // one thread per segment: start position, value of a flat segment, plan of an active one
 __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_start, double* __restrict__ seg_val,
                                         SegPlan* __restrict__ seg_plan, uint8_t* __restrict__ row_slot,
@@ -474,13 +482,24 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
   return L;
 }
 
-// one thread per tile: the segment rows it spans, its packet size
-__global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, int64_t n_tiles,
-                                     uint32_t* __restrict__ pkt_size) {
+// one thread per tile: the tile row itself (channel, sample range), the segment rows it
+// spans, its packet size
+__global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, const int64_t* __restrict__ tile_prefix,
+                                     int64_t n_waves, int64_t n_tiles, uint32_t* __restrict__ pkt_size) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  TileDesc td = tiles[t];
-  const WfmWave w = P.waves[td.wave];
+  // the channel whose tile range holds t: last w with tile_prefix[w] <= t (channels without samples own no tile)
+  int64_t lo_w = 0, hi_w = n_waves - 1;
+  while (lo_w < hi_w) {
+    const int64_t mid = (lo_w + hi_w + 1) >> 1;
+    if (tile_prefix[mid] <= t) lo_w = mid; else hi_w = mid - 1;
+  }
+  const WfmWave w = P.waves[lo_w];
+  TileDesc td;
+  td.j0 = (t - tile_prefix[lo_w]) * (int64_t)P.tile_samples;
+  td.out0 = w.out_off + td.j0;
+  td.wave = (int32_t)lo_w;
+  td.cnt = (int32_t)min((int64_t)P.tile_samples, w.n - td.j0);
   const int32_t* st = P.seg_start + w.seg_begin;
   const int lo = owning_segment(st, w.n_seg, td.j0);
   const int hi = max(lo, owning_segment(st, w.n_seg, td.j0 + td.cnt - 1));
@@ -903,14 +922,15 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(const __grid_cons
   }
 }
 
-cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, int32_t* seg_start, double* seg_val,
-                           SegPlan* seg_plan, uint8_t* row_slot, CTerm* cterms, TileDesc* tiles, uint32_t* pkt_size,
-                           cudaStream_t stream) {
+cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream) {
   const int threads = 128;
   auto blocks = [&](int64_t items) { return (unsigned)((items + threads - 1) / threads); };
+  if (n.n_waves > 0 && n.n_segs > 0) mark_seg_wave_kernel<<<blocks(n.n_waves * 32), threads, 0, stream>>>(P, b.seg_wave, n.n_waves);
   if (n.n_segs > 0)
-    prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, seg_start, seg_val, seg_plan, row_slot, cterms, n.n_segs);
-  if (n.n_tiles > 0) prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, tiles, n.n_tiles, pkt_size);
+    prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, b.seg_start, b.seg_val, b.seg_plan, b.row_slot, b.cterms,
+                                                                      n.n_segs);
+  if (n.n_tiles > 0)
+    prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, b.tiles, b.tile_prefix, n.n_waves, n.n_tiles, b.pkt_size);
   return cudaGetLastError();
 }
 

@@ -56,7 +56,7 @@ _lib = None
 _lib_lock = threading.Lock()
 
 EXPORTS = [
-    'wfm_abi_version', 'wfm_last_error', 'wfm_device_count',
+    'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
     'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c'

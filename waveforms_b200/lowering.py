@@ -109,10 +109,30 @@ class LoweredBatch:
     total_samples: int
     any_complex: bool
 
+    _TABLES = ('waves', 'seg_bound', 'seg_ptr', 'facs', 'terms', 'refs', 'args',
+               'x')
+
     def nbytes(self):
-        return sum(a.nbytes for a in (self.waves, self.seg_bound, self.seg_ptr,
-                                      self.facs, self.terms, self.refs,
-                                      self.args, self.x))
+        return sum(getattr(self, k).nbytes for k in self._TABLES)
+
+    def pin(self):
+        """Copy of this batch whose tables live in ONE page-locked host buffer
+        (torch owns it), so ``wfm_program_create`` uploads them at link speed."""
+        import torch
+        sizes = [(k, getattr(self, k)) for k in self._TABLES]
+        total = sum((a.nbytes + 255) & ~255 for _, a in sizes)
+        buf = torch.empty(max(total, 256), dtype=torch.uint8, pin_memory=True)
+        host = buf.numpy()
+        out, off = {}, 0
+        for k, a in sizes:
+            view = host[off:off + a.nbytes].view(a.dtype)
+            view[...] = np.ascontiguousarray(a).reshape(-1)
+            out[k] = view
+            off += (a.nbytes + 255) & ~255
+        b = LoweredBatch(total_samples=self.total_samples,
+                         any_complex=self.any_complex, **out)
+        b._pinned = buf  # keeps the buffer alive
+        return b
 
 
 # ---------------------------------------------------------------------------
