@@ -50,6 +50,7 @@
 #include "wfm_multidrag.cuh"
 #include "wfm_internal.h"
 
+
 namespace wfm {
 
 constexpr int kThreads = 256;  // 8 autonomous warps per CTA
@@ -98,9 +99,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 // shared -> global, write-once data: L2 evict-first
-__device__ __forceinline__ void bulk_s2g_evict_first(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ void bulk_s2g_evict_first(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t policy) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
                "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
                : "memory");
@@ -693,6 +697,40 @@ __device__ __forceinline__ void fill_run(OutT* __restrict__ s_out, int a, int b,
   for (int p = a_al + lane * V; p < b_al; p += 32 * V) fill_vec(s_out + p, val);
 }
 
+// n_rows 512-byte rows of the warp's tile buffer <- val: every lane stores 16 bytes per
+// row, fully unrolled per size so that the fill is n_rows stores and nothing else
+template <int R>
+__device__ __forceinline__ void fill_rows(unsigned char* p, uint4 v) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) *reinterpret_cast<uint4*>(p + r * 512) = v;
+}
+__device__ __forceinline__ void fill_tile(unsigned char* p, int n_rows, double val, bool f32) {
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (__double_as_longlong(val) != 0) {
+    if (f32) {
+      v.x = v.y = v.z = v.w = __float_as_uint((float)val);
+    } else {
+      v.x = v.z = (uint32_t)__double2loint(val);
+      v.y = v.w = (uint32_t)__double2hiint(val);
+    }
+  }
+  switch (n_rows) {  // tile_samples is a multiple of 128: 2 rows each in fp64, 1 row in fp32
+    case 16: fill_rows<16>(p, v); break;
+    case 14: fill_rows<14>(p, v); break;
+    case 12: fill_rows<12>(p, v); break;
+    case 10: fill_rows<10>(p, v); break;
+    case 8: fill_rows<8>(p, v); break;
+    case 7: fill_rows<7>(p, v); break;
+    case 6: fill_rows<6>(p, v); break;
+    case 5: fill_rows<5>(p, v); break;
+    case 4: fill_rows<4>(p, v); break;
+    case 3: fill_rows<3>(p, v); break;
+    case 2: fill_rows<2>(p, v); break;
+    case 1: fill_rows<1>(p, v); break;
+    default: break;
+  }
+}
+
 // per-warp shared-memory slice (dynamic shared memory; all sub-arrays 16-byte aligned):
 //   [out: tile_samples x OutT][slots: n_slots x kSlotStride][packet buffer 0][packet buffer 1][2 mbarriers]
 __host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int pkt_cap, size_t esz) {
@@ -753,8 +791,11 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   }
   __syncwarp();
 
-  // packet of the first tile -> buffer 0; offsets of the second tile -> registers
-  uint32_t off_next = 0, end_next = 0;  // packet of tile t + n_warps, 16-byte units
+  // packet pipeline: tile t's packet is in flight into buffer 0, tile t+G's offsets sit in
+  // registers (its packet goes into the other buffer at the top of iteration t).  The kernel
+  // sits exactly at its 128-register budget: a third pipeline stage (L2 prefetch of tile
+  // t+2G) or a hoisted L2 policy register spill in this loop and cost 4-9 % (measured)
+  uint32_t off_next = 0, end_next = 0;    // packet of tile t + G, 16-byte units
   {
     const uint32_t o0 = P.pkt_off[t], o1 = P.pkt_off[t + 1];
     if (lane == 0) {
@@ -807,19 +848,10 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     if (lane == 0 && store_pending) bulk_wait_read_all();
     __syncwarp();
 
-    // base fill: the whole tile <- the zero-segment value; flat segments with another
-    // value and the active samples overwrite it below
-    {
-      const int n_fill = (cnt + V - 1) & ~(V - 1);  // the tile buffer is a multiple of V
-      if (__double_as_longlong(base) == 0) {
-        // +0.0, the usual case: 16-byte stores of the zero register
-#pragma unroll 4
-        for (int p = lane * V; p < n_fill; p += 32 * V) *reinterpret_cast<uint4*>(s_out + p) = make_uint4(0u, 0u, 0u, 0u);
-      } else {
-#pragma unroll 1
-        for (int p = lane * V; p < n_fill; p += 32 * V) fill_vec(s_out + p, base);
-      }
-    }
+    // base fill: the whole tile BUFFER (tile_samples, a multiple of 128) <- the zero-segment
+    // value; flat segments with another value and the active samples overwrite it below
+    fill_tile(reinterpret_cast<unsigned char*>(s_out) + lane * 16, P.tile_samples * (int)sizeof(OutT) / 512, base,
+              sizeof(OutT) == 4);
     __syncwarp();
 
     const ARow* __restrict__ arows = reinterpret_cast<const ARow*>(pk + sizeof(PacketHeader));
@@ -884,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       __syncwarp();
       const int n_bulk = cnt & ~(V - 1);  // 16-byte multiple; the ragged tail goes out as scalars
       if (lane == 0 && n_bulk > 0) {
-        bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT));
+        bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT), l2_evict_first_policy());
         store_pending = true;
       }
       if (n_bulk + lane < cnt) dst[n_bulk + lane] = s_out[n_bulk + lane];
