@@ -276,6 +276,7 @@ def main():
     tdt = torch.float64 if args.dtype == 'f64' else torch.float32
 
     prog = engine.Program(batch, local_rank)
+    kernel_layout = prog.info()
     out = torch.empty(batch.total_samples, dtype=tdt, device=f'cuda:{local_rank}')
     stream = torch.cuda.current_stream()
 
@@ -378,6 +379,7 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
             'data': 'synthetic', 'config': config, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofline, 'cpu_baseline': cpu,
+            'kernel_layout': kernel_layout,
             'host': {'frame_build_s': t_build, 'frame_lower_s': t_lower, 'ir_bytes': int(batch.nbytes()),
                      'checksum_ch0': checksum}}
     print(json.dumps(line), flush=True)

@@ -176,6 +176,10 @@ int  wfm_program_destroy(wfm_program_t prog);
 int64_t wfm_program_total_samples(wfm_program_t prog);
 /* number of kernel launches issued through this program so far */
 int64_t wfm_program_launch_count(wfm_program_t prog);
+/* how the program was laid out for the sampling kernel: out[0..n) of
+ * {tile_samples, packet_buffer_bytes, value_slots, n_tiles, packet_area_bytes,
+ *  table_arena_bytes, samples_per_lane_unit, shared_bytes_per_cta}, n <= 8 */
+int  wfm_program_info(wfm_program_t prog, int64_t* out, int32_t n);
 
 int  wfm_sample(wfm_program_t prog, const WfmLaunch* launch, void* stream);
 int  wfm_sample_host(wfm_program_t prog, const WfmLaunch* launch);

@@ -12,7 +12,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 LIB = HERE / 'libwfmb200.so'
 SOURCES = ['wfm_api.cu', 'wfm_sample.cu', 'wfm_iir.cu', 'wfm_fft.cu']
-HEADERS = ['wfm_internal.h', 'wfm_basis.cuh', 'wfm_math.cuh', 'wfm_multidrag.cuh',
+HEADERS = ['wfm_internal.h', 'wfm_basis.cuh', 'wfm_math.cuh', 'wfm_multidrag.cuh', 'wfm_erf_table.h',
            '../../include/wfm_b200.h']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',

@@ -451,6 +451,15 @@ int64_t wfm_program_total_samples(wfm_program_t prog) { return prog ? prog->tota
 
 int64_t wfm_program_launch_count(wfm_program_t prog) { return prog ? prog->launches : -1; }
 
+int wfm_program_info(wfm_program_t prog, int64_t* out, int32_t n) {
+  if (!prog || !out) return fail(WFM_EINVAL, "null program or output");
+  const int64_t v[8] = {prog->dev.tile_samples, prog->dev.pkt_cap, prog->dev.n_slots, prog->n_tiles,
+                        (int64_t)prog->packets.bytes, (int64_t)prog->arena.bytes, wfm::kUnit,
+                        (int64_t)wfm::sample_smem_bytes(prog->dev, WFM_F64)};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  return WFM_OK;
+}
+
 static int check_launch(wfm_program_t prog, const WfmLaunch* l, int64_t* first, int64_t* count, int64_t* need) {
   if (!prog || !l) return fail(WFM_EINVAL, "null program or launch");
   const int64_t nw = (int64_t)prog->waves.size();

@@ -26,8 +26,15 @@ namespace wfm {
 constexpr int kUnit = WFM_K1_UNIT;
 constexpr int kMinTileSamples = 128;
 constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
-// shared memory per warp: 8 * WFM_K1_MIN_BLOCKS warps share the SM's 227 KB (1 KB per CTA is reserved)
-constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024) / 8) & ~127;
+// shared memory per warp: 8 * WFM_K1_MIN_BLOCKS warps share the SM's 227 KB (1 KB per CTA is reserved
+// by the driver, 2.5 KB hold the CTA's copy of the erf coefficient table)
+// 1: the CTA keeps a shared-memory copy of the erf coefficient table (2.5 KB).  Measured
+// within noise of reading it through L1 (610 vs 616 GSa/s on cfg2), so the default leaves
+// the shared memory to the packet buffers.
+#ifndef WFM_K1_ERF_SMEM
+#define WFM_K1_ERF_SMEM 0
+#endif
+constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K1_ERF_SMEM ? 2560 : 0)) / 8) & ~127;
 
 // Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of kUnit
 // doubles in the warp's shared slice, slot-major (slot k of lane l at byte

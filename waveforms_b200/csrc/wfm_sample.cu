@@ -246,7 +246,8 @@ static __device__ __noinline__ double term_product_ext(const DevProgram& P, int 
 // lane's value slots (slot k at sl + k * kSlotStride, slot 0 holds 1.0).
 __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                          bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
-                                         const double (&x)[kUnit], unsigned char* __restrict__ sl) {
+                                         const double (&x)[kUnit], unsigned char* __restrict__ sl,
+                                         const double* __restrict__ erf_s) {
   unsigned char* dst = sl + kSlotStride;  // slot 1
   // -- one range reduction + both polynomials per frequency
   const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(blk);
@@ -306,7 +307,7 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
       for (int u = 0; u < kUnit; ++u) r.v[u] = f_gaussian(sub(x[u], shift), a0);
     } else if (func == WFM_ERF) {
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) r.v[u] = erf(dvd(sub(x[u], shift), a0));
+      for (int u = 0; u < kUnit; ++u) r.v[u] = erf_tab(dvd(sub(x[u], shift), a0), erf_s);
     } else {
       const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
 #pragma unroll 1
@@ -774,6 +775,16 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
   unsigned char* sl = s_slots + lane * 8 * kUnit;  // this lane's value slots
 
+  // the erf coefficient table next to the tile buffers (global / L1 latency showed up as
+  // long-scoreboard stalls in the generic rows); the only block-level barrier of the kernel
+#if WFM_K1_ERF_SMEM
+  __shared__ double s_erf[kErfIntervals * (kErfDegree + 1)];
+  for (int i = threadIdx.x; i < kErfIntervals * (kErfDegree + 1); i += kThreads) s_erf[i] = (&kErfTab[0][0])[i];
+  __syncthreads();
+#else
+  const double* s_erf = &kErfTab[0][0];
+#endif
+
   const int n_warps = gridDim.x * kWarpsPerCta;
   int t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
   if (t >= tile_end) return;
@@ -815,7 +826,8 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   for (; t < tile_end; t += n_warps) {
     const unsigned char* pk = s_pkt + (size_t)buf * P.pkt_cap;
     // prefetch: the next tile's packet into the other buffer (its previous tile is done:
-    // every lane passed the __syncwarp that ends an iteration), the offsets of the tile after
+    // every lane passed the __syncwarp that ends an iteration), the offsets of the tile after.
+    // (Per-lane cp.async instead of the bulk copy was measured 5 % slower.)
     if (t + n_warps < tile_end) {
       if (lane == 0) {
         mbar_expect_tx(s_bar + (buf ^ 1), (end_next - off_next) * 16u);
@@ -897,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           }
         } else {
           r = eval_unit(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
-                        (int)rw.w, we, x, sl);
+                        (int)rw.w, we, x, sl, s_erf);
         }
 #pragma unroll
         for (int u = 0; u < kUnit; ++u)

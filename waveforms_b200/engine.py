@@ -58,7 +58,7 @@ _lib_lock = threading.Lock()
 EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
-    'wfm_program_launch_count', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
+    'wfm_program_launch_count', 'wfm_program_info', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
     'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c'
 ]
 
@@ -86,6 +86,7 @@ def load_library():
         lib.wfm_program_total_samples.restype = C.c_int64
         lib.wfm_program_launch_count.argtypes = [C.c_void_p]
         lib.wfm_program_launch_count.restype = C.c_int64
+        lib.wfm_program_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
         lib.wfm_sample.argtypes = [C.c_void_p, C.POINTER(_Launch), C.c_void_p]
         lib.wfm_sample_host.argtypes = [C.c_void_p, C.POINTER(_Launch)]
         lib.wfm_sosfilt.argtypes = [
@@ -213,6 +214,14 @@ class Program:
     @property
     def launch_count(self):
         return int(self._lib.wfm_program_launch_count(self._h))
+
+    def info(self):
+        """Layout chosen for the sampling kernel (wfm_program_info)."""
+        out = (C.c_int64 * 8)()
+        _check(self._lib.wfm_program_info(self._h, out, 8))
+        keys = ('tile_samples', 'packet_buffer_bytes', 'value_slots', 'n_tiles', 'packet_area_bytes',
+                'table_arena_bytes', 'samples_per_lane_unit', 'shared_bytes_per_cta')
+        return dict(zip(keys, (int(v) for v in out)))
 
     def default_dtype(self):
         return WFM_C128 if self.batch.any_complex else WFM_F64
