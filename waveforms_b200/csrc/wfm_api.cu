@@ -215,9 +215,10 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
       if (a.fac < 0 || a.term < 0 || b.fac < a.fac || b.term < a.term || b.fac > d->n_facs || b.term > d->n_terms)
         return fail(WFM_EINVAL, "segment %lld: pointer table not monotone", (long long)s);
       const int nf = b.fac - a.fac;
-      local_max = std::max(local_max, nf);
+      int n_values = 0;  // value slots the segment needs: every row but the sine placeholders
       for (int k = 0; k < nf; ++k) {
         const WfmFactor& f = d->facs[a.fac + k];
+        n_values += f.func != WFM_NOP;
         if (f.func == WFM_COS_SINCOS) {
           if (k + 1 >= nf || d->facs[a.fac + k + 1].func != WFM_NOP)
             return fail(WFM_EINVAL, "segment %lld: COS_SINCOS row %d needs a NOP row after it", (long long)s, k);
@@ -232,6 +233,7 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
             return fail(WFM_EINVAL, "segment %lld: COS_ROT row %d: bad base row", (long long)s, k);
         }
       }
+      local_max = std::max(local_max, n_values);
       for (int t = a.term; t < b.term; ++t) {
         const WfmTerm& tm = d->terms[t];
         if (tm.n_ref < 0 || tm.ref_begin < 0 || (int64_t)tm.ref_begin + tm.n_ref > d->n_refs)
@@ -328,7 +330,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   }
   {
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
-    const double ir = ((double)d->n_facs * 40.0 /* SRow 16, RRow 64, GRow 32; NOP rows vanish */ +
+    const double ir = ((double)d->n_facs * 28.0 /* SRow, CRow, GRow: 32 bytes each; NOP rows vanish */ +
                        (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
     const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
     int ts = wfm::kMaxTileSamples, cap = 0;

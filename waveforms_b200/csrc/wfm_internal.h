@@ -43,27 +43,31 @@ constexpr int kMaxSlots = 12;
 constexpr int kSlotStride = 32 * 8 * kUnit;  // bytes between consecutive slots
 
 // ---- the device program of ONE active segment (built on the device at upload) ------------
-// The ABI factor rows of a segment are regrouped BY CLASS so that the interpreter runs
-// three tight loops and decodes no opcode on the hot rows:
-//   SRow[n_sc]   WFM_COS_SINCOS: slots 1+2i (cos) and 2+2i (sin)       <- sincos(w * (x - shift))
-//   RRow[n_rot]  WFM_COS_ROT   : slot 1+2 n_sc+j   <- cos(w * (x - shift)) by rotation of its base
-//   GRow[n_gen]  everything else: slot 1+2 n_sc+n_rot+k  (switch on the basis id)
+// The ABI factor rows of a segment are regrouped so that the interpreter decodes no opcode
+// on the hot rows and never stores a sine:
+//   per WFM_COS_SINCOS row, in ABI order:
+//     SRow          slot <- cos(a), a = w * (x - shift); (cos a, sin a) stay in registers for
+//     CRow[n_child] slot <- cos(w * (x - shift')) of every WFM_COS_ROT row based on it, by rotation
+//   GRow[n_gen]     everything else (switch on the basis id)
 //   CTerm[n_term]
-// WFM_NOP rows (the sine placeholders of the ABI) vanish.
+// Value slots follow that order (slot 0 holds 1.0): one per SRow, CRow and GRow.  The ABI's
+// WFM_NOP rows (sine placeholders) vanish.
 struct SRow {
   double shift, w;
-};
-static_assert(sizeof(SRow) == 16, "SRow layout");
-
-struct RRow {
-  double shift, w;
-  double bshift;     // shift of the base WFM_COS_SINCOS row
-  double D, cD, sD;  // D ~ w * (bshift - shift) and its cosine / sine (host constants)
-  uint32_t base_off; // byte offset of the base row's cosine slot (its sine follows at + kSlotStride)
+  uint32_t n_child;  // CRows that follow
   uint32_t pad0;
   double pad1;
 };
-static_assert(sizeof(RRow) == 64, "RRow layout");
+static_assert(sizeof(SRow) == 32, "SRow layout");
+
+// cos(a_t), a_t = w * (x - shift) rounded exactly as the reference rounds it, from the parent's
+// (cos, sin)(a): a_t = a + D + eps with D ~ w * (parent shift - shift) a host constant (cos D,
+// sin D tabulated) and eps = (a_t - a) - D the MEASURED residual (|eps| ~ ulp(a))
+struct CRow {
+  double shift;
+  double D, cD, sD;
+};
+static_assert(sizeof(CRow) == 32, "CRow layout");
 
 struct GRow {
   int32_t func;     // WFM_* basis id
@@ -86,7 +90,7 @@ constexpr uint32_t kCTermGroupEnd = 1, kCTermExt = 2;
 
 // per segment, parallel to the ABI segment table
 struct SegPlan {
-  uint8_t n_sc, n_rot, n_gen, flags;
+  uint8_t n_sc, n_rot, n_gen, flags;  // n_rot: CRows of all SRows together
   uint16_t n_term;
   uint16_t blk16;  // bytes / 16 of its rows + terms in a packet (0 for a wide segment)
 };
@@ -98,7 +102,7 @@ constexpr uint32_t kSegWide = 1;
 // Built once per program on the device.  A packet is everything ONE tile needs,
 // contiguous in global memory (16-byte aligned, size a multiple of 16) so that a
 // warp brings it into shared memory with ONE TMA bulk copy:
-//   PacketHeader | ARow[n_arows + 1] | PatchRow[n_patch] | per active segment: SRow.. RRow.. GRow.. CTerm..
+//   PacketHeader | ARow[n_arows + 1] | PatchRow[n_patch] | per active segment: {SRow CRow..}.. GRow.. CTerm..
 // Zero segments do not appear at all: the kernel fills the tile with `base` first.
 struct PacketHeader {
   int64_t out0;   // index of the tile's first sample in the output buffer

@@ -242,53 +242,52 @@ static __device__ __noinline__ double term_product_ext(const DevProgram& P, int 
 }
 
 // ---- the hot evaluator: one UNIT (kUnit samples of one active segment) per call -------------
-// blk: the segment's rows in the staged packet (SRow.. RRow.. GRow.. CTerm..); sl: this
+// blk: the segment's rows in the staged packet ({SRow CRow..}.. GRow.. CTerm..); sl: this
 // lane's value slots (slot k at sl + k * kSlotStride, slot 0 holds 1.0).
 __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                          bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
                                          const double (&x)[kUnit], unsigned char* __restrict__ sl,
                                          const double* __restrict__ erf_s) {
   unsigned char* dst = sl + kSlotStride;  // slot 1
-  // -- one range reduction + both polynomials per frequency
-  const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(blk);
+  // -- one range reduction + both polynomials per frequency; the further cosines of that
+  // frequency (other shifts) by rotation of (cos, sin) while they are still in registers
+  const unsigned char* __restrict__ row = blk;
 #pragma unroll 1
   for (int i = 0; i < n_sc; ++i) {
-    const double shift = sr[i].shift, wv = sr[i].w;
+    const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(row);
+    const double wv = sr->w;
+    const int n_child = (int)sr->n_child;
     double a[kUnit];
     Val s, c;
+    {
+      const double shift = sr->shift;
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) a[u] = mul(wv, sub(x[u], shift));
+      for (int u = 0; u < kUnit; ++u) a[u] = mul(wv, sub(x[u], shift));
+    }
     sincos_cw_n<kUnit>(a, s.v, c.v);
     st_slot(dst, c);
-    st_slot(dst + kSlotStride, s);
-    dst += 2 * kSlotStride;
-  }
-  // -- further cosines of a frequency already reduced: cos(a_t), a_t = w*(x - shift) rounded
-  // exactly as the reference rounds it, from the base row's (cos, sin)(a_b): a_t = a_b + D + eps
-  // with D a host constant (cos D, sin D tabulated) and eps = (a_t - a_b) - D the MEASURED
-  // residual (|eps| ~ ulp(a)), expanded to second order
-  const RRow* __restrict__ rr = reinterpret_cast<const RRow*>(sr + n_sc);
-#pragma unroll 1
-  for (int j = 0; j < n_rot; ++j) {
-    const double shift = rr[j].shift, wv = rr[j].w, bshift = rr[j].bshift;
-    const double D = rr[j].D, cD = rr[j].cD, sD = rr[j].sD;
-    const unsigned char* bp = sl + rr[j].base_off;
-    const Val cb = ld_slot(bp), sb = ld_slot(bp + kSlotStride);
-    Val r;
-#pragma unroll
-    for (int u = 0; u < kUnit; ++u) {
-      const double a_t = mul(wv, sub(x[u], shift));
-      const double a_b = mul(wv, sub(x[u], bshift));
-      const double eps = sub(sub(a_t, a_b), D);
-      const double C = fma(cb.v[u], cD, -(sb.v[u] * sD));
-      const double S = fma(sb.v[u], cD, cb.v[u] * sD);
-      r.v[u] = fma(-0.5 * eps * eps, C, fma(-eps, S, C));
-    }
-    st_slot(dst, r);
     dst += kSlotStride;
+    row += sizeof(SRow);
+#pragma unroll 1
+    for (int j = 0; j < n_child; ++j) {
+      const CRow* __restrict__ cr = reinterpret_cast<const CRow*>(row);
+      const double shift = cr->shift, D = cr->D, cD = cr->cD, sD = cr->sD;
+      Val r;
+#pragma unroll
+      for (int u = 0; u < kUnit; ++u) {
+        const double a_t = mul(wv, sub(x[u], shift));
+        const double eps = sub(sub(a_t, a[u]), D);  // second-order expansion in eps below
+        const double C = fma(c.v[u], cD, -(s.v[u] * sD));
+        const double S = fma(s.v[u], cD, c.v[u] * sD);
+        r.v[u] = fma(-0.5 * eps * eps, C, fma(-eps, S, C));
+      }
+      st_slot(dst, r);
+      dst += kSlotStride;
+      row += sizeof(CRow);
+    }
   }
   // -- every other basis function
-  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(rr + n_rot);
+  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(blk + (n_sc + n_rot) * 32);
 #pragma unroll 1
   for (int k = 0; k < n_gen; ++k) {
     const int func = gr[k].func;
@@ -398,17 +397,25 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
     else if (f == WFM_COS_ROT) ++n_rot;
     else if (f != WFM_NOP) ++n_gen;
   }
-  const bool wide = 2 * n_sc + n_rot + n_gen > kMaxSlots || nt > 255;
-  int i_sc = 0, i_rot = 0, i_gen = 0;
-  for (int r = 0; r < nf; ++r) {
-    const int f = P.facs[p0.fac + r].func;
-    int slot = 0;
+  const bool wide = n_sc + n_rot + n_gen > kMaxSlots || nt > 255;
+  // slots: every WFM_COS_SINCOS row (ABI order) followed by the WFM_COS_ROT rows based on it, then the rest
+  {
+    int next = 1;
+    for (int r = 0; r < nf; ++r) row_slot[p0.fac + r] = 0;
     if (!wide) {
-      if (f == WFM_COS_SINCOS) slot = 1 + 2 * i_sc++;
-      else if (f == WFM_COS_ROT) slot = 1 + 2 * n_sc + i_rot++;
-      else if (f != WFM_NOP) slot = 1 + 2 * n_sc + n_rot + i_gen++;
+      for (int r = 0; r < nf; ++r) {
+        if (P.facs[p0.fac + r].func != WFM_COS_SINCOS) continue;
+        row_slot[p0.fac + r] = (uint8_t)next++;
+        for (int q = r + 1; q < nf; ++q) {
+          const WfmFactor f = P.facs[p0.fac + q];
+          if (f.func == WFM_COS_ROT && (int)P.args[f.arg_off] == r) row_slot[p0.fac + q] = (uint8_t)next++;
+        }
+      }
+      for (int r = 0; r < nf; ++r) {
+        const int f = P.facs[p0.fac + r].func;
+        if (f != WFM_COS_SINCOS && f != WFM_COS_ROT && f != WFM_NOP) row_slot[p0.fac + r] = (uint8_t)next++;
+      }
     }
-    row_slot[p0.fac + r] = (uint8_t)slot;
   }
   for (int t = 0; t < nt; ++t) {
     const WfmTerm tm = P.terms[p0.term + t];
@@ -432,7 +439,7 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
   pl.n_gen = (uint8_t)min(n_gen, 255);
   pl.flags = wide ? kSegWide : 0u;
   pl.n_term = (uint16_t)min(nt, 65535);
-  pl.blk16 = wide ? 0 : (uint16_t)((n_sc * sizeof(SRow) + n_rot * sizeof(RRow) + n_gen * sizeof(GRow) + nt * sizeof(CTerm)) / 16);
+  pl.blk16 = wide ? 0 : (uint16_t)((n_sc * sizeof(SRow) + n_rot * sizeof(CRow) + n_gen * sizeof(GRow) + nt * sizeof(CTerm)) / 16);
   seg_plan[s] = pl;
 }
 
@@ -643,21 +650,25 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
         arows[ia] = r;
       }
       if (!(pl.flags & kSegWide)) {
-        SRow* sr = reinterpret_cast<SRow*>(blk);
-        RRow* rr = reinterpret_cast<RRow*>(sr + pl.n_sc);
-        GRow* gr = reinterpret_cast<GRow*>(rr + pl.n_rot);
+        // trig rows sit in slot order (SRow and CRow are both 32 bytes, one slot each)
+        GRow* gr = reinterpret_cast<GRow*>(blk + (pl.n_sc + pl.n_rot) * 32);
         CTerm* ct = reinterpret_cast<CTerm*>(gr + pl.n_gen);
-        for (int r = lane; r < p1.fac - p0.fac; r += 32) {
+        const int nf = p1.fac - p0.fac;
+        for (int r = lane; r < nf; r += 32) {
           const WfmFactor f = P.facs[p0.fac + r];
           const int slot = P.row_slot[p0.fac + r];
           if (f.func == WFM_COS_SINCOS) {
-            sr[(slot - 1) / 2] = SRow{f.shift, f.a0};
+            uint32_t n_child = 0;
+            for (int q = r + 1; q < nf; ++q) {
+              const WfmFactor g = P.facs[p0.fac + q];
+              n_child += (g.func == WFM_COS_ROT && (int)P.args[g.arg_off] == r);
+            }
+            *reinterpret_cast<SRow*>(blk + (slot - 1) * 32) = SRow{f.shift, f.a0, n_child, 0u, 0.0};
           } else if (f.func == WFM_COS_ROT) {
             const double* __restrict__ p = P.args + f.arg_off;  // [base_row, base_shift, D, cos D, sin D]
-            const int base_slot = P.row_slot[p0.fac + (int)p[0]];
-            rr[slot - 1 - 2 * pl.n_sc] = RRow{f.shift, f.a0, p[1], p[2], p[3], p[4], (uint32_t)(base_slot * kSlotStride), 0u, 0.0};
+            *reinterpret_cast<CRow*>(blk + (slot - 1) * 32) = CRow{f.shift, p[2], p[3], p[4]};
           } else if (f.func != WFM_NOP) {
-            gr[slot - 1 - 2 * pl.n_sc - pl.n_rot] = GRow{f.func, f.arg_off, f.shift, f.a0, f.a1};
+            gr[slot - 1 - pl.n_sc - pl.n_rot] = GRow{f.func, f.arg_off, f.shift, f.a0, f.a1};
           }
         }
         for (int q = lane; q < p1.term - p0.term; q += 32)
