@@ -212,7 +212,7 @@ def run_cpu(chans, steps, warmup, procs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames', type=int, default=64, help='frames per GPU per step')
@@ -285,13 +285,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        prog.sample_device(dtype=code, out=out)
-    barrier()
     clock_lines, stop_evt = [], threading.Event()
     sampler = threading.Thread(target=clock_sampler, args=(stop_evt, clock_lines, local_rank), daemon=True)
     sampler.start()
-    time.sleep(0.35)
+    for _ in range(args.warmup):
+        prog.sample_device(dtype=code, out=out)
+    barrier()
+    # keep the GPU under the same load while nvidia-smi (100 ms period) collects a few samples:
+    # the timed region itself lasts only steps x ~0.8 ms
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.6:
+        for _ in range(20):
+            prog.sample_device(dtype=code, out=out)
+        torch.cuda.synchronize()
     launches0 = prog.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -363,7 +369,8 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': 'wfm::sample_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': samples_per_step * esz, 'launch_ms': k1_ms,
-                'traffic': traffic['dram_bytes_per_launch'] if traffic else None,
+                # one ncu --set full capture at frames_per_launch frames, scaled to this launch's frames
+            'traffic': (traffic['dram_bytes_per_launch'] * args.frames / traffic['frames_per_launch']) if traffic else None,
                 'traffic_source': traffic.get('source') if traffic else None}
 
     cpu = None

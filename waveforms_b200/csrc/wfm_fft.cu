@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -38,15 +39,18 @@
 
 namespace wfm {
 
-constexpr int kFftThreads = 256;
+constexpr int kFftThreads = 512;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
+constexpr int kSmemBudget = 227 * 1024 - 1024;
 
 struct FftPlan {
   int L;
   int n_stage;
   int radix[kMaxStages];
-  const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)
+  uint32_t inv_ns[kMaxStages];  // ceil(2^32 / Ns) of every stage: j / Ns = umulhi(j, inv) for j < 2^16
+  const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)  (global memory)
+  int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -123,46 +127,51 @@ __device__ __forceinline__ void dft_small<7>(double2 (&v)[7], double sgn) {
   for (int p = 0; p < 7; ++p) v[p] = o[p];
 }
 
-// one Stockham stage of radix R over C interleaved transforms (point p of
-// transform c lives at [p*C + c])
+// one Stockham stage of radix R over C = 2^LOGC interleaved transforms (point p of
+// transform c lives at [p*C + c]); tw: the length-L table (shared or global memory)
 template <int R>
-__device__ __forceinline__ void stockham_stage(const double2* __restrict__ a, double2* __restrict__ b, int L, int C,
-                                               int Ns, const double2* __restrict__ tw, double sgn) {
+__device__ __forceinline__ void stockham_stage(const double2* __restrict__ a, double2* __restrict__ b, int L, int logc,
+                                               int Ns, uint32_t inv_ns, const double2* __restrict__ tw, double sgn) {
   const int nb = L / R;        // butterflies per transform
   const int tstep = nb / Ns;   // L / (Ns*R): table stride of this stage
-  for (int jj = threadIdx.x; jj < nb * C; jj += blockDim.x) {
-    const int c = jj % C, j = jj / C;
-    const int k = j % Ns;
+  const int cmask = (1 << logc) - 1;
+  const int total = nb << logc;
+  for (int jj = threadIdx.x; jj < total; jj += blockDim.x) {
+    const int c = jj & cmask, j = jj >> logc;
+    const int q = Ns == 1 ? j : (int)__umulhi((uint32_t)j, inv_ns);  // j / Ns
+    const int k = j - q * Ns;
     double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double2 x = a[(j + r * nb) * C + c];
-      if (r > 0 && k > 0) {
-        double2 w = __ldg(tw + k * r * tstep);
+    for (int r = 0; r < R; ++r) v[r] = a[((j + r * nb) << logc) + c];
+    if (k > 0) {
+      const int t1 = k * tstep;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        double2 w = tw[t1 * r];
         w.y *= -sgn;  // table holds exp(-i..): forward (sgn=-1) keeps it, inverse conjugates
-        x = cmul(x, w);
+        v[r] = cmul(v[r], w);
       }
-      v[r] = x;
     }
     dft_small<R>(v, sgn);
-    const int j0 = (j / Ns) * Ns * R + k;
+    const int j0 = q * Ns * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) b[(j0 + r * Ns) * C + c] = v[r];
+    for (int r = 0; r < R; ++r) b[((j0 + r * Ns) << logc) + c] = v[r];
   }
 }
 
-// C interleaved transforms of length P.L in shared memory; returns the buffer
+// C = 2^logc interleaved transforms of length P.L in shared memory; returns the buffer
 // that holds the result.  All threads of the CTA must call it.
-__device__ double2* smem_fft(double2* a, double2* b, const FftPlan& P, int C, double sgn) {
+__device__ double2* smem_fft(double2* a, double2* b, const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw) {
   int Ns = 1;
   for (int s = 0; s < P.n_stage; ++s) {
     const int R = P.radix[s];
+    const uint32_t inv = P.inv_ns[s];
     switch (R) {
-      case 2: stockham_stage<2>(a, b, P.L, C, Ns, P.tw, sgn); break;
-      case 3: stockham_stage<3>(a, b, P.L, C, Ns, P.tw, sgn); break;
-      case 4: stockham_stage<4>(a, b, P.L, C, Ns, P.tw, sgn); break;
-      case 5: stockham_stage<5>(a, b, P.L, C, Ns, P.tw, sgn); break;
-      default: stockham_stage<7>(a, b, P.L, C, Ns, P.tw, sgn); break;
+      case 2: stockham_stage<2>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+      case 3: stockham_stage<3>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+      case 4: stockham_stage<4>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+      case 5: stockham_stage<5>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+      default: stockham_stage<7>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
     }
     __syncthreads();
     double2* t = a; a = b; b = t;
@@ -171,11 +180,24 @@ __device__ double2* smem_fft(double2* a, double2* b, const FftPlan& P, int C, do
   return a;
 }
 
-// exp(sgn * 2 pi i * m / n), 0 <= m < n, accurate to ~1 ulp
-__device__ __forceinline__ double2 big_twiddle(int64_t m, int64_t n, double sgn) {
-  double s, c;
-  sincospi(2.0 * (double)m / (double)n, &s, &c);
-  return make_double2(c, sgn * s);
+// the plan's twiddle table: staged behind the two ping-pong buffers when it fits
+__device__ __forceinline__ const double2* stage_twiddles(const FftPlan& P, double2* smem_after_buffers) {
+  if (!P.tw_in_smem) return P.tw;
+  for (int p = threadIdx.x; p < P.L; p += blockDim.x) smem_after_buffers[p] = P.tw[p];
+  return smem_after_buffers;  // visible after the caller's next __syncthreads()
+}
+
+// Inter-pass twiddles W_n^m = exp(-2 pi i m / n), 0 <= m < n, from two small host tables
+// (long double): m = 1024 h + l, W^m = hi[h] * lo[l].  One complex multiply instead of a
+// sincospi per element; the 1024 + n/1024 entries stay in L1.
+struct BigTwiddle {
+  const double2* hi;  // W_n^(1024 h)
+  const double2* lo;  // W_n^l, l < 1024
+};
+__device__ __forceinline__ double2 big_twiddle(const BigTwiddle& T, int64_t m, double sgn) {
+  double2 w = cmul(__ldg(T.hi + (m >> 10)), __ldg(T.lo + (m & 1023)));
+  w.y *= -sgn;  // tables hold exp(-i ..): forward (sgn = -1) keeps it, inverse conjugates
+  return w;
 }
 
 extern __shared__ __align__(16) unsigned char fft_smem_raw[];
@@ -186,35 +208,39 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
                                                                         const double2* __restrict__ H) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + P.L;
+  const double2* tw = stage_twiddles(P, b + P.L);
   const double* xs = x + (int64_t)blockIdx.x * stride;
   double* ys = y + (int64_t)blockIdx.x * stride;
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = make_double2(xs[p], 0.0);
   __syncthreads();
-  double2* f = smem_fft(a, b, P, 1, -1.0);
+  double2* f = smem_fft(a, b, P, 0, -1.0, tw);
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) f[p] = cmul(f[p], __ldg(H + p));
   __syncthreads();
-  double2* g = smem_fft(f, f == a ? b : a, P, 1, +1.0);
+  double2* g = smem_fft(f, f == a ? b : a, P, 0, +1.0, tw);
   const double inv = 1.0 / (double)P.L;
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) ys[p] = g[p].x * inv;
 }
 
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
-// element (r, n2) of the [N1][N2] view; the inter-pass twiddle W_n^(sgn * r * n2) is
-// applied after the transform (first pass of a forward-structured transform) or
-// before it (last pass of the fused filter, undoing the forward pass)
+// element (r, n2) of the [N1][N2] view; C = 2^logc adjacent columns per CTA.  The inter-pass
+// twiddle W_n^(sgn * r * n2) (r * n2 < n: no reduction needed) is applied after the
+// transform (first pass of a forward-structured transform) or before it (last pass of the
+// fused filter, undoing the forward pass)
 template <bool kTwAfter, bool kRealIn, bool kRealOut>
-__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, int N2, int C, const void* __restrict__ in,
-                                                               void* __restrict__ out, int64_t in_stride,
-                                                               int64_t out_stride, double sgn, double scale) {
-  const int N1 = P.L;
-  const int64_t n = (int64_t)N1 * N2;
+__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
+                                                               const void* __restrict__ in, void* __restrict__ out,
+                                                               int64_t in_stride, int64_t out_stride, double sgn,
+                                                               double scale) {
+  const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + (size_t)N1 * C;
-  const int c0 = blockIdx.x * C;
+  double2* b = a + ((size_t)N1 << logc);
+  const double2* tw = stage_twiddles(P, b + ((size_t)N1 << logc));
+  const int c0 = blockIdx.x << logc;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
-  for (int e = threadIdx.x; e < N1 * C; e += blockDim.x) {
-    const int c = e % C, r = e / C;
+  const int total = N1 << logc;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e & (C - 1), r = e >> logc;
     double2 v = make_double2(0.0, 0.0);
     if (c < cw) {
       const int64_t idx = (int64_t)r * N2 + c0 + c;
@@ -223,62 +249,68 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, int N2
       } else {
         v = static_cast<const double2*>(in)[sig * in_stride + idx];
       }
-      if (!kTwAfter) v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, sgn));
+      if (!kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
     }
     a[e] = v;
   }
   __syncthreads();
-  double2* f = smem_fft(a, b, P, C, sgn);
-  for (int e = threadIdx.x; e < N1 * C; e += blockDim.x) {
-    const int c = e % C, r = e / C;
+  double2* f = smem_fft(a, b, P, logc, sgn, tw);
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = e & (C - 1), r = e >> logc;
     if (c >= cw) continue;
     const int64_t idx = (int64_t)r * N2 + c0 + c;
     double2 v = f[e];
-    if (kTwAfter) v = cmul(v, big_twiddle(((int64_t)r * (c0 + c)) % n, n, sgn));
+    if (kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
     if (kRealOut) static_cast<double*>(out)[sig * out_stride + idx] = v.x * scale;
     else static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
   }
 }
 
 // ---- four-step, kernel B: row transforms of length N2 on scratch[k1][*] --------------
+// C = 2^logc adjacent rows per CTA.
 // kFilter: FFT -> * Hp[k1*N2 + k2] -> IFFT, in place (spectrum stays transposed)
 // else   : FFT (sgn) and scatter to natural order out[k1 + N1*k2], scaled
+#ifndef WFM_FFT_ROWS_MINB
+#define WFM_FFT_ROWS_MINB 2
+#endif
 template <bool kFilter>
-__global__ void __launch_bounds__(kFftThreads) fft_rows_kernel(FftPlan P, int N1, int C, double2* __restrict__ data,
+__global__ void __launch_bounds__(kFftThreads, WFM_FFT_ROWS_MINB) fft_rows_kernel(FftPlan P, int N1, int logc, double2* __restrict__ data,
                                                                double2* __restrict__ out, int64_t stride,
                                                                int64_t out_stride, const double2* __restrict__ Hp,
                                                                double sgn, double scale) {
-  const int N2 = P.L;
+  const int N2 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + (size_t)N2 * C;
-  const int r0 = blockIdx.x * C;
+  double2* b = a + ((size_t)N2 << logc);
+  const double2* tw = stage_twiddles(P, b + ((size_t)N2 << logc));
+  const int r0 = blockIdx.x << logc;
   const int rw = min(C, N1 - r0);
   const int64_t sig = blockIdx.y;
   double2* base = data + sig * stride;
-  // rows are contiguous in memory: iterate row-major for coalescing
-  for (int e = threadIdx.x; e < N2 * C; e += blockDim.x) {
-    const int c = e / N2, p = e % N2;
-    a[p * C + c] = (c < rw) ? base[(int64_t)(r0 + c) * N2 + p] : make_double2(0.0, 0.0);
+  // rows are contiguous in memory: row by row for coalescing
+  for (int c = 0; c < C; ++c) {
+    const double2* __restrict__ row = base + (int64_t)(r0 + c) * N2;
+    for (int p = threadIdx.x; p < N2; p += blockDim.x) a[(p << logc) + c] = (c < rw) ? row[p] : make_double2(0.0, 0.0);
   }
   __syncthreads();
-  double2* f = smem_fft(a, b, P, C, kFilter ? -1.0 : sgn);
+  double2* f = smem_fft(a, b, P, logc, kFilter ? -1.0 : sgn, tw);
   if (kFilter) {
-    for (int e = threadIdx.x; e < N2 * C; e += blockDim.x) {
-      const int c = e / N2, p = e % N2;
-      if (c < rw) f[p * C + c] = cmul(f[p * C + c], __ldg(Hp + (int64_t)(r0 + c) * N2 + p));
+    for (int c = 0; c < rw; ++c) {
+      const double2* __restrict__ hrow = Hp + (int64_t)(r0 + c) * N2;
+      for (int p = threadIdx.x; p < N2; p += blockDim.x) f[(p << logc) + c] = cmul(f[(p << logc) + c], __ldg(hrow + p));
     }
     __syncthreads();
-    double2* g = smem_fft(f, f == a ? b : a, P, C, +1.0);
-    for (int e = threadIdx.x; e < N2 * C; e += blockDim.x) {
-      const int c = e / N2, p = e % N2;
-      if (c < rw) base[(int64_t)(r0 + c) * N2 + p] = g[p * C + c];
+    double2* g = smem_fft(f, f == a ? b : a, P, logc, +1.0, tw);
+    for (int c = 0; c < rw; ++c) {
+      double2* __restrict__ row = base + (int64_t)(r0 + c) * N2;
+      for (int p = threadIdx.x; p < N2; p += blockDim.x) row[p] = g[(p << logc) + c];
     }
   } else {
     double2* o = out + sig * out_stride;
     // natural order: X[k1 + N1*k2]; for fixed k2 the C rows are adjacent
-    for (int e = threadIdx.x; e < N2 * C; e += blockDim.x) {
-      const int c = e % C, p = e / C;
-      if (c < rw) o[(int64_t)(r0 + c) + (int64_t)N1 * p] = cscale(f[p * C + c], scale);
+    const int total = N2 << logc;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int c = e & (C - 1), p = e >> logc;
+      if (c < rw) o[(int64_t)(r0 + c) + (int64_t)N1 * p] = cscale(f[e], scale);
     }
   }
 }
@@ -288,10 +320,11 @@ __global__ void __launch_bounds__(kFftThreads) fft_c2c_single_kernel(FftPlan P, 
                                                                      int64_t stride, double sgn, double scale) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + P.L;
+  const double2* tw = stage_twiddles(P, b + P.L);
   double2* d = data + (int64_t)blockIdx.x * stride;
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = d[p];
   __syncthreads();
-  double2* f = smem_fft(a, b, P, 1, sgn);
+  double2* f = smem_fft(a, b, P, 0, sgn, tw);
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) d[p] = cscale(f[p], scale);
 }
 
@@ -378,11 +411,32 @@ static bool is_smooth(int64_t n) {
 }
 
 static std::mutex g_tw_mutex;
-static std::map<std::pair<int, int>, double2*> g_tw_cache;  // (device, L) -> table
+static std::map<std::pair<int, int>, double2*> g_tw_cache;              // (device, L) -> table
+static std::map<std::pair<int, int64_t>, BigTwiddle> g_big_tw_cache;     // (device, n) -> inter-pass tables
 
-static cudaError_t get_plan(int L, FftPlan* plan) {
+static cudaError_t upload_table(const std::vector<double2>& host, double2** out) {
+  double2* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double2) * host.size());
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(d, host.data(), sizeof(double2) * host.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return e; }
+  *out = d;
+  return cudaSuccess;
+}
+
+// plan of a length-L transform run with `points` complex points per ping-pong buffer
+// (L * interleave); *smem = dynamic shared memory the kernels need
+static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) {
   plan->L = L;
   if (!factor_smooth(L, plan->radix, &plan->n_stage)) return cudaErrorInvalidValue;
+  int64_t ns = 1;
+  for (int s = 0; s < plan->n_stage; ++s) {
+    plan->inv_ns[s] = (uint32_t)(((uint64_t(1) << 32) + ns - 1) / ns);  // exact quotient for j < 2^16
+    ns *= plan->radix[s];
+  }
+  const size_t buffers = 2 * sizeof(double2) * (size_t)points;
+  plan->tw_in_smem = buffers + sizeof(double2) * (size_t)L <= (size_t)kSmemBudget;
+  *smem = buffers + (plan->tw_in_smem ? sizeof(double2) * (size_t)L : 0);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -396,13 +450,40 @@ static cudaError_t get_plan(int L, FftPlan* plan) {
       host[p] = make_double2((double)cosl(ang), (double)-sinl(ang));
     }
     double2* d = nullptr;
-    e = cudaMalloc(&d, sizeof(double2) * (size_t)L);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(d, host.data(), sizeof(double2) * (size_t)L, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d); return e; }
+    if ((e = upload_table(host, &d)) != cudaSuccess) return e;
     it = g_tw_cache.emplace(std::make_pair(dev, L), d).first;
   }
   plan->tw = it->second;
+  return cudaSuccess;
+}
+
+static cudaError_t get_big_twiddle(int64_t n, BigTwiddle* T) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto it = g_big_tw_cache.find({dev, n});
+  if (it == g_big_tw_cache.end()) {
+    const long double two_pi = 6.283185307179586476925286766559L;
+    const int64_t n_hi = (n >> 10) + 1;
+    std::vector<double2> hi((size_t)n_hi), lo(1024);
+    for (int64_t h = 0; h < n_hi; ++h) {
+      long double ang = two_pi * (long double)(h << 10) / (long double)n;
+      hi[h] = make_double2((double)cosl(ang), (double)-sinl(ang));
+    }
+    for (int l = 0; l < 1024; ++l) {
+      long double ang = two_pi * (long double)l / (long double)n;
+      lo[l] = make_double2((double)cosl(ang), (double)-sinl(ang));
+    }
+    BigTwiddle t{nullptr, nullptr};
+    double2 *dh = nullptr, *dl = nullptr;
+    if ((e = upload_table(hi, &dh)) != cudaSuccess) return e;
+    if ((e = upload_table(lo, &dl)) != cudaSuccess) { cudaFree(dh); return e; }
+    t.hi = dh;
+    t.lo = dl;
+    it = g_big_tw_cache.emplace(std::make_pair(dev, n), t).first;
+  }
+  *T = it->second;
   return cudaSuccess;
 }
 
@@ -425,12 +506,35 @@ static int64_t next_smooth(int64_t m) {
   return m;
 }
 
+// stream-ordered scratch: keep freed blocks in the device's pool instead of returning them
+// to the driver at every synchronisation (the default release threshold is 0)
+static void keep_pool_memory() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static int tile_width(int L, int want) { return std::max(1, std::min(want, kMaxPoints / L)); }
+// log2 of the number of interleaved transforms per CTA: the largest power of two <= want
+// whose two ping-pong buffers fit
+static int tile_logc(int L, int want_log) {
+  int lc = want_log;
+  while (lc > 0 && ((int64_t)L << lc) > kMaxPoints) --lc;
+  return lc;
+}
 
 // plain complex transform of n_sig signals, natural order, in place; n 7-smooth
 static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t stride, double sgn, double scale,
@@ -438,27 +542,31 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   cudaError_t e;
   if (n <= kMaxPoints) {
     FftPlan P;
-    if ((e = get_plan((int)n, &P)) != cudaSuccess) return e;
-    const size_t smem = 2 * sizeof(double2) * (size_t)n;
+    size_t smem;
+    if ((e = get_plan((int)n, n, &P, &smem)) != cudaSuccess) return e;
     if ((e = set_smem(fft_c2c_single_kernel, smem)) != cudaSuccess) return e;
     fft_c2c_single_kernel<<<(unsigned)n_sig, kFftThreads, smem, st>>>(P, data, stride, sgn, scale);
     return cudaGetLastError();
   }
   int N1, N2;
   if (!split_two_level(n, &N1, &N2)) return cudaErrorNotSupported;
+  const int lc1 = tile_logc(N1, 3), lc2 = tile_logc(N2, 2);
   FftPlan P1, P2;
-  if ((e = get_plan(N1, &P1)) != cudaSuccess) return e;
-  if ((e = get_plan(N2, &P2)) != cudaSuccess) return e;
+  BigTwiddle T;
+  size_t smem1, smem2;
+  if ((e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1)) != cudaSuccess) return e;
+  if ((e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2)) != cudaSuccess) return e;
+  if ((e = get_big_twiddle(n, &T)) != cudaSuccess) return e;
+  keep_pool_memory();
   double2* scratch = nullptr;
   if ((e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_sig, st)) != cudaSuccess) return e;
-  const int C1 = tile_width(N1, 8), C2 = tile_width(N2, 4);
-  const size_t smem1 = 2 * sizeof(double2) * (size_t)N1 * C1, smem2 = 2 * sizeof(double2) * (size_t)N2 * C2;
+  const int C1 = 1 << lc1, C2 = 1 << lc2;
   dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
   if ((e = set_smem(fft_cols_kernel<true, false, false>, smem1)) != cudaSuccess) goto done;
-  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, data, scratch, stride, n, sgn, 1.0);
+  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0);
   if ((e = cudaGetLastError()) != cudaSuccess) goto done;
   if ((e = set_smem(fft_rows_kernel<false>, smem2)) != cudaSuccess) goto done;
-  fft_rows_kernel<false><<<g2, kFftThreads, smem2, st>>>(P2, N1, C2, scratch, data, n, stride, nullptr, sgn, scale);
+  fft_rows_kernel<false><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, data, n, stride, nullptr, sgn, scale);
   e = cudaGetLastError();
 done:
   cudaFreeAsync(scratch, st);
@@ -510,6 +618,44 @@ extern "C" int wfm_fft_c2c(double* data, int64_t n_sig, int64_t n, int64_t strid
   return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
 }
 
+namespace wfm {
+
+// Hp[k1*N2 + k2] = H[k1 + N1*k2]: the transposed spectrum order the row pass produces
+__global__ void permute_h_kernel(const double2* __restrict__ H, double2* __restrict__ Hp, int N1, int N2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N1 * N2) return;
+  const int k1 = (int)(i / N2), k2 = (int)(i % N2);
+  Hp[i] = H[(int64_t)k1 + (int64_t)N1 * k2];
+}
+
+// pinned staging for the caller's H (pageable host memory): the call returns without waiting
+// for the stream, so the response must not be read from the caller's buffer after return.
+// One buffer per calling thread; an event guards its reuse.
+struct HStage {
+  void* host = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t used = nullptr;
+  cudaError_t reserve(size_t need) {
+    cudaError_t e = cudaSuccess;
+    if (used) {
+      if ((e = cudaEventSynchronize(used)) != cudaSuccess) return e;  // the previous call's copy has left the buffer
+    } else if ((e = cudaEventCreateWithFlags(&used, cudaEventDisableTiming)) != cudaSuccess) {
+      return e;
+    }
+    if (need > bytes) {
+      if (host) cudaFreeHost(host);
+      host = nullptr;
+      bytes = 0;
+      if ((e = cudaMallocHost(&host, need)) != cudaSuccess) return e;
+      bytes = need;
+    }
+    return cudaSuccess;
+  }
+};
+static thread_local HStage g_hstage;
+
+}  // namespace wfm
+
 extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n, int64_t stride, const double* H,
                               void* stream) {
   using namespace wfm;
@@ -517,56 +663,61 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
   if (n_sig == 0 || n == 0) return WFM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  const std::complex<double>* Hc = reinterpret_cast<const std::complex<double>*>(H);
+  keep_pool_memory();
+  // H: caller's host memory -> pinned staging -> device, asynchronously
+  const size_t h_bytes = sizeof(double2) * (size_t)n;
+  if ((e = g_hstage.reserve(h_bytes)) != cudaSuccess) return WFM_ECUDA;
+  memcpy(g_hstage.host, H, h_bytes);
   double2* dH = nullptr;
-  if ((e = cudaMallocAsync(&dH, sizeof(double2) * (size_t)n, st)) != cudaSuccess) return WFM_ECUDA;
+  if ((e = cudaMallocAsync(&dH, h_bytes, st)) != cudaSuccess) return WFM_ECUDA;
+  e = cudaMemcpyAsync(dH, g_hstage.host, h_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventRecord(g_hstage.used, st);
   int rc = WFM_OK;
   int N1 = 0, N2 = 0;
   const bool smooth = is_smooth(n);
-  if (smooth && n <= kMaxPoints) {
+  if (e != cudaSuccess) {
+    // fall through to the common exit
+  } else if (smooth && n <= kMaxPoints) {
     FftPlan P;
-    e = get_plan((int)n, &P);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, H, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st);
-    const size_t smem = 2 * sizeof(double2) * (size_t)n;
+    size_t smem;
+    e = get_plan((int)n, n, &P, &smem);
     if (e == cudaSuccess) e = set_smem(fft_filter_single_kernel, smem);
     if (e == cudaSuccess) {
       fft_filter_single_kernel<<<(unsigned)n_sig, kFftThreads, smem, st>>>(P, x, y, stride, dH);
       e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // H is pageable host memory
   } else if (smooth && split_two_level(n, &N1, &N2)) {
-    // permute H to the transposed spectrum order the row pass produces
-    std::vector<std::complex<double>> Hp((size_t)n);
-    for (int k1 = 0; k1 < N1; ++k1)
-      for (int k2 = 0; k2 < N2; ++k2) Hp[(size_t)k1 * N2 + k2] = Hc[(size_t)k1 + (size_t)N1 * k2];
+    const int lc1 = tile_logc(N1, 3), lc2 = tile_logc(N2, 2);
     FftPlan P1, P2;
-    double2* scratch = nullptr;
-    e = get_plan(N1, &P1);
-    if (e == cudaSuccess) e = get_plan(N2, &P2);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, Hp.data(), sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st);
+    BigTwiddle T;
+    size_t smem1 = 0, smem2 = 0;
+    double2 *scratch = nullptr, *dHp = nullptr;
+    e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1);
+    if (e == cudaSuccess) e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2);
+    if (e == cudaSuccess) e = get_big_twiddle(n, &T);
+    if (e == cudaSuccess) e = cudaMallocAsync(&dHp, h_bytes, st);
     if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_sig, st);
-    const int C1 = tile_width(N1, 8), C2 = tile_width(N2, 4);
-    const size_t smem1 = 2 * sizeof(double2) * (size_t)N1 * C1, smem2 = 2 * sizeof(double2) * (size_t)N2 * C2;
+    const int C1 = 1 << lc1, C2 = 1 << lc2;
     dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
     if (e == cudaSuccess) {
-      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, x, scratch, stride, n, -1.0, 1.0);
-      fft_rows_kernel<true><<<g2, kFftThreads, smem2, st>>>(P2, N1, C2, scratch, nullptr, n, 0, dH, -1.0, 1.0);
-      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, N2, C1, scratch, y, n, stride, +1.0,
+      permute_h_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dH, dHp, N1, N2);
+      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, x, scratch, stride, n, -1.0, 1.0);
+      fft_rows_kernel<true><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, dHp, -1.0, 1.0);
+      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, scratch, y, n, stride, +1.0,
                                                                           1.0 / (double)n);
       e = cudaGetLastError();
     }
     if (scratch) cudaFreeAsync(scratch, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // Hp is a local
+    if (dHp) cudaFreeAsync(dHp, st);
   } else {
     // generic: complex copy, forward, * H, inverse, real part
     double2* c = nullptr;
     e = cudaMallocAsync(&c, sizeof(double2) * (size_t)n * (size_t)n_sig, st);
     const int T = 256;
     dim3 gn((unsigned)((n + T - 1) / T), (unsigned)n_sig);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dH, H, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
       real_to_complex_kernel<<<gn, T, 0, st>>>(x, stride, c, n);
       e = c2c_any(c, n_sig, n, n, -1.0, 1.0, st);
@@ -580,7 +731,6 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
       e = cudaGetLastError();
     }
     if (c) cudaFreeAsync(c, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaErrorNotSupported) rc = WFM_EUNSUPPORTED;
   }
   cudaFreeAsync(dH, st);

@@ -73,60 +73,86 @@ __device__ __forceinline__ void biquad_step(const Biquad& q, double x, double& z
 }
 
 // ---------------------------------------------------------------------------
-// exact: one thread per signal, sequential in time
+// exact: ONE WARP per signal, sequential in time.  The warp loads 32 consecutive
+// samples with one coalesced access (the next block is already in flight), every lane
+// runs the same recurrence on the broadcast samples (the state is replicated, so no
+// lane waits for another) and lane l keeps output l: loads and stores are full lines
+// and the only serial cost left is the recurrence's own dependency chain.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) sosfilt_exact_kernel(IirParams P, const double* __restrict__ x, double* y,
-                                                             int64_t n_sig, int64_t n, int64_t stride,
-                                                             const double* __restrict__ zi, double* __restrict__ zf) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kExactWarps = 4;  // warps (= signals) per CTA
+
+__device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(32 * kExactWarps) sosfilt_exact_kernel(const __grid_constant__ IirParams P,
+                                                                         const double* __restrict__ x, double* y,
+                                                                         int64_t n_sig, int64_t n, int64_t stride,
+                                                                         const double* __restrict__ zi,
+                                                                         double* __restrict__ zf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * kExactWarps + (threadIdx.x >> 5);
   if (s >= n_sig) return;
+  const int S = P.n_sections;
   double z0[kMaxSections], z1[kMaxSections];
 #pragma unroll
   for (int k = 0; k < kMaxSections; ++k) {
-    z0[k] = (zi && k < P.n_sections) ? zi[(s * P.n_sections + k) * 2 + 0] : 0.0;
-    z1[k] = (zi && k < P.n_sections) ? zi[(s * P.n_sections + k) * 2 + 1] : 0.0;
+    z0[k] = (zi && k < S) ? zi[(s * S + k) * 2 + 0] : 0.0;
+    z1[k] = (zi && k < S) ? zi[(s * S + k) * 2 + 1] : 0.0;
   }
   const double* __restrict__ xs = x + s * stride;
   double* ys = y + s * stride;
   const bool shift = P.initial != 0.0;
-  constexpr int U = 8;
-  int64_t j = 0;
-  for (; j + U <= n; j += U) {
-    double v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = xs[j + u];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double cur = shift ? sub(v[u], P.initial) : v[u];
-#pragma unroll
-      for (int k = 0; k < kMaxSections; ++k)
-        if (k < P.n_sections) {
-          double out;
-          biquad_step(P.sec[k], cur, z0[k], z1[k], out);
-          cur = out;
+  double nxt = lane < n ? xs[lane] : 0.0;
+  for (int64_t base = 0; base < n; base += 32) {
+    const double mine = nxt;
+    if (base + 32 + lane < n) nxt = xs[base + 32 + lane];  // in flight while this block is filtered
+    const int cnt = (int)min((int64_t)32, n - base);
+    double out = 0.0;
+    if (S == 1) {  // the common cases without the section loop
+      const Biquad q = P.sec[0];
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        if (l < cnt) {
+          double cur = shfl_f64(mine, l), o;
+          if (shift) cur = sub(cur, P.initial);
+          biquad_step(q, cur, z0[0], z1[0], o);
+          if (lane == l) out = o;
         }
-      v[u] = shift ? add(cur, P.initial) : cur;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) ys[j + u] = v[u];
-  }
-  for (; j < n; ++j) {
-    double cur = shift ? sub(xs[j], P.initial) : xs[j];
-#pragma unroll
-    for (int k = 0; k < kMaxSections; ++k)
-      if (k < P.n_sections) {
-        double out;
-        biquad_step(P.sec[k], cur, z0[k], z1[k], out);
-        cur = out;
       }
-    ys[j] = shift ? add(cur, P.initial) : cur;
+    } else if (S == 2) {
+      const Biquad q0 = P.sec[0], q1 = P.sec[1];
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        if (l < cnt) {
+          double cur = shfl_f64(mine, l), o, o2;
+          if (shift) cur = sub(cur, P.initial);
+          biquad_step(q0, cur, z0[0], z1[0], o);
+          biquad_step(q1, o, z0[1], z1[1], o2);
+          if (lane == l) out = o2;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int l = 0; l < cnt; ++l) {
+        double cur = shfl_f64(mine, l);
+        if (shift) cur = sub(cur, P.initial);
+#pragma unroll
+        for (int k = 0; k < kMaxSections; ++k)
+          if (k < S) {
+            double o;
+            biquad_step(P.sec[k], cur, z0[k], z1[k], o);
+            cur = o;
+          }
+        if (lane == l) out = cur;
+      }
+    }
+    if (lane < cnt) ys[base + lane] = shift ? add(out, P.initial) : out;
   }
-  if (zf) {
+  if (zf && lane == 0) {
 #pragma unroll
     for (int k = 0; k < kMaxSections; ++k)
-      if (k < P.n_sections) {
-        zf[(s * P.n_sections + k) * 2 + 0] = z0[k];
-        zf[(s * P.n_sections + k) * 2 + 1] = z1[k];
+      if (k < S) {
+        zf[(s * S + k) * 2 + 0] = z0[k];
+        zf[(s * S + k) * 2 + 1] = z1[k];
       }
   }
 }
@@ -139,11 +165,13 @@ __device__ __forceinline__ void matvec(const double* __restrict__ M, double a, d
   rb = fma(M[2], a, M[3] * b);
 }
 
-__global__ void __launch_bounds__(kIirThreads) sosfilt_scan_kernel(IirParams P, const IirScanTables* __restrict__ T,
-                                                                     const double* __restrict__ x, double* y,
+__global__ void __launch_bounds__(kIirThreads, 2) sosfilt_scan_kernel(const __grid_constant__ IirParams P,
+                                                                        const __grid_constant__ IirScanTables TT,
+                                                                        const double* __restrict__ x, double* y,
                                                                      int64_t n, int64_t stride,
                                                                      const double* __restrict__ zi,
                                                                      double* __restrict__ zf) {
+  const IirScanTables* __restrict__ T = &TT;  // ~10 KB of kernel parameters (constant bank): no table upload per call
   __shared__ double s_tile[kIirThreads * kIirRow];
   __shared__ double s_tot[8][2];
   __shared__ double s_carry[kMaxSections][2];
@@ -278,10 +306,38 @@ struct LfilterParams {
   double a[kMaxOrder + 1];
 };
 
-__global__ void __launch_bounds__(128) lfilter_exact_kernel(LfilterParams P, const double* __restrict__ x, double* y,
-                                                             int64_t n_sig, int64_t n, int64_t stride,
-                                                             const double* __restrict__ zi, double* __restrict__ zf) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one lfilter step on the replicated state (M = order)
+template <int M>
+__device__ __forceinline__ double lfilter_step(const LfilterParams& P, double xv, double (&z)[kMaxOrder]) {
+  if (M == 0) return mul(P.b[0], xv);
+  const double yv = add(z[0], mul(P.b[0], xv));
+#pragma unroll
+  for (int k = 0; k < M - 1; ++k) z[k] = sub(add(z[k + 1], mul(xv, P.b[k + 1])), mul(yv, P.a[k + 1]));
+  z[M - 1] = sub(mul(xv, P.b[M]), mul(yv, P.a[M]));
+  return yv;
+}
+__device__ __forceinline__ double lfilter_step_any(const LfilterParams& P, double xv, double (&z)[kMaxOrder]) {
+  const int M = P.order;
+  if (M == 0) return mul(P.b[0], xv);
+  const double yv = add(z[0], mul(P.b[0], xv));
+#pragma unroll
+  for (int k = 0; k < kMaxOrder - 1; ++k)
+    if (k < M - 1) z[k] = sub(add(z[k + 1], mul(xv, P.b[k + 1])), mul(yv, P.a[k + 1]));
+#pragma unroll
+  for (int k = 0; k < kMaxOrder; ++k)
+    if (k == M - 1) z[k] = sub(mul(xv, P.b[M]), mul(yv, P.a[M]));
+  return yv;
+}
+
+// ONE WARP per signal (see sosfilt_exact_kernel): coalesced block loads, the recurrence
+// replicated in every lane, lane l keeps output l
+__global__ void __launch_bounds__(32 * kExactWarps) lfilter_exact_kernel(const __grid_constant__ LfilterParams P,
+                                                                         const double* __restrict__ x, double* y,
+                                                                         int64_t n_sig, int64_t n, int64_t stride,
+                                                                         const double* __restrict__ zi,
+                                                                         double* __restrict__ zf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * kExactWarps + (threadIdx.x >> 5);
   if (s >= n_sig) return;
   const int M = P.order;
   double z[kMaxOrder];
@@ -289,23 +345,36 @@ __global__ void __launch_bounds__(128) lfilter_exact_kernel(LfilterParams P, con
   for (int k = 0; k < kMaxOrder; ++k) z[k] = (zi && k < M) ? zi[s * M + k] : 0.0;
   const double* __restrict__ xs = x + s * stride;
   double* ys = y + s * stride;
-  for (int64_t j = 0; j < n; ++j) {
-    const double xv = xs[j];
-    double yv;
-    if (M == 0) {
-      yv = mul(P.b[0], xv);
+  double nxt = lane < n ? xs[lane] : 0.0;
+  for (int64_t base = 0; base < n; base += 32) {
+    const double mine = nxt;
+    if (base + 32 + lane < n) nxt = xs[base + 32 + lane];
+    const int cnt = (int)min((int64_t)32, n - base);
+    double out = 0.0;
+    if (M == 1) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l)
+        if (l < cnt) {
+          const double o = lfilter_step<1>(P, shfl_f64(mine, l), z);
+          if (lane == l) out = o;
+        }
+    } else if (M == 2) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l)
+        if (l < cnt) {
+          const double o = lfilter_step<2>(P, shfl_f64(mine, l), z);
+          if (lane == l) out = o;
+        }
     } else {
-      yv = add(z[0], mul(P.b[0], xv));
-#pragma unroll
-      for (int k = 0; k < kMaxOrder - 1; ++k)
-        if (k < M - 1) z[k] = sub(add(z[k + 1], mul(xv, P.b[k + 1])), mul(yv, P.a[k + 1]));
-#pragma unroll
-      for (int k = 0; k < kMaxOrder; ++k)
-        if (k == M - 1) z[k] = sub(mul(xv, P.b[M]), mul(yv, P.a[M]));
+#pragma unroll 1
+      for (int l = 0; l < cnt; ++l) {
+        const double o = lfilter_step_any(P, shfl_f64(mine, l), z);
+        if (lane == l) out = o;
+      }
     }
-    ys[j] = yv;
+    if (lane < cnt) ys[base + lane] = out;
   }
-  if (zf) {
+  if (zf && lane == 0) {
 #pragma unroll
     for (int k = 0; k < kMaxOrder; ++k)
       if (k < M) zf[s * M + k] = z[k];
@@ -355,52 +424,50 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
   }
   const size_t state_bytes = sizeof(double) * 2 * (size_t)n_sections * (size_t)n_sig;
   double *d_zi = nullptr, *d_zf = nullptr;
-  IirScanTables* d_tab = nullptr;
   cudaError_t e = cudaSuccess;
-  auto cleanup = [&]() {
-    cudaFree(d_zi);
-    cudaFree(d_zf);
-    cudaFree(d_tab);
-  };
+  // stream-ordered scratch for the states (pageable host sources are staged by the driver
+  // before cudaMemcpyAsync returns, so no synchronisation is needed for them)
   if (zi) {
-    e = cudaMalloc(&d_zi, state_bytes);
+    e = cudaMallocAsync(&d_zi, state_bytes, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, state_bytes, cudaMemcpyHostToDevice, st);
   }
-  if (e == cudaSuccess && zf) e = cudaMalloc(&d_zf, state_bytes);
+  if (e == cudaSuccess && zf) e = cudaMallocAsync(&d_zf, state_bytes, st);
   if (e == cudaSuccess && n > 0) {
     if (mode == WFM_IIR_EXACT) {
-      const int threads = 128;
-      const unsigned blocks = (unsigned)((n_sig + threads - 1) / threads);
-      sosfilt_exact_kernel<<<blocks, threads, 0, st>>>(P, x, y, n_sig, n, stride, d_zi, d_zf);
+      const unsigned blocks = (unsigned)((n_sig + kExactWarps - 1) / kExactWarps);
+      sosfilt_exact_kernel<<<blocks, 32 * kExactWarps, 0, st>>>(P, x, y, n_sig, n, stride, d_zi, d_zf);
       e = cudaGetLastError();
     } else {
-      std::vector<IirScanTables> tab(1);
+      static thread_local IirScanTables tab;
       for (int k = 0; k < n_sections; ++k) {
         const M2 A{-(long double)P.sec[k].a1, 1.0L, -(long double)P.sec[k].a2, 0.0L};
         const M2 AT = mpow(A, kIirT);
-        for (int l = 0; l < 32; ++l) put(tab[0].lane[k][l], mpow(AT, l));
-        for (int d = 0; d < 5; ++d) put(tab[0].lvl[k][d], mpow(AT, 1L << d));
-        put(tab[0].warp[k], mpow(AT, 32));
+        M2 pw{1, 0, 0, 1};
+        for (int l = 0; l < 32; ++l) {
+          put(tab.lane[k][l], pw);
+          pw = mm(pw, AT);
+        }
+        put(tab.warp[k], pw);  // AT^32
+        M2 sq = AT;
+        for (int d = 0; d < 5; ++d) {
+          put(tab.lvl[k][d], sq);
+          sq = mm(sq, sq);
+        }
       }
-      e = cudaMalloc(&d_tab, sizeof(IirScanTables));
-      if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, tab.data(), sizeof(IirScanTables), cudaMemcpyHostToDevice, st);
-      if (e == cudaSuccess) {
-        // the pageable source must outlive the async copy
-        e = cudaStreamSynchronize(st);
-      }
-      if (e == cudaSuccess) {
-        sosfilt_scan_kernel<<<(unsigned)n_sig, kIirThreads, 0, st>>>(P, d_tab, x, y, n, stride, d_zi, d_zf);
-        e = cudaGetLastError();
-      }
+      sosfilt_scan_kernel<<<(unsigned)n_sig, kIirThreads, 0, st>>>(P, tab, x, y, n, stride, d_zi, d_zf);
+      e = cudaGetLastError();
     }
   } else if (e == cudaSuccess && zf && zi) {
     e = cudaMemcpyAsync(d_zf, d_zi, state_bytes, cudaMemcpyDeviceToDevice, st);
   } else if (e == cudaSuccess && zf) {
     e = cudaMemsetAsync(d_zf, 0, state_bytes, st);
   }
-  if (e == cudaSuccess && zf) e = cudaMemcpyAsync(zf, d_zf, state_bytes, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && (d_zi || d_zf || d_tab)) e = cudaStreamSynchronize(st);  // before freeing scratch
-  cleanup();
+  if (e == cudaSuccess && zf) {
+    e = cudaMemcpyAsync(zf, d_zf, state_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the caller reads zf on return
+  }
+  if (d_zi) cudaFreeAsync(d_zi, st);
+  if (d_zf) cudaFreeAsync(d_zf, st);
   return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
 }
 
@@ -423,19 +490,20 @@ extern "C" int wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t
   double *d_zi = nullptr, *d_zf = nullptr;
   cudaError_t e = cudaSuccess;
   if (zi && M > 0) {
-    e = cudaMalloc(&d_zi, state_bytes);
+    e = cudaMallocAsync(&d_zi, state_bytes, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, sizeof(double) * M * n_sig, cudaMemcpyHostToDevice, st);
   }
-  if (e == cudaSuccess && zf && M > 0) e = cudaMalloc(&d_zf, state_bytes);
+  if (e == cudaSuccess && zf && M > 0) e = cudaMallocAsync(&d_zf, state_bytes, st);
   if (e == cudaSuccess) {
-    const int threads = 128;
-    lfilter_exact_kernel<<<(unsigned)((n_sig + threads - 1) / threads), threads, 0, st>>>(P, x, y, n_sig, n, stride,
-                                                                                        d_zi, d_zf);
+    lfilter_exact_kernel<<<(unsigned)((n_sig + kExactWarps - 1) / kExactWarps), 32 * kExactWarps, 0, st>>>(
+        P, x, y, n_sig, n, stride, d_zi, d_zf);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess && d_zf) e = cudaMemcpyAsync(zf, d_zf, sizeof(double) * M * n_sig, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && (d_zi || d_zf)) e = cudaStreamSynchronize(st);
-  cudaFree(d_zi);
-  cudaFree(d_zf);
+  if (e == cudaSuccess && d_zf) {
+    e = cudaMemcpyAsync(zf, d_zf, sizeof(double) * M * n_sig, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the caller reads zf on return
+  }
+  if (d_zi) cudaFreeAsync(d_zi, st);
+  if (d_zf) cudaFreeAsync(d_zf, st);
   return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
 }
