@@ -144,3 +144,65 @@ def test_chunked_sampling_matches_reference_semantics(ns):
                          for a, k in ((0.0, 2500), (2.5e-6, 2500), (5e-6, 1000))])
     want = sosfilt(sos, O.waveform_call(w.bounds, w.seq, xs))
     assert rel_err(np.concatenate(chunks), want) <= FP64_TOL
+
+
+def test_batched_channel_filters_match_per_channel(ns):
+    """sample_batch(filters='own') groups channels that share a filter and a length into one
+    batched IIR call; exact mode must equal sampling every channel on its own, scan mode
+    must agree within the fp64 tolerance for a well-conditioned filter."""
+    from waveforms_b200 import sample_batch
+    rng = np.random.default_rng(11)
+    sos = tf2sos(*butter(2, 0.08))
+    ws = []
+    for k in range(9):
+        w = rng.uniform(-0.5, 0.5) * (ns.square(1e-6 * (1 + k % 3), edge=5e-9) >> (2e-6 + 0.3e-6 * k))
+        w.start, w.stop, w.sample_rate = 0.0, 8e-6 if k != 4 else 6e-6, 2e9  # one ragged channel
+        if k != 7:
+            w.filters = (sos, 0.0) if k % 2 else (sos, 0.1)
+        ws.append(w)
+    per = [w.sample() for w in ws]
+    got = sample_batch(ws, iir_mode='exact').numpy()
+    for a, b in zip(got, per):
+        assert np.array_equal(a, b)
+    got = sample_batch(ws, iir_mode='scan').numpy()
+    for a, b in zip(got, per):
+        assert rel_err(a, b) <= FP64_TOL
+
+
+def test_iir_mode_policy():
+    from waveforms_b200 import dsp
+    assert dsp.resolve_iir_mode(1000) == 'exact' and dsp.resolve_iir_mode(400000) == 'scan'
+    assert dsp.resolve_iir_mode(400000, 'exact') == 'exact'
+    with pytest.raises(ValueError):
+        dsp.resolve_iir_mode(10, 'fast')
+
+
+def test_cfg4_pipeline_full_size_properties():
+    """BASELINE configs[3] at full size (400 000 samples per channel): size-independent
+    properties of the device pipeline.  (a) the scan IIR is linear: f(a x1 + b x2) =
+    a f(x1) + b f(x2) within the filter's noise; (b) exact and scan modes agree within that
+    noise; (c) correct_reflection(reflection(x)) returns x."""
+    import torch
+    from waveforms_b200 import distortion as D, dsp
+    rate, n = 2e9, 400000
+    sos = D.exp_decay_filter([-0.03, 0.02], [0.1e-6, 0.3e-6], rate, inv=True, output='sos')
+    rng = np.random.default_rng(20260004)
+    # flux-like inputs: piecewise-constant plateaus
+    x = np.zeros((4, n))
+    for s in range(4):
+        for _ in range(20):
+            a = int(rng.integers(0, n - 12000))
+            x[s, a:a + int(rng.integers(200, 10000))] += rng.uniform(-0.5, 0.5)
+    dx = _dev(x)
+    ys, _ = dsp.sosfilt_device(sos, dx.clone(), mode='scan')
+    ye, _ = dsp.sosfilt_device(sos, dx.clone(), mode='exact')
+    scale = float(ye.abs().max())
+    assert float((ys - ye).abs().max()) <= 2e-11 * scale  # exp-decay poles at 1 - 2.5e-3: noise gain ~1e5
+    comb = 0.7 * dx[0] - 1.3 * dx[1]
+    yc, _ = dsp.sosfilt_device(sos, comb.clone(), mode='scan')
+    assert float((yc - (0.7 * ys[0] - 1.3 * ys[1])).abs().max()) <= 2e-11 * scale
+    # `.real` after the inverse transform drops Im(H) at the Nyquist bin (test_gpu_fft.py): project it out
+    alt = torch.from_numpy(np.where(np.arange(n) % 2 == 0, 1.0, -1.0)).cuda()
+    xr = dx - (dx @ alt)[:, None] / n * alt
+    back = D.correct_reflection(D.reflection(xr.clone(), 0.05, 13.3e-9, rate), 0.05, 13.3e-9, rate)
+    assert float((back - xr).abs().max()) <= 1e-12 * float(xr.abs().max())

@@ -60,7 +60,7 @@ class BatchResult:
 
 
 def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
-                 filters='own'):
+                 filters='own', iir_mode=None):
     """Sample every waveform in ``waveforms`` on its own start/stop/sample_rate
     grid.  ``dtype``: np.float64 (reference parity, 1e-12) or np.float32
     (fp32 output, 1e-6).  ``devices``: list of CUDA device indices to shard the
@@ -68,7 +68,8 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     whose tensors stay on the GPUs.
 
     ``filters='own'`` applies each waveform's ``.filters`` (sample-time IIR,
-    waveform.py:193-203) on the device; ``None`` skips them."""
+    waveform.py:193-203) on the device; ``None`` skips them.  ``iir_mode``:
+    'exact' | 'scan' | 'auto' (default: ``dsp.IIR_MODE``)."""
     import torch
     engine.require_gpu()
     items = [channel_grid(w, sample_rate) for w in waveforms]
@@ -86,7 +87,7 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
             out = prog.sample_device(dtype=code)
             if filters == 'own':
                 from .dsp import apply_channel_filters
-                apply_channel_filters(out, batch, waveforms[lo:hi])
+                apply_channel_filters(out, batch, waveforms[lo:hi], mode=iir_mode)
             prog.close()
         tensors.append(out)
         for k in range(hi - lo):

@@ -18,9 +18,28 @@ def _stream(torch, device):
 IIR_EXACT, IIR_SCAN = 0, 1
 _IIR_MODES = {'exact': IIR_EXACT, 'scan': IIR_SCAN}
 
+# How the sample-time IIR (Waveform.sample(filters=...), sample_batch) runs:
+#   'exact'  sequential-in-time kernel, bit-identical to scipy.signal.sosfilt; one warp per
+#            signal, ~60 ns per sample per signal whatever the batch size
+#   'scan'   block-parallel associative scan (the throughput path, 2.6 TB/s on B200); equals
+#            the sequential result up to the filter's own rounding-noise gain
+#   'auto'   exact up to IIR_AUTO_EXACT_MAX samples per signal, scan above
+IIR_MODE = 'auto'
+IIR_AUTO_EXACT_MAX = 32768
+
+
+def resolve_iir_mode(n, mode=None):
+    mode = IIR_MODE if mode is None else mode
+    if mode == 'auto':
+        return 'exact' if n <= IIR_AUTO_EXACT_MAX else 'scan'
+    if mode not in _IIR_MODES:
+        raise ValueError(f'unknown IIR mode {mode!r}')
+    return mode
+
 
 def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None,
                    mode='exact'):
+    # mode: 'exact' | 'scan' | 'auto' | None (= the module-level IIR_MODE)
     """In-place-capable cascaded biquad filter on a CUDA f64 tensor ``x`` of
     shape (n,) or (n_sig, n) (row stride = x.stride(0)).  Returns (y, zf).
 
@@ -32,6 +51,7 @@ def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None,
     x2 = x if x.dim() == 2 else x.unsqueeze(0)
     assert x2.dtype == torch.float64 and x2.stride(1) == 1
     n_sig, n = x2.shape
+    mode = resolve_iir_mode(n, mode)
     y = x2 if out is None else (out if out.dim() == 2 else out.unsqueeze(0))
     nsec = sos.shape[0]
     zi_arr = None
@@ -60,21 +80,35 @@ def sample_and_filter(chan, grid, sos, initial, zi):
         dev = prog.sample_device(dtype=engine.WFM_F64)
         sig = dev[:grid.n]
         _, zf = sosfilt_device(sos, sig, initial=initial or 0.0, zi=zi,
-                               want_zf=zi is not None)
+                               want_zf=zi is not None, mode=None)
         host = sig.cpu().numpy()
     finally:
         prog.close()
     return host, (zf[0] if zf is not None else None)
 
 
-def apply_channel_filters(out, batch, waveforms):
-    """Apply each waveform's own ``.filters`` to its slice of ``out``."""
+def apply_channel_filters(out, batch, waveforms, mode=None):
+    """Apply each waveform's own ``.filters`` to its slice of ``out`` (flat device
+    tensor of the whole batch).  Channels that share a filter and a length and sit
+    at a constant pitch in the buffer go through ONE batched call (n_sig signals)."""
+    groups = {}
     for k, w in enumerate(waveforms):
         if w.filters is None:
             continue
         sos, initial = w.filters
-        off, n = int(batch.waves['out_off'][k]), int(batch.waves['n'][k])
-        sosfilt_device(sos, out[off:off + n], initial=initial or 0.0)
+        sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64)).reshape(-1, 6)
+        key = (sos.tobytes(), float(initial or 0.0), int(batch.waves['n'][k]))
+        groups.setdefault(key, (sos, [])) [1].append(k)
+    for (_, initial, n), (sos, idx) in groups.items():
+        offs = [int(batch.waves['out_off'][k]) for k in idx]
+        pitch = offs[1] - offs[0] if len(offs) > 1 else n
+        regular = len(offs) > 1 and pitch >= n and all(b - a == pitch for a, b in zip(offs, offs[1:]))
+        if regular:
+            view = out[offs[0]:offs[0] + pitch * (len(offs) - 1) + n].as_strided((len(offs), n), (pitch, 1))
+            sosfilt_device(sos, view, initial=initial, mode=mode)
+        else:
+            for off in offs:
+                sosfilt_device(sos, out[off:off + n], initial=initial, mode=mode)
 
 
 def lfilter_device(b, a, x, zi=None, want_zf=False):
