@@ -82,3 +82,81 @@ def test_unsupported_basis_raises(ns):
     w = ns.function(lambda t: t**2)
     with pytest.raises(UnsupportedBasis):
         w(np.linspace(0, 1, 5))
+
+
+def _oracle_sample(w):
+    """Oracle evaluation of a waveforms_b200 object on its own sample() grid."""
+    from oracle import wfm_oracle as O
+    x = O.sample_grid(w.start, w.stop, w.sample_rate)
+    if hasattr(w, 'wlist'):
+        return O.stack_call(list(w.wlist), x, getattr(w, 'offset', 0), getattr(w, 'shift', 0))
+    return O.waveform_call(w.bounds, w.seq, x, w.min, w.max)
+
+
+def test_wide_segments_take_the_slow_evaluator(ns):
+    """A stack whose members overlap with 9 different carrier frequencies: the merged segments
+    need more than 12 value slots (kSegWide) and are evaluated from the ABI tables."""
+    from waveforms_b200.lowering import lower
+    from waveforms_b200.batch import channel_grid
+    pulses = []
+    for k in range(9):
+        I, _ = ns.mixing(0.1 * (k + 1) * ns.cosPulse(200e-9) >> (150e-9 + 5e-9 * k), freq=(20 + 7 * k) * 1e6, phase=0.1 * k,
+                         DRAGScaling=3e-10)
+        pulses.append(I)
+    w = ns.WaveVStack(pulses)
+    w.start, w.stop, w.sample_rate = 0.0, 400e-9, 4e9
+    b = lower([channel_grid(w)])
+    assert np.diff(b.seg_ptr['fac']).max() > 12
+    got = w.sample()
+    assert rel_err(got, _oracle_sample(w)) <= FP64_TOL
+
+
+def test_cold_tiles_take_the_global_path(ns):
+    """Hundreds of tiny active segments inside one tile: the tile's packet does not fit a
+    warp's buffer (kPacketCold) and the tile is evaluated from the global tables."""
+    rng = np.random.default_rng(3)
+    w = ns.zero()
+    for k in range(300):
+        w = w + rng.uniform(0.1, 1) * (ns.gaussian(1.5e-9) >> (2e-9 + 3e-9 * k))
+    w.start, w.stop, w.sample_rate = 0.0, 1e-6, 4e9
+    from waveforms_b200 import engine
+    from waveforms_b200.lowering import lower
+    from waveforms_b200.batch import channel_grid
+    prog = engine.Program(lower([channel_grid(w)]))
+    info = prog.info()
+    prog.close()
+    got = w.sample()
+    assert got.shape == (4000, )
+    assert rel_err(got, _oracle_sample(w)) <= FP64_TOL
+    assert info['tile_samples'] >= 128
+
+
+def test_empty_and_degenerate_inputs(ns):
+    from waveforms_b200 import sample_batch
+    assert len(sample_batch([])) == 0
+    z = ns.zero()
+    z.start, z.stop, z.sample_rate = 0.0, 1e-6, 1e9
+    assert np.array_equal(z.sample(), np.zeros(1000))
+    e = ns.cosPulse(20e-9)
+    e.start, e.stop, e.sample_rate = 1e-6, 1e-6, 1e9  # np.arange(start, start) is empty
+    assert e.sample().shape == (0, )
+    one = ns.one() * 0.25
+    one.start, one.stop, one.sample_rate = 0.0, 3e-9, 1e9
+    assert np.array_equal(one.sample(), np.full(3, 0.25))
+    res = sample_batch([z, e, one]).numpy()
+    assert [len(r) for r in res] == [1000, 0, 3] and np.array_equal(res[2], np.full(3, 0.25))
+    with pytest.raises(ValueError):
+        ns.cosPulse(1e-9).sample()  # grid not set (waveform.py:183-186)
+
+
+def test_single_sample_and_tile_edges(ns):
+    """Lengths around the tile size and the 16-byte store granularity."""
+    w = 0.3 * ns.cosPulse(40e-9) >> 30e-9
+    for n in (1, 2, 3, 127, 1023, 1024, 1025, 2049):
+        w.start, w.stop, w.sample_rate = 0.0, n * 1e-10, 1e10
+        got, want = w.sample(), _oracle_sample(w)
+        assert got.shape == want.shape and abs(len(got) - n) <= 1  # np.arange's length rule, fp rounding included
+        if np.max(np.abs(want)) > 0:
+            assert rel_err(got, want) <= FP64_TOL
+        else:
+            assert np.array_equal(got, want)
