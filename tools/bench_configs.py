@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""K1 on the other BASELINE.json configs at (per-GPU) full size, device-resident:
+  cfg3  RB batch: 4096 channels x depth-1000 back-to-back DRAG cosPulses, I and Q (all samples active)
+  cfg4  flux channels: 256 x 400 000 samples, 20 erf-edged squares each
+  cfg5  sweep: 12 500 waveforms (one GPU's share of 100 000) x 20 000 samples of drag_sin / drag_sinx
+A few channels are built through the drop-in API and lowered; the batch is `replicate`d to
+full size with distinct amplitudes.  CUDA events, warm.  One JSON object on stdout.
+
+    python tools/bench_configs.py [--reps 5] [--only cfg3,cfg5]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / 'tests' / 'golden'))
+
+
+def build(cfg, ns):
+    import cases
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower, replicate
+    rng = np.random.default_rng(20260000 + int(cfg[3]))
+    if cfg == 'cfg3':
+        chans = []
+        for ch in range(4):
+            for which in (0, 1):
+                chans.append(cases.rb_channel(ns, np.random.default_rng(20260003 + ch), 1000, ch, which=which)[0])
+        base, copies = lower([channel_grid(w) for w in chans]), 4096 // 4
+    elif cfg == 'cfg4':
+        chans = [cases.flux_channel(ns, rng, 20, 200e-6, 2e9)[0] for _ in range(8)]
+        base, copies = lower([channel_grid(w) for w in chans]), 256 // 8
+    else:
+        chans = []
+        for k in range(10):
+            mk = ns.drag_sinx if k == 9 else ns.drag_sin
+            kw = dict(block_freq=(-250e6, 180e6)) if k == 9 else dict(block_freq=(-250e6, ))
+            w = rng.uniform(0.1, 1) * mk(rng.uniform(50e6, 150e6), 30e-9, plateau=0, delta=1e6, phase=rng.uniform(0, 6),
+                                          t0=100e-9, **kw)
+            w.start, w.stop, w.sample_rate = 0.0, 4e-6, 5e9
+            chans.append(w)
+        base, copies = lower([channel_grid(w) for w in chans]), 12500 // 10
+    scale = 2.0 ** -(np.arange(copies) % 4)  # exact scalings: replica c == replica 0 * 2^-k bit for bit
+    return chans, base, replicate(base, copies, amp_scale=scale), scale
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--only', default='cfg3,cfg4,cfg5')
+    args = ap.parse_args()
+    import torch
+    import bench
+    from waveforms_b200 import engine
+    ns = bench.b200_namespace()
+    from waveforms_b200 import multy_drag
+    ns.drag_sin, ns.drag_sinx = multy_drag.drag_sin, multy_drag.drag_sinx
+    peak = bench.measured_peak()[0]
+    res = {}
+    for cfg in args.only.split(','):
+        chans, base, batch, scale = build(cfg, ns)
+        prog = engine.Program(batch, 0)
+        out = torch.empty(batch.total_samples, dtype=torch.float64, device='cuda')
+        prog.sample_device(dtype=engine.WFM_F64, out=out)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.reps + 1)]
+        ev[0].record()
+        for k in range(args.reps):
+            prog.sample_device(dtype=engine.WFM_F64, out=out)
+            ev[k + 1].record()
+        torch.cuda.synchronize()
+        ms = min(ev[k].elapsed_time(ev[k + 1]) for k in range(args.reps))
+        n = int(batch.waves['n'].sum())
+        # size-independent check: every replica equals replica 0 times its (power-of-two) amplitude scale
+        per = base.total_samples
+        v = out.view(len(scale), per)
+        ok = bool(torch.equal(v, v[0][None, :] * torch.from_numpy(scale).cuda()[:, None]))
+        res[cfg] = {'channels': len(batch.waves), 'samples': n, 'ms': ms, 'GSa/s': n / ms / 1e6, 'GB/s': n * 8 / ms / 1e6,
+                    'roofline_frac': n * 8 / ms / 1e6 / peak, 'replicas_bit_exact': ok, 'layout': prog.info()}
+        prog.close()
+        del out
+        torch.cuda.empty_cache()
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == '__main__':
+    main()

@@ -134,7 +134,9 @@ struct WfmProgram {
   wfm::DevProgram dev{};
   std::vector<WfmWave> waves;  // host copy (output sizing, channel ranges)
   pool::Block arena{nullptr, 0};    // every table of the program
+  pool::Block tile_tables{nullptr, 0};  // tile rows, packet sizes / offsets (sized once the tile size is chosen)
   pool::Block packets{nullptr, 0};  // the tile packets (sized by the device pre-pass)
+  int sizing_passes = 0;
   pool::Block stage{nullptr, 0};    // device staging buffer of wfm_sample_host
   wfm::TileDesc* d_tiles = nullptr;
   std::vector<int64_t> tile_prefix;  // tiles before channel w
@@ -149,6 +151,7 @@ struct WfmProgram {
     // cudaFree used to wait for them implicitly
     cudaDeviceSynchronize();
     pool::release(device, arena);
+    pool::release(device, tile_tables);
     pool::release(device, packets);
     pool::release(device, stage);
   }
@@ -317,55 +320,21 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->waves.assign(d->waves, d->waves + d->n_waves);
   p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
 
-  // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample),
-  // the value slots and two packet buffers (double-buffered).  Take the largest tile (a
-  // multiple of 128 samples) whose AVERAGE packet leaves a 4x margin in a packet buffer
-  // for tiles where pulses cluster; a tile whose packet still does not fit takes the
-  // kernel's cold path.
   int64_t samples = 0, total = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
     samples += d->waves[w].n;
     total = std::max(total, d->waves[w].out_off + d->waves[w].n);
     if (d->waves[w].flags & WFM_WAVE_COMPLEX) p->any_complex = true;
   }
-  {
-    const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
-    const double ir = ((double)d->n_facs * 28.0 /* SRow, CRow, GRow: 32 bytes each; NOP rows vanish */ +
-                       (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
-    const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
-    int ts = wfm::kMaxTileSamples, cap = 0;
-    for (;; ts -= 128) {
-      cap = ((wfm::kWarpSliceBytes - fixed - ts * 8) / 2) & ~15;
-      if (ts <= wfm::kMinTileSamples || (cap >= 256 && 64.0 + 4.0 * ir * ts <= cap)) break;
-    }
-    p->dev.tile_samples = ts;
-    p->dev.pkt_cap = std::max(cap, 64);
-  }
-  const int64_t tile_samples = p->dev.tile_samples;
-  // tiles: tile_samples consecutive samples of one channel; only the per-channel prefix is
-  // built here, the tile rows are generated on the device
-  p->tile_prefix.resize(d->n_waves + 1);
-  int64_t n_tiles = 0;
-  for (int64_t w = 0; w < d->n_waves; ++w) {
-    p->tile_prefix[w] = n_tiles;
-    n_tiles += (d->waves[w].n + tile_samples - 1) / tile_samples;
-  }
-  p->tile_prefix[d->n_waves] = n_tiles;
-  p->n_tiles = n_tiles;
   p->total_samples = total;
-  if (n_tiles >= INT32_MAX) {
-    delete p;
-    return fail(WFM_EINVAL, "too many tiles (%lld)", (long long)n_tiles);
-  }
 
-  // ONE arena for every table (ABI tables + the tables the pre-pass derives), 256-byte aligned slots
+  // arena 1: every table that does not depend on the tile size (ABI tables + segment plans), 256-byte aligned slots
   size_t arena_bytes = 0;
   auto reserve = [&](size_t bytes) {
     const size_t off = arena_bytes;
     arena_bytes += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
     return off;
   };
-  const size_t nt1 = (size_t)n_tiles + 1;
   const size_t o_waves = reserve(sizeof(WfmWave) * d->n_waves), o_bound = reserve(sizeof(double) * d->n_segs),
                o_segptr = reserve(sizeof(WfmSegPtr) * (d->n_segs + 1)), o_facs = reserve(sizeof(WfmFactor) * d->n_facs),
                o_terms = reserve(sizeof(WfmTerm) * d->n_terms), o_refs = reserve(sizeof(WfmRef) * d->n_refs),
@@ -373,9 +342,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                o_segwave = reserve(sizeof(int32_t) * d->n_segs), o_segstart = reserve(sizeof(int32_t) * d->n_segs),
                o_segval = reserve(sizeof(double) * d->n_segs), o_plan = reserve(sizeof(wfm::SegPlan) * d->n_segs),
                o_rowslot = reserve((size_t)d->n_facs), o_cterms = reserve(sizeof(wfm::CTerm) * d->n_terms),
-               o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_tiles = reserve(sizeof(wfm::TileDesc) * n_tiles),
-               o_pktsize = reserve(sizeof(uint32_t) * nt1), o_pktoff = reserve(sizeof(uint32_t) * nt1),
-               o_scratch = reserve(sizeof(uint32_t) * (nt1 / 4096 + 2));
+               o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_stats = reserve(sizeof(uint32_t) * 2);
   cudaError_t e = pool::alloc(device, arena_bytes, &p->arena);
   if (e != cudaSuccess) {
     delete p;
@@ -395,7 +362,6 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   up(o_refs, d->refs, sizeof(WfmRef) * d->n_refs);
   up(o_args, d->args, sizeof(double) * d->n_args);
   up(o_x, d->x, sizeof(double) * d->n_x);
-  up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
   p->dev.waves = (const WfmWave*)(base + o_waves);
   p->dev.seg_bound = (const double*)(base + o_bound);
   p->dev.seg_ptr = (const WfmSegPtr*)(base + o_segptr);
@@ -410,24 +376,93 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->dev.seg_plan = (const wfm::SegPlan*)(base + o_plan);
   p->dev.row_slot = (const uint8_t*)(base + o_rowslot);
   p->dev.cterms = (const wfm::CTerm*)(base + o_cterms);
-  p->dev.pkt_off = (const uint32_t*)(base + o_pktoff);
-  p->d_tiles = (wfm::TileDesc*)(base + o_tiles);
   tm.lap("arena + uploads");
 
-  // device pre-pass 1: owning channel of every segment, segment start positions and flat
-  // values, segment plans, the tile rows with their packet sizes; then the packet offsets
+  // device pre-pass 1a: owning channel of every segment, segment start positions and flat
+  // values, segment plans
   wfm::PrepareBuffers pb{(int32_t*)(base + o_segwave), (int32_t*)(base + o_segstart), (double*)(base + o_segval),
                          (wfm::SegPlan*)(base + o_plan), (uint8_t*)(base + o_rowslot), (wfm::CTerm*)(base + o_cterms),
-                         p->d_tiles, (const int64_t*)(base + o_prefix), (uint32_t*)(base + o_pktsize)};
-  if (e == cudaSuccess)
-    e = wfm::launch_prepare(p->dev, wfm::PrepareCounts{d->n_waves, d->n_segs, d->n_facs, d->n_terms, n_tiles}, pb, 0);
-  if (e == cudaSuccess)
-    e = wfm::launch_scan((uint32_t*)(base + o_pktsize), (uint32_t*)(base + o_pktoff), (uint32_t*)(base + o_scratch), n_tiles, 0);
+                         nullptr, (const int64_t*)(base + o_prefix), nullptr};
+  wfm::PrepareCounts pc{d->n_waves, d->n_segs, d->n_facs, d->n_terms, 0};
+  if (e == cudaSuccess) e = wfm::launch_prepare_segments(p->dev, pc, pb, 0);
+
+  // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample), the
+  // value slots and two packet buffers.  Take the LARGEST tile (a multiple of 128 samples)
+  // for which every tile's packet fits its buffer, measured on the device: start from the
+  // size the average packet density allows and step down while more than 1 tile in 4096 would
+  // not fit (those take the kernel's cold path).
+  uint32_t* d_stats = (uint32_t*)(base + o_stats);
+  const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
+  auto cap_of = [&](int ts) { return ((wfm::kWarpSliceBytes - fixed - ts * 8) / 2) & ~15; };
+  int ts = wfm::kMaxTileSamples;
+  {
+    const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
+    const double ir = ((double)d->n_facs * 28.0 /* SRow, CRow, GRow: 32 bytes each; NOP rows vanish */ +
+                       (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
+    while (ts > wfm::kMinTileSamples && !(cap_of(ts) >= 256 && 64.0 + ir * ts <= cap_of(ts))) ts -= 128;
+  }
+  int64_t n_tiles = 0;
+  int sizing_passes = 0;
+  for (;; ts -= 128) {
+    p->dev.tile_samples = ts;
+    p->dev.pkt_cap = std::max(cap_of(ts), 64);
+    p->tile_prefix.resize(d->n_waves + 1);
+    n_tiles = 0;
+    for (int64_t w = 0; w < d->n_waves; ++w) {
+      p->tile_prefix[w] = n_tiles;
+      n_tiles += (d->waves[w].n + ts - 1) / ts;
+    }
+    p->tile_prefix[d->n_waves] = n_tiles;
+    if (n_tiles >= INT32_MAX) {
+      delete p;
+      return fail(WFM_EINVAL, "too many tiles (%lld)", (long long)n_tiles);
+    }
+    if (e != cudaSuccess || ts <= wfm::kMinTileSamples || n_tiles == 0) break;
+    // sizing pass: statistics only
+    uint32_t stats[2] = {0, 0};
+    e = cudaMemsetAsync(d_stats, 0, sizeof(stats), 0);
+    up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
+    pc.n_tiles = n_tiles;
+    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, d_stats, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // also: tile_prefix may be rewritten now
+    ++sizing_passes;
+    if (e != cudaSuccess || (int64_t)stats[1] * 4096 <= n_tiles) break;
+  }
+  p->n_tiles = n_tiles;
+  p->sizing_passes = sizing_passes;
+  tm.lap("device pre-pass 1 (tile size)");
+
+  // arena 2: the tile tables
+  size_t tiles_bytes = 0;
+  auto reserve2 = [&](size_t bytes) {
+    const size_t off = tiles_bytes;
+    tiles_bytes += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    return off;
+  };
+  const size_t nt1 = (size_t)n_tiles + 1;
+  const size_t o_tiles = reserve2(sizeof(wfm::TileDesc) * n_tiles), o_pktsize = reserve2(sizeof(uint32_t) * nt1),
+               o_pktoff = reserve2(sizeof(uint32_t) * nt1), o_scratch = reserve2(sizeof(uint32_t) * (nt1 / 4096 + 2));
+  if (e == cudaSuccess) e = pool::alloc(device, tiles_bytes, &p->tile_tables);
+  char* base2 = (char*)p->tile_tables.p;
   uint32_t total16 = 0;
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(&total16, (uint32_t*)(base + o_pktoff) + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-  tm.lap("device pre-pass 1");
+  if (e == cudaSuccess) {
+    p->d_tiles = (wfm::TileDesc*)(base2 + o_tiles);
+    p->dev.pkt_off = (const uint32_t*)(base2 + o_pktoff);
+    pb.tiles = p->d_tiles;
+    pb.pkt_size = (uint32_t*)(base2 + o_pktsize);
+    pc.n_tiles = n_tiles;
+    up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
+    // pre-pass 1b: the tile rows with their packet sizes; then the packet offsets
+    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, nullptr, 0);
+    if (e == cudaSuccess)
+      e = wfm::launch_scan((uint32_t*)(base2 + o_pktsize), (uint32_t*)(base2 + o_pktoff), (uint32_t*)(base2 + o_scratch),
+                           n_tiles, 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&total16, (uint32_t*)(base2 + o_pktoff) + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  }
+  tm.lap("device pre-pass 1 (tiles)");
   // pass 2: the packets themselves
   if (e == cudaSuccess) e = pool::alloc(device, std::max<size_t>((size_t)total16 * 16, 16), &p->packets);
   p->dev.packets = (const unsigned char*)p->packets.p;
@@ -456,7 +491,7 @@ int64_t wfm_program_launch_count(wfm_program_t prog) { return prog ? prog->launc
 int wfm_program_info(wfm_program_t prog, int64_t* out, int32_t n) {
   if (!prog || !out) return fail(WFM_EINVAL, "null program or output");
   const int64_t v[8] = {prog->dev.tile_samples, prog->dev.pkt_cap, prog->dev.n_slots, prog->n_tiles,
-                        (int64_t)prog->packets.bytes, (int64_t)prog->arena.bytes, wfm::kUnit,
+                        (int64_t)prog->packets.bytes, (int64_t)(prog->arena.bytes + prog->tile_tables.bytes), wfm::kUnit,
                         (int64_t)wfm::sample_smem_bytes(prog->dev, WFM_F64)};
   for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
   return WFM_OK;

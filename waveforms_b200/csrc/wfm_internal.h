@@ -192,10 +192,14 @@ struct PrepareBuffers {
   uint32_t* pkt_size;          // [n_tiles + 1]
 };
 
-// pass 1: owning channel of every segment, segment start positions, flat values, segment
-// plans, slot map, compact terms, the tile rows with their segment range and packet size
-// (16-byte units) -> pkt_size[n_tiles]
-cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream);
+// pass 1a: owning channel of every segment, segment start positions, flat values, segment
+// plans, slot map, compact terms (independent of the tile size)
+cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream);
+// pass 1b: the tile rows with their segment range and packet size (16-byte units) ->
+// tiles[n_tiles], pkt_size[n_tiles] (either may be NULL: sizing pass) and, if stats != NULL,
+// stats[0] = max packet size (16-byte units, as if every packet fitted), stats[1] = tiles that do not fit P.pkt_cap
+cudaError_t launch_prepare_tiles(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, uint32_t* stats,
+                                 cudaStream_t stream);
 // exclusive scan: pkt_size[n] -> pkt_off[n + 1] (pkt_off[n] = total); scratch holds ceil(n / 4096) + 1 words
 cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* scratch, int64_t n, cudaStream_t stream);
 // pass 2: write the packets

@@ -495,30 +495,48 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
 }
 
 // one thread per tile: the tile row itself (channel, sample range), the segment rows it
-// spans, its packet size
+// spans, its packet size.  tiles / pkt_size may be NULL (sizing pass: only the statistics);
+// stats[0] = largest packet (16-byte units), stats[1] = tiles whose packet does not fit
 __global__ void prepare_tiles_kernel(DevProgram P, TileDesc* __restrict__ tiles, const int64_t* __restrict__ tile_prefix,
-                                     int64_t n_waves, int64_t n_tiles, uint32_t* __restrict__ pkt_size) {
+                                     int64_t n_waves, int64_t n_tiles, uint32_t* __restrict__ pkt_size,
+                                     uint32_t* __restrict__ stats) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  // the channel whose tile range holds t: last w with tile_prefix[w] <= t (channels without samples own no tile)
-  int64_t lo_w = 0, hi_w = n_waves - 1;
-  while (lo_w < hi_w) {
-    const int64_t mid = (lo_w + hi_w + 1) >> 1;
-    if (tile_prefix[mid] <= t) lo_w = mid; else hi_w = mid - 1;
+  uint32_t full16 = 0, cold = 0;
+  if (t < n_tiles) {
+    // the channel whose tile range holds t: last w with tile_prefix[w] <= t (channels without samples own no tile)
+    int64_t lo_w = 0, hi_w = n_waves - 1;
+    while (lo_w < hi_w) {
+      const int64_t mid = (lo_w + hi_w + 1) >> 1;
+      if (tile_prefix[mid] <= t) lo_w = mid; else hi_w = mid - 1;
+    }
+    const WfmWave w = P.waves[lo_w];
+    TileDesc td;
+    td.j0 = (t - tile_prefix[lo_w]) * (int64_t)P.tile_samples;
+    td.out0 = w.out_off + td.j0;
+    td.wave = (int32_t)lo_w;
+    td.cnt = (int32_t)min((int64_t)P.tile_samples, w.n - td.j0);
+    const int32_t* st = P.seg_start + w.seg_begin;
+    const int lo = owning_segment(st, w.n_seg, td.j0);
+    const int hi = max(lo, owning_segment(st, w.n_seg, td.j0 + td.cnt - 1));
+    td.seg0 = w.seg_begin + lo;
+    td.nb = hi - lo + 1;
+    TileLayout L = measure_tile(P, td, w);
+    if (tiles) tiles[t] = td;
+    if (pkt_size) pkt_size[t] = (uint32_t)(L.bytes() / 16);
+    cold = L.cold ? 1u : 0u;
+    L.cold = false;
+    full16 = (uint32_t)(L.bytes() / 16);  // what the packet WOULD need
   }
-  const WfmWave w = P.waves[lo_w];
-  TileDesc td;
-  td.j0 = (t - tile_prefix[lo_w]) * (int64_t)P.tile_samples;
-  td.out0 = w.out_off + td.j0;
-  td.wave = (int32_t)lo_w;
-  td.cnt = (int32_t)min((int64_t)P.tile_samples, w.n - td.j0);
-  const int32_t* st = P.seg_start + w.seg_begin;
-  const int lo = owning_segment(st, w.n_seg, td.j0);
-  const int hi = max(lo, owning_segment(st, w.n_seg, td.j0 + td.cnt - 1));
-  td.seg0 = w.seg_begin + lo;
-  td.nb = hi - lo + 1;
-  tiles[t] = td;
-  pkt_size[t] = (uint32_t)(measure_tile(P, td, w).bytes() / 16);
+  if (stats) {  // one pair of atomics per warp (every lane of the warp takes part)
+    for (int d = 16; d; d >>= 1) {
+      full16 = max(full16, __shfl_xor_sync(0xffffffffu, full16, d));
+      cold += __shfl_xor_sync(0xffffffffu, cold, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(stats, full16);
+      if (cold) atomicAdd(stats + 1, cold);
+    }
+  }
 }
 
 // ---- exclusive scan of the packet sizes (three small kernels) -----------------------------
@@ -977,15 +995,23 @@ __global__ void __launch_bounds__(kThreads) sample_kernel_c128(const __grid_cons
   }
 }
 
-cudaError_t launch_prepare(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream) {
+cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream) {
   const int threads = 128;
   auto blocks = [&](int64_t items) { return (unsigned)((items + threads - 1) / threads); };
   if (n.n_waves > 0 && n.n_segs > 0) mark_seg_wave_kernel<<<blocks(n.n_waves * 32), threads, 0, stream>>>(P, b.seg_wave, n.n_waves);
   if (n.n_segs > 0)
     prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, b.seg_start, b.seg_val, b.seg_plan, b.row_slot, b.cterms,
                                                                       n.n_segs);
-  if (n.n_tiles > 0)
-    prepare_tiles_kernel<<<blocks(n.n_tiles), threads, 0, stream>>>(P, b.tiles, b.tile_prefix, n.n_waves, n.n_tiles, b.pkt_size);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prepare_tiles(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, uint32_t* stats,
+                                 cudaStream_t stream) {
+  if (n.n_tiles <= 0) return cudaSuccess;
+  const int threads = 128;
+  prepare_tiles_kernel<<<(unsigned)((n.n_tiles + threads - 1) / threads), threads, 0, stream>>>(P, b.tiles, b.tile_prefix,
+                                                                                              n.n_waves, n.n_tiles,
+                                                                                              b.pkt_size, stats);
   return cudaGetLastError();
 }
 
