@@ -226,8 +226,16 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
 // twiddle W_n^(sgn * r * n2) (r * n2 < n: no reduction needed) is applied after the
 // transform (first pass of a forward-structured transform) or before it (last pass of the
 // fused filter, undoing the forward pass)
+// column pass: 4 interleaved columns per CTA and two CTAs per SM (32 warps) measured 14 % faster
+// than 8 columns and one CTA (cfg4, n = 625 x 640)
+#ifndef WFM_FFT_COLS_MINB
+#define WFM_FFT_COLS_MINB 2
+#endif
+#ifndef WFM_FFT_COLS_LOGC
+#define WFM_FFT_COLS_LOGC 2
+#endif
 template <bool kTwAfter, bool kRealIn, bool kRealOut>
-__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
+__global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
                                                                const void* __restrict__ in, void* __restrict__ out,
                                                                int64_t in_stride, int64_t out_stride, double sgn,
                                                                double scale) {
@@ -550,7 +558,7 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   }
   int N1, N2;
   if (!split_two_level(n, &N1, &N2)) return cudaErrorNotSupported;
-  const int lc1 = tile_logc(N1, 3), lc2 = tile_logc(N2, 2);
+  const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, 2);
   FftPlan P1, P2;
   BigTwiddle T;
   size_t smem1, smem2;
@@ -687,7 +695,7 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
       e = cudaGetLastError();
     }
   } else if (smooth && split_two_level(n, &N1, &N2)) {
-    const int lc1 = tile_logc(N1, 3), lc2 = tile_logc(N2, 2);
+    const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, 2);
     FftPlan P1, P2;
     BigTwiddle T;
     size_t smem1 = 0, smem2 = 0;
