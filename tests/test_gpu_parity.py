@@ -160,3 +160,26 @@ def test_single_sample_and_tile_edges(ns):
             assert rel_err(got, want) <= FP64_TOL
         else:
             assert np.array_equal(got, want)
+
+
+def test_program_info_and_pool_trim(ns):
+    """wfm_program_info reports the kernel layout; the library's device-memory cache survives
+    create/destroy cycles and wfm_trim() empties it without breaking later programs."""
+    from waveforms_b200 import engine
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower
+    w = 0.5 * ns.cosPulse(20e-9) >> 50e-9
+    w.start, w.stop, w.sample_rate = 0.0, 1e-6, 2e9
+    batch = lower([channel_grid(w)])
+    first = None
+    for k in range(3):
+        prog = engine.Program(batch)
+        info = prog.info()
+        assert info['tile_samples'] % 128 == 0 and 128 <= info['tile_samples'] <= 1024
+        assert info['n_tiles'] == -(-2000 // info['tile_samples']) and info['samples_per_lane_unit'] in (1, 2, 4)
+        y = prog.sample_host()
+        prog.close()
+        first = y if first is None else first
+        assert np.array_equal(y, first)
+        if k == 1:
+            assert engine.load_library().wfm_trim() == 0

@@ -76,7 +76,18 @@ struct Block {
 };
 constexpr int kMaxDevices = 64;
 std::mutex mu;
-std::vector<Block> cache[kMaxDevices];
+std::vector<Block> cache[kMaxDevices];  // oldest first
+size_t cached_bytes[kMaxDevices] = {0};
+
+// at most this much idle device memory is kept per device (WFM_POOL_LIMIT_MB, default 16 GiB of 180)
+size_t limit_bytes() {
+  static const size_t v = [] {
+    const char* s = std::getenv("WFM_POOL_LIMIT_MB");
+    const long long mb = s ? std::atoll(s) : 16384;
+    return (size_t)std::max<long long>(mb, 0) << 20;
+  }();
+  return v;
+}
 
 size_t round_up(size_t bytes) {
   const size_t g = bytes >= (size_t(1) << 20) ? (size_t(1) << 20) : 4096;  // 1 MiB granules for large blocks
@@ -86,6 +97,7 @@ size_t round_up(size_t bytes) {
 void trim_device(int dev) {
   for (const Block& b : cache[dev]) cudaFree(b.p);
   cache[dev].clear();
+  cached_bytes[dev] = 0;
 }
 
 // the current device must be `dev`
@@ -99,6 +111,7 @@ cudaError_t alloc(int dev, size_t bytes, Block* out) {
       if (c[i].bytes >= bytes && c[i].bytes <= 2 * bytes && (best < 0 || c[i].bytes < c[best].bytes)) best = i;
     if (best >= 0) {
       *out = c[best];
+      cached_bytes[dev] -= c[best].bytes;
       c.erase(c.begin() + best);
       return cudaSuccess;
     }
@@ -126,6 +139,13 @@ void release(int dev, const Block& b) {
   }
   std::lock_guard<std::mutex> lk(mu);
   cache[dev].push_back(b);
+  cached_bytes[dev] += b.bytes;
+  // over the limit: give the oldest idle blocks back to the driver (the caller's device is current)
+  while (cached_bytes[dev] > limit_bytes() && !cache[dev].empty()) {
+    cudaFree(cache[dev].front().p);
+    cached_bytes[dev] -= cache[dev].front().bytes;
+    cache[dev].erase(cache[dev].begin());
+  }
 }
 }  // namespace pool
 
