@@ -362,7 +362,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                o_segwave = reserve(sizeof(int32_t) * d->n_segs), o_segstart = reserve(sizeof(int32_t) * d->n_segs),
                o_segval = reserve(sizeof(double) * d->n_segs), o_plan = reserve(sizeof(wfm::SegPlan) * d->n_segs),
                o_rowslot = reserve((size_t)d->n_facs), o_cterms = reserve(sizeof(wfm::CTerm) * d->n_terms),
-               o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_stats = reserve(sizeof(uint32_t) * 2);
+               o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_stats = reserve(sizeof(uint64_t) * 2);
   cudaError_t e = pool::alloc(device, arena_bytes, &p->arena);
   if (e != cudaSuccess) {
     delete p;
@@ -404,7 +404,22 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                          (wfm::SegPlan*)(base + o_plan), (uint8_t*)(base + o_rowslot), (wfm::CTerm*)(base + o_cterms),
                          nullptr, (const int64_t*)(base + o_prefix), nullptr};
   wfm::PrepareCounts pc{d->n_waves, d->n_segs, d->n_facs, d->n_terms, 0};
+  p->dev.unit = 1;
   if (e == cudaSuccess) e = wfm::launch_prepare_segments(p->dev, pc, pb, 0);
+
+  // Unit: samples per lane and evaluation.  Dense programs (more than two rounds of 32 active
+  // samples in an average 1024-sample tile) evaluate two samples per lane, sparse ones one.
+  {
+    unsigned long long active = 0;
+    unsigned long long* d_active = (unsigned long long*)(base + o_stats);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_active, 0, sizeof(active), 0);
+    if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&active, d_active, sizeof(active), cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    const char* force = std::getenv("WFM_K1_UNIT");
+    if (force && (force[0] == '1' || force[0] == '2')) p->dev.unit = force[0] - '0';
+    else p->dev.unit = (samples > 0 && (double)active * 1024.0 > 64.0 * (double)samples) ? 2 : 1;
+  }
 
   // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample), the
   // value slots and two packet buffers.  Take the LARGEST tile (a multiple of 128 samples)
@@ -412,7 +427,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   // size the average packet density allows and step down while more than 1 tile in 4096 would
   // not fit (those take the kernel's cold path).
   uint32_t* d_stats = (uint32_t*)(base + o_stats);
-  const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots);
+  const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots, p->dev.unit);
   auto cap_of = [&](int ts) { return ((wfm::kWarpSliceBytes - fixed - ts * 8) / 2) & ~15; };
   int ts = wfm::kMaxTileSamples;
   {
@@ -511,7 +526,7 @@ int64_t wfm_program_launch_count(wfm_program_t prog) { return prog ? prog->launc
 int wfm_program_info(wfm_program_t prog, int64_t* out, int32_t n) {
   if (!prog || !out) return fail(WFM_EINVAL, "null program or output");
   const int64_t v[8] = {prog->dev.tile_samples, prog->dev.pkt_cap, prog->dev.n_slots, prog->n_tiles,
-                        (int64_t)prog->packets.bytes, (int64_t)(prog->arena.bytes + prog->tile_tables.bytes), wfm::kUnit,
+                        (int64_t)prog->packets.bytes, (int64_t)(prog->arena.bytes + prog->tile_tables.bytes), prog->dev.unit,
                         (int64_t)wfm::sample_smem_bytes(prog->dev, WFM_F64)};
   for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
   return WFM_OK;

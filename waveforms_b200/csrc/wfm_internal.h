@@ -16,14 +16,12 @@ namespace wfm {
 #ifndef WFM_K1_MAX_TILE
 #define WFM_K1_MAX_TILE 1024
 #endif
-// samples one lane evaluates together (a UNIT: consecutive samples of one active
-// segment).  Two independent dependency chains per lane hide the fp64 latencies the
-// interpreter is bound by at 16 warps per SM, and the row decoding is paid once per
-// unit instead of once per sample.
-#ifndef WFM_K1_UNIT
-#define WFM_K1_UNIT 2
-#endif
-constexpr int kUnit = WFM_K1_UNIT;
+// Samples one lane evaluates together (a UNIT: consecutive samples of one active segment),
+// chosen per program (DevProgram::unit).  Two samples per lane run as independent dependency
+// chains and pay the row decoding once: the dense case (RB batches: every sample active,
+// many rounds per tile; +39 % measured on cfg3).  One sample per lane needs fewer registers
+// and half the slot memory: the sparse case (control frames: at most ~2 rounds per tile;
+// +4.5 % measured on cfg2).
 constexpr int kMinTileSamples = 128;
 constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
 // shared memory per warp: 8 * WFM_K1_MIN_BLOCKS warps share the SM's 227 KB (1 KB per CTA is reserved
@@ -36,11 +34,11 @@ constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
 #endif
 constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K1_ERF_SMEM ? 2560 : 0)) / 8) & ~127;
 
-// Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of kUnit
+// Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of `unit`
 // doubles in the warp's shared slice, slot-major (slot k of lane l at byte
-// k * kSlotStride + l * 8 * kUnit: conflict-free).  Slot 0 always holds 1.0.
+// k * slot_stride(unit) + l * 8 * unit: conflict-free).  Slot 0 always holds 1.0.
 constexpr int kMaxSlots = 12;
-constexpr int kSlotStride = 32 * 8 * kUnit;  // bytes between consecutive slots
+__host__ __device__ constexpr int slot_stride(int unit) { return 32 * 8 * unit; }  // bytes between consecutive slots
 
 // ---- the device program of ONE active segment (built on the device at upload) ------------
 // The ABI factor rows of a segment are regrouped so that the interpreter decodes no opcode
@@ -77,7 +75,8 @@ struct GRow {
 static_assert(sizeof(GRow) == 32, "GRow layout");
 
 // amp * v[o0] * v[o1] * v[o2]: up to three exponent-1 references as BYTE offsets of
-// their value slots; a missing reference points at slot 0 (1.0; x * 1.0 is exact),
+// their value slots for unit = 1 (slot * 256; the kernel scales them by its unit); a
+// missing reference points at slot 0 (1.0; x * 1.0 is exact),
 // so the product needs no loop and no branch.  Terms that do not fit (more
 // references, an exponent != 1) carry kCTermExt and are read from the ABI tables.
 struct CTerm {
@@ -114,7 +113,7 @@ struct PacketHeader {
   uint16_t cnt;      // samples in the tile
   uint16_t n_arows;  // active segments intersecting the tile
   uint16_t n_patch;  // flat segments whose value differs from `base`
-  uint16_t n_units;  // units (kUnit consecutive samples of one active segment) in the tile
+  uint16_t n_units;  // units (DevProgram::unit consecutive samples of one active segment) in the tile
   uint32_t reserved[2];
 };
 static_assert(sizeof(PacketHeader) == 64, "PacketHeader layout");
@@ -158,6 +157,7 @@ struct DevProgram {
   const int32_t* seg_wave;   // [n_segs] owning channel (host-built; pre-pass only)
   const uint32_t* pkt_off;       // [n_tiles + 1] packet offsets in 16-byte units
   const unsigned char* packets;  // the tile packets
+  int unit;          // samples per lane unit: 1 or 2
   int tile_samples;  // kMinTileSamples .. kMaxTileSamples, multiple of 128
   int n_slots;       // value slots per lane in shared memory: 1 (the constant 1.0) + max rows per segment
   int pkt_cap;       // bytes of ONE packet buffer in a warp's shared slice (two buffers per warp)
@@ -195,6 +195,8 @@ struct PrepareBuffers {
 // pass 1a: owning channel of every segment, segment start positions, flat values, segment
 // plans, slot map, compact terms (independent of the tile size)
 cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream);
+// total[0] += samples owned by active segments (needs seg_start; decides DevProgram::unit)
+cudaError_t launch_count_active(const DevProgram& P, int64_t n_segs, unsigned long long* total, cudaStream_t stream);
 // pass 1b: the tile rows with their segment range and packet size (16-byte units) ->
 // tiles[n_tiles], pkt_size[n_tiles] (either may be NULL: sizing pass) and, if stats != NULL,
 // stats[0] = max packet size (16-byte units, as if every packet fitted), stats[1] = tiles that do not fit P.pkt_cap
@@ -206,7 +208,7 @@ cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* s
 cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int64_t n_tiles, unsigned char* packets,
                                 cudaStream_t stream);
 // shared memory per warp besides the output tile and the two packet buffers
-int warp_fixed_bytes(int n_slots);
+int warp_fixed_bytes(int n_slots, int unit);
 size_t sample_smem_bytes(const DevProgram& P, int dtype);
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,

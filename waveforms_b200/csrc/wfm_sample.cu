@@ -32,9 +32,9 @@
 //      buffer, the whole tile is filled with the channel's zero-segment value
 //      (16-byte shared stores, no table look-ups); the constant plateaus listed in
 //      the packet are rewritten.  No abscissa is computed for flat samples.
-//   3. Active samples.  The tile's active samples are grouped into UNITS (kUnit
+//   3. Active samples.  The tile's active samples are grouped into UNITS (1 or 2
 //      consecutive samples of one segment) that are dealt round-robin to the lanes.
-//      A lane interprets the segment program once per unit — the kUnit samples run
+//      A lane interprets the segment program once per unit — the unit's samples run
 //      as independent dependency chains — and writes the values into the tile.
 //   4. Store.  fence.proxy.async, __syncwarp, lane 0 issues the bulk store of the
 //      whole tile with an L2 evict-first policy (the output is write-once; it must
@@ -154,28 +154,31 @@ struct WaveEval {
   uint32_t flags;
 };
 
-// kUnit values of one lane
+// U values of one lane
+template <int U>
 struct Val {
-  double v[kUnit];
+  double v[U];
 };
-__device__ __forceinline__ Val ld_slot(const unsigned char* p) {
-  Val r;
-  if constexpr (kUnit == 2) {
+template <int U>
+__device__ __forceinline__ Val<U> ld_slot(const unsigned char* p) {
+  Val<U> r;
+  if constexpr (U == 2) {
     const double2 d = *reinterpret_cast<const double2*>(p);
     r.v[0] = d.x;
     r.v[1] = d.y;
   } else {
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) r.v[u] = reinterpret_cast<const double*>(p)[u];
+    for (int u = 0; u < U; ++u) r.v[u] = reinterpret_cast<const double*>(p)[u];
   }
   return r;
 }
-__device__ __forceinline__ void st_slot(unsigned char* p, const Val& r) {
-  if constexpr (kUnit == 2) {
+template <int U>
+__device__ __forceinline__ void st_slot(unsigned char* p, const Val<U>& r) {
+  if constexpr (U == 2) {
     *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
   } else {
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) reinterpret_cast<double*>(p)[u] = r.v[u];
+    for (int u = 0; u < U; ++u) reinterpret_cast<double*>(p)[u] = r.v[u];
   }
 }
 
@@ -226,6 +229,7 @@ static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int s
 // product of an extended term (more than three references or an exponent != 1) from the
 // ABI tables; the factor values are the ones already sitting in the lane's value slots
 static __device__ __noinline__ double term_product_ext(const DevProgram& P, int seg, int it, const unsigned char* sl, int u) {
+  const int kSlotStride = slot_stride(P.unit);
   const WfmSegPtr p0 = P.seg_ptr[seg];
   const WfmTerm tm = P.terms[p0.term + it];
   double prod = 1.0;
@@ -241,13 +245,15 @@ static __device__ __noinline__ double term_product_ext(const DevProgram& P, int 
   return prod;
 }
 
-// ---- the hot evaluator: one UNIT (kUnit samples of one active segment) per call -------------
+// ---- the hot evaluator: one UNIT (U samples of one active segment) per call ------------------
 // blk: the segment's rows in the staged packet ({SRow CRow..}.. GRow.. CTerm..); sl: this
 // lane's value slots (slot k at sl + k * kSlotStride, slot 0 holds 1.0).
-__device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
+template <int U>
+__device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                          bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
-                                         const double (&x)[kUnit], unsigned char* __restrict__ sl,
+                                         const double (&x)[U], unsigned char* __restrict__ sl,
                                          const double* __restrict__ erf_s) {
+  constexpr int kSlotStride = slot_stride(U);
   unsigned char* dst = sl + kSlotStride;  // slot 1
   // -- one range reduction + both polynomials per frequency; the further cosines of that
   // frequency (other shifts) by rotation of (cos, sin) while they are still in registers
@@ -257,14 +263,14 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
     const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(row);
     const double wv = sr->w;
     const int n_child = (int)sr->n_child;
-    double a[kUnit];
-    Val s, c;
+    double a[U];
+    Val<U> s, c;
     {
       const double shift = sr->shift;
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) a[u] = mul(wv, sub(x[u], shift));
+      for (int u = 0; u < U; ++u) a[u] = mul(wv, sub(x[u], shift));
     }
-    sincos_cw_n<kUnit>(a, s.v, c.v);
+    sincos_cw_n<U>(a, s.v, c.v);
     st_slot(dst, c);
     dst += kSlotStride;
     row += sizeof(SRow);
@@ -272,9 +278,9 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
     for (int j = 0; j < n_child; ++j) {
       const CRow* __restrict__ cr = reinterpret_cast<const CRow*>(row);
       const double shift = cr->shift, D = cr->D, cD = cr->cD, sD = cr->sD;
-      Val r;
+      Val<U> r;
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) {
+      for (int u = 0; u < U; ++u) {
         const double a_t = mul(wv, sub(x[u], shift));
         const double eps = sub(sub(a_t, a[u]), D);  // second-order expansion in eps below
         const double C = fma(c.v[u], cD, -(s.v[u] * sD));
@@ -292,34 +298,34 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
   for (int k = 0; k < n_gen; ++k) {
     const int func = gr[k].func;
     const double shift = gr[k].shift, a0 = gr[k].a0;
-    Val r;
+    Val<U> r;
     if (func == WFM_COS) {
-      double a[kUnit], s[kUnit];
+      double a[U], s[U];
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) a[u] = mul(a0, sub(x[u], shift));
-      sincos_cw_n<kUnit>(a, s, r.v);
+      for (int u = 0; u < U; ++u) a[u] = mul(a0, sub(x[u], shift));
+      sincos_cw_n<U>(a, s, r.v);
     } else if (func == WFM_LINEAR) {
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) r.v[u] = sub(x[u], shift);
+      for (int u = 0; u < U; ++u) r.v[u] = sub(x[u], shift);
     } else if (func == WFM_GAUSSIAN) {
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) r.v[u] = f_gaussian(sub(x[u], shift), a0);
+      for (int u = 0; u < U; ++u) r.v[u] = f_gaussian(sub(x[u], shift), a0);
     } else if (func == WFM_ERF) {
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) r.v[u] = erf_tab(dvd(sub(x[u], shift), a0), erf_s);
+      for (int u = 0; u < U; ++u) r.v[u] = erf_tab(dvd(sub(x[u], shift), a0), erf_s);
     } else {
       const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
 #pragma unroll 1
-      for (int u = 0; u < kUnit; ++u) r.v[u] = eval_factor(fa, x[u], P.args);
+      for (int u = 0; u < U; ++u) r.v[u] = eval_factor(fa, x[u], P.args);
     }
     st_slot(dst, r);
     dst += kSlotStride;
   }
   // -- terms
   const uint4* __restrict__ ct = reinterpret_cast<const uint4*>(gr + n_gen);
-  Val total, grp;
+  Val<U> total, grp;
 #pragma unroll
-  for (int u = 0; u < kUnit; ++u) {
+  for (int u = 0; u < U; ++u) {
     total.v[u] = w.offset;
     grp.v[u] = 0.0;
   }
@@ -327,20 +333,21 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
   for (int it = 0; it < n_term; ++it) {
     const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags
     const double amp = __hiloint2double((int)c.y, (int)c.x);
-    Val prod;
+    Val<U> prod;
     if (has_ext && (c.w >> 16) & kCTermExt) {
 #pragma unroll 1
-      for (int u = 0; u < kUnit; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
+      for (int u = 0; u < U; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
     } else {
-      const Val f0 = ld_slot(sl + (c.z & 0xffffu)), f1 = ld_slot(sl + (c.z >> 16)), f2 = ld_slot(sl + (c.w & 0xffffu));
+      const Val<U> f0 = ld_slot<U>(sl + (c.z & 0xffffu) * U), f1 = ld_slot<U>(sl + (c.z >> 16) * U),
+                   f2 = ld_slot<U>(sl + (c.w & 0xffffu) * U);
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) prod.v[u] = mul(mul(f0.v[u], f1.v[u]), f2.v[u]);
+      for (int u = 0; u < U; ++u) prod.v[u] = mul(mul(f0.v[u], f1.v[u]), f2.v[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) grp.v[u] = add(grp.v[u], mul(amp, prod.v[u]));
+    for (int u = 0; u < U; ++u) grp.v[u] = add(grp.v[u], mul(amp, prod.v[u]));
     if ((c.w >> 16) & kCTermGroupEnd) {
 #pragma unroll
-      for (int u = 0; u < kUnit; ++u) {
+      for (int u = 0; u < U; ++u) {
         total.v[u] = add(total.v[u], grp.v[u]);
         grp.v[u] = 0.0;
       }
@@ -348,7 +355,7 @@ __device__ __forceinline__ Val eval_unit(const unsigned char* __restrict__ blk, 
   }
   if (w.flags & WFM_WAVE_CLIP) {
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) total.v[u] = clip_value(total.v[u], w.clip_lo, w.clip_hi);
+    for (int u = 0; u < U; ++u) total.v[u] = clip_value(total.v[u], w.clip_lo, w.clip_hi);
   }
   return total;
 }
@@ -360,6 +367,20 @@ __global__ void mark_seg_wave_kernel(DevProgram P, int32_t* __restrict__ seg_wav
   if (w >= n_waves) return;
   const int seg_begin = P.waves[w].seg_begin, n_seg = P.waves[w].n_seg;
   for (int k = threadIdx.x & 31; k < n_seg; k += 32) seg_wave[seg_begin + k] = (int32_t)w;
+}
+
+// samples owned by active segments (one thread per segment, after prepare_segments_kernel)
+__global__ void count_active_kernel(DevProgram P, int64_t n_segs, unsigned long long* __restrict__ total) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long len = 0;
+  if (s < n_segs && P.seg_ptr[s + 1].fac > P.seg_ptr[s].fac) {
+    const WfmWave w = P.waves[P.seg_wave[s]];
+    const int k = (int)(s - w.seg_begin);
+    const int64_t hi = (k + 1 < w.n_seg) ? (int64_t)P.seg_start[s + 1] : w.n;
+    len = (unsigned long long)max((int64_t)0, hi - (int64_t)P.seg_start[s]);
+  }
+  for (int d = 16; d; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
+  if ((threadIdx.x & 31) == 0 && len) atomicAdd(total, len);
 }
 
 // one thread per segment: start position, value of a flat segment, plan of an active one
@@ -424,7 +445,7 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
     for (int r = 0; r < tm.n_ref && !ext; ++r) {
       const WfmRef rf = P.refs[tm.ref_begin + r];
       if (rf.kind != WFM_POW_ONE) ext = true;
-      else o[r] = (uint16_t)(row_slot[p0.fac + rf.slot] * kSlotStride);
+      else o[r] = (uint16_t)(row_slot[p0.fac + rf.slot] * slot_stride(1));
     }
     uint16_t flags = (tm.flags & WFM_TERM_GROUP_END) ? kCTermGroupEnd : 0u;
     if (ext) {
@@ -484,7 +505,7 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
     if (p1.fac > p0.fac) {
       L.n_arows += 1;
       L.blk16 += P.seg_plan[w.seg_begin + k].blk16;
-      L.n_units += (b - a + kUnit - 1) / kUnit;
+      L.n_units += (b - a + P.unit - 1) / P.unit;
     } else if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) {
       L.n_patch += 1;
     }
@@ -694,7 +715,7 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
         blk += (size_t)pl.blk16 * 16;
       }
       ia += 1;
-      first += (b - a + kUnit - 1) / kUnit;
+      first += (b - a + P.unit - 1) / P.unit;
     } else {
       const double v = P.seg_val[seg];
       if (__double_as_longlong(v) != __double_as_longlong(w.offset)) {
@@ -762,9 +783,9 @@ __device__ __forceinline__ void fill_tile(unsigned char* p, int n_rows, double v
 }
 
 // per-warp shared-memory slice (dynamic shared memory; all sub-arrays 16-byte aligned):
-//   [out: tile_samples x OutT][slots: n_slots x kSlotStride][packet buffer 0][packet buffer 1][2 mbarriers]
-__host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int pkt_cap, size_t esz) {
-  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * kSlotStride + 2 * (size_t)pkt_cap + 16;
+//   [out: tile_samples x OutT][slots: n_slots x slot_stride(unit)][packet buffer 0][packet buffer 1][2 mbarriers]
+__host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int unit, int pkt_cap, size_t esz) {
+  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * slot_stride(unit) + 2 * (size_t)pkt_cap + 16;
   return (b + 127) & ~(size_t)127;
 }
 
@@ -789,7 +810,7 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
-template <typename OutT, bool kAccumulate>
+template <typename OutT, bool kAccumulate, int U>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
                   OutT* __restrict__ out) {
@@ -797,12 +818,13 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   // this warp's private slice
-  unsigned char* slice = k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, sizeof(OutT));
+  unsigned char* slice = k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, U, P.pkt_cap, sizeof(OutT));
   OutT* s_out = reinterpret_cast<OutT*>(slice);
   unsigned char* s_slots = slice + (size_t)P.tile_samples * sizeof(OutT);
+  constexpr int kSlotStride = slot_stride(U);
   unsigned char* s_pkt = s_slots + (size_t)P.n_slots * kSlotStride;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
-  unsigned char* sl = s_slots + lane * 8 * kUnit;  // this lane's value slots
+  unsigned char* sl = s_slots + lane * 8 * U;  // this lane's value slots
 
   // the erf coefficient table next to the tile buffers (global / L1 latency showed up as
   // long-scoreboard stalls in the generic rows); the only block-level barrier of the kernel
@@ -824,9 +846,9 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    Val one;  // slot 0: the unit a missing term reference multiplies by
+    Val<U> one;  // slot 0: the unit a missing term reference multiplies by
 #pragma unroll
-    for (int u = 0; u < kUnit; ++u) one.v[u] = 1.0;
+    for (int u = 0; u < U; ++u) one.v[u] = 1.0;
     st_slot(sl, one);
   }
   __syncwarp();
@@ -917,31 +939,31 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
         const uint4 rw = reinterpret_cast<const uint4*>(arows)[lo];  // ARow: start first | rel len | n_sc n_rot n_gen n_term | gseg
         const int start = rw.x & 0xffffu, first = rw.x >> 16, rel = rw.y & 0xfffu, len = rw.y >> 16;
         const uint32_t sflags = (rw.y >> 12) & 0xfu;
-        const int jj = start + (i - first) * kUnit;
-        const int n_valid = min(kUnit, start + len - jj);
-        double x[kUnit];
+        const int jj = start + (i - first) * U;
+        const int n_valid = min(U, start + len - jj);
+        double x[U];
         if (plain_grid) {
           // the tile's sample index fits 32 bits (channels hold < 2^31 samples)
           const int jg = (int)j0 + jj;
 #pragma unroll
-          for (int u = 0; u < kUnit; ++u) x[u] = add(t0, mul((double)(jg + u), delta));
+          for (int u = 0; u < U; ++u) x[u] = add(t0, mul((double)(jg + u), delta));
         } else {
 #pragma unroll 1
-          for (int u = 0; u < kUnit; ++u) x[u] = abscissa(P.waves[h->wave], P.x, j0 + min(jj + u, cnt - 1));
+          for (int u = 0; u < U; ++u) x[u] = abscissa(P.waves[h->wave], P.x, j0 + min(jj + u, cnt - 1));
         }
-        Val r;
+        Val<U> r;
         if (sflags & kSegWide) {
 #pragma unroll 1
-          for (int u = 0; u < kUnit; ++u) {
+          for (int u = 0; u < U; ++u) {
             double im;
             eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
           }
         } else {
-          r = eval_unit(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+          r = eval_unit<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
                         (int)rw.w, we, x, sl, s_erf);
         }
 #pragma unroll
-        for (int u = 0; u < kUnit; ++u)
+        for (int u = 0; u < U; ++u)
           if (u < n_valid) s_out[jj + u] = (OutT)r.v[u];
       }
     }
@@ -1005,6 +1027,12 @@ cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n,
   return cudaGetLastError();
 }
 
+cudaError_t launch_count_active(const DevProgram& P, int64_t n_segs, unsigned long long* total, cudaStream_t stream) {
+  if (n_segs <= 0) return cudaSuccess;
+  count_active_kernel<<<(unsigned)((n_segs + 127) / 128), 128, 0, stream>>>(P, n_segs, total);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prepare_tiles(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, uint32_t* stats,
                                  cudaStream_t stream) {
   if (n.n_tiles <= 0) return cudaSuccess;
@@ -1031,16 +1059,16 @@ cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int6
   return cudaGetLastError();
 }
 
-int warp_fixed_bytes(int n_slots) { return n_slots * kSlotStride + 16 + 128; }
+int warp_fixed_bytes(int n_slots, int unit) { return n_slots * slot_stride(unit) + 16 + 128; }
 
 size_t sample_smem_bytes(const DevProgram& P, int dtype) {
-  return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
+  return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.unit, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
 }
 
-template <typename OutT, bool kAcc>
+template <typename OutT, bool kAcc, int U>
 static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                      int dtype, void* out, cudaStream_t stream) {
-  auto k = sample_kernel<OutT, kAcc>;
+  auto k = sample_kernel<OutT, kAcc, U>;
   const size_t smem = sample_smem_bytes(P, dtype);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1059,12 +1087,19 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
                           int accumulate, void* out, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
   if (tile_begin + n_tiles > INT32_MAX) return cudaErrorInvalidValue;
-  if (dtype == WFM_F64)
-    return accumulate ? launch_persistent<double, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
-                      : launch_persistent<double, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
-  if (dtype == WFM_F32)
-    return accumulate ? launch_persistent<float, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
-                      : launch_persistent<float, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  if (dtype == WFM_F64 || dtype == WFM_F32) {
+    const int sel = (dtype == WFM_F32 ? 4 : 0) | (accumulate ? 2 : 0) | (P.unit == 2 ? 1 : 0);
+    switch (sel) {
+      case 0: return launch_persistent<double, false, 1>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 1: return launch_persistent<double, false, 2>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 2: return launch_persistent<double, true, 1>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 3: return launch_persistent<double, true, 2>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 4: return launch_persistent<float, false, 1>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 5: return launch_persistent<float, false, 2>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      case 6: return launch_persistent<float, true, 1>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      default: return launch_persistent<float, true, 2>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    }
+  }
   dim3 grid((unsigned)n_tiles), block(kThreads);
   if (accumulate) sample_kernel_c128<true><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
   else sample_kernel_c128<false><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
