@@ -175,7 +175,7 @@ def test_program_info_and_pool_trim(ns):
     for k in range(3):
         prog = engine.Program(batch)
         info = prog.info()
-        assert info['tile_samples'] % 128 == 0 and 128 <= info['tile_samples'] <= 1024
+        assert info['tile_samples'] % 128 == 0 and 128 <= info['tile_samples'] <= 1536
         assert info['n_tiles'] == -(-2000 // info['tile_samples']) and info['samples_per_lane_unit'] in (1, 2, 4)
         y = prog.sample_host()
         prog.close()

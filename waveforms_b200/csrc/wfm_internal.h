@@ -14,7 +14,7 @@ namespace wfm {
 #define WFM_K1_MIN_BLOCKS 2  // resident 8-warp CTAs per SM the kernel is sized for
 #endif
 #ifndef WFM_K1_MAX_TILE
-#define WFM_K1_MAX_TILE 1024
+#define WFM_K1_MAX_TILE 1536
 #endif
 // Samples one lane evaluates together (a UNIT: consecutive samples of one active segment),
 // chosen per program (DevProgram::unit).  Two samples per lane run as independent dependency

@@ -766,10 +766,16 @@ __device__ __forceinline__ void fill_tile(unsigned char* p, int n_rows, double v
     }
   }
   switch (n_rows) {  // tile_samples is a multiple of 128: 2 rows each in fp64, 1 row in fp32
+    case 24: fill_rows<24>(p, v); break;
+    case 22: fill_rows<22>(p, v); break;
+    case 20: fill_rows<20>(p, v); break;
+    case 18: fill_rows<18>(p, v); break;
     case 16: fill_rows<16>(p, v); break;
     case 14: fill_rows<14>(p, v); break;
     case 12: fill_rows<12>(p, v); break;
+    case 11: fill_rows<11>(p, v); break;
     case 10: fill_rows<10>(p, v); break;
+    case 9: fill_rows<9>(p, v); break;
     case 8: fill_rows<8>(p, v); break;
     case 7: fill_rows<7>(p, v); break;
     case 6: fill_rows<6>(p, v); break;
