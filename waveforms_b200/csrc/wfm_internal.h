@@ -13,6 +13,9 @@ namespace wfm {
 #ifndef WFM_K1_MIN_BLOCKS
 #define WFM_K1_MIN_BLOCKS 2  // resident 8-warp CTAs per SM the kernel is sized for
 #endif
+#ifndef WFM_K1_WARPS
+#define WFM_K1_WARPS 8  // autonomous warps per CTA
+#endif
 #ifndef WFM_K1_MAX_TILE
 #define WFM_K1_MAX_TILE 1536
 #endif
@@ -32,7 +35,7 @@ constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
 #ifndef WFM_K1_ERF_SMEM
 #define WFM_K1_ERF_SMEM 0
 #endif
-constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K1_ERF_SMEM ? 2560 : 0)) / 8) & ~127;
+constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K1_ERF_SMEM ? 2560 : 0)) / WFM_K1_WARPS) & ~127;
 
 // Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of `unit`
 // doubles in the warp's shared slice, slot-major (slot k of lane l at byte

@@ -53,7 +53,7 @@
 
 namespace wfm {
 
-constexpr int kThreads = 256;  // 8 autonomous warps per CTA
+constexpr int kThreads = 32 * WFM_K1_WARPS;  // autonomous warps per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
 
 template <typename T> struct OutVec;
