@@ -10,7 +10,7 @@ def find(marker, start=0):
     for i in range(start, len(cu)):
         if marker in cu[i]: return i + 1
     raise KeyError(marker)
-marks = [('eval: head', 'Val eval_unit('), ('eval: sincos rows', 'for (int i = 0; i < n_sc; ++i)'), ('eval: rot rows', 'for (int j = 0; j < n_child; ++j)'),
+marks = [('eval: head', 'Val<U> eval_unit('), ('eval: sincos rows', 'for (int i = 0; i < n_sc; ++i)'), ('eval: rot rows', 'for (int j = 0; j < n_child; ++j)'),
          ('eval: generic rows', '// -- every other basis function'), ('eval: terms', '  // -- terms'), ('eval: end', '// ---- pre-pass (once per program)')]
 k0 = find('sample_kernel(const __grid_constant__')
 marks2 = [('kernel: setup', 'sample_kernel(const __grid_constant__'), ('tile: prefetch + packet wait', '  for (; t < tile_end; t += n_warps) {'),
