@@ -149,6 +149,28 @@ void release(int dev, const Block& b) {
 }
 }  // namespace pool
 
+// Small results the host needs from the pre-pass (counters, packet totals) are written by a
+// one-thread kernel into MAPPED pinned host memory instead of being copied: a cudaMemcpy D2H
+// would queue on the device->host copy engine behind another thread's multi-gigabyte readback.
+__global__ void export_words_kernel(const uint32_t* __restrict__ src, volatile uint32_t* dst, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+static uint32_t* mapped_scratch() {
+  static thread_local uint32_t* p = nullptr;
+  if (!p && cudaHostAlloc((void**)&p, 256, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) p = nullptr;
+  return p;
+}
+// n 32-bit words from device memory -> dst (host), complete after the stream is synchronised
+static cudaError_t read_words(void* dst_host, const void* src_dev, int n, cudaStream_t st) {
+  uint32_t* m = mapped_scratch();
+  if (!m) return cudaErrorMemoryAllocation;
+  export_words_kernel<<<1, 32, 0, st>>>((const uint32_t*)src_dev, m, n);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) memcpy(dst_host, m, sizeof(uint32_t) * n);
+  return e;
+}
+
 struct WfmProgram {
   int device = 0;
   wfm::DevProgram dev{};
@@ -157,6 +179,9 @@ struct WfmProgram {
   pool::Block tile_tables{nullptr, 0};  // tile rows, packet sizes / offsets (sized once the tile size is chosen)
   pool::Block packets{nullptr, 0};  // the tile packets (sized by the device pre-pass)
   int sizing_passes = 0;
+  // one event per stream wfm_sample was called on: destroy waits for exactly that work
+  std::vector<std::pair<cudaStream_t, cudaEvent_t>> launch_events;
+  std::mutex ev_mu;
   pool::Block stage{nullptr, 0};    // device staging buffer of wfm_sample_host
   wfm::TileDesc* d_tiles = nullptr;
   std::vector<int64_t> tile_prefix;  // tiles before channel w
@@ -167,9 +192,13 @@ struct WfmProgram {
 
   ~WfmProgram() {
     DeviceGuard g(device);
-    // kernels launched through this program (on any stream) may still read the tables;
-    // cudaFree used to wait for them implicitly
-    cudaDeviceSynchronize();
+    // kernels launched through this program may still read the tables (cudaFree used to wait
+    // for them implicitly): wait for the last launch on every stream that was used — not for
+    // the whole device, another thread's copies may be in flight
+    for (auto& se : launch_events) {
+      cudaEventSynchronize(se.second);
+      cudaEventDestroy(se.second);
+    }
     pool::release(device, arena);
     pool::release(device, tile_tables);
     pool::release(device, packets);
@@ -328,6 +357,10 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   if (!out) return fail(WFM_EINVAL, "null output handle");
   *out = nullptr;
   StageTimer tm("program_create");
+  // all device work of this call runs on the calling thread's own stream: two host threads
+  // (a scheduler double-buffering its batches) overlap one batch's upload and pre-pass with
+  // the other's device->host copy instead of serialising on the legacy default stream
+  const cudaStream_t ST = cudaStreamPerThread;
   int max_rows = 0;
   int rc = validate(d, &max_rows);
   if (rc != WFM_OK) return rc;
@@ -372,7 +405,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   char* base = (char*)p->arena.p;
   auto up = [&](size_t off, const void* host, size_t bytes) {
     // pinned host tables (cudaHostAlloc / torch pin_memory) copy at link speed; pageable ones are staged by the driver
-    if (e == cudaSuccess && bytes > 0) e = cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess && bytes > 0) e = cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, ST);
   };
   up(o_waves, d->waves, sizeof(WfmWave) * d->n_waves);
   up(o_bound, d->seg_bound, sizeof(double) * d->n_segs);
@@ -405,17 +438,16 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                          nullptr, (const int64_t*)(base + o_prefix), nullptr};
   wfm::PrepareCounts pc{d->n_waves, d->n_segs, d->n_facs, d->n_terms, 0};
   p->dev.unit = 1;
-  if (e == cudaSuccess) e = wfm::launch_prepare_segments(p->dev, pc, pb, 0);
+  if (e == cudaSuccess) e = wfm::launch_prepare_segments(p->dev, pc, pb, ST);
 
   // Unit: samples per lane and evaluation.  Dense programs (more than two rounds of 32 active
   // samples in an average 1024-sample tile) evaluate two samples per lane, sparse ones one.
   {
     unsigned long long active = 0;
     unsigned long long* d_active = (unsigned long long*)(base + o_stats);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_active, 0, sizeof(active), 0);
-    if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&active, d_active, sizeof(active), cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_active, 0, sizeof(active), ST);
+    if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, ST);
+    if (e == cudaSuccess) e = read_words(&active, d_active, 2, ST);
     const char* force = std::getenv("WFM_K1_UNIT");
     if (force && (force[0] == '1' || force[0] == '2')) p->dev.unit = force[0] - '0';
     else p->dev.unit = (samples > 0 && (double)active * 1024.0 > 64.0 * (double)samples) ? 2 : 1;
@@ -455,12 +487,11 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     if (e != cudaSuccess || ts <= wfm::kMinTileSamples || n_tiles == 0) break;
     // sizing pass: statistics only
     uint32_t stats[2] = {0, 0};
-    e = cudaMemsetAsync(d_stats, 0, sizeof(stats), 0);
+    e = cudaMemsetAsync(d_stats, 0, sizeof(stats), ST);
     up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
     pc.n_tiles = n_tiles;
-    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, d_stats, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);  // also: tile_prefix may be rewritten now
+    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, d_stats, ST);
+    if (e == cudaSuccess) e = read_words(stats, d_stats, 2, ST);  // synchronises: tile_prefix may be rewritten now
     ++sizing_passes;
     if (e != cudaSuccess || (int64_t)stats[1] * 4096 <= n_tiles) break;
   }
@@ -489,20 +520,18 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     pc.n_tiles = n_tiles;
     up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
     // pre-pass 1b: the tile rows with their packet sizes; then the packet offsets
-    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, nullptr, 0);
+    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, nullptr, ST);
     if (e == cudaSuccess)
       e = wfm::launch_scan((uint32_t*)(base2 + o_pktsize), (uint32_t*)(base2 + o_pktoff), (uint32_t*)(base2 + o_scratch),
-                           n_tiles, 0);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(&total16, (uint32_t*)(base2 + o_pktoff) + n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+                           n_tiles, ST);
+    if (e == cudaSuccess) e = read_words(&total16, (uint32_t*)(base2 + o_pktoff) + n_tiles, 1, ST);
   }
   tm.lap("device pre-pass 1 (tiles)");
   // pass 2: the packets themselves
   if (e == cudaSuccess) e = pool::alloc(device, std::max<size_t>((size_t)total16 * 16, 16), &p->packets);
   p->dev.packets = (const unsigned char*)p->packets.p;
-  if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, n_tiles, (unsigned char*)p->packets.p, 0);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, n_tiles, (unsigned char*)p->packets.p, ST);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ST);
   tm.lap("device pre-pass 2");
   if (e != cudaSuccess) {
     delete p;
@@ -560,7 +589,18 @@ int wfm_sample(wfm_program_t prog, const WfmLaunch* l, void* stream) {
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
   WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, l->accumulate, l->out,
                               (cudaStream_t)stream));
-  if (t1 > t0) prog->launches += 1;
+  if (t1 > t0) {
+    prog->launches += 1;
+    std::lock_guard<std::mutex> lk(prog->ev_mu);
+    cudaEvent_t ev = nullptr;
+    for (auto& se : prog->launch_events)
+      if (se.first == (cudaStream_t)stream) ev = se.second;
+    if (!ev) {
+      WFM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      prog->launch_events.emplace_back((cudaStream_t)stream, ev);
+    }
+    WFM_CUDA(cudaEventRecord(ev, (cudaStream_t)stream));
+  }
   return WFM_OK;
 }
 
@@ -570,6 +610,7 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   if (rc != WFM_OK) return rc;
   if (l->accumulate) return fail(WFM_EUNSUPPORTED, "accumulate is not available with host buffers");
   StageTimer tm("sample_host");
+  const cudaStream_t ST = cudaStreamPerThread;  // see wfm_program_create
   DeviceGuard g(prog->device);
   const size_t esz = l->dtype == WFM_F64 ? 8 : (l->dtype == WFM_F32 ? 4 : 16);
   // only the extent actually covered by the requested channels is staged/copied
@@ -585,13 +626,13 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   }
   tm.lap("stage alloc");
   // padding between channels is never written by the kernel: keep it defined
-  WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, 0));
+  WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, ST));
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->stage.p, 0));
+  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->stage.p, ST));
   if (t1 > t0) prog->launches += 1;
   WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->stage.p + (size_t)lo * esz,
-                           (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, 0));
-  WFM_CUDA(cudaStreamSynchronize(0));
+                           (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, ST));
+  WFM_CUDA(cudaStreamSynchronize(ST));
   tm.lap("memset+kernel+D2H");
   return WFM_OK;
 }
