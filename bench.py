@@ -333,14 +333,19 @@ def main():
         # every call on the calling thread's stream).  Every step still uploads its IR and
         # reads back every sample.
         import concurrent.futures as cf
-        hosts = [host_np, torch.empty(batch.total_samples, dtype=tdt, pin_memory=True).numpy()]
+        hosts = [host_np]
+        try:
+            hosts.append(torch.empty(batch.total_samples, dtype=tdt, pin_memory=True).numpy())
+        except RuntimeError:  # no room for a second pinned buffer: single-buffered steps
+            pass
+        n_thr = len(hosts)
 
         def one_step(k):
             p2 = engine.Program(batch, local_rank)
-            p2.sample_host(dtype=code, out=hosts[k % 2])
+            p2.sample_host(dtype=code, out=hosts[k % n_thr])
             p2.close()
 
-        with cf.ThreadPoolExecutor(max_workers=2) as pool:
+        with cf.ThreadPoolExecutor(max_workers=n_thr) as pool:
             list(pool.map(one_step, range(4)))  # warm-up: both threads, both buffers
             barrier()
             t0 = time.perf_counter()
@@ -355,8 +360,8 @@ def main():
                'h2d_bytes_per_step': int(batch.nbytes()), 'd2h_bytes_per_step': int(batch.total_samples * esz),
                'steps': e_steps, 'ms_per_step': dt / e_steps * 1e3,
                'path': 'per step: wfm_program_create(pinned host IR -> device, device pre-pass) + wfm_sample_host(kernel + '
-                       'D2H of every sample into pinned host memory) + wfm_program_destroy; two host threads alternate the '
-                       'steps (double buffering)'}
+                       'D2H of every sample into pinned host memory) + wfm_program_destroy; %d host thread(s) alternate the '
+                       'steps (double buffering)' % n_thr}
         checksum = float(host_np[:N_SAMP].sum())
     else:
         prog.close()
