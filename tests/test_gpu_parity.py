@@ -183,3 +183,54 @@ def test_program_info_and_pool_trim(ns):
         assert np.array_equal(y, first)
         if k == 1:
             assert engine.load_library().wfm_trim() == 0
+
+
+def _small_batch(ns, n=6):
+    rng = np.random.default_rng(21)
+    ws = []
+    for k in range(n):
+        I, Q = ns.mixing(rng.uniform(0.2, 1) * ns.cosPulse(30e-9) >> (60e-9 + 41e-9 * k), freq=rng.uniform(-150e6, 150e6),
+                         phase=rng.uniform(0, 6), DRAGScaling=3e-10)
+        w = I if k % 2 else Q
+        w.start, w.stop, w.sample_rate = 0.0, 0.5e-6 + 7e-9 * k, 2e9
+        ws.append(w)
+    return ws
+
+
+def test_channel_subrange_and_stream(ns):
+    """wfm_sample over a sub-range of the program's channels, on a non-default stream, writes
+    exactly those channels' samples."""
+    import torch
+    from waveforms_b200 import engine
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower
+    ws = _small_batch(ns)
+    batch = lower([channel_grid(w) for w in ws])
+    prog = engine.Program(batch)
+    full = prog.sample_device().cpu().numpy()
+    stream = torch.cuda.Stream()
+    out = torch.full((batch.total_samples, ), -7.0, dtype=torch.float64, device='cuda')
+    with torch.cuda.stream(stream):
+        prog.sample_device(out=out, first_wave=2, n_wave=3, stream=stream.cuda_stream)
+    stream.synchronize()
+    got = out.cpu().numpy()
+    prog.close()
+    for k, w in enumerate(ws):
+        off, n = int(batch.waves['out_off'][k]), int(batch.waves['n'][k])
+        if 2 <= k < 5:
+            assert np.array_equal(got[off:off + n], full[off:off + n])
+        else:
+            assert np.all(got[off:off + n] == -7.0)
+
+
+def test_sample_batch_over_two_devices(ns):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from waveforms_b200 import sample_batch
+    ws = _small_batch(ns, 9)
+    one = sample_batch(ws, devices=[0]).numpy()
+    two = sample_batch(ws, devices=[0, 1])
+    assert {t.device.index for t in two.tensors} == {0, 1}
+    for a, b in zip(one, two.numpy()):
+        assert np.array_equal(a, b)
