@@ -18,10 +18,10 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / 'tests' / 'golden'))
+import cases  # noqa: E402
 
 
 def build(cfg, ns):
-    import cases
     from waveforms_b200.batch import channel_grid
     from waveforms_b200.lowering import lower, replicate
     rng = np.random.default_rng(20260000 + int(cfg[3]))
@@ -84,6 +84,50 @@ def main():
         prog.close()
         del out
         torch.cuda.empty_cache()
+    # configs 1 and 2 are tiny (0.16 / 64 MB of output): their figure of merit is latency
+    import time
+    lat = {}
+    for name in ('cfg1', 'cfg2x1'):
+        if name == 'cfg1':
+            x_wav, y_wav = cases._readme(ns)
+            chans = [x_wav, y_wav]
+            for w in chans:
+                w.start, w.stop, w.sample_rate = -1e-6, 9e-6, 1e9
+        else:
+            chans = bench.build_frame(ns)
+        from waveforms_b200.batch import channel_grid
+        from waveforms_b200.lowering import lower
+        batch = lower([channel_grid(w) for w in chans]).pin()
+        prog = engine.Program(batch, 0)
+        out = torch.empty(batch.total_samples, dtype=torch.float64, device='cuda')
+        for _ in range(3):
+            prog.sample_device(dtype=engine.WFM_F64, out=out)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(21)]
+        ev[0].record()
+        for k in range(20):
+            prog.sample_device(dtype=engine.WFM_F64, out=out)
+            ev[k + 1].record()
+        torch.cuda.synchronize()
+        k1_us = min(ev[k].elapsed_time(ev[k + 1]) for k in range(20)) * 1e3
+        t0 = time.perf_counter()
+        for _ in range(20):
+            prog.sample_device(dtype=engine.WFM_F64, out=out)
+        torch.cuda.synchronize()
+        launch_us = (time.perf_counter() - t0) / 20 * 1e6
+        prog.close()
+        host = torch.empty(batch.total_samples, dtype=torch.float64, pin_memory=True).numpy()
+        ts = []
+        for _ in range(6):
+            t0 = time.perf_counter()
+            p2 = engine.Program(batch, 0)
+            p2.sample_host(out=host)
+            p2.close()
+            ts.append((time.perf_counter() - t0) * 1e6)
+        n = int(batch.waves['n'].sum())
+        lat[name] = {'channels': len(chans), 'samples': n, 'k1_device_us': k1_us, 'k1_back_to_back_wall_us': launch_us,
+                     'create_sample_host_destroy_us': min(ts[1:]), 'GSa/s_device': n / k1_us / 1e3}
+    res['latency'] = lat
     print(json.dumps(res, indent=1))
 
 
