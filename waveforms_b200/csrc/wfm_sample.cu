@@ -282,10 +282,12 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const double a_t = mul(wv, sub(x[u], shift));
-        const double eps = sub(sub(a_t, a[u]), D);  // second-order expansion in eps below
+        // cos(a + D + eps) = C - eps S - eps^2 C / 2 ...: |eps| ~ ulp(a) (4e-11 at 1e5 rad, the
+        // far end of a 100 us frame at 200 MHz), so the second-order term (< 1e-21) is dropped
+        const double eps = sub(sub(a_t, a[u]), D);
         const double C = fma(c.v[u], cD, -(s.v[u] * sD));
         const double S = fma(s.v[u], cD, c.v[u] * sD);
-        r.v[u] = fma(-0.5 * eps * eps, C, fma(-eps, S, C));
+        r.v[u] = fma(-eps, S, C);
       }
       st_slot(dst, r);
       dst += kSlotStride;
