@@ -57,9 +57,11 @@ struct SRow {
   double shift, w;
   uint32_t n_child;  // CRows that follow
   uint32_t pad0;
-  double pad1;
+  // two-sample units on an affine grid: the second sample's (cos, sin) by rotation of the
+  // first's by D = w * delta (+ the measured residual), instead of a second range reduction
+  double D, cD, sD;
 };
-static_assert(sizeof(SRow) == 32, "SRow layout");
+static_assert(sizeof(SRow) == 48, "SRow layout");
 
 // cos(a_t), a_t = w * (x - shift) rounded exactly as the reference rounds it, from the parent's
 // (cos, sin)(a): a_t = a + D + eps with D ~ w * (parent shift - shift) a host constant (cos D,

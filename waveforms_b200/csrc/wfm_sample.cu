@@ -252,7 +252,7 @@ template <int U>
 __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                          bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
                                          const double (&x)[U], unsigned char* __restrict__ sl,
-                                         const double* __restrict__ erf_s) {
+                                         const double* __restrict__ erf_s, bool affine) {
   constexpr int kSlotStride = slot_stride(U);
   unsigned char* dst = sl + kSlotStride;  // slot 1
   // -- one range reduction + both polynomials per frequency; the further cosines of that
@@ -270,7 +270,23 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
 #pragma unroll
       for (int u = 0; u < U; ++u) a[u] = mul(wv, sub(x[u], shift));
     }
-    sincos_cw_n<U>(a, s.v, c.v);
+    if (U == 2 && affine) {
+      // second sample of the unit: rotation of the first by D = w * delta plus the MEASURED
+      // residual eps = (a1 - a0) - D (first order; |eps| ~ ulp(a)), not a second range reduction
+      const double a0[1] = {a[0]};
+      double s0[1], c0[1];
+      sincos_cw_n<1>(a0, s0, c0);
+      const double D = sr->D, cD = sr->cD, sD = sr->sD;
+      const double eps = sub(sub(a[U - 1], a[0]), D);
+      const double C = fma(c0[0], cD, -(s0[0] * sD));
+      const double S = fma(s0[0], cD, c0[0] * sD);
+      c.v[0] = c0[0];
+      s.v[0] = s0[0];
+      c.v[U - 1] = fma(-eps, S, C);
+      s.v[U - 1] = fma(eps, C, S);
+    } else {
+      sincos_cw_n<U>(a, s.v, c.v);
+    }
     st_slot(dst, c);
     dst += kSlotStride;
     row += sizeof(SRow);
@@ -295,7 +311,7 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
     }
   }
   // -- every other basis function
-  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(blk + (n_sc + n_rot) * 32);
+  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(blk + n_sc * (int)sizeof(SRow) + n_rot * (int)sizeof(CRow));
 #pragma unroll 1
   for (int k = 0; k < n_gen; ++k) {
     const int func = gr[k].func;
@@ -691,8 +707,8 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
         arows[ia] = r;
       }
       if (!(pl.flags & kSegWide)) {
-        // trig rows sit in slot order (SRow and CRow are both 32 bytes, one slot each)
-        GRow* gr = reinterpret_cast<GRow*>(blk + (pl.n_sc + pl.n_rot) * 32);
+        // trig rows sit in slot order: slot s starts after (s - 1) rows, of which the SRows are 16 bytes longer
+        GRow* gr = reinterpret_cast<GRow*>(blk + pl.n_sc * sizeof(SRow) + pl.n_rot * sizeof(CRow));
         CTerm* ct = reinterpret_cast<CTerm*>(gr + pl.n_gen);
         const int nf = p1.fac - p0.fac;
         for (int r = lane; r < nf; r += 32) {
@@ -700,14 +716,23 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
           const int slot = P.row_slot[p0.fac + r];
           if (f.func == WFM_COS_SINCOS) {
             uint32_t n_child = 0;
+            int g = 0;  // SRows before this one
+            for (int q = 0; q < r; ++q) g += P.facs[p0.fac + q].func == WFM_COS_SINCOS;
             for (int q = r + 1; q < nf; ++q) {
-              const WfmFactor g = P.facs[p0.fac + q];
-              n_child += (g.func == WFM_COS_ROT && (int)P.args[g.arg_off] == r);
+              const WfmFactor c = P.facs[p0.fac + q];
+              n_child += (c.func == WFM_COS_ROT && (int)P.args[c.arg_off] == r);
             }
-            *reinterpret_cast<SRow*>(blk + (slot - 1) * 32) = SRow{f.shift, f.a0, n_child, 0u, 0.0};
+            const double D = f.a0 * w.delta;
+            double sD, cD;
+            sincos(D, &sD, &cD);
+            *reinterpret_cast<SRow*>(blk + (slot - 1) * sizeof(CRow) + g * (sizeof(SRow) - sizeof(CRow))) =
+                SRow{f.shift, f.a0, n_child, 0u, D, cD, sD};
           } else if (f.func == WFM_COS_ROT) {
             const double* __restrict__ p = P.args + f.arg_off;  // [base_row, base_shift, D, cos D, sin D]
-            *reinterpret_cast<CRow*>(blk + (slot - 1) * 32) = CRow{f.shift, p[2], p[3], p[4]};
+            int g = 0;  // SRows up to and including its parent
+            for (int q = 0; q <= (int)p[0]; ++q) g += P.facs[p0.fac + q].func == WFM_COS_SINCOS;
+            *reinterpret_cast<CRow*>(blk + (slot - 1) * sizeof(CRow) + g * (sizeof(SRow) - sizeof(CRow))) =
+                CRow{f.shift, p[2], p[3], p[4]};
           } else if (f.func != WFM_NOP) {
             gr[slot - 1 - pl.n_sc - pl.n_rot] = GRow{f.func, f.arg_off, f.shift, f.a0, f.a1};
           }
@@ -968,7 +993,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           }
         } else {
           r = eval_unit<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
-                        (int)rw.w, we, x, sl, s_erf);
+                        (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
