@@ -39,6 +39,9 @@
 
 namespace wfm {
 
+#ifndef WFM_FFT_MAX_RADIX
+#define WFM_FFT_MAX_RADIX 4  // largest power-of-two butterfly: 4, 8 or 16
+#endif
 constexpr int kFftThreads = 512;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
@@ -127,6 +130,48 @@ __device__ __forceinline__ void dft_small<7>(double2 (&v)[7], double sgn) {
   for (int p = 0; p < 7; ++p) v[p] = o[p];
 }
 
+// R = R1*R2 point DFT in registers (Cooley-Tukey inside the thread): input index n = n1 + R1*n2,
+// output index k = R2*k1 + k2; cs/sn hold cos / sin of 2 pi m / R.  Fully unrolled: every index is a
+// compile-time constant, so v stays in registers.
+template <int R1, int R2>
+__device__ __forceinline__ void dft_composite(double2 (&v)[R1 * R2], double sgn, const double* cs, const double* sn) {
+  constexpr int R = R1 * R2;
+  double2 y[R];
+#pragma unroll
+  for (int n1 = 0; n1 < R1; ++n1) {
+    double2 t[R2];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) t[n2] = v[n1 + R1 * n2];
+    dft_small<R2>(t, sgn);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int m = (n1 * k2) % R;
+      y[n1 * R2 + k2] = m == 0 ? t[k2] : cmul(t[k2], make_double2(cs[m], sgn * sn[m]));
+    }
+  }
+#pragma unroll
+  for (int k2 = 0; k2 < R2; ++k2) {
+    double2 t[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) t[n1] = y[n1 * R2 + k2];
+    dft_small<R1>(t, sgn);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) v[R2 * k1 + k2] = t[k1];
+  }
+}
+template <>
+__device__ __forceinline__ void dft_small<8>(double2 (&v)[8], double sgn) {
+  constexpr double cs[8] = {1.0, 0.7071067811865476, 6.123233995736766e-17, -0.7071067811865475, -1.0, -0.7071067811865477, -1.8369701987210297e-16, 0.7071067811865474};
+  constexpr double sn[8] = {0.0, 0.7071067811865475, 1.0, 0.7071067811865476, 1.2246467991473532e-16, -0.7071067811865475, -1.0, -0.7071067811865477};
+  dft_composite<2, 4>(v, sgn, cs, sn);
+}
+template <>
+__device__ __forceinline__ void dft_small<16>(double2 (&v)[16], double sgn) {
+  constexpr double cs[16] = {1.0, 0.9238795325112867, 0.7071067811865476, 0.38268343236508984, 6.123233995736766e-17, -0.3826834323650897, -0.7071067811865475, -0.9238795325112867, -1.0, -0.9238795325112868, -0.7071067811865477, -0.38268343236509034, -1.8369701987210297e-16, 0.38268343236509, 0.7071067811865474, 0.9238795325112865};
+  constexpr double sn[16] = {0.0, 0.3826834323650898, 0.7071067811865475, 0.9238795325112867, 1.0, 0.9238795325112867, 0.7071067811865476, 0.3826834323650899, 1.2246467991473532e-16, -0.38268343236508967, -0.7071067811865475, -0.9238795325112865, -1.0, -0.9238795325112866, -0.7071067811865477, -0.3826834323650904};
+  dft_composite<4, 4>(v, sgn, cs, sn);
+}
+
 // one Stockham stage of radix R over C = 2^LOGC interleaved transforms (point p of
 // transform c lives at [p*C + c]); tw: the length-L table (shared or global memory)
 template <int R>
@@ -171,6 +216,12 @@ __device__ double2* smem_fft(double2* a, double2* b, const FftPlan& P, int logc,
       case 3: stockham_stage<3>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
       case 4: stockham_stage<4>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
       case 5: stockham_stage<5>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+#if WFM_FFT_MAX_RADIX >= 8
+      case 8: stockham_stage<8>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+#endif
+#if WFM_FFT_MAX_RADIX >= 16
+      case 16: stockham_stage<16>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+#endif
       default: stockham_stage<7>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
     }
     __syncthreads();
@@ -400,6 +451,20 @@ static bool factor_smooth(int64_t n, int* radix, int* n_stage) {
       n /= r;
     }
   }
+#if WFM_FFT_MAX_RADIX >= 16
+  while (n % 16 == 0) {
+    if (k >= kMaxStages) return false;
+    radix[k++] = 16;
+    n /= 16;
+  }
+#endif
+#if WFM_FFT_MAX_RADIX >= 8
+  while (n % 8 == 0) {
+    if (k >= kMaxStages) return false;
+    radix[k++] = 8;
+    n /= 8;
+  }
+#endif
   while (n % 4 == 0) {
     if (k >= kMaxStages) return false;
     radix[k++] = 4;
