@@ -115,6 +115,32 @@ def summarize_clocks(lines):
             'samples': len(sm)}
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and the pinned host buffers it allocates from now on) to the NUMA
+    node of its GPU: with one rank per GPU the device<->host copies of all ranks otherwise
+    land on whichever node the processes started on.  Best effort; returns a note."""
+    try:
+        out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(device_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith('00000000:'):
+            bdf = '0000:' + bdf.split(':', 1)[1]
+        node = int(Path(f'/sys/bus/pci/devices/{bdf}/numa_node').read_text().strip())
+        if node < 0:
+            return 'numa: single node'
+        cpus = []
+        for part in Path(f'/sys/devices/system/node/node{node}/cpulist').read_text().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f'numa: node {node} has no allowed cpus'
+        os.sched_setaffinity(0, allowed)
+        return f'numa: node {node}, {len(allowed)} cpus'
+    except Exception as exc:  # noqa: BLE001
+        return f'numa: not bound ({type(exc).__name__})'
+
+
 def measured_peak():
     p = ROOT / 'MEASURED_PEAKS.json'
     if p.exists():
@@ -258,6 +284,7 @@ def main():
     from waveforms_b200.batch import channel_grid
     from waveforms_b200.lowering import lower, replicate
 
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else 'numa: not bound (single rank)'
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -403,7 +430,7 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
             'data': 'synthetic', 'config': config, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': roofline, 'cpu_baseline': cpu,
-            'kernel_layout': kernel_layout,
+            'kernel_layout': kernel_layout, 'numa': numa_note,
             'host': {'frame_build_s': t_build, 'frame_lower_s': t_lower, 'ir_bytes': int(batch.nbytes()),
                      'checksum_ch0': checksum}}
     print(json.dumps(line), flush=True)
