@@ -51,6 +51,10 @@
 #include "wfm_internal.h"
 
 
+#ifndef WFM_K1_SKIP_UNIT_REFS
+#define WFM_K1_SKIP_UNIT_REFS 1  // +3.5 % on the dense RB batch, neutral on sparse frames
+#endif
+
 namespace wfm {
 
 constexpr int kThreads = 32 * WFM_K1_WARPS;  // autonomous warps per CTA
@@ -356,10 +360,25 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
 #pragma unroll 1
       for (int u = 0; u < U; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
     } else {
+#if WFM_K1_SKIP_UNIT_REFS
+      // only the references the term has (an absent one is slot 0 = 1.0: the product is the same)
+      prod = ld_slot<U>(sl + (c.z & 0xffffu) * U);
+      if (c.z >> 16) {
+        const Val<U> f1 = ld_slot<U>(sl + (c.z >> 16) * U);
+#pragma unroll
+        for (int u = 0; u < U; ++u) prod.v[u] = mul(prod.v[u], f1.v[u]);
+        if (c.w & 0xffffu) {
+          const Val<U> f2 = ld_slot<U>(sl + (c.w & 0xffffu) * U);
+#pragma unroll
+          for (int u = 0; u < U; ++u) prod.v[u] = mul(prod.v[u], f2.v[u]);
+        }
+      }
+#else
       const Val<U> f0 = ld_slot<U>(sl + (c.z & 0xffffu) * U), f1 = ld_slot<U>(sl + (c.z >> 16) * U),
                    f2 = ld_slot<U>(sl + (c.w & 0xffffu) * U);
 #pragma unroll
       for (int u = 0; u < U; ++u) prod.v[u] = mul(mul(f0.v[u], f1.v[u]), f2.v[u]);
+#endif
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) grp.v[u] = add(grp.v[u], mul(amp, prod.v[u]));
