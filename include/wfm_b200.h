@@ -150,7 +150,8 @@ typedef struct WfmProgram* wfm_program_t;
 /* output element types */
 #define WFM_F64 0
 #define WFM_F32 1
-#define WFM_C128 2  /* interleaved (re, im) doubles */
+#define WFM_C128 2  /* interleaved (re, im) doubles; assembled from two real planes in scratch that
+                       belongs to the program: WFM_C128 launches of ONE program must be stream-ordered */
 
 typedef struct WfmLaunch {
   int64_t first_wave;  /* channels [first_wave, first_wave + n_wave) */

@@ -189,6 +189,10 @@ struct WfmProgram {
   int64_t total_samples = 0;  // extent of the output buffer in samples
   int64_t launches = 0;
   bool any_complex = false;
+  // complex128 output: a planar twin (channels [0, n) = real parts, [n, 2n) = imaginary parts,
+  // both real-valued programs for the fast kernel) and the scratch the two planes are sampled into
+  WfmProgram* planar = nullptr;
+  pool::Block cscratch{nullptr, 0};
 
   ~WfmProgram() {
     DeviceGuard g(device);
@@ -199,6 +203,8 @@ struct WfmProgram {
       cudaEventSynchronize(se.second);
       cudaEventDestroy(se.second);
     }
+    delete planar;
+    pool::release(device, cscratch);
     pool::release(device, arena);
     pool::release(device, tile_tables);
     pool::release(device, packets);
@@ -537,6 +543,59 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     delete p;
     return fail(WFM_ECUDA, "uploading the program failed: %s", cudaGetErrorString(e));
   }
+  if (p->any_complex) {
+    // the planar twin: every table twice, the second copy's amplitudes = the imaginary parts
+    const int64_t nw = d->n_waves, ns = d->n_segs, nf = d->n_facs, nt = d->n_terms, nr = d->n_refs;
+    std::vector<WfmWave> waves2(2 * nw);
+    std::vector<double> bound2(2 * ns);
+    std::vector<WfmSegPtr> segptr2(2 * ns + 1);
+    std::vector<WfmFactor> facs2(2 * nf);
+    std::vector<WfmTerm> terms2(2 * nt);
+    std::vector<WfmRef> refs2(2 * nr);
+    for (int c = 0; c < 2; ++c) {
+      for (int64_t w = 0; w < nw; ++w) {
+        WfmWave v = d->waves[w];
+        v.flags &= ~(uint32_t)WFM_WAVE_COMPLEX;
+        v.seg_begin += (int32_t)(c * ns);
+        v.out_off += c * ((total + 3) & ~(int64_t)3);  // planes stay 16-byte aligned
+        if (c == 1) {
+          v.offset = 0.0;  // offsets and clipping act on the real part
+          v.flags &= ~(uint32_t)WFM_WAVE_CLIP;
+        }
+        waves2[c * nw + w] = v;
+      }
+      for (int64_t k = 0; k < ns; ++k) {
+        bound2[c * ns + k] = d->seg_bound[k];
+        segptr2[c * ns + k] = WfmSegPtr{(int32_t)(d->seg_ptr[k].fac + c * nf), (int32_t)(d->seg_ptr[k].term + c * nt)};
+      }
+      for (int64_t k = 0; k < nf; ++k) facs2[c * nf + k] = d->facs[k];  // argument pool and abscissae are shared
+      for (int64_t k = 0; k < nt; ++k) {
+        WfmTerm t = d->terms[k];
+        if (c == 1) t.amp_re = t.amp_im;
+        t.amp_im = 0.0;
+        t.ref_begin += (int32_t)(c * nr);
+        terms2[c * nt + k] = t;
+      }
+      for (int64_t k = 0; k < nr; ++k) refs2[c * nr + k] = d->refs[k];
+    }
+    segptr2[2 * ns] = WfmSegPtr{(int32_t)(2 * nf), (int32_t)(2 * nt)};
+    WfmProgramDesc d2 = *d;
+    d2.n_waves = 2 * nw; d2.waves = waves2.data();
+    d2.n_segs = 2 * ns; d2.seg_bound = bound2.data(); d2.seg_ptr = segptr2.data();
+    d2.n_facs = 2 * nf; d2.facs = facs2.data();
+    d2.n_terms = 2 * nt; d2.terms = terms2.data();
+    d2.n_refs = 2 * nr; d2.refs = refs2.data();
+    if (2 * (double)ns > INT32_MAX - 2 || 2 * (double)nf > INT32_MAX || 2 * (double)nt > INT32_MAX || 2 * (double)nr > INT32_MAX) {
+      delete p;
+      return fail(WFM_EINVAL, "complex program too large for 32-bit indices once split into planes");
+    }
+    const int rc2 = wfm_program_create(&d2, device, &p->planar);
+    if (rc2 != WFM_OK) {
+      delete p;
+      return rc2;
+    }
+    tm.lap("planar twin (complex output)");
+  }
   *out = p;
   return WFM_OK;
 }
@@ -580,6 +639,42 @@ static int check_launch(wfm_program_t prog, const WfmLaunch* l, int64_t* first, 
   return WFM_OK;
 }
 
+// the launch(es) of one sampling request: channels [first, first + count) -> out (device)
+static int launch_request(wfm_program_t prog, int64_t first, int64_t count, int dtype, int accumulate, void* out,
+                          cudaStream_t st) {
+  const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
+  if (dtype != WFM_C128) {
+    WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, dtype, accumulate, out, st));
+    return WFM_OK;
+  }
+  // complex128: real and imaginary plane by the real-valued kernel into scratch, then
+  // interleaved.  The scratch belongs to the program: complex launches of one program must be
+  // stream-ordered.
+  const int64_t total = (prog->total_samples + 3) & ~(int64_t)3, nw = (int64_t)prog->waves.size();  // plane stride
+  const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(total, 4) * 2;
+  if (prog->cscratch.bytes < bytes) {
+    pool::release(prog->device, prog->cscratch);
+    prog->cscratch = pool::Block{nullptr, 0};
+    cudaError_t ea = pool::alloc(prog->device, bytes, &prog->cscratch);
+    if (ea != cudaSuccess)
+      return fail(WFM_ENOMEM, "allocating the %zu-byte plane scratch failed: %s", bytes, cudaGetErrorString(ea));
+  }
+  double* re = (double*)prog->cscratch.p;
+  double* im = nullptr;
+  if (prog->planar) {
+    WfmProgram* q = prog->planar;
+    im = re + total;
+    const int64_t a0 = q->tile_prefix[first], a1 = q->tile_prefix[first + count];
+    const int64_t b0 = q->tile_prefix[nw + first], b1 = q->tile_prefix[nw + first + count];
+    WFM_CUDA(wfm::launch_sample(q->dev, q->d_tiles, a0, a1 - a0, WFM_F64, 0, re, st));
+    WFM_CUDA(wfm::launch_sample(q->dev, q->d_tiles, b0, b1 - b0, WFM_F64, 0, re, st));
+  } else {
+    WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, WFM_F64, 0, re, st));
+  }
+  WFM_CUDA(wfm::launch_interleave_c128(prog->d_tiles + t0, t1 - t0, re, im, out, accumulate, st));
+  return WFM_OK;
+}
+
 int wfm_sample(wfm_program_t prog, const WfmLaunch* l, void* stream) {
   int64_t first, count, need;
   int rc = check_launch(prog, l, &first, &count, &need);
@@ -587,8 +682,8 @@ int wfm_sample(wfm_program_t prog, const WfmLaunch* l, void* stream) {
   if ((uintptr_t)l->out % 16) return fail(WFM_EINVAL, "output buffer must be 16-byte aligned");
   DeviceGuard g(prog->device);
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, l->accumulate, l->out,
-                              (cudaStream_t)stream));
+  rc = launch_request(prog, first, count, l->dtype, l->accumulate, l->out, (cudaStream_t)stream);
+  if (rc != WFM_OK) return rc;
   if (t1 > t0) {
     prog->launches += 1;
     std::lock_guard<std::mutex> lk(prog->ev_mu);
@@ -628,7 +723,10 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   // padding between channels is never written by the kernel: keep it defined
   WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, ST));
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
-  WFM_CUDA(wfm::launch_sample(prog->dev, prog->d_tiles, t0, t1 - t0, l->dtype, 0, prog->stage.p, ST));
+  {
+    const int rc2 = launch_request(prog, first, count, l->dtype, 0, prog->stage.p, ST);
+    if (rc2 != WFM_OK) return rc2;
+  }
   if (t1 > t0) prog->launches += 1;
   WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->stage.p + (size_t)lo * esz,
                            (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, ST));

@@ -218,5 +218,8 @@ size_t sample_smem_bytes(const DevProgram& P, int dtype);
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
                           int accumulate, void* out, cudaStream_t stream);
+// out[tile samples] = (re, im) (+ out when accumulate); im may be NULL (zero imaginary part)
+cudaError_t launch_interleave_c128(const TileDesc* tiles, int64_t n_tiles, const double* re, const double* im, void* out,
+                                   int accumulate, cudaStream_t stream);
 
 }  // namespace wfm

@@ -1042,31 +1042,34 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   if (lane == 0 && store_pending) bulk_wait_read_all();  // shared memory must outlive the copy's reads
 }
 
-// complex128 output: interleaved (re, im); one sample per thread per row, ABI tables.
+// complex128 output: the real and the imaginary PLANE are sampled by the real-valued kernel
+// (a planar twin of the program, wfm_api.cu) into scratch; this kernel interleaves them
+// tile by tile (exactly the samples of the requested channels, no padding touched).
+// im == nullptr: a real program read as complex.
 template <bool kAccumulate>
-__global__ void __launch_bounds__(kThreads) sample_kernel_c128(const __grid_constant__ DevProgram P,
-                                                               const TileDesc* __restrict__ tiles, double2* __restrict__ out) {
+__global__ void __launch_bounds__(256) interleave_c128_kernel(const TileDesc* __restrict__ tiles, const double* __restrict__ re,
+                                                              const double* __restrict__ im, double2* __restrict__ out) {
   const TileDesc td = tiles[blockIdx.x];
-  const WfmWave w = P.waves[td.wave];
-  const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
-  const int32_t* __restrict__ st = P.seg_start + td.seg0;
+  const double* __restrict__ r = re + td.out0;
+  const double* __restrict__ i = im ? im + td.out0 : nullptr;
   double2* __restrict__ dst = out + td.out0;
-  for (int jj = threadIdx.x; jj < td.cnt; jj += kThreads) {
-    const double x = abscissa(w, P.x, td.j0 + jj);
-    int lo = 0, hi = td.nb - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
-    }
-    double re, im;
-    eval_segment_slow(P, td.seg0 + lo, we, x, re, im);
+  for (int j = threadIdx.x; j < td.cnt; j += blockDim.x) {
+    double2 v = make_double2(r[j], i ? i[j] : 0.0);
     if (kAccumulate) {
-      double2 o = dst[jj];
-      re = add(o.x, re);
-      im = add(o.y, im);
+      const double2 o = dst[j];
+      v.x = add(o.x, v.x);
+      v.y = add(o.y, v.y);
     }
-    dst[jj] = make_double2(re, im);
+    dst[j] = v;
   }
+}
+
+cudaError_t launch_interleave_c128(const TileDesc* tiles, int64_t n_tiles, const double* re, const double* im, void* out,
+                                   int accumulate, cudaStream_t stream) {
+  if (n_tiles == 0) return cudaSuccess;
+  if (accumulate) interleave_c128_kernel<true><<<(unsigned)n_tiles, 256, 0, stream>>>(tiles, re, im, (double2*)out);
+  else interleave_c128_kernel<false><<<(unsigned)n_tiles, 256, 0, stream>>>(tiles, re, im, (double2*)out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n, const PrepareBuffers& b, cudaStream_t stream) {
@@ -1152,10 +1155,7 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
       default: return launch_persistent<float, true, 2>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
     }
   }
-  dim3 grid((unsigned)n_tiles), block(kThreads);
-  if (accumulate) sample_kernel_c128<true><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
-  else sample_kernel_c128<false><<<grid, block, 0, stream>>>(P, tiles + tile_begin, (double2*)out);
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;  // WFM_C128 is assembled from two real planes (wfm_api.cu)
 }
 
 }  // namespace wfm
