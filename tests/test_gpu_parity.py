@@ -234,3 +234,55 @@ def test_sample_batch_over_two_devices(ns):
     assert {t.device.index for t in two.tensors} == {0, 1}
     for a, b in zip(one, two.numpy()):
         assert np.array_equal(a, b)
+
+
+def test_very_long_channel(ns):
+    """Maximum sizes: one channel of 3e8 samples (2.4 GB of fp64 output, 200 k tiles).  The
+    device result stays on the GPU; windows at the start, in the middle and at the very end
+    are compared with the oracle evaluated on exactly those abscissae (x[j] = t0 + j*delta
+    with j up to 3e8 must round as np.arange does)."""
+    import torch
+    from oracle import wfm_oracle as O
+    from waveforms_b200 import engine
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower
+    n, rate = 300_000_000, 2e9
+    t_end = n / rate
+    w = ns.zero()
+    for t0 in (50e-9, 0.5 * t_end + 3e-9, t_end - 40e-9):
+        I, _ = ns.mixing(0.8 * ns.cosPulse(30e-9) >> t0, freq=137e6, phase=0.4, DRAGScaling=3e-10)
+        w = w + I
+    w.start, w.stop, w.sample_rate = 0.0, t_end, rate
+    chan, grid = channel_grid(w)
+    assert grid.n == n
+    prog = engine.Program(lower([(chan, grid)]))
+    out = prog.sample_device()
+    torch.cuda.synchronize()
+    prog.close()
+    delta = grid.delta
+    for centre in (50e-9, 0.5 * t_end + 3e-9, t_end - 40e-9):
+        j0 = max(int(centre * rate) - 200, 0)
+        j1 = min(j0 + 400, n)
+        x = grid.t0 + np.arange(j0, j1, dtype=np.float64) * delta
+        want = O.waveform_call(w.bounds, w.seq, x)
+        got = out[j0:j1].cpu().numpy()
+        assert np.max(np.abs(want)) > 0.1
+        assert rel_err(got, want) <= FP64_TOL
+    # everything else is exactly zero: the sum of |y| comes from the three pulses only
+    total = float(out.abs().sum())
+    ref_total = 0.0
+    for centre in (50e-9, 0.5 * t_end + 3e-9, t_end - 40e-9):
+        j0 = max(int(centre * rate) - 200, 0)
+        ref_total += float(out[j0:min(j0 + 400, n)].abs().sum())
+    assert abs(total - ref_total) <= 1e-9 * ref_total
+    del out
+    torch.cuda.empty_cache()
+
+
+def test_too_long_channel_is_rejected(ns):
+    from waveforms_b200 import engine
+    from waveforms_b200.lowering import Channel, Grid, lower
+    w = ns.cosPulse(20e-9)
+    batch = lower([(w._channel(), Grid(n=2**31 - 1, t0=0.0, delta=1e-9))])
+    with pytest.raises(engine.EngineError, match='2\\^31'):
+        engine.Program(batch)
