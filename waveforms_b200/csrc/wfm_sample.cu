@@ -397,6 +397,198 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
   return total;
 }
 
+// ---- the fp32 evaluator (WFM_F32 output, 1e-6 parity) --------------------------------------
+// Arguments and range reductions stay in fp64 (a 200 MHz carrier reaches 1e5 rad: fp32 cannot
+// even hold the argument), everything after the reduction runs in fp32: the polynomial work,
+// the rotations, the products and the sums.  fp32 dependent-issue latency is a fraction of
+// fp64's, which is what this kernel is bound by.  Value slots hold floats (same slot area).
+template <int U>
+struct ValF {
+  float v[U];
+};
+template <int U>
+__device__ __forceinline__ ValF<U> ld_slot_f(const unsigned char* p) {
+  ValF<U> r;
+  if constexpr (U == 2) {
+    const float2 d = *reinterpret_cast<const float2*>(p);
+    r.v[0] = d.x;
+    r.v[1] = d.y;
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) r.v[u] = reinterpret_cast<const float*>(p)[u];
+  }
+  return r;
+}
+template <int U>
+__device__ __forceinline__ void st_slot_f(unsigned char* p, const ValF<U>& r) {
+  if constexpr (U == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) reinterpret_cast<float*>(p)[u] = r.v[u];
+  }
+}
+
+// sin and cos of an fp64 argument to fp32 accuracy: fp64 Cody-Waite reduction (two terms of
+// pi/2 are plenty for a 24-bit result), fp32 minimax kernels on [-pi/4, pi/4]
+__device__ __forceinline__ void sincos_f32(double a, float& s_out, float& c_out) {
+  if (!(fabs(a) <= 1073741824.0)) {
+    const SinCos r = sincos_cw(a);
+    s_out = (float)r.s;
+    c_out = (float)r.c;
+    return;
+  }
+  const double q = rint(a * kTrig[0]);
+  double rd = fma(-q, kTrig[1], a);
+  rd = fma(-q, kTrig[2], rd);
+  const float r = (float)rd, z = r * r;
+  // fdlibm k_sinf / k_cosf coefficients
+  const float ps = fmaf(fmaf(fmaf(2.7183114939898219064e-6f, z, -1.9839334836096632576e-4f), z, 8.3333293858894631756e-3f), z,
+                        -1.6666666641626524e-1f);
+  const float s = fmaf(r * z, ps, r);
+  const float pc = fmaf(fmaf(fmaf(2.4390448796277409065e-5f, z, -1.3886763774609929e-3f), z, 4.1666623323739063189e-2f), z,
+                        -4.9999999725103100312e-1f);
+  const float c = fmaf(z, pc, 1.0f);
+  const int n = (int)q;
+  const bool odd = n & 1;
+  const float ss = odd ? c : s, cc = odd ? s : c;
+  s_out = __uint_as_float(__float_as_uint(ss) ^ ((uint32_t)(n & 2) << 30));
+  c_out = __uint_as_float(__float_as_uint(cc) ^ ((uint32_t)((n + 1) & 2) << 30));
+}
+
+template <int U>
+__device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
+                                                const DevProgram& P, int gseg, const WaveEval& w, const double (&x)[U],
+                                                unsigned char* __restrict__ sl) {
+  constexpr int kStride = 32 * 4 * U;  // float slots: half the fp64 stride inside the same slot area
+  unsigned char* dst = sl + kStride;   // slot 1 (slot 0 holds 1.0f)
+  const unsigned char* __restrict__ row = blk;
+#pragma unroll 1
+  for (int i = 0; i < n_sc; ++i) {
+    const SRow* __restrict__ sr = reinterpret_cast<const SRow*>(row);
+    const double wv = sr->w, shift = sr->shift;
+    const int n_child = (int)sr->n_child;
+    double a[U];
+    ValF<U> s, c;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      a[u] = mul(wv, sub(x[u], shift));
+      sincos_f32(a[u], s.v[u], c.v[u]);
+    }
+    st_slot_f(dst, c);
+    dst += kStride;
+    row += sizeof(SRow);
+#pragma unroll 1
+    for (int j = 0; j < n_child; ++j) {
+      const CRow* __restrict__ cr = reinterpret_cast<const CRow*>(row);
+      const double cshift = cr->shift, D = cr->D;
+      const float cD = (float)cr->cD, sD = (float)cr->sD;
+      ValF<U> r;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float eps = (float)sub(sub(mul(wv, sub(x[u], cshift)), a[u]), D);
+        const float C = fmaf(c.v[u], cD, -(s.v[u] * sD));
+        const float S = fmaf(s.v[u], cD, c.v[u] * sD);
+        r.v[u] = fmaf(-eps, S, C);
+      }
+      st_slot_f(dst, r);
+      dst += kStride;
+      row += sizeof(CRow);
+    }
+  }
+  const GRow* __restrict__ gr = reinterpret_cast<const GRow*>(row);
+#pragma unroll 1
+  for (int k = 0; k < n_gen; ++k) {
+    const int func = gr[k].func;
+    const double shift = gr[k].shift, a0 = gr[k].a0;
+    ValF<U> r;
+    if (func == WFM_COS) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float sn;
+        sincos_f32(mul(a0, sub(x[u], shift)), sn, r.v[u]);
+      }
+    } else if (func == WFM_LINEAR) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) r.v[u] = (float)sub(x[u], shift);
+    } else if (func == WFM_GAUSSIAN) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float q = (float)sub(x[u], shift) / (float)a0;
+        r.v[u] = expf(-q * q);
+      }
+    } else if (func == WFM_ERF) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) r.v[u] = erff((float)sub(x[u], shift) / (float)a0);
+    } else {
+      const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) r.v[u] = (float)eval_factor(fa, x[u], P.args);
+    }
+    st_slot_f(dst, r);
+    dst += kStride;
+  }
+  const uint4* __restrict__ ct = reinterpret_cast<const uint4*>(gr + n_gen);
+  ValF<U> total, grp;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    total.v[u] = (float)w.offset;
+    grp.v[u] = 0.0f;
+  }
+#pragma unroll 1
+  for (int it = 0; it < n_term; ++it) {
+    const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags (offsets for fp64 unit-1 slots: halve for floats)
+    const float amp = (float)__hiloint2double((int)c.y, (int)c.x);
+    ValF<U> prod;
+    if ((c.w >> 16) & kCTermExt) {
+      // extended terms read fp64 slots: evaluate the segment's term in fp64 from the ABI tables
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+        const WfmSegPtr p0 = P.seg_ptr[gseg];
+        const WfmTerm tm = P.terms[p0.term + it];
+        double pr = 1.0;
+        for (int r = 0; r < tm.n_ref; ++r) {
+          const WfmRef ref = P.refs[tm.ref_begin + r];
+          double v = (double)reinterpret_cast<const float*>(sl + P.row_slot[p0.fac + ref.slot] * kStride)[u];
+          if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
+          else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
+          pr *= v;
+        }
+        prod.v[u] = (float)pr;
+      }
+    } else {
+      prod = ld_slot_f<U>(sl + ((c.z & 0xffffu) * U >> 1));
+      if (c.z >> 16) {
+        const ValF<U> f1 = ld_slot_f<U>(sl + ((c.z >> 16) * U >> 1));
+#pragma unroll
+        for (int u = 0; u < U; ++u) prod.v[u] *= f1.v[u];
+        if (c.w & 0xffffu) {
+          const ValF<U> f2 = ld_slot_f<U>(sl + ((c.w & 0xffffu) * U >> 1));
+#pragma unroll
+          for (int u = 0; u < U; ++u) prod.v[u] *= f2.v[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) grp.v[u] = fmaf(amp, prod.v[u], grp.v[u]);
+    if ((c.w >> 16) & kCTermGroupEnd) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        total.v[u] += grp.v[u];
+        grp.v[u] = 0.0f;
+      }
+    }
+  }
+  Val<U> out;
+#pragma unroll
+  for (int u = 0; u < U; ++u) out.v[u] = (double)total.v[u];
+  if (w.flags & WFM_WAVE_CLIP) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) out.v[u] = clip_value(out.v[u], w.clip_lo, w.clip_hi);
+  }
+  return out;
+}
+
 // ---- pre-pass (once per program) ----------------------------------------------------------
 // one warp per channel: the owning channel of each of its segment rows
 __global__ void mark_seg_wave_kernel(DevProgram P, int32_t* __restrict__ seg_wave, int64_t n_waves) {
@@ -898,10 +1090,17 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    Val<U> one;  // slot 0: the unit a missing term reference multiplies by
+    if constexpr (sizeof(OutT) == 4) {
+      ValF<U> one;  // slot 0: the unit a missing term reference multiplies by (fp32 evaluator: float slots)
 #pragma unroll
-    for (int u = 0; u < U; ++u) one.v[u] = 1.0;
-    st_slot(sl, one);
+      for (int u = 0; u < U; ++u) one.v[u] = 1.0f;
+      st_slot_f(s_slots + lane * 4 * U, one);
+    } else {
+      Val<U> one;
+#pragma unroll
+      for (int u = 0; u < U; ++u) one.v[u] = 1.0;
+      st_slot(sl, one);
+    }
   }
   __syncwarp();
 
@@ -1011,8 +1210,13 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
             eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
           }
         } else {
-          r = eval_unit<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
-                        (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X));
+          if constexpr (sizeof(OutT) == 4) {
+            r = eval_unit_f32<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
+                                 (int)rw.w, we, x, s_slots + lane * 4 * U);
+          } else {
+            r = eval_unit<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                             (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X));
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
