@@ -286,3 +286,22 @@ def test_too_long_channel_is_rejected(ns):
     batch = lower([(w._channel(), Grid(n=2**31 - 1, t0=0.0, delta=1e-9))])
     with pytest.raises(engine.EngineError, match='2\\^31'):
         engine.Program(batch)
+
+
+@pytest.mark.parametrize('unit', ['1', '2'])
+@pytest.mark.parametrize('name', ['readme_x_sample', 'cfg2_xy_stack', 'cfg2_z', 'cfg3_rb_I', 'cfg3_rb_Q', 'cfg5_drag_sin',
+                                  'complex_amp'])
+def test_both_unit_sizes(name, unit, golden, monkeypatch):
+    """The kernel evaluates one or two samples per lane (chosen from the program's density);
+    both evaluators must meet the fp64 tolerance on sparse and dense programs alike."""
+    if name not in golden:
+        pytest.skip('case not in the golden set')
+    monkeypatch.setenv('WFM_K1_UNIT', unit)
+    rec = golden[name]
+    got = b200_eval(rec)
+    assert got.shape == rec['expect'].shape
+    assert rel_err(got, rec['expect']) <= FP64_TOL
+    if not name.startswith('complex') and rec['grid'][0] == 'sample':
+        from waveforms_b200 import sample_batch
+        f32 = sample_batch([b200_object(rec)], dtype=np.float32).numpy()[0]
+        assert rel_err(f32.astype(np.float64), rec['expect']) <= FP32_TOL
