@@ -171,7 +171,8 @@ def test_batched_channel_filters_match_per_channel(ns):
 
 def test_iir_mode_policy():
     from waveforms_b200 import dsp
-    assert dsp.resolve_iir_mode(1000) == 'exact' and dsp.resolve_iir_mode(400000) == 'scan'
+    assert dsp.IIR_MODE == 'exact' and dsp.resolve_iir_mode(400000) == 'exact'  # drop-in path: parity first
+    assert dsp.resolve_iir_mode(1000, 'auto') == 'exact' and dsp.resolve_iir_mode(400000, 'auto') == 'scan'
     assert dsp.resolve_iir_mode(400000, 'exact') == 'exact'
     with pytest.raises(ValueError):
         dsp.resolve_iir_mode(10, 'fast')

@@ -60,7 +60,7 @@ class BatchResult:
 
 
 def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
-                 filters='own', iir_mode=None):
+                 filters='own', iir_mode='auto'):
     """Sample every waveform in ``waveforms`` on its own start/stop/sample_rate
     grid.  ``dtype``: np.float64 (reference parity, 1e-12) or np.float32
     (fp32 output, 1e-6).  ``devices``: list of CUDA device indices to shard the
@@ -69,7 +69,9 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
 
     ``filters='own'`` applies each waveform's ``.filters`` (sample-time IIR,
     waveform.py:193-203) on the device; ``None`` skips them.  ``iir_mode``:
-    'exact' | 'scan' | 'auto' (default: ``dsp.IIR_MODE``)."""
+    'exact' (bit-identical to scipy, sequential in time) | 'scan' (block-parallel,
+    equal up to the filter's rounding-noise gain) | 'auto' (exact up to 32 768
+    samples per channel, scan above; the default here) | None (``dsp.IIR_MODE``)."""
     import torch
     engine.require_gpu()
     items = [channel_grid(w, sample_rate) for w in waveforms]

@@ -24,7 +24,9 @@ _IIR_MODES = {'exact': IIR_EXACT, 'scan': IIR_SCAN}
 #   'scan'   block-parallel associative scan (the throughput path, 2.6 TB/s on B200); equals
 #            the sequential result up to the filter's own rounding-noise gain
 #   'auto'   exact up to IIR_AUTO_EXACT_MAX samples per signal, scan above
-IIR_MODE = 'auto'
+# The drop-in single-waveform path (Waveform.sample, _sample_iter) defaults to 'exact': parity
+# with the reference first.  The batched path (sample_batch) defaults to 'auto'.
+IIR_MODE = 'exact'
 IIR_AUTO_EXACT_MAX = 32768
 
 
