@@ -107,28 +107,24 @@ __global__ void __launch_bounds__(32 * kExactWarps) sosfilt_exact_kernel(const _
     if (base + 32 + lane < n) nxt = xs[base + 32 + lane];  // in flight while this block is filtered
     const int cnt = (int)min((int64_t)32, n - base);
     double out = 0.0;
-    if (S == 1) {  // the common cases without the section loop
-      const Biquad q = P.sec[0];
-#pragma unroll 8
+    if (S == 1 && cnt == 32) {  // full blocks of the common cases: no branch between the samples, so the
+      const Biquad q = P.sec[0];  // 32 broadcasts are issued ahead of the recurrence that consumes them
+#pragma unroll
       for (int l = 0; l < 32; ++l) {
-        if (l < cnt) {
-          double cur = shfl_f64(mine, l), o;
-          if (shift) cur = sub(cur, P.initial);
-          biquad_step(q, cur, z0[0], z1[0], o);
-          if (lane == l) out = o;
-        }
+        double cur = shfl_f64(mine, l), o;
+        if (shift) cur = sub(cur, P.initial);
+        biquad_step(q, cur, z0[0], z1[0], o);
+        if (lane == l) out = o;
       }
-    } else if (S == 2) {
+    } else if (S == 2 && cnt == 32) {
       const Biquad q0 = P.sec[0], q1 = P.sec[1];
-#pragma unroll 8
+#pragma unroll
       for (int l = 0; l < 32; ++l) {
-        if (l < cnt) {
-          double cur = shfl_f64(mine, l), o, o2;
-          if (shift) cur = sub(cur, P.initial);
-          biquad_step(q0, cur, z0[0], z1[0], o);
-          biquad_step(q1, o, z0[1], z1[1], o2);
-          if (lane == l) out = o2;
-        }
+        double cur = shfl_f64(mine, l), o, o2;
+        if (shift) cur = sub(cur, P.initial);
+        biquad_step(q0, cur, z0[0], z1[0], o);
+        biquad_step(q1, o, z0[1], z1[1], o2);
+        if (lane == l) out = o2;
       }
     } else {
 #pragma unroll 1
@@ -351,20 +347,18 @@ __global__ void __launch_bounds__(32 * kExactWarps) lfilter_exact_kernel(const _
     if (base + 32 + lane < n) nxt = xs[base + 32 + lane];
     const int cnt = (int)min((int64_t)32, n - base);
     double out = 0.0;
-    if (M == 1) {
-#pragma unroll 8
-      for (int l = 0; l < 32; ++l)
-        if (l < cnt) {
-          const double o = lfilter_step<1>(P, shfl_f64(mine, l), z);
-          if (lane == l) out = o;
-        }
-    } else if (M == 2) {
-#pragma unroll 8
-      for (int l = 0; l < 32; ++l)
-        if (l < cnt) {
-          const double o = lfilter_step<2>(P, shfl_f64(mine, l), z);
-          if (lane == l) out = o;
-        }
+    if (M == 1 && cnt == 32) {  // full blocks: no branch between the samples (see sosfilt_exact_kernel)
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const double o = lfilter_step<1>(P, shfl_f64(mine, l), z);
+        if (lane == l) out = o;
+      }
+    } else if (M == 2 && cnt == 32) {
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const double o = lfilter_step<2>(P, shfl_f64(mine, l), z);
+        if (lane == l) out = o;
+      }
     } else {
 #pragma unroll 1
       for (int l = 0; l < cnt; ++l) {
