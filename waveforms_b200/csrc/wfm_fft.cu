@@ -254,22 +254,32 @@ __device__ __forceinline__ double2 big_twiddle(const BigTwiddle& T, int64_t m, d
 extern __shared__ __align__(16) unsigned char fft_smem_raw[];
 
 // ---- one-level fused filter: n <= kMaxPoints -------------------------------------
+// One CTA per PAIR of real signals: z = x_a + i x_b goes through one complex transform.  H is
+// the Hermitian part of the caller's response (hermitian_part_kernel), so ifft(fft(z) H) =
+// y_a + i y_b with both real.
 __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan P, const double* __restrict__ x,
                                                                         double* __restrict__ y, int64_t stride,
-                                                                        const double2* __restrict__ H) {
+                                                                        int64_t n_sig, const double2* __restrict__ H) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + P.L;
   const double2* tw = stage_twiddles(P, b + P.L);
-  const double* xs = x + (int64_t)blockIdx.x * stride;
-  double* ys = y + (int64_t)blockIdx.x * stride;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = make_double2(xs[p], 0.0);
+  const int64_t s0 = 2 * (int64_t)blockIdx.x;
+  const bool two = s0 + 1 < n_sig;
+  const double* xs = x + s0 * stride;
+  const double* xs2 = xs + (two ? stride : 0);
+  double* ys = y + s0 * stride;
+  for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = make_double2(xs[p], two ? xs2[p] : 0.0);
   __syncthreads();
   double2* f = smem_fft(a, b, P, 0, -1.0, tw);
   for (int p = threadIdx.x; p < P.L; p += blockDim.x) f[p] = cmul(f[p], __ldg(H + p));
   __syncthreads();
   double2* g = smem_fft(f, f == a ? b : a, P, 0, +1.0, tw);
   const double inv = 1.0 / (double)P.L;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) ys[p] = g[p].x * inv;
+  for (int p = threadIdx.x; p < P.L; p += blockDim.x) {
+    const double2 v = g[p];
+    ys[p] = v.x * inv;
+    if (two) ys[stride + p] = v.y * inv;
+  }
 }
 
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
@@ -289,7 +299,9 @@ template <bool kTwAfter, bool kRealIn, bool kRealOut>
 __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
                                                                const void* __restrict__ in, void* __restrict__ out,
                                                                int64_t in_stride, int64_t out_stride, double sgn,
-                                                               double scale) {
+                                                               double scale, int64_t n_real) {
+  // kRealIn / kRealOut: blockIdx.y is a PAIR of real signals (2y, 2y+1 < n_real) packed as the
+  // real and imaginary part of one complex signal (the filter's response is Hermitian)
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + ((size_t)N1 << logc);
@@ -304,7 +316,9 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
     if (c < cw) {
       const int64_t idx = (int64_t)r * N2 + c0 + c;
       if (kRealIn) {
-        v.x = static_cast<const double*>(in)[sig * in_stride + idx];
+        const double* xa = static_cast<const double*>(in) + 2 * sig * in_stride + idx;
+        v.x = xa[0];
+        if (2 * sig + 1 < n_real) v.y = xa[in_stride];
       } else {
         v = static_cast<const double2*>(in)[sig * in_stride + idx];
       }
@@ -320,8 +334,13 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
     const int64_t idx = (int64_t)r * N2 + c0 + c;
     double2 v = f[e];
     if (kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
-    if (kRealOut) static_cast<double*>(out)[sig * out_stride + idx] = v.x * scale;
-    else static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
+    if (kRealOut) {
+      double* ya = static_cast<double*>(out) + 2 * sig * out_stride + idx;
+      ya[0] = v.x * scale;
+      if (2 * sig + 1 < n_real) ya[out_stride] = v.y * scale;
+    } else {
+      static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
+    }
   }
 }
 
@@ -426,19 +445,24 @@ __global__ void bluestein_post_kernel(const double2* __restrict__ c, int64_t M, 
   const int64_t sig = blockIdx.y;
   x[sig * x_stride + k] = cscale(cmul(c[sig * M + k], chirp(k, n, sgn)), scale);
 }
+// pair blockIdx.y = real signals (2y, 2y+1) <-> one complex signal
 __global__ void real_to_complex_kernel(const double* __restrict__ x, int64_t x_stride, double2* __restrict__ c,
-                                       int64_t n) {
+                                       int64_t n, int64_t n_real) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t sig = blockIdx.y;
-  c[sig * n + k] = make_double2(x[sig * x_stride + k], 0.0);
+  const double* xa = x + 2 * sig * x_stride + k;
+  c[sig * n + k] = make_double2(xa[0], 2 * sig + 1 < n_real ? xa[x_stride] : 0.0);
 }
 __global__ void complex_to_real_kernel(const double2* __restrict__ c, int64_t n, double* __restrict__ y,
-                                       int64_t y_stride) {
+                                       int64_t y_stride, int64_t n_real) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t sig = blockIdx.y;
-  y[sig * y_stride + k] = c[sig * n + k].x;
+  const double2 v = c[sig * n + k];
+  double* ya = y + 2 * sig * y_stride + k;
+  ya[0] = v.x;
+  if (2 * sig + 1 < n_real) ya[y_stride] = v.y;
 }
 
 // =============================== host side =============================================
@@ -636,7 +660,7 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   const int C1 = 1 << lc1, C2 = 1 << lc2;
   dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
   if ((e = set_smem(fft_cols_kernel<true, false, false>, smem1)) != cudaSuccess) goto done;
-  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0);
+  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) goto done;
   if ((e = set_smem(fft_rows_kernel<false>, smem2)) != cudaSuccess) goto done;
   fft_rows_kernel<false><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, data, n, stride, nullptr, sgn, scale);
@@ -693,12 +717,26 @@ extern "C" int wfm_fft_c2c(double* data, int64_t n_sig, int64_t n, int64_t strid
 
 namespace wfm {
 
-// Hp[k1*N2 + k2] = H[k1 + N1*k2]: the transposed spectrum order the row pass produces
+// Hermitian part of the response: Hs[k] = (H[k] + conj(H[(n-k) mod n])) / 2.  For real x,
+// real(ifft(fft(x) H)) = ifft(fft(x) Hs) exactly (the anti-Hermitian part of H only feeds the
+// imaginary part the reference drops with `.real`, distortion.py:210,220) — and with a
+// Hermitian response TWO real signals ride through one complex transform as z = x_a + i x_b.
+// H Hermitian already (reflection filters, real convolution kernels; all but the Nyquist bin):
+// the sum of two equal numbers halved is exact, Hs == H bit for bit.
+__device__ __forceinline__ double2 hermitian_part(const double2* __restrict__ H, int64_t k, int64_t n) {
+  const double2 p = H[k], q = H[k == 0 ? 0 : n - k];
+  return make_double2(0.5 * (p.x + q.x), 0.5 * (p.y - q.y));
+}
+__global__ void hermitian_part_kernel(const double2* __restrict__ H, double2* __restrict__ Hs, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) Hs[k] = hermitian_part(H, k, n);
+}
+// Hp[k1*N2 + k2] = Hs[k1 + N1*k2]: the transposed spectrum order the row pass produces
 __global__ void permute_h_kernel(const double2* __restrict__ H, double2* __restrict__ Hp, int N1, int N2) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N1 * N2) return;
   const int k1 = (int)(i / N2), k2 = (int)(i % N2);
-  Hp[i] = H[(int64_t)k1 + (int64_t)N1 * k2];
+  Hp[i] = hermitian_part(H, (int64_t)k1 + (int64_t)N1 * k2, (int64_t)N1 * N2);
 }
 
 // pinned staging for the caller's H (pageable host memory): the call returns without waiting
@@ -748,62 +786,72 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
   int rc = WFM_OK;
   int N1 = 0, N2 = 0;
   const bool smooth = is_smooth(n);
+  const int64_t n_pair = (n_sig + 1) / 2;  // two real signals per complex transform
+  const int T = 256;
+  const unsigned gH = (unsigned)((n + T - 1) / T);
   if (e != cudaSuccess) {
     // fall through to the common exit
   } else if (smooth && n <= kMaxPoints) {
     FftPlan P;
     size_t smem;
     e = get_plan((int)n, n, &P, &smem);
+    double2* dHs = nullptr;
     if (e == cudaSuccess) e = set_smem(fft_filter_single_kernel, smem);
+    if (e == cudaSuccess) e = cudaMallocAsync(&dHs, h_bytes, st);
     if (e == cudaSuccess) {
-      fft_filter_single_kernel<<<(unsigned)n_sig, kFftThreads, smem, st>>>(P, x, y, stride, dH);
+      hermitian_part_kernel<<<gH, T, 0, st>>>(dH, dHs, n);
+      fft_filter_single_kernel<<<(unsigned)n_pair, kFftThreads, smem, st>>>(P, x, y, stride, n_sig, dHs);
       e = cudaGetLastError();
     }
+    if (dHs) cudaFreeAsync(dHs, st);
   } else if (smooth && split_two_level(n, &N1, &N2)) {
     const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, 2);
     FftPlan P1, P2;
-    BigTwiddle T;
+    BigTwiddle BT;
     size_t smem1 = 0, smem2 = 0;
     double2 *scratch = nullptr, *dHp = nullptr;
     e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1);
     if (e == cudaSuccess) e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2);
-    if (e == cudaSuccess) e = get_big_twiddle(n, &T);
+    if (e == cudaSuccess) e = get_big_twiddle(n, &BT);
     if (e == cudaSuccess) e = cudaMallocAsync(&dHp, h_bytes, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_sig, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
     const int C1 = 1 << lc1, C2 = 1 << lc2;
-    dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
+    dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_pair), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_pair);
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
     if (e == cudaSuccess) {
-      permute_h_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dH, dHp, N1, N2);
-      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, x, scratch, stride, n, -1.0, 1.0);
+      permute_h_kernel<<<gH, T, 0, st>>>(dH, dHp, N1, N2);
+      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, stride, n, -1.0, 1.0,
+                                                                         n_sig);
       fft_rows_kernel<true><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, dHp, -1.0, 1.0);
-      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, scratch, y, n, stride, +1.0,
-                                                                          1.0 / (double)n);
+      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, stride, +1.0,
+                                                                          1.0 / (double)n, n_sig);
       e = cudaGetLastError();
     }
     if (scratch) cudaFreeAsync(scratch, st);
     if (dHp) cudaFreeAsync(dHp, st);
   } else {
     // generic: complex copy, forward, * H, inverse, real part
-    double2* c = nullptr;
-    e = cudaMallocAsync(&c, sizeof(double2) * (size_t)n * (size_t)n_sig, st);
-    const int T = 256;
-    dim3 gn((unsigned)((n + T - 1) / T), (unsigned)n_sig);
+    double2 *c = nullptr, *dHs = nullptr;
+    e = cudaMallocAsync(&c, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&dHs, h_bytes, st);
+    dim3 gn(gH, (unsigned)n_pair);
     if (e == cudaSuccess) {
-      real_to_complex_kernel<<<gn, T, 0, st>>>(x, stride, c, n);
-      e = c2c_any(c, n_sig, n, n, -1.0, 1.0, st);
+      hermitian_part_kernel<<<gH, T, 0, st>>>(dH, dHs, n);
+      real_to_complex_kernel<<<gn, T, 0, st>>>(x, stride, c, n, n_sig);
+      e = c2c_any(c, n_pair, n, n, -1.0, 1.0, st);
     }
     if (e == cudaSuccess) {
-      pointwise_mul_kernel<<<gn, T, 0, st>>>(c, dH, n, n);
-      e = c2c_any(c, n_sig, n, n, +1.0, 1.0 / (double)n, st);
+      pointwise_mul_kernel<<<gn, T, 0, st>>>(c, dHs, n, n);
+      e = c2c_any(c, n_pair, n, n, +1.0, 1.0 / (double)n, st);
     }
     if (e == cudaSuccess) {
-      complex_to_real_kernel<<<gn, T, 0, st>>>(c, n, y, stride);
+      complex_to_real_kernel<<<gn, T, 0, st>>>(c, n, y, stride, n_sig);
       e = cudaGetLastError();
     }
     if (c) cudaFreeAsync(c, st);
+    if (dHs) cudaFreeAsync(dHs, st);
     if (e == cudaErrorNotSupported) rc = WFM_EUNSUPPORTED;
   }
   cudaFreeAsync(dH, st);
