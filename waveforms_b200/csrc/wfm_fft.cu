@@ -172,11 +172,45 @@ __device__ __forceinline__ void dft_small<16>(double2 (&v)[16], double sgn) {
   dft_composite<4, 4>(v, sgn, cs, sn);
 }
 
-// one Stockham stage of radix R over C = 2^LOGC interleaved transforms (point p of
-// transform c lives at [p*C + c]); tw: the length-L table (shared or global memory)
+// ---- Stockham stages ------------------------------------------------------------------
+// C = 2^logc interleaved transforms live in shared memory, point p of transform c at
+// [p*C + c].  A stage reads its R inputs through `in(p, c)` and hands its R outputs to
+// `out(p, c, v)`: the middle stages use the shared-memory accessors below, the FIRST stage
+// of a transform reads global memory directly and the LAST one writes global memory (or
+// multiplies by the response on the way to shared memory), so loading, filtering and storing
+// cost no passes of their own over shared memory — the shared-memory data pipe is what
+// bounds these kernels (ncu: 75 % of its peak, profiles/r1o_k3_ncu_details.txt).
+struct SmemIn {
+  const double2* a;
+  int logc;
+  __device__ __forceinline__ double2 operator()(int p, int c) const { return a[(p << logc) + c]; }
+};
+struct SmemOut {
+  double2* b;
+  int logc;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const { b[(p << logc) + c] = v; }
+};
+
+// twiddles W^(k r), r = 1..R-1, of one butterfly: W^k, W^2k, W^4k (W^8k) come from the table,
+// the others are their products (one or two roundings more; keeps 3 of 7 table reads at R = 8)
 template <int R>
-__device__ __forceinline__ void stockham_stage(const double2* __restrict__ a, double2* __restrict__ b, int L, int logc,
-                                               int Ns, uint32_t inv_ns, const double2* __restrict__ tw, double sgn) {
+__device__ __forceinline__ void load_twiddles(double2 (&w)[R], const double2* __restrict__ tw, int t1, double sgn) {
+#pragma unroll
+  for (int r = 1; r < R; r <<= 1) {
+    w[r] = tw[t1 * r];
+    w[r].y *= -sgn;  // table holds exp(-i..): forward (sgn=-1) keeps it, inverse conjugates
+  }
+#pragma unroll
+  for (int r = 3; r < R; ++r) {
+    if ((r & (r - 1)) == 0) continue;
+    const int hi = r >= 8 ? 8 : (r >= 4 ? 4 : 2);
+    w[r] = cmul(w[hi], w[r - hi]);
+  }
+}
+
+template <int R, class In, class Out>
+__device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, int Ns, uint32_t inv_ns,
+                                               const double2* __restrict__ tw, double sgn) {
   const int nb = L / R;        // butterflies per transform
   const int tstep = nb / Ns;   // L / (Ns*R): table stride of this stage
   const int cmask = (1 << logc) - 1;
@@ -187,48 +221,73 @@ __device__ __forceinline__ void stockham_stage(const double2* __restrict__ a, do
     const int k = j - q * Ns;
     double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = a[((j + r * nb) << logc) + c];
+    for (int r = 0; r < R; ++r) v[r] = in(j + r * nb, c);
     if (k > 0) {
-      const int t1 = k * tstep;
+      double2 w[R];
+      load_twiddles<R>(w, tw, k * tstep, sgn);
 #pragma unroll
-      for (int r = 1; r < R; ++r) {
-        double2 w = tw[t1 * r];
-        w.y *= -sgn;  // table holds exp(-i..): forward (sgn=-1) keeps it, inverse conjugates
-        v[r] = cmul(v[r], w);
-      }
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
     }
     dft_small<R>(v, sgn);
     const int j0 = q * Ns * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) b[((j0 + r * Ns) << logc) + c] = v[r];
+    for (int r = 0; r < R; ++r) out(j0 + r * Ns, c, v[r]);
   }
 }
 
-// C = 2^logc interleaved transforms of length P.L in shared memory; returns the buffer
-// that holds the result.  All threads of the CTA must call it.
-__device__ double2* smem_fft(double2* a, double2* b, const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw) {
-  int Ns = 1;
-  for (int s = 0; s < P.n_stage; ++s) {
-    const int R = P.radix[s];
-    const uint32_t inv = P.inv_ns[s];
-    switch (R) {
-      case 2: stockham_stage<2>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
-      case 3: stockham_stage<3>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
-      case 4: stockham_stage<4>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
-      case 5: stockham_stage<5>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+template <class In, class Out>
+__device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc, int Ns, uint32_t inv,
+                                          const double2* __restrict__ tw, double sgn) {
+  switch (R) {
+    case 2: stockham_stage<2>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 3: stockham_stage<3>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 4: stockham_stage<4>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 5: stockham_stage<5>(in, out, L, logc, Ns, inv, tw, sgn); break;
 #if WFM_FFT_MAX_RADIX >= 8
-      case 8: stockham_stage<8>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+    case 8: stockham_stage<8>(in, out, L, logc, Ns, inv, tw, sgn); break;
 #endif
 #if WFM_FFT_MAX_RADIX >= 16
-      case 16: stockham_stage<16>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
+    case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, tw, sgn); break;
 #endif
-      default: stockham_stage<7>(a, b, P.L, logc, Ns, inv, tw, sgn); break;
-    }
-    __syncthreads();
-    double2* t = a; a = b; b = t;
-    Ns *= R;
+    default: stockham_stage<7>(in, out, L, logc, Ns, inv, tw, sgn); break;
   }
-  return a;
+}
+
+// One length-P.L transform of C = 2^logc interleaved signals.  Stage 0 reads through `in`
+// and writes buf0; stage s >= 1 reads buf[(s-1)&1] and writes buf[s&1]; the last stage
+// writes through `out` instead.  `in` may read buf1 (never buf0).  Ends with a block
+// barrier, so what `out` wrote to shared memory is visible.  All threads must call it.
+template <class In, class Out>
+__device__ __forceinline__ void smem_fft(const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw, In in,
+                                         Out out, double2* buf0, double2* buf1) {
+  const int S = P.n_stage;
+  if (S == 0) {  // L == 1: the transform is the identity
+    for (int c = threadIdx.x; c < (1 << logc); c += blockDim.x) out(0, c, in(0, c));
+    __syncthreads();
+    return;
+  }
+  if (S == 1) {
+    stage_any(P.radix[0], in, out, P.L, logc, 1, P.inv_ns[0], tw, sgn);
+    __syncthreads();
+    return;
+  }
+  stage_any(P.radix[0], in, SmemOut{buf0, logc}, P.L, logc, 1, P.inv_ns[0], tw, sgn);
+  __syncthreads();
+  int Ns = P.radix[0];
+  double2 *src = buf0, *dst = buf1;
+  for (int s = 1; s < S - 1; ++s) {
+    stage_any(P.radix[s], SmemIn{src, logc}, SmemOut{dst, logc}, P.L, logc, Ns, P.inv_ns[s], tw, sgn);
+    __syncthreads();
+    double2* t = src; src = dst; dst = t;
+    Ns *= P.radix[s];
+  }
+  stage_any(P.radix[S - 1], SmemIn{src, logc}, out, P.L, logc, Ns, P.inv_ns[S - 1], tw, sgn);
+  __syncthreads();
+}
+// the buffer the last stage of smem_fft(.., buf0, buf1) may write through `out` (the one it
+// does not read)
+__device__ __forceinline__ double2* last_stage_target(const FftPlan& P, double2* buf0, double2* buf1) {
+  return ((P.n_stage - 1) & 1) ? buf1 : buf0;
 }
 
 // the plan's twiddle table: staged behind the two ping-pong buffers when it fits
@@ -257,6 +316,25 @@ extern __shared__ __align__(16) unsigned char fft_smem_raw[];
 // One CTA per PAIR of real signals: z = x_a + i x_b goes through one complex transform.  H is
 // the Hermitian part of the caller's response (hermitian_part_kernel), so ifft(fft(z) H) =
 // y_a + i y_b with both real.
+struct PairIn {  // two real signals -> one complex
+  const double* xa;
+  const double* xb;  // nullptr: odd tail
+  __device__ __forceinline__ double2 operator()(int p, int) const { return make_double2(xa[p], xb ? xb[p] : 0.0); }
+};
+struct PairOut {
+  double* ya;
+  double* yb;
+  double scale;
+  __device__ __forceinline__ void operator()(int p, int, double2 v) const {
+    ya[p] = v.x * scale;
+    if (yb) yb[p] = v.y * scale;
+  }
+};
+struct MulHOut {  // spectrum x response on the way to shared memory
+  double2* z;
+  const double2* __restrict__ H;
+  __device__ __forceinline__ void operator()(int p, int, double2 v) const { z[p] = cmul(v, __ldg(H + p)); }
+};
 __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan P, const double* __restrict__ x,
                                                                         double* __restrict__ y, int64_t stride,
                                                                         int64_t n_sig, const double2* __restrict__ H) {
@@ -266,20 +344,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
   const int64_t s0 = 2 * (int64_t)blockIdx.x;
   const bool two = s0 + 1 < n_sig;
   const double* xs = x + s0 * stride;
-  const double* xs2 = xs + (two ? stride : 0);
   double* ys = y + s0 * stride;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = make_double2(xs[p], two ? xs2[p] : 0.0);
-  __syncthreads();
-  double2* f = smem_fft(a, b, P, 0, -1.0, tw);
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) f[p] = cmul(f[p], __ldg(H + p));
-  __syncthreads();
-  double2* g = smem_fft(f, f == a ? b : a, P, 0, +1.0, tw);
-  const double inv = 1.0 / (double)P.L;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) {
-    const double2 v = g[p];
-    ys[p] = v.x * inv;
-    if (two) ys[stride + p] = v.y * inv;
-  }
+  double2* z = last_stage_target(P, a, b);
+  smem_fft(P, 0, -1.0, tw, PairIn{xs, two ? xs + stride : nullptr}, MulHOut{z, H}, a, b);
+  smem_fft(P, 0, +1.0, tw, SmemIn{z, 0}, PairOut{ys, two ? ys + stride : nullptr, 1.0 / (double)P.L}, z == a ? b : a, z);
 }
 
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
@@ -295,13 +363,55 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
 #ifndef WFM_FFT_COLS_LOGC
 #define WFM_FFT_COLS_LOGC 2
 #endif
+// kRealIn / kRealOut: the signal index is a PAIR of real signals packed as the real and
+// imaginary part of one complex signal (the filter's response is Hermitian); pb == nullptr
+// for the odd tail
+template <bool kTwBefore, bool kRealIn>
+struct ColsIn {
+  const void* pa;
+  const void* pb;
+  BigTwiddle T;
+  int N2, c0, cw;
+  double sgn;
+  __device__ __forceinline__ double2 operator()(int r, int c) const {
+    double2 v = make_double2(0.0, 0.0);
+    if (c < cw) {
+      const int64_t idx = (int64_t)r * N2 + c0 + c;
+      if (kRealIn) {
+        v.x = static_cast<const double*>(pa)[idx];
+        if (pb) v.y = static_cast<const double*>(pb)[idx];
+      } else {
+        v = static_cast<const double2*>(pa)[idx];
+      }
+      if (kTwBefore) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
+    }
+    return v;
+  }
+};
+template <bool kTwAfter, bool kRealOut>
+struct ColsOut {
+  void* pa;
+  void* pb;
+  BigTwiddle T;
+  int N2, c0, cw;
+  double sgn, scale;
+  __device__ __forceinline__ void operator()(int r, int c, double2 v) const {
+    if (c >= cw) return;
+    const int64_t idx = (int64_t)r * N2 + c0 + c;
+    if (kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
+    if (kRealOut) {
+      static_cast<double*>(pa)[idx] = v.x * scale;
+      if (pb) static_cast<double*>(pb)[idx] = v.y * scale;
+    } else {
+      static_cast<double2*>(pa)[idx] = cscale(v, scale);
+    }
+  }
+};
 template <bool kTwAfter, bool kRealIn, bool kRealOut>
 __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
                                                                const void* __restrict__ in, void* __restrict__ out,
                                                                int64_t in_stride, int64_t out_stride, double sgn,
                                                                double scale, int64_t n_real) {
-  // kRealIn / kRealOut: blockIdx.y is a PAIR of real signals (2y, 2y+1 < n_real) packed as the
-  // real and imaginary part of one complex signal (the filter's response is Hermitian)
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + ((size_t)N1 << logc);
@@ -309,39 +419,26 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
   const int c0 = blockIdx.x << logc;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
-  const int total = N1 << logc;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int c = e & (C - 1), r = e >> logc;
-    double2 v = make_double2(0.0, 0.0);
-    if (c < cw) {
-      const int64_t idx = (int64_t)r * N2 + c0 + c;
-      if (kRealIn) {
-        const double* xa = static_cast<const double*>(in) + 2 * sig * in_stride + idx;
-        v.x = xa[0];
-        if (2 * sig + 1 < n_real) v.y = xa[in_stride];
-      } else {
-        v = static_cast<const double2*>(in)[sig * in_stride + idx];
-      }
-      if (!kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
-    }
-    a[e] = v;
+  const bool two = 2 * sig + 1 < n_real;
+  ColsIn<!kTwAfter, kRealIn> src;
+  if (kRealIn) {
+    src.pa = static_cast<const double*>(in) + 2 * sig * in_stride;
+    src.pb = two ? static_cast<const double*>(in) + (2 * sig + 1) * in_stride : nullptr;
+  } else {
+    src.pa = static_cast<const double2*>(in) + sig * in_stride;
+    src.pb = nullptr;
   }
-  __syncthreads();
-  double2* f = smem_fft(a, b, P, logc, sgn, tw);
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int c = e & (C - 1), r = e >> logc;
-    if (c >= cw) continue;
-    const int64_t idx = (int64_t)r * N2 + c0 + c;
-    double2 v = f[e];
-    if (kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
-    if (kRealOut) {
-      double* ya = static_cast<double*>(out) + 2 * sig * out_stride + idx;
-      ya[0] = v.x * scale;
-      if (2 * sig + 1 < n_real) ya[out_stride] = v.y * scale;
-    } else {
-      static_cast<double2*>(out)[sig * out_stride + idx] = cscale(v, scale);
-    }
+  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn;
+  ColsOut<kTwAfter, kRealOut> dst;
+  if (kRealOut) {
+    dst.pa = static_cast<double*>(out) + 2 * sig * out_stride;
+    dst.pb = two ? static_cast<double*>(out) + (2 * sig + 1) * out_stride : nullptr;
+  } else {
+    dst.pa = static_cast<double2*>(out) + sig * out_stride;
+    dst.pb = nullptr;
   }
+  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale;
+  smem_fft(P, logc, sgn, tw, src, dst, a, b);
 }
 
 // ---- four-step, kernel B: row transforms of length N2 on scratch[k1][*] --------------
@@ -351,6 +448,37 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
 #ifndef WFM_FFT_ROWS_MINB
 #define WFM_FFT_ROWS_MINB 2
 #endif
+struct RowsIn {
+  const double2* rows;  // first row of the tile
+  int N2, rw;
+  __device__ __forceinline__ double2 operator()(int p, int c) const {
+    return c < rw ? rows[(int64_t)c * N2 + p] : make_double2(0.0, 0.0);
+  }
+};
+struct RowsOut {
+  double2* rows;
+  int N2, rw;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const {
+    if (c < rw) rows[(int64_t)c * N2 + p] = v;
+  }
+};
+struct RowsMulHOut {
+  double2* z;
+  const double2* __restrict__ hrows;  // Hp at the tile's first row
+  int N2, rw, logc;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const {
+    if (c < rw) v = cmul(v, __ldg(hrows + (int64_t)c * N2 + p));
+    z[(p << logc) + c] = v;
+  }
+};
+struct NaturalOut {  // X[k1 + N1*k2]: for fixed k2 the C rows of the tile are adjacent
+  double2* o;
+  int N1, rw;
+  double scale;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const {
+    if (c < rw) o[(int64_t)c + (int64_t)N1 * p] = cscale(v, scale);
+  }
+};
 template <bool kFilter>
 __global__ void __launch_bounds__(kFftThreads, WFM_FFT_ROWS_MINB) fft_rows_kernel(FftPlan P, int N1, int logc, double2* __restrict__ data,
                                                                double2* __restrict__ out, int64_t stride,
@@ -363,47 +491,33 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_ROWS_MINB) fft_rows_kerne
   const int r0 = blockIdx.x << logc;
   const int rw = min(C, N1 - r0);
   const int64_t sig = blockIdx.y;
-  double2* base = data + sig * stride;
-  // rows are contiguous in memory: row by row for coalescing
-  for (int c = 0; c < C; ++c) {
-    const double2* __restrict__ row = base + (int64_t)(r0 + c) * N2;
-    for (int p = threadIdx.x; p < N2; p += blockDim.x) a[(p << logc) + c] = (c < rw) ? row[p] : make_double2(0.0, 0.0);
-  }
-  __syncthreads();
-  double2* f = smem_fft(a, b, P, logc, kFilter ? -1.0 : sgn, tw);
+  double2* rows = data + sig * stride + (int64_t)r0 * N2;
   if (kFilter) {
-    for (int c = 0; c < rw; ++c) {
-      const double2* __restrict__ hrow = Hp + (int64_t)(r0 + c) * N2;
-      for (int p = threadIdx.x; p < N2; p += blockDim.x) f[(p << logc) + c] = cmul(f[(p << logc) + c], __ldg(hrow + p));
-    }
-    __syncthreads();
-    double2* g = smem_fft(f, f == a ? b : a, P, logc, +1.0, tw);
-    for (int c = 0; c < rw; ++c) {
-      double2* __restrict__ row = base + (int64_t)(r0 + c) * N2;
-      for (int p = threadIdx.x; p < N2; p += blockDim.x) row[p] = g[(p << logc) + c];
-    }
+    double2* z = last_stage_target(P, a, b);
+    smem_fft(P, logc, -1.0, tw, RowsIn{rows, N2, rw}, RowsMulHOut{z, Hp + (int64_t)r0 * N2, N2, rw, logc}, a, b);
+    smem_fft(P, logc, +1.0, tw, SmemIn{z, logc}, RowsOut{rows, N2, rw}, z == a ? b : a, z);
   } else {
-    double2* o = out + sig * out_stride;
-    // natural order: X[k1 + N1*k2]; for fixed k2 the C rows are adjacent
-    const int total = N2 << logc;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      const int c = e & (C - 1), p = e >> logc;
-      if (c < rw) o[(int64_t)(r0 + c) + (int64_t)N1 * p] = cscale(f[e], scale);
-    }
+    smem_fft(P, logc, sgn, tw, RowsIn{rows, N2, rw}, NaturalOut{out + sig * out_stride + r0, N1, rw, scale}, a, b);
   }
 }
 
 // ---- one-level plain c2c ------------------------------------------------------------
+struct PlainIn {
+  const double2* d;
+  __device__ __forceinline__ double2 operator()(int p, int) const { return d[p]; }
+};
+struct PlainOut {
+  double2* d;
+  double scale;
+  __device__ __forceinline__ void operator()(int p, int, double2 v) const { d[p] = cscale(v, scale); }
+};
 __global__ void __launch_bounds__(kFftThreads) fft_c2c_single_kernel(FftPlan P, double2* __restrict__ data,
                                                                      int64_t stride, double sgn, double scale) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + P.L;
   const double2* tw = stage_twiddles(P, b + P.L);
   double2* d = data + (int64_t)blockIdx.x * stride;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) a[p] = d[p];
-  __syncthreads();
-  double2* f = smem_fft(a, b, P, 0, sgn, tw);
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) d[p] = cscale(f[p], scale);
+  smem_fft(P, 0, sgn, tw, PlainIn{d}, PlainOut{d, scale}, a, b);
 }
 
 // ---- Bluestein helpers ----------------------------------------------------------------
