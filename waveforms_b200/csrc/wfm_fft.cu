@@ -42,7 +42,13 @@ namespace wfm {
 #ifndef WFM_FFT_MAX_RADIX
 #define WFM_FFT_MAX_RADIX 8  // largest power-of-two butterfly: 4, 8 or 16 (measured on cfg4: 6.11 / 5.90 / 6.30 ms)
 #endif
-constexpr int kFftThreads = 512;
+#ifndef WFM_FFT_BIG_RADIX
+#define WFM_FFT_BIG_RADIX 1  // composite butterflies held in registers: 1 = 10 (2x5), 2 = also 25 (5x5)
+#endif
+#ifndef WFM_FFT_THREADS
+#define WFM_FFT_THREADS 512
+#endif
+constexpr int kFftThreads = WFM_FFT_THREADS;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
 constexpr int kSmemBudget = 227 * 1024 - 1024;
@@ -172,6 +178,21 @@ __device__ __forceinline__ void dft_small<16>(double2 (&v)[16], double sgn) {
   dft_composite<4, 4>(v, sgn, cs, sn);
 }
 
+#if WFM_FFT_BIG_RADIX
+template <>
+__device__ __forceinline__ void dft_small<10>(double2 (&v)[10], double sgn) {
+  constexpr double cs[10] = {1.0, 0.8090169943749475, 0.30901699437494745, -0.30901699437494734, -0.8090169943749473, -1.0, -0.8090169943749476, -0.30901699437494756, 0.30901699437494723, 0.8090169943749473};
+  constexpr double sn[10] = {0.0, 0.5877852522924731, 0.9510565162951535, 0.9510565162951536, 0.5877852522924732, 1.2246467991473532e-16, -0.587785252292473, -0.9510565162951535, -0.9510565162951536, -0.5877852522924734};
+  dft_composite<2, 5>(v, sgn, cs, sn);
+}
+template <>
+__device__ __forceinline__ void dft_small<25>(double2 (&v)[25], double sgn) {
+  constexpr double cs[25] = {1.0, 0.9685831611286311, 0.8763066800438636, 0.7289686274214116, 0.5358267949789965, 0.30901699437494745, 0.06279051952931353, -0.1873813145857246, -0.4257792915650727, -0.6374239897486897, -0.8090169943749473, -0.9297764858882513, -0.9921147013144778, -0.9921147013144779, -0.9297764858882515, -0.8090169943749478, -0.6374239897486895, -0.42577929156507216, -0.18738131458572463, 0.06279051952931283, 0.30901699437494723, 0.5358267949789968, 0.7289686274214112, 0.8763066800438631, 0.968583161128631};
+  constexpr double sn[25] = {0.0, 0.2486898871648548, 0.4817536741017153, 0.6845471059286886, 0.8443279255020151, 0.9510565162951535, 0.9980267284282716, 0.9822872507286887, 0.9048270524660195, 0.7705132427757893, 0.5877852522924732, 0.36812455268467814, 0.12533323356430454, -0.12533323356430429, -0.3681245526846779, -0.5877852522924727, -0.7705132427757894, -0.9048270524660198, -0.9822872507286887, -0.9980267284282716, -0.9510565162951536, -0.844327925502015, -0.684547105928689, -0.4817536741017161, -0.24868988716485535};
+  dft_composite<5, 5>(v, sgn, cs, sn);
+}
+#endif
+
 // ---- Stockham stages ------------------------------------------------------------------
 // C = 2^logc interleaved transforms live in shared memory, point p of transform c at
 // [p*C + c].  A stage reads its R inputs through `in(p, c)` and hands its R outputs to
@@ -203,7 +224,7 @@ __device__ __forceinline__ void load_twiddles(double2 (&w)[R], const double2* __
 #pragma unroll
   for (int r = 3; r < R; ++r) {
     if ((r & (r - 1)) == 0) continue;
-    const int hi = r >= 8 ? 8 : (r >= 4 ? 4 : 2);
+    const int hi = r >= 16 ? 16 : (r >= 8 ? 8 : (r >= 4 ? 4 : 2));
     w[r] = cmul(w[hi], w[r - hi]);
   }
 }
@@ -248,6 +269,12 @@ __device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc
 #endif
 #if WFM_FFT_MAX_RADIX >= 16
     case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, tw, sgn); break;
+#endif
+#if WFM_FFT_BIG_RADIX
+    case 10: stockham_stage<10>(in, out, L, logc, Ns, inv, tw, sgn); break;
+#endif
+#if WFM_FFT_BIG_RADIX >= 2
+    case 25: stockham_stage<25>(in, out, L, logc, Ns, inv, tw, sgn); break;
 #endif
     default: stockham_stage<7>(in, out, L, logc, Ns, inv, tw, sgn); break;
   }
@@ -448,6 +475,9 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
 #ifndef WFM_FFT_ROWS_MINB
 #define WFM_FFT_ROWS_MINB 2
 #endif
+#ifndef WFM_FFT_ROWS_LOGC
+#define WFM_FFT_ROWS_LOGC 2
+#endif
 struct RowsIn {
   const double2* rows;  // first row of the tile
   int N2, rw;
@@ -582,6 +612,25 @@ __global__ void complex_to_real_kernel(const double2* __restrict__ c, int64_t n,
 // =============================== host side =============================================
 static bool factor_smooth(int64_t n, int* radix, int* n_stage) {
   int k = 0;
+#if WFM_FFT_BIG_RADIX >= 2
+  while (n % 25 == 0) {
+    if (k >= kMaxStages) return false;
+    radix[k++] = 25;
+    n /= 25;
+  }
+#endif
+#if WFM_FFT_BIG_RADIX
+  if (n % 10 == 0) {  // a 5 takes the lone 2 the larger power-of-two butterflies would leave over
+    int e = 0;
+    for (int64_t m = n; m % 2 == 0; m /= 2) ++e;
+    const int per = WFM_FFT_MAX_RADIX >= 16 ? 4 : (WFM_FFT_MAX_RADIX >= 8 ? 3 : 2);
+    if (e % per == 1) {
+      if (k >= kMaxStages) return false;
+      radix[k++] = 10;
+      n /= 10;
+    }
+  }
+#endif
   for (int r : {7, 5, 3}) {
     while (n % r == 0) {
       if (k >= kMaxStages) return false;
@@ -761,7 +810,7 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   }
   int N1, N2;
   if (!split_two_level(n, &N1, &N2)) return cudaErrorNotSupported;
-  const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, 2);
+  const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, WFM_FFT_ROWS_LOGC);
   FftPlan P1, P2;
   BigTwiddle T;
   size_t smem1, smem2;
@@ -919,7 +968,7 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
     }
     if (dHs) cudaFreeAsync(dHs, st);
   } else if (smooth && split_two_level(n, &N1, &N2)) {
-    const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, 2);
+    const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, WFM_FFT_ROWS_LOGC);
     FftPlan P1, P2;
     BigTwiddle BT;
     size_t smem1 = 0, smem2 = 0;
