@@ -1,0 +1,138 @@
+"""Vectorised pulse-train builder: the tables it produces from parameter
+arrays are the tables ``lower()`` produces from the objects the drop-in API builds pulse
+by pulse (reference construction: waveform.py:1190-1201 cosPulse, :1123-1150 gaussian,
+:1110-1120 square, :1487-1527 mixing, :508-511 ``>>``) — compared field by field, bit for
+bit; the GPU test then compares the sampled arrays."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import b200_namespace
+from waveforms_b200.batch import channel_grid
+from waveforms_b200.builder import PulseTemplate, UntraceablePulse, pulse_train_batch
+from waveforms_b200.lowering import lower
+
+COS_ROT = 34
+
+
+@pytest.fixture(scope='module')
+def ns():
+    return b200_namespace()
+
+
+def assert_same_tables(got, want):
+    for k in ('waves', 'seg_bound', 'seg_ptr', 'terms', 'refs'):
+        assert np.array_equal(getattr(got, k), getattr(want, k)), k
+    for f in ('func', 'shift', 'a0', 'a1'):
+        assert np.array_equal(got.facs[f], want.facs[f]), f
+    # the argument pool is shared / ordered differently; what every row points at is the same
+    for i in np.nonzero(got.facs['func'] == COS_ROT)[0]:
+        a, b = int(got.facs['arg_off'][i]), int(want.facs['arg_off'][i])
+        assert np.array_equal(got.args[a:a + 5], want.args[b:b + 5])
+    plain = np.nonzero((got.facs['func'] != COS_ROT) & (want.facs['arg_off'] != 0))[0]
+    for i in plain:
+        a, b = int(got.facs['arg_off'][i]), int(want.facs['arg_off'][i])
+        n = min(len(got.args) - a, len(want.args) - b, 4)
+        assert np.array_equal(got.args[a:a + n], want.args[b:b + n])
+    assert got.total_samples == want.total_samples and got.any_complex == want.any_complex
+
+
+def object_batch(ns, fns, idx, t0, start, stop, rate):
+    chans = []
+    for row_i, row_t in zip(idx, t0):
+        w = ns.WaveVStack([fns[int(i)](float(t)) for i, t in zip(row_i, row_t)])
+        w.start, w.stop, w.sample_rate = start, stop, rate
+        chans.append(w)
+    return chans, lower([channel_grid(w) for w in chans])
+
+
+def drag_fns(ns, which):
+    fns = []
+    for amp in (0.5, 1.0):
+        for phase in (0, np.pi / 2, np.pi, 3 * np.pi / 2):
+            fns.append(lambda t0, amp=amp, phase=phase: ns.mixing(
+                amp * ns.cosPulse(20e-9) >> t0, freq=-60e6, phase=phase, DRAGScaling=4e-10)[which])
+    return fns
+
+
+@pytest.mark.parametrize('which', [0, 1])
+def test_rb_batch_back_to_back(ns, which):
+    """cfg3's construction: back-to-back DRAG cosPulses; shared edges appear once."""
+    fns = drag_fns(ns, which)
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(3 + which)
+    depth, n_ch = 200, 4
+    idx = rng.integers(0, len(fns), (n_ch, depth))
+    t0 = np.tile(100e-9 + 20e-9 * np.arange(depth) + 10e-9, (n_ch, 1))
+    stop = 100e-9 + 20e-9 * depth + 900e-9
+    got = pulse_train_batch(templates, idx, t0, 0, stop, 2e9)
+    _, want = object_batch(ns, fns, idx, t0, 0, stop, 2e9)
+    assert_same_tables(got, want)
+    assert len(got.seg_bound) < n_ch * (2 * depth + 1)  # the shared edges were merged
+
+
+def test_mixed_shapes_with_gaps_and_ragged_channels(ns):
+    """cfg2's XY construction (alternating cosPulse / gaussian DRAG pulses at random offsets)
+    plus erf-edged squares (several segments per pulse), channels of different lengths."""
+    fns = [
+        lambda t0: ns.mixing(0.7 * ns.cosPulse(20e-9) >> t0, freq=123e6, phase=0.3, DRAGScaling=5e-10)[0],
+        lambda t0: ns.mixing(0.4 * ns.gaussian(20e-9) >> t0, freq=-77e6, phase=2.1, DRAGScaling=3e-10)[0],
+        lambda t0: -0.25 * ns.square(60e-9, edge=2e-9) >> t0,
+        lambda t0: 0.3 * ns.gaussian(30e-9, plateau=20e-9) >> t0,
+        lambda t0: (0.5 + 0.25j) * ns.cosPulse(16e-9) >> t0,
+    ]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(11)
+    idx, t0 = [], []
+    for n in (37, 1, 0, 12):
+        idx.append(rng.integers(0, len(fns), n))
+        t0.append(200e-9 + 400e-9 * np.arange(n) + rng.uniform(0, 100e-9, n))
+    got = pulse_train_batch(templates, idx, t0, 0, 20e-6, 2e9)
+    _, want = object_batch(ns, fns, idx, t0, 0, 20e-6, 2e9)
+    assert_same_tables(got, want)
+    assert got.any_complex
+
+
+def test_untraceable_dependence_is_refused(ns):
+    # arithmetic the tracer does not record raises at once ...
+    with pytest.raises(UntraceablePulse):
+        PulseTemplate.trace(lambda t0: (t0 * 1e6) * ns.cosPulse(20e-9) >> t0)
+    # ... and a dependence hidden behind float() is caught by the check at a second start time
+    with pytest.raises(UntraceablePulse):
+        PulseTemplate.trace(lambda t0: ns.mixing(ns.cosPulse(20e-9) >> t0, freq=50e6, phase=float(t0) * 1e6)[0])
+    with pytest.raises(UntraceablePulse):
+        PulseTemplate.trace(lambda t0: ns.cos(2 * math.pi * 50e6))  # never returns to zero
+
+
+def test_overlap_is_refused(ns):
+    tp = PulseTemplate.trace(lambda t0: ns.cosPulse(20e-9) >> t0)
+    with pytest.raises(ValueError, match='overlapping'):
+        pulse_train_batch([tp], [[0, 0]], [[100e-9, 110e-9]], 0, 1e-6, 2e9)
+    pulse_train_batch([tp], [[0, 0]], [[100e-9, 120e-9]], 0, 1e-6, 2e9)  # touching is fine
+
+
+@pytest.mark.gpu
+def test_builder_samples_equal_object_api(ns):
+    """The GPU output of a builder batch is bit-identical to sampling the object-built stacks."""
+    from waveforms_b200 import engine
+    fns = drag_fns(ns, 0) + [lambda t0: -0.25 * ns.square(60e-9, edge=2e-9) >> t0]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(21)
+    idx = [rng.integers(0, 8, 150), rng.integers(0, 9, 40), rng.integers(0, 8, 150)]
+    t0 = [110e-9 + 20e-9 * np.arange(150), 300e-9 + 70e-9 * np.arange(40), 110e-9 + 20e-9 * np.arange(150)]
+    got = pulse_train_batch(templates, idx, t0, 0, 4e-6, 2e9)
+    chans, want = object_batch(ns, fns, idx, t0, 0, 4e-6, 2e9)
+    outs = []
+    for batch in (got, want):
+        prog = engine.Program(batch, 0)
+        outs.append(prog.sample_device(dtype=engine.WFM_F64).cpu().numpy())
+        prog.close()
+    assert np.array_equal(outs[0], outs[1])
+    n = int(got.waves['n'][0])
+    assert np.array_equal(outs[0][:n], chans[0].sample())
+    # the public entry point: parameter arrays in, device-resident channels out
+    from waveforms_b200.batch import sample_pulse_trains
+    res = sample_pulse_trains(templates, idx, t0, 0, 4e-6, 2e9)
+    for c, w in enumerate(chans):
+        assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())

@@ -48,10 +48,42 @@ def build(cfg, ns):
     return chans, base, replicate(base, copies, amp_scale=scale), scale
 
 
+def build_cfg3_vectorised(ns, n_ch, depth=1000):
+    """cfg3 with EVERY channel distinct (no replication), built from parameter arrays by
+    waveforms_b200.builder: channel ch -> outputs 2*ch (I) and 2*ch+1 (Q), the same random
+    Clifford-like sequence on both.  Returns (LoweredBatch, host seconds, spot-check closure)."""
+    import time
+    from waveforms_b200.builder import PulseTemplate, pulse_train_batch
+    amps, phases = (0.5, 1.0), (0, np.pi / 2, np.pi, 3 * np.pi / 2)
+
+    def fn(f8, a, p, which):
+        return lambda t0: ns.mixing(amps[a] * ns.cosPulse(20e-9) >> t0, freq=-20e6 * (1 + f8), phase=phases[p],
+                                    DRAGScaling=4e-10)[which]
+    t_begin = time.perf_counter()
+    fns = [fn(f8, a, p, which) for which in (0, 1) for f8 in range(8) for a in range(2) for p in range(4)]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(20260003)
+    gate = rng.integers(0, 8, (n_ch, depth))                       # (amp, phase) of every pulse
+    per_ch = (np.arange(n_ch) % 8)[:, None] * 8 + gate            # + the channel's carrier
+    idx = np.stack([per_ch, 64 + per_ch], axis=1).reshape(2 * n_ch, depth)
+    t0 = np.tile(100e-9 + 20e-9 * np.arange(depth) + 10e-9, (2 * n_ch, 1))
+    stop = 100e-9 + 20e-9 * depth + 900e-9
+    batch = pulse_train_batch(templates, idx, t0, 0, stop, 2e9)
+    host_s = time.perf_counter() - t_begin
+
+    def object_channel(row):
+        w = ns.WaveVStack([fns[int(i)](float(t)) for i, t in zip(idx[row], t0[row])])
+        w.start, w.stop, w.sample_rate = 0, stop, 2e9
+        return w
+    return batch, host_s, object_channel
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--only', default='cfg3,cfg4,cfg5')
+    ap.add_argument('--cfg3v-channels', type=int, default=512,
+                    help="channels of the builder-made cfg3 batch ('cfg3v' in --only); 512 = one GPU's share of 4096 on 8 GPUs")
     args = ap.parse_args()
     import torch
     import bench
@@ -62,6 +94,34 @@ def main():
     peak = bench.measured_peak()[0]
     res = {}
     for cfg in args.only.split(','):
+        if cfg == 'cfg3v':
+            import time
+            batch, host_s, object_channel = build_cfg3_vectorised(ns, args.cfg3v_channels)
+            t0 = time.perf_counter()
+            prog = engine.Program(batch, 0)
+            out = prog.sample_device(dtype=engine.WFM_F64)
+            torch.cuda.synchronize()
+            create_s = time.perf_counter() - t0
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.reps + 1)]
+            ev[0].record()
+            for k in range(args.reps):
+                prog.sample_device(dtype=engine.WFM_F64, out=out)
+                ev[k + 1].record()
+            torch.cuda.synchronize()
+            ms = min(ev[k].elapsed_time(ev[k + 1]) for k in range(args.reps))
+            n = int(batch.waves['n'].sum())
+            ok = True
+            for row in (1, len(batch.waves) - 2):  # one Q and one I output against the object API, bit for bit
+                off, cnt = int(batch.waves['out_off'][row]), int(batch.waves['n'][row])
+                ok = ok and bool(np.array_equal(out[off:off + cnt].cpu().numpy(), object_channel(row).sample()))
+            res[cfg] = {'channels': len(batch.waves), 'pulses': int(len(batch.waves)) * 1000, 'samples': n,
+                        'host_build_s': host_s, 'ir_GB': batch.nbytes() / 1e9, 'create_and_first_sample_s': create_s,
+                        'ms': ms, 'GSa/s': n / ms / 1e6, 'roofline_frac': n * 8 / ms / 1e6 / peak,
+                        'equals_object_api_bit_exact': ok, 'layout': prog.info()}
+            prog.close()
+            del out
+            torch.cuda.empty_cache()
+            continue
         chans, base, batch, scale = build(cfg, ns)
         prog = engine.Program(batch, 0)
         out = torch.empty(batch.total_samples, dtype=torch.float64, device='cuda')

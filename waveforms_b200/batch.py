@@ -98,6 +98,37 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     return BatchResult(tensors, table, dtype)
 
 
+def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
+                        dtype=np.float64, devices=None):
+    """Channels given as PARAMETER ARRAYS instead of objects: channel ``c`` is the
+    stack of pulses ``templates[tmpl_idx[c][k]]`` started at ``t0[c][k]``
+    (``builder.PulseTemplate.trace`` / ``builder.pulse_train_batch``), sampled on
+    ``np.arange(start, stop, 1/sample_rate)``.  Same sharding and result type as
+    ``sample_batch``; the tables are those the object API would have produced."""
+    import torch
+    from .builder import pulse_train_batch
+    engine.require_gpu()
+    if devices is None:
+        devices = [torch.cuda.current_device()]
+    code = {np.dtype(np.float64): engine.WFM_F64,
+            np.dtype(np.float32): engine.WFM_F32,
+            np.dtype(np.complex128): engine.WFM_C128}[np.dtype(dtype)]
+    ranges = shard_ranges([max(len(r), 1) for r in t0], len(devices))
+    tensors, table = [], []
+    for slot, (dev, (lo, hi)) in enumerate(zip(devices, ranges)):
+        batch = pulse_train_batch(templates, tmpl_idx[lo:hi], t0[lo:hi], start, stop,
+                                  sample_rate)
+        with torch.cuda.device(dev):
+            prog = engine.Program(batch, dev)
+            out = prog.sample_device(dtype=code)
+            prog.close()
+        tensors.append(out)
+        for k in range(hi - lo):
+            table.append((slot, int(batch.waves['out_off'][k]),
+                          int(batch.waves['n'][k])))
+    return BatchResult(tensors, table, dtype)
+
+
 def rank_shard(weights, rank=None, world=None):
     """The contiguous channel range ``(lo, hi)`` this process owns when the job
     runs as one process per GPU (torchrun): RANK / WORLD_SIZE from the
