@@ -43,8 +43,17 @@
 
 namespace wfm {
 
-constexpr int kIirThreads = 256;
-constexpr int kIirT = 16;                          // samples per thread per tile
+#ifndef WFM_IIR_THREADS
+#define WFM_IIR_THREADS 256
+#endif
+#ifndef WFM_IIR_T
+#define WFM_IIR_T 16
+#endif
+#ifndef WFM_IIR_MINB
+#define WFM_IIR_MINB 2
+#endif
+constexpr int kIirThreads = WFM_IIR_THREADS;
+constexpr int kIirT = WFM_IIR_T;                   // samples per thread per tile
 constexpr int kIirTile = kIirThreads * kIirT;      // 4096
 constexpr int kIirRow = kIirT + 1;                 // padded smem row (bank spread)
 constexpr int kMaxSections = 8;
@@ -161,7 +170,7 @@ __device__ __forceinline__ void matvec(const double* __restrict__ M, double a, d
   rb = fma(M[2], a, M[3] * b);
 }
 
-__global__ void __launch_bounds__(kIirThreads, 2) sosfilt_scan_kernel(const __grid_constant__ IirParams P,
+__global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_kernel(const __grid_constant__ IirParams P,
                                                                         const __grid_constant__ IirScanTables TT,
                                                                         const double* __restrict__ x, double* y,
                                                                      int64_t n, int64_t stride,
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kIirThreads, 2) sosfilt_scan_kernel(const __gr
                                                                      double* __restrict__ zf) {
   const IirScanTables* __restrict__ T = &TT;  // ~10 KB of kernel parameters (constant bank): no table upload per call
   __shared__ double s_tile[kIirThreads * kIirRow];
-  __shared__ double s_tot[8][2];
+  __shared__ double s_tot[kIirThreads / 32][2];
   __shared__ double s_carry[kMaxSections][2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t sig = blockIdx.x;
