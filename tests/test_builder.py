@@ -38,10 +38,12 @@ def assert_same_tables(got, want):
     assert got.total_samples == want.total_samples and got.any_complex == want.any_complex
 
 
-def object_batch(ns, fns, idx, t0, start, stop, rate):
+def object_batch(ns, fns, idx, t0, start, stop, rate, params=None):
     chans = []
-    for row_i, row_t in zip(idx, t0):
-        w = ns.WaveVStack([fns[int(i)](float(t)) for i, t in zip(row_i, row_t)])
+    names = list(params or {})
+    for c, (row_i, row_t) in enumerate(zip(idx, t0)):
+        extra = [[float(v) for v in params[n][c]] for n in names]
+        w = ns.WaveVStack([fns[int(i)](float(t), *[e[k] for e in extra]) for k, (i, t) in enumerate(zip(row_i, row_t))])
         w.start, w.stop, w.sample_rate = start, stop, rate
         chans.append(w)
     return chans, lower([channel_grid(w) for w in chans])
@@ -94,10 +96,45 @@ def test_mixed_shapes_with_gaps_and_ragged_channels(ns):
     assert got.any_complex
 
 
+def test_per_pulse_amplitude_and_phase(ns):
+    """Amplitude and phase as per-pulse parameter arrays (virtual-Z phases, calibrated
+    amplitudes): the products and sums the algebra forms with them (mul / add of term
+    amplitudes, -phase / w in cos(), _waveform.pyx:68-88, waveform.py:1153-1168) are replayed."""
+    fns = [
+        lambda t0, amp, phase: ns.mixing(amp * ns.cosPulse(20e-9) >> t0, freq=-60e6, phase=phase,
+                                         DRAGScaling=4e-10)[0],
+        lambda t0, amp, phase: ns.mixing(amp * ns.gaussian(20e-9) >> t0, freq=145e6, phase=phase,
+                                         DRAGScaling=7e-10)[1],
+        lambda t0, amp, phase: (amp * ns.square(50e-9, edge=2e-9) >> t0) * 0.5,
+    ]
+    templates = [PulseTemplate.trace(f, params=('t0', 'amp', 'phase')) for f in fns]
+    rng = np.random.default_rng(17)
+    idx, t0, amp, phase = [], [], [], []
+    for n in (60, 7, 33):
+        idx.append(rng.integers(0, len(fns), n))
+        t0.append(150e-9 + 80e-9 * np.arange(n) + rng.uniform(0, 20e-9, n))
+        amp.append(rng.uniform(-1, 1, n))
+        phase.append(rng.uniform(0, 2 * np.pi, n))
+    params = {'amp': amp, 'phase': phase}
+    got = pulse_train_batch(templates, idx, t0, 0, 6e-6, 2e9, params=params)
+    _, want = object_batch(ns, fns, idx, t0, 0, 6e-6, 2e9, params=params)
+    assert_same_tables(got, want)
+    with pytest.raises(ValueError, match='parameter array'):
+        pulse_train_batch(templates, idx, t0, 0, 6e-6, 2e9, params={'amp': amp})
+    # a parameter value that changes the STRUCTURE (amplitude exactly 0: the algebra drops the
+    # pulse) is caught by the spot check against the object API
+    amp0 = [np.zeros_like(a) for a in amp]
+    with pytest.raises(UntraceablePulse):
+        pulse_train_batch(templates, idx, t0, 0, 6e-6, 2e9, params={'amp': amp0, 'phase': phase})
+
+
 def test_untraceable_dependence_is_refused(ns):
     # arithmetic the tracer does not record raises at once ...
     with pytest.raises(UntraceablePulse):
-        PulseTemplate.trace(lambda t0: (t0 * 1e6) * ns.cosPulse(20e-9) >> t0)
+        PulseTemplate.trace(lambda t0: (t0 ** 2 * 1e12) * ns.cosPulse(20e-9) >> t0)
+    # a basis-function argument (here the carrier frequency) cannot vary per pulse
+    with pytest.raises(UntraceablePulse):
+        PulseTemplate.trace(lambda t0, f: ns.mixing(ns.cosPulse(20e-9) >> t0, freq=f * 1e8)[0], params=('t0', 'f'))
     # ... and a dependence hidden behind float() is caught by the check at a second start time
     with pytest.raises(UntraceablePulse):
         PulseTemplate.trace(lambda t0: ns.mixing(ns.cosPulse(20e-9) >> t0, freq=50e6, phase=float(t0) * 1e6)[0])
@@ -134,5 +171,14 @@ def test_builder_samples_equal_object_api(ns):
     # the public entry point: parameter arrays in, device-resident channels out
     from waveforms_b200.batch import sample_pulse_trains
     res = sample_pulse_trains(templates, idx, t0, 0, 4e-6, 2e9)
+    for c, w in enumerate(chans):
+        assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())
+    # per-pulse amplitude and phase arrays
+    fn = lambda t0, amp, phase: ns.mixing(amp * ns.gaussian(20e-9) >> t0, freq=145e6, phase=phase, DRAGScaling=7e-10)[1]
+    tp = PulseTemplate.trace(fn, params=('t0', 'amp', 'phase'))
+    t0 = [200e-9 + 60e-9 * np.arange(50)] * 2
+    params = {'amp': [rng.uniform(-1, 1, 50) for _ in range(2)], 'phase': [rng.uniform(0, 6, 50) for _ in range(2)]}
+    res = sample_pulse_trains([tp], [np.zeros(50, int)] * 2, t0, 0, 4e-6, 2e9, params=params)
+    chans, _ = object_batch(ns, [fn], [np.zeros(50, int)] * 2, t0, 0, 4e-6, 2e9, params=params)
     for c, w in enumerate(chans):
         assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())

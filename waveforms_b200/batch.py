@@ -99,12 +99,14 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
 
 
 def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
-                        dtype=np.float64, devices=None):
+                        dtype=np.float64, devices=None, params=None):
     """Channels given as PARAMETER ARRAYS instead of objects: channel ``c`` is the
     stack of pulses ``templates[tmpl_idx[c][k]]`` started at ``t0[c][k]``
     (``builder.PulseTemplate.trace`` / ``builder.pulse_train_batch``), sampled on
-    ``np.arange(start, stop, 1/sample_rate)``.  Same sharding and result type as
-    ``sample_batch``; the tables are those the object API would have produced."""
+    ``np.arange(start, stop, 1/sample_rate)``; ``params = {name: array like t0}``
+    carries the templates' further per-pulse parameters (amplitude, phase ...).
+    Same sharding and result type as ``sample_batch``; the tables are those the
+    object API would have produced."""
     import torch
     from .builder import pulse_train_batch
     engine.require_gpu()
@@ -117,7 +119,8 @@ def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
     tensors, table = [], []
     for slot, (dev, (lo, hi)) in enumerate(zip(devices, ranges)):
         batch = pulse_train_batch(templates, tmpl_idx[lo:hi], t0[lo:hi], start, stop,
-                                  sample_rate)
+                                  sample_rate,
+                                  params={k: v[lo:hi] for k, v in (params or {}).items()})
         with torch.cuda.device(dev):
             prog = engine.Program(batch, dev)
             out = prog.sample_device(dtype=code)

@@ -37,105 +37,158 @@ class UntraceablePulse(ValueError):
     """The pulse's tables depend on its start time in a way the tracer did not record."""
 
 
-class SymTime(float):
-    """A float that remembers how it was computed from the symbolic start time ``t0``.
-    Its value is the probe start time's, so comparisons, sorting and hashing inside the
-    algebra behave exactly as for a plain float.  Only the operations the algebra
-    applies to times are traceable (+, -, unary -, round); anything else raises."""
+class Sym(float):
+    """A float that remembers how it was computed from the symbolic pulse parameters (the
+    start time ``t0``, an amplitude, a phase ...).  Its value is the probe point's, so
+    comparisons, sorting and hashing inside the algebra behave exactly as for a plain
+    float.  +, -, *, /, unary - and round() are recorded; anything else (powers, math
+    functions, complex arithmetic) either raises or silently yields a plain number, which
+    the check at a second parameter point then exposes."""
     __slots__ = ('expr', )
 
-    def __new__(cls, value, expr=('t0', )):
+    def __new__(cls, value, expr=('p', 't0')):
         self = super().__new__(cls, value)
         self.expr = expr
         return self
 
     @staticmethod
     def _expr(v):
-        return v.expr if isinstance(v, SymTime) else ('const', float(v))
+        return v.expr if isinstance(v, Sym) else ('const', float(v))
+
+    @staticmethod
+    def _real(o):
+        return isinstance(o, (int, float, np.integer, np.floating)) and not isinstance(o, bool)
+
+    def _bin(self, o, op, fn, swap):
+        if not self._real(o):
+            return NotImplemented
+        a, b = (o, self) if swap else (self, o)
+        return Sym(fn(float(a), float(b)), (op, self._expr(a), self._expr(b)))
 
     def __add__(self, o):
-        return SymTime(float(self) + float(o), ('add', self.expr, self._expr(o)))
+        return self._bin(o, 'add', lambda a, b: a + b, False)
 
     def __radd__(self, o):
-        return SymTime(float(o) + float(self), ('add', self._expr(o), self.expr))
+        return self._bin(o, 'add', lambda a, b: a + b, True)
 
     def __sub__(self, o):
-        return SymTime(float(self) - float(o), ('sub', self.expr, self._expr(o)))
+        return self._bin(o, 'sub', lambda a, b: a - b, False)
 
     def __rsub__(self, o):
-        return SymTime(float(o) - float(self), ('sub', self._expr(o), self.expr))
+        return self._bin(o, 'sub', lambda a, b: a - b, True)
+
+    def __mul__(self, o):
+        return self._bin(o, 'mul', lambda a, b: a * b, False)
+
+    def __rmul__(self, o):
+        return self._bin(o, 'mul', lambda a, b: a * b, True)
+
+    def __truediv__(self, o):
+        return self._bin(o, 'div', lambda a, b: a / b, False)
+
+    def __rtruediv__(self, o):
+        return self._bin(o, 'div', lambda a, b: a / b, True)
 
     def __neg__(self):
-        return SymTime(-float(self), ('neg', self.expr))
+        return Sym(-float(self), ('neg', self.expr))
 
     def __pos__(self):
         return self
 
     def __round__(self, nd=None):
         if nd is None:
-            raise UntraceablePulse('round() to an integer of a symbolic time')
-        return SymTime(round(float(self), nd), ('round', self.expr, nd))
+            raise UntraceablePulse('round() to an integer of a symbolic parameter')
+        return Sym(round(float(self), nd), ('round', self.expr, nd))
 
     def _untraceable(self, *_):
-        raise UntraceablePulse('the pulse multiplies / divides / exponentiates its start time; '
-                               'only +, - and round() of the start time can be traced')
+        raise UntraceablePulse('powers / remainders of a symbolic pulse parameter cannot be traced')
 
-    __mul__ = __rmul__ = __truediv__ = __rtruediv__ = __pow__ = __rpow__ = _untraceable
-    __floordiv__ = __rfloordiv__ = __mod__ = __rmod__ = _untraceable
+    __pow__ = __rpow__ = __floordiv__ = __rfloordiv__ = __mod__ = __rmod__ = _untraceable
+
+
+SymTime = Sym  # the start time was the first traced parameter
 
 
 _round_ufuncs = {}
 
 
-def _eval(expr, t0):
-    """Replay a recorded expression over the float64 array ``t0`` (element-wise IEEE
+def _eval(expr, env):
+    """Replay a recorded expression over float64 arrays ``env[name]`` (element-wise IEEE
     operations: identical to the Python float arithmetic of the trace)."""
     op = expr[0]
-    if op == 't0':
-        return t0
+    if op == 'p':
+        return env[expr[1]]
     if op == 'const':
         return np.float64(expr[1])
     if op == 'neg':
-        return -_eval(expr[1], t0)
+        return -_eval(expr[1], env)
     if op == 'round':
         nd = expr[2]
         uf = _round_ufuncs.get(nd)
         if uf is None:  # Python's correctly rounded decimal round(), not np.round's scaling
             uf = _round_ufuncs[nd] = np.frompyfunc(lambda v, nd=nd: round(v, nd), 1, 1)
-        return uf(np.asarray(_eval(expr[1], t0), dtype=np.float64)).astype(np.float64)
-    a, b = _eval(expr[1], t0), _eval(expr[2], t0)
-    return a + b if op == 'add' else a - b
+        return uf(np.asarray(_eval(expr[1], env), dtype=np.float64)).astype(np.float64)
+    a, b = _eval(expr[1], env), _eval(expr[2], env)
+    if op == 'add':
+        return a + b
+    if op == 'sub':
+        return a - b
+    if op == 'mul':
+        return a * b
+    return a / b
 
 
 _cos_uf = np.frompyfunc(math.cos, 1, 1)  # the libm calls lowering._emit_rows makes
 _sin_uf = np.frompyfunc(math.sin, 1, 1)
 
 
-class PulseTemplate:
-    """The lowered tables of ONE pulse as a function of its start time."""
+_PROBE = {'t0': (1.0e-6, 2.37e-6)}
 
-    def __init__(self, fn, probe=1.0e-6, check=2.37e-6):
+
+def _probe_values(params, probe, check):
+    """Two generic parameter points: the trace runs at the first, the check at the second."""
+    pv, cv = {}, {}
+    for i, name in enumerate(params):
+        d = _PROBE.get(name, (0.6180339887498949 + 0.0817 * i, 0.4142135623730951 + 0.0613 * i))
+        pv[name] = float((probe or {}).get(name, d[0]))
+        cv[name] = float((check or {}).get(name, d[1]))
+    return pv, cv
+
+
+class PulseTemplate:
+    """The lowered tables of ONE pulse shape as a function of its parameters: the start time
+    ``t0`` and any further scalar the pulse is built from (amplitude, phase ...)."""
+
+    def __init__(self, fn, params=('t0', ), probe=None, check=None):
         self.fn = fn
-        w = fn(SymTime(probe))
+        self.params = tuple(params)
+        pv, cv = _probe_values(self.params, probe, check)
+        w = fn(*[Sym(pv[n], ('p', n)) for n in self.params])
         self._extract(w.bounds, w.seq)
-        self._verify(check)
+        self._verify(cv)
 
     @classmethod
-    def trace(cls, fn, **kw):
-        """``fn(t0) -> Waveform`` built with the ordinary object API, e.g.
+    def trace(cls, fn, params=('t0', ), **kw):
+        """``fn(*params) -> Waveform`` built with the ordinary object API, e.g.
         ``lambda t0: mixing(0.5 * cosPulse(20e-9) >> t0, freq=-80e6, phase=pi/2,
-        DRAGScaling=4e-10)[0]``."""
-        return cls(fn, **kw)
+        DRAGScaling=4e-10)[0]`` or, with per-pulse amplitude and phase,
+        ``PulseTemplate.trace(lambda t0, amp, phase: mixing(amp * cosPulse(20e-9) >> t0,
+        freq=-80e6, phase=phase, DRAGScaling=4e-10)[0], params=('t0', 'amp', 'phase'))``.
+        ``probe`` / ``check``: dicts of the two parameter points used for tracing and for
+        the self-check (defaults are generic values; give your own if the pulse's structure
+        depends on the parameter range)."""
+        return cls(fn, params, **kw)
 
     # -- tracing -------------------------------------------------------------------
     def _extract(self, bounds, seq):
         if not bounds or bounds[-1] != math.inf or seq[-1] != A.ZERO or seq[0] != A.ZERO:
             raise UntraceablePulse('a pulse template must be zero before its first and after its '
                                    'last bound')
-        self.bound_expr = [SymTime._expr(b) for b in bounds[:-1]]
+        self.bound_expr = [Sym._expr(b) for b in bounds[:-1]]
         pools = _Pools()
         self.seg_fac, self.seg_term = [], []       # local CSR starts of the finite segments
         self.sym_shift = []                        # (fac row, expr)
+        self.sym_amp = []                          # (term row, expr)
         self.rot_rows = []                         # (fac row, local arg_off, w, base-shift expr)
         has_args = []                              # fac rows that own a block of the argument pool
         cplx = False
@@ -151,21 +204,27 @@ class PulseTemplate:
                         seen.add(f)
                         order.append(f)
             rows, _ = _plan_slots(order)  # the plan _lower_segment is about to emit
-            base = pools.n_fac
-            plain = (tuple((tuple((*f[:-1], float(f[-1])) for f in factors), expo) for factors, expo in s[0]), s[1])
+            base, base_term = pools.n_fac, pools.n_term
+            plain = (tuple((tuple((*f[:-1], float(f[-1])) for f in factors), expo) for factors, expo in s[0]),
+                     tuple(float(v) if isinstance(v, Sym) else v for v in s[1]))
             cplx = _lower_segment(pools, [plain]) or cplx
+            for k, amp in enumerate(s[1]):
+                if isinstance(amp, Sym):
+                    self.sym_amp.append((base_term + k, amp.expr))
             for r, row in enumerate(rows):
                 has_args.append(row[0] == 'rot' or
                                 (row[0] == 'plain' and bool(PACKERS[row[1][0]](row[1][1:-1])[2])))
                 if row[0] == 'nop':
                     continue
                 f = row[1]
-                if isinstance(f[-1], SymTime):
+                if isinstance(f[-1], Sym):
                     self.sym_shift.append((base + r, f[-1].expr))
-                if any(isinstance(a, SymTime) for a in f[1:-1]):
-                    raise UntraceablePulse('a basis-function argument depends on the start time')
+                if any(isinstance(a, Sym) for a in f[1:-1]):
+                    raise UntraceablePulse('a basis-function argument (frequency, width ...) depends on a '
+                                           'traced parameter; only start times, phases and amplitudes can vary '
+                                           'per pulse — use one template per value')
                 if row[0] == 'rot':
-                    self.rot_rows.append((base + r, pools.fac[base + r][1], f[1], SymTime._expr(row[3][-1])))
+                    self.rot_rows.append((base + r, pools.fac[base + r][1], f[1], Sym._expr(row[3][-1])))
         self.n_seg = len(bounds) - 1
         self.facs = np.array(pools.fac, dtype=FACTOR_DT) if pools.fac else np.zeros(0, FACTOR_DT)
         self.terms = np.array(pools.term, dtype=TERM_DT) if pools.term else np.zeros(0, TERM_DT)
@@ -176,55 +235,81 @@ class PulseTemplate:
         self.has_args = np.asarray(has_args, dtype=np.int64)
         self.complex = cplx
 
-    def instantiate(self, t0):
-        """Tables of ``len(t0)`` instances: (bounds[P, n_seg], facs[P, nf], args[P, na]);
-        ``arg_off`` stays local to the instance."""
-        t0 = np.ascontiguousarray(t0, dtype=np.float64)
-        # start times repeat across channels (a gate grid): evaluate the distinct ones only
-        uniq, inverse = np.unique(t0, return_inverse=True)
-        if len(uniq) <= len(t0) // 2:
-            b, f, a = self.instantiate(uniq)
-            return b[inverse], f[inverse], a[inverse]
-        P = len(t0)
+    def instantiate(self, t0, **more):
+        """Tables of ``len(t0)`` instances: (bounds[P, n_seg], facs[P, nf], args[P, na],
+        amps[P, n_sym_amp]); ``arg_off`` stays local to the instance."""
+        env = {'t0': np.ascontiguousarray(t0, dtype=np.float64)}
+        for n in self.params:
+            if n != 't0':
+                env[n] = np.ascontiguousarray(more[n], dtype=np.float64)
+        P = len(env['t0'])
+        # parameter points repeat across channels (a gate grid): evaluate the distinct ones only
+        if P > 1:
+            pts = np.stack([env[n] for n in self.params], axis=1)
+            uniq, inverse = np.unique(pts, axis=0, return_inverse=True)
+            inverse = inverse.reshape(-1)
+            if len(uniq) <= P // 2:
+                out = self.instantiate(**{n: uniq[:, i] for i, n in enumerate(self.params)})
+                return tuple(o[inverse] for o in out)
         bounds = np.empty((P, self.n_seg), dtype=np.float64)
         for j, e in enumerate(self.bound_expr):
-            bounds[:, j] = _eval(e, t0)
+            bounds[:, j] = _eval(e, env)
         facs = np.tile(self.facs, P).reshape(P, len(self.facs))
         for r, e in self.sym_shift:
-            facs['shift'][:, r] = _eval(e, t0)
+            facs['shift'][:, r] = _eval(e, env)
+        amps = np.empty((P, len(self.sym_amp)), dtype=np.float64)
+        for i, (_, e) in enumerate(self.sym_amp):
+            amps[:, i] = _eval(e, env)
         args = np.tile(self.args, P).reshape(P, len(self.args))
         for r, off, w, base_expr in self.rot_rows:
             # lowering._emit_rows: delta = w * (s_b - s_t); block (slot, s_b, delta, cos, sin)
-            s_b = np.broadcast_to(_eval(base_expr, t0), (P, ))
+            s_b = np.broadcast_to(_eval(base_expr, env), (P, ))
             delta = w * (s_b - facs['shift'][:, r])
             args[:, off + 1] = s_b
             args[:, off + 2] = delta
             args[:, off + 3] = _cos_uf(delta).astype(np.float64)
             args[:, off + 4] = _sin_uf(delta).astype(np.float64)
-        return bounds, facs, args
+        return bounds, facs, args, amps
 
-    def _verify(self, t_check):
-        """Replay at a second start time against a plain-float build there."""
-        w = self.fn(float(t_check))
+    def instance_terms(self, amps):
+        """terms[P, nt] with the traced amplitudes filled in (``ref_begin`` local)."""
+        P = len(amps)
+        t = np.tile(self.terms, P).reshape(P, len(self.terms))
+        for i, (row, _) in enumerate(self.sym_amp):
+            t['amp_re'][:, row] = amps[:, i]
+        return t
+
+    def _verify(self, point):
+        """Replay at a second parameter point against a plain-float build there."""
+        w = self.fn(*[point[n] for n in self.params])
         ref = PulseTemplate.__new__(PulseTemplate)
         ref._extract(w.bounds, w.seq)
-        b, f, a = self.instantiate(np.array([t_check]))
+        b, f, a, amps = self.instantiate(**{n: np.array([point[n]]) for n in self.params})
         same = (ref.n_seg == self.n_seg and np.array_equal(np.array([float(x) for x in w.bounds[:-1]]), b[0])
                 and np.array_equal(ref.facs, f[0]) and np.array_equal(ref.args, a[0])
-                and np.array_equal(ref.terms, self.terms) and np.array_equal(ref.refs, self.refs))
+                and np.array_equal(ref.terms, self.instance_terms(amps)[0]) and np.array_equal(ref.refs, self.refs))
         if not same:
-            raise UntraceablePulse('the tables traced with a symbolic start time do not reproduce a '
-                                   f'plain build at t0={t_check!r}: the pulse depends on its start '
-                                   'time through an operation the tracer cannot follow')
+            raise UntraceablePulse('the tables traced with symbolic parameters do not reproduce a plain build at '
+                                   f'{point!r}: the pulse depends on a parameter through an operation the tracer '
+                                   'cannot follow (math functions, complex arithmetic, float()), or its structure '
+                                   'changes with the parameter value')
 
 
-def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate) -> LoweredBatch:
+def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=None,
+                      spot_check=4) -> LoweredBatch:
     """One channel per row: channel ``c`` is the stack of pulses ``templates[tmpl_idx[c][k]]``
     started at ``t0[c][k]`` (time-ordered, non-overlapping), sampled on
     ``np.arange(start, stop, 1/sample_rate)`` — the ``LoweredBatch`` that
-    ``lower([channel_grid(WaveVStack([fn(t) for ...]))])`` yields, built with NumPy.
-    ``tmpl_idx`` / ``t0``: 2-D arrays or lists of 1-D arrays (ragged channels)."""
+    ``lower([channel_grid(WaveVStack([fn(t, ...) for ...]))])`` yields, built with NumPy.
+    ``tmpl_idx`` / ``t0``: 2-D arrays or lists of 1-D arrays (ragged channels); ``params``:
+    ``{name: array shaped like t0}`` for the templates' further parameters (amplitude,
+    phase ...).  ``spot_check`` pulses per template are rebuilt through the object API and
+    compared bit for bit (guards against a structure that changes with the parameter
+    values, e.g. an amplitude that is exactly zero)."""
     n_ch = len(t0)
+    params = params or {}
+    flat = {k: (np.concatenate([np.asarray(r, dtype=np.float64) for r in v]) if n_ch else np.zeros(0))
+            for k, v in params.items()}
     counts = np.array([len(r) for r in t0], dtype=np.int64)
     T = np.concatenate([np.asarray(r, dtype=np.float64) for r in t0]) if n_ch else np.zeros(0)
     M = np.concatenate([np.asarray(r, dtype=np.int64) for r in tmpl_idx]) if n_ch else np.zeros(0, np.int64)
@@ -266,7 +351,13 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate) -> Lowe
         idx = np.nonzero(M == m)[0]
         if not len(idx):
             continue
-        b, f, a = tp.instantiate(T[idx])
+        missing = [n for n in tp.params if n != 't0' and n not in flat]
+        if missing:
+            raise ValueError(f'template {m} needs the parameter array(s) {missing}')
+        more = {n: flat[n][idx] for n in tp.params if n != 't0'}
+        b, f, a, amps = tp.instantiate(T[idx], **more)
+        for j in (np.random.default_rng(m).choice(len(idx), min(spot_check, len(idx)), replace=False) if spot_check else ()):
+            tp._verify({'t0': float(T[idx[j]]), **{n: float(v[j]) for n, v in more.items()}})
         first_edge[idx], last_edge[idx] = b[:, 0], b[:, -1]
         sp = seg_pos[idx][:, None] + np.arange(tp.n_seg)[None, :]
         seg_bound[sp] = b
@@ -276,7 +367,7 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate) -> Lowe
             f['arg_off'] += (arg_off[idx][:, None] * tp.has_args[None, :]).astype(np.int32)
             facs[fac_off[idx][:, None] + np.arange(len(tp.facs))[None, :]] = f
         if len(tp.terms):
-            t = np.tile(tp.terms, len(idx)).reshape(len(idx), len(tp.terms))
+            t = tp.instance_terms(amps)
             t['ref_begin'] += ref_off[idx][:, None].astype(np.int32)
             terms[term_off[idx][:, None] + np.arange(len(tp.terms))[None, :]] = t
         if len(tp.refs):
