@@ -98,6 +98,31 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     return BatchResult(tensors, table, dtype)
 
 
+def from_wire(record, kind=None):
+    """A waveform shipped WITHOUT Python objects: the reference's
+    flat list (``Waveform.tolist``, waveform.py:259-276; ``WaveVStack.tolist``,
+    :823-835 — the two layouts cannot be told apart, so ``kind='stack'`` selects
+    the latter) or its ``(header, body)`` tree (``totree``, :342-353).  Objects pass
+    through unchanged."""
+    from .waveform import Waveform, WaveVStack
+    if isinstance(record, Waveform):
+        return record
+    if kind == 'stack':
+        return WaveVStack.fromlist(list(record))
+    if isinstance(record, tuple) and len(record) == 2 and isinstance(record[1], tuple):
+        return Waveform.fromtree(record)
+    if isinstance(record, (list, tuple)):
+        return Waveform.fromlist(list(record))
+    raise TypeError(f'not a waveform, a tolist() list or a totree() tree: {type(record).__name__}')
+
+
+def sample_wire(records, kinds=None, **kw):
+    """``sample_batch`` for channels given in the reference's wire formats (see
+    ``from_wire``); ``kinds[i] = 'stack'`` marks ``WaveVStack.tolist`` records."""
+    kinds = kinds or [None] * len(records)
+    return sample_batch([from_wire(r, k) for r, k in zip(records, kinds)], **kw)
+
+
 def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
                         dtype=np.float64, devices=None, params=None):
     """Channels given as PARAMETER ARRAYS instead of objects: channel ``c`` is the
