@@ -338,6 +338,20 @@ def main():
     launches = prog.launch_count - launches0
     # keep the sampler alive through the e2e leg as well, then summarise the timed region only
     n_kernel_clock = len(clock_lines)
+    # a pure-store fill of the same buffer in the same run (calibration of what a
+    # store-only kernel reaches on this box; torch's fill kernel, not part of the product path)
+    fill_ms = None
+    if rank == 0:
+        fe = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        out.fill_(0.5)
+        torch.cuda.synchronize()
+        fe[0].record(stream)
+        for k in range(6):
+            out.fill_(float(k))
+            fe[k + 1].record(stream)
+        torch.cuda.synchronize()
+        fill_ms = min(fe[k].elapsed_time(fe[k + 1]) for k in range(6))
+    fill_gbs = out.numel() * esz / (fill_ms * 1e-3) / 1e9 if fill_ms else None
 
     t = torch.tensor([total_ms], dtype=torch.float64, device=f'cuda:{local_rank}')
     if world > 1:
@@ -411,7 +425,11 @@ def main():
                 'algorithmic_bytes_per_launch': samples_per_step * esz, 'launch_ms': k1_ms,
                 # one ncu --set full capture at frames_per_launch frames, scaled to this launch's frames
             'traffic': (traffic['dram_bytes_per_launch'] * args.frames / traffic['frames_per_launch']) if traffic else None,
-                'traffic_source': traffic.get('source') if traffic else None}
+                'traffic_source': traffic.get('source') if traffic else None,
+                'frac_of_nominal_8TBs': achieved / 8000.0,
+                'store_fill_same_run': {'GB/s': fill_gbs, 'frac_of_it': achieved / fill_gbs,
+                                        'what': 'torch fill_ of the same output buffer, best of 6, CUDA events'}
+                if fill_gbs else None}
 
     cpu = None
     if not args.no_cpu and world == 1:
