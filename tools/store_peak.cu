@@ -51,6 +51,55 @@ __global__ void bulk_kernel(unsigned char* out, size_t bytes, uint32_t chunk) {
   }
 }
 
+// NON-persistent bulk stores: every warp stores `per_warp` consecutive chunks and exits
+// (grid = n_chunks / (warps * per_warp)): does a huge short-lived grid reach what memset reaches?
+__global__ void bulk_once_kernel(unsigned char* out, size_t bytes, uint32_t chunk, int per_warp) {
+  extern __shared__ __align__(128) unsigned char buf[];
+  for (uint32_t i = threadIdx.x * 16; i < chunk; i += blockDim.x * 16) *reinterpret_cast<uint4*>(buf + i) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t warp = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const size_t n_chunks = bytes / chunk;
+  if (lane == 0) {
+    for (int k = 0; k < per_warp; ++k) {
+      const size_t c = warp * per_warp + k;
+      if (c >= n_chunks) break;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c * chunk), "r"(smem_u32(buf)), "r"(chunk) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+// persistent, but every CTA owns a CONTIGUOUS range of the buffer (blocked instead of round-robin)
+__global__ void bulk_blocked_kernel(unsigned char* out, size_t bytes, uint32_t chunk) {
+  extern __shared__ __align__(128) unsigned char buf[];
+  for (uint32_t i = threadIdx.x * 16; i < chunk; i += blockDim.x * 16) *reinterpret_cast<uint4*>(buf + i) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpc = blockDim.x / 32;
+  const size_t n_chunks = bytes / chunk;
+  const size_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const size_t lo = blockIdx.x * per_cta, hi = lo + per_cta < n_chunks ? lo + per_cta : n_chunks;
+  if (lane == 0) {
+    for (size_t c = lo + (threadIdx.x >> 5); c < hi; c += wpc) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c * chunk), "r"(smem_u32(buf)), "r"(chunk) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+// registers, non-persistent: every thread stores `per_thread` 16-byte elements (strided by the CTA) and exits
+__global__ void st_few_kernel(double2* out, size_t n2, double v, int per_thread) {
+  const size_t base = (size_t)blockIdx.x * blockDim.x * per_thread + threadIdx.x;
+  const double2 val = make_double2(v, v);
+  for (int k = 0; k < per_thread; ++k) {
+    const size_t i = base + (size_t)k * blockDim.x;
+    if (i < n2) out[i] = val;
+  }
+}
+
 template <typename F>
 float time_it(F f, int reps) {
   cudaEvent_t a, b;
@@ -88,7 +137,24 @@ int main() {
     float ms = time_it([&] { st_kernel<<<(unsigned)(bytes / 16 / 256), 256>>>((double2*)out, bytes / 16, 0.0); }, 10);
     printf("st.v2.f64   one elem per thread    %8.3f ms  %8.1f GB/s\n", ms, bytes / ms / 1e6);
   }
-  for (uint32_t chunk : {1024u, 2048u, 4096u, 8192u, 16384u, 32768u}) for (int warps : {1, 4, 8}) for (int per_sm : {1, 2}) {
+  for (int per_thread : {2, 4, 16, 64}) {
+    const size_t n2 = bytes / 16;
+    float ms = time_it([&] { st_few_kernel<<<(unsigned)((n2 + 256ull * per_thread - 1) / (256ull * per_thread)), 256>>>((double2*)out, n2, 0.0, per_thread); }, 10);
+    printf("st.v2.f64   %2d elems per thread, non-persistent  %8.3f ms  %8.1f GB/s\n", per_thread, ms, bytes / ms / 1e6);
+  }
+  CK(cudaFuncSetAttribute(bulk_once_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(bulk_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  for (uint32_t chunk : {4096u, 10240u, 16384u}) for (int warps : {4, 8}) for (int per_warp : {1, 2, 4, 16}) {
+    const size_t n_chunks = bytes / chunk;
+    const unsigned grid = (unsigned)((n_chunks + (size_t)warps * per_warp - 1) / ((size_t)warps * per_warp));
+    float ms = time_it([&] { bulk_once_kernel<<<grid, warps * 32, chunk>>>(out, bytes, chunk, per_warp); }, 10);
+    printf("bulk s2g NON-persistent chunk %5u B, %d warps/CTA, %2d chunks/warp (grid %7u)  %8.3f ms  %8.1f GB/s\n", chunk, warps, per_warp, grid, ms, bytes / ms / 1e6);
+  }
+  for (uint32_t chunk : {4096u, 10240u}) for (int per_sm : {1, 2}) {
+    float ms = time_it([&] { bulk_blocked_kernel<<<sms * per_sm, 256, chunk>>>(out, bytes, chunk); }, 10);
+    printf("bulk s2g persistent BLOCKED ranges chunk %5u B, 8 warps x %d CTA/SM  %8.3f ms  %8.1f GB/s\n", chunk, per_sm, ms, bytes / ms / 1e6);
+  }
+  for (uint32_t chunk : {8192u}) for (int warps : {8}) for (int per_sm : {1, 2}) {
     CK(cudaFuncSetAttribute(bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CK(cudaFuncSetAttribute(bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     float ms = time_it([&] { bulk_kernel<true><<<sms * per_sm, warps * 32, chunk>>>(out, bytes, chunk); }, 10);

@@ -44,6 +44,7 @@
 //
 // Algorithmic traffic: 8 B (4 B) per sample, write-only.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include <algorithm>
 #include "wfm_basis.cuh"
@@ -1052,6 +1053,11 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
   }
 }
 
+// Tiles per warp of a launch: 0 = persistent grid (CTAs per SM x SMs), k > 0 = a grid of short-lived CTAs
+// whose warps take about k tiles each, handed out by the hardware CTA scheduler (dynamic balance).
+#ifndef WFM_K1_TILES_PER_WARP
+#define WFM_K1_TILES_PER_WARP 0
+#endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
 template <typename OutT, bool kAccumulate, int U>
@@ -1337,7 +1343,10 @@ static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles,
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem)) != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   const int64_t want = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per_sm);
+  int64_t cap = (int64_t)sms * per_sm;  // persistent: every warp walks tiles w, w+G, ...
+  static const int tiles_per_warp = [] { const char* v = getenv("WFM_K1_TILES_PER_WARP"); return v ? atoi(v) : WFM_K1_TILES_PER_WARP; }();
+  if (tiles_per_warp > 0) cap = std::max<int64_t>(cap, (want + tiles_per_warp - 1) / tiles_per_warp);
+  const unsigned grid = (unsigned)std::min<int64_t>(want, cap);
   k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out);
   return cudaGetLastError();
 }
