@@ -182,3 +182,32 @@ def test_builder_samples_equal_object_api(ns):
     chans, _ = object_batch(ns, [fn], [np.zeros(50, int)] * 2, t0, 0, 4e-6, 2e9, params=params)
     for c, w in enumerate(chans):
         assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())
+
+
+def test_channel_shards_equal_slices_of_the_whole_batch(ns):
+    """Multi-GPU (SURVEY §8e): ``sample_pulse_trains`` shards the parameter arrays by channel;
+    the tables of a shard are the matching slice of the whole batch's (no exchange needed)."""
+    from waveforms_b200.batch import shard_ranges
+    fns = drag_fns(ns, 0)
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(8)
+    counts = [40, 3, 0, 25, 40, 17, 9]
+    idx = [rng.integers(0, 8, n) for n in counts]
+    t0 = [110e-9 + 20e-9 * np.arange(n) for n in counts]
+    whole = pulse_train_batch(templates, idx, t0, 0, 1e-6, 2e9)
+    ranges = shard_ranges([max(n, 1) for n in counts], 3)
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(counts)
+    for lo, hi in ranges:
+        part = pulse_train_batch(templates, idx[lo:hi], t0[lo:hi], 0, 1e-6, 2e9)
+        if hi == lo:
+            assert len(part.waves) == 0
+            continue
+        s0 = int(whole.waves['seg_begin'][lo])
+        ns_ = len(part.seg_bound)
+        f0, t_0 = int(whole.seg_ptr['fac'][s0]), int(whole.seg_ptr['term'][s0])
+        assert np.array_equal(part.seg_bound, whole.seg_bound[s0:s0 + ns_])
+        assert np.array_equal(part.seg_ptr['fac'], whole.seg_ptr['fac'][s0:s0 + ns_ + 1] - f0)
+        assert np.array_equal(part.seg_ptr['term'], whole.seg_ptr['term'][s0:s0 + ns_ + 1] - t_0)
+        assert np.array_equal(part.facs['shift'], whole.facs['shift'][f0:f0 + len(part.facs)])
+        assert np.array_equal(part.terms['amp_re'], whole.terms['amp_re'][t_0:t_0 + len(part.terms)])
+        assert np.array_equal(part.waves['n'], whole.waves['n'][lo:hi]) and part.waves['out_off'][0] == 0

@@ -90,6 +90,27 @@ __global__ void bulk_blocked_kernel(unsigned char* out, size_t bytes, uint32_t c
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
+// persistent grid, chunks handed out DYNAMICALLY (atomic counter, one fetch per chunk per warp)
+__global__ void bulk_dynamic_kernel(unsigned char* out, size_t bytes, uint32_t chunk, unsigned long long* counter, int batch) {
+  extern __shared__ __align__(128) unsigned char buf[];
+  for (uint32_t i = threadIdx.x * 16; i < chunk; i += blockDim.x * 16) *reinterpret_cast<uint4*>(buf + i) = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t n_chunks = bytes / chunk;
+  if (lane == 0) {
+    for (;;) {
+      const size_t c0 = atomicAdd(counter, (unsigned long long)batch);
+      if (c0 >= n_chunks) break;
+      for (size_t c = c0; c < c0 + batch && c < n_chunks; ++c) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c * chunk), "r"(smem_u32(buf)), "r"(chunk) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
 // registers, non-persistent: every thread stores `per_thread` 16-byte elements (strided by the CTA) and exits
 __global__ void st_few_kernel(double2* out, size_t n2, double v, int per_thread) {
   const size_t base = (size_t)blockIdx.x * blockDim.x * per_thread + threadIdx.x;
@@ -153,6 +174,15 @@ int main() {
   for (uint32_t chunk : {4096u, 10240u}) for (int per_sm : {1, 2}) {
     float ms = time_it([&] { bulk_blocked_kernel<<<sms * per_sm, 256, chunk>>>(out, bytes, chunk); }, 10);
     printf("bulk s2g persistent BLOCKED ranges chunk %5u B, 8 warps x %d CTA/SM  %8.3f ms  %8.1f GB/s\n", chunk, per_sm, ms, bytes / ms / 1e6);
+  }
+  {
+    unsigned long long* counter;
+    CK(cudaMalloc(&counter, 8));
+    CK(cudaFuncSetAttribute(bulk_dynamic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (uint32_t chunk : {10240u}) for (int per_sm : {2}) for (int batch : {1, 4, 8, 16, 32}) {
+      float ms = time_it([&] { CK(cudaMemsetAsync(counter, 0, 8)); bulk_dynamic_kernel<<<sms * per_sm, 256, chunk>>>(out, bytes, chunk, counter, batch); }, 10);
+      printf("bulk s2g persistent DYNAMIC (atomic counter, %2d chunks per fetch) chunk %5u B, 8 warps x %d CTA/SM  %8.3f ms  %8.1f GB/s\n", batch, chunk, per_sm, ms, bytes / ms / 1e6);
+    }
   }
   for (uint32_t chunk : {8192u}) for (int warps : {8}) for (int per_sm : {1, 2}) {
     CK(cudaFuncSetAttribute(bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
