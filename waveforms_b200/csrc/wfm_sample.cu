@@ -1058,12 +1058,17 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 #ifndef WFM_K1_TILES_PER_WARP
 #define WFM_K1_TILES_PER_WARP 0
 #endif
+// 0: every warp of the persistent grid walks tiles w, w+G, ... (static); B >= 2 (power of two): batches of B
+// consecutive tiles are drawn from a device counter (dynamic balance across SMs)
+#ifndef WFM_K1_DYNAMIC
+#define WFM_K1_DYNAMIC 0
+#endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
 template <typename OutT, bool kAccumulate, int U>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
-                  OutT* __restrict__ out) {
+                  OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
   constexpr int V = OutVec<OutT>::N;
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
@@ -1086,8 +1091,31 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   const double* s_erf = &kErfTab[0][0];
 #endif
 
+#if WFM_K1_DYNAMIC
+  // tiles are handed out in aligned batches of kBatch consecutive tiles from a device counter
+  // (zeroed before the launch): warps on slower SMs simply take fewer batches.  nb = the batch
+  // this warp takes next (fetched one batch ahead, so the packet pipeline can look two tiles on)
+  constexpr int kBatch = WFM_K1_DYNAMIC;
+  static_assert(kBatch >= 2 && (kBatch & (kBatch - 1)) == 0, "batch: a power of two >= 2");
+  int t, nb;
+  {
+    unsigned int b0 = 0, b1 = 0;
+    if (lane == 0) {
+      b0 = atomicAdd(tile_counter, 2u * kBatch);  // two batches at once: the current and the next
+      b1 = b0 + kBatch;
+    }
+    t = tile_begin + (int)__shfl_sync(0xffffffffu, b0, 0);
+    nb = tile_begin + (int)__shfl_sync(0xffffffffu, b1, 0);
+  }
+#define K1_POS(tt) (((tt) - tile_begin) & (kBatch - 1))
+#define K1_NEXT1(tt) (K1_POS(tt) < kBatch - 1 ? (tt) + 1 : nb)
+#define K1_NEXT2(tt) (K1_POS(tt) < kBatch - 2 ? (tt) + 2 : (K1_POS(tt) == kBatch - 2 ? nb : nb + 1))
+#else
   const int n_warps = gridDim.x * kWarpsPerCta;
   int t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
+#define K1_NEXT1(tt) ((tt) + n_warps)
+#define K1_NEXT2(tt) ((tt) + 2 * n_warps)
+#endif
   if (t >= tile_end) return;
 
   if (lane == 0) {
@@ -1121,30 +1149,44 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       mbar_expect_tx(s_bar, (o1 - o0) * 16u);
       bulk_g2s(s_pkt, P.packets + (size_t)o0 * 16, (o1 - o0) * 16u, s_bar);
     }
-    if (t + n_warps < tile_end) {
-      off_next = P.pkt_off[t + n_warps];
-      end_next = P.pkt_off[t + n_warps + 1];
+    if (K1_NEXT1(t) < tile_end) {
+      off_next = P.pkt_off[K1_NEXT1(t)];
+      end_next = P.pkt_off[K1_NEXT1(t) + 1];
     }
   }
   uint32_t phases = 0;         // bit b: parity to wait for on buffer b
   int buf = 0;
   bool store_pending = false;  // lane 0: a bulk store may still be reading s_out
 
+  auto advance = [&]() {
+#if WFM_K1_DYNAMIC
+    // leaving the last tile of a batch: this warp moves into batch nb and draws the one after
+    const bool last = K1_POS(t) == kBatch - 1;
+    t = K1_NEXT1(t);
+    if (last) {
+      unsigned int b = 0;
+      if (lane == 0) b = atomicAdd(tile_counter, (unsigned int)kBatch);
+      nb = tile_begin + (int)__shfl_sync(0xffffffffu, b, 0);
+    }
+#else
+    t += n_warps;
+#endif
+  };
 #pragma unroll 1
-  for (; t < tile_end; t += n_warps) {
+  for (; t < tile_end; advance()) {
     const unsigned char* pk = s_pkt + (size_t)buf * P.pkt_cap;
     // prefetch: the next tile's packet into the other buffer (its previous tile is done:
     // every lane passed the __syncwarp that ends an iteration), the offsets of the tile after.
     // (Per-lane cp.async instead of the bulk copy was measured 5 % slower.)
-    if (t + n_warps < tile_end) {
+    if (K1_NEXT1(t) < tile_end) {
       if (lane == 0) {
         mbar_expect_tx(s_bar + (buf ^ 1), (end_next - off_next) * 16u);
         bulk_g2s(s_pkt + (size_t)(buf ^ 1) * P.pkt_cap, P.packets + (size_t)off_next * 16, (end_next - off_next) * 16u,
                  s_bar + (buf ^ 1));
       }
-      if (t + 2 * n_warps < tile_end) {
-        off_next = P.pkt_off[t + 2 * n_warps];
-        end_next = P.pkt_off[t + 2 * n_warps + 1];
+      if (K1_NEXT2(t) < tile_end) {
+        off_next = P.pkt_off[K1_NEXT2(t)];
+        end_next = P.pkt_off[K1_NEXT2(t) + 1];
       }
     }
     mbar_wait(s_bar + buf, (phases >> buf) & 1u);
@@ -1347,8 +1389,17 @@ static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles,
   static const int tiles_per_warp = [] { const char* v = getenv("WFM_K1_TILES_PER_WARP"); return v ? atoi(v) : WFM_K1_TILES_PER_WARP; }();
   if (tiles_per_warp > 0) cap = std::max<int64_t>(cap, (want + tiles_per_warp - 1) / tiles_per_warp);
   const unsigned grid = (unsigned)std::min<int64_t>(want, cap);
-  k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out);
-  return cudaGetLastError();
+  unsigned int* counter = nullptr;
+#if WFM_K1_DYNAMIC
+  if ((e = cudaMallocAsync(&counter, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+#endif
+  k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, counter);
+  e = cudaGetLastError();
+#if WFM_K1_DYNAMIC
+  cudaFreeAsync(counter, stream);
+#endif
+  return e;
 }
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
