@@ -1098,14 +1098,13 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   constexpr int kBatch = WFM_K1_DYNAMIC;
   static_assert(kBatch >= 2 && (kBatch & (kBatch - 1)) == 0, "batch: a power of two >= 2");
   int t, nb;
+  unsigned int fetch = 0;  // lane 0: the batch after nb, drawn one batch early so nobody waits for the atomic
   {
-    unsigned int b0 = 0, b1 = 0;
-    if (lane == 0) {
-      b0 = atomicAdd(tile_counter, 2u * kBatch);  // two batches at once: the current and the next
-      b1 = b0 + kBatch;
-    }
+    unsigned int b0 = 0;
+    if (lane == 0) b0 = atomicAdd(tile_counter, 2u * kBatch);  // two batches at once: the current and the next
     t = tile_begin + (int)__shfl_sync(0xffffffffu, b0, 0);
-    nb = tile_begin + (int)__shfl_sync(0xffffffffu, b1, 0);
+    nb = t + kBatch;
+    if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
   }
 #define K1_POS(tt) (((tt) - tile_begin) & (kBatch - 1))
 #define K1_NEXT1(tt) (K1_POS(tt) < kBatch - 1 ? (tt) + 1 : nb)
@@ -1154,9 +1153,9 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       end_next = P.pkt_off[K1_NEXT1(t) + 1];
     }
   }
-  uint32_t phases = 0;         // bit b: parity to wait for on buffer b
-  int buf = 0;
-  bool store_pending = false;  // lane 0: a bulk store may still be reading s_out
+  // it = tiles this warp has started: packet buffer it & 1, whose mbarrier completes its (it >> 1)-th phase
+  uint32_t it = 0;
+#define buf ((int)(it & 1u))
 
   auto advance = [&]() {
 #if WFM_K1_DYNAMIC
@@ -1164,9 +1163,8 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     const bool last = K1_POS(t) == kBatch - 1;
     t = K1_NEXT1(t);
     if (last) {
-      unsigned int b = 0;
-      if (lane == 0) b = atomicAdd(tile_counter, (unsigned int)kBatch);
-      nb = tile_begin + (int)__shfl_sync(0xffffffffu, b, 0);
+      nb = tile_begin + (int)__shfl_sync(0xffffffffu, fetch, 0);
+      if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
     }
 #else
     t += n_warps;
@@ -1189,8 +1187,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
         end_next = P.pkt_off[K1_NEXT2(t) + 1];
       }
     }
-    mbar_wait(s_bar + buf, (phases >> buf) & 1u);
-    phases ^= 1u << buf;
+    mbar_wait(s_bar + buf, (it >> 1) & 1u);
 
     const PacketHeader* __restrict__ h = reinterpret_cast<const PacketHeader*>(pk);
     const int cnt = h->cnt;
@@ -1202,12 +1199,12 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     if (flags & kPacketCold) {
       sample_tile_cold<OutT, kAccumulate>(P, tiles[t], dst, lane);
       __syncwarp();
-      buf ^= 1;
+      ++it;
       continue;
     }
 
     // the previous tile's bulk store must have finished READING the tile buffer
-    if (lane == 0 && store_pending) bulk_wait_read_all();
+    if (lane == 0) bulk_wait_read_all();  // returns at once when no store is outstanding
     __syncwarp();
 
     // base fill: the whole tile BUFFER (tile_samples, a multiple of 128) <- the zero-segment
@@ -1284,14 +1281,14 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       const int n_bulk = cnt & ~(V - 1);  // 16-byte multiple; the ragged tail goes out as scalars
       if (lane == 0 && n_bulk > 0) {
         bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT), l2_evict_first_policy());
-        store_pending = true;
       }
       if (n_bulk + lane < cnt) dst[n_bulk + lane] = s_out[n_bulk + lane];
     }
     __syncwarp();  // all reads of the packet and of the tail of s_out are done
-    buf ^= 1;
+    ++it;
   }
-  if (lane == 0 && store_pending) bulk_wait_read_all();  // shared memory must outlive the copy's reads
+  if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the copy's reads
+#undef buf
 }
 
 // complex128 output: the real and the imaginary PLANE are sampled by the real-valued kernel
