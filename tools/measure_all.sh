@@ -9,6 +9,8 @@ python bench.py > $o/${tag}_bench_cfg2.json 2> $o/${tag}_bench.err; tail -c 1500
 python bench.py --impl reference --steps 5 --warmup 3 > $o/${tag}_bench_cfg2_reference_arm.json 2>> $o/${tag}_bench.err
 python bench.py --dtype f32 --no-cpu --no-e2e > $o/${tag}_bench_cfg2_f32.json 2>> $o/${tag}_bench.err
 python tools/bench_configs.py --only cfg3,cfg3v,cfg4,cfg5 > $o/${tag}_k1_other_configs.json 2> $o/${tag}_configs.err
+# config 3 at FULL size on one GPU, every channel distinct (vectorised builder): 8192 outputs, 8.2 M pulses
+python tools/bench_configs.py --only cfg3v --cfg3v-channels 4096 > $o/${tag}_cfg3_full_builder.json 2>> $o/${tag}_configs.err
 python tools/bench_dsp.py --cpu > $o/${tag}_dsp_cfg4.json 2> $o/${tag}_dsp.err
 # launch lists (cold-cache, serialised: shares of the step, not absolute times)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches_cfg2.csv \

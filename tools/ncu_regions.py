@@ -13,7 +13,7 @@ def find(marker, start=0):
 marks = [('eval: head', 'Val<U> eval_unit('), ('eval: sincos rows', 'for (int i = 0; i < n_sc; ++i)'), ('eval: rot rows', 'for (int j = 0; j < n_child; ++j)'),
          ('eval: generic rows', '// -- every other basis function'), ('eval: terms', '  // -- terms'), ('eval: end', '// ---- pre-pass (once per program)')]
 k0 = find('sample_kernel(const __grid_constant__')
-marks2 = [('kernel: setup', 'sample_kernel(const __grid_constant__'), ('tile: prefetch + packet wait', '  for (; t < tile_end; t += n_warps) {'),
+marks2 = [('kernel: setup', 'sample_kernel(const __grid_constant__'), ('tile: prefetch + packet wait', '  for (; t < tile_end; advance()) {'),
           ('tile: header', 'const PacketHeader* __restrict__ h'), ('tile: wait store read', "// the previous tile's bulk store must have finished"),
           ('tile: fill', '// base fill'), ('tile: patches', '// ---- flat segments with their own value'),
           ('tile: unit loop', "// ---- the tile's ACTIVE samples"), ('tile: store', '    // ---- store ---'), ('kernel: end', '// complex128 output')]
