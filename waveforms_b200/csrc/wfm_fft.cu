@@ -201,12 +201,18 @@ __device__ __forceinline__ void dft_small<25>(double2 (&v)[25], double sgn) {
 // multiplies by the response on the way to shared memory), so loading, filtering and storing
 // cost no passes of their own over shared memory — the shared-memory data pipe is what
 // bounds these kernels (ncu: 75 % of its peak, profiles/r1o_k3_ncu_details.txt).
+// accessors that have no inter-pass twiddle carry this no-op (a member, so they stay aggregates)
+#define WFM_NO_RUN_TWIDDLE \
+  template <int R>         \
+  __device__ __forceinline__ void twiddle_run(double2 (&)[R], int, int, int) const {}
 struct SmemIn {
+  WFM_NO_RUN_TWIDDLE
   const double2* a;
   int logc;
   __device__ __forceinline__ double2 operator()(int p, int c) const { return a[(p << logc) + c]; }
 };
 struct SmemOut {
+  WFM_NO_RUN_TWIDDLE
   double2* b;
   int logc;
   __device__ __forceinline__ void operator()(int p, int c, double2 v) const { b[(p << logc) + c] = v; }
@@ -243,6 +249,7 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
     double2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = in(j + r * nb, c);
+    in.template twiddle_run<R>(v, j, nb, c);  // inter-pass twiddles of the run j, j+nb, ... (column passes)
     if (k > 0) {
       double2 w[R];
       load_twiddles<R>(w, tw, k * tstep, sgn);
@@ -251,6 +258,8 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
     }
     dft_small<R>(v, sgn);
     const int j0 = q * Ns * R + k;
+#pragma unroll
+    out.template twiddle_run<R>(v, j0, Ns, c);
 #pragma unroll
     for (int r = 0; r < R; ++r) out(j0 + r * Ns, c, v[r]);
   }
@@ -343,12 +352,14 @@ extern __shared__ __align__(16) unsigned char fft_smem_raw[];
 // One CTA per PAIR of real signals: z = x_a + i x_b goes through one complex transform.  H is
 // the Hermitian part of the caller's response (hermitian_part_kernel), so ifft(fft(z) H) =
 // y_a + i y_b with both real.
-struct PairIn {  // two real signals -> one complex
+struct PairIn {
+  WFM_NO_RUN_TWIDDLE  // two real signals -> one complex
   const double* xa;
   const double* xb;  // nullptr: odd tail
   __device__ __forceinline__ double2 operator()(int p, int) const { return make_double2(xa[p], xb ? xb[p] : 0.0); }
 };
 struct PairOut {
+  WFM_NO_RUN_TWIDDLE
   double* ya;
   double* yb;
   double scale;
@@ -357,7 +368,8 @@ struct PairOut {
     if (yb) yb[p] = v.y * scale;
   }
 };
-struct MulHOut {  // spectrum x response on the way to shared memory
+struct MulHOut {
+  WFM_NO_RUN_TWIDDLE  // spectrum x response on the way to shared memory
   double2* z;
   const double2* __restrict__ H;
   __device__ __forceinline__ void operator()(int p, int, double2 v) const { z[p] = cmul(v, __ldg(H + p)); }
@@ -410,9 +422,21 @@ struct ColsIn {
       } else {
         v = static_cast<const double2*>(pa)[idx];
       }
-      if (kTwBefore) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
     }
     return v;
+  }
+  // rows r0, r0+step, ... of column c0+c: W^(col r0) (W^(col step))^q — two table look-ups per run
+  // instead of one per element (the look-ups were 2/3 of the L1 sectors of the column passes)
+  template <int R>
+  __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
+    if (!kTwBefore || c >= cw) return;
+    double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
+    const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      v[q] = cmul(v[q], w);
+      if (q + 1 < R) w = cmul(w, ws);
+    }
   }
 };
 template <bool kTwAfter, bool kRealOut>
@@ -422,10 +446,20 @@ struct ColsOut {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn, scale;
+  template <int R>
+  __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
+    if (!kTwAfter || c >= cw) return;
+    double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
+    const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      v[q] = cmul(v[q], w);
+      if (q + 1 < R) w = cmul(w, ws);
+    }
+  }
   __device__ __forceinline__ void operator()(int r, int c, double2 v) const {
     if (c >= cw) return;
     const int64_t idx = (int64_t)r * N2 + c0 + c;
-    if (kTwAfter) v = cmul(v, big_twiddle(T, (int64_t)r * (c0 + c), sgn));
     if (kRealOut) {
       static_cast<double*>(pa)[idx] = v.x * scale;
       if (pb) static_cast<double*>(pb)[idx] = v.y * scale;
@@ -479,6 +513,7 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kerne
 #define WFM_FFT_ROWS_LOGC 2
 #endif
 struct RowsIn {
+  WFM_NO_RUN_TWIDDLE
   const double2* rows;  // first row of the tile
   int N2, rw;
   __device__ __forceinline__ double2 operator()(int p, int c) const {
@@ -486,6 +521,7 @@ struct RowsIn {
   }
 };
 struct RowsOut {
+  WFM_NO_RUN_TWIDDLE
   double2* rows;
   int N2, rw;
   __device__ __forceinline__ void operator()(int p, int c, double2 v) const {
@@ -493,6 +529,7 @@ struct RowsOut {
   }
 };
 struct RowsMulHOut {
+  WFM_NO_RUN_TWIDDLE
   double2* z;
   const double2* __restrict__ hrows;  // Hp at the tile's first row
   int N2, rw, logc;
@@ -501,7 +538,8 @@ struct RowsMulHOut {
     z[(p << logc) + c] = v;
   }
 };
-struct NaturalOut {  // X[k1 + N1*k2]: for fixed k2 the C rows of the tile are adjacent
+struct NaturalOut {
+  WFM_NO_RUN_TWIDDLE  // X[k1 + N1*k2]: for fixed k2 the C rows of the tile are adjacent
   double2* o;
   int N1, rw;
   double scale;
@@ -533,10 +571,12 @@ __global__ void __launch_bounds__(kFftThreads, WFM_FFT_ROWS_MINB) fft_rows_kerne
 
 // ---- one-level plain c2c ------------------------------------------------------------
 struct PlainIn {
+  WFM_NO_RUN_TWIDDLE
   const double2* d;
   __device__ __forceinline__ double2 operator()(int p, int) const { return d[p]; }
 };
 struct PlainOut {
+  WFM_NO_RUN_TWIDDLE
   double2* d;
   double scale;
   __device__ __forceinline__ void operator()(int p, int, double2 v) const { d[p] = cscale(v, scale); }
