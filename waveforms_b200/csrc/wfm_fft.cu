@@ -49,6 +49,16 @@ namespace wfm {
 #define WFM_FFT_THREADS 512
 #endif
 constexpr int kFftThreads = WFM_FFT_THREADS;
+// the row pass has the radix-10 stage: 320 threads x 2 CTAs leave it 102 registers (no spills) and match the 320
+// radix-8 / 256 radix-10 butterflies of a 640-point x 4 tile (measured 512 / 448 / 384 / 320: 2.27 / 2.21 / 2.20 / 2.19 ms)
+#ifndef WFM_FFT_ROWS_THREADS
+#define WFM_FFT_ROWS_THREADS 320
+#endif
+constexpr int kFftRowsThreads = WFM_FFT_ROWS_THREADS;
+#ifndef WFM_FFT_COLS_THREADS
+#define WFM_FFT_COLS_THREADS WFM_FFT_THREADS
+#endif
+constexpr int kFftColsThreads = WFM_FFT_COLS_THREADS;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
 constexpr int kSmemBudget = 227 * 1024 - 1024;
@@ -258,7 +268,6 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
     }
     dft_small<R>(v, sgn);
     const int j0 = q * Ns * R + k;
-#pragma unroll
     out.template twiddle_run<R>(v, j0, Ns, c);
 #pragma unroll
     for (int r = 0; r < R; ++r) out(j0 + r * Ns, c, v[r]);
@@ -469,7 +478,7 @@ struct ColsOut {
   }
 };
 template <bool kTwAfter, bool kRealIn, bool kRealOut>
-__global__ void __launch_bounds__(kFftThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
+__global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
                                                                const void* __restrict__ in, void* __restrict__ out,
                                                                int64_t in_stride, int64_t out_stride, double sgn,
                                                                double scale, int64_t n_real) {
@@ -548,7 +557,7 @@ struct NaturalOut {
   }
 };
 template <bool kFilter>
-__global__ void __launch_bounds__(kFftThreads, WFM_FFT_ROWS_MINB) fft_rows_kernel(FftPlan P, int N1, int logc, double2* __restrict__ data,
+__global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_kernel(FftPlan P, int N1, int logc, double2* __restrict__ data,
                                                                double2* __restrict__ out, int64_t stride,
                                                                int64_t out_stride, const double2* __restrict__ Hp,
                                                                double sgn, double scale) {
@@ -863,10 +872,10 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   const int C1 = 1 << lc1, C2 = 1 << lc2;
   dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
   if ((e = set_smem(fft_cols_kernel<true, false, false>, smem1)) != cudaSuccess) goto done;
-  fft_cols_kernel<true, false, false><<<g1, kFftThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0, 0);
+  fft_cols_kernel<true, false, false><<<g1, kFftColsThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0, 0);
   if ((e = cudaGetLastError()) != cudaSuccess) goto done;
   if ((e = set_smem(fft_rows_kernel<false>, smem2)) != cudaSuccess) goto done;
-  fft_rows_kernel<false><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, data, n, stride, nullptr, sgn, scale);
+  fft_rows_kernel<false><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, data, n, stride, nullptr, sgn, scale);
   e = cudaGetLastError();
 done:
   cudaFreeAsync(scratch, st);
@@ -1025,10 +1034,10 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
     if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
     if (e == cudaSuccess) {
       permute_h_kernel<<<gH, T, 0, st>>>(dH, dHp, N1, N2);
-      fft_cols_kernel<true, true, false><<<g1, kFftThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, stride, n, -1.0, 1.0,
+      fft_cols_kernel<true, true, false><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, stride, n, -1.0, 1.0,
                                                                          n_sig);
-      fft_rows_kernel<true><<<g2, kFftThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, dHp, -1.0, 1.0);
-      fft_cols_kernel<false, false, true><<<g1, kFftThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, stride, +1.0,
+      fft_rows_kernel<true><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, dHp, -1.0, 1.0);
+      fft_cols_kernel<false, false, true><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, stride, +1.0,
                                                                           1.0 / (double)n, n_sig);
       e = cudaGetLastError();
     }
