@@ -219,7 +219,8 @@ int  wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na,
  * HOST interleaved complex [n]; arbitrary n.  x, y DEVICE f64 (may alias; signal s
  * of y starts at y + s*stride).  Only the Hermitian part of H contributes to the
  * real part, so signals 2p and 2p+1 share one complex transform (real / imaginary
- * part): a signal's rounding error scales with the larger of its pair. */
+ * part): a signal's rounding error scales with the larger of its pair, and a
+ * non-finite sample in one signal reaches its partner's output too. */
 int  wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n,
                     int64_t stride, const double* H, void* stream);
 
