@@ -305,3 +305,42 @@ def test_both_unit_sizes(name, unit, golden, monkeypatch):
         from waveforms_b200 import sample_batch
         f32 = sample_batch([b200_object(rec)], dtype=np.float32).numpy()[0]
         assert rel_err(f32.astype(np.float64), rec['expect']) <= FP32_TOL
+
+
+@pytest.mark.parametrize('name', ['readme_x_sample', 'cfg2_xy_stack', 'cfg2_z', 'cfg3_rb_I', 'cfg4_flux', 'cfg5_drag_sin',
+                                  'complex_amp', 'boundary_hits'])
+def test_dynamic_deal_equals_static_deal(name, golden, monkeypatch):
+    """WFM_K1_DEAL=dynamic hands the tiles out in batches from a device counter instead of the
+    static round-robin: which warp computes a tile must not change a single bit of it."""
+    if name not in golden:
+        pytest.skip('case not in the golden set')
+    rec = golden[name]
+    monkeypatch.setenv('WFM_K1_DEAL', 'static')
+    static = b200_eval(rec)
+    monkeypatch.setenv('WFM_K1_DEAL', 'dynamic')
+    dynamic = b200_eval(rec)
+    assert np.array_equal(static, dynamic)
+    assert rel_err(dynamic, rec['expect']) <= FP64_TOL
+
+
+def test_dynamic_deal_many_tiles_and_subranges(ns, monkeypatch):
+    """A batch with thousands of tiles of uneven work, whole and as channel sub-ranges (tile_begin
+    not a multiple of the batch size): both deals agree bit for bit."""
+    from waveforms_b200 import sample_batch
+    rng = np.random.default_rng(99)
+    chans = []
+    for k in range(37):
+        w = ns.zero()
+        for j in range(int(rng.integers(0, 6))):
+            w = w + rng.uniform(-1, 1) * (ns.gaussian(40e-9) >> float(rng.uniform(1e-6, 60e-6)))
+        w.start, w.stop, w.sample_rate = 0.0, float(rng.uniform(20e-6, 70e-6)), 2e9
+        chans.append(w)
+    monkeypatch.setenv('WFM_K1_DEAL', 'static')
+    want = sample_batch(chans).numpy()
+    monkeypatch.setenv('WFM_K1_DEAL', 'dynamic')
+    got = sample_batch(chans).numpy()
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    part = sample_batch(chans[5:19]).numpy()
+    for a, b in zip(part, want[5:19]):
+        assert np.array_equal(a, b)

@@ -44,6 +44,7 @@
 //
 // Algorithmic traffic: 8 B (4 B) per sample, write-only.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <cstdlib>
 #include <stdint.h>
 #include <algorithm>
@@ -1058,14 +1059,13 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 #ifndef WFM_K1_TILES_PER_WARP
 #define WFM_K1_TILES_PER_WARP 0
 #endif
-// 0: every warp of the persistent grid walks tiles w, w+G, ... (static); B >= 2 (power of two): batches of B
-// consecutive tiles are drawn from a device counter (dynamic balance across SMs)
+// batch size of the dynamic deal (WFM_K1_DEAL=dynamic at run time; the default deal is static)
 #ifndef WFM_K1_DYNAMIC
-#define WFM_K1_DYNAMIC 0
+#define WFM_K1_DYNAMIC 4
 #endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
-template <typename OutT, bool kAccumulate, int U>
+template <typename OutT, bool kAccumulate, int U, int kBatch>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
                   OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
@@ -1091,30 +1091,36 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   const double* s_erf = &kErfTab[0][0];
 #endif
 
-#if WFM_K1_DYNAMIC
-  // tiles are handed out in aligned batches of kBatch consecutive tiles from a device counter
-  // (zeroed before the launch): warps on slower SMs simply take fewer batches.  nb = the batch
-  // this warp takes next (fetched one batch ahead, so the packet pipeline can look two tiles on)
-  constexpr int kBatch = WFM_K1_DYNAMIC;
-  static_assert(kBatch >= 2 && (kBatch & (kBatch - 1)) == 0, "batch: a power of two >= 2");
-  int t, nb;
-  unsigned int fetch = 0;  // lane 0: the batch after nb, drawn one batch early so nobody waits for the atomic
-  {
+  // kBatch == 0: the static deal, warp w of the persistent grid walks tiles w, w+G, ...
+  // kBatch >= 2: the dynamic deal, tiles are handed out in aligned batches of kBatch consecutive tiles from a device
+  // counter (zeroed before the launch): warps on slower SMs simply take fewer batches.  nb = the batch this warp takes
+  // next; the one after is drawn one batch early by lane 0 (fetch), so nobody waits for the atomic's round trip and
+  // the packet pipeline can still look two tiles on
+  static_assert(kBatch == 0 || (kBatch >= 2 && (kBatch & (kBatch - 1)) == 0), "batch: 0 or a power of two >= 2");
+  const int n_warps = gridDim.x * kWarpsPerCta;
+  int t, nb = 0;
+  unsigned int fetch = 0;
+  if constexpr (kBatch > 0) {
     unsigned int b0 = 0;
     if (lane == 0) b0 = atomicAdd(tile_counter, 2u * kBatch);  // two batches at once: the current and the next
     t = tile_begin + (int)__shfl_sync(0xffffffffu, b0, 0);
     nb = t + kBatch;
     if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
+  } else {
+    t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
   }
-#define K1_POS(tt) (((tt) - tile_begin) & (kBatch - 1))
-#define K1_NEXT1(tt) (K1_POS(tt) < kBatch - 1 ? (tt) + 1 : nb)
-#define K1_NEXT2(tt) (K1_POS(tt) < kBatch - 2 ? (tt) + 2 : (K1_POS(tt) == kBatch - 2 ? nb : nb + 1))
-#else
-  const int n_warps = gridDim.x * kWarpsPerCta;
-  int t = tile_begin + blockIdx.x * kWarpsPerCta + warp_in_cta;
-#define K1_NEXT1(tt) ((tt) + n_warps)
-#define K1_NEXT2(tt) ((tt) + 2 * n_warps)
-#endif
+  auto next1 = [&](int tt) -> int {
+    if constexpr (kBatch > 0) return (((tt) - tile_begin) & (kBatch - 1)) < kBatch - 1 ? tt + 1 : nb;
+    else return tt + n_warps;
+  };
+  auto next2 = [&](int tt) -> int {
+    if constexpr (kBatch > 0) {
+      const int pos = (tt - tile_begin) & (kBatch - 1);
+      return pos < kBatch - 2 ? tt + 2 : (pos == kBatch - 2 ? nb : nb + 1);
+    } else {
+      return tt + 2 * n_warps;
+    }
+  };
   if (t >= tile_end) return;
 
   if (lane == 0) {
@@ -1148,9 +1154,9 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       mbar_expect_tx(s_bar, (o1 - o0) * 16u);
       bulk_g2s(s_pkt, P.packets + (size_t)o0 * 16, (o1 - o0) * 16u, s_bar);
     }
-    if (K1_NEXT1(t) < tile_end) {
-      off_next = P.pkt_off[K1_NEXT1(t)];
-      end_next = P.pkt_off[K1_NEXT1(t) + 1];
+    if (next1(t) < tile_end) {
+      off_next = P.pkt_off[next1(t)];
+      end_next = P.pkt_off[next1(t) + 1];
     }
   }
   // it = tiles this warp has started: packet buffer it & 1, whose mbarrier completes its (it >> 1)-th phase
@@ -1158,17 +1164,17 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
 #define buf ((int)(it & 1u))
 
   auto advance = [&]() {
-#if WFM_K1_DYNAMIC
-    // leaving the last tile of a batch: this warp moves into batch nb and draws the one after
-    const bool last = K1_POS(t) == kBatch - 1;
-    t = K1_NEXT1(t);
-    if (last) {
-      nb = tile_begin + (int)__shfl_sync(0xffffffffu, fetch, 0);
-      if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
+    if constexpr (kBatch > 0) {
+      // leaving the last tile of a batch: this warp moves into batch nb and draws the one after the next
+      const bool last = ((t - tile_begin) & (kBatch - 1)) == kBatch - 1;
+      t = next1(t);
+      if (last) {
+        nb = tile_begin + (int)__shfl_sync(0xffffffffu, fetch, 0);
+        if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
+      }
+    } else {
+      t += n_warps;
     }
-#else
-    t += n_warps;
-#endif
   };
 #pragma unroll 1
   for (; t < tile_end; advance()) {
@@ -1176,15 +1182,15 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     // prefetch: the next tile's packet into the other buffer (its previous tile is done:
     // every lane passed the __syncwarp that ends an iteration), the offsets of the tile after.
     // (Per-lane cp.async instead of the bulk copy was measured 5 % slower.)
-    if (K1_NEXT1(t) < tile_end) {
+    if (next1(t) < tile_end) {
       if (lane == 0) {
         mbar_expect_tx(s_bar + (buf ^ 1), (end_next - off_next) * 16u);
         bulk_g2s(s_pkt + (size_t)(buf ^ 1) * P.pkt_cap, P.packets + (size_t)off_next * 16, (end_next - off_next) * 16u,
                  s_bar + (buf ^ 1));
       }
-      if (K1_NEXT2(t) < tile_end) {
-        off_next = P.pkt_off[K1_NEXT2(t)];
-        end_next = P.pkt_off[K1_NEXT2(t) + 1];
+      if (next2(t) < tile_end) {
+        off_next = P.pkt_off[next2(t)];
+        end_next = P.pkt_off[next2(t) + 1];
       }
     }
     mbar_wait(s_bar + buf, (it >> 1) & 1u);
@@ -1369,10 +1375,34 @@ size_t sample_smem_bytes(const DevProgram& P, int dtype) {
   return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.unit, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
 }
 
-template <typename OutT, bool kAcc, int U>
-static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
-                                     int dtype, void* out, cudaStream_t stream) {
-  auto k = sample_kernel<OutT, kAcc, U>;
+// tile counters of the dynamic deal: one ring per device, never freed
+constexpr int kCounterSlots = 1024;
+struct CounterRing {
+  unsigned int* counters = nullptr;
+  cudaEvent_t used[kCounterSlots] = {};
+  int next = 0;
+  std::mutex mu;
+};
+static CounterRing* counter_ring(int dev) {
+  static std::mutex mu;
+  static CounterRing* rings[64] = {};
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!rings[dev]) {
+    CounterRing* r = new CounterRing;
+    if (cudaMalloc(&r->counters, sizeof(unsigned int) * kCounterSlots) != cudaSuccess) {
+      delete r;
+      return nullptr;
+    }
+    rings[dev] = r;
+  }
+  return rings[dev];
+}
+
+template <typename OutT, bool kAcc, int U, int kBatch>
+static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                               int dtype, void* out, cudaStream_t stream) {
+  auto k = sample_kernel<OutT, kAcc, U, kBatch>;
   const size_t smem = sample_smem_bytes(P, dtype);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1386,17 +1416,47 @@ static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles,
   static const int tiles_per_warp = [] { const char* v = getenv("WFM_K1_TILES_PER_WARP"); return v ? atoi(v) : WFM_K1_TILES_PER_WARP; }();
   if (tiles_per_warp > 0) cap = std::max<int64_t>(cap, (want + tiles_per_warp - 1) / tiles_per_warp);
   const unsigned grid = (unsigned)std::min<int64_t>(want, cap);
-  unsigned int* counter = nullptr;
-#if WFM_K1_DYNAMIC
-  if ((e = cudaMallocAsync(&counter, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+  if (kBatch == 0) {
+    k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, nullptr);
+    return cudaGetLastError();
+  }
+  // the tile counter of this launch: the next slot of a per-device ring (allocated once), zeroed on the launch's
+  // stream; the slot's event makes a launch that comes kCounterSlots launches later wait for this one
+  CounterRing* ring = counter_ring(dev);
+  if (!ring) return cudaErrorMemoryAllocation;
+  int slot;
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(ring->mu);
+    slot = ring->next;
+    ring->next = (ring->next + 1) % kCounterSlots;
+    if (!ring->used[slot]) {
+      if ((e = cudaEventCreateWithFlags(&ring->used[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
+    } else if ((e = cudaStreamWaitEvent(stream, ring->used[slot], 0)) != cudaSuccess) {
+      return e;
+    }
+    ev = ring->used[slot];
+  }
+  unsigned int* counter = ring->counters + slot;
   if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-#endif
   k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, counter);
-  e = cudaGetLastError();
-#if WFM_K1_DYNAMIC
-  cudaFreeAsync(counter, stream);
-#endif
-  return e;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return cudaEventRecord(ev, stream);
+}
+
+// The deal of a launch.  Dynamic (batches of WFM_K1_DYNAMIC tiles drawn from a counter) is the default whenever the warps
+// have several batches each to draw: measured +7..10 % on near-pure-store programs (cfg4) and on very uneven tiles (cfg5),
+// +2 % on dense cfg3, +-1 % on the control frames (cfg2); small launches keep the static deal (no counter to
+// allocate and zero).  WFM_K1_DEAL=static|dynamic overrides.
+template <typename OutT, bool kAcc, int U>
+static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                                     int dtype, void* out, cudaStream_t stream) {
+  const char* deal = getenv("WFM_K1_DEAL");
+  bool dynamic = n_tiles >= (int64_t)16 * 1024;  // >= ~7 tiles per warp of a full persistent grid
+  if (deal && deal[0] == 'd') dynamic = true;
+  if (deal && deal[0] == 's') dynamic = false;
+  if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  return launch_deal<OutT, kAcc, U, 0>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 }
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
