@@ -1452,7 +1452,9 @@ template <typename OutT, bool kAcc, int U>
 static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                      int dtype, void* out, cudaStream_t stream) {
   const char* deal = getenv("WFM_K1_DEAL");
-  bool dynamic = n_tiles >= (int64_t)16 * 1024;  // >= ~7 tiles per warp of a full persistent grid
+  // >= ~7 tiles per warp of a full persistent grid; fp32 output keeps the static deal (its tiles are half as long, the
+  // counter traffic doubles: 856 static against 811-822 GSa/s dynamic on cfg2)
+  bool dynamic = n_tiles >= (int64_t)16 * 1024 && sizeof(OutT) == 8;
   if (deal && deal[0] == 'd') dynamic = true;
   if (deal && deal[0] == 's') dynamic = false;
   if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
