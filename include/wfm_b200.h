@@ -234,6 +234,14 @@ int  wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n,
 int  wfm_fft_c2c(double* data, int64_t n_sig, int64_t n, int64_t stride,
                  int32_t sign, void* stream);
 
+/* ---- calibrations (diagnostics: what bench.py quotes its rooflines against) ----
+ * wfm_calibrate_fp64: out[0] = fp64 FMA lane-operations per second of the current device
+ * (8 independent chains per thread, best of `reps` launches on `stream`), out[1] = ms of one launch.
+ * wfm_calibrate_copy: pinned cudaMemcpyAsync ceiling of the current device, dir 0 = device->host,
+ * 1 = host->device: out[0] = best GB/s of one copy of `bytes`, out[1] = GB/s over `reps` copies. */
+int  wfm_calibrate_fp64(double* out, int32_t reps, void* stream);
+int  wfm_calibrate_copy(int64_t bytes, int32_t dir, int32_t reps, double* out);
+
 #ifdef __cplusplus
 }
 #endif

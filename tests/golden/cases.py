@@ -262,6 +262,42 @@ def complex_exp(ns):
 
 
 @case
+def stack_complex_amp(ns):
+    # a stack accumulates in complex128 and returns the REAL part (waveform.py:681-693)
+    t = np.linspace(-3, 3, 1201)
+    wl = [(0.5 + 0.25j) * ns.cosPulse(1.5), 1j * (ns.gaussian(1.0) >> 0.7),
+          (ns.cos(7.0) * ns.square(2.0)) >> -0.5]
+    w = ns.WaveVStack(wl) + 0.125
+    return w, ('explicit', t)
+
+
+@case
+def complex_zero_imag(ns):
+    # (1j*1j) * w: amplitude (-1+0j) -> the reference returns complex128 with a zero imaginary part
+    t = np.linspace(-2, 2, 801)
+    w = (1j * 1j) * (ns.cos(5.0) * ns.square(2.0))
+    return w, ('explicit', t)
+
+
+@case
+def complex_unsampled(ns):
+    # the only complex segment lies outside the sampled range -> float64 output
+    t = np.linspace(-2, 2, 801)
+    w = ns.gaussian(1.0) + 1j * (ns.square(1.0) >> 10)
+    return w, ('explicit', t)
+
+
+@case
+def filters_complex(ns):
+    # sample-time IIR of a complex channel: scipy filters both planes
+    from scipy.signal import butter, tf2sos
+    b, a = butter(2, 40.0, 'lowpass', fs=1000)
+    w = (1 + 0.5j) * (ns.square(0.8) >> 0.1) + 0.25
+    w.filters = (tf2sos(b, a), 0.25)
+    return _sampled(w, -1, 1, 1000)
+
+
+@case
 def boundary_hits(ns):
     # abscissae that coincide exactly with segment bounds: half-open [lo, hi)
     t = np.arange(-8, 9) * 0.25

@@ -77,25 +77,55 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     items = [channel_grid(w, sample_rate) for w in waveforms]
     if devices is None:
         devices = [torch.cuda.current_device()]
+    np_dtype = np.dtype(dtype)
     code = {np.dtype(np.float64): engine.WFM_F64,
             np.dtype(np.float32): engine.WFM_F32,
-            np.dtype(np.complex128): engine.WFM_C128}[np.dtype(dtype)]
+            np.dtype(np.complex128): engine.WFM_C128}[np_dtype]
+    filtered = filters == 'own' and any(w.filters is not None for w in waveforms)
+    if filtered and code == engine.WFM_C128:
+        raise TypeError('sample_batch(filters=\'own\') filters real channels; sample complex '
+                        'channels one by one (Waveform.sample) or pass filters=None')
+    # the IIR runs on float64 samples: an fp32 batch with filters is sampled and filtered in
+    # float64 and cast at the end
+    run_code = engine.WFM_F64 if (filtered and code == engine.WFM_F32) else code
     ranges = shard_ranges([g.n for _, g in items], len(devices))
-    tensors, table = [], []
-    for slot, (dev, (lo, hi)) in enumerate(zip(devices, ranges)):
-        batch = lower(items[lo:hi])
+    shards = [(dev, lo, hi, lower(items[lo:hi])) for dev, (lo, hi) in zip(devices, ranges)]
+
+    def run(shard):
+        # one host thread per device: upload, pre-pass, K1 and the filters of every device run
+        # concurrently; nothing here waits for another device
+        dev, lo, hi, batch = shard
         with torch.cuda.device(dev):
             prog = engine.Program(batch, dev)
-            out = prog.sample_device(dtype=code)
-            if filters == 'own':
+            out = prog.sample_device(dtype=run_code)
+            if filtered:
                 from .dsp import apply_channel_filters
                 apply_channel_filters(out, batch, waveforms[lo:hi], mode=iir_mode)
-            prog.close()
+            if run_code != code:
+                out = out.to(torch.float32)
+        return prog, out
+
+    results = _run_shards(run, shards)
+    tensors, table = [], []
+    for slot, ((dev, lo, hi, batch), (prog, out)) in enumerate(zip(shards, results)):
         tensors.append(out)
         for k in range(hi - lo):
             table.append((slot, int(batch.waves['out_off'][k]),
                           int(batch.waves['n'][k])))
+    for prog, _ in results:  # destroy waits for the program's last launch: only after ALL devices were launched
+        prog.close()
     return BatchResult(tensors, table, dtype)
+
+
+def _run_shards(fn, shards):
+    """fn(shard) for every shard: inline for one device, one host thread per device
+    otherwise (ctypes releases the GIL inside the library, so uploads, pre-passes and
+    launches of different devices overlap)."""
+    if len(shards) <= 1:
+        return [fn(s) for s in shards]
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(max_workers=len(shards)) as pool:
+        return list(pool.map(fn, shards))
 
 
 def from_wire(record, kind=None):
@@ -141,19 +171,27 @@ def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
             np.dtype(np.float32): engine.WFM_F32,
             np.dtype(np.complex128): engine.WFM_C128}[np.dtype(dtype)]
     ranges = shard_ranges([max(len(r), 1) for r in t0], len(devices))
-    tensors, table = [], []
-    for slot, (dev, (lo, hi)) in enumerate(zip(devices, ranges)):
+    shards = [(dev, lo, hi) for dev, (lo, hi) in zip(devices, ranges)]
+
+    def run(shard):
+        dev, lo, hi = shard
         batch = pulse_train_batch(templates, tmpl_idx[lo:hi], t0[lo:hi], start, stop,
                                   sample_rate,
                                   params={k: v[lo:hi] for k, v in (params or {}).items()})
         with torch.cuda.device(dev):
             prog = engine.Program(batch, dev)
             out = prog.sample_device(dtype=code)
-            prog.close()
+        return prog, out, batch
+
+    results = _run_shards(run, shards)
+    tensors, table = [], []
+    for slot, ((dev, lo, hi), (prog, out, batch)) in enumerate(zip(shards, results)):
         tensors.append(out)
         for k in range(hi - lo):
             table.append((slot, int(batch.waves['out_off'][k]),
                           int(batch.waves['n'][k])))
+    for prog, _, _ in results:
+        prog.close()
     return BatchResult(tensors, table, dtype)
 
 

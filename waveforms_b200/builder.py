@@ -207,7 +207,8 @@ class PulseTemplate:
             base, base_term = pools.n_fac, pools.n_term
             plain = (tuple((tuple((*f[:-1], float(f[-1])) for f in factors), expo) for factors, expo in s[0]),
                      tuple(float(v) if isinstance(v, Sym) else v for v in s[1]))
-            cplx = _lower_segment(pools, [plain]) or cplx
+            # channels built here are stacks: WaveVStack returns the real part (waveform.py:693)
+            cplx = _lower_segment(pools, [plain], real_only=True) or cplx
             for k, amp in enumerate(s[1]):
                 if isinstance(amp, Sym):
                     self.sym_amp.append((base_term + k, amp.expr))

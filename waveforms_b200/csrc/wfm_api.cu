@@ -254,12 +254,58 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
       if (!known_func(f.func)) return fail(WFM_EUNSUPPORTED, "factor %lld: unknown basis id %d", (long long)k, f.func);
       if (f.arg_off < 0 || f.arg_off > d->n_args)
         return fail(WFM_EINVAL, "factor %lld: argument offset out of range", (long long)k);
-      if (f.func == WFM_INTERP) {
-        if (f.arg_off + 2 > d->n_args) return fail(WFM_EINVAL, "factor %lld: INTERP header out of range", (long long)k);
-        double n = d->args[f.arg_off];
-        if (!(n >= 1) || f.arg_off + 2 + (int64_t)n > d->n_args)
-          return fail(WFM_EINVAL, "factor %lld: INTERP table out of range", (long long)k);
+      // every basis function's block of the argument pool must lie inside the pool (the device reads
+      // it unchecked): layouts as in wfm_basis.cuh / wfm_multidrag.cuh
+      const int64_t room = d->n_args - f.arg_off;
+      const double* pool = d->args ? d->args + f.arg_off : nullptr;
+      auto need = [&](int64_t n) { return n <= room; };
+      bool ok = true;
+      switch (f.func) {
+        case WFM_INTERP: {
+          ok = need(2);
+          if (ok) {
+            const double n = pool[0];
+            ok = n >= 1 && n < 2147483647.0 && need(2 + (int64_t)n);
+          }
+          break;
+        }
+        case WFM_LINEARCHIRP: ok = need(2); break;
+        case WFM_EXPONENTIALCHIRP:
+        case WFM_HYPERBOLICCHIRP:
+        case WFM_D_GAUSSIAN: ok = need(1); break;
+        case WFM_DRAG: ok = need(5); break;
+        case WFM_MOLLIFIER:
+          if ((int)f.a1 != 0) {
+            ok = need(2);
+            if (ok) {
+              const double nc = pool[1];
+              ok = nc >= 0 && nc < 2147483647.0 && need(2 + (int64_t)nc);
+            }
+          }
+          break;
+        case WFM_DRAG_SIN:
+        case WFM_DRAG_SINX: {
+          ok = need(8);
+          if (!ok) break;
+          const double m = pool[5];
+          ok = m >= 0 && m < 1024 && need(8 + 2 * ((int64_t)m + 1));
+          if (ok && f.func == WFM_DRAG_SINX) {
+            const int64_t tb = 8 + 2 * ((int64_t)m + 1);
+            ok = need(tb + 4);
+            if (ok && pool[tb + 3] > 0) {
+              const double rows = pool[tb + 3];
+              ok = rows < 1024 && need(tb + 5);
+              if (ok) {
+                const double L = pool[tb + 4];
+                ok = L >= 0 && L < 65536 && need(tb + 5 + 2 * (int64_t)rows + 2 * (int64_t)rows * (int64_t)L);
+              }
+            }
+          }
+          break;
+        }
+        default: break;
       }
+      if (!ok) return fail(WFM_EINVAL, "factor %lld (basis id %d): argument block out of range", (long long)k, f.func);
     }
     return 0;
   });

@@ -1399,17 +1399,54 @@ static CounterRing* counter_ring(int dev) {
   return rings[dev];
 }
 
+// Per kernel instantiation and device: the shared-memory attribute and the occupancy of the (few) slice sizes seen so
+// far, so that a steady-state launch costs one cudaGetDevice and the launch itself (the README example spends more
+// time in cudaFuncSetAttribute / cudaOccupancyMax... than in the kernel).
+struct LaunchCfg {
+  int sms = 0;
+  size_t smem_attr = 0;  // largest dynamic shared-memory size the attribute has been raised to
+  struct Occ {
+    size_t smem;
+    int per_sm;
+  };
+  Occ occ[8] = {};
+  int n_occ = 0;
+};
+template <typename K>
+static cudaError_t launch_cfg(K k, LaunchCfg* table, std::mutex& mu, size_t smem, int* sms, int* per_sm) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(mu);
+  LaunchCfg& c = table[dev];
+  if (!c.sms && (e = cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if (smem > c.smem_attr) {
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    c.smem_attr = smem;
+  }
+  *sms = c.sms;
+  for (int i = 0; i < c.n_occ; ++i)
+    if (c.occ[i].smem == smem) {
+      *per_sm = c.occ[i].per_sm;
+      return cudaSuccess;
+    }
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k, kThreads, smem)) != cudaSuccess) return e;
+  c.occ[c.n_occ % 8] = LaunchCfg::Occ{smem, *per_sm};
+  c.n_occ = std::min(c.n_occ + 1, 8);
+  return cudaSuccess;
+}
+
 template <typename OutT, bool kAcc, int U, int kBatch>
 static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                int dtype, void* out, cudaStream_t stream) {
   auto k = sample_kernel<OutT, kAcc, U, kBatch>;
+  static LaunchCfg cfg_table[64];
+  static std::mutex cfg_mu;
   const size_t smem = sample_smem_bytes(P, dtype);
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   int dev = 0, sms = 0, per_sm = 0;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, smem)) != cudaSuccess) return e;
+  cudaError_t e = launch_cfg(k, cfg_table, cfg_mu, smem, &sms, &per_sm);
+  if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   const int64_t want = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   int64_t cap = (int64_t)sms * per_sm;  // persistent: every warp walks tiles w, w+G, ...
@@ -1421,27 +1458,24 @@ static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64
     return cudaGetLastError();
   }
   // the tile counter of this launch: the next slot of a per-device ring (allocated once), zeroed on the launch's
-  // stream; the slot's event makes a launch that comes kCounterSlots launches later wait for this one
+  // stream; the slot's event makes a launch that comes kCounterSlots launches later wait for this one.  The ring's
+  // mutex is held until the event is recorded: a thread that wraps around to this slot waits for THIS launch.
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   CounterRing* ring = counter_ring(dev);
   if (!ring) return cudaErrorMemoryAllocation;
-  int slot;
-  cudaEvent_t ev;
-  {
-    std::lock_guard<std::mutex> lk(ring->mu);
-    slot = ring->next;
-    ring->next = (ring->next + 1) % kCounterSlots;
-    if (!ring->used[slot]) {
-      if ((e = cudaEventCreateWithFlags(&ring->used[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
-    } else if ((e = cudaStreamWaitEvent(stream, ring->used[slot], 0)) != cudaSuccess) {
-      return e;
-    }
-    ev = ring->used[slot];
+  std::lock_guard<std::mutex> lk(ring->mu);
+  const int slot = ring->next;
+  ring->next = (ring->next + 1) % kCounterSlots;
+  if (!ring->used[slot]) {
+    if ((e = cudaEventCreateWithFlags(&ring->used[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
+  } else if ((e = cudaStreamWaitEvent(stream, ring->used[slot], 0)) != cudaSuccess) {
+    return e;
   }
   unsigned int* counter = ring->counters + slot;
   if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
   k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, counter);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  return cudaEventRecord(ev, stream);
+  return cudaEventRecord(ring->used[slot], stream);
 }
 
 // The deal of a launch.  Dynamic (batches of WFM_K1_DYNAMIC tiles drawn from a counter) is the default whenever the warps
@@ -1451,12 +1485,13 @@ static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64
 template <typename OutT, bool kAcc, int U>
 static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                      int dtype, void* out, cudaStream_t stream) {
-  const char* deal = getenv("WFM_K1_DEAL");
+  const char* dv = getenv("WFM_K1_DEAL");  // a scan of environ (~0.1 us); read per launch so that tests can flip it
+  const char deal = dv ? dv[0] : '\0';
   // >= ~7 tiles per warp of a full persistent grid; fp32 output keeps the static deal (its tiles are half as long, the
   // counter traffic doubles: 856 static against 811-822 GSa/s dynamic on cfg2)
   bool dynamic = n_tiles >= (int64_t)16 * 1024 && sizeof(OutT) == 8;
-  if (deal && deal[0] == 'd') dynamic = true;
-  if (deal && deal[0] == 's') dynamic = false;
+  if (deal == 'd') dynamic = true;
+  if (deal == 's') dynamic = false;
   if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
   return launch_deal<OutT, kAcc, U, 0>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 }

@@ -75,24 +75,47 @@ def sosfilt_device(sos, x, initial=0.0, zi=None, want_zf=False, out=None,
 
 def sample_and_filter(chan, grid, sos, initial, zi):
     """Waveform.sample with ``filters=(sos, initial)``: K1 then K2 on the
-    device, one device->host copy of the filtered result."""
+    device, one device->host copy of the filtered result.  A channel with
+    complex amplitudes is filtered plane by plane (the filter is real and linear:
+    sosfilt(sos, re + 1j*im) = sosfilt(sos, re) + 1j*sosfilt(sos, im), which is what
+    scipy computes for a complex input; ``initial`` acts on the real plane)."""
+    import torch
     batch = lower([(chan, grid)])
     prog = engine.Program(batch)
     try:
-        dev = prog.sample_device(dtype=engine.WFM_F64)
-        sig = dev[:grid.n]
-        _, zf = sosfilt_device(sos, sig, initial=initial or 0.0, zi=zi,
-                               want_zf=zi is not None, mode=None)
-        host = sig.cpu().numpy()
+        if not batch.any_complex:
+            dev = prog.sample_device(dtype=engine.WFM_F64)
+            sig = dev[:grid.n]
+            _, zf = sosfilt_device(sos, sig, initial=initial or 0.0, zi=zi,
+                                   want_zf=zi is not None, mode=None)
+            host = sig.cpu().numpy()
+            return host, (zf[0] if zf is not None else None)
+        dev = prog.sample_device(dtype=engine.WFM_C128)[:grid.n]
+        planes = torch.view_as_real(dev).permute(1, 0).contiguous()  # (2, n): real, imaginary
+        zi_c = None if zi is None else np.asarray(zi, dtype=np.complex128)
+        ini = complex(initial or 0.0)
+        zfs = []
+        for k, part in enumerate((np.real, np.imag)):
+            _, zf = sosfilt_device(sos, planes[k], initial=float(part(ini)),
+                                   zi=None if zi_c is None else part(zi_c),
+                                   want_zf=zi is not None, mode=None)
+            zfs.append(zf)
+        host = planes.cpu().numpy()
+        host = host[0] + 1j * host[1]
+        zf = None if zi is None else zfs[0][0] + 1j * zfs[1][0]
+        return host, zf
     finally:
         prog.close()
-    return host, (zf[0] if zf is not None else None)
 
 
 def apply_channel_filters(out, batch, waveforms, mode=None):
     """Apply each waveform's own ``.filters`` to its slice of ``out`` (flat device
     tensor of the whole batch).  Channels that share a filter and a length and sit
     at a constant pitch in the buffer go through ONE batched call (n_sig signals)."""
+    import torch
+    if out.dtype != torch.float64:
+        raise TypeError('sample-time IIR filters run on float64 samples; got '
+                        f'{out.dtype} (sample_batch filters in float64 and casts)')
     groups = {}
     for k, w in enumerate(waveforms):
         if w.filters is None:

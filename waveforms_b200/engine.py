@@ -59,7 +59,7 @@ EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_program_info', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
-    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c'
+    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c', 'wfm_calibrate_fp64', 'wfm_calibrate_copy'
 ]
 
 
@@ -106,6 +106,8 @@ def load_library():
         lib.wfm_fft_c2c.argtypes = [
             C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p
         ]
+        lib.wfm_calibrate_fp64.argtypes = [C.POINTER(C.c_double), C.c_int32, C.c_void_p]
+        lib.wfm_calibrate_copy.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         if lib.wfm_abi_version() != 1:
             raise EngineUnavailable('libwfmb200.so ABI version mismatch')
         _lib = lib
@@ -142,6 +144,27 @@ def check_function_lib(function_lib):
     raise UnsupportedBasis(
         'function_lib= with user callables is not supported: basis functions '
         'are evaluated by the CUDA kernel (ids 1..17)')
+
+
+def calibrate_fp64(reps=3, device=None):
+    """fp64 FMA lane-operations per second of ``device`` (the FP64-pipe ceiling
+    dense programs are quoted against), measured now."""
+    torch = _torch()
+    lib = require_gpu()
+    out = (C.c_double * 2)()
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        _check(lib.wfm_calibrate_fp64(out, reps, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return {'dfma_per_s': out[0], 'tflops': 2 * out[0] / 1e12, 'launch_ms': out[1]}
+
+
+def calibrate_copy(nbytes, direction='d2h', reps=3, device=None):
+    """GB/s of a pinned cudaMemcpyAsync of ``nbytes`` on ``device`` (best, sustained)."""
+    torch = _torch()
+    lib = require_gpu()
+    out = (C.c_double * 2)()
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        _check(lib.wfm_calibrate_copy(int(nbytes), 0 if direction == 'd2h' else 1, reps, out))
+    return {'best_GBs': out[0], 'sustained_GBs': out[1]}
 
 
 # -- grids -------------------------------------------------------------------
@@ -261,7 +284,32 @@ class Program:
 
 
 # -- single-channel helpers used by Waveform.__call__/sample -------------------
-def _run_one(chan: Channel, grid: Grid, want_complex=None):
+def _is_complex_amp(v):
+    return isinstance(v, (complex, np.complexfloating))
+
+
+def wants_complex(chan: Channel, grid: Grid) -> bool:
+    """The reference's output dtype rule (calc_parts, _waveform.pyx:155-169):
+    complex128 as soon as ONE non-zero segment that receives at least one
+    sample has a complex-typed amplitude — whatever its imaginary part is — and
+    float64 otherwise.  A ``WaveVStack`` always returns ``out.real``
+    (waveform.py:693)."""
+    if chan.real_only:
+        return False
+    for bounds, seq in chan.members:
+        cand = [k for k, s in enumerate(seq)
+                if s != A.ZERO and any(_is_complex_amp(v) for v in s[1])]
+        if not cand:
+            continue
+        edges = grid.searchsorted(bounds)
+        for k in cand:
+            lo = 0 if k == 0 else int(edges[k - 1])
+            if lo < int(edges[k]):
+                return True
+    return False
+
+
+def _run_one(chan: Channel, grid: Grid):
     batch = lower([(chan, grid)])
     prog = Program(batch)
     try:
@@ -269,7 +317,13 @@ def _run_one(chan: Channel, grid: Grid, want_complex=None):
         res = prog.sample_host(dtype=dtype)
     finally:
         prog.close()
-    return res[:grid.n]
+    res = res[:grid.n]
+    want = wants_complex(chan, grid)
+    if want and res.dtype != np.complex128:
+        res = res.astype(np.complex128)
+    elif not want and res.dtype == np.complex128:
+        res = np.ascontiguousarray(res.real)  # the complex segments received no sample
+    return res
 
 
 def sample_one(chan: Channel, grid: Grid, out=None, accumulate=False,
@@ -299,9 +353,8 @@ def sample_parts(chan: Channel, grid: Grid):
     (calc_parts' return value, _waveform.pyx:155-169).  Values come from the
     device; the index ranges are host bookkeeping on the abscissae."""
     (bounds, seq), = chan.members
-    xs = grid.materialize()
     sig = _run_one(chan, grid)
-    edges = np.searchsorted(xs, bounds)
+    edges = grid.searchsorted(bounds)
     parts = []
     start = 0
     for k, stop in enumerate(edges):

@@ -76,6 +76,36 @@ class Grid:
     x_last: float | None = None
     x: np.ndarray | None = None
 
+    def searchsorted(self, bounds) -> np.ndarray:
+        """``np.searchsorted(x, bounds)`` (side='left') without materialising an
+        affine grid: a division for the guess, then exact comparisons against
+        the rounded grid values ``t0 + j*delta`` (host bookkeeping only: which
+        segments receive samples, ``frag=True`` index ranges)."""
+        b = np.asarray(bounds, dtype=np.float64).reshape(-1)
+        if self.x is not None or not self.delta > 0 or self.n == 0:
+            return np.searchsorted(self.materialize(), b)
+        n = self.n
+
+        def xs(j):
+            v = self.t0 + j.astype(np.float64) * self.delta
+            if self.x_last is not None:
+                v = np.where(j == n - 1, self.x_last, v)
+            return v
+
+        with np.errstate(invalid='ignore', over='ignore'):
+            g = np.ceil((b - self.t0) / self.delta)
+        j = np.where(g >= n, n, np.where(g > 0, g, 0))  # NaN -> 0, fixed below
+        j = np.where(np.isnan(g), n, j).astype(np.int64)
+        for _ in range(64):
+            down = (j > 0) & (xs(np.maximum(j - 1, 0)) >= b)
+            up = (j < n) & (xs(np.minimum(j, n - 1)) < b)
+            if not (down.any() or up.any()):
+                break
+            j = j - down + (up & ~down)
+        else:  # a pathological grid: fall back to the plain search
+            return np.searchsorted(self.materialize(), b)
+        return j
+
     def materialize(self) -> np.ndarray:
         """Host copy of the abscissae (host bookkeeping such as ``frag=True``
         index ranges; never used to compute sample values)."""
@@ -93,6 +123,9 @@ class Channel:
     clip: tuple | None = None
     offset: float = 0
     pre_shift: float = 0
+    # WaveVStack.__call__ accumulates in complex128 and returns ``out.real``
+    # (waveform.py:681-693): only the real parts of the amplitudes reach the result
+    real_only: bool = False
     _lowered: object = field(default=None, repr=False, compare=False)
 
 
@@ -331,10 +364,11 @@ def _emit_rows(pools, rows):
         pools.n_fac += 1
 
 
-def _lower_segment(pools, groups):
+def _lower_segment(pools, groups, real_only=False):
     """groups: list of expressions (one per stack member active here, in member
     order).  Appends the segment's factors / terms / refs to the pools.
-    Returns True if any amplitude is complex."""
+    Returns True if any amplitude has a non-zero imaginary part (``real_only``:
+    imaginary parts are dropped, the channel returns ``.real``)."""
     order, seen = [], set()
     for expr in groups:
         for factors, _ in expr[0]:
@@ -355,6 +389,8 @@ def _lower_segment(pools, groups):
                 pools.n_ref += 1
             if isinstance(amp, complex) or isinstance(amp, np.complexfloating):
                 re, im = float(amp.real), float(amp.imag)
+                if real_only:
+                    im = 0.0
                 cplx = cplx or im != 0.0
             else:
                 re, im = float(amp), 0.0
@@ -399,14 +435,14 @@ def _lower_channel(pools, chan):
         pools.segfac.append(pools.n_fac)
         pools.segterm.append(pools.n_term)
         if groups:
-            cplx = _lower_segment(pools, groups) or cplx
+            cplx = _lower_segment(pools, groups, chan.real_only) or cplx
     return seg_begin, len(bounds), cplx
 
 
 def lower(items) -> LoweredBatch:
     """items: iterable of (Channel, Grid).  Output offsets are assigned
-    back-to-back, each channel's start padded to a multiple of 2 samples so
-    16-byte vector stores stay aligned."""
+    back-to-back, each channel's start padded to a multiple of 4 samples so
+    16-byte vector stores stay aligned for fp32 and fp64 output."""
     pools = _Pools()
     items = list(items)
     waves = np.zeros(len(items), dtype=WAVE_DT)

@@ -436,7 +436,8 @@ class WaveVStack(Waveform):
     def _channel(self):
         from .lowering import Channel
         return Channel(members=list(self.wlist), clip=None,
-                       offset=self.offset, pre_shift=self.shift)
+                       offset=self.offset, pre_shift=self.shift,
+                       real_only=True)
 
     def __call__(self, x, frag=False, out=None, function_lib=None):
         assert frag is False, 'WaveVStack does not support frag mode'
