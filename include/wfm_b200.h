@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define WFM_ABI_VERSION 1
+#define WFM_ABI_VERSION 2
 
 /* error codes */
 #define WFM_OK            0
@@ -76,8 +76,13 @@ enum {
 #define WFM_WAVE_CLIP           0x4u  /* np.clip(v, clip_lo, clip_hi) on non-zero segments */
 #define WFM_WAVE_PRESHIFT       0x8u  /* x' = x - pre_shift (WaveVStack.shift) */
 #define WFM_WAVE_COMPLEX        0x10u /* channel has complex amplitudes        */
+#define WFM_WAVE_PAIR           0x20u /* TWO output rows (the I and Q of one mixing() call,
+                                         waveform.py:1487-1527) that share their segment table and
+                                         every basis-function evaluation: terms flagged
+                                         WFM_TERM_PLANE1 sum into the second row (out_off2, offset2).
+                                         A pair is real-valued and unclipped. */
 
-/* one output channel (a Waveform, or a whole WaveVStack) — 96 bytes */
+/* one output channel (a Waveform, or a whole WaveVStack), or an I/Q pair of them — 112 bytes */
 typedef struct WfmWave {
   double   t0;        /* affine grid: x[j] = t0 + j*delta (multiply, then add; never fused) */
   double   delta;
@@ -92,6 +97,8 @@ typedef struct WfmWave {
   int32_t  n_seg;     /* rows; the last one has bound +inf */
   uint32_t flags;
   uint32_t reserved;
+  int64_t  out_off2;  /* WFM_WAVE_PAIR: first sample of the second row in the output buffer */
+  double   offset2;   /* WFM_WAVE_PAIR: accumulator start of the second row */
 } WfmWave;
 
 /* per segment: where its distinct factors and its terms start; row n_segs
@@ -111,6 +118,8 @@ typedef struct WfmFactor {
 
 /* WfmTerm.flags */
 #define WFM_TERM_GROUP_END 0x1u /* last term of a stack member: fold the group sum into the channel accumulator */
+#define WFM_TERM_PLANE1    0x2u /* the term belongs to the SECOND row of a WFM_WAVE_PAIR channel; within a segment
+                                   all first-row terms come before the second-row terms */
 
 /* amp * prod(refs) — 32 bytes */
 typedef struct WfmTerm {

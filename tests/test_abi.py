@@ -29,12 +29,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(lib, name), name
     assert sorted(engine.EXPORTS) == declared_functions()
-    assert lib.wfm_abi_version() == 1
+    assert lib.wfm_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from waveforms_b200 import lowering as L
-    assert L.WAVE_DT.itemsize == 96 and L.WAVE_DT.fields['n'][1] == 56
+    assert L.WAVE_DT.itemsize == 112 and L.WAVE_DT.fields['n'][1] == 56
+    assert L.WAVE_DT.fields['out_off2'][1] == 96 and L.WAVE_DT.fields['offset2'][1] == 104
     assert L.WAVE_DT.fields['seg_begin'][1] == 80 and L.WAVE_DT.fields['flags'][1] == 88
     assert L.SEGPTR_DT.itemsize == 8
     assert L.FACTOR_DT.itemsize == 32 and L.FACTOR_DT.fields['shift'][1] == 8

@@ -72,9 +72,13 @@ def test_batch_matches_single(ns):
         for ch in (I, Q):
             ch.start, ch.stop, ch.sample_rate = 0, (0.4e-6 + 13e-9 * k), 2e9  # ragged lengths
             ws.append(ch)
-    res = sample_batch(ws).numpy()
-    for w, y in zip(ws, res):
+    res = sample_batch(ws, pair_iq=False).numpy()
+    paired = sample_batch(ws).numpy()  # default: I and Q of one mixing() call share their cosines
+    for w, y, yp in zip(ws, res, paired):
         assert np.array_equal(y, w.sample())
+        # a pair takes ONE sincos per frequency for both rows: the rotation base of the second row's cosines differs
+        # from the unpaired evaluation, the values by an ulp or two
+        assert rel_err(yp, y) <= 4e-15
 
 
 def test_unsupported_basis_raises(ns):

@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import engine
-from .lowering import lower
+from .lowering import can_pair, find_pairs, lower
 
 
 def channel_grid(w, sample_rate=None):
@@ -60,7 +60,7 @@ class BatchResult:
 
 
 def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
-                 filters='own', iir_mode='auto'):
+                 filters='own', iir_mode='auto', pair_iq='auto'):
     """Sample every waveform in ``waveforms`` on its own start/stop/sample_rate
     grid.  ``dtype``: np.float64 (reference parity, 1e-12) or np.float32
     (fp32 output, 1e-6).  ``devices``: list of CUDA device indices to shard the
@@ -71,7 +71,14 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     waveform.py:193-203) on the device; ``None`` skips them.  ``iir_mode``:
     'exact' (bit-identical to scipy, sequential in time) | 'scan' (block-parallel,
     equal up to the filter's rounding-noise gain) | 'auto' (exact up to 32 768
-    samples per channel, scan above; the default here) | None (``dsp.IIR_MODE``)."""
+    samples per channel, scan above; the default here) | None (``dsp.IIR_MODE``).
+
+    ``pair_iq``: 'auto' evaluates ADJACENT channels that share their grid and most
+    of their basis functions — the I and Q of one ``mixing()`` call
+    (waveform.py:1487-1527) — as one I/Q pair: every cos / envelope factor is
+    computed once and feeds both outputs (the second row's cosines are rotated from
+    the shared sincos: equal to unpaired sampling to a few ulp); ``False`` keeps every channel
+    on its own; ``True`` requires channels (0, 1), (2, 3) ... to pair."""
     import torch
     engine.require_gpu()
     items = [channel_grid(w, sample_rate) for w in waveforms]
@@ -89,7 +96,27 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     # float64 and cast at the end
     run_code = engine.WFM_F64 if (filtered and code == engine.WFM_F32) else code
     ranges = shard_ranges([g.n for _, g in items], len(devices))
-    shards = [(dev, lo, hi, lower(items[lo:hi])) for dev, (lo, hi) in zip(devices, ranges)]
+    if np_dtype == np.dtype(np.complex128):
+        pair_iq = False
+    if pair_iq is True:
+        # an odd cut would split a pair: move it to the next even channel
+        ranges = [(lo + (lo & 1) if lo < len(items) else lo, hi + (hi & 1) if hi < len(items) else hi)
+                  for lo, hi in ranges]
+
+    def lowered(lo, hi):
+        part = items[lo:hi]
+        if pair_iq == 'auto':
+            part = find_pairs(part)
+        elif pair_iq is True:
+            if len(part) % 2:
+                raise ValueError('pair_iq=True needs an even number of channels')
+            for a, b in zip(part[0::2], part[1::2]):
+                if not can_pair(a, b, min_shared=0.0):
+                    raise ValueError('pair_iq=True: channels differ in grid, clip or are complex')
+            part = [((a[0], b[0]), a[1]) for a, b in zip(part[0::2], part[1::2])]
+        return lower(part)
+
+    shards = [(dev, lo, hi, lowered(lo, hi)) for dev, (lo, hi) in zip(devices, ranges)]
 
     def run(shard):
         # one host thread per device: upload, pre-pass, K1 and the filters of every device run
@@ -109,9 +136,8 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     tensors, table = [], []
     for slot, ((dev, lo, hi, batch), (prog, out)) in enumerate(zip(shards, results)):
         tensors.append(out)
-        for k in range(hi - lo):
-            table.append((slot, int(batch.waves['out_off'][k]),
-                          int(batch.waves['n'][k])))
+        for k in range(batch.n_channels):
+            table.append((slot, int(batch.chan_off[k]), int(batch.chan_n[k])))
     for prog, _ in results:  # destroy waits for the program's last launch: only after ALL devices were launched
         prog.close()
     return BatchResult(tensors, table, dtype)
@@ -187,9 +213,8 @@ def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
     tensors, table = [], []
     for slot, ((dev, lo, hi), (prog, out, batch)) in enumerate(zip(shards, results)):
         tensors.append(out)
-        for k in range(hi - lo):
-            table.append((slot, int(batch.waves['out_off'][k]),
-                          int(batch.waves['n'][k])))
+        for k in range(batch.n_channels):
+            table.append((slot, int(batch.chan_off[k]), int(batch.chan_n[k])))
     for prog, _, _ in results:
         prog.close()
     return BatchResult(tensors, table, dtype)

@@ -29,7 +29,7 @@ import numpy as np
 
 from . import _algebra as A
 from . import engine
-from .lowering import (PACKERS, FACTOR_DT, REF_DT, SEGPTR_DT, TERM_DT, WAVE_COMPLEX,
+from .lowering import (PACKERS, FACTOR_DT, REF_DT, SEGPTR_DT, TERM_DT, WAVE_COMPLEX, WAVE_PAIR,
                        WAVE_DT, LoweredBatch, _Pools, _lower_segment, _plan_slots)
 
 
@@ -164,8 +164,21 @@ class PulseTemplate:
         self.params = tuple(params)
         pv, cv = _probe_values(self.params, probe, check)
         w = fn(*[Sym(pv[n], ('p', n)) for n in self.params])
-        self._extract(w.bounds, w.seq)
+        self._extract(*self._bounds_seqs(w))
         self._verify(cv)
+
+    @staticmethod
+    def _bounds_seqs(w):
+        """``fn`` returns one Waveform, or the (I, Q) tuple of a ``mixing`` call: an I/Q PAIR
+        template (both outputs of every pulse, their shared basis functions evaluated once)."""
+        if isinstance(w, (tuple, list)):
+            if len(w) != 2:
+                raise UntraceablePulse('a pair template returns exactly two waveforms (I, Q)')
+            a, b = w
+            if tuple(float(x) for x in a.bounds) != tuple(float(x) for x in b.bounds):
+                raise UntraceablePulse('the two waveforms of a pair template must share their bounds')
+            return a.bounds, a.seq, b.seq
+        return w.bounds, w.seq, None
 
     @classmethod
     def trace(cls, fn, params=('t0', ), **kw):
@@ -180,8 +193,10 @@ class PulseTemplate:
         return cls(fn, params, **kw)
 
     # -- tracing -------------------------------------------------------------------
-    def _extract(self, bounds, seq):
-        if not bounds or bounds[-1] != math.inf or seq[-1] != A.ZERO or seq[0] != A.ZERO:
+    def _extract(self, bounds, seq, seq2=None):
+        self.pair = seq2 is not None
+        both = (seq, ) if seq2 is None else (seq, seq2)
+        if not bounds or bounds[-1] != math.inf or any(q[-1] != A.ZERO or q[0] != A.ZERO for q in both):
             raise UntraceablePulse('a pulse template must be zero before its first and after its '
                                    'last bound')
         self.bound_expr = [Sym._expr(b) for b in bounds[:-1]]
@@ -192,26 +207,32 @@ class PulseTemplate:
         self.rot_rows = []                         # (fac row, local arg_off, w, base-shift expr)
         has_args = []                              # fac rows that own a block of the argument pool
         cplx = False
-        for s in seq[:-1]:
+        for i in range(len(seq) - 1):
             self.seg_fac.append(pools.n_fac)
             self.seg_term.append(pools.n_term)
-            if s == A.ZERO:
+            parts = [(q[i], plane) for plane, q in enumerate(both) if q[i] != A.ZERO]
+            if not parts:
                 continue
             order, seen = [], set()
-            for factors, _ in s[0]:
-                for f in factors:
-                    if f not in seen:
-                        seen.add(f)
-                        order.append(f)
+            for s, _ in parts:
+                for factors, _e in s[0]:
+                    for f in factors:
+                        if f not in seen:
+                            seen.add(f)
+                            order.append(f)
             rows, _ = _plan_slots(order)  # the plan _lower_segment is about to emit
             base, base_term = pools.n_fac, pools.n_term
-            plain = (tuple((tuple((*f[:-1], float(f[-1])) for f in factors), expo) for factors, expo in s[0]),
-                     tuple(float(v) if isinstance(v, Sym) else v for v in s[1]))
+            plain = [(tuple((tuple((*f[:-1], float(f[-1])) for f in factors), expo) for factors, expo in s[0]),
+                      tuple(float(v) if isinstance(v, Sym) else v for v in s[1])) for s, _ in parts]
             # channels built here are stacks: WaveVStack returns the real part (waveform.py:693)
-            cplx = _lower_segment(pools, [plain], real_only=True) or cplx
-            for k, amp in enumerate(s[1]):
-                if isinstance(amp, Sym):
-                    self.sym_amp.append((base_term + k, amp.expr))
+            cplx = _lower_segment(pools, plain, real_only=True,
+                                  planes=[pl for _, pl in parts] if self.pair else None) or cplx
+            k0 = 0
+            for s, _ in parts:
+                for k, amp in enumerate(s[1]):
+                    if isinstance(amp, Sym):
+                        self.sym_amp.append((base_term + k0 + k, amp.expr))
+                k0 += len(s[1])
             for r, row in enumerate(rows):
                 has_args.append(row[0] == 'rot' or
                                 (row[0] == 'plain' and bool(PACKERS[row[1][0]](row[1][1:-1])[2])))
@@ -284,9 +305,10 @@ class PulseTemplate:
         """Replay at a second parameter point against a plain-float build there."""
         w = self.fn(*[point[n] for n in self.params])
         ref = PulseTemplate.__new__(PulseTemplate)
-        ref._extract(w.bounds, w.seq)
+        w_bounds, w_seq, w_seq2 = self._bounds_seqs(w)
+        ref._extract(w_bounds, w_seq, w_seq2)
         b, f, a, amps = self.instantiate(**{n: np.array([point[n]]) for n in self.params})
-        same = (ref.n_seg == self.n_seg and np.array_equal(np.array([float(x) for x in w.bounds[:-1]]), b[0])
+        same = (ref.n_seg == self.n_seg and np.array_equal(np.array([float(x) for x in w_bounds[:-1]]), b[0])
                 and np.array_equal(ref.facs, f[0]) and np.array_equal(ref.args, a[0])
                 and np.array_equal(ref.terms, self.instance_terms(amps)[0]) and np.array_equal(ref.refs, self.refs))
         if not same:
@@ -401,16 +423,22 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=
     ch_seg_lo = seg_off[ch_first[:-1]] + np.arange(n_ch)
     ch_seg_hi = tail + 1
     grid = engine.arange_grid(start, stop, 1 / sample_rate)
+    pair = bool(templates) and bool(templates[0].pair)
+    if any(bool(t.pair) != pair for t in templates):
+        raise ValueError('pair templates (fn returns (I, Q)) and single-output templates cannot share a batch')
+    rows = 2 if pair else 1
+    pitch = (grid.n + 3) & ~3
     waves = np.zeros(n_ch, dtype=WAVE_DT)
     waves['t0'], waves['delta'], waves['n'] = grid.t0, grid.delta, grid.n
-    waves['out_off'] = np.arange(n_ch, dtype=np.int64) * ((grid.n + 3) & ~3)
+    waves['out_off'] = np.arange(n_ch, dtype=np.int64) * (rows * pitch)
+    waves['out_off2'] = waves['out_off'] + pitch if pair else 0
     waves['seg_begin'] = kept_before[ch_seg_lo]
     waves['n_seg'] = kept_before[ch_seg_hi] - kept_before[ch_seg_lo]
     cplx_t = np.array([t.complex for t in templates], dtype=bool)
     ch_cplx = np.zeros(n_ch, dtype=bool)
     if P:
         np.logical_or.at(ch_cplx, ch_of, cplx_t[M])
-    waves['flags'] = np.where(ch_cplx, WAVE_COMPLEX, 0)
+    waves['flags'] = np.where(ch_cplx, WAVE_COMPLEX, 0) | (WAVE_PAIR if pair else 0)
     return LoweredBatch(waves=waves, seg_bound=seg_bound, seg_ptr=seg_ptr, facs=facs, terms=terms,
                         refs=refs, args=args, x=np.zeros(0, np.float64),
-                        total_samples=int(n_ch * ((grid.n + 3) & ~3)), any_complex=bool(ch_cplx.any()))
+                        total_samples=int(n_ch * rows * pitch), any_complex=bool(ch_cplx.any()))

@@ -354,6 +354,13 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
       }
       if (b.term > a.term && !(d->terms[b.term - 1].flags & WFM_TERM_GROUP_END))
         return fail(WFM_EINVAL, "segment %lld: last term does not close its group", (long long)s);
+      // I/Q pairs: the first row's terms, then the second row's; the first row ends on a closed group
+      for (int t = a.term + 1; t < b.term; ++t) {
+        const bool p_prev = d->terms[t - 1].flags & WFM_TERM_PLANE1, p_cur = d->terms[t].flags & WFM_TERM_PLANE1;
+        if (p_prev && !p_cur) return fail(WFM_EINVAL, "segment %lld: second-row terms must follow the first row's", (long long)s);
+        if (!p_prev && p_cur && !(d->terms[t - 1].flags & WFM_TERM_GROUP_END))
+          return fail(WFM_EINVAL, "segment %lld: the first row's last term does not close its group", (long long)s);
+      }
     }
     int cur = max_rows.load();
     while (local_max > cur && !max_rows.compare_exchange_weak(cur, local_max)) {
@@ -373,6 +380,13 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
     if ((wv.flags & WFM_WAVE_EXPLICIT_X) && (wv.x_off < 0 || wv.x_off + wv.n > d->n_x))
       return fail(WFM_EINVAL, "channel %lld: explicit abscissae out of range", (long long)w);
     if (wv.out_off % 4) return fail(WFM_EINVAL, "channel %lld: out_off must be a multiple of 4 (16-byte stores)", (long long)w);
+    if (wv.flags & WFM_WAVE_PAIR) {
+      if (wv.out_off2 < 0 || wv.out_off2 % 4) return fail(WFM_EINVAL, "channel %lld: out_off2 must be a non-negative multiple of 4", (long long)w);
+      if (wv.flags & (WFM_WAVE_CLIP | WFM_WAVE_COMPLEX))
+        return fail(WFM_EINVAL, "channel %lld: an I/Q pair is real-valued and unclipped", (long long)w);
+      const int64_t lo = std::min(wv.out_off, wv.out_off2), hi = std::max(wv.out_off, wv.out_off2);
+      if (lo + wv.n > hi) return fail(WFM_EINVAL, "channel %lld: the two rows of the pair overlap", (long long)w);
+    }
   }
   return WFM_OK;
 }
@@ -424,12 +438,17 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->device = device;
   p->waves.assign(d->waves, d->waves + d->n_waves);
   p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
+  p->dev.planes = 1;
 
   int64_t samples = 0, total = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
     samples += d->waves[w].n;
     total = std::max(total, d->waves[w].out_off + d->waves[w].n);
     if (d->waves[w].flags & WFM_WAVE_COMPLEX) p->any_complex = true;
+    if (d->waves[w].flags & WFM_WAVE_PAIR) {
+      p->dev.planes = 2;
+      total = std::max(total, d->waves[w].out_off2 + d->waves[w].n);
+    }
   }
   p->total_samples = total;
 
@@ -445,7 +464,8 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                o_terms = reserve(sizeof(WfmTerm) * d->n_terms), o_refs = reserve(sizeof(WfmRef) * d->n_refs),
                o_args = reserve(sizeof(double) * d->n_args), o_x = reserve(sizeof(double) * d->n_x),
                o_segwave = reserve(sizeof(int32_t) * d->n_segs), o_segstart = reserve(sizeof(int32_t) * d->n_segs),
-               o_segval = reserve(sizeof(double) * d->n_segs), o_plan = reserve(sizeof(wfm::SegPlan) * d->n_segs),
+               o_segval = reserve(sizeof(double) * d->n_segs),
+               o_segval1 = reserve(p->dev.planes == 2 ? sizeof(double) * d->n_segs : 0), o_plan = reserve(sizeof(wfm::SegPlan) * d->n_segs),
                o_rowslot = reserve((size_t)d->n_facs), o_cterms = reserve(sizeof(wfm::CTerm) * d->n_terms),
                o_prefix = reserve(sizeof(int64_t) * (d->n_waves + 1)), o_stats = reserve(sizeof(uint64_t) * 2);
   cudaError_t e = pool::alloc(device, arena_bytes, &p->arena);
@@ -478,6 +498,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->dev.seg_wave = (const int32_t*)(base + o_segwave);
   p->dev.seg_start = (const int32_t*)(base + o_segstart);
   p->dev.seg_val = (const double*)(base + o_segval);
+  p->dev.seg_val1 = p->dev.planes == 2 ? (const double*)(base + o_segval1) : nullptr;
   p->dev.seg_plan = (const wfm::SegPlan*)(base + o_plan);
   p->dev.row_slot = (const uint8_t*)(base + o_rowslot);
   p->dev.cterms = (const wfm::CTerm*)(base + o_cterms);
@@ -486,7 +507,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   // device pre-pass 1a: owning channel of every segment, segment start positions and flat
   // values, segment plans
   wfm::PrepareBuffers pb{(int32_t*)(base + o_segwave), (int32_t*)(base + o_segstart), (double*)(base + o_segval),
-                         (wfm::SegPlan*)(base + o_plan), (uint8_t*)(base + o_rowslot), (wfm::CTerm*)(base + o_cterms),
+                         p->dev.planes == 2 ? (double*)(base + o_segval1) : nullptr, (wfm::SegPlan*)(base + o_plan), (uint8_t*)(base + o_rowslot), (wfm::CTerm*)(base + o_cterms),
                          nullptr, (const int64_t*)(base + o_prefix), nullptr};
   wfm::PrepareCounts pc{d->n_waves, d->n_segs, d->n_facs, d->n_terms, 0};
   p->dev.unit = 1;
@@ -512,7 +533,8 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   // not fit (those take the kernel's cold path).
   uint32_t* d_stats = (uint32_t*)(base + o_stats);
   const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots, p->dev.unit);
-  auto cap_of = [&](int ts) { return ((wfm::kWarpSliceBytes - fixed - ts * 8) / 2) & ~15; };
+  // (an I/Q pair program keeps one tile buffer per output row)
+  auto cap_of = [&](int ts) { return ((wfm::kWarpSliceBytes - fixed - ts * 8 * p->dev.planes) / 2) & ~15; };
   int ts = wfm::kMaxTileSamples;
   {
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
@@ -604,6 +626,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
         v.flags &= ~(uint32_t)WFM_WAVE_COMPLEX;
         v.seg_begin += (int32_t)(c * ns);
         v.out_off += c * ((total + 3) & ~(int64_t)3);  // planes stay 16-byte aligned
+        v.out_off2 += c * ((total + 3) & ~(int64_t)3);
         if (c == 1) {
           v.offset = 0.0;  // offsets and clipping act on the real part
           v.flags &= ~(uint32_t)WFM_WAVE_CLIP;
@@ -678,7 +701,10 @@ static int check_launch(wfm_program_t prog, const WfmLaunch* l, int64_t* first, 
       if (prog->waves[w].flags & WFM_WAVE_COMPLEX)
         return fail(WFM_EINVAL, "channel %lld has complex amplitudes: request WFM_C128 output", (long long)w);
   int64_t ext = 0;
-  for (int64_t w = *first; w < *first + *count; ++w) ext = std::max(ext, prog->waves[w].out_off + prog->waves[w].n);
+  for (int64_t w = *first; w < *first + *count; ++w) {
+    ext = std::max(ext, prog->waves[w].out_off + prog->waves[w].n);
+    if (prog->waves[w].flags & WFM_WAVE_PAIR) ext = std::max(ext, prog->waves[w].out_off2 + prog->waves[w].n);
+  }
   *need = ext;
   if (!l->out && ext > 0) return fail(WFM_EINVAL, "null output buffer");
   if (l->out_elems < ext) return fail(WFM_EINVAL, "output buffer too small: %lld < %lld", (long long)l->out_elems, (long long)ext);

@@ -91,6 +91,8 @@ struct CTerm {
 };
 static_assert(sizeof(CTerm) == 16, "CTerm layout");
 constexpr uint32_t kCTermGroupEnd = 1, kCTermExt = 2;
+// first term of the SECOND row of an I/Q pair: the first row's sum is complete (stored before this term is added)
+constexpr uint32_t kCTermPlaneSwitch = 4;
 
 // per segment, parallel to the ABI segment table
 struct SegPlan {
@@ -120,8 +122,10 @@ struct PacketHeader {
   uint16_t n_patch;  // flat segments whose value differs from `base`
   uint16_t n_units;  // units (DevProgram::unit consecutive samples of one active segment) in the tile
   uint32_t reserved[2];
+  int64_t out1;   // WFM_WAVE_PAIR: the same tile of the second row
+  double base1;   //                and that row's zero-segment value
 };
-static_assert(sizeof(PacketHeader) == 64, "PacketHeader layout");
+static_assert(sizeof(PacketHeader) == 80, "PacketHeader layout");
 constexpr uint32_t kPacketCold = 0x80000000u;  // header only: the tile takes the global-table path
 
 // one ACTIVE segment of the tile; row n_arows is a sentinel closing the ranges
@@ -138,7 +142,7 @@ static_assert(sizeof(ARow) == 16, "ARow layout");
 // a flat run [a, b) of the tile with its own value
 struct PatchRow {
   uint16_t a, b;
-  uint32_t reserved;
+  uint32_t plane;  // 0 / 1: row of an I/Q pair
   double val;
 };
 static_assert(sizeof(PatchRow) == 16, "PatchRow layout");
@@ -159,6 +163,7 @@ struct DevProgram {
   const CTerm* cterms;       // parallel to terms
   const int32_t* seg_start;  // [n_segs] first sample (channel-relative) owned by the segment
   const double* seg_val;     // [n_segs] value of a FLAT segment (offset + constant terms, clipped)
+  const double* seg_val1;    // [n_segs] the same for the second row of I/Q pairs (planes == 2)
   const int32_t* seg_wave;   // [n_segs] owning channel (host-built; pre-pass only)
   const uint32_t* pkt_off;       // [n_tiles + 1] packet offsets in 16-byte units
   const unsigned char* packets;  // the tile packets
@@ -166,6 +171,7 @@ struct DevProgram {
   int tile_samples;  // kMinTileSamples .. kMaxTileSamples, multiple of 128
   int n_slots;       // value slots per lane in shared memory: 1 (the constant 1.0) + max rows per segment
   int pkt_cap;       // bytes of ONE packet buffer in a warp's shared slice (two buffers per warp)
+  int planes;        // 2 if any channel is an I/Q pair (two tile buffers per warp), else 1
 };
 
 // one warp's work item: up to DevProgram::tile_samples consecutive samples of channel `wave`
@@ -189,6 +195,7 @@ struct PrepareBuffers {
   int32_t* seg_wave;
   int32_t* seg_start;
   double* seg_val;
+  double* seg_val1;
   SegPlan* seg_plan;
   uint8_t* row_slot;
   CTerm* cterms;

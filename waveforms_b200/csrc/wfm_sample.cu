@@ -156,8 +156,9 @@ __device__ int first_sample_at_or_after(const WfmWave& w, const double* __restri
 
 // the few channel fields a sample evaluation needs
 struct WaveEval {
-  double offset, clip_lo, clip_hi;
+  double offset;
   uint32_t flags;
+  int32_t wave;  // clip limits are read from the channel row when WFM_WAVE_CLIP is set (rare: not kept in registers)
 };
 
 // U values of one lane
@@ -202,16 +203,18 @@ static __device__ __noinline__ double eval_row_direct(const WfmFactor& f, double
 // Order of operations = the reference's (_waveform.pyx:134-152, waveform.py:690-692):
 // every term is amp * (((1 * f1^n1) * f2^n2) * ...), a member's terms are summed left to
 // right starting from 0, the member sums are added to the accumulator (offset).
-static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int seg, const WaveEval& w, double x,
-                                                      double& out_re, double& out_im) {
+template <bool kPlanes>
+static __device__ __forceinline__ void eval_segment_slow_impl(const DevProgram& P, int seg, const WaveEval& w, double x,
+                                                           double& out_re, double& out_im, int plane, double offset1) {
   const WfmSegPtr p0 = P.seg_ptr[seg], p1 = P.seg_ptr[seg + 1];
-  out_re = w.offset;
+  out_re = (kPlanes && plane) ? offset1 : w.offset;
   out_im = 0.0;
   if (p1.term == p0.term) return;  // zero segment: untouched by clip (calc_parts skips it)
   double g_re = 0.0, g_im = 0.0;
 #pragma unroll 1
   for (int t = p0.term; t < p1.term; ++t) {
     const WfmTerm tm = P.terms[t];
+    if (kPlanes && (int)((tm.flags & WFM_TERM_PLANE1) != 0) != plane) continue;
     double prod = 1.0;
 #pragma unroll 1
     for (int r = 0; r < tm.n_ref; ++r) {
@@ -229,7 +232,17 @@ static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int s
       g_re = g_im = 0.0;
     }
   }
-  if (w.flags & WFM_WAVE_CLIP) out_re = clip_value(out_re, w.clip_lo, w.clip_hi);
+  if (w.flags & WFM_WAVE_CLIP) out_re = clip_value(out_re, P.waves[w.wave].clip_lo, P.waves[w.wave].clip_hi);
+}
+static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int seg, const WaveEval& w, double x,
+                                                      double& out_re, double& out_im) {
+  eval_segment_slow_impl<false>(P, seg, w, x, out_re, out_im, 0, 0.0);
+}
+// one row of an I/Q pair: plane 0 / 1, only that row's terms are summed (row 1 starts from offset1)
+static __device__ __noinline__ void eval_segment_slow_row(const DevProgram& P, int seg, const WaveEval& w, double x,
+                                                          double& out_re, int plane, double offset1) {
+  double im;
+  eval_segment_slow_impl<true>(P, seg, w, x, out_re, im, plane, offset1);
 }
 
 // product of an extended term (more than three references or an exponent != 1) from the
@@ -254,11 +267,20 @@ static __device__ __noinline__ double term_product_ext(const DevProgram& P, int 
 // ---- the hot evaluator: one UNIT (U samples of one active segment) per call ------------------
 // blk: the segment's rows in the staged packet ({SRow CRow..}.. GRow.. CTerm..); sl: this
 // lane's value slots (slot k at sl + k * kSlotStride, slot 0 holds 1.0).
-template <int U>
+struct NoSwitch {
+  template <typename T>
+  __device__ __forceinline__ void operator()(const T&) const {}
+};
+// kPair: the segment may belong to an I/Q pair.  Its terms list the first row's groups, then the second row's; the
+// first second-row term carries kCTermPlaneSwitch: the first row's sum is complete there, `on_switch(total)` hands it
+// to the caller (who stores it) and the accumulation restarts from offset1.  `plane1` tells which row the returned
+// total belongs to.
+template <int U, bool kPair, typename Switch>
 __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                          bool has_ext, const DevProgram& P, int gseg, const WaveEval& w,
                                          const double (&x)[U], unsigned char* __restrict__ sl,
-                                         const double* __restrict__ erf_s, bool affine) {
+                                         const double* __restrict__ erf_s, bool affine, const double* offset1, bool& plane1,
+                                         Switch on_switch) {
   constexpr int kSlotStride = slot_stride(U);
   unsigned char* dst = sl + kSlotStride;  // slot 1
   // -- one range reduction + both polynomials per frequency; the further cosines of that
@@ -353,10 +375,19 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
     total.v[u] = w.offset;
     grp.v[u] = 0.0;
   }
+  if constexpr (kPair) plane1 = false;
 #pragma unroll 1
   for (int it = 0; it < n_term; ++it) {
     const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags
     const double amp = __hiloint2double((int)c.y, (int)c.x);
+    if constexpr (kPair) {
+      if ((c.w >> 16) & kCTermPlaneSwitch) {
+        on_switch(total);
+        plane1 = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u) total.v[u] = *offset1;  // the packet header in shared memory: not held in registers
+      }
+    }
     Val<U> prod;
     if (has_ext && (c.w >> 16) & kCTermExt) {
 #pragma unroll 1
@@ -394,7 +425,7 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
   }
   if (w.flags & WFM_WAVE_CLIP) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) total.v[u] = clip_value(total.v[u], w.clip_lo, w.clip_hi);
+    for (int u = 0; u < U; ++u) total.v[u] = clip_value(total.v[u], P.waves[w.wave].clip_lo, P.waves[w.wave].clip_hi);
   }
   return total;
 }
@@ -458,10 +489,11 @@ __device__ __forceinline__ void sincos_f32(double a, float& s_out, float& c_out)
   c_out = __uint_as_float(__float_as_uint(cc) ^ ((uint32_t)((n + 1) & 2) << 30));
 }
 
-template <int U>
+template <int U, bool kPair, typename Switch>
 __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict__ blk, int n_sc, int n_rot, int n_gen, int n_term,
                                                 const DevProgram& P, int gseg, const WaveEval& w, const double (&x)[U],
-                                                unsigned char* __restrict__ sl) {
+                                                unsigned char* __restrict__ sl, const double* offset1, bool& plane1,
+                                                Switch on_switch) {
   constexpr int kStride = 32 * 4 * U;  // float slots: half the fp64 stride inside the same slot area
   unsigned char* dst = sl + kStride;   // slot 1 (slot 0 holds 1.0f)
   const unsigned char* __restrict__ row = blk;
@@ -537,10 +569,22 @@ __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict_
     total.v[u] = (float)w.offset;
     grp.v[u] = 0.0f;
   }
+  if constexpr (kPair) plane1 = false;
 #pragma unroll 1
   for (int it = 0; it < n_term; ++it) {
     const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags (offsets for fp64 unit-1 slots: halve for floats)
     const float amp = (float)__hiloint2double((int)c.y, (int)c.x);
+    if constexpr (kPair) {
+      if ((c.w >> 16) & kCTermPlaneSwitch) {
+        Val<U> t0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) t0.v[u] = (double)total.v[u];
+        on_switch(t0);
+        plane1 = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u) total.v[u] = (float)*offset1;
+      }
+    }
     ValF<U> prod;
     if ((c.w >> 16) & kCTermExt) {
       // extended terms read fp64 slots: evaluate the segment's term in fp64 from the ABI tables
@@ -586,7 +630,7 @@ __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict_
   for (int u = 0; u < U; ++u) out.v[u] = (double)total.v[u];
   if (w.flags & WFM_WAVE_CLIP) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) out.v[u] = clip_value(out.v[u], w.clip_lo, w.clip_hi);
+    for (int u = 0; u < U; ++u) out.v[u] = clip_value(out.v[u], P.waves[w.wave].clip_lo, P.waves[w.wave].clip_hi);
   }
   return out;
 }
@@ -616,8 +660,8 @@ __global__ void count_active_kernel(DevProgram P, int64_t n_segs, unsigned long 
 
 // one thread per segment: start position, value of a flat segment, plan of an active one
 __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_start, double* __restrict__ seg_val,
-                                        SegPlan* __restrict__ seg_plan, uint8_t* __restrict__ row_slot,
-                                        CTerm* __restrict__ cterms, int64_t n_segs) {
+                                        double* __restrict__ seg_val1, SegPlan* __restrict__ seg_plan,
+                                        uint8_t* __restrict__ row_slot, CTerm* __restrict__ cterms, int64_t n_segs) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_segs) return;
   const WfmWave w = P.waves[P.seg_wave[s]];
@@ -625,21 +669,27 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
   seg_start[s] = k == 0 ? 0 : first_sample_at_or_after(w, P.x, (int)w.n, P.seg_bound[s - 1]);
   const WfmSegPtr p0 = P.seg_ptr[s], p1 = P.seg_ptr[s + 1];
   const int nf = p1.fac - p0.fac, nt = p1.term - p0.term;
-  double val = w.offset;
-  if (nf == 0 && nt > 0) {
-    // constant segment: offset + sum over stack members of (0 + sum of their constant terms)
-    double grp = 0.0;
-    for (int t = p0.term; t < p1.term; ++t) {
-      const WfmTerm tm = P.terms[t];
-      grp = add(grp, tm.n_ref > 0 ? CUDART_NAN : tm.amp_re);  // a term with factors would make the segment active
-      if (tm.flags & WFM_TERM_GROUP_END) {
-        val = add(val, grp);
-        grp = 0.0;
+  // value of a FLAT segment, per row of an I/Q pair: offset + sum over stack members of (0 + sum of their constant
+  // terms); a row without terms here is a zero segment of that row (untouched by clip, calc_parts skips it)
+  for (int plane = 0; plane < (seg_val1 ? 2 : 1); ++plane) {
+    double val = plane ? w.offset2 : w.offset;
+    if (nf == 0 && nt > 0) {
+      double grp = 0.0;
+      bool any = false;
+      for (int t = p0.term; t < p1.term; ++t) {
+        const WfmTerm tm = P.terms[t];
+        if ((int)((tm.flags & WFM_TERM_PLANE1) != 0) != plane) continue;
+        any = true;
+        grp = add(grp, tm.n_ref > 0 ? CUDART_NAN : tm.amp_re);  // a term with factors would make the segment active
+        if (tm.flags & WFM_TERM_GROUP_END) {
+          val = add(val, grp);
+          grp = 0.0;
+        }
       }
+      if (any && (w.flags & WFM_WAVE_CLIP)) val = fmin(fmax(val, w.clip_lo), w.clip_hi);
     }
-    if (w.flags & WFM_WAVE_CLIP) val = fmin(fmax(val, w.clip_lo), w.clip_hi);
+    (plane ? seg_val1 : seg_val)[s] = val;
   }
-  seg_val[s] = val;
 
   // plan: rows by class, value slots in class order
   int n_sc = 0, n_rot = 0, n_gen = 0;
@@ -679,6 +729,8 @@ __global__ void prepare_segments_kernel(DevProgram P, int32_t* __restrict__ seg_
       else o[r] = (uint16_t)(row_slot[p0.fac + rf.slot] * slot_stride(1));
     }
     uint16_t flags = (tm.flags & WFM_TERM_GROUP_END) ? kCTermGroupEnd : 0u;
+    // the first second-row term of an I/Q pair
+    if ((tm.flags & WFM_TERM_PLANE1) && (t == 0 || !(P.terms[p0.term + t - 1].flags & WFM_TERM_PLANE1))) flags |= kCTermPlaneSwitch;
     if (ext) {
       flags |= kCTermExt;
       o[0] = o[1] = o[2] = 0;
@@ -737,8 +789,10 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
       L.n_arows += 1;
       L.blk16 += P.seg_plan[w.seg_begin + k].blk16;
       L.n_units += (b - a + P.unit - 1) / P.unit;
-    } else if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) {
-      L.n_patch += 1;
+    } else {
+      if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) L.n_patch += 1;
+      if ((w.flags & WFM_WAVE_PAIR) && __double_as_longlong(P.seg_val1[w.seg_begin + k]) != __double_as_longlong(w.offset2))
+        L.n_patch += 1;
     }
   }
   // ARow::rel addresses 16-byte units with 12 bits
@@ -889,6 +943,8 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
     h.n_patch = L.cold ? 0 : (uint16_t)L.n_patch;
     h.n_units = L.cold ? 0 : (uint16_t)L.n_units;
     h.reserved[0] = h.reserved[1] = 0;
+    h.out1 = (w.flags & WFM_WAVE_PAIR) ? w.out_off2 + td.j0 : td.out0;
+    h.base1 = w.offset2;
     *reinterpret_cast<PacketHeader*>(pk) = h;
   }
   if (L.cold) return;
@@ -962,6 +1018,13 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
         if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 0u, v};
         ip += 1;
       }
+      if (w.flags & WFM_WAVE_PAIR) {
+        const double v1 = P.seg_val1[seg];
+        if (__double_as_longlong(v1) != __double_as_longlong(w.offset2)) {
+          if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 1u, v1};
+          ip += 1;
+        }
+      }
     }
   }
   if (lane == 0 && L.n_arows) {
@@ -1029,18 +1092,20 @@ __device__ __forceinline__ void fill_tile(unsigned char* p, int n_rows, double v
 }
 
 // per-warp shared-memory slice (dynamic shared memory; all sub-arrays 16-byte aligned):
-//   [out: tile_samples x OutT][slots: n_slots x slot_stride(unit)][packet buffer 0][packet buffer 1][2 mbarriers]
-__host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int unit, int pkt_cap, size_t esz) {
-  size_t b = (size_t)tile_samples * esz + (size_t)n_slots * slot_stride(unit) + 2 * (size_t)pkt_cap + 16;
+//   [out: planes x tile_samples x OutT][slots: n_slots x slot_stride(unit)][packet buffer 0][packet buffer 1][2 mbarriers]
+// (planes = 2 when the program holds I/Q pairs: one tile buffer per output row)
+__host__ __device__ inline size_t warp_slice_bytes(int tile_samples, int n_slots, int unit, int pkt_cap, size_t esz, int planes) {
+  size_t b = (size_t)planes * tile_samples * esz + (size_t)n_slots * slot_stride(unit) + 2 * (size_t)pkt_cap + 16;
   return (b + 127) & ~(size_t)127;
 }
 
 // the cold path of a tile (its packet would not fit the warp's buffers): per-sample
 // search, tables in global memory, direct stores
-template <typename OutT, bool kAccumulate>
-__device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDesc& td, OutT* __restrict__ dst, int lane) {
+template <typename OutT, bool kAccumulate, bool kPair>
+__device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDesc& td, OutT* __restrict__ out, int lane) {
+  OutT* __restrict__ dst = out + td.out0;
   const WfmWave w = P.waves[td.wave];
-  const WaveEval we{w.offset, w.clip_lo, w.clip_hi, w.flags};
+  const WaveEval we{w.offset, w.flags, td.wave};
   const int32_t* __restrict__ st = P.seg_start + td.seg0;
   for (int jj = lane; jj < td.cnt; jj += 32) {
     int lo = 0, hi = td.nb - 1;
@@ -1049,8 +1114,17 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
       if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
     }
     double re, im;
-    eval_segment_slow(P, td.seg0 + lo, we, abscissa(w, P.x, td.j0 + jj), re, im);
-    dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
+    const double xv = abscissa(w, P.x, td.j0 + jj);
+    if (kPair && (w.flags & WFM_WAVE_PAIR)) {
+      OutT* __restrict__ dst1 = out + w.out_off2 + td.j0;
+      eval_segment_slow_row(P, td.seg0 + lo, we, xv, re, 0, 0.0);
+      dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
+      eval_segment_slow_row(P, td.seg0 + lo, we, xv, re, 1, w.offset2);
+      dst1[jj] = kAccumulate ? (OutT)add((double)dst1[jj], re) : (OutT)re;
+    } else {
+      eval_segment_slow(P, td.seg0 + lo, we, xv, re, im);
+      dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
+    }
   }
 }
 
@@ -1065,17 +1139,19 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 #endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
-template <typename OutT, bool kAccumulate, int U, int kBatch>
+template <typename OutT, bool kAccumulate, int U, int kBatch, bool kPair>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
                   OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
   constexpr int V = OutVec<OutT>::N;
+  constexpr int kPlanes = kPair ? 2 : 1;
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   // this warp's private slice
-  unsigned char* slice = k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, U, P.pkt_cap, sizeof(OutT));
+  unsigned char* slice =
+      k1_smem + (size_t)warp_in_cta * warp_slice_bytes(P.tile_samples, P.n_slots, U, P.pkt_cap, sizeof(OutT), kPlanes);
   OutT* s_out = reinterpret_cast<OutT*>(slice);
-  unsigned char* s_slots = slice + (size_t)P.tile_samples * sizeof(OutT);
+  unsigned char* s_slots = slice + (size_t)kPlanes * P.tile_samples * sizeof(OutT);
   constexpr int kSlotStride = slot_stride(U);
   unsigned char* s_pkt = s_slots + (size_t)P.n_slots * kSlotStride;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
@@ -1203,7 +1279,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     OutT* __restrict__ dst = out + h->out0;
 
     if (flags & kPacketCold) {
-      sample_tile_cold<OutT, kAccumulate>(P, tiles[t], dst, lane);
+      sample_tile_cold<OutT, kAccumulate, kPair>(P, tiles[t], out, lane);
       __syncwarp();
       ++it;
       continue;
@@ -1217,20 +1293,23 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     // value; flat segments with another value and the active samples overwrite it below
     fill_tile(reinterpret_cast<unsigned char*>(s_out) + lane * 16, P.tile_samples * (int)sizeof(OutT) / 512, base,
               sizeof(OutT) == 4);
+    if constexpr (kPair) {
+      if (flags & WFM_WAVE_PAIR)
+        fill_tile(reinterpret_cast<unsigned char*>(s_out + P.tile_samples) + lane * 16, P.tile_samples * (int)sizeof(OutT) / 512,
+                  h->base1, sizeof(OutT) == 4);
+    }
     __syncwarp();
 
     const ARow* __restrict__ arows = reinterpret_cast<const ARow*>(pk + sizeof(PacketHeader));
     const PatchRow* __restrict__ patches = reinterpret_cast<const PatchRow*>(arows + (n_arows ? n_arows + 1 : 0));
     // ---- flat segments with their own value ----------------------------------------------
-    for (int i = 0; i < n_patch; ++i) fill_run(s_out, (int)patches[i].a, (int)patches[i].b, patches[i].val, lane);
+    for (int i = 0; i < n_patch; ++i)
+      fill_run(kPair && patches[i].plane ? s_out + P.tile_samples : s_out, (int)patches[i].a, (int)patches[i].b, patches[i].val,
+               lane);
 
     // ---- the tile's ACTIVE samples: units dealt round-robin to the lanes -------------------
     if (n_units > 0) {
-      WaveEval we{base, 0.0, 0.0, flags};
-      if (flags & WFM_WAVE_CLIP) {
-        we.clip_lo = P.waves[h->wave].clip_lo;
-        we.clip_hi = P.waves[h->wave].clip_hi;
-      }
+      const WaveEval we{base, flags, h->wave};
       const double t0 = h->t0, delta = h->delta;
       const int64_t j0 = h->j0;
       const bool plain_grid = !(flags & (WFM_WAVE_EXPLICIT_X | WFM_WAVE_LAST_OVERRIDE | WFM_WAVE_PRESHIFT));
@@ -1254,24 +1333,55 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           for (int u = 0; u < U; ++u) x[u] = abscissa(P.waves[h->wave], P.x, j0 + min(jj + u, cnt - 1));
         }
         Val<U> r;
-        if (sflags & kSegWide) {
-#pragma unroll 1
-          for (int u = 0; u < U; ++u) {
-            double im;
-            eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
-          }
-        } else {
-          if constexpr (sizeof(OutT) == 4) {
-            r = eval_unit_f32<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
-                                 (int)rw.w, we, x, s_slots + lane * 4 * U);
-          } else {
-            r = eval_unit<U>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
-                             (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X));
-          }
-        }
+        if constexpr (kPair) {
+          bool plane1 = false;
+          // the first row of an I/Q pair is complete when its last term has been added: into the first tile buffer
+          auto first_row = [&](const Val<U>& v) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (u < n_valid) s_out[jj + u] = (OutT)r.v[u];
+            for (int u = 0; u < U; ++u)
+              if (u < n_valid) s_out[jj + u] = (OutT)v.v[u];
+          };
+          if (sflags & kSegWide) {
+            const bool two = flags & WFM_WAVE_PAIR;
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) eval_segment_slow_row(P, (int)rw.w, we, x[u], r.v[u], 0, 0.0);
+            if (two) {
+              first_row(r);
+              plane1 = true;
+#pragma unroll 1
+              for (int u = 0; u < U; ++u) eval_segment_slow_row(P, (int)rw.w, we, x[u], r.v[u], 1, h->base1);
+            }
+          } else if constexpr (sizeof(OutT) == 4) {
+            r = eval_unit_f32<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
+                                       (int)rw.w, we, x, s_slots + lane * 4 * U, &h->base1, plane1, first_row);
+          } else {
+            r = eval_unit<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                                   (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X), &h->base1, plane1, first_row);
+          }
+          OutT* row_buf = plane1 ? s_out + P.tile_samples : s_out;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (u < n_valid) row_buf[jj + u] = (OutT)r.v[u];
+        } else {
+          NoSwitch none;
+          bool unused;
+          if (sflags & kSegWide) {
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+              double im;
+              eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
+            }
+          } else if constexpr (sizeof(OutT) == 4) {
+            r = eval_unit_f32<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
+                                        (int)rw.w, we, x, s_slots + lane * 4 * U, nullptr, unused, none);
+          } else {
+            r = eval_unit<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                                    (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X), nullptr, unused, none);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (u < n_valid) s_out[jj + u] = (OutT)r.v[u];
+        }
       }
     }
 
@@ -1280,15 +1390,31 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
       // out += tile (Waveform.__call__(..., accumulate=True)): read-modify-write epilogue
       __syncwarp();
       for (int p = lane; p < cnt; p += 32) dst[p] = (OutT)add((double)dst[p], (double)s_out[p]);
+      if constexpr (kPair) {
+        if (flags & WFM_WAVE_PAIR) {
+          OutT* __restrict__ dst1 = out + h->out1;
+          for (int p = lane; p < cnt; p += 32) dst1[p] = (OutT)add((double)dst1[p], (double)s_out[P.tile_samples + p]);
+        }
+      }
     } else {
-      // the whole tile as one TMA bulk copy
+      // the whole tile as one TMA bulk copy (an I/Q pair: one per row)
       fence_proxy_async_smem();
       __syncwarp();
       const int n_bulk = cnt & ~(V - 1);  // 16-byte multiple; the ragged tail goes out as scalars
       if (lane == 0 && n_bulk > 0) {
-        bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT), l2_evict_first_policy());
+        const uint64_t policy = l2_evict_first_policy();
+        bulk_s2g_evict_first(dst, s_out, (uint32_t)n_bulk * sizeof(OutT), policy);
+        if constexpr (kPair) {
+          if (flags & WFM_WAVE_PAIR)
+            bulk_s2g_evict_first(out + h->out1, s_out + P.tile_samples, (uint32_t)n_bulk * sizeof(OutT), policy);
+        }
       }
-      if (n_bulk + lane < cnt) dst[n_bulk + lane] = s_out[n_bulk + lane];
+      if (n_bulk + lane < cnt) {
+        dst[n_bulk + lane] = s_out[n_bulk + lane];
+        if constexpr (kPair) {
+          if (flags & WFM_WAVE_PAIR) (out + h->out1)[n_bulk + lane] = s_out[P.tile_samples + n_bulk + lane];
+        }
+      }
     }
     __syncwarp();  // all reads of the packet and of the tail of s_out are done
     ++it;
@@ -1332,8 +1458,8 @@ cudaError_t launch_prepare_segments(const DevProgram& P, const PrepareCounts& n,
   auto blocks = [&](int64_t items) { return (unsigned)((items + threads - 1) / threads); };
   if (n.n_waves > 0 && n.n_segs > 0) mark_seg_wave_kernel<<<blocks(n.n_waves * 32), threads, 0, stream>>>(P, b.seg_wave, n.n_waves);
   if (n.n_segs > 0)
-    prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, b.seg_start, b.seg_val, b.seg_plan, b.row_slot, b.cterms,
-                                                                      n.n_segs);
+    prepare_segments_kernel<<<blocks(n.n_segs), threads, 0, stream>>>(P, b.seg_start, b.seg_val, b.seg_val1, b.seg_plan,
+                                                                      b.row_slot, b.cterms, n.n_segs);
   return cudaGetLastError();
 }
 
@@ -1372,7 +1498,7 @@ cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int6
 int warp_fixed_bytes(int n_slots, int unit) { return n_slots * slot_stride(unit) + 16 + 128; }
 
 size_t sample_smem_bytes(const DevProgram& P, int dtype) {
-  return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.unit, P.pkt_cap, dtype == WFM_F32 ? 4 : 8);
+  return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.unit, P.pkt_cap, dtype == WFM_F32 ? 4 : 8, P.planes == 2 ? 2 : 1);
 }
 
 // tile counters of the dynamic deal: one ring per device, never freed
@@ -1437,10 +1563,10 @@ static cudaError_t launch_cfg(K k, LaunchCfg* table, std::mutex& mu, size_t smem
   return cudaSuccess;
 }
 
-template <typename OutT, bool kAcc, int U, int kBatch>
+template <typename OutT, bool kAcc, int U, int kBatch, bool kPair>
 static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                int dtype, void* out, cudaStream_t stream) {
-  auto k = sample_kernel<OutT, kAcc, U, kBatch>;
+  auto k = sample_kernel<OutT, kAcc, U, kBatch, kPair>;
   static LaunchCfg cfg_table[64];
   static std::mutex cfg_mu;
   const size_t smem = sample_smem_bytes(P, dtype);
@@ -1492,14 +1618,21 @@ static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles,
   bool dynamic = n_tiles >= (int64_t)16 * 1024 && sizeof(OutT) == 8;
   if (deal == 'd') dynamic = true;
   if (deal == 's') dynamic = false;
-  if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
-  return launch_deal<OutT, kAcc, U, 0>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  if (P.planes == 2) {
+    if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    return launch_deal<OutT, kAcc, U, 0, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  }
+  if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  return launch_deal<OutT, kAcc, U, 0, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 }
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
                           int accumulate, void* out, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
   if (tile_begin + n_tiles > INT32_MAX) return cudaErrorInvalidValue;
+#ifdef WFM_K1_ONLY  // register-allocation experiments: one instantiation only (compiles in seconds)
+  return launch_deal<double, false, 1, WFM_K1_DYNAMIC, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+#else
   if (dtype == WFM_F64 || dtype == WFM_F32) {
     const int sel = (dtype == WFM_F32 ? 4 : 0) | (accumulate ? 2 : 0) | (P.unit == 2 ? 1 : 0);
     switch (sel) {
@@ -1514,6 +1647,7 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
     }
   }
   return cudaErrorInvalidValue;  // WFM_C128 is assembled from two real planes (wfm_api.cu)
+#endif
 }
 
 }  // namespace wfm

@@ -122,10 +122,10 @@ def apply_channel_filters(out, batch, waveforms, mode=None):
             continue
         sos, initial = w.filters
         sos = np.ascontiguousarray(np.asarray(sos, dtype=np.float64)).reshape(-1, 6)
-        key = (sos.tobytes(), float(initial or 0.0), int(batch.waves['n'][k]))
+        key = (sos.tobytes(), float(initial or 0.0), int(batch.chan_n[k]))
         groups.setdefault(key, (sos, [])) [1].append(k)
     for (_, initial, n), (sos, idx) in groups.items():
-        offs = [int(batch.waves['out_off'][k]) for k in idx]
+        offs = [int(batch.chan_off[k]) for k in idx]
         pitch = offs[1] - offs[0] if len(offs) > 1 else n
         regular = len(offs) > 1 and pitch >= n and all(b - a == pitch for a, b in zip(offs, offs[1:]))
         if regular:

@@ -108,7 +108,7 @@ def load_library():
         ]
         lib.wfm_calibrate_fp64.argtypes = [C.POINTER(C.c_double), C.c_int32, C.c_void_p]
         lib.wfm_calibrate_copy.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
-        if lib.wfm_abi_version() != 1:
+        if lib.wfm_abi_version() != 2:
             raise EngineUnavailable('libwfmb200.so ABI version mismatch')
         _lib = lib
         return lib

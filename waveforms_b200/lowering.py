@@ -36,14 +36,15 @@ WAVE_DT = np.dtype([('t0', '<f8'), ('delta', '<f8'), ('x_last', '<f8'),
                     ('clip_lo', '<f8'), ('clip_hi', '<f8'),
                     ('pre_shift', '<f8'), ('offset', '<f8'), ('n', '<i8'),
                     ('out_off', '<i8'), ('x_off', '<i8'), ('seg_begin', '<i4'),
-                    ('n_seg', '<i4'), ('flags', '<u4'), ('reserved', '<u4')])
+                    ('n_seg', '<i4'), ('flags', '<u4'), ('reserved', '<u4'),
+                    ('out_off2', '<i8'), ('offset2', '<f8')])
 SEGPTR_DT = np.dtype([('fac', '<i4'), ('term', '<i4')])
 FACTOR_DT = np.dtype([('func', '<i4'), ('arg_off', '<i4'), ('shift', '<f8'),
                       ('a0', '<f8'), ('a1', '<f8')])
 TERM_DT = np.dtype([('amp_re', '<f8'), ('amp_im', '<f8'), ('ref_begin', '<i4'),
                     ('n_ref', '<i4'), ('flags', '<u4'), ('reserved', '<u4')])
 REF_DT = np.dtype([('expo', '<f8'), ('slot', '<i4'), ('kind', '<i4')])
-assert WAVE_DT.itemsize == 96 and FACTOR_DT.itemsize == 32
+assert WAVE_DT.itemsize == 112 and FACTOR_DT.itemsize == 32
 assert TERM_DT.itemsize == 32 and REF_DT.itemsize == 16
 
 WAVE_EXPLICIT_X = 0x1
@@ -51,7 +52,9 @@ WAVE_LAST_OVERRIDE = 0x2
 WAVE_CLIP = 0x4
 WAVE_PRESHIFT = 0x8
 WAVE_COMPLEX = 0x10
+WAVE_PAIR = 0x20
 TERM_GROUP_END = 0x1
+TERM_PLANE1 = 0x2
 POW_ONE, POW_INT, POW_GEN = 0, 1, 2
 MAX_INT_POW = 64
 
@@ -141,6 +144,26 @@ class LoweredBatch:
     x: np.ndarray
     total_samples: int
     any_complex: bool
+    # output row of every INPUT channel, in input order: (first sample, samples).  Equal to
+    # waves['out_off'] / waves['n'] unless channels were fused into I/Q pairs (one wave, two rows)
+    chan_off: np.ndarray = None
+    chan_n: np.ndarray = None
+
+    def __post_init__(self):
+        if self.chan_off is None:
+            pair = (self.waves['flags'] & WAVE_PAIR) != 0
+            if pair.any():
+                off = np.stack([self.waves['out_off'], self.waves['out_off2']], 1)
+                keep = np.stack([np.ones(len(pair), bool), pair], 1)
+                self.chan_off = off[keep]
+                self.chan_n = np.repeat(self.waves['n'], 1 + pair.astype(np.int64))
+            else:
+                self.chan_off = self.waves['out_off'].copy()
+                self.chan_n = self.waves['n'].copy()
+
+    @property
+    def n_channels(self):
+        return len(self.chan_off)
 
     _TABLES = ('waves', 'seg_bound', 'seg_ptr', 'facs', 'terms', 'refs', 'args',
                'x')
@@ -163,7 +186,8 @@ class LoweredBatch:
             out[k] = view
             off += (a.nbytes + 255) & ~255
         b = LoweredBatch(total_samples=self.total_samples,
-                         any_complex=self.any_complex, **out)
+                         any_complex=self.any_complex, chan_off=self.chan_off,
+                         chan_n=self.chan_n, **out)
         b._pinned = buf  # keeps the buffer alive
         return b
 
@@ -364,11 +388,13 @@ def _emit_rows(pools, rows):
         pools.n_fac += 1
 
 
-def _lower_segment(pools, groups, real_only=False):
+def _lower_segment(pools, groups, real_only=False, planes=None):
     """groups: list of expressions (one per stack member active here, in member
     order).  Appends the segment's factors / terms / refs to the pools.
     Returns True if any amplitude has a non-zero imaginary part (``real_only``:
-    imaginary parts are dropped, the channel returns ``.real``)."""
+    imaginary parts are dropped, the channel returns ``.real``).  ``planes[i]``
+    (I/Q pairs): output row 0 / 1 of group i, non-decreasing; the distinct
+    factors are shared by both rows."""
     order, seen = [], set()
     for expr in groups:
         for factors, _ in expr[0]:
@@ -379,9 +405,10 @@ def _lower_segment(pools, groups, real_only=False):
     rows, slot_of = _plan_slots(order)
     _emit_rows(pools, rows)
     cplx = False
-    for expr in groups:
+    for g, expr in enumerate(groups):
         terms, amps = expr
         last = len(amps) - 1
+        plane_flag = TERM_PLANE1 if (planes is not None and planes[g]) else 0
         for k, ((factors, exponents), amp) in enumerate(zip(terms, amps)):
             ref_begin = pools.n_ref
             for f, n in zip(factors, exponents):
@@ -395,17 +422,17 @@ def _lower_segment(pools, groups, real_only=False):
             else:
                 re, im = float(amp), 0.0
             pools.term.append((re, im, ref_begin, pools.n_ref - ref_begin,
-                               TERM_GROUP_END if k == last else 0, 0))
+                               (TERM_GROUP_END if k == last else 0) | plane_flag, 0))
             pools.n_term += 1
     return cplx
 
 
 def _merge_members(members):
-    """Union the members' bounds.  Returns (bounds, per-segment list of member
-    expressions that are non-zero there, in member order)."""
+    """Union the members' bounds.  Returns (bounds, per-segment list of the INDICES
+    of the members that are non-zero there, in member order)."""
     if len(members) == 1:
         bounds, seq = members[0]
-        return list(bounds), [[] if s == A.ZERO else [s] for s in seq]
+        return list(bounds), [[] if s == A.ZERO else [(0, s)] for s in seq]
     edges = set()
     for bounds, _ in members:
         edges.update(bounds)
@@ -414,20 +441,27 @@ def _merge_members(members):
     merged.append(math.inf)
     marr = np.asarray(merged, dtype=np.float64)
     active = [[] for _ in merged]
-    for bounds, seq in members:
+    for m, (bounds, seq) in enumerate(members):
         lo = 0  # merged index where the member's current segment starts
         for b, s in zip(bounds, seq):
             hi = int(np.searchsorted(marr, b, side='left')) + 1 if b != math.inf \
                 else len(merged)
             if s != A.ZERO:
                 for k in range(lo, hi):
-                    active[k].append(s)
+                    active[k].append((m, s))
             lo = hi
     return merged, active
 
 
-def _lower_channel(pools, chan):
-    bounds, active = _merge_members(chan.members)
+def _lower_channel(pools, chan, partner=None):
+    """One channel, or an I/Q pair (``partner`` = the second row): the pair's
+    members share one segment table — the union of all their bounds — and every
+    segment lists the first row's groups, then the second row's."""
+    members = list(chan.members)
+    n_first = len(members)
+    if partner is not None:
+        members += list(partner.members)
+    bounds, active = _merge_members(members)
     seg_begin = len(pools.bound)
     cplx = False
     for b, groups in zip(bounds, active):
@@ -435,14 +469,71 @@ def _lower_channel(pools, chan):
         pools.segfac.append(pools.n_fac)
         pools.segterm.append(pools.n_term)
         if groups:
-            cplx = _lower_segment(pools, groups, chan.real_only) or cplx
+            planes = [int(m >= n_first) for m, _ in groups] if partner is not None else None
+            cplx = _lower_segment(pools, [s for _, s in groups], chan.real_only, planes) or cplx
     return seg_begin, len(bounds), cplx
 
 
+def _has_complex_amp(chan):
+    return any(isinstance(v, (complex, np.complexfloating)) and not chan.real_only
+               for _, seq in chan.members for s in seq if s != A.ZERO for v in s[1])
+
+
+def _clipped(chan):
+    return chan.clip is not None and (chan.clip[0] != -math.inf or chan.clip[1] != math.inf)
+
+
+def can_pair(item_a, item_b, min_shared=0.5):
+    """True if two (Channel, Grid) items can be evaluated as ONE I/Q pair: the same
+    grid and pre-shift, real-valued and unclipped, and at least ``min_shared`` of
+    the second channel's distinct basis-function evaluations already occur in the
+    first one (the two outputs of one ``mixing`` call share 4 of their 5)."""
+    (a, ga), (b, gb) = item_a, item_b
+    if ga.x is not None or gb.x is not None:
+        if ga.x is None or gb.x is None or ga.x is not gb.x and not np.array_equal(ga.x, gb.x):
+            return False
+    elif (ga.n, ga.t0, ga.delta, ga.x_last) != (gb.n, gb.t0, gb.delta, gb.x_last):
+        return False
+    if ga.n != gb.n or a.pre_shift != b.pre_shift or a.real_only != b.real_only:
+        return False
+    if _clipped(a) or _clipped(b) or _has_complex_amp(a) or _has_complex_amp(b):
+        return False
+
+    def factors(ch):
+        out = set()
+        for _, seq in ch.members:
+            for s in seq:
+                if s != A.ZERO:
+                    for fs, _ in s[0]:
+                        out.update(fs)
+        return out
+
+    fa, fb = factors(a), factors(b)
+    if not fa or not fb:
+        return False
+    return len(fa & fb) >= min_shared * len(fb)
+
+
+def find_pairs(items, min_shared=0.5):
+    """Greedy left-to-right pairing of ADJACENT channels (how ``mixing`` hands out
+    I and Q).  Returns a list of items for ``lower``: ``(chan, grid)`` or
+    ``((chan_i, chan_q), grid)``, in input order."""
+    out, k = [], 0
+    while k < len(items):
+        if k + 1 < len(items) and can_pair(items[k], items[k + 1], min_shared):
+            out.append(((items[k][0], items[k + 1][0]), items[k][1]))
+            k += 2
+        else:
+            out.append(items[k])
+            k += 1
+    return out
+
+
 def lower(items) -> LoweredBatch:
-    """items: iterable of (Channel, Grid).  Output offsets are assigned
-    back-to-back, each channel's start padded to a multiple of 4 samples so
-    16-byte vector stores stay aligned for fp32 and fp64 output."""
+    """items: iterable of (Channel, Grid), or ((Channel, Channel), Grid) for two
+    channels evaluated as one I/Q pair (``find_pairs``).  Output offsets are
+    assigned back-to-back, each channel's start padded to a multiple of 4 samples
+    so 16-byte vector stores stay aligned for fp32 and fp64 output."""
     pools = _Pools()
     items = list(items)
     waves = np.zeros(len(items), dtype=WAVE_DT)
@@ -450,8 +541,12 @@ def lower(items) -> LoweredBatch:
     x_off = 0
     out_off = 0
     any_complex = False
+    chan_off, chan_n = [], []
     for i, (chan, grid) in enumerate(items):
-        seg_begin, n_seg, cplx = _lower_channel(pools, chan)
+        partner = None
+        if isinstance(chan, tuple):
+            chan, partner = chan
+        seg_begin, n_seg, cplx = _lower_channel(pools, chan, partner)
         any_complex = any_complex or cplx
         w = waves[i]
         flags = 0
@@ -466,8 +561,7 @@ def lower(items) -> LoweredBatch:
             if grid.x_last is not None:
                 flags |= WAVE_LAST_OVERRIDE
                 w['x_last'] = grid.x_last
-        if chan.clip is not None and (chan.clip[0] != -math.inf
-                                      or chan.clip[1] != math.inf):
+        if _clipped(chan):
             flags |= WAVE_CLIP
             w['clip_lo'], w['clip_hi'] = chan.clip
         if chan.pre_shift != 0:
@@ -481,8 +575,20 @@ def lower(items) -> LoweredBatch:
         w['out_off'] = out_off
         w['seg_begin'] = seg_begin
         w['n_seg'] = n_seg
-        w['flags'] = flags
+        chan_off.append(out_off)
+        chan_n.append(grid.n)
         out_off += (grid.n + 3) & ~3
+        if partner is not None:
+            if cplx or _clipped(chan) or _clipped(partner):
+                raise ValueError('an I/Q pair must be real-valued and unclipped (see can_pair)')
+            flags |= WAVE_PAIR
+            off2 = partner.offset
+            w['offset2'] = off2.real if isinstance(off2, complex) else off2
+            w['out_off2'] = out_off
+            chan_off.append(out_off)
+            chan_n.append(grid.n)
+            out_off += (grid.n + 3) & ~3
+        w['flags'] = flags
     n_segs = len(pools.bound)
     seg_ptr = np.zeros(n_segs + 1, dtype=SEGPTR_DT)
     seg_ptr['fac'][:n_segs] = pools.segfac
@@ -502,7 +608,9 @@ def lower(items) -> LoweredBatch:
         args=np.asarray(pools.args, dtype=np.float64),
         x=np.concatenate(xs) if xs else np.zeros(0, np.float64),
         total_samples=out_off,
-        any_complex=any_complex)
+        any_complex=any_complex,
+        chan_off=np.asarray(chan_off, dtype=np.int64),
+        chan_n=np.asarray(chan_n, dtype=np.int64))
 
 
 def replicate(batch: LoweredBatch, copies: int, amp_scale=None) -> LoweredBatch:
@@ -516,6 +624,7 @@ def replicate(batch: LoweredBatch, copies: int, amp_scale=None) -> LoweredBatch:
     waves = np.tile(batch.waves, R)
     rep = np.repeat(np.arange(R), nw)
     waves['out_off'] += rep * batch.total_samples
+    waves['out_off2'] += rep * batch.total_samples
     waves['seg_begin'] += (rep * ns).astype(np.int32)
     waves['x_off'] += rep * len(batch.x)
     seg_ptr = np.zeros(R * ns + 1, dtype=SEGPTR_DT)
@@ -540,4 +649,7 @@ def replicate(batch: LoweredBatch, copies: int, amp_scale=None) -> LoweredBatch:
                         refs=np.tile(batch.refs, R),
                         args=np.tile(batch.args, R), x=np.tile(batch.x, R),
                         total_samples=batch.total_samples * R,
-                        any_complex=batch.any_complex)
+                        any_complex=batch.any_complex,
+                        chan_off=(np.tile(batch.chan_off, R) +
+                                  np.repeat(np.arange(R), len(batch.chan_off)) * batch.total_samples),
+                        chan_n=np.tile(batch.chan_n, R))
