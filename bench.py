@@ -22,6 +22,13 @@ One JSON line on stdout (rank 0):
            the measured HBM bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the reference's compiled evaluator (oracle/_ref) or the oracle
            port timed on this host on a bounded sample (rank 0, N=1)
+and, at N = 1 (tools/bench_extras.py; --no-extras skips them):
+  parity        this step's output rows compared with the reference evaluator, in the run
+  calibration   in-run fp64-FMA and pinned-copy ceilings (wfm_calibrate_*)
+  configs       cfg1..cfg5 (BASELINE.json configs[0..4]) through K1 at per-GPU full size:
+                GSa/s, roofline {bound, frac}, cpu_baseline, parity each
+  pipeline_cfg4 sample -> sosfilt -> correct_reflection (-> predistort ker) per stage
+  fp32          the same cfg2 batch with fp32 output (1e-6 parity)
 """
 from __future__ import annotations
 
@@ -245,6 +252,8 @@ def main():
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip configs / pipeline_cfg4 / fp32 / calibration (N = 1 sections)')
+    ap.add_argument('--quick', action='store_true', help='extras at reduced size (smoke runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -266,12 +275,15 @@ def main():
         procs = os.cpu_count() or 1
         n, dt, kind = run_cpu(chans, args.steps, args.warmup, procs)
         gsa = n / dt / 1e9
+        # same config as the GPU arm (the same frame, 64 of which make the GPU's step); a CPU step is a BOUNDED
+        # sample of that workload: one of the frames
         line = {'impl': 'reference', 'metric': 'Waveform.sample GSa/s (batched)', 'value': gsa, 'unit': 'GSa/s',
                 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': dict(config, frames_per_gpu=1, note='one step = ONE frame (40 channels) on the host cores'),
+                'config': config,
                 'cpu_baseline': {'value': gsa, 'unit': 'GSa/s', 'cores': procs, 'kind': kind,
-                                 'sample': 'one full frame (40 ch x 200k samples) per step, process pool over channels'},
+                                 'sample': 'each step = ONE frame of the workload (40 ch x 200k samples) on the host cores, '
+                                           'process pool over channels'},
                 'e2e': {'value': gsa, 'unit': 'GSa/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
         print(json.dumps(line), flush=True)
@@ -282,7 +294,7 @@ def main():
     import torch.distributed as dist
     from waveforms_b200 import engine
     from waveforms_b200.batch import channel_grid
-    from waveforms_b200.lowering import lower, replicate
+    from waveforms_b200.lowering import find_pairs, lower, replicate
 
     numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else 'numa: not bound (single rank)'
     torch.cuda.set_device(local_rank)
@@ -293,11 +305,13 @@ def main():
     chans = build_frame(ns, seed=20260002)
     t_build = time.perf_counter() - t_b0
     t_l0 = time.perf_counter()
-    frame = lower([channel_grid(w) for w in chans])
+    frame = lower(find_pairs([channel_grid(w) for w in chans]))
     t_lower = time.perf_counter() - t_l0
     rng = np.random.default_rng(1000 + rank)
-    batch = replicate(frame, args.frames, amp_scale=rng.uniform(0.5, 1.0, args.frames))
-    samples_per_step = int(batch.waves['n'].sum())
+    frame_scale = rng.uniform(0.5, 1.0, args.frames)
+    frame_scale[0] = 1.0  # frame 0 is the unscaled frame the in-run parity check compares with the reference
+    batch = replicate(frame, args.frames, amp_scale=frame_scale)
+    samples_per_step = int(batch.chan_n.sum())
     code = engine.WFM_F64 if args.dtype == 'f64' else engine.WFM_F32
     esz = 8 if args.dtype == 'f64' else 4
     tdt = torch.float64 if args.dtype == 'f64' else torch.float32
@@ -336,9 +350,24 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     launches = prog.launch_count - launches0
-    # keep the sampler alive through the e2e leg as well, then summarise the timed region only
     n_kernel_clock = len(clock_lines)
-    # SURVEY §8d: a pure-store fill of the same buffer in the same run (calibration of what a
+
+    # ---- in-run parity: rows of THIS step's output against the reference evaluator
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from tools import bench_extras as X
+        rows = [0, 7, 20, 39]  # XY and Z channels of frame 0 (amplitude scale 1)
+        worst = 0.0
+        for r in rows:
+            off, cnt = int(batch.chan_off[r]), int(batch.chan_n[r])
+            got = out[off:off + cnt].cpu().numpy().astype(np.float64)
+            worst = max(worst, X.rel_err(got, X.cpu_sample(chans[r])))
+        tol = 1e-12 if args.dtype == 'f64' else 1e-6
+        parity = {'max_rel_err': worst, 'n_checked': len(rows), 'samples_checked': len(rows) * N_SAMP, 'tol': tol,
+                  'ok': bool(worst <= tol), 'against': X.ref_calc()[1],
+                  'what': 'full-size channels (200 000 samples) of frame 0 of the timed batch vs the reference evaluator'}
+
+    # SURVEY 8d: a pure-store fill of the same buffer in the same run (calibration of what a
     # store-only kernel reaches on this box; torch's fill kernel, not part of the product path)
     fill_ms = None
     if rank == 0:
@@ -361,51 +390,81 @@ def main():
 
     # ---- e2e: C-ABI with host buffers (IR upload + kernel + D2H every step)
     e2e = None
+    calibration = {}
     if not args.no_e2e:
-        host = torch.empty(batch.total_samples, dtype=tdt, pin_memory=True)
-        host_np = host.numpy()
         prog.close()
         del out
         torch.cuda.empty_cache()
+        # the ceiling first: what a plain pinned cudaMemcpy of this step's bytes reaches on this rank, with every rank
+        # copying at the same time (the e2e leg is bound by exactly these copies)
+        barrier()
+        d2h = engine.calibrate_copy(batch.total_samples * esz, 'd2h', 3, local_rank)
+        barrier()
+        h2d = engine.calibrate_copy(min(batch.nbytes(), 1 << 30), 'h2d', 3, local_rank)
+        calibration['copy'] = {'d2h_GBs': d2h['sustained_GBs'], 'd2h_best_GBs': d2h['best_GBs'], 'h2d_GBs': h2d['sustained_GBs'],
+                               'd2h_bytes': int(batch.total_samples * esz), 'concurrent_ranks': world,
+                               'what': 'cudaMemcpyAsync between pinned host and device memory, all ranks at once (wfm_calibrate_copy)'}
+
+        def run_e2e(batch_e, code_e, tdt_e, esz_e, steps_e):
+            host = torch.empty(batch_e.total_samples, dtype=tdt_e, pin_memory=True)
+            hosts = [host.numpy()]
+            try:
+                hosts.append(torch.empty(batch_e.total_samples, dtype=tdt_e, pin_memory=True).numpy())
+            except RuntimeError:  # no room for a second pinned buffer: single-buffered steps
+                pass
+            n_thr = len(hosts)
+            import concurrent.futures as cf
+
+            def one_step(k):
+                p2 = engine.Program(batch_e, local_rank)
+                p2.sample_host(dtype=code_e, out=hosts[k % n_thr])
+                p2.close()
+
+            # two host threads, each with its own pinned output buffer, alternate the steps: one step's upload +
+            # pre-pass overlaps the other's device->host copy (the library runs every call on the calling thread's
+            # stream).  Every step still uploads its IR and reads back every sample.
+            with cf.ThreadPoolExecutor(max_workers=n_thr) as pool:
+                list(pool.map(one_step, range(4)))  # warm-up: both threads, both buffers
+                barrier()
+                t0 = time.perf_counter()
+                list(pool.map(one_step, range(steps_e)))
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=f'cuda:{local_rank}')
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            d2h_bytes = int(batch_e.total_samples * esz_e)
+            floor_s = d2h_bytes / (d2h['sustained_GBs'] * 1e9)
+            return {'value': samples_per_step * world * steps_e / dt / 1e9, 'unit': 'GSa/s',
+                    'h2d_bytes_per_step': int(batch_e.nbytes()), 'd2h_bytes_per_step': d2h_bytes,
+                    'steps': steps_e, 'ms_per_step': dt / steps_e * 1e3,
+                    'copy_floor_ms_per_step': floor_s * 1e3, 'frac_of_copy_ceiling': floor_s / (dt / steps_e),
+                    'host_threads': n_thr}, float(hosts[0][:N_SAMP].sum())
+
         e_steps = max(4, min(args.steps, 6))
         batch = batch.pin()  # the step's inputs (the IR tables) in pinned host memory
-        # two host threads, each with its own pinned output buffer, alternate the steps: one
-        # step's upload + pre-pass overlaps the other's device->host copy (the library runs
-        # every call on the calling thread's stream).  Every step still uploads its IR and
-        # reads back every sample.
-        import concurrent.futures as cf
-        hosts = [host_np]
-        try:
-            hosts.append(torch.empty(batch.total_samples, dtype=tdt, pin_memory=True).numpy())
-        except RuntimeError:  # no room for a second pinned buffer: single-buffered steps
-            pass
-        n_thr = len(hosts)
-
-        def one_step(k):
-            p2 = engine.Program(batch, local_rank)
-            p2.sample_host(dtype=code, out=hosts[k % n_thr])
-            p2.close()
-
-        with cf.ThreadPoolExecutor(max_workers=n_thr) as pool:
-            list(pool.map(one_step, range(4)))  # warm-up: both threads, both buffers
-            barrier()
-            t0 = time.perf_counter()
-            list(pool.map(one_step, range(e_steps)))
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=f'cuda:{local_rank}')
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {'value': samples_per_step * world * e_steps / dt / 1e9, 'unit': 'GSa/s',
-               'h2d_bytes_per_step': int(batch.nbytes()), 'd2h_bytes_per_step': int(batch.total_samples * esz),
-               'steps': e_steps, 'ms_per_step': dt / e_steps * 1e3,
-               'path': 'per step: wfm_program_create(pinned host IR -> device, device pre-pass) + wfm_sample_host(kernel + '
+        e2e, checksum = run_e2e(batch, code, tdt, esz, e_steps)
+        e2e['path'] = ('per step: wfm_program_create(pinned host IR -> device, device pre-pass) + wfm_sample_host(kernel + '
                        'D2H of every sample into pinned host memory) + wfm_program_destroy; %d host thread(s) alternate the '
-                       'steps (double buffering)' % n_thr}
-        checksum = float(host_np[:N_SAMP].sum())
+                       'steps (double buffering); frac_of_copy_ceiling = time a plain pinned D2H copy of the same bytes takes '
+                       '(measured in this run, all ranks at once) / step time' % e2e['host_threads'])
+        # the host build beside it: this frame through the object API (as the reference builds it) + lowering
+        per_frame_s = t_build + t_lower
+        e2e['with_host_build'] = {
+            'object_api_s_per_distinct_frame': per_frame_s,
+            'GSa/s_if_every_frame_is_rebuilt': samples_per_step / (args.frames * per_frame_s + e2e['ms_per_step'] * 1e-3) / 1e9,
+            'note': 'the timed steps re-submit frames whose objects already exist (replicated with distinct amplitudes); a '
+                    'scheduler that rebuilds every frame through the object API spends this much host time per frame '
+                    '(the reference spends the same: the algebra is its own); waveforms_b200.builder removes it for pulse '
+                    'trains (configs.cfg3.host_build_s)'}
+        if args.dtype == 'f64' and not args.no_extras:
+            # fp32 output halves the bytes read back (north_star allows 1e-6): same steps, float32 buffers
+            e32, _ = run_e2e(batch, engine.WFM_F32, torch.float32, 4, e_steps)
+            e2e['fp32'] = {k: e32[k] for k in ('value', 'unit', 'd2h_bytes_per_step', 'ms_per_step', 'frac_of_copy_ceiling')}
     else:
         prog.close()
+        del out
         checksum = None
     stop_evt.set()
     sampler.join(timeout=3)
@@ -424,7 +483,7 @@ def main():
                 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': samples_per_step * esz, 'launch_ms': k1_ms,
                 # one ncu --set full capture at frames_per_launch frames, scaled to this launch's frames
-            'traffic': (traffic['dram_bytes_per_launch'] * args.frames / traffic['frames_per_launch']) if traffic else None,
+                'traffic': (traffic['dram_bytes_per_launch'] * args.frames / traffic['frames_per_launch']) if traffic else None,
                 'traffic_source': traffic.get('source') if traffic else None,
                 'frac_of_nominal_8TBs': achieved / 8000.0,
                 'store_fill_same_run': {'GB/s': fill_gbs, 'frac_of_it': achieved / fill_gbs,
@@ -447,10 +506,45 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
             'data': 'synthetic', 'config': config, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity,
             'kernel_layout': kernel_layout, 'numa': numa_note,
             'host': {'frame_build_s': t_build, 'frame_lower_s': t_lower, 'ir_bytes': int(batch.nbytes()),
                      'checksum_ch0': checksum}}
+
+    # ---- N = 1 only: the other configs, the cfg4 pipeline, the fp32 line, calibrations
+    if world == 1 and not args.no_extras and args.dtype == 'f64':
+        from tools import bench_extras as X
+        t_x = time.perf_counter()
+        try:
+            fp64 = engine.calibrate_fp64(5)
+            calibration['fp64'] = dict(fp64, what='8 independent DFMA chains per thread, 8 x 256 threads per SM, best of 5 '
+                                                  '(wfm_calibrate_fp64); dfma_per_s = fp64 FMA lane-operations per second')
+            # fp32 output of the SAME batch (north_star: 1e-6)
+            prog32 = engine.Program(batch, local_rank)
+            out32 = torch.empty(batch.total_samples, dtype=torch.float32, device=f'cuda:{local_rank}')
+            m32, b32 = X.time_gpu(torch, lambda: prog32.sample_device(dtype=engine.WFM_F32, out=out32), 50)
+            worst32 = 0.0
+            for r in (0, 20):
+                off, cnt = int(batch.chan_off[r]), int(batch.chan_n[r])
+                worst32 = max(worst32, X.rel_err(out32[off:off + cnt].cpu().numpy().astype(np.float64), X.cpu_sample(chans[r])))
+            line['fp32'] = {'value': samples_per_step / m32 / 1e6, 'unit': 'GSa/s', 'ms': m32,
+                            'roofline': {'bound': 'hbm', 'achieved': samples_per_step * 4 / m32 / 1e6, 'peak': peak, 'unit': 'GB/s',
+                                         'frac': samples_per_step * 4 / m32 / 1e6 / peak},
+                            'parity': {'max_rel_err': worst32, 'n_checked': 2, 'tol': 1e-6, 'ok': bool(worst32 <= 1e-6)}}
+            prog32.close()
+            del out32
+            torch.cuda.empty_cache()
+            line['configs'] = X.config_lines(ns, torch, engine, peak, fp64, quick=args.quick)
+            line['configs']['cfg2'] = {'channels': CHANNELS * args.frames, 'samples': samples_per_step, 'ms': k1_ms, 'GSa/s': value,
+                                       'roofline': {k: roofline[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac')},
+                                       'cpu_baseline': cpu, 'parity': parity, 'note': 'the headline workload (this line)'}
+            line['pipeline_cfg4'] = X.pipeline_cfg4(ns, torch, engine, peak, quick=args.quick)
+        except Exception as exc:  # noqa: BLE001 - the headline line must survive a failing extra section
+            import traceback
+            line['extras_error'] = ''.join(traceback.format_exception_only(type(exc), exc)).strip()
+            print(traceback.format_exc(), file=sys.stderr)
+        line['extras_s'] = time.perf_counter() - t_x
+    line['calibration'] = calibration or None
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

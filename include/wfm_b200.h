@@ -237,6 +237,26 @@ int  wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na,
 int  wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n,
                     int64_t stride, const double* H, void* stream);
 
+/* A response kept on the device (the kernel convolution of predistort, distortion.py:329-333, applies the same
+ * kernel to every batch): wfm_fft_response_create uploads H (HOST interleaved complex [n], np.fft.fftfreq order)
+ * once, on the current device; wfm_fft_filter_prepared then computes, for n_sig real signals of n_valid <= n samples
+ * each, the first n_valid samples of real(ifft(fft(x zero-padded to n) * H)) — the zero padding of a linear
+ * convolution is neither read nor written.  x, y DEVICE f64 with their own pitches (may alias). */
+typedef struct WfmFftResponse* wfm_fft_response_t;
+int  wfm_fft_response_create(const double* H, int64_t n, wfm_fft_response_t* out);
+int  wfm_fft_response_destroy(wfm_fft_response_t r);
+int  wfm_fft_filter_prepared(const double* x, double* y, int64_t n_sig, int64_t n_valid,
+                             int64_t x_stride, int64_t y_stride, wfm_fft_response_t r, void* stream);
+
+/* reflection (inverse = 0) / correct_reflection (inverse = 1) of distortion.py:208-221:
+ * y = real(ifft(fft(x) * H)) resp. / H with H(f) = (1 - A) / (1 - A exp(-2 pi i f tau)) on the
+ * np.fft.fftfreq(n, 1 / sample_rate) grid.  The response is built on the device and cached per
+ * (device, n, A, tau, sample_rate, inverse): the reference rebuilds it with NumPy on every call.
+ * x, y DEVICE f64 with their own pitches (may alias). */
+int  wfm_reflection_filter(const double* x, double* y, int64_t n_sig, int64_t n,
+                           int64_t x_stride, int64_t y_stride, double A, double tau,
+                           double sample_rate, int32_t inverse, void* stream);
+
 /* plain complex DFT of n_sig signals (DEVICE interleaved complex128, in
  * place), forward (sign = -1) or inverse with 1/n scaling (sign = +1) —
  * np.fft.fft / np.fft.ifft. */

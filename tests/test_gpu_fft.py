@@ -145,3 +145,44 @@ def test_correct_reflection_symbolic(ns):
     c = D.correct_reflection(w, 0.05, 13.3e-9)
     want = 1 / (1 - 0.05) * w - 0.05 / (1 - 0.05) * (w >> 13.3e-9)
     assert c.bounds == want.bounds and c.seq == want.seq
+
+
+@pytest.mark.parametrize('n', [64, 1000, 6144, 40000, 400000, 997])
+@pytest.mark.parametrize('inverse', [False, True])
+def test_reflection_response_built_on_the_device(n, inverse):
+    """wfm_reflection_filter builds H(f) = (1 - A) / (1 - A exp(-2 pi i f tau)) on the device (and caches it):
+    same result as numpy with the reference's host-built response (distortion.py:188-221)."""
+    import torch
+    from waveforms_b200.dsp import reflection_device
+    rng = np.random.default_rng(n)
+    fs, A, tau = 2e9, 0.05, 13.3e-9
+    x = rng.standard_normal((3, n))
+    freq = np.fft.fftfreq(n, 1 / fs)
+    H = (1 - A) / (1 - A * np.exp(-2j * np.pi * freq * tau))
+    want = np.fft.ifft(np.fft.fft(x, axis=-1) / H, axis=-1).real if inverse else np.fft.ifft(np.fft.fft(x, axis=-1) * H, axis=-1).real
+    dev = torch.from_numpy(x).cuda()
+    got = reflection_device(dev, A, tau, fs, inverse).cpu().numpy()
+    assert rel_err(got, want) <= FP64_TOL
+    out = torch.empty(3, n + 5, dtype=torch.float64, device='cuda')[:, :n]  # second call: cached response, own output pitch
+    got2 = reflection_device(dev, A, tau, fs, inverse, out=out).cpu().numpy()
+    assert np.array_equal(got, got2)
+    assert np.array_equal(dev.cpu().numpy(), x)  # the input is only read
+
+
+@pytest.mark.parametrize('n,K', [(1000, 31), (5000, 400), (20000, 1801), (400000, 1801)])
+def test_prepared_response_convolution_without_padding_buffers(n, K):
+    """predistort's centred kernel convolution (distortion.py:329-333) through a response prepared once on
+    the device; the zero padding up to the 7-smooth transform length is never stored."""
+    import torch
+    from scipy.signal import fftconvolve
+    from waveforms_b200 import distortion as D
+    rng = np.random.default_rng(n + K)
+    sig = rng.standard_normal((3, n))
+    ker = rng.standard_normal(K) * np.hanning(K)
+    want = np.stack([fftconvolve(np.hstack([np.zeros(n), s, np.zeros(n)]), ker, mode='full')[n + K // 2:2 * n + K // 2] for s in sig])
+    dev = torch.from_numpy(sig).cuda()
+    got = D.predistort(dev, ker=ker)
+    assert rel_err(got.cpu().numpy(), want) <= FP64_TOL
+    assert np.array_equal(dev.cpu().numpy(), sig)
+    got1 = D.predistort(sig[1], ker=ker)  # NumPy in, NumPy out, one signal, cached response
+    assert isinstance(got1, np.ndarray) and rel_err(got1, want[1]) <= FP64_TOL

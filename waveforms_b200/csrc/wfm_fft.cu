@@ -361,18 +361,25 @@ extern __shared__ __align__(16) unsigned char fft_smem_raw[];
 // One CTA per PAIR of real signals: z = x_a + i x_b goes through one complex transform.  H is
 // the Hermitian part of the caller's response (hermitian_part_kernel), so ifft(fft(z) H) =
 // y_a + i y_b with both real.
+// nv: samples the signals really hold (<= transform length): reads beyond are zeros, writes beyond are dropped — the
+// zero padding of a linear convolution costs no pass over memory
 struct PairIn {
   WFM_NO_RUN_TWIDDLE  // two real signals -> one complex
   const double* xa;
   const double* xb;  // nullptr: odd tail
-  __device__ __forceinline__ double2 operator()(int p, int) const { return make_double2(xa[p], xb ? xb[p] : 0.0); }
+  int nv;
+  __device__ __forceinline__ double2 operator()(int p, int) const {
+    return p < nv ? make_double2(xa[p], xb ? xb[p] : 0.0) : make_double2(0.0, 0.0);
+  }
 };
 struct PairOut {
   WFM_NO_RUN_TWIDDLE
   double* ya;
   double* yb;
   double scale;
+  int nv;
   __device__ __forceinline__ void operator()(int p, int, double2 v) const {
+    if (p >= nv) return;
     ya[p] = v.x * scale;
     if (yb) yb[p] = v.y * scale;
   }
@@ -385,17 +392,18 @@ struct MulHOut {
 };
 __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan P, const double* __restrict__ x,
                                                                         double* __restrict__ y, int64_t stride,
-                                                                        int64_t n_sig, const double2* __restrict__ H) {
+                                                                        int64_t y_stride, int64_t n_sig,
+                                                                        const double2* __restrict__ H, int nv) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + P.L;
   const double2* tw = stage_twiddles(P, b + P.L);
   const int64_t s0 = 2 * (int64_t)blockIdx.x;
   const bool two = s0 + 1 < n_sig;
   const double* xs = x + s0 * stride;
-  double* ys = y + s0 * stride;
+  double* ys = y + s0 * y_stride;
   double2* z = last_stage_target(P, a, b);
-  smem_fft(P, 0, -1.0, tw, PairIn{xs, two ? xs + stride : nullptr}, MulHOut{z, H}, a, b);
-  smem_fft(P, 0, +1.0, tw, SmemIn{z, 0}, PairOut{ys, two ? ys + stride : nullptr, 1.0 / (double)P.L}, z == a ? b : a, z);
+  smem_fft(P, 0, -1.0, tw, PairIn{xs, two ? xs + stride : nullptr, nv}, MulHOut{z, H}, a, b);
+  smem_fft(P, 0, +1.0, tw, SmemIn{z, 0}, PairOut{ys, two ? ys + y_stride : nullptr, 1.0 / (double)P.L, nv}, z == a ? b : a, z);
 }
 
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
@@ -421,13 +429,16 @@ struct ColsIn {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn;
+  int64_t nv;  // real input: samples the signals hold (zeros beyond)
   __device__ __forceinline__ double2 operator()(int r, int c) const {
     double2 v = make_double2(0.0, 0.0);
     if (c < cw) {
       const int64_t idx = (int64_t)r * N2 + c0 + c;
       if (kRealIn) {
-        v.x = static_cast<const double*>(pa)[idx];
-        if (pb) v.y = static_cast<const double*>(pb)[idx];
+        if (idx < nv) {
+          v.x = static_cast<const double*>(pa)[idx];
+          if (pb) v.y = static_cast<const double*>(pb)[idx];
+        }
       } else {
         v = static_cast<const double2*>(pa)[idx];
       }
@@ -455,6 +466,7 @@ struct ColsOut {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn, scale;
+  int64_t nv;  // real output: samples kept (writes beyond are dropped)
   template <int R>
   __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
     if (!kTwAfter || c >= cw) return;
@@ -470,6 +482,7 @@ struct ColsOut {
     if (c >= cw) return;
     const int64_t idx = (int64_t)r * N2 + c0 + c;
     if (kRealOut) {
+      if (idx >= nv) return;
       static_cast<double*>(pa)[idx] = v.x * scale;
       if (pb) static_cast<double*>(pb)[idx] = v.y * scale;
     } else {
@@ -481,7 +494,7 @@ template <bool kTwAfter, bool kRealIn, bool kRealOut>
 __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_kernel(FftPlan P, BigTwiddle T, int N2, int logc,
                                                                const void* __restrict__ in, void* __restrict__ out,
                                                                int64_t in_stride, int64_t out_stride, double sgn,
-                                                               double scale, int64_t n_real) {
+                                                               double scale, int64_t n_real, int64_t nv) {
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + ((size_t)N1 << logc);
@@ -498,7 +511,7 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     src.pa = static_cast<const double2*>(in) + sig * in_stride;
     src.pb = nullptr;
   }
-  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn;
+  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn; src.nv = nv;
   ColsOut<kTwAfter, kRealOut> dst;
   if (kRealOut) {
     dst.pa = static_cast<double*>(out) + 2 * sig * out_stride;
@@ -507,7 +520,7 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     dst.pa = static_cast<double2*>(out) + sig * out_stride;
     dst.pb = nullptr;
   }
-  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale;
+  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv;
   smem_fft(P, logc, sgn, tw, src, dst, a, b);
 }
 
@@ -872,7 +885,7 @@ static cudaError_t c2c_smooth(double2* data, int64_t n_sig, int64_t n, int64_t s
   const int C1 = 1 << lc1, C2 = 1 << lc2;
   dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_sig), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_sig);
   if ((e = set_smem(fft_cols_kernel<true, false, false>, smem1)) != cudaSuccess) goto done;
-  fft_cols_kernel<true, false, false><<<g1, kFftColsThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0, 0);
+  fft_cols_kernel<true, false, false><<<g1, kFftColsThreads, smem1, st>>>(P1, T, N2, lc1, data, scratch, stride, n, sgn, 1.0, 0, n);
   if ((e = cudaGetLastError()) != cudaSuccess) goto done;
   if ((e = set_smem(fft_rows_kernel<false>, smem2)) != cudaSuccess) goto done;
   fft_rows_kernel<false><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, data, n, stride, nullptr, sgn, scale);
@@ -979,6 +992,193 @@ static thread_local HStage g_hstage;
 
 }  // namespace wfm
 
+// ---- the response in the layout the chosen path reads ---------------------------------------
+// single-CTA and generic paths: the Hermitian part in natural order; two-level path: the
+// Hermitian part in the transposed order the row pass produces.
+namespace wfm {
+enum FilterPath { kPathSingle, kPathTwoLevel, kPathGeneric };
+static FilterPath choose_path(int64_t n, int* N1, int* N2) {
+  const bool smooth = is_smooth(n);
+  if (smooth && n <= kMaxPoints) return kPathSingle;
+  if (smooth && split_two_level(n, N1, N2)) return kPathTwoLevel;
+  return kPathGeneric;
+}
+// dH: natural-order response on the device -> ready (n complex, caller-allocated)
+static cudaError_t prepare_response(const double2* dH, double2* ready, int64_t n, cudaStream_t st) {
+  int N1 = 0, N2 = 0;
+  const int T = 256;
+  const unsigned gH = (unsigned)((n + T - 1) / T);
+  if (choose_path(n, &N1, &N2) == kPathTwoLevel) permute_h_kernel<<<gH, T, 0, st>>>(dH, ready, N1, N2);
+  else hermitian_part_kernel<<<gH, T, 0, st>>>(dH, ready, n);
+  return cudaGetLastError();
+}
+
+// y = real(ifft(fft(x) * H)) with the response already prepared (prepare_response)
+// n: transform length; nv <= n: samples the signals hold (the rest of the circular grid is zero padding that is never
+// read or written: x and y are n_sig rows of nv samples at their pitches)
+static int run_filter(const double* x, double* y, int64_t n_sig, int64_t n, int64_t x_stride, int64_t y_stride,
+                      const double2* ready, cudaStream_t st, int64_t nv = -1) {
+  if (nv < 0) nv = n;
+  cudaError_t e = cudaSuccess;
+  int rc = WFM_OK;
+  int N1 = 0, N2 = 0;
+  const FilterPath path = choose_path(n, &N1, &N2);
+  const int64_t n_pair = (n_sig + 1) / 2;  // two real signals per complex transform
+  const int T = 256;
+  const unsigned gH = (unsigned)((n + T - 1) / T);
+  if (path == kPathSingle) {
+    FftPlan P;
+    size_t smem;
+    e = get_plan((int)n, n, &P, &smem);
+    if (e == cudaSuccess) e = set_smem(fft_filter_single_kernel, smem);
+    if (e == cudaSuccess) {
+      fft_filter_single_kernel<<<(unsigned)n_pair, kFftThreads, smem, st>>>(P, x, y, x_stride, y_stride, n_sig, ready, (int)nv);
+      e = cudaGetLastError();
+    }
+  } else if (path == kPathTwoLevel) {
+    const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, WFM_FFT_ROWS_LOGC);
+    FftPlan P1, P2;
+    BigTwiddle BT;
+    size_t smem1 = 0, smem2 = 0;
+    double2* scratch = nullptr;
+    e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1);
+    if (e == cudaSuccess) e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2);
+    if (e == cudaSuccess) e = get_big_twiddle(n, &BT);
+    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
+    const int C1 = 1 << lc1, C2 = 1 << lc2;
+    dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_pair), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_pair);
+    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
+    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
+    if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
+    if (e == cudaSuccess) {
+      fft_cols_kernel<true, true, false><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, x_stride, n, -1.0, 1.0,
+                                                                         n_sig, nv);
+      fft_rows_kernel<true><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, ready, -1.0, 1.0);
+      fft_cols_kernel<false, false, true><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, y_stride, +1.0,
+                                                                          1.0 / (double)n, n_sig, nv);
+      e = cudaGetLastError();
+    }
+    if (scratch) cudaFreeAsync(scratch, st);
+  } else {
+    // generic: complex copy, forward, * H, inverse, real part
+    if (nv != n) return WFM_EUNSUPPORTED;  // padded grids are chosen 7-smooth by the callers
+    double2* c = nullptr;
+    e = cudaMallocAsync(&c, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
+    dim3 gn(gH, (unsigned)n_pair);
+    if (e == cudaSuccess) {
+      real_to_complex_kernel<<<gn, T, 0, st>>>(x, x_stride, c, n, n_sig);
+      e = c2c_any(c, n_pair, n, n, -1.0, 1.0, st);
+    }
+    if (e == cudaSuccess) {
+      pointwise_mul_kernel<<<gn, T, 0, st>>>(c, ready, n, n);
+      e = c2c_any(c, n_pair, n, n, +1.0, 1.0 / (double)n, st);
+    }
+    if (e == cudaSuccess) {
+      complex_to_real_kernel<<<gn, T, 0, st>>>(c, n, y, y_stride, n_sig);
+      e = cudaGetLastError();
+    }
+    if (c) cudaFreeAsync(c, st);
+    if (e == cudaErrorNotSupported) rc = WFM_EUNSUPPORTED;
+  }
+  if (rc != WFM_OK) return rc;
+  return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
+}
+
+// H(f) = (1 - A) / (1 - A exp(-2 pi i f tau)) (distortion.py:188-205) or its reciprocal, on the np.fft.fftfreq(n, d)
+// grid: f[k] = idx(k) * val, val = 1 / (n d) (numpy's own two steps), phase = ((-2 pi) f) tau rounded as numpy rounds it
+__global__ void reflection_response_kernel(double2* __restrict__ H, int64_t n, double val, double A, double tau, int inverse) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t idx = k < (n + 1) / 2 ? k : k - n;
+  const double f = (double)idx * val;
+  const double ph = __dmul_rn(__dmul_rn(-6.283185307179586, f), tau);
+  double sn, cs;
+  sincos(ph, &sn, &cs);
+  const double dr = 1.0 - A * cs, di = -(A * sn);  // 1 - A e
+  const double g = 1.0 - A;
+  if (inverse) {
+    H[k] = make_double2(dr / g, di / g);
+  } else {
+    const double m = g / (dr * dr + di * di);
+    H[k] = make_double2(dr * m, -di * m);
+  }
+}
+
+// prepared responses of reflection filters, kept on the device: a flux-line calibration uses the same (A, tau) for
+// every batch, the reference rebuilds H with NumPy on every call (distortion.py:209, :219)
+struct ReflKey {
+  int dev;
+  int64_t n;
+  double A, tau, fs;
+  int inverse;
+  bool operator==(const ReflKey& o) const {
+    return dev == o.dev && n == o.n && A == o.A && tau == o.tau && fs == o.fs && inverse == o.inverse;
+  }
+};
+struct ReflEntry {
+  ReflKey key;
+  double2* ready;
+  cudaEvent_t done;
+  uint64_t stamp;
+};
+static std::mutex g_refl_mu;
+static std::vector<ReflEntry> g_refl_cache;
+static uint64_t g_refl_clock = 0;
+constexpr size_t kReflCacheEntries = 16;
+}  // namespace wfm
+
+// a response kept on the device in the layout its transform length needs (wfm_fft_response_create)
+struct WfmFftResponse {
+  int device;
+  int64_t n;
+  double2* ready;
+};
+
+extern "C" int wfm_fft_response_create(const double* H, int64_t n, WfmFftResponse** out) {
+  using namespace wfm;
+  if (!H || !out || n <= 0) return WFM_EINVAL;
+  *out = nullptr;
+  keep_pool_memory();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return WFM_ECUDA;
+  const size_t h_bytes = sizeof(double2) * (size_t)n;
+  double2 *nat = nullptr, *ready = nullptr;
+  const cudaStream_t st = cudaStreamPerThread;
+  if (cudaMalloc(&ready, h_bytes) != cudaSuccess) return WFM_ENOMEM;
+  cudaError_t e = cudaMallocAsync(&nat, h_bytes, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nat, H, h_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = prepare_response(nat, ready, n, st);
+  if (nat) cudaFreeAsync(nat, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // ready for any stream from now on
+  if (e != cudaSuccess) {
+    cudaFree(ready);
+    return WFM_ECUDA;
+  }
+  *out = new WfmFftResponse{dev, n, ready};
+  return WFM_OK;
+}
+
+extern "C" int wfm_fft_response_destroy(WfmFftResponse* r) {
+  if (!r) return WFM_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(r->device);
+  cudaFree(r->ready);  // waits for work that still reads it
+  if (prev >= 0) cudaSetDevice(prev);
+  delete r;
+  return WFM_OK;
+}
+
+extern "C" int wfm_fft_filter_prepared(const double* x, double* y, int64_t n_sig, int64_t n_valid, int64_t x_stride,
+                                       int64_t y_stride, WfmFftResponse* r, void* stream) {
+  using namespace wfm;
+  if (!x || !y || !r || n_sig < 0 || n_valid < 0 || n_valid > r->n || (n_sig > 1 && (x_stride < n_valid || y_stride < n_valid)))
+    return WFM_EINVAL;
+  if (n_sig == 0 || n_valid == 0) return WFM_OK;
+  keep_pool_memory();
+  return run_filter(x, y, n_sig, r->n, x_stride, y_stride, r->ready, (cudaStream_t)stream, n_valid);
+}
+
 extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t n, int64_t stride, const double* H,
                               void* stream) {
   using namespace wfm;
@@ -991,82 +1191,75 @@ extern "C" int wfm_fft_filter(const double* x, double* y, int64_t n_sig, int64_t
   const size_t h_bytes = sizeof(double2) * (size_t)n;
   if ((e = g_hstage.reserve(h_bytes)) != cudaSuccess) return WFM_ECUDA;
   memcpy(g_hstage.host, H, h_bytes);
-  double2* dH = nullptr;
+  double2 *dH = nullptr, *ready = nullptr;
   if ((e = cudaMallocAsync(&dH, h_bytes, st)) != cudaSuccess) return WFM_ECUDA;
   e = cudaMemcpyAsync(dH, g_hstage.host, h_bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaEventRecord(g_hstage.used, st);
-  int rc = WFM_OK;
-  int N1 = 0, N2 = 0;
-  const bool smooth = is_smooth(n);
-  const int64_t n_pair = (n_sig + 1) / 2;  // two real signals per complex transform
-  const int T = 256;
-  const unsigned gH = (unsigned)((n + T - 1) / T);
-  if (e != cudaSuccess) {
-    // fall through to the common exit
-  } else if (smooth && n <= kMaxPoints) {
-    FftPlan P;
-    size_t smem;
-    e = get_plan((int)n, n, &P, &smem);
-    double2* dHs = nullptr;
-    if (e == cudaSuccess) e = set_smem(fft_filter_single_kernel, smem);
-    if (e == cudaSuccess) e = cudaMallocAsync(&dHs, h_bytes, st);
-    if (e == cudaSuccess) {
-      hermitian_part_kernel<<<gH, T, 0, st>>>(dH, dHs, n);
-      fft_filter_single_kernel<<<(unsigned)n_pair, kFftThreads, smem, st>>>(P, x, y, stride, n_sig, dHs);
-      e = cudaGetLastError();
-    }
-    if (dHs) cudaFreeAsync(dHs, st);
-  } else if (smooth && split_two_level(n, &N1, &N2)) {
-    const int lc1 = tile_logc(N1, WFM_FFT_COLS_LOGC), lc2 = tile_logc(N2, WFM_FFT_ROWS_LOGC);
-    FftPlan P1, P2;
-    BigTwiddle BT;
-    size_t smem1 = 0, smem2 = 0;
-    double2 *scratch = nullptr, *dHp = nullptr;
-    e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1);
-    if (e == cudaSuccess) e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2);
-    if (e == cudaSuccess) e = get_big_twiddle(n, &BT);
-    if (e == cudaSuccess) e = cudaMallocAsync(&dHp, h_bytes, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
-    const int C1 = 1 << lc1, C2 = 1 << lc2;
-    dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_pair), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_pair);
-    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
-    if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
-    if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
-    if (e == cudaSuccess) {
-      permute_h_kernel<<<gH, T, 0, st>>>(dH, dHp, N1, N2);
-      fft_cols_kernel<true, true, false><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, stride, n, -1.0, 1.0,
-                                                                         n_sig);
-      fft_rows_kernel<true><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, dHp, -1.0, 1.0);
-      fft_cols_kernel<false, false, true><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, stride, +1.0,
-                                                                          1.0 / (double)n, n_sig);
-      e = cudaGetLastError();
-    }
-    if (scratch) cudaFreeAsync(scratch, st);
-    if (dHp) cudaFreeAsync(dHp, st);
-  } else {
-    // generic: complex copy, forward, * H, inverse, real part
-    double2 *c = nullptr, *dHs = nullptr;
-    e = cudaMallocAsync(&c, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&dHs, h_bytes, st);
-    dim3 gn(gH, (unsigned)n_pair);
-    if (e == cudaSuccess) {
-      hermitian_part_kernel<<<gH, T, 0, st>>>(dH, dHs, n);
-      real_to_complex_kernel<<<gn, T, 0, st>>>(x, stride, c, n, n_sig);
-      e = c2c_any(c, n_pair, n, n, -1.0, 1.0, st);
-    }
-    if (e == cudaSuccess) {
-      pointwise_mul_kernel<<<gn, T, 0, st>>>(c, dHs, n, n);
-      e = c2c_any(c, n_pair, n, n, +1.0, 1.0 / (double)n, st);
-    }
-    if (e == cudaSuccess) {
-      complex_to_real_kernel<<<gn, T, 0, st>>>(c, n, y, stride, n_sig);
-      e = cudaGetLastError();
-    }
-    if (c) cudaFreeAsync(c, st);
-    if (dHs) cudaFreeAsync(dHs, st);
-    if (e == cudaErrorNotSupported) rc = WFM_EUNSUPPORTED;
-  }
+  if (e == cudaSuccess) e = cudaMallocAsync(&ready, h_bytes, st);
+  if (e == cudaSuccess) e = prepare_response(dH, ready, n, st);
+  int rc = e == cudaSuccess ? run_filter(x, y, n_sig, n, stride, stride, ready, st) : WFM_ECUDA;
+  if (ready) cudaFreeAsync(ready, st);
   cudaFreeAsync(dH, st);
-  if (rc != WFM_OK) return rc;
-  return e == cudaSuccess ? WFM_OK : WFM_ECUDA;
+  return rc;
+}
+
+// reflection (inverse = 0) / correct_reflection (inverse = 1) of /root/reference/waveforms/distortion.py:208-221 for
+// n_sig real signals: y = real(ifft(fft(x) * H)), resp. / H, H = reflection_filter(np.fft.fftfreq(n, 1 / sample_rate),
+// A, tau) built on the device and cached.  x and y may alias; each has its own pitch.
+extern "C" int wfm_reflection_filter(const double* x, double* y, int64_t n_sig, int64_t n, int64_t x_stride,
+                                     int64_t y_stride, double A, double tau, double sample_rate, int32_t inverse,
+                                     void* stream) {
+  using namespace wfm;
+  if (!x || !y || n_sig < 0 || n < 0 || (n_sig > 1 && (x_stride < n || y_stride < n)) || !(sample_rate > 0)) return WFM_EINVAL;
+  if (n_sig == 0 || n == 0) return WFM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  keep_pool_memory();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return WFM_ECUDA;
+  const ReflKey key{dev, n, A, tau, sample_rate, inverse ? 1 : 0};
+  double2* ready = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_refl_mu);
+    for (auto& en : g_refl_cache)
+      if (en.key == key) {
+        en.stamp = ++g_refl_clock;
+        ready = en.ready;
+        if (cudaStreamWaitEvent(st, en.done, 0) != cudaSuccess) return WFM_ECUDA;  // built on another stream, maybe
+        break;
+      }
+    if (!ready) {
+      const size_t h_bytes = sizeof(double2) * (size_t)n;
+      double2* nat = nullptr;
+      if (g_refl_cache.size() >= kReflCacheEntries) {  // evict the least recently used response
+        size_t old = 0;
+        for (size_t i = 1; i < g_refl_cache.size(); ++i)
+          if (g_refl_cache[i].stamp < g_refl_cache[old].stamp) old = i;
+        cudaEventSynchronize(g_refl_cache[old].done);
+        cudaFree(g_refl_cache[old].ready);
+        cudaEventDestroy(g_refl_cache[old].done);
+        g_refl_cache.erase(g_refl_cache.begin() + old);
+      }
+      ReflEntry en{key, nullptr, nullptr, ++g_refl_clock};
+      if (cudaMalloc(&en.ready, h_bytes) != cudaSuccess) return WFM_ENOMEM;
+      e = cudaMallocAsync(&nat, h_bytes, st);
+      if (e == cudaSuccess) {
+        const double d = 1.0 / sample_rate;            // np.fft.fftfreq(n, 1 / sample_rate): val = 1.0 / (n * d)
+        const double val = 1.0 / ((double)n * d);
+        reflection_response_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nat, n, val, A, tau, inverse ? 1 : 0);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = prepare_response(nat, en.ready, n, st);
+      if (nat) cudaFreeAsync(nat, st);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&en.done, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(en.done, st);
+      if (e != cudaSuccess) {
+        cudaFree(en.ready);
+        return WFM_ECUDA;
+      }
+      g_refl_cache.push_back(en);
+      ready = en.ready;
+    }
+  }
+  return run_filter(x, y, n_sig, n, x_stride, y_stride, ready, st);
 }

@@ -25,11 +25,15 @@ from scipy.signal import lfiltic, tf2zpk, zpk2sos, zpk2tf
 from . import dsp
 
 
-def _to_device(sig):
-    """(tensor, was_numpy)"""
+def _to_device(sig, copy=True):
+    """(tensor, was_numpy).  A CUDA tensor is copied unless ``copy=False`` (the caller
+    names its own output buffer, so the input is only read)."""
     import torch
     if isinstance(sig, torch.Tensor):
-        return sig.to(dtype=torch.float64).contiguous().clone(), False
+        t = sig.to(dtype=torch.float64)
+        if copy:
+            return t.contiguous().clone(), False
+        return (t if t.stride(-1) == 1 else t.contiguous()), False
     arr = np.ascontiguousarray(np.asarray(sig, dtype=np.float64))
     return torch.from_numpy(arr).cuda(), True
 
@@ -132,27 +136,26 @@ def reflection_filter(f, A, tau):
     return (1 - A) / (1 - A * np.exp(-2j * np.pi * f * tau))
 
 
-def reflection(sig, A, tau, sample_rate):
-    """ifft(fft(sig) * H).real on the GPU (reference :208-210)."""
-    dev, was_np = _to_device(sig)
-    freq = np.fft.fftfreq(dev.shape[-1], 1 / sample_rate)
-    out = dsp.fft_filter_device(dev, reflection_filter(freq, A, tau), out=dev)
-    return _from_device(out, was_np)
+def reflection(sig, A, tau, sample_rate, out=None):
+    """ifft(fft(sig) * H).real on the GPU (reference :208-210).  ``out``: CUDA tensor
+    that receives the result when ``sig`` is a CUDA tensor (may be ``sig`` itself)."""
+    dev, was_np = _to_device(sig, copy=out is None)
+    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=False, out=dev if out is None else out)
+    return _from_device(res, was_np)
 
 
-def correct_reflection(sig, A, tau, sample_rate=None):
+def correct_reflection(sig, A, tau, sample_rate=None, out=None):
     """Waveform -> symbolic inverse (sig/(1-A) - A/(1-A) (sig >> tau));
-    sampled signal -> ifft(fft(sig) / H).real on the GPU (reference :213-223)."""
+    sampled signal -> ifft(fft(sig) / H).real on the GPU (reference :213-223).
+    ``out``: CUDA tensor that receives the result when ``sig`` is a CUDA tensor."""
     from .waveform import Waveform
     if isinstance(sig, Waveform):
         return 1 / (1 - A) * sig - A / (1 - A) * (sig >> tau)
     if sample_rate is None:
         raise ValueError('sample_rate is not given')
-    dev, was_np = _to_device(sig)
-    freq = np.fft.fftfreq(dev.shape[-1], 1 / sample_rate)
-    out = dsp.fft_filter_device(dev, 1 / reflection_filter(freq, A, tau),
-                                out=dev)
-    return _from_device(out, was_np)
+    dev, was_np = _to_device(sig, copy=out is None)
+    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=True, out=dev if out is None else out)
+    return _from_device(res, was_np)
 
 
 def combine_filters(filters):
@@ -209,11 +212,27 @@ def dsp_next_fast_len(m):
     return m
 
 
+_KERNEL_RESPONSES = {}  # (kernel bytes, n, device) -> dsp.PreparedResponse, least recently used first
+
+
+def _kernel_response(ker, n, device):
+    """The centred-convolution response of ``ker`` for signals of ``n`` samples, prepared
+    on ``device`` once: a calibration applies the same kernel to every batch."""
+    key = (ker.tobytes(), int(n), int(device))
+    resp = _KERNEL_RESPONSES.pop(key, None)
+    if resp is None:
+        Hk, _ = _centered_kernel_response(ker, n)
+        resp = dsp.PreparedResponse(Hk, device)
+        while len(_KERNEL_RESPONSES) >= 8:
+            _KERNEL_RESPONSES.pop(next(iter(_KERNEL_RESPONSES))).close()
+    _KERNEL_RESPONSES[key] = resp
+    return resp
+
+
 def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
                initial_x=None, initial_y=None, zi=None, return_zf: bool = False):
     """IIR predistortion (lfilter with lfiltic initial state) followed by an
     optional centred kernel convolution; reference :289-337."""
-    import torch
     dev, was_np = _to_device(sig)
     zf = None
     if filters is not None:
@@ -235,13 +254,9 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
         if zf is not None and dev.dim() == 1:
             zf = zf[0]
     if ker is not None:
-        ker = np.asarray(ker, dtype=np.float64)
-        n = dev.shape[-1]
-        Hk, L = _centered_kernel_response(ker, n)
-        pad = torch.zeros(dev.shape[:-1] + (L, ), dtype=torch.float64,
-                          device=dev.device)
-        pad[..., :n] = dev
-        dev = dsp.fft_filter_device(pad, Hk, out=pad)[..., :n].contiguous()
+        ker = np.ascontiguousarray(np.asarray(ker, dtype=np.float64))
+        # the zero padding of the linear convolution exists only inside the transform
+        dev = _kernel_response(ker, dev.shape[-1], dev.device.index).apply(dev, out=dev)
     out = _from_device(dev, was_np)
     return (out, zf) if return_zf else out
 

@@ -178,6 +178,66 @@ def fft_filter_device(x, H, out=None):
     return y if x.dim() == 2 else y[0]
 
 
+class PreparedResponse:
+    """A frequency response kept on one device in the layout its transform length needs
+    (``wfm_fft_response_create``): upload and preparation happen once, ``apply`` filters
+    batches of real signals of ``n_valid <= n`` samples whose zero padding up to the
+    transform length ``n`` is neither stored nor moved."""
+
+    def __init__(self, H, device=None):
+        import torch
+        lib = engine.require_gpu()
+        H = np.ascontiguousarray(np.asarray(H, dtype=np.complex128).reshape(-1))
+        self.n = H.size
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._lib = lib
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            engine._check(lib.wfm_fft_response_create(H.ctypes.data, self.n, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.wfm_fft_response_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def apply(self, x, out=None):
+        """first ``x.shape[-1]`` samples of real(ifft(fft(x zero-padded to n) * H)); x: CUDA
+        f64 (n_valid,) or (n_sig, n_valid); ``out`` may be ``x``."""
+        import torch
+        x2 = x if x.dim() == 2 else x.unsqueeze(0)
+        assert x2.dtype == torch.float64 and x2.stride(1) == 1 and x2.shape[1] <= self.n
+        y = torch.empty_like(x2) if out is None else (out if out.dim() == 2 else out.unsqueeze(0))
+        assert y.dtype == torch.float64 and y.stride(1) == 1 and y.shape == x2.shape
+        n_sig, nv = x2.shape
+        rc = self._lib.wfm_fft_filter_prepared(x2.data_ptr(), y.data_ptr(), n_sig, nv, x2.stride(0), y.stride(0),
+                                               self._h, _stream(torch, x.device))
+        engine._check(rc)
+        return y if x.dim() == 2 else y[0]
+
+
+def reflection_device(x, A, tau, sample_rate, inverse, out=None):
+    """reflection / correct_reflection of distortion.py:208-221 on a CUDA f64 tensor (n,)
+    or (n_sig, n): real(ifft(fft(x) * H)) (``inverse``: / H) with
+    H(f) = (1 - A) / (1 - A exp(-2 pi i f tau)) on the np.fft.fftfreq(n, 1 / sample_rate)
+    grid.  The response is built ON THE DEVICE and cached per (n, A, tau, sample_rate,
+    direction): nothing but four scalars crosses the bus."""
+    import torch
+    lib = engine.require_gpu()
+    x2 = x if x.dim() == 2 else x.unsqueeze(0)
+    assert x2.dtype == torch.float64 and x2.stride(1) == 1
+    n_sig, n = x2.shape
+    y = torch.empty_like(x2) if out is None else (out if out.dim() == 2 else out.unsqueeze(0))
+    assert y.dtype == torch.float64 and y.stride(1) == 1 and y.shape == x2.shape
+    rc = lib.wfm_reflection_filter(x2.data_ptr(), y.data_ptr(), n_sig, n, x2.stride(0), y.stride(0),
+                                   float(A), float(tau), float(sample_rate), int(bool(inverse)),
+                                   _stream(torch, x.device))
+    engine._check(rc)
+    return y if x.dim() == 2 else y[0]
+
+
 def fft_c2c_device(z, inverse=False):
     """np.fft.fft / np.fft.ifft of a CUDA complex128 tensor (n,) or (n_sig, n),
     in place."""

@@ -59,7 +59,8 @@ EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_program_info', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
-    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_c2c', 'wfm_calibrate_fp64', 'wfm_calibrate_copy'
+    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_response_create', 'wfm_fft_response_destroy',
+    'wfm_fft_filter_prepared', 'wfm_reflection_filter', 'wfm_fft_c2c', 'wfm_calibrate_fp64', 'wfm_calibrate_copy'
 ]
 
 
@@ -102,6 +103,15 @@ def load_library():
         lib.wfm_fft_filter.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
             C.c_void_p, C.c_void_p
+        ]
+        lib.wfm_fft_response_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        lib.wfm_fft_response_destroy.argtypes = [C.c_void_p]
+        lib.wfm_fft_filter_prepared.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p
+        ]
+        lib.wfm_reflection_filter.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+            C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p
         ]
         lib.wfm_fft_c2c.argtypes = [
             C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p
