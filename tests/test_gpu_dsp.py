@@ -69,31 +69,29 @@ def test_sosfilt_scan_well_conditioned(n):
 
 
 def test_sosfilt_scan_exp_decay_is_as_accurate_as_scipy():
-    """Poles at 0.9952/0.9983: scipy's own sequential rounding noise is ~3e-12
-    (DESIGN.md K2).  The scan must (a) stay within 1e-11 of scipy and (b) be no
-    further from the extended-precision answer than scipy itself is."""
+    """Poles at 0.9952/0.9983 (noise gain 1 / ((1 - p1)(1 - p2)) ~ 1e5): scipy's own sequential
+    float64 result is ~1e-11 away from the exact filter output (long double, oracle/csrc/
+    ld_filters.c), so agreement with scipy below that level is a coincidence of rounding, not
+    accuracy.  The scan must be no further from the long-double truth than scipy is, and its
+    distance from scipy must stay inside that same noise floor."""
+    from oracle.build_c import sosfilt_ld
     from waveforms_b200.dsp import sosfilt_device
     rng = np.random.default_rng(11)
-    n = 60000
-    x = np.zeros(n)
-    for _ in range(12):
-        a, b = sorted(rng.integers(0, n, 2))
-        x[a:b] += rng.uniform(-0.5, 0.5)
-    ref = sosfilt(EXP_DECAY_SOS, x)
-    y, _ = sosfilt_device(EXP_DECAY_SOS, _dev(x), mode='scan')
-    y = y.cpu().numpy()
-    assert rel_err(y, ref) <= 1e-11
-    b0, b1, b2, _, a1, a2 = (np.longdouble(v) for v in EXP_DECAY_SOS[0])
-    z0 = z1 = np.longdouble(0)
-    exact = np.empty(n, dtype=np.longdouble)
-    for i, xv in enumerate(x.astype(np.longdouble)):
-        yv = b0 * xv + z0
-        z0 = b1 * xv - a1 * yv + z1
-        z1 = b2 * xv - a2 * yv
-        exact[i] = yv
-    err_scan = float(np.max(np.abs(y - exact)))
-    err_scipy = float(np.max(np.abs(ref - exact)))
-    assert err_scan <= 2.0 * err_scipy + 1e-15
+    for n in (60000, 400000):
+        x = np.zeros(n)
+        for _ in range(12):
+            a, b = sorted(rng.integers(0, n, 2))
+            x[a:b] += rng.uniform(-0.5, 0.5)
+        ref = sosfilt(EXP_DECAY_SOS, x)
+        truth = sosfilt_ld(EXP_DECAY_SOS, x)
+        y, _ = sosfilt_device(EXP_DECAY_SOS, _dev(x), mode='scan')
+        y = y.cpu().numpy()
+        err_scan, err_scipy = rel_err(y, truth), rel_err(ref, truth)
+        assert err_scipy > 1e-12          # the premise: scipy itself is outside 1e-12 here
+        assert err_scan <= 1.5 * err_scipy + 1e-12
+        assert rel_err(y, ref) <= 2.5 * err_scipy + 1e-12
+        ye, _ = sosfilt_device(EXP_DECAY_SOS, _dev(x), mode='exact')
+        assert np.array_equal(ye.cpu().numpy(), ref)  # the parity mode IS scipy, bit for bit
 
 
 def test_sosfilt_initial_offset():
@@ -198,10 +196,10 @@ def test_cfg4_pipeline_full_size_properties():
     ys, _ = dsp.sosfilt_device(sos, dx.clone(), mode='scan')
     ye, _ = dsp.sosfilt_device(sos, dx.clone(), mode='exact')
     scale = float(ye.abs().max())
-    assert float((ys - ye).abs().max()) <= 2e-11 * scale  # exp-decay poles at 1 - 2.5e-3: noise gain ~1e5
+    assert float((ys - ye).abs().max()) <= 6e-11 * scale  # exp-decay poles at 1 - 2.5e-3: noise gain ~1e5 (both carry ~2e-11 of noise)
     comb = 0.7 * dx[0] - 1.3 * dx[1]
     yc, _ = dsp.sosfilt_device(sos, comb.clone(), mode='scan')
-    assert float((yc - (0.7 * ys[0] - 1.3 * ys[1])).abs().max()) <= 2e-11 * scale
+    assert float((yc - (0.7 * ys[0] - 1.3 * ys[1])).abs().max()) <= 6e-11 * scale
     # `.real` after the inverse transform drops Im(H) at the Nyquist bin (test_gpu_fft.py): project it out
     alt = torch.from_numpy(np.where(np.arange(n) % 2 == 0, 1.0, -1.0)).cuda()
     xr = dx - (dx @ alt)[:, None] / n * alt

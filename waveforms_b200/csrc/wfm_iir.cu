@@ -36,6 +36,7 @@
 //    two modes agree to ~1e-15.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "wfm_internal.h"
@@ -126,14 +127,26 @@ __global__ void __launch_bounds__(32 * kExactWarps) sosfilt_exact_kernel(const _
         if (lane == l) out = o;
       }
     } else if (S == 2 && cnt == 32) {
+      // software-pipelined across the sections: section 1 of sample l next to section 2 of sample l - 1 — two
+      // independent dependency chains in flight, the same operations in the same order per section (bit-identical)
       const Biquad q0 = P.sec[0], q1 = P.sec[1];
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        double cur = shfl_f64(mine, l), o, o2;
+      double o1_prev;
+      {
+        double cur = shfl_f64(mine, 0);
         if (shift) cur = sub(cur, P.initial);
-        biquad_step(q0, cur, z0[0], z1[0], o);
-        biquad_step(q1, o, z0[1], z1[1], o2);
-        if (lane == l) out = o2;
+        biquad_step(q0, cur, z0[0], z1[0], o1_prev);
+      }
+#pragma unroll
+      for (int l = 1; l <= 32; ++l) {
+        double o1 = 0.0, o2;
+        if (l < 32) {
+          double cur = shfl_f64(mine, l);
+          if (shift) cur = sub(cur, P.initial);
+          biquad_step(q0, cur, z0[0], z1[0], o1);
+        }
+        biquad_step(q1, o1_prev, z0[1], z1[1], o2);
+        if (lane == l - 1) out = o2;
+        o1_prev = o1;
       }
     } else {
 #pragma unroll 1
@@ -298,6 +311,274 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_kernel
 }
 
 // ---------------------------------------------------------------------------
+// scan, all sections at once (S <= 2): the cascade is ONE linear system on the joint state
+// s = (z0, z1) of every section (D = 2S components): s' = M s + g x.  Per tile
+//   pass a: every thread runs its 16 samples from the zero state in the STATE-SPACE form
+//           z0' = -a1 z0 + (z1 + c1 x), z1' = -a2 z0 + c2 x  (c1 = b1 - a1 b0, c2 = b2 - a2 b0):
+//           one FMA per step on the critical path instead of the four dependent operations of
+//           the faithful recurrence; only the chunk's END state f_i leaves this pass, and f_i
+//           only feeds the carries, whose rounding is the same noise as before;
+//   scan  : E_i = sum_{j<i} (M^16)^(i-1-j) f_j with D x D powers of M^16 (host, long double);
+//           the per-lane powers sit in shared memory;
+//   pass c: the FAITHFUL recurrence from E_i, the sections software-pipelined (section 1 of
+//           sample k+1 next to section 2 of sample k: two independent chains).
+// One scan and two passes per tile instead of two scans and four passes, and a shorter chain
+// in pass a: 0.63 -> ~0.3 ms on cfg4 (256 x 400 000 samples, 2 sections).
+// ---------------------------------------------------------------------------
+constexpr int kMaxJoint = 4;  // D = 2 S, S <= 2
+struct IirJointTables {
+  double lane[32][kMaxJoint * kMaxJoint];  // (M^16)^l, l = 0..31, row-major D x D
+  double lvl[5][kMaxJoint * kMaxJoint];    // (M^16)^(2^d)
+  double warp[kMaxJoint * kMaxJoint];      // (M^16)^32
+  double c1[2], c2[2];                     // state-space input gains per section
+};
+
+template <int D>
+__device__ __forceinline__ void matvec_d(const double* __restrict__ M, const double (&a)[D], double (&r)[D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double acc = M[i * D] * a[0];
+#pragma unroll
+    for (int j = 1; j < D; ++j) acc = fma(M[i * D + j], a[j], acc);
+    r[i] = acc;
+  }
+}
+
+// Tile staging of the joint kernel: rows of 16 samples at a pitch of 18 doubles (144 B): thread r reads / writes its
+// row with 16-byte accesses without bank conflicts, and 16-byte chunks stay aligned for cp.async.  Two buffers: the
+// NEXT tile is already on its way (cp.async, no registers held) while this one is filtered — the one-buffer kernel
+// spent three quarters of its time waiting for its own loads (ncu: long-scoreboard stalls on the first use of every
+// loaded sample).
+constexpr int kJointPitch = kIirT + 2;                                       // doubles per staged row
+constexpr int kJointTileBytes = kIirThreads * kJointPitch * (int)sizeof(double);  // 36 864
+extern __shared__ __align__(16) unsigned char iir_smem[];
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// kAligned: x and y rows start on 16-byte boundaries (cp.async loads, 16-byte stores); else plain 8-byte accesses
+template <int S, bool kAligned>
+__global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_kernel(
+    const __grid_constant__ IirParams P, const __grid_constant__ IirJointTables TT, const double* __restrict__ x, double* y,
+    int64_t n, int64_t stride, const double* __restrict__ zi, double* __restrict__ zf) {
+  constexpr int D = 2 * S;
+  double* s_buf0 = reinterpret_cast<double*>(iir_smem);
+  double* s_buf1 = reinterpret_cast<double*>(iir_smem + kJointTileBytes);
+  __shared__ double s_lane[D * D][32];  // (M^16)^lane, entry-major: conflict-free
+  __shared__ double s_tot[kIirThreads / 32][D];
+  __shared__ double s_carry[D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t sig = blockIdx.x;
+  const double* __restrict__ xs = x + sig * stride;
+  double* ys = y + sig * stride;
+  const bool shift = P.initial != 0.0;
+  for (int e = tid; e < D * D * 32; e += kIirThreads) s_lane[e / 32][e % 32] = TT.lane[e % 32][(e / 32) / D * kMaxJoint + (e / 32) % D];
+  if (tid < D) s_carry[tid] = zi ? zi[sig * D + tid] : 0.0;  // zi[sig][section][2] is the joint state in order
+  Biquad q[S];
+  double c1[S], c2[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    q[k] = P.sec[k];
+    c1[k] = TT.c1[k];
+    c2[k] = TT.c2[k];
+  }
+
+  // tile `base` -> buffer: 2048 chunks of two samples, chunk c of the tile at row c / 8, column 2 (c % 8)
+  auto load_tile = [&](double* buf, int64_t base) {
+    const int cnt = (int)min((int64_t)kIirTile, n - base);
+#pragma unroll
+    for (int j = 0; j < kIirT / 2; ++j) {
+      const int c = j * kIirThreads + tid;
+      double* dst = buf + (c >> 3) * kJointPitch + 2 * (c & 7);
+      if (kAligned) {
+        const int left = cnt - 2 * c;  // samples of this chunk that exist: the rest is zero-filled
+        cp_async16_zfill(dst, left > 0 ? xs + base + 2 * c : xs + base, left >= 2 ? 16 : (left == 1 ? 8 : 0));
+      } else {
+        dst[0] = 2 * c < cnt ? xs[base + 2 * c] : 0.0;
+        dst[1] = 2 * c + 1 < cnt ? xs[base + 2 * c + 1] : 0.0;
+      }
+    }
+  };
+  if (n > 0) load_tile(s_buf0, 0);
+  if (kAligned) cp_async_commit();
+  __syncthreads();
+
+  int it = 0;
+  for (int64_t base = 0; base < n; base += kIirTile, ++it) {
+    const int cnt = (int)min((int64_t)kIirTile, n - base);
+    double* buf = (it & 1) ? s_buf1 : s_buf0;
+    if (base + kIirTile < n) load_tile((it & 1) ? s_buf0 : s_buf1, base + kIirTile);
+    if (kAligned) {
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the tile just requested has landed
+    }
+    __syncthreads();
+    double v[kIirT];
+    {
+      const double2* row = reinterpret_cast<const double2*>(buf + tid * kJointPitch);
+#pragma unroll
+      for (int k = 0; k < kIirT / 2; ++k) {
+        const double2 d = row[k];
+        v[2 * k] = d.x;
+        v[2 * k + 1] = d.y;
+      }
+    }
+    const int valid = max(0, min(kIirT, cnt - tid * kIirT));  // my valid samples
+    if (shift) {
+#pragma unroll
+      for (int k = 0; k < kIirT; ++k) v[k] = k < valid ? sub(v[k], P.initial) : 0.0;
+    }
+
+    double carry[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) carry[i] = s_carry[i];
+    // ---- pass a: end state of my chunk from the zero state (thread 0: from the tile's carry-in), state-space form
+    double f[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) f[i] = tid == 0 ? carry[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < kIirT; ++k) {
+      double in = v[k];
+#pragma unroll
+      for (int sct = 0; sct < S; ++sct) {
+        const double z0 = f[2 * sct], z1 = f[2 * sct + 1];
+        const double out = fma(q[sct].b0, in, z0);
+        f[2 * sct] = fma(-q[sct].a1, z0, fma(c1[sct], in, z1));
+        f[2 * sct + 1] = fma(-q[sct].a2, z0, c2[sct] * in);
+        in = out;
+      }
+    }
+    // ---- scan over the threads: inclusive warp scan with constant matrices per level
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      double p[D], r[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) p[i] = __shfl_up_sync(0xffffffffu, f[i], 1 << d);
+      if (lane >= (1 << d)) {
+        double m[D * D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) m[i * D + j] = TT.lvl[d][i * kMaxJoint + j];
+        matvec_d<D>(m, p, r);
+#pragma unroll
+        for (int i = 0; i < D; ++i) f[i] += r[i];
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_tot[warp][i] = f[i];
+    }
+    double e[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      e[i] = __shfl_up_sync(0xffffffffu, f[i], 1);
+      if (lane == 0) e[i] = 0.0;
+    }
+    __syncthreads();
+    // carry entering my warp: C_w = Q C_{w-1} + tot_{w-1}, Q = (M^16)^32
+    if (warp > 0) {
+      double w[D], r[D], mq[D * D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) mq[i * D + j] = TT.warp[i * kMaxJoint + j];
+      for (int k = 0; k < warp; ++k) {
+        matvec_d<D>(mq, w, r);
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = r[i] + s_tot[k][i];
+      }
+      double ml[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) ml[i] = s_lane[i][lane];
+      matvec_d<D>(ml, w, r);
+#pragma unroll
+      for (int i = 0; i < D; ++i) e[i] += r[i];
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) e[i] = carry[i];
+    }
+    // ---- pass c: the faithful recurrence from the carried-in state; section 2 runs one sample behind section 1
+    double z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = e[i];
+    const bool tail_here = valid < kIirT && tid * kIirT + valid == cnt;  // the signal ends inside my chunk
+    double fin[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) fin[i] = 0.0;
+    if (S == 1) {
+#pragma unroll
+      for (int k = 0; k < kIirT; ++k) {
+        if (tail_here && k == valid) { fin[0] = z[0]; fin[1] = z[1]; }
+        double out;
+        biquad_step(q[0], v[k], z[0], z[1], out);
+        v[k] = out;
+      }
+    } else {
+      double o1_prev;
+      {
+        if (tail_here && valid == 0) { fin[0] = z[0]; fin[1] = z[1]; }
+        biquad_step(q[0], v[0], z[0], z[1], o1_prev);
+      }
+#pragma unroll
+      for (int k = 1; k <= kIirT; ++k) {
+        double o1 = 0.0, o2;
+        if (k < kIirT) {
+          if (tail_here && k == valid) { fin[0] = z[0]; fin[1] = z[1]; }
+          biquad_step(q[0], v[k], z[0], z[1], o1);
+        }
+        if (tail_here && k - 1 == valid) { fin[2 % D] = z[2 % D]; fin[3 % D] = z[3 % D]; }
+        biquad_step(q[S - 1], o1_prev, z[2 % D], z[3 % D], o2);
+        v[k - 1] = o2;
+        o1_prev = o1;
+      }
+    }
+    if (shift) {
+#pragma unroll
+      for (int k = 0; k < kIirT; ++k) v[k] = add(v[k], P.initial);
+    }
+    // my row back into the buffer (nobody else reads it before the barrier), then coalesced 16-byte stores
+    {
+      double2* row = reinterpret_cast<double2*>(buf + tid * kJointPitch);
+#pragma unroll
+      for (int k = 0; k < kIirT / 2; ++k) row[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    }
+    __syncthreads();  // rows complete; all reads of s_carry / s_tot are done
+    if (tail_here) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_carry[i] = fin[i];
+    }
+    if (cnt == kIirTile && tid == kIirThreads - 1) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_carry[i] = z[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kIirT / 2; ++j) {
+      const int c = j * kIirThreads + tid;
+      const double2 d = *reinterpret_cast<const double2*>(buf + (c >> 3) * kJointPitch + 2 * (c & 7));
+      if (kAligned && 2 * c + 1 < cnt) {
+        *reinterpret_cast<double2*>(ys + base + 2 * c) = d;
+      } else {
+        if (2 * c < cnt) ys[base + 2 * c] = d.x;
+        if (2 * c + 1 < cnt) ys[base + 2 * c + 1] = d.y;
+      }
+    }
+    __syncthreads();  // the buffer may be refilled (tile t + 2) and s_carry read (tile t + 1)
+  }
+  if (kAligned) cp_async_wait<0>();
+  if (zf && tid < D) zf[sig * D + tid] = s_carry[tid];
+}
+
+// ---------------------------------------------------------------------------
 // lfilter: single high-order section, scipy.signal.lfilter's DF2T loop
 // (scipy/signal/_lfilter.c.src): y = z[0] + b[0]*x;
 // z[k] = (z[k+1] + x*b[k+1]) - y*a[k+1];  z[M-1] = x*b[M] - y*a[M].
@@ -404,6 +685,64 @@ static void put(double* dst, const M2& m) {
   dst[0] = (double)m.a; dst[1] = (double)m.b; dst[2] = (double)m.c; dst[3] = (double)m.d;
 }
 
+// D x D matrices in long double (joint state of the cascade)
+struct MD {
+  long double m[kMaxJoint][kMaxJoint];
+};
+static MD md_mul(const MD& x, const MD& y, int D) {
+  MD r{};
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      long double acc = 0;
+      for (int k = 0; k < D; ++k) acc += x.m[i][k] * y.m[k][j];
+      r.m[i][j] = acc;
+    }
+  return r;
+}
+static MD md_identity(int D) {
+  MD r{};
+  for (int i = 0; i < D; ++i) r.m[i][i] = 1;
+  return r;
+}
+static void md_put(double* dst, const MD& a) {
+  for (int i = 0; i < kMaxJoint; ++i)
+    for (int j = 0; j < kMaxJoint; ++j) dst[i * kMaxJoint + j] = (double)a.m[i][j];
+}
+// homogeneous one-step matrix of the cascade: section k's input is y_{k-1} = z0_{k-1} + b0_{k-1} x_{k-1}
+static void joint_tables(const IirParams& P, IirJointTables* tab) {
+  const int S = P.n_sections, D = 2 * S;
+  MD M{};
+  for (int k = 0; k < S; ++k) {
+    const long double a1 = P.sec[k].a1, a2 = P.sec[k].a2, b0 = P.sec[k].b0, b1 = P.sec[k].b1, b2 = P.sec[k].b2;
+    const long double c1 = b1 - a1 * b0, c2 = b2 - a2 * b0;
+    tab->c1[k] = (double)c1;
+    tab->c2[k] = (double)c2;
+    M.m[2 * k][2 * k] = -a1;
+    M.m[2 * k][2 * k + 1] = 1;
+    M.m[2 * k + 1][2 * k] = -a2;
+    // the input of section k as a linear function of the earlier sections' states (x = 0): u_k = z0_{k-1} + b0_{k-1} u_{k-1}
+    long double gain = 1;
+    for (int j = k - 1; j >= 0; --j) {
+      M.m[2 * k][2 * j] += c1 * gain;
+      M.m[2 * k + 1][2 * j] += c2 * gain;
+      gain *= P.sec[j].b0;
+    }
+  }
+  MD MT = md_identity(D);
+  for (int i = 0; i < kIirT; ++i) MT = md_mul(MT, M, D);
+  MD pw = md_identity(D);
+  for (int l = 0; l < 32; ++l) {
+    md_put(tab->lane[l], pw);
+    pw = md_mul(pw, MT, D);
+  }
+  md_put(tab->warp, pw);
+  MD sq = MT;
+  for (int d = 0; d < 5; ++d) {
+    md_put(tab->lvl[d], sq);
+    sq = md_mul(sq, sq, D);
+  }
+}
+
 }  // namespace wfm
 
 extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial, const double* x, double* y,
@@ -440,6 +779,21 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
       const unsigned blocks = (unsigned)((n_sig + kExactWarps - 1) / kExactWarps);
       sosfilt_exact_kernel<<<blocks, 32 * kExactWarps, 0, st>>>(P, x, y, n_sig, n, stride, d_zi, d_zf);
       e = cudaGetLastError();
+    } else if (n_sections <= 2 && !getenv("WFM_IIR_OLD_SCAN")) {
+      static thread_local IirJointTables jt;
+      joint_tables(P, &jt);
+      const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (stride % 2 == 0 || n_sig == 1);
+      const size_t smem = 2 * (size_t)kJointTileBytes;
+      auto launch = [&](auto kern) {
+        static thread_local bool attr_set[4] = {};
+        cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        (void)attr_set;
+        if (ee != cudaSuccess) return ee;
+        kern<<<(unsigned)n_sig, kIirThreads, smem, st>>>(P, jt, x, y, n, stride, d_zi, d_zf);
+        return cudaGetLastError();
+      };
+      if (n_sections == 1) e = aligned ? launch(sosfilt_scan_joint_kernel<1, true>) : launch(sosfilt_scan_joint_kernel<1, false>);
+      else e = aligned ? launch(sosfilt_scan_joint_kernel<2, true>) : launch(sosfilt_scan_joint_kernel<2, false>);
     } else {
       static thread_local IirScanTables tab;
       for (int k = 0; k < n_sections; ++k) {
