@@ -173,7 +173,10 @@ def test_builder_samples_equal_object_api(ns):
     from waveforms_b200.batch import sample_pulse_trains
     res = sample_pulse_trains(templates, idx, t0, 0, 4e-6, 2e9)
     for c, w in enumerate(chans):
-        assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())
+        # a channel sampled alone may take another unit size than inside the (mostly active) batch: samples that
+        # follow the first one of a unit take their cosines by rotation, equal to a few ulp
+        got_c, want_c = res.channel(c).cpu().numpy(), w.sample()
+        assert np.max(np.abs(got_c - want_c)) <= 4e-15 * np.max(np.abs(want_c))
     # per-pulse amplitude and phase arrays
     fn = lambda t0, amp, phase: ns.mixing(amp * ns.gaussian(20e-9) >> t0, freq=145e6, phase=phase, DRAGScaling=7e-10)[1]
     tp = PulseTemplate.trace(fn, params=('t0', 'amp', 'phase'))
@@ -182,7 +185,10 @@ def test_builder_samples_equal_object_api(ns):
     res = sample_pulse_trains([tp], [np.zeros(50, int)] * 2, t0, 0, 4e-6, 2e9, params=params)
     chans, _ = object_batch(ns, [fn], [np.zeros(50, int)] * 2, t0, 0, 4e-6, 2e9, params=params)
     for c, w in enumerate(chans):
-        assert np.array_equal(res.channel(c).cpu().numpy(), w.sample())
+        # a channel sampled alone may take another unit size than inside the (mostly active) batch: samples that
+        # follow the first one of a unit take their cosines by rotation, equal to a few ulp
+        got_c, want_c = res.channel(c).cpu().numpy(), w.sample()
+        assert np.max(np.abs(got_c - want_c)) <= 4e-15 * np.max(np.abs(want_c))
 
 
 def test_channel_shards_equal_slices_of_the_whole_batch(ns):

@@ -439,6 +439,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->waves.assign(d->waves, d->waves + d->n_waves);
   p->dev.n_slots = 1 + std::max(1, std::min(max_rows, wfm::kMaxSlots));
   p->dev.planes = 1;
+  p->dev.dense = 0;
 
   int64_t samples = 0, total = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
@@ -522,8 +523,10 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, ST);
     if (e == cudaSuccess) e = read_words(&active, d_active, 2, ST);
     const char* force = std::getenv("WFM_K1_UNIT");
-    if (force && (force[0] == '1' || force[0] == '2')) p->dev.unit = force[0] - '0';
+    if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) p->dev.unit = force[0] - '0';
+    else if (samples > 0 && (double)active * 2.0 > (double)samples) p->dev.unit = wfm::kDenseUnit;  // mostly active: dense kernel
     else p->dev.unit = (samples > 0 && (double)active * 1024.0 > 64.0 * (double)samples) ? 2 : 1;
+    p->dev.dense = p->dev.unit == wfm::kDenseUnit ? 1 : 0;
   }
 
   // Tile size.  A warp's slice of shared memory holds the output tile (8 B per sample), the
@@ -533,8 +536,11 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   // not fit (those take the kernel's cold path).
   uint32_t* d_stats = (uint32_t*)(base + o_stats);
   const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots, p->dev.unit);
-  // (an I/Q pair program keeps one tile buffer per output row)
-  auto cap_of = [&](int ts) { return ((wfm::kWarpSliceBytes - fixed - ts * 8 * p->dev.planes) / 2) & ~15; };
+  // (an I/Q pair program keeps one tile buffer per output row; the dense kernel keeps none)
+  auto cap_of = [&](int ts) {
+    if (p->dev.dense) return ((wfm::kDenseSliceBytes - fixed) / 2) & ~15;
+    return ((wfm::kWarpSliceBytes - fixed - ts * 8 * p->dev.planes) / 2) & ~15;
+  };
   int ts = wfm::kMaxTileSamples;
   {
     const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;

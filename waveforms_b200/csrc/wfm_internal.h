@@ -37,6 +37,13 @@ constexpr int kMaxTileSamples = WFM_K1_MAX_TILE;
 #endif
 constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K1_ERF_SMEM ? 2560 : 0)) / WFM_K1_WARPS) & ~127;
 
+// The DENSE kernel (programs whose samples are mostly active, e.g. randomized-benchmarking batches): one CTA of 12
+// autonomous warps per SM at up to 168 registers, four samples per lane unit, results stored straight from registers
+// (no tile buffer): its warp slice holds the value slots and the two packet buffers only.
+constexpr int kDenseWarps = 12;
+constexpr int kDenseUnit = 4;
+constexpr int kDenseSliceBytes = ((227 * 1024 - 1024) / kDenseWarps) & ~127;
+
 // Value slots of one segment evaluation: per lane kMaxSlots + 1 slots of `unit`
 // doubles in the warp's shared slice, slot-major (slot k of lane l at byte
 // k * slot_stride(unit) + l * 8 * unit: conflict-free).  Slot 0 always holds 1.0.
@@ -172,6 +179,7 @@ struct DevProgram {
   int n_slots;       // value slots per lane in shared memory: 1 (the constant 1.0) + max rows per segment
   int pkt_cap;       // bytes of ONE packet buffer in a warp's shared slice (two buffers per warp)
   int planes;        // 2 if any channel is an I/Q pair (two tile buffers per warp), else 1
+  int dense;         // 1: sampled by the dense kernel (unit == kDenseUnit, every flat segment listed as a patch row)
 };
 
 // one warp's work item: up to DevProgram::tile_samples consecutive samples of channel `wave`

@@ -173,6 +173,12 @@ __device__ __forceinline__ Val<U> ld_slot(const unsigned char* p) {
     const double2 d = *reinterpret_cast<const double2*>(p);
     r.v[0] = d.x;
     r.v[1] = d.y;
+  } else if constexpr (U == 4) {
+    const double2 d0 = reinterpret_cast<const double2*>(p)[0], d1 = reinterpret_cast<const double2*>(p)[1];
+    r.v[0] = d0.x;
+    r.v[1] = d0.y;
+    r.v[2] = d1.x;
+    r.v[3] = d1.y;
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) r.v[u] = reinterpret_cast<const double*>(p)[u];
@@ -183,6 +189,9 @@ template <int U>
 __device__ __forceinline__ void st_slot(unsigned char* p, const Val<U>& r) {
   if constexpr (U == 2) {
     *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
+  } else if constexpr (U == 4) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(r.v[0], r.v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(r.v[2], r.v[3]);
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) reinterpret_cast<double*>(p)[u] = r.v[u];
@@ -234,15 +243,19 @@ static __device__ __forceinline__ void eval_segment_slow_impl(const DevProgram& 
   }
   if (w.flags & WFM_WAVE_CLIP) out_re = clip_value(out_re, P.waves[w.wave].clip_lo, P.waves[w.wave].clip_hi);
 }
-static __device__ __noinline__ void eval_segment_slow(const DevProgram& P, int seg, const WaveEval& w, double x,
-                                                      double& out_re, double& out_im) {
-  eval_segment_slow_impl<false>(P, seg, w, x, out_re, out_im, 0, 0.0);
+// (arguments and result BY VALUE: a reference would force the caller's per-sample arrays into local memory)
+static __device__ __noinline__ double eval_segment_slow(const DevProgram& P, int seg, double offset, uint32_t flags, int wave,
+                                                        double x) {
+  double re, im;
+  eval_segment_slow_impl<false>(P, seg, WaveEval{offset, flags, wave}, x, re, im, 0, 0.0);
+  return re;
 }
 // one row of an I/Q pair: plane 0 / 1, only that row's terms are summed (row 1 starts from offset1)
-static __device__ __noinline__ void eval_segment_slow_row(const DevProgram& P, int seg, const WaveEval& w, double x,
-                                                          double& out_re, int plane, double offset1) {
-  double im;
-  eval_segment_slow_impl<true>(P, seg, w, x, out_re, im, plane, offset1);
+static __device__ __noinline__ double eval_segment_slow_row(const DevProgram& P, int seg, double offset, uint32_t flags, int wave,
+                                                            double x, int plane, double offset1) {
+  double re, im;
+  eval_segment_slow_impl<true>(P, seg, WaveEval{offset, flags, wave}, x, re, im, plane, offset1);
+  return re;
 }
 
 // product of an extended term (more than three references or an exponent != 1) from the
@@ -298,20 +311,23 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
 #pragma unroll
       for (int u = 0; u < U; ++u) a[u] = mul(wv, sub(x[u], shift));
     }
-    if (U == 2 && affine) {
-      // second sample of the unit: rotation of the first by D = w * delta plus the MEASURED
-      // residual eps = (a1 - a0) - D (first order; |eps| ~ ulp(a)), not a second range reduction
+    if (U >= 2 && affine) {
+      // the further samples of the unit: rotation of the previous one by D = w * delta plus the MEASURED residual
+      // eps = (a[u] - a[u-1]) - D (first order; |eps| ~ ulp(a)), not another range reduction
       const double a0[1] = {a[0]};
       double s0[1], c0[1];
       sincos_cw_n<1>(a0, s0, c0);
       const double D = sr->D, cD = sr->cD, sD = sr->sD;
-      const double eps = sub(sub(a[U - 1], a[0]), D);
-      const double C = fma(c0[0], cD, -(s0[0] * sD));
-      const double S = fma(s0[0], cD, c0[0] * sD);
       c.v[0] = c0[0];
       s.v[0] = s0[0];
-      c.v[U - 1] = fma(-eps, S, C);
-      s.v[U - 1] = fma(eps, C, S);
+#pragma unroll
+      for (int u = 1; u < U; ++u) {
+        const double eps = sub(sub(a[u], a[u - 1]), D);
+        const double C = fma(c.v[u - 1], cD, -(s.v[u - 1] * sD));
+        const double S = fma(s.v[u - 1], cD, c.v[u - 1] * sD);
+        c.v[u] = fma(-eps, S, C);
+        s.v[u] = fma(eps, C, S);
+      }
     } else {
       sincos_cw_n<U>(a, s.v, c.v);
     }
@@ -361,7 +377,7 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
       for (int u = 0; u < U; ++u) r.v[u] = erf_tab(dvd(sub(x[u], shift), a0), erf_s);
     } else {
       const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < U; ++u) r.v[u] = eval_factor(fa, x[u], P.args);
     }
     st_slot(dst, r);
@@ -390,7 +406,7 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
     }
     Val<U> prod;
     if (has_ext && (c.w >> 16) & kCTermExt) {
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < U; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
     } else {
 #if WFM_K1_SKIP_UNIT_REFS
@@ -446,6 +462,12 @@ __device__ __forceinline__ ValF<U> ld_slot_f(const unsigned char* p) {
     const float2 d = *reinterpret_cast<const float2*>(p);
     r.v[0] = d.x;
     r.v[1] = d.y;
+  } else if constexpr (U == 4) {
+    const float4 d = *reinterpret_cast<const float4*>(p);
+    r.v[0] = d.x;
+    r.v[1] = d.y;
+    r.v[2] = d.z;
+    r.v[3] = d.w;
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) r.v[u] = reinterpret_cast<const float*>(p)[u];
@@ -456,6 +478,8 @@ template <int U>
 __device__ __forceinline__ void st_slot_f(unsigned char* p, const ValF<U>& r) {
   if constexpr (U == 2) {
     *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else if constexpr (U == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) reinterpret_cast<float*>(p)[u] = r.v[u];
@@ -556,7 +580,7 @@ __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict_
       for (int u = 0; u < U; ++u) r.v[u] = erff((float)sub(x[u], shift) / (float)a0);
     } else {
       const FacArgs fa{func, gr[k].arg_off, shift, a0, gr[k].a1};
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < U; ++u) r.v[u] = (float)eval_factor(fa, x[u], P.args);
     }
     st_slot_f(dst, r);
@@ -588,7 +612,7 @@ __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict_
     ValF<U> prod;
     if ((c.w >> 16) & kCTermExt) {
       // extended terms read fp64 slots: evaluate the segment's term in fp64 from the ABI tables
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < U; ++u) {
         const WfmSegPtr p0 = P.seg_ptr[gseg];
         const WfmTerm tm = P.terms[p0.term + it];
@@ -790,8 +814,10 @@ __device__ TileLayout measure_tile(const DevProgram& P, const TileDesc& td, cons
       L.blk16 += P.seg_plan[w.seg_begin + k].blk16;
       L.n_units += (b - a + P.unit - 1) / P.unit;
     } else {
-      if (__double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) L.n_patch += 1;
-      if ((w.flags & WFM_WAVE_PAIR) && __double_as_longlong(P.seg_val1[w.seg_begin + k]) != __double_as_longlong(w.offset2))
+      // dense programs have no base fill: every flat run is a patch row
+      if (P.dense || __double_as_longlong(P.seg_val[w.seg_begin + k]) != __double_as_longlong(w.offset)) L.n_patch += 1;
+      if ((w.flags & WFM_WAVE_PAIR) &&
+          (P.dense || __double_as_longlong(P.seg_val1[w.seg_begin + k]) != __double_as_longlong(w.offset2)))
         L.n_patch += 1;
     }
   }
@@ -1014,13 +1040,13 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
       first += (b - a + P.unit - 1) / P.unit;
     } else {
       const double v = P.seg_val[seg];
-      if (__double_as_longlong(v) != __double_as_longlong(w.offset)) {
+      if (P.dense || __double_as_longlong(v) != __double_as_longlong(w.offset)) {
         if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 0u, v};
         ip += 1;
       }
       if (w.flags & WFM_WAVE_PAIR) {
         const double v1 = P.seg_val1[seg];
-        if (__double_as_longlong(v1) != __double_as_longlong(w.offset2)) {
+        if (P.dense || __double_as_longlong(v1) != __double_as_longlong(w.offset2)) {
           if (lane == 0) patches[ip] = PatchRow{(uint16_t)a, (uint16_t)b, 1u, v1};
           ip += 1;
         }
@@ -1113,16 +1139,16 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
       const int mid = (lo + hi + 1) >> 1;
       if ((int64_t)st[mid] <= td.j0 + jj) lo = mid; else hi = mid - 1;
     }
-    double re, im;
+    double re;
     const double xv = abscissa(w, P.x, td.j0 + jj);
     if (kPair && (w.flags & WFM_WAVE_PAIR)) {
       OutT* __restrict__ dst1 = out + w.out_off2 + td.j0;
-      eval_segment_slow_row(P, td.seg0 + lo, we, xv, re, 0, 0.0);
+      re = eval_segment_slow_row(P, td.seg0 + lo, we.offset, we.flags, we.wave, xv, 0, 0.0);
       dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
-      eval_segment_slow_row(P, td.seg0 + lo, we, xv, re, 1, w.offset2);
+      re = eval_segment_slow_row(P, td.seg0 + lo, we.offset, we.flags, we.wave, xv, 1, w.offset2);
       dst1[jj] = kAccumulate ? (OutT)add((double)dst1[jj], re) : (OutT)re;
     } else {
-      eval_segment_slow(P, td.seg0 + lo, we, xv, re, im);
+      re = eval_segment_slow(P, td.seg0 + lo, we.offset, we.flags, we.wave, xv);
       dst[jj] = kAccumulate ? (OutT)add((double)dst[jj], re) : (OutT)re;
     }
   }
@@ -1329,7 +1355,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
 #pragma unroll
           for (int u = 0; u < U; ++u) x[u] = add(t0, mul((double)(jg + u), delta));
         } else {
-#pragma unroll 1
+#pragma unroll
           for (int u = 0; u < U; ++u) x[u] = abscissa(P.waves[h->wave], P.x, j0 + min(jj + u, cnt - 1));
         }
         Val<U> r;
@@ -1343,13 +1369,13 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           };
           if (sflags & kSegWide) {
             const bool two = flags & WFM_WAVE_PAIR;
-#pragma unroll 1
-            for (int u = 0; u < U; ++u) eval_segment_slow_row(P, (int)rw.w, we, x[u], r.v[u], 0, 0.0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 0, 0.0);
             if (two) {
               first_row(r);
               plane1 = true;
-#pragma unroll 1
-              for (int u = 0; u < U; ++u) eval_segment_slow_row(P, (int)rw.w, we, x[u], r.v[u], 1, h->base1);
+#pragma unroll
+              for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 1, h->base1);
             }
           } else if constexpr (sizeof(OutT) == 4) {
             r = eval_unit_f32<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
@@ -1366,11 +1392,8 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           NoSwitch none;
           bool unused;
           if (sflags & kSegWide) {
-#pragma unroll 1
-            for (int u = 0; u < U; ++u) {
-              double im;
-              eval_segment_slow(P, (int)rw.w, we, x[u], r.v[u], im);
-            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow(P, (int)rw.w, we.offset, we.flags, we.wave, x[u]);
           } else if constexpr (sizeof(OutT) == 4) {
             r = eval_unit_f32<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
                                         (int)rw.w, we, x, s_slots + lane * 4 * U, nullptr, unused, none);
@@ -1421,6 +1444,261 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
   }
   if (lane == 0) bulk_wait_read_all();  // shared memory must outlive the copy's reads
 #undef buf
+}
+
+// ---- the DENSE sampling kernel -------------------------------------------------------------
+// Programs whose samples are mostly ACTIVE (randomized-benchmarking batches: back-to-back pulses) are bound by the
+// interpreter, not by the store: ncu on cfg3 showed 28 % of the issued instructions were fp64 arithmetic, the rest
+// row / term decoding, slot traffic and the unit bookkeeping, all paid once per UNIT.  This kernel therefore
+//   * evaluates FOUR consecutive samples per lane unit (the decode cost per sample halves against two; samples 1..3
+//     take their (cos, sin) from the previous one by rotation: one range reduction per frequency and unit),
+//   * runs ONE CTA of 12 autonomous warps per SM at up to 168 registers (the four dependency chains of a unit are
+//     the latency hiding that the second CTA used to provide),
+//   * stores results straight from registers (two 16-byte stores per lane and row; a warp round covers 1 KB of
+//     consecutive samples) — no tile buffer, so a warp's shared-memory slice holds only value slots and packets and
+//     the tile can be long,
+//   * writes flat runs (zero / constant segments, ALL listed as patch rows in dense programs) directly as well.
+// Packets, the pre-pass, the deal of the tiles and the evaluator are the sparse kernel's.
+constexpr int kDenseThreads = 32 * kDenseWarps;
+
+__host__ __device__ inline size_t dense_slice_bytes(int n_slots, int pkt_cap) {
+  size_t b = (size_t)n_slots * slot_stride(kDenseUnit) + 2 * (size_t)pkt_cap + 16;
+  return (b + 127) & ~(size_t)127;
+}
+
+// U consecutive results -> global memory (16-byte stores when the address allows)
+template <typename OutT, bool kAccumulate, int U>
+__device__ __forceinline__ void store_unit(OutT* __restrict__ p, const Val<U>& r, int n_valid) {
+  if (kAccumulate) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < n_valid) p[u] = (OutT)add((double)p[u], r.v[u]);
+    return;
+  }
+  if (n_valid == U && ((uintptr_t)p & 15) == 0) {
+    if constexpr (sizeof(OutT) == 8) {
+#pragma unroll
+      for (int u = 0; u < U; u += 2) *reinterpret_cast<double2*>(p + u) = make_double2(r.v[u], r.v[u + 1]);
+    } else {
+      static_assert(U == 4, "fp32 dense stores are one float4");
+      *reinterpret_cast<float4*>(p) = make_float4((float)r.v[0], (float)r.v[1], (float)r.v[2], (float)r.v[3]);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < n_valid) p[u] = (OutT)r.v[u];
+  }
+}
+
+// [a, b) of a channel row <- val, by the whole warp
+template <typename OutT, bool kAccumulate>
+__device__ __forceinline__ void fill_global(OutT* __restrict__ row, int a, int b, double val, int lane) {
+  if (kAccumulate) {
+    if (val != 0.0)
+      for (int p = a + lane; p < b; p += 32) row[p] = (OutT)add((double)row[p], val);
+    return;
+  }
+  constexpr int V = OutVec<OutT>::N;
+  // head up to the first 16-byte boundary, vector body, tail
+  const int mis = (int)(((uintptr_t)(row + a) & 15) / sizeof(OutT));
+  const int head = min(b - a, mis ? V - mis : 0);
+  if (lane < head) row[a + lane] = (OutT)val;
+  const int a2 = a + head, nvec = (b - a2) / V;
+  for (int q = lane; q < nvec; q += 32) {
+    if constexpr (sizeof(OutT) == 8) *reinterpret_cast<double2*>(row + a2 + q * V) = make_double2(val, val);
+    else {
+      const float f = (float)val;
+      *reinterpret_cast<float4*>(row + a2 + q * V) = make_float4(f, f, f, f);
+    }
+  }
+  const int t0 = a2 + nvec * V;
+  if (t0 + lane < b) row[t0 + lane] = (OutT)val;
+}
+
+template <typename OutT, bool kAccumulate, int kBatch, bool kPair>
+__global__ void __launch_bounds__(kDenseThreads, 1)
+    sample_dense_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
+                        OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
+  constexpr int U = kDenseUnit;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  unsigned char* slice = k1_smem + (size_t)warp_in_cta * dense_slice_bytes(P.n_slots, P.pkt_cap);
+  unsigned char* s_slots = slice;
+  constexpr int kSlotStride = slot_stride(U);
+  unsigned char* s_pkt = s_slots + (size_t)P.n_slots * kSlotStride;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
+  unsigned char* sl = s_slots + lane * 8 * U;  // this lane's value slots
+  const double* s_erf = &kErfTab[0][0];
+
+  static_assert(kBatch == 0 || (kBatch >= 2 && (kBatch & (kBatch - 1)) == 0), "batch: 0 or a power of two >= 2");
+  const int n_warps = gridDim.x * kDenseWarps;
+  int t, nb = 0;
+  unsigned int fetch = 0;
+  if constexpr (kBatch > 0) {
+    unsigned int b0 = 0;
+    if (lane == 0) b0 = atomicAdd(tile_counter, 2u * kBatch);
+    t = tile_begin + (int)__shfl_sync(0xffffffffu, b0, 0);
+    nb = t + kBatch;
+    if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
+  } else {
+    t = tile_begin + blockIdx.x * kDenseWarps + warp_in_cta;
+  }
+  auto next1 = [&](int tt) -> int {
+    if constexpr (kBatch > 0) return (((tt) - tile_begin) & (kBatch - 1)) < kBatch - 1 ? tt + 1 : nb;
+    else return tt + n_warps;
+  };
+  auto next2 = [&](int tt) -> int {
+    if constexpr (kBatch > 0) {
+      const int pos = (tt - tile_begin) & (kBatch - 1);
+      return pos < kBatch - 2 ? tt + 2 : (pos == kBatch - 2 ? nb : nb + 1);
+    } else {
+      return tt + 2 * n_warps;
+    }
+  };
+  if (t >= tile_end) return;
+  if (lane == 0) {
+    mbar_init(s_bar, 1);
+    mbar_init(s_bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (sizeof(OutT) == 4) {
+    ValF<U> one;
+#pragma unroll
+    for (int u = 0; u < U; ++u) one.v[u] = 1.0f;
+    st_slot_f(s_slots + lane * 4 * U, one);
+  } else {
+    Val<U> one;
+#pragma unroll
+    for (int u = 0; u < U; ++u) one.v[u] = 1.0;
+    st_slot(sl, one);
+  }
+  __syncwarp();
+
+  uint32_t off_next = 0, end_next = 0;
+  {
+    const uint32_t o0 = P.pkt_off[t], o1 = P.pkt_off[t + 1];
+    if (lane == 0) {
+      mbar_expect_tx(s_bar, (o1 - o0) * 16u);
+      bulk_g2s(s_pkt, P.packets + (size_t)o0 * 16, (o1 - o0) * 16u, s_bar);
+    }
+    if (next1(t) < tile_end) {
+      off_next = P.pkt_off[next1(t)];
+      end_next = P.pkt_off[next1(t) + 1];
+    }
+  }
+  uint32_t it = 0;
+  auto advance = [&]() {
+    if constexpr (kBatch > 0) {
+      const bool last = ((t - tile_begin) & (kBatch - 1)) == kBatch - 1;
+      t = next1(t);
+      if (last) {
+        nb = tile_begin + (int)__shfl_sync(0xffffffffu, fetch, 0);
+        if (lane == 0) fetch = atomicAdd(tile_counter, (unsigned int)kBatch);
+      }
+    } else {
+      t += n_warps;
+    }
+  };
+#pragma unroll 1
+  for (; t < tile_end; advance()) {
+    const int buf = (int)(it & 1u);
+    const unsigned char* pk = s_pkt + (size_t)buf * P.pkt_cap;
+    if (next1(t) < tile_end) {
+      if (lane == 0) {
+        mbar_expect_tx(s_bar + (buf ^ 1), (end_next - off_next) * 16u);
+        bulk_g2s(s_pkt + (size_t)(buf ^ 1) * P.pkt_cap, P.packets + (size_t)off_next * 16, (end_next - off_next) * 16u,
+                 s_bar + (buf ^ 1));
+      }
+      if (next2(t) < tile_end) {
+        off_next = P.pkt_off[next2(t)];
+        end_next = P.pkt_off[next2(t) + 1];
+      }
+    }
+    mbar_wait(s_bar + buf, (it >> 1) & 1u);
+
+    const PacketHeader* __restrict__ h = reinterpret_cast<const PacketHeader*>(pk);
+    const uint32_t flags = h->flags;
+    if (flags & kPacketCold) {
+      sample_tile_cold<OutT, kAccumulate, kPair>(P, tiles[t], out, lane);
+      __syncwarp();
+      ++it;
+      continue;
+    }
+    const int n_arows = h->n_arows, n_patch = h->n_patch, n_units = h->n_units;
+    OutT* __restrict__ dst0 = out + h->out0;
+    OutT* dst1 = dst0;
+    if constexpr (kPair) dst1 = out + h->out1;
+    const ARow* __restrict__ arows = reinterpret_cast<const ARow*>(pk + sizeof(PacketHeader));
+    const PatchRow* __restrict__ patches = reinterpret_cast<const PatchRow*>(arows + (n_arows ? n_arows + 1 : 0));
+    // ---- flat runs: every zero / constant segment of the tile is listed (dense programs) ----------------------------
+    for (int i = 0; i < n_patch; ++i)
+      fill_global<OutT, kAccumulate>((kPair && patches[i].plane) ? dst1 : dst0, (int)patches[i].a, (int)patches[i].b, patches[i].val,
+                                     lane);
+    // ---- active samples: units of four, results straight to global memory ------------------------------------------
+    if (n_units > 0) {
+      const WaveEval we{h->base, flags, h->wave};
+      const double t0 = h->t0, delta = h->delta;
+      const int j0 = (int)h->j0, cnt = h->cnt;
+      const bool plain_grid = !(flags & (WFM_WAVE_EXPLICIT_X | WFM_WAVE_LAST_OVERRIDE | WFM_WAVE_PRESHIFT));
+      int lo = 0;
+#pragma unroll 1
+      for (int i = lane; i < n_units; i += 32) {
+        while ((int)arows[lo + 1].first <= i) ++lo;
+        const uint4 rw = reinterpret_cast<const uint4*>(arows)[lo];
+        const int start = rw.x & 0xffffu, first = rw.x >> 16, rel = rw.y & 0xfffu, len = rw.y >> 16;
+        const uint32_t sflags = (rw.y >> 12) & 0xfu;
+        const int jj = start + (i - first) * U;
+        const int n_valid = min(U, start + len - jj);
+        double x[U];
+        if (plain_grid) {
+          const int jg = j0 + jj;
+#pragma unroll
+          for (int u = 0; u < U; ++u) x[u] = add(t0, mul((double)(jg + u), delta));
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) x[u] = abscissa(P.waves[h->wave], P.x, h->j0 + min(jj + u, cnt - 1));
+        }
+        Val<U> r;
+        if constexpr (kPair) {
+          bool plane1 = false;
+          auto first_row = [&](const Val<U>& v) { store_unit<OutT, kAccumulate, U>(dst0 + jj, v, n_valid); };
+          if (sflags & kSegWide) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 0, 0.0);
+            if (flags & WFM_WAVE_PAIR) {
+              first_row(r);
+              plane1 = true;
+#pragma unroll
+              for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 1, h->base1);
+            }
+          } else if constexpr (sizeof(OutT) == 4) {
+            r = eval_unit_f32<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
+                                       (int)rw.w, we, x, s_slots + lane * 4 * U, &h->base1, plane1, first_row);
+          } else {
+            r = eval_unit<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                                   (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X), &h->base1, plane1, first_row);
+          }
+          store_unit<OutT, kAccumulate, U>((plane1 ? dst1 : dst0) + jj, r, n_valid);
+        } else {
+          NoSwitch none;
+          bool unused;
+          if (sflags & kSegWide) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow(P, (int)rw.w, we.offset, we.flags, we.wave, x[u]);
+          } else if constexpr (sizeof(OutT) == 4) {
+            r = eval_unit_f32<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
+                                        (int)rw.w, we, x, s_slots + lane * 4 * U, nullptr, unused, none);
+          } else {
+            r = eval_unit<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, true, P,
+                                    (int)rw.w, we, x, sl, s_erf, !(flags & WFM_WAVE_EXPLICIT_X), nullptr, unused, none);
+          }
+          store_unit<OutT, kAccumulate, U>(dst0 + jj, r, n_valid);
+        }
+      }
+    }
+    __syncwarp();  // all reads of the packet are done: its buffer may be refilled
+    ++it;
+  }
 }
 
 // complex128 output: the real and the imaginary PLANE are sampled by the real-valued kernel
@@ -1498,6 +1776,7 @@ cudaError_t launch_fill_packets(const DevProgram& P, const TileDesc* tiles, int6
 int warp_fixed_bytes(int n_slots, int unit) { return n_slots * slot_stride(unit) + 16 + 128; }
 
 size_t sample_smem_bytes(const DevProgram& P, int dtype) {
+  if (P.dense) return kDenseWarps * dense_slice_bytes(P.n_slots, P.pkt_cap);
   return kWarpsPerCta * warp_slice_bytes(P.tile_samples, P.n_slots, P.unit, P.pkt_cap, dtype == WFM_F32 ? 4 : 8, P.planes == 2 ? 2 : 1);
 }
 
@@ -1539,7 +1818,7 @@ struct LaunchCfg {
   int n_occ = 0;
 };
 template <typename K>
-static cudaError_t launch_cfg(K k, LaunchCfg* table, std::mutex& mu, size_t smem, int* sms, int* per_sm) {
+static cudaError_t launch_cfg(K k, LaunchCfg* table, std::mutex& mu, size_t smem, int* sms, int* per_sm, int threads = kThreads) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -1557,30 +1836,28 @@ static cudaError_t launch_cfg(K k, LaunchCfg* table, std::mutex& mu, size_t smem
       *per_sm = c.occ[i].per_sm;
       return cudaSuccess;
     }
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k, kThreads, smem)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k, threads, smem)) != cudaSuccess) return e;
   c.occ[c.n_occ % 8] = LaunchCfg::Occ{smem, *per_sm};
   c.n_occ = std::min(c.n_occ + 1, 8);
   return cudaSuccess;
 }
 
-template <typename OutT, bool kAcc, int U, int kBatch, bool kPair>
-static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
-                               int dtype, void* out, cudaStream_t stream) {
-  auto k = sample_kernel<OutT, kAcc, U, kBatch, kPair>;
-  static LaunchCfg cfg_table[64];
-  static std::mutex cfg_mu;
+template <typename OutT, int kBatch, typename K>
+static cudaError_t launch_kernel(K k, int threads, const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                                 int dtype, void* out, cudaStream_t stream, LaunchCfg* cfg_table, std::mutex& cfg_mu) {
+  const int warps = threads / 32;
   const size_t smem = sample_smem_bytes(P, dtype);
   int dev = 0, sms = 0, per_sm = 0;
-  cudaError_t e = launch_cfg(k, cfg_table, cfg_mu, smem, &sms, &per_sm);
+  cudaError_t e = launch_cfg(k, cfg_table, cfg_mu, smem, &sms, &per_sm, threads);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  const int64_t want = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t want = (n_tiles + warps - 1) / warps;
   int64_t cap = (int64_t)sms * per_sm;  // persistent: every warp walks tiles w, w+G, ...
   static const int tiles_per_warp = [] { const char* v = getenv("WFM_K1_TILES_PER_WARP"); return v ? atoi(v) : WFM_K1_TILES_PER_WARP; }();
   if (tiles_per_warp > 0) cap = std::max<int64_t>(cap, (want + tiles_per_warp - 1) / tiles_per_warp);
   const unsigned grid = (unsigned)std::min<int64_t>(want, cap);
   if (kBatch == 0) {
-    k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, nullptr);
+    k<<<grid, threads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, nullptr);
     return cudaGetLastError();
   }
   // the tile counter of this launch: the next slot of a per-device ring (allocated once), zeroed on the launch's
@@ -1599,9 +1876,27 @@ static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64
   }
   unsigned int* counter = ring->counters + slot;
   if ((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-  k<<<grid, kThreads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, counter);
+  k<<<grid, threads, smem, stream>>>(P, tiles, (int)tile_begin, (int)(tile_begin + n_tiles), (OutT*)out, counter);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return cudaEventRecord(ring->used[slot], stream);
+}
+
+template <typename OutT, bool kAcc, int U, int kBatch, bool kPair>
+static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                               int dtype, void* out, cudaStream_t stream) {
+  static LaunchCfg cfg_table[64];
+  static std::mutex cfg_mu;
+  return launch_kernel<OutT, kBatch>(sample_kernel<OutT, kAcc, U, kBatch, kPair>, kThreads, P, tiles, tile_begin, n_tiles, dtype,
+                                     out, stream, cfg_table, cfg_mu);
+}
+
+template <typename OutT, bool kAcc, int kBatch, bool kPair>
+static cudaError_t launch_dense(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
+                                int dtype, void* out, cudaStream_t stream) {
+  static LaunchCfg cfg_table[64];
+  static std::mutex cfg_mu;
+  return launch_kernel<OutT, kBatch>(sample_dense_kernel<OutT, kAcc, kBatch, kPair>, kDenseThreads, P, tiles, tile_begin, n_tiles,
+                                     dtype, out, stream, cfg_table, cfg_mu);
 }
 
 // The deal of a launch.  Dynamic (batches of WFM_K1_DYNAMIC tiles drawn from a counter) is the default whenever the warps
@@ -1633,6 +1928,35 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
 #ifdef WFM_K1_ONLY  // register-allocation experiments: one instantiation only (compiles in seconds)
   return launch_deal<double, false, 1, WFM_K1_DYNAMIC, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 #else
+  if (P.dense && (dtype == WFM_F64 || dtype == WFM_F32)) {
+    const char* dv = getenv("WFM_K1_DEAL");
+    const char deal = dv ? dv[0] : '\0';
+    bool dynamic = n_tiles >= (int64_t)8 * 1024;
+    if (deal == 'd') dynamic = true;
+    if (deal == 's') dynamic = false;
+    const int sel = (dtype == WFM_F32 ? 8 : 0) | (accumulate ? 4 : 0) | (P.planes == 2 ? 2 : 0) | (dynamic ? 1 : 0);
+    switch (sel) {
+#define WFM_DENSE_CASE(n, T, acc, batch, pair) \
+  case n: return launch_dense<T, acc, batch, pair>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      WFM_DENSE_CASE(0, double, false, 0, false)
+      WFM_DENSE_CASE(1, double, false, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(2, double, false, 0, true)
+      WFM_DENSE_CASE(3, double, false, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(4, double, true, 0, false)
+      WFM_DENSE_CASE(5, double, true, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(6, double, true, 0, true)
+      WFM_DENSE_CASE(7, double, true, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(8, float, false, 0, false)
+      WFM_DENSE_CASE(9, float, false, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(10, float, false, 0, true)
+      WFM_DENSE_CASE(11, float, false, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(12, float, true, 0, false)
+      WFM_DENSE_CASE(13, float, true, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(14, float, true, 0, true)
+      default: return launch_dense<float, true, WFM_K1_DYNAMIC, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+#undef WFM_DENSE_CASE
+    }
+  }
   if (dtype == WFM_F64 || dtype == WFM_F32) {
     const int sel = (dtype == WFM_F32 ? 4 : 0) | (accumulate ? 2 : 0) | (P.unit == 2 ? 1 : 0);
     switch (sel) {
