@@ -159,13 +159,17 @@ typedef struct WfmProgram* wfm_program_t;
 /* output element types */
 #define WFM_F64 0
 #define WFM_F32 1
+#define WFM_F32_FAST 3 /* float output by an fp32 EVALUATOR (fp64 arguments and range reductions, fp32 polynomials,
+                          products and sums): ~10 % faster than WFM_F32, which evaluates in fp64 and rounds at the store.
+                          Its error is ~1e-7 x (sum of the term magnitudes of a segment): inside 1e-6 of the channel's
+                          peak unless large terms cancel (e.g. a DRAG scaling with w * s >> 1).  Opt-in. */
 #define WFM_C128 2  /* interleaved (re, im) doubles; assembled from two real planes in scratch that
                        belongs to the program: WFM_C128 launches of ONE program must be stream-ordered */
 
 typedef struct WfmLaunch {
   int64_t first_wave;  /* channels [first_wave, first_wave + n_wave) */
   int64_t n_wave;      /* 0 = all from first_wave                    */
-  int32_t dtype;       /* WFM_F64 | WFM_F32 | WFM_C128               */
+  int32_t dtype;       /* WFM_F64 | WFM_F32 | WFM_F32_FAST | WFM_C128 */
   int32_t accumulate;  /* 0: out = value; 1: out += value            */
   void*   out;         /* DEVICE pointer (wfm_sample) / HOST pointer (wfm_sample_host) */
   int64_t out_elems;   /* capacity of out, in elements of dtype      */

@@ -701,7 +701,7 @@ static int check_launch(wfm_program_t prog, const WfmLaunch* l, int64_t* first, 
   *first = l->first_wave;
   *count = l->n_wave == 0 ? nw - l->first_wave : l->n_wave;
   if (*first < 0 || *count < 0 || *first + *count > nw) return fail(WFM_EINVAL, "channel range out of bounds");
-  if (l->dtype != WFM_F64 && l->dtype != WFM_F32 && l->dtype != WFM_C128) return fail(WFM_EINVAL, "bad dtype");
+  if (l->dtype != WFM_F64 && l->dtype != WFM_F32 && l->dtype != WFM_F32_FAST && l->dtype != WFM_C128) return fail(WFM_EINVAL, "bad dtype");
   if (prog->any_complex && l->dtype != WFM_C128)
     for (int64_t w = *first; w < *first + *count; ++w)
       if (prog->waves[w].flags & WFM_WAVE_COMPLEX)
@@ -785,7 +785,7 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   StageTimer tm("sample_host");
   const cudaStream_t ST = cudaStreamPerThread;  // see wfm_program_create
   DeviceGuard g(prog->device);
-  const size_t esz = l->dtype == WFM_F64 ? 8 : (l->dtype == WFM_F32 ? 4 : 16);
+  const size_t esz = l->dtype == WFM_F64 ? 8 : ((l->dtype == WFM_F32 || l->dtype == WFM_F32_FAST) ? 4 : 16);
   // only the extent actually covered by the requested channels is staged/copied
   int64_t lo = INT64_MAX;
   for (int64_t w = first; w < first + count; ++w) lo = std::min(lo, prog->waves[w].out_off);

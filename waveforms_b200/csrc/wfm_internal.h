@@ -40,7 +40,10 @@ constexpr int kWarpSliceBytes = ((227 * 1024 / WFM_K1_MIN_BLOCKS - 1024 - (WFM_K
 // The DENSE kernel (programs whose samples are mostly active, e.g. randomized-benchmarking batches): one CTA of 12
 // autonomous warps per SM at up to 168 registers, four samples per lane unit, results stored straight from registers
 // (no tile buffer): its warp slice holds the value slots and the two packet buffers only.
-constexpr int kDenseWarps = 12;
+#ifndef WFM_K1_DENSE_WARPS
+#define WFM_K1_DENSE_WARPS 12
+#endif
+constexpr int kDenseWarps = WFM_K1_DENSE_WARPS;
 constexpr int kDenseUnit = 4;
 constexpr int kDenseSliceBytes = ((227 * 1024 - 1024) / kDenseWarps) & ~127;
 

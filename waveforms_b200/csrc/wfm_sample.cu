@@ -174,7 +174,9 @@ __device__ __forceinline__ Val<U> ld_slot(const unsigned char* p) {
     r.v[0] = d.x;
     r.v[1] = d.y;
   } else if constexpr (U == 4) {
-    const double2 d0 = reinterpret_cast<const double2*>(p)[0], d1 = reinterpret_cast<const double2*>(p)[1];
+    // four-sample slots are two 16-byte halves 512 bytes apart (lane l at l * 16 in each): a lane-contiguous
+    // 32-byte layout puts lanes l and l + 4 of a quarter warp on the same banks
+    const double2 d0 = *reinterpret_cast<const double2*>(p), d1 = *reinterpret_cast<const double2*>(p + 512);
     r.v[0] = d0.x;
     r.v[1] = d0.y;
     r.v[2] = d1.x;
@@ -190,8 +192,8 @@ __device__ __forceinline__ void st_slot(unsigned char* p, const Val<U>& r) {
   if constexpr (U == 2) {
     *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
   } else if constexpr (U == 4) {
-    reinterpret_cast<double2*>(p)[0] = make_double2(r.v[0], r.v[1]);
-    reinterpret_cast<double2*>(p)[1] = make_double2(r.v[2], r.v[3]);
+    *reinterpret_cast<double2*>(p) = make_double2(r.v[0], r.v[1]);
+    *reinterpret_cast<double2*>(p + 512) = make_double2(r.v[2], r.v[3]);
   } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) reinterpret_cast<double*>(p)[u] = r.v[u];
@@ -269,7 +271,9 @@ static __device__ __noinline__ double term_product_ext(const DevProgram& P, int 
   for (int r = 0; r < tm.n_ref; ++r) {
     const WfmRef ref = P.refs[tm.ref_begin + r];
     const int slot = P.row_slot[p0.fac + ref.slot];
-    double v = reinterpret_cast<const double*>(sl + slot * kSlotStride)[u];
+    // sample u of the slot (four-sample units: two 16-byte halves 512 bytes apart, see ld_slot)
+    const unsigned char* sp = sl + slot * kSlotStride;
+    double v = P.unit == 4 ? reinterpret_cast<const double*>(sp + (u >> 1) * 512)[u & 1] : reinterpret_cast<const double*>(sp)[u];
     if (ref.kind == WFM_POW_INT) v = pow_small_int(v, (int)ref.expo);
     else if (ref.kind == WFM_POW_GEN) v = pow(v, ref.expo);
     prod = mul(prod, v);
@@ -1165,7 +1169,10 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 #endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
-template <typename OutT, bool kAccumulate, int U, int kBatch, bool kPair>
+// kF32Eval (float output only): the fp32 EVALUATOR (eval_unit_f32) instead of the fp64 one rounded at the store.
+// Faster, but its error is ~1e-7 x (sum of the term magnitudes), so segments whose terms cancel (a DRAG scaling with
+// w * s >> 1) leave the 1e-6 tolerance: WFM_F32_FAST is opt-in, WFM_F32 always evaluates in fp64.
+template <typename OutT, bool kAccumulate, int U, int kBatch, bool kPair, bool kF32Eval>
 __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     sample_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
                   OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
@@ -1231,7 +1238,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    if constexpr (sizeof(OutT) == 4) {
+    if constexpr (kF32Eval) {
       ValF<U> one;  // slot 0: the unit a missing term reference multiplies by (fp32 evaluator: float slots)
 #pragma unroll
       for (int u = 0; u < U; ++u) one.v[u] = 1.0f;
@@ -1377,7 +1384,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
 #pragma unroll
               for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 1, h->base1);
             }
-          } else if constexpr (sizeof(OutT) == 4) {
+          } else if constexpr (kF32Eval) {
             r = eval_unit_f32<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
                                        (int)rw.w, we, x, s_slots + lane * 4 * U, &h->base1, plane1, first_row);
           } else {
@@ -1394,7 +1401,7 @@ __global__ void __launch_bounds__(kThreads, WFM_K1_MIN_BLOCKS)
           if (sflags & kSegWide) {
 #pragma unroll
             for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow(P, (int)rw.w, we.offset, we.flags, we.wave, x[u]);
-          } else if constexpr (sizeof(OutT) == 4) {
+          } else if constexpr (kF32Eval) {
             r = eval_unit_f32<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
                                         (int)rw.w, we, x, s_slots + lane * 4 * U, nullptr, unused, none);
           } else {
@@ -1515,7 +1522,7 @@ __device__ __forceinline__ void fill_global(OutT* __restrict__ row, int a, int b
   if (t0 + lane < b) row[t0 + lane] = (OutT)val;
 }
 
-template <typename OutT, bool kAccumulate, int kBatch, bool kPair>
+template <typename OutT, bool kAccumulate, int kBatch, bool kPair, bool kF32Eval>
 __global__ void __launch_bounds__(kDenseThreads, 1)
     sample_dense_kernel(const __grid_constant__ DevProgram P, const TileDesc* __restrict__ tiles, int tile_begin, int tile_end,
                         OutT* __restrict__ out, unsigned int* __restrict__ tile_counter) {
@@ -1527,7 +1534,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
   constexpr int kSlotStride = slot_stride(U);
   unsigned char* s_pkt = s_slots + (size_t)P.n_slots * kSlotStride;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pkt + 2 * (size_t)P.pkt_cap);
-  unsigned char* sl = s_slots + lane * 8 * U;  // this lane's value slots
+  unsigned char* sl = s_slots + lane * 16;  // this lane's value slots (two 16-byte halves per slot, see ld_slot)
   const double* s_erf = &kErfTab[0][0];
 
   static_assert(kBatch == 0 || (kBatch >= 2 && (kBatch & (kBatch - 1)) == 0), "batch: 0 or a power of two >= 2");
@@ -1561,7 +1568,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
     mbar_init(s_bar + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if constexpr (sizeof(OutT) == 4) {
+  if constexpr (kF32Eval) {
     ValF<U> one;
 #pragma unroll
     for (int u = 0; u < U; ++u) one.v[u] = 1.0f;
@@ -1671,7 +1678,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
 #pragma unroll
               for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow_row(P, (int)rw.w, we.offset, we.flags, we.wave, x[u], 1, h->base1);
             }
-          } else if constexpr (sizeof(OutT) == 4) {
+          } else if constexpr (kF32Eval) {
             r = eval_unit_f32<U, true>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
                                        (int)rw.w, we, x, s_slots + lane * 4 * U, &h->base1, plane1, first_row);
           } else {
@@ -1685,7 +1692,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
           if (sflags & kSegWide) {
 #pragma unroll
             for (int u = 0; u < U; ++u) r.v[u] = eval_segment_slow(P, (int)rw.w, we.offset, we.flags, we.wave, x[u]);
-          } else if constexpr (sizeof(OutT) == 4) {
+          } else if constexpr (kF32Eval) {
             r = eval_unit_f32<U, false>(pk + rel * 16, rw.z & 0xffu, (rw.z >> 8) & 0xffu, (rw.z >> 16) & 0xffu, rw.z >> 24, P,
                                         (int)rw.w, we, x, s_slots + lane * 4 * U, nullptr, unused, none);
           } else {
@@ -1881,21 +1888,21 @@ static cudaError_t launch_kernel(K k, int threads, const DevProgram& P, const Ti
   return cudaEventRecord(ring->used[slot], stream);
 }
 
-template <typename OutT, bool kAcc, int U, int kBatch, bool kPair>
+template <typename OutT, bool kAcc, int U, int kBatch, bool kPair, bool kF32Eval = false>
 static cudaError_t launch_deal(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                int dtype, void* out, cudaStream_t stream) {
   static LaunchCfg cfg_table[64];
   static std::mutex cfg_mu;
-  return launch_kernel<OutT, kBatch>(sample_kernel<OutT, kAcc, U, kBatch, kPair>, kThreads, P, tiles, tile_begin, n_tiles, dtype,
+  return launch_kernel<OutT, kBatch>(sample_kernel<OutT, kAcc, U, kBatch, kPair, kF32Eval>, kThreads, P, tiles, tile_begin, n_tiles, dtype,
                                      out, stream, cfg_table, cfg_mu);
 }
 
-template <typename OutT, bool kAcc, int kBatch, bool kPair>
+template <typename OutT, bool kAcc, int kBatch, bool kPair, bool kF32Eval = false>
 static cudaError_t launch_dense(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                 int dtype, void* out, cudaStream_t stream) {
   static LaunchCfg cfg_table[64];
   static std::mutex cfg_mu;
-  return launch_kernel<OutT, kBatch>(sample_dense_kernel<OutT, kAcc, kBatch, kPair>, kDenseThreads, P, tiles, tile_begin, n_tiles,
+  return launch_kernel<OutT, kBatch>(sample_dense_kernel<OutT, kAcc, kBatch, kPair, kF32Eval>, kDenseThreads, P, tiles, tile_begin, n_tiles,
                                      dtype, out, stream, cfg_table, cfg_mu);
 }
 
@@ -1903,7 +1910,7 @@ static cudaError_t launch_dense(const DevProgram& P, const TileDesc* tiles, int6
 // have several batches each to draw: measured +7..10 % on near-pure-store programs (cfg4) and on very uneven tiles (cfg5),
 // +2 % on dense cfg3, +-1 % on the control frames (cfg2); small launches keep the static deal (no counter to
 // allocate and zero).  WFM_K1_DEAL=static|dynamic overrides.
-template <typename OutT, bool kAcc, int U>
+template <typename OutT, bool kAcc, int U, bool kF32Eval = false>
 static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles,
                                      int dtype, void* out, cudaStream_t stream) {
   const char* dv = getenv("WFM_K1_DEAL");  // a scan of environ (~0.1 us); read per launch so that tests can flip it
@@ -1914,17 +1921,31 @@ static cudaError_t launch_persistent(const DevProgram& P, const TileDesc* tiles,
   if (deal == 'd') dynamic = true;
   if (deal == 's') dynamic = false;
   if (P.planes == 2) {
-    if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
-    return launch_deal<OutT, kAcc, U, 0, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, true, kF32Eval>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    return launch_deal<OutT, kAcc, U, 0, true, kF32Eval>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
   }
-  if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
-  return launch_deal<OutT, kAcc, U, 0, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  if (dynamic) return launch_deal<OutT, kAcc, U, WFM_K1_DYNAMIC, false, kF32Eval>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  return launch_deal<OutT, kAcc, U, 0, false, kF32Eval>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 }
 
 cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t tile_begin, int64_t n_tiles, int dtype,
                           int accumulate, void* out, cudaStream_t stream) {
   if (n_tiles == 0) return cudaSuccess;
   if (tile_begin + n_tiles > INT32_MAX) return cudaErrorInvalidValue;
+  // WFM_F32_FAST: float output by the fp32 evaluator (not with accumulate: that is the careful path anyway)
+  const bool fast32 = dtype == WFM_F32_FAST && !accumulate;
+  if (dtype == WFM_F32_FAST) dtype = WFM_F32;
+  if (fast32) {
+    if (P.dense) {
+      const bool dyn = n_tiles >= (int64_t)8 * 1024;
+      if (P.planes == 2) return dyn ? launch_dense<float, false, WFM_K1_DYNAMIC, true, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+                                    : launch_dense<float, false, 0, true, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      return dyn ? launch_dense<float, false, WFM_K1_DYNAMIC, false, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+                 : launch_dense<float, false, 0, false, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    }
+    if (P.unit == 2) return launch_persistent<float, false, 2, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+    return launch_persistent<float, false, 1, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+  }
 #ifdef WFM_K1_ONLY  // register-allocation experiments: one instantiation only (compiles in seconds)
   return launch_deal<double, false, 1, WFM_K1_DYNAMIC, false>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 #else

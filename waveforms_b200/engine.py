@@ -24,8 +24,8 @@ import os
 _LIB_PATH = Path(os.environ.get('WFM_LIB') or
                  Path(__file__).resolve().parent / 'csrc' / 'libwfmb200.so')
 
-WFM_F64, WFM_F32, WFM_C128 = 0, 1, 2
-_NP_DTYPE = {WFM_F64: np.float64, WFM_F32: np.float32, WFM_C128: np.complex128}
+WFM_F64, WFM_F32, WFM_C128, WFM_F32_FAST = 0, 1, 2, 3
+_NP_DTYPE = {WFM_F64: np.float64, WFM_F32: np.float32, WFM_C128: np.complex128, WFM_F32_FAST: np.float32}
 
 
 class EngineUnavailable(RuntimeError):
@@ -266,7 +266,7 @@ class Program:
         torch = _torch()
         if dtype is None:
             dtype = self.default_dtype()
-        tdt = {WFM_F64: torch.float64, WFM_F32: torch.float32,
+        tdt = {WFM_F64: torch.float64, WFM_F32: torch.float32, WFM_F32_FAST: torch.float32,
                WFM_C128: torch.complex128}[dtype]
         if out is None:
             alloc = torch.zeros if accumulate else torch.empty
