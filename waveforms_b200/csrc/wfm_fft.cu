@@ -215,17 +215,28 @@ __device__ __forceinline__ void dft_small<25>(double2 (&v)[25], double sgn) {
 #define WFM_NO_RUN_TWIDDLE \
   template <int R>         \
   __device__ __forceinline__ void twiddle_run(double2 (&)[R], int, int, int) const {}
+// Shared-memory index of element i of a ping-pong buffer: one 16-byte pad after every 2^WFM_FFT_PAD elements.  A Stockham
+// stage WRITES its outputs at a lane stride of R * C elements (a multiple of 8 for every radix / interleave used here:
+// all lanes of a quarter warp on the same bank group, 4..8-way conflicts; ncu counted 15 M conflicts per row pass); the
+// pad rotates the bank group every 2^WFM_FFT_PAD elements and costs 3 % of the buffer.  0 = unpadded.
+#ifndef WFM_FFT_PAD
+#define WFM_FFT_PAD 0  // measured on cfg4 (625 x 640): 2.24 ms padded (5) / 2.26 (4) against 2.20 unpadded: the reads pay what the writes gain
+#endif
+__host__ __device__ __forceinline__ constexpr int spad(int i) { return WFM_FFT_PAD ? i + (i >> WFM_FFT_PAD) : i; }
+__host__ __device__ __forceinline__ constexpr size_t padded_points(size_t points) {
+  return WFM_FFT_PAD ? points + (points >> WFM_FFT_PAD) + 1 : points;
+}
 struct SmemIn {
   WFM_NO_RUN_TWIDDLE
   const double2* a;
   int logc;
-  __device__ __forceinline__ double2 operator()(int p, int c) const { return a[(p << logc) + c]; }
+  __device__ __forceinline__ double2 operator()(int p, int c) const { return a[spad((p << logc) + c)]; }
 };
 struct SmemOut {
   WFM_NO_RUN_TWIDDLE
   double2* b;
   int logc;
-  __device__ __forceinline__ void operator()(int p, int c, double2 v) const { b[(p << logc) + c] = v; }
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const { b[spad((p << logc) + c)] = v; }
 };
 
 // twiddles W^(k r), r = 1..R-1, of one butterfly: W^k, W^2k, W^4k (W^8k) come from the table,
@@ -388,15 +399,15 @@ struct MulHOut {
   WFM_NO_RUN_TWIDDLE  // spectrum x response on the way to shared memory
   double2* z;
   const double2* __restrict__ H;
-  __device__ __forceinline__ void operator()(int p, int, double2 v) const { z[p] = cmul(v, __ldg(H + p)); }
+  __device__ __forceinline__ void operator()(int p, int, double2 v) const { z[spad(p)] = cmul(v, __ldg(H + p)); }
 };
 __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan P, const double* __restrict__ x,
                                                                         double* __restrict__ y, int64_t stride,
                                                                         int64_t y_stride, int64_t n_sig,
                                                                         const double2* __restrict__ H, int nv) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + P.L;
-  const double2* tw = stage_twiddles(P, b + P.L);
+  double2* b = a + padded_points(P.L);
+  const double2* tw = stage_twiddles(P, b + padded_points(P.L));
   const int64_t s0 = 2 * (int64_t)blockIdx.x;
   const bool two = s0 + 1 < n_sig;
   const double* xs = x + s0 * stride;
@@ -497,8 +508,8 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
                                                                double scale, int64_t n_real, int64_t nv) {
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + ((size_t)N1 << logc);
-  const double2* tw = stage_twiddles(P, b + ((size_t)N1 << logc));
+  double2* b = a + padded_points((size_t)N1 << logc);
+  const double2* tw = stage_twiddles(P, b + padded_points((size_t)N1 << logc));
   const int c0 = blockIdx.x << logc;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
@@ -557,7 +568,7 @@ struct RowsMulHOut {
   int N2, rw, logc;
   __device__ __forceinline__ void operator()(int p, int c, double2 v) const {
     if (c < rw) v = cmul(v, __ldg(hrows + (int64_t)c * N2 + p));
-    z[(p << logc) + c] = v;
+    z[spad((p << logc) + c)] = v;
   }
 };
 struct NaturalOut {
@@ -576,8 +587,8 @@ __global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_k
                                                                double sgn, double scale) {
   const int N2 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + ((size_t)N2 << logc);
-  const double2* tw = stage_twiddles(P, b + ((size_t)N2 << logc));
+  double2* b = a + padded_points((size_t)N2 << logc);
+  const double2* tw = stage_twiddles(P, b + padded_points((size_t)N2 << logc));
   const int r0 = blockIdx.x << logc;
   const int rw = min(C, N1 - r0);
   const int64_t sig = blockIdx.y;
@@ -606,8 +617,8 @@ struct PlainOut {
 __global__ void __launch_bounds__(kFftThreads) fft_c2c_single_kernel(FftPlan P, double2* __restrict__ data,
                                                                      int64_t stride, double sgn, double scale) {
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
-  double2* b = a + P.L;
-  const double2* tw = stage_twiddles(P, b + P.L);
+  double2* b = a + padded_points(P.L);
+  const double2* tw = stage_twiddles(P, b + padded_points(P.L));
   double2* d = data + (int64_t)blockIdx.x * stride;
   smem_fft(P, 0, sgn, tw, PlainIn{d}, PlainOut{d, scale}, a, b);
 }
@@ -756,7 +767,7 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
     plan->inv_ns[s] = (uint32_t)(((uint64_t(1) << 32) + ns - 1) / ns);  // exact quotient for j < 2^16
     ns *= plan->radix[s];
   }
-  const size_t buffers = 2 * sizeof(double2) * (size_t)points;
+  const size_t buffers = 2 * sizeof(double2) * padded_points((size_t)points);
   plan->tw_in_smem = buffers + sizeof(double2) * (size_t)L <= (size_t)kSmemBudget;
   *smem = buffers + (plan->tw_in_smem ? sizeof(double2) * (size_t)L : 0);
   int dev = 0;
