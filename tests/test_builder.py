@@ -218,3 +218,77 @@ def test_channel_shards_equal_slices_of_the_whole_batch(ns):
         assert np.array_equal(part.facs['shift'], whole.facs['shift'][f0:f0 + len(part.facs)])
         assert np.array_equal(part.terms['amp_re'], whole.terms['amp_re'][t_0:t_0 + len(part.terms)])
         assert np.array_equal(part.waves['n'], whole.waves['n'][lo:hi]) and part.waves['out_off'][0] == 0
+
+
+def test_sweep_with_per_pulse_basis_arguments(ns):
+    """A parameter SWEEP (BASELINE configs[4]: amplitude x frequency x phase of multi-notch DRAG waveforms): the traced
+    parameters reach basis-function ARGUMENTS — the packers' arithmetic on them (2 pi (freq + delta),
+    2 pi delta t0 + phase, t0 + width / 2 ...) is replayed over the arrays.  (A `mixing` call whose carrier frequency
+    AND phase vary per pulse changes the canonical ORDER of its cosines with their values: such a sweep needs one
+    template per ordering; the spot check refuses it instead of building a wrong table.)"""
+    import warnings
+    from waveforms_b200 import multy_drag
+
+    def sweep(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sin(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, ), phase=phase, t0=t0)
+
+    def sweep_x(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sinx(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, 180e6), phase=phase, t0=t0)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        fns = [sweep, sweep_x]
+        templates = [PulseTemplate.trace(f, params=('t0', 'amp', 'freq', 'phase'),
+                                         probe={'t0': 100e-9, 'amp': 0.61, 'freq': 87e6, 'phase': 0.3},
+                                         check={'t0': 140e-9, 'amp': 0.27, 'freq': 133e6, 'phase': 2.1}) for f in fns]
+        rng = np.random.default_rng(5)
+        n_ch = 12
+        idx = [[int(rng.integers(0, 2))] for _ in range(n_ch)]          # one waveform per channel, as in the sweep
+        t0 = [[100e-9] for _ in range(n_ch)]
+        params = {'amp': [[rng.uniform(0.1, 1)] for _ in range(n_ch)], 'freq': [[rng.uniform(50e6, 150e6)] for _ in range(n_ch)],
+                  'phase': [[rng.uniform(0, 6)] for _ in range(n_ch)]}
+        got = pulse_train_batch(templates, idx, t0, 0, 4e-6, 5e9, params=params)
+        _, want = object_batch(ns, fns, idx, t0, 0, 4e-6, 5e9, params=params)
+    for k in ('waves', 'seg_bound', 'seg_ptr', 'terms', 'refs'):
+        assert np.array_equal(getattr(got, k), getattr(want, k)), k
+    for f in ('func', 'shift', 'a0', 'a1'):
+        assert np.array_equal(got.facs[f], want.facs[f]), f
+    # every factor's block of the argument pool, entry for entry
+    n_arg = {16: 8 + 2 * 3 + 4, 17: 8 + 2 * 3 + 5, 34: 5}
+    for i in range(len(got.facs)):
+        fn_id = int(got.facs['func'][i])
+        a, b = int(got.facs['arg_off'][i]), int(want.facs['arg_off'][i])
+        n = n_arg.get(fn_id, 0)
+        assert np.array_equal(got.args[a:a + n], want.args[b:b + n]), (i, fn_id)
+    # a dependence the packers cannot carry (the notch matrices depend on delta) is refused
+    with pytest.raises(UntraceablePulse):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            PulseTemplate.trace(lambda t0, delta: multy_drag.drag_sin(87e6, 30e-9, delta=delta, block_freq=(-250e6, ), t0=t0),
+                                params=('t0', 'delta'), probe={'t0': 1e-7, 'delta': 1e6}, check={'t0': 1.2e-7, 'delta': 2e6})
+
+
+@pytest.mark.gpu
+def test_sweep_batch_on_the_gpu(ns):
+    """cfg5 built from parameter arrays and sampled: equal to the object API's waveforms sampled one by one."""
+    import warnings
+    from waveforms_b200 import multy_drag
+    from waveforms_b200.batch import sample_pulse_trains
+
+    def sweep(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sin(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, ), phase=phase, t0=t0)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        tp = PulseTemplate.trace(sweep, params=('t0', 'amp', 'freq', 'phase'), probe={'t0': 100e-9, 'amp': 0.61, 'freq': 87e6, 'phase': 0.3},
+                                 check={'t0': 100e-9, 'amp': 0.27, 'freq': 133e6, 'phase': 2.1})
+        rng = np.random.default_rng(9)
+        n = 40
+        amp, freq, phase = rng.uniform(0.1, 1, (n, 1)), rng.uniform(50e6, 150e6, (n, 1)), rng.uniform(0, 6, (n, 1))
+        res = sample_pulse_trains([tp], np.zeros((n, 1), np.int64), np.full((n, 1), 100e-9), 0.0, 4e-6, 5e9,
+                                  params={'amp': amp, 'freq': freq, 'phase': phase}).numpy()
+        for c in (0, 17, n - 1):
+            w = sweep(100e-9, float(amp[c, 0]), float(freq[c, 0]), float(phase[c, 0]))
+            w.start, w.stop, w.sample_rate = 0.0, 4e-6, 5e9
+            want = w.sample()
+            assert np.max(np.abs(res[c] - want)) <= 4e-15 * np.max(np.abs(want))

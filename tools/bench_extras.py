@@ -180,7 +180,7 @@ def config_lines(ns, torch, engine, peak, fp64, quick=False):
     res['cfg1'] = line
 
     # ---- cfg3: RB batch, I/Q pairs, every channel distinct (vectorised builder) -------------
-    n_ch = 128 if quick else 512  # 512 channel pairs = one GPU's share of 4096 on 8 GPUs
+    n_ch = 128 if quick else 1024  # channel pairs; the full config is 4096 (512 per GPU on 8 GPUs)
     amps, phases = (0.5, 1.0), (0, np.pi / 2, np.pi, 3 * np.pi / 2)
 
     def fn(f8, a, p):
@@ -232,28 +232,47 @@ def config_lines(ns, torch, engine, peak, fp64, quick=False):
     del out
     res['cfg4'] = line
 
-    # ---- cfg5: multi-notch DRAG sweep, one GPU's share (12 500 x 20 000 samples) ------------
-    rng = np.random.default_rng(20260005)
-    chans = []
-    for k in range(10):
-        mk = multy_drag.drag_sinx if k == 9 else multy_drag.drag_sin
-        kw = dict(block_freq=(-250e6, 180e6)) if k == 9 else dict(block_freq=(-250e6, ))
-        with warnings.catch_warnings():
-            warnings.simplefilter('ignore')
-            w = rng.uniform(0.1, 1) * mk(rng.uniform(50e6, 150e6), 30e-9, plateau=0, delta=1e6, phase=rng.uniform(0, 6),
-                                          t0=100e-9, **kw)
-        w.start, w.stop, w.sample_rate = 0.0, 4e-6, 5e9
-        chans.append(w)
-    base = lower([channel_grid(w) for w in chans])
-    copies = (2500 if quick else 12500) // 10
-    batch = replicate(base, copies, amp_scale=2.0 ** -(np.arange(copies) % 4))
+    # ---- cfg5: multi-notch DRAG sweep, one GPU's share (12 500 x 20 000 samples), every waveform distinct -----------
+    # amplitude x frequency x phase grid built from PARAMETER ARRAYS (waveforms_b200.builder): 90 % drag_sin, 10 % drag_sinx
+    def sweep(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sin(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, ), phase=phase, t0=t0)
+
+    def sweep_x(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sinx(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, 180e6), phase=phase, t0=t0)
+
+    t_b = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        probe = {'t0': 100e-9, 'amp': 0.61, 'freq': 87e6, 'phase': 0.3}
+        check = {'t0': 100e-9, 'amp': 0.27, 'freq': 133e6, 'phase': 2.1}
+        tps = [PulseTemplate.trace(f, params=('t0', 'amp', 'freq', 'phase'), probe=probe, check=check) for f in (sweep, sweep_x)]
+        n_a, n_f, n_p = (25, 20, 5) if quick else (50, 50, 5)
+        A, F, Ph = np.meshgrid(np.linspace(0.1, 1.0, n_a), np.linspace(50e6, 150e6, n_f), np.linspace(0, 2 * np.pi, n_p, endpoint=False),
+                               indexing='ij')
+        n_w = A.size
+        kind = (np.arange(n_w) % 10 == 9).astype(np.int64)
+        col = lambda v: v.reshape(-1, 1)
+        batch = pulse_train_batch(tps, col(kind), np.full((n_w, 1), 100e-9), 0.0, 4e-6, 5e9,
+                                  params={'amp': col(A), 'freq': col(F), 'phase': col(Ph)})
+    build_s = time.perf_counter() - t_b
     prog, out, line = _program_line(torch, engine, batch, peak)
-    line['parity'] = _check_rows(out, batch, [0, 9], [chans[0], chans[9]])
-    per, n = time_cpu(lambda: cpu_sample(chans[0]), 1.0)
+    rows = [3, 9, n_w - 1]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        objs = []
+        for r in rows:  # full-size units through the object API
+            w = (sweep_x if kind[r] else sweep)(100e-9, float(A.flat[r]), float(F.flat[r]), float(Ph.flat[r]))
+            w = ns.WaveVStack([w])
+            w.start, w.stop, w.sample_rate = 0.0, 4e-6, 5e9
+            objs.append(w)
+    line['parity'] = _check_rows(out, batch, rows, objs)
+    per, n = time_cpu(lambda: cpu_sample(objs[0]), 1.0)
     line['cpu_baseline'] = {'value': 20000 / per / 1e9, 'unit': 'GSa/s', 'cores': 1, 'kind': 'port',
                             'sample': 'one drag_sin waveform (20 000 samples) by the oracle port (ids 16/17 are Python in the '
                                       'reference), %d passes' % n}
-    line['note'] = '9 drag_sin + 1 drag_sinx shapes x %d amplitude-scaled replicas (12 500 = the share of one of 8 GPUs)' % copies
+    line.update({'host_build_s': build_s,
+                 'note': '%d x %d x %d amplitude x frequency x phase sweep = %d distinct waveforms (12 500 = the share of one of 8 '
+                         'GPUs), built from parameter arrays' % (n_a, n_f, n_p, n_w)})
     prog.close()
     del out
     torch.cuda.empty_cache()

@@ -30,14 +30,14 @@ import numpy as np
 from . import _algebra as A
 from . import engine
 from .lowering import (PACKERS, FACTOR_DT, REF_DT, SEGPTR_DT, TERM_DT, WAVE_COMPLEX, WAVE_PAIR,
-                       WAVE_DT, LoweredBatch, _Pools, _lower_segment, _plan_slots)
+                       WAVE_DT, LoweredBatch, TracedFloat, _Pools, _lower_segment, _plan_slots)
 
 
 class UntraceablePulse(ValueError):
     """The pulse's tables depend on its start time in a way the tracer did not record."""
 
 
-class Sym(float):
+class Sym(TracedFloat):
     """A float that remembers how it was computed from the symbolic pulse parameters (the
     start time ``t0``, an amplitude, a phase ...).  Its value is the probe point's, so
     comparisons, sorting and hashing inside the algebra behave exactly as for a plain
@@ -204,7 +204,9 @@ class PulseTemplate:
         self.seg_fac, self.seg_term = [], []       # local CSR starts of the finite segments
         self.sym_shift = []                        # (fac row, expr)
         self.sym_amp = []                          # (term row, expr)
-        self.rot_rows = []                         # (fac row, local arg_off, w, base-shift expr)
+        self.sym_arg = []                          # (fac row, 'a0' | 'a1', expr): traced inline basis-function arguments
+        self.sym_pool = []                         # (local index in the argument pool, expr): traced pool entries
+        self.rot_rows = []                         # (fac row, local arg_off, w expr, base-shift expr)
         has_args = []                              # fac rows that own a block of the argument pool
         cplx = False
         for i in range(len(seq) - 1):
@@ -241,12 +243,23 @@ class PulseTemplate:
                 f = row[1]
                 if isinstance(f[-1], Sym):
                     self.sym_shift.append((base + r, f[-1].expr))
-                if any(isinstance(a, Sym) for a in f[1:-1]):
-                    raise UntraceablePulse('a basis-function argument (frequency, width ...) depends on a '
-                                           'traced parameter; only start times, phases and amplitudes can vary '
-                                           'per pulse — use one template per value')
+                # a traced basis-function ARGUMENT (frequency, phase, ... of a parameter sweep): whatever the packer
+                # derives from it by + - * / is replayed; anything else (np.sin of it, a matrix built from it)
+                # comes out as a plain number and is exposed by the check at the second parameter point
+                if row[0] == 'plain' and any(isinstance(a, Sym) for a in f[1:-1]):
+                    a0, a1, pool = PACKERS[f[0]](f[1:-1])
+                    if isinstance(a0, Sym):
+                        self.sym_arg.append((base + r, 'a0', a0.expr))
+                    if isinstance(a1, Sym):
+                        self.sym_arg.append((base + r, 'a1', a1.expr))
+                    off = pools.fac[base + r][1]
+                    for i, v in enumerate(pool):
+                        if isinstance(v, Sym):
+                            self.sym_pool.append((off + i, v.expr))
+                if row[0] in ('sincos', 'rot') and isinstance(f[1], Sym):
+                    self.sym_arg.append((base + r, 'a0', f[1].expr))
                 if row[0] == 'rot':
-                    self.rot_rows.append((base + r, pools.fac[base + r][1], f[1], Sym._expr(row[3][-1])))
+                    self.rot_rows.append((base + r, pools.fac[base + r][1], Sym._expr(f[1]), Sym._expr(row[3][-1])))
         self.n_seg = len(bounds) - 1
         self.facs = np.array(pools.fac, dtype=FACTOR_DT) if pools.fac else np.zeros(0, FACTOR_DT)
         self.terms = np.array(pools.term, dtype=TERM_DT) if pools.term else np.zeros(0, TERM_DT)
@@ -257,14 +270,13 @@ class PulseTemplate:
         self.has_args = np.asarray(has_args, dtype=np.int64)
         self.complex = cplx
 
-    def instantiate(self, t0, **more):
-        """Tables of ``len(t0)`` instances: (bounds[P, n_seg], facs[P, nf], args[P, na],
+    def instantiate(self, t0=None, **more):
+        """Tables of P instances: (bounds[P, n_seg], facs[P, nf], args[P, na],
         amps[P, n_sym_amp]); ``arg_off`` stays local to the instance."""
-        env = {'t0': np.ascontiguousarray(t0, dtype=np.float64)}
-        for n in self.params:
-            if n != 't0':
-                env[n] = np.ascontiguousarray(more[n], dtype=np.float64)
-        P = len(env['t0'])
+        if t0 is not None:
+            more = dict(more, t0=t0)
+        env = {n: np.ascontiguousarray(more[n], dtype=np.float64) for n in self.params}
+        P = len(env[self.params[0]])
         # parameter points repeat across channels (a gate grid): evaluate the distinct ones only
         if P > 1:
             pts = np.stack([env[n] for n in self.params], axis=1)
@@ -279,13 +291,18 @@ class PulseTemplate:
         facs = np.tile(self.facs, P).reshape(P, len(self.facs))
         for r, e in self.sym_shift:
             facs['shift'][:, r] = _eval(e, env)
+        for r, field, e in self.sym_arg:
+            facs[field][:, r] = _eval(e, env)
         amps = np.empty((P, len(self.sym_amp)), dtype=np.float64)
         for i, (_, e) in enumerate(self.sym_amp):
             amps[:, i] = _eval(e, env)
         args = np.tile(self.args, P).reshape(P, len(self.args))
-        for r, off, w, base_expr in self.rot_rows:
+        for i, e in self.sym_pool:
+            args[:, i] = _eval(e, env)
+        for r, off, w_expr, base_expr in self.rot_rows:
             # lowering._emit_rows: delta = w * (s_b - s_t); block (slot, s_b, delta, cos, sin)
             s_b = np.broadcast_to(_eval(base_expr, env), (P, ))
+            w = _eval(w_expr, env)
             delta = w * (s_b - facs['shift'][:, r])
             args[:, off + 1] = s_b
             args[:, off + 2] = delta

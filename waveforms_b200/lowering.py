@@ -192,6 +192,17 @@ class LoweredBatch:
         return b
 
 
+class TracedFloat(float):
+    """Base of ``builder.Sym``: a float that remembers how it was computed.  The packers
+    below keep such values as they are (``_f``) so that the vectorised builder can replay
+    a basis-function ARGUMENT (a frequency, a phase ...) over parameter arrays."""
+    __slots__ = ()
+
+
+def _f(v):
+    return v if isinstance(v, TracedFloat) else float(v)
+
+
 # ---------------------------------------------------------------------------
 # per-function argument packing.  Each packer returns (a0, a1, pool_list);
 # the device readers are in csrc/wfm_basis.cuh (same order).
@@ -202,7 +213,7 @@ def _pack_none(args):
 
 def _pack_one(args):
     v, = args
-    return float(v), 0.0, ()
+    return _f(v), 0.0, ()
 
 
 def _pack_interp(args):
@@ -213,22 +224,22 @@ def _pack_interp(args):
         raise ValueError('INTERP needs at least one point')
     # np.linspace(start, stop, n): step = (stop-start)/(n-1); xp[j]=j*step+start
     step = (stop - start) / (n - 1) if n > 1 else 0.0
-    return float(start), float(stop), (float(n), float(step), *pts.tolist())
+    return _f(start), _f(stop), (float(n), float(step), *pts.tolist())
 
 
 def _pack_linearchirp(args):
     f0, f1, T, phi0 = args
-    return float(f0), float(phi0), (float((f1 - f0) / (2 * T)), float(2 * np.pi))
+    return _f(f0), _f(phi0), (_f((f1 - f0) / (2 * T)), _f(2 * np.pi))
 
 
 def _pack_expchirp(args):
     f0, alpha, phi0 = args
-    return float(alpha), float(phi0), (float(2 * math.pi * f0), )
+    return _f(alpha), _f(phi0), (_f(2 * math.pi * f0), )
 
 
 def _pack_hypchirp(args):
     f0, k, phi0 = args
-    return float(k), float(phi0), (float(2 * np.pi * f0 / k), )
+    return _f(k), _f(phi0), (_f(2 * np.pi * f0 / k), )
 
 
 def _pack_drag(args):
@@ -237,10 +248,10 @@ def _pack_drag(args):
     k1 = 2 * np.pi * (freq + delta)
     k2 = 2 * np.pi * delta * t0 + phase
     if block_freq is None or block_freq - delta == 0:
-        return float(t0), float(o), (float(k1), float(k2), 0.0, 0.0, 0.0)
+        return _f(t0), _f(o), (_f(k1), _f(k2), 0.0, 0.0, 0.0)
     b = 1 / np.pi / 2 / (block_freq - delta)
-    return float(t0), float(o), (float(k1), float(k2), 1.0, float(-b * o),
-                                 float(2 * o))
+    return _f(t0), _f(o), (_f(k1), _f(k2), 1.0, _f(-b * o),
+                                 _f(2 * o))
 
 
 def _mollifier_poly(d):
@@ -255,15 +266,15 @@ def _pack_mollifier(args):
     r, d = args
     d = int(d)
     if d == 0:
-        return float(r), 0.0, ()
-    coeffs = [float(c) for c in _mollifier_poly(d).coeffs]
-    return float(r), float(d), (float(r**d), float(len(coeffs)), *coeffs)
+        return _f(r), 0.0, ()
+    coeffs = [_f(c) for c in _mollifier_poly(d).coeffs]
+    return _f(r), _f(d), (_f(r**d), _f(len(coeffs)), *coeffs)
 
 
 def _pack_dgaussian(args):
     s, n = args
     n = int(n)
-    return float(s), float(n), (float((-1)**n / s**n), )
+    return _f(s), _f(n), (_f((-1)**n / s**n), )
 
 
 PACKERS = {
@@ -374,7 +385,7 @@ def _emit_rows(pools, rows):
             pools.fac.append(_pack_factor(pools, row[1]))
         elif kind == 'sincos':
             f = row[1]
-            pools.fac.append((COS_SINCOS, 0, float(f[-1]), float(f[1]), 0.0))
+            pools.fac.append((COS_SINCOS, 0, float(f[-1]), _f(f[1]), 0.0))
         elif kind == 'nop':
             pools.fac.append((NOP, 0, 0.0, 0.0, 0.0))
         else:
@@ -384,7 +395,7 @@ def _emit_rows(pools, rows):
             off = pools.arg_block(('rot', w, s_t, s_b, base_slot),
                                   (float(base_slot), float(s_b), delta,
                                    math.cos(delta), math.sin(delta)))
-            pools.fac.append((COS_ROT, off, float(s_t), float(w), 0.0))
+            pools.fac.append((COS_ROT, off, float(s_t), _f(w), 0.0))
         pools.n_fac += 1
 
 

@@ -16,7 +16,7 @@ import numpy as np
 
 from ._algebra import (NDIGITS, DeviceBasis, _zero, basic_wave, inf, pi,
                        registerBaseFunc)
-from .lowering import register_packer
+from .lowering import _f, register_packer
 from .waveform import Waveform
 
 
@@ -89,7 +89,7 @@ def _common_pool(t0, freq, width, delta, phase, plateau, B, Amat, m, norm):
     rows = Amat[:, 0].copy()
     rows[0] = 1.0
     P = (B[:, :, 0] * rows[:, None]).sum(axis=0) / norm
-    return [float(k1), float(k2), float(tm1), float(tm2), float(plateau),
+    return [_f(k1), _f(k2), _f(tm1), _f(tm2), _f(plateau),
             float(m), float(P[0]), float(P[1]), *G[0].tolist(), *G[1].tolist()]
 
 
@@ -105,7 +105,7 @@ def pack_drag_sin(args):
     pool = _common_pool(t0, freq, width, delta, phase, plateau, B, Amat, m,
                         coeff)
     pool += [0.0, 0.0, 0.0, 0.0]  # no tabs: tl, tr, half width, rows
-    return float(t0), float(o), tuple(pool)
+    return _f(t0), float(o), tuple(pool)
 
 
 def pack_drag_sinx(args):
@@ -127,13 +127,13 @@ def pack_drag_sinx(args):
     tr = t0 + plateau + width / 2 + tab * width / 2
     rows = nb + 1
     L = len(left.coeffs)
-    pool += [float(tl), float(tr), float(width / 2), float(rows), float(L)]
+    pool += [_f(tl), _f(tr), float(width / 2), float(rows), float(L)]
     pool += B[:, 0, 0].tolist() + B[:, 1, 0].tolist()
     for poly in (left, right):
         for n in range(rows):
             c = np.atleast_1d(np.polyder(poly, m=n).coeffs)
             pool += [0.0] * (L - len(c)) + [float(v) for v in c]
-    return float(t0), float(o), tuple(pool)
+    return _f(t0), float(o), tuple(pool)
 
 
 DRAG_SIN = registerBaseFunc(DeviceBasis('DRAG_SIN'))
