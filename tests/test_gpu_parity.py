@@ -73,7 +73,7 @@ def test_batch_matches_single(ns):
             ch.start, ch.stop, ch.sample_rate = 0, (0.4e-6 + 13e-9 * k), 2e9  # ragged lengths
             ws.append(ch)
     res = sample_batch(ws, pair_iq=False).numpy()
-    paired = sample_batch(ws).numpy()  # default: I and Q of one mixing() call share their cosines
+    paired = sample_batch(ws, pair_iq=True).numpy()  # I and Q of one mixing() call share their cosines
     for w, y, yp in zip(ws, res, paired):
         assert np.array_equal(y, w.sample())
         # a pair takes ONE sincos per frequency for both rows: the rotation base of the second row's cosines differs
@@ -292,12 +292,13 @@ def test_too_long_channel_is_rejected(ns):
         engine.Program(batch)
 
 
-@pytest.mark.parametrize('unit', ['1', '2'])
-@pytest.mark.parametrize('name', ['readme_x_sample', 'cfg2_xy_stack', 'cfg2_z', 'cfg3_rb_I', 'cfg3_rb_Q', 'cfg5_drag_sin',
-                                  'complex_amp'])
+@pytest.mark.parametrize('unit', ['1', '2', '4'])
+@pytest.mark.parametrize('name', ['readme_x_sample', 'cfg2_xy_stack', 'cfg2_z', 'cfg3_rb_I', 'cfg3_rb_Q', 'cfg4_flux', 'cfg5_drag_sin',
+                                  'cfg5_drag_sinx', 'basis_zoo', 'clip_minmax', 'stack_ops', 'boundary_hits', 'complex_amp'])
 def test_both_unit_sizes(name, unit, golden, monkeypatch):
-    """The kernel evaluates one or two samples per lane (chosen from the program's density);
-    both evaluators must meet the fp64 tolerance on sparse and dense programs alike."""
+    """The kernel evaluates one, two (sparse kernel) or four (dense kernel: direct stores, every flat run a
+    patch row) samples per lane, chosen from the program's density; every evaluator must meet the fp64
+    tolerance on sparse and dense programs alike."""
     if name not in golden:
         pytest.skip('case not in the golden set')
     monkeypatch.setenv('WFM_K1_UNIT', unit)
@@ -309,6 +310,34 @@ def test_both_unit_sizes(name, unit, golden, monkeypatch):
         from waveforms_b200 import sample_batch
         f32 = sample_batch([b200_object(rec)], dtype=np.float32).numpy()[0]
         assert rel_err(f32.astype(np.float64), rec['expect']) <= FP32_TOL
+        fast = sample_batch([b200_object(rec)], dtype=np.float32, fast_fp32=True).numpy()[0]
+        assert rel_err(fast.astype(np.float64), rec['expect']) <= FP32_TOL
+
+
+@pytest.mark.parametrize('unit', ['1', '2', '4'])
+def test_unit_sizes_on_pairs_and_accumulate(unit, ns, monkeypatch):
+    """I/Q pairs and the accumulate epilogue through every kernel variant (small programs take the one-sample
+    sparse kernel by default, so the other variants are forced here)."""
+    from test_gpu_parity import _oracle_sample
+    from waveforms_b200 import sample_batch
+    monkeypatch.setenv('WFM_K1_UNIT', unit)
+    rng = np.random.default_rng(31)
+    ws = []
+    for k in range(6):
+        I, Q = ns.mixing(rng.uniform(0.2, 1) * ns.cosPulse(30e-9) >> (40e-9 + 37e-9 * k), freq=rng.uniform(-200e6, 200e6),
+                         phase=rng.uniform(0, 6), DRAGScaling=rng.uniform(2e-10, 1e-9))
+        Q = Q + 0.25
+        for w in (I, Q):
+            w.start, w.stop, w.sample_rate = 0, 0.45e-6, 2e9
+        ws += [I, Q]
+    got = sample_batch(ws, pair_iq=True).numpy()
+    for w, y in zip(ws, got):
+        assert rel_err(y, _oracle_sample(w)) <= FP64_TOL
+    x = np.linspace(-50e-9, 0.5e-6, 1201)
+    acc = np.full_like(x, 0.5)
+    ws[0](x, out=acc, accumulate=True)
+    from oracle import wfm_oracle as O
+    assert rel_err(acc - 0.5, O.waveform_call(ws[0].bounds, ws[0].seq, x)) <= 1e-11  # (y + 0.5) - 0.5 rounds once more
 
 
 @pytest.mark.parametrize('name', ['readme_x_sample', 'cfg2_xy_stack', 'cfg2_z', 'cfg3_rb_I', 'cfg4_flux', 'cfg5_drag_sin',

@@ -17,6 +17,14 @@ from helpers import FP32_TOL, FP64_TOL, rel_err
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def pair_small_batches(monkeypatch):
+    """'auto' pairing starts at batch.PAIR_MIN_SAMPLES samples (small launches are latency-bound); the batches
+    here are small and pairs are (part of) what is tested."""
+    from waveforms_b200 import batch
+    monkeypatch.setattr(batch, 'PAIR_MIN_SAMPLES', 0)
+
 N_PROGRAMS = 240
 
 

@@ -15,6 +15,14 @@ from waveforms_b200.builder import PulseTemplate, pulse_train_batch
 from waveforms_b200.lowering import (TERM_PLANE1, WAVE_PAIR, can_pair, find_pairs, lower)
 
 
+@pytest.fixture(autouse=True)
+def pair_small_batches(monkeypatch):
+    """'auto' pairing starts at batch.PAIR_MIN_SAMPLES samples (small launches are latency-bound); the batches
+    here are small and pairs are (part of) what is tested."""
+    from waveforms_b200 import batch
+    monkeypatch.setattr(batch, 'PAIR_MIN_SAMPLES', 0)
+
+
 PAIR_TOL = 4e-15  # paired vs unpaired evaluation: rotation bases differ, a few ulp
 
 
@@ -82,6 +90,18 @@ def test_unrelated_or_unpairable_channels_stay_single(ns):
     b = lower(find_pairs(items))
     assert b.n_channels == 5 and len(b.waves) == 4
     assert b.chan_off.tolist() == [0, 2000, 4000, 6000, 8000]
+
+
+def test_auto_pairing_starts_at_a_batch_size(ns, monkeypatch):
+    from waveforms_b200 import batch
+    I, Q = iq(ns)
+    items = [channel_grid(I), channel_grid(Q)]
+    monkeypatch.setattr(batch, 'PAIR_MIN_SAMPLES', 4_000_000)
+    assert len(batch.plan_pairs(items, 'auto')) == 2          # 4000 samples: two work items, lower latency
+    assert len(batch.plan_pairs(items * 1000, 'auto')) == 1000  # 4 M samples: paired
+    assert len(batch.plan_pairs(items, True)) == 1 and len(batch.plan_pairs(items, False)) == 2
+    with pytest.raises(ValueError):
+        batch.plan_pairs(items[:1], True)
 
 
 def test_stack_pair_merges_member_bounds(ns):

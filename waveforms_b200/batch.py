@@ -14,6 +14,9 @@ from . import engine
 from .lowering import can_pair, find_pairs, lower
 
 
+PAIR_MIN_SAMPLES = 4_000_000  # 'auto' pairing of I/Q channels starts at this batch size (per device)
+
+
 def channel_grid(w, sample_rate=None):
     """(Channel, Grid) of a Waveform/WaveVStack exactly as ``sample()`` would
     evaluate it (waveform.py:173-190)."""
@@ -23,6 +26,24 @@ def channel_grid(w, sample_rate=None):
             f'Waveform is not initialized. {w.start=}, {w.stop=}, sample_rate={rate}'
         )
     return w._channel(), engine.arange_grid(w.start, w.stop, 1 / rate)
+
+
+def plan_pairs(items, pair_iq='auto'):
+    """The items ``lower`` gets for one device's channels: (Channel, Grid), or
+    ((Channel, Channel), Grid) for two channels evaluated as one I/Q pair."""
+    items = list(items)
+    if pair_iq == 'auto':
+        if sum(g.n for _, g in items) >= PAIR_MIN_SAMPLES:
+            return find_pairs(items)
+        return items
+    if pair_iq is True:
+        if len(items) % 2:
+            raise ValueError('pair_iq=True needs an even number of channels')
+        for a, b in zip(items[0::2], items[1::2]):
+            if not can_pair(a, b, min_shared=0.0):
+                raise ValueError('pair_iq=True: channels differ in grid, clip or are complex')
+        return [((a[0], b[0]), a[1]) for a, b in zip(items[0::2], items[1::2])]
+    return items
 
 
 def shard_ranges(weights, n_shards):
@@ -78,6 +99,10 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
     segment's terms, see include/wfm_b200.h) instead of fp64 arithmetic rounded at
     the store, which meets 1e-6 on every program.
 
+    (Batches below ``PAIR_MIN_SAMPLES`` samples stay unpaired under 'auto': a pair is one
+    work item per tile instead of two, and a launch that cannot fill the GPU is bound by
+    the latency of its longest item — the README example is 1.8 x slower paired.)
+
     ``pair_iq``: 'auto' evaluates ADJACENT channels that share their grid and most
     of their basis functions — the I and Q of one ``mixing()`` call
     (waveform.py:1487-1527) — as one I/Q pair: every cos / envelope factor is
@@ -110,20 +135,7 @@ def sample_batch(waveforms, sample_rate=None, dtype=np.float64, devices=None,
         ranges = [(lo + (lo & 1) if lo < len(items) else lo, hi + (hi & 1) if hi < len(items) else hi)
                   for lo, hi in ranges]
 
-    def lowered(lo, hi):
-        part = items[lo:hi]
-        if pair_iq == 'auto':
-            part = find_pairs(part)
-        elif pair_iq is True:
-            if len(part) % 2:
-                raise ValueError('pair_iq=True needs an even number of channels')
-            for a, b in zip(part[0::2], part[1::2]):
-                if not can_pair(a, b, min_shared=0.0):
-                    raise ValueError('pair_iq=True: channels differ in grid, clip or are complex')
-            part = [((a[0], b[0]), a[1]) for a, b in zip(part[0::2], part[1::2])]
-        return lower(part)
-
-    shards = [(dev, lo, hi, lowered(lo, hi)) for dev, (lo, hi) in zip(devices, ranges)]
+    shards = [(dev, lo, hi, lower(plan_pairs(items[lo:hi], pair_iq))) for dev, (lo, hi) in zip(devices, ranges)]
 
     def run(shard):
         # one host thread per device: upload, pre-pass, K1 and the filters of every device run

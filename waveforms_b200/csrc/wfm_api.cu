@@ -516,16 +516,24 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
 
   // Unit: samples per lane and evaluation.  Dense programs (more than two rounds of 32 active
   // samples in an average 1024-sample tile) evaluate two samples per lane, sparse ones one.
+  // (Small programs skip the question and its round trip to the host: their figure of merit is latency — the README
+  // example is 20 000 samples — and the unit size only tunes throughput.)
+  const bool small_program = samples <= (int64_t)1 << 20;
   {
-    unsigned long long active = 0;
-    unsigned long long* d_active = (unsigned long long*)(base + o_stats);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_active, 0, sizeof(active), ST);
-    if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, ST);
-    if (e == cudaSuccess) e = read_words(&active, d_active, 2, ST);
     const char* force = std::getenv("WFM_K1_UNIT");
-    if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) p->dev.unit = force[0] - '0';
-    else if (samples > 0 && (double)active * 2.0 > (double)samples) p->dev.unit = wfm::kDenseUnit;  // mostly active: dense kernel
-    else p->dev.unit = (samples > 0 && (double)active * 1024.0 > 64.0 * (double)samples) ? 2 : 1;
+    if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) {
+      p->dev.unit = force[0] - '0';
+    } else if (small_program) {
+      p->dev.unit = 1;
+    } else {
+      unsigned long long active = 0;
+      unsigned long long* d_active = (unsigned long long*)(base + o_stats);
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_active, 0, sizeof(active), ST);
+      if (e == cudaSuccess) e = wfm::launch_count_active(p->dev, d->n_segs, d_active, ST);
+      if (e == cudaSuccess) e = read_words(&active, d_active, 2, ST);
+      if (samples > 0 && (double)active * 2.0 > (double)samples) p->dev.unit = wfm::kDenseUnit;  // mostly active: dense kernel
+      else p->dev.unit = (samples > 0 && (double)active * 1024.0 > 64.0 * (double)samples) ? 2 : 1;
+    }
     p->dev.dense = p->dev.unit == wfm::kDenseUnit ? 1 : 0;
   }
 
@@ -604,7 +612,11 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     if (e == cudaSuccess)
       e = wfm::launch_scan((uint32_t*)(base2 + o_pktsize), (uint32_t*)(base2 + o_pktoff), (uint32_t*)(base2 + o_scratch),
                            n_tiles, ST);
-    if (e == cudaSuccess) e = read_words(&total16, (uint32_t*)(base2 + o_pktoff) + n_tiles, 1, ST);
+    // the packet area: its exact size comes from the scan; a small program takes the upper bound (no packet exceeds its
+    // buffer: larger tiles are cold, header only) and saves the round trip
+    if (small_program && (size_t)n_tiles * (size_t)std::max(p->dev.pkt_cap, 96) <= ((size_t)4 << 20))
+      total16 = (uint32_t)(((size_t)n_tiles * (size_t)std::max(p->dev.pkt_cap, 96) + 15) / 16);
+    else if (e == cudaSuccess) e = read_words(&total16, (uint32_t*)(base2 + o_pktoff) + n_tiles, 1, ST);
   }
   tm.lap("device pre-pass 1 (tiles)");
   // pass 2: the packets themselves

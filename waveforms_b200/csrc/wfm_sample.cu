@@ -1764,9 +1764,31 @@ cudaError_t launch_prepare_tiles(const DevProgram& P, const PrepareCounts& n, co
   return cudaGetLastError();
 }
 
+// one block: the whole scan of a small program in one launch (the README example has 16 tiles)
+__global__ void __launch_bounds__(kScanBlock) scan_small_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  const int base = threadIdx.x * kScanItems;
+  uint32_t item[kScanItems];
+  uint32_t v = 0;
+  for (int i = 0; i < kScanItems; ++i) {
+    item[i] = base + i < n ? in[base + i] : 0;
+    v += item[i];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(v, &total);
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += item[i];
+  }
+  if (threadIdx.x == 0) out[n] = total;
+}
+
 cudaError_t launch_scan(const uint32_t* pkt_size, uint32_t* pkt_off, uint32_t* scratch, int64_t n, cudaStream_t stream) {
   const int64_t n_blocks = (n + kScanTile - 1) / kScanTile;
   if (n_blocks == 0) return cudaMemsetAsync(pkt_off, 0, sizeof(uint32_t), stream);
+  if (n_blocks == 1) {
+    scan_small_kernel<<<1, kScanBlock, 0, stream>>>(pkt_size, pkt_off, (int)n);
+    return cudaGetLastError();
+  }
   scan_reduce_kernel<<<(unsigned)n_blocks, kScanBlock, 0, stream>>>(pkt_size, scratch, n);
   scan_sums_kernel<<<1, kScanBlock, 0, stream>>>(scratch, n_blocks);
   scan_apply_kernel<<<(unsigned)n_blocks, kScanBlock, 0, stream>>>(pkt_size, scratch, pkt_off, n, n_blocks);
