@@ -101,9 +101,10 @@ def roofline(samples, ms, esz, peak, fp64=None, fp64_ops_per_sample=None):
         ops = samples * fp64_ops_per_sample / (ms * 1e-3)
         r['fp64_pipe'] = {'ops_per_sample': fp64_ops_per_sample, 'achieved_Gops': ops / 1e9,
                           'peak_Gops': fp64['dfma_per_s'] / 1e9, 'frac': ops / fp64['dfma_per_s'],
-                          'note': 'fp64 instructions x lanes per output sample, counted from the lowered tables '
-                                  '(range reduction 6 + two degree-6/7 polynomials 17 per sincos, 9 per rotated cosine, '
-                                  '2-3 per term, 2 per abscissa); peak = in-run DFMA calibration (wfm_calibrate_fp64)'}
+                          'note': 'fp64 instructions per output sample counted from the lowered tables (15 per sincos row of a '
+                                  'four-sample unit, 9 per rotated cosine, 2-3 per term, 2 per abscissa; ncu counts 42.7 on cfg3: '
+                                  'profiles/r2a_k1_cfg3_raw.csv, pipe 39.7 % active) x samples / time against the in-run DFMA '
+                                  'calibration (wfm_calibrate_fp64)'}
         if r['fp64_pipe']['frac'] > r['frac']:
             r['bound'] = 'fp64'
     return r
@@ -120,7 +121,9 @@ def fp64_ops_per_sample(batch):
     terms = len(batch.terms)
     refs = len(batch.refs)
     rows = 2 if (batch.waves['flags'] & 0x20).any() else 1
-    per_seg = (n_sc * 25 + n_rot * 9 + n_gen * 30 + terms * 2 + max(refs - terms, 0)) / n_seg_active + 2
+    # one range reduction + both polynomials ~24 fp64 instructions; the further samples of a four-sample unit take
+    # their (cos, sin) by rotation (~12): (24 + 3 * 12) / 4 = 15 per sample
+    per_seg = (n_sc * 15 + n_rot * 9 + n_gen * 30 + terms * 2 + max(refs - terms, 0)) / n_seg_active + 2
     return per_seg / rows
 
 
