@@ -1167,6 +1167,10 @@ __device__ __noinline__ void sample_tile_cold(const DevProgram& P, const TileDes
 #ifndef WFM_K1_DYNAMIC
 #define WFM_K1_DYNAMIC 4
 #endif
+// the dense kernel's tiles are long (hundreds of active samples each): smaller batches balance the tail of a launch
+#ifndef WFM_K1_DENSE_DYNAMIC
+#define WFM_K1_DENSE_DYNAMIC 2
+#endif
 extern __shared__ __align__(128) unsigned char k1_smem[];
 
 // kF32Eval (float output only): the fp32 EVALUATOR (eval_unit_f32) instead of the fp64 one rounded at the store.
@@ -1960,9 +1964,9 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
   if (fast32) {
     if (P.dense) {
       const bool dyn = n_tiles >= (int64_t)8 * 1024;
-      if (P.planes == 2) return dyn ? launch_dense<float, false, WFM_K1_DYNAMIC, true, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+      if (P.planes == 2) return dyn ? launch_dense<float, false, WFM_K1_DENSE_DYNAMIC, true, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
                                     : launch_dense<float, false, 0, true, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
-      return dyn ? launch_dense<float, false, WFM_K1_DYNAMIC, false, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
+      return dyn ? launch_dense<float, false, WFM_K1_DENSE_DYNAMIC, false, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream)
                  : launch_dense<float, false, 0, false, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
     }
     if (P.unit == 2) return launch_persistent<float, false, 2, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
@@ -1982,21 +1986,21 @@ cudaError_t launch_sample(const DevProgram& P, const TileDesc* tiles, int64_t ti
 #define WFM_DENSE_CASE(n, T, acc, batch, pair) \
   case n: return launch_dense<T, acc, batch, pair>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
       WFM_DENSE_CASE(0, double, false, 0, false)
-      WFM_DENSE_CASE(1, double, false, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(1, double, false, WFM_K1_DENSE_DYNAMIC, false)
       WFM_DENSE_CASE(2, double, false, 0, true)
-      WFM_DENSE_CASE(3, double, false, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(3, double, false, WFM_K1_DENSE_DYNAMIC, true)
       WFM_DENSE_CASE(4, double, true, 0, false)
-      WFM_DENSE_CASE(5, double, true, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(5, double, true, WFM_K1_DENSE_DYNAMIC, false)
       WFM_DENSE_CASE(6, double, true, 0, true)
-      WFM_DENSE_CASE(7, double, true, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(7, double, true, WFM_K1_DENSE_DYNAMIC, true)
       WFM_DENSE_CASE(8, float, false, 0, false)
-      WFM_DENSE_CASE(9, float, false, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(9, float, false, WFM_K1_DENSE_DYNAMIC, false)
       WFM_DENSE_CASE(10, float, false, 0, true)
-      WFM_DENSE_CASE(11, float, false, WFM_K1_DYNAMIC, true)
+      WFM_DENSE_CASE(11, float, false, WFM_K1_DENSE_DYNAMIC, true)
       WFM_DENSE_CASE(12, float, true, 0, false)
-      WFM_DENSE_CASE(13, float, true, WFM_K1_DYNAMIC, false)
+      WFM_DENSE_CASE(13, float, true, WFM_K1_DENSE_DYNAMIC, false)
       WFM_DENSE_CASE(14, float, true, 0, true)
-      default: return launch_dense<float, true, WFM_K1_DYNAMIC, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
+      default: return launch_dense<float, true, WFM_K1_DENSE_DYNAMIC, true>(P, tiles, tile_begin, n_tiles, dtype, out, stream);
 #undef WFM_DENSE_CASE
     }
   }
