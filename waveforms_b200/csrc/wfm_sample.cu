@@ -398,44 +398,49 @@ __device__ __forceinline__ Val<U> eval_unit(const unsigned char* __restrict__ bl
   if constexpr (kPair) plane1 = false;
 #pragma unroll 1
   for (int it = 0; it < n_term; ++it) {
-    const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags
+    const uint4 c = ct[it];  // CTerm: amp | o0 o1 | o2 flags (offsets in bytes for THIS unit size: scaled when the packet was built)
     const double amp = __hiloint2double((int)c.y, (int)c.x);
-    if constexpr (kPair) {
-      if ((c.w >> 16) & kCTermPlaneSwitch) {
-        on_switch(total);
-        plane1 = true;
+    const uint32_t fl = c.w >> 16;
+    bool ext = false;
+    if (fl & (kCTermPlaneSwitch | kCTermExt)) {  // one test on the common path
+      if constexpr (kPair) {
+        if (fl & kCTermPlaneSwitch) {
+          on_switch(total);
+          plane1 = true;
 #pragma unroll
-        for (int u = 0; u < U; ++u) total.v[u] = *offset1;  // the packet header in shared memory: not held in registers
+          for (int u = 0; u < U; ++u) total.v[u] = *offset1;  // the packet header in shared memory: not held in registers
+        }
       }
+      ext = has_ext && (fl & kCTermExt);
     }
     Val<U> prod;
-    if (has_ext && (c.w >> 16) & kCTermExt) {
+    if (ext) {
 #pragma unroll
       for (int u = 0; u < U; ++u) prod.v[u] = term_product_ext(P, gseg, it, sl, u);
     } else {
 #if WFM_K1_SKIP_UNIT_REFS
       // only the references the term has (an absent one is slot 0 = 1.0: the product is the same)
-      prod = ld_slot<U>(sl + (c.z & 0xffffu) * U);
+      prod = ld_slot<U>(sl + (c.z & 0xffffu));
       if (c.z >> 16) {
-        const Val<U> f1 = ld_slot<U>(sl + (c.z >> 16) * U);
+        const Val<U> f1 = ld_slot<U>(sl + (c.z >> 16));
 #pragma unroll
         for (int u = 0; u < U; ++u) prod.v[u] = mul(prod.v[u], f1.v[u]);
         if (c.w & 0xffffu) {
-          const Val<U> f2 = ld_slot<U>(sl + (c.w & 0xffffu) * U);
+          const Val<U> f2 = ld_slot<U>(sl + (c.w & 0xffffu));
 #pragma unroll
           for (int u = 0; u < U; ++u) prod.v[u] = mul(prod.v[u], f2.v[u]);
         }
       }
 #else
-      const Val<U> f0 = ld_slot<U>(sl + (c.z & 0xffffu) * U), f1 = ld_slot<U>(sl + (c.z >> 16) * U),
-                   f2 = ld_slot<U>(sl + (c.w & 0xffffu) * U);
+      const Val<U> f0 = ld_slot<U>(sl + (c.z & 0xffffu)), f1 = ld_slot<U>(sl + (c.z >> 16)),
+                   f2 = ld_slot<U>(sl + (c.w & 0xffffu));
 #pragma unroll
       for (int u = 0; u < U; ++u) prod.v[u] = mul(mul(f0.v[u], f1.v[u]), f2.v[u]);
 #endif
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) grp.v[u] = add(grp.v[u], mul(amp, prod.v[u]));
-    if ((c.w >> 16) & kCTermGroupEnd) {
+    if (fl & kCTermGroupEnd) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         total.v[u] = add(total.v[u], grp.v[u]);
@@ -631,13 +636,13 @@ __device__ __forceinline__ Val<U> eval_unit_f32(const unsigned char* __restrict_
         prod.v[u] = (float)pr;
       }
     } else {
-      prod = ld_slot_f<U>(sl + ((c.z & 0xffffu) * U >> 1));
+      prod = ld_slot_f<U>(sl + ((c.z & 0xffffu) >> 1));
       if (c.z >> 16) {
-        const ValF<U> f1 = ld_slot_f<U>(sl + ((c.z >> 16) * U >> 1));
+        const ValF<U> f1 = ld_slot_f<U>(sl + ((c.z >> 16) >> 1));
 #pragma unroll
         for (int u = 0; u < U; ++u) prod.v[u] *= f1.v[u];
         if (c.w & 0xffffu) {
-          const ValF<U> f2 = ld_slot_f<U>(sl + ((c.w & 0xffffu) * U >> 1));
+          const ValF<U> f2 = ld_slot_f<U>(sl + ((c.w & 0xffffu) >> 1));
 #pragma unroll
           for (int u = 0; u < U; ++u) prod.v[u] *= f2.v[u];
         }
@@ -1037,7 +1042,14 @@ __global__ void __launch_bounds__(256) fill_packets_kernel(DevProgram P, const T
           }
         }
         for (int q = lane; q < p1.term - p0.term; q += 32)
-          reinterpret_cast<uint4*>(ct)[q] = reinterpret_cast<const uint4*>(P.cterms + p0.term)[q];
+          {
+            // the slot offsets of the packet's terms are scaled by the unit here, once, not per evaluation
+            uint4 c = reinterpret_cast<const uint4*>(P.cterms + p0.term)[q];
+            const uint32_t U = (uint32_t)P.unit;
+            c.z = ((c.z & 0xffffu) * U) | (((c.z >> 16) * U) << 16);
+            c.w = ((c.w & 0xffffu) * U) | (c.w & 0xffff0000u);
+            reinterpret_cast<uint4*>(ct)[q] = c;
+          }
         blk += (size_t)pl.blk16 * 16;
       }
       ia += 1;
