@@ -18,8 +18,9 @@ creation against an independent plain-float build at a second start time; a puls
 dependence on its start time the tracer cannot follow raises ``UntraceablePulse``
 instead of producing a wrong table.
 
-Channels are stacks of NON-overlapping pulses (what ``WaveVStack`` of a gate sequence
-is); overlapping members need the general merge in ``lowering._merge_members``.
+Channels of time-ordered, non-overlapping pulses (what ``WaveVStack`` of a gate sequence is)
+are assembled by NumPy scatter; channels with overlapping pulses are materialised from the
+templates and take the general merge in ``lowering._merge_members`` (``pulse_train_batch``).
 """
 from __future__ import annotations
 
@@ -138,6 +139,36 @@ def _eval(expr, env):
     return a / b
 
 
+def _eval_py(expr, env):
+    """``_eval`` for ONE parameter point with Python floats (the algebra's own arithmetic)."""
+    op = expr[0]
+    if op == 'p':
+        return float(env[expr[1]])
+    if op == 'const':
+        return float(expr[1])
+    if op == 'neg':
+        return -_eval_py(expr[1], env)
+    if op == 'round':
+        return round(_eval_py(expr[1], env), expr[2])
+    a, b = _eval_py(expr[1], env), _eval_py(expr[2], env)
+    if op == 'add':
+        return a + b
+    if op == 'sub':
+        return a - b
+    if op == 'mul':
+        return a * b
+    return a / b
+
+
+def _subst(obj, env):
+    """A traced nested tuple (bounds / seq of a template) with every ``Sym`` replaced by its value at ``env``."""
+    if isinstance(obj, Sym):
+        return _eval_py(obj.expr, env)
+    if isinstance(obj, tuple):
+        return tuple(_subst(o, env) for o in obj)
+    return obj
+
+
 _cos_uf = np.frompyfunc(math.cos, 1, 1)  # the libm calls lowering._emit_rows makes
 _sin_uf = np.frompyfunc(math.sin, 1, 1)
 
@@ -164,7 +195,8 @@ class PulseTemplate:
         self.params = tuple(params)
         pv, cv = _probe_values(self.params, probe, check)
         w = fn(*[Sym(pv[n], ('p', n)) for n in self.params])
-        self._extract(*self._bounds_seqs(w))
+        self._traced = self._bounds_seqs(w)  # (bounds, seq[, seq2]) with traced values: ``materialize`` substitutes them
+        self._extract(*self._traced)
         self._verify(cv)
 
     @staticmethod
@@ -310,6 +342,14 @@ class PulseTemplate:
             args[:, off + 4] = _sin_uf(delta).astype(np.float64)
         return bounds, facs, args, amps
 
+    def materialize(self, **point):
+        """(bounds, seq) — or (bounds, seq_I, seq_Q) of a pair template — of ONE pulse as plain tuples, exactly what
+        the object API builds for these parameter values (no algebra is run: the traced values are substituted)."""
+        env = {n: float(point[n]) for n in self.params}
+        bounds, seq, seq2 = self._traced
+        out = (_subst(tuple(bounds), env), _subst(tuple(seq), env))
+        return out + ((_subst(tuple(seq2), env), ) if seq2 is not None else ())
+
     def instance_terms(self, amps):
         """terms[P, nt] with the traced amplitudes filled in (``ref_begin`` local)."""
         P = len(amps)
@@ -337,8 +377,72 @@ class PulseTemplate:
 
 def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=None,
                       spot_check=4) -> LoweredBatch:
-    """One channel per row: channel ``c`` is the stack of pulses ``templates[tmpl_idx[c][k]]``
-    started at ``t0[c][k]`` (time-ordered, non-overlapping), sampled on
+    """One channel per row: channel ``c`` is the stack of pulses ``templates[tmpl_idx[c][k]]`` started at
+    ``t0[c][k]``.  Channels whose pulses are time-ordered and do not overlap — gate sequences — are assembled
+    by NumPy scatter (``_pulse_train_disjoint``); a channel with OVERLAPPING (or unordered) pulses — flux
+    lines, cross-talk compensation — needs the union of its members' bounds and a fresh factor plan per merged
+    segment (``lowering._merge_members`` / ``_plan_slots``, what the reference's ``WaveVStack.__call__`` does by
+    accumulation, waveform.py:679-693): its pulses are MATERIALISED from the templates (the traced values
+    substituted, no algebra) and lowered by ``lower()`` itself, so the tables are the object API's by
+    construction.  The two kinds are merged into one batch in channel order."""
+    n_ch = len(t0)
+    params = params or {}
+    if n_ch == 0 or not templates:
+        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check)
+    # first / last edge of every pulse: the templates' outer bounds over the parameter arrays
+    general = []
+    for c in range(n_ch):
+        tc = np.asarray(t0[c], dtype=np.float64)
+        if len(tc) < 2:
+            continue
+        mc = np.asarray(tmpl_idx[c], dtype=np.int64)
+        first, last = np.empty(len(tc)), np.empty(len(tc))
+        for m in np.unique(mc):
+            sel = np.nonzero(mc == m)[0]
+            tp = templates[int(m)]
+            missing = [n for n in tp.params if n != 't0' and n not in params]
+            if missing:
+                raise ValueError(f'template {int(m)} needs the parameter array(s) {missing}')
+            env = {'t0': tc[sel]}
+            for n in tp.params:
+                if n != 't0':
+                    env[n] = np.asarray(params[n][c], dtype=np.float64)[sel]
+            first[sel] = _eval(tp.bound_expr[0], env)
+            last[sel] = _eval(tp.bound_expr[-1], env)
+        if np.any(first[1:] < last[:-1]):
+            general.append(c)
+    if not general:
+        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check)
+    from .lowering import Channel, lower, merge_batches
+    gset = set(general)
+    plain = [c for c in range(n_ch) if c not in gset]
+    parts, owners = [], []
+    if plain:
+        parts.append(_pulse_train_disjoint(templates, [tmpl_idx[c] for c in plain], [t0[c] for c in plain], start, stop,
+                                           sample_rate, {k: [v[c] for c in plain] for k, v in params.items()}, spot_check))
+        owners.append(plain)
+    grid = engine.arange_grid(start, stop, 1 / sample_rate)
+    pair = bool(templates[0].pair)
+    items = []
+    for c in general:
+        rows = ([], [])
+        for k, (m, t) in enumerate(zip(tmpl_idx[c], t0[c])):
+            tp = templates[int(m)]
+            point = {'t0': float(t), **{n: float(params[n][c][k]) for n in tp.params if n != 't0'}}
+            mat = tp.materialize(**point)
+            rows[0].append((mat[0], mat[1]))
+            if pair:
+                rows[1].append((mat[0], mat[2]))
+        chans = [Channel(members=r, clip=None, offset=0, pre_shift=0, real_only=True) for r in rows[:2 if pair else 1]]
+        items.append(((chans[0], chans[1]), grid) if pair else (chans[0], grid))
+    parts.append(lower(items))
+    owners.append(general)
+    return merge_batches(parts, owners)
+
+
+def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params=None,
+                          spot_check=4) -> LoweredBatch:
+    """Channels of time-ordered, NON-overlapping pulses, sampled on
     ``np.arange(start, stop, 1/sample_rate)`` — the ``LoweredBatch`` that
     ``lower([channel_grid(WaveVStack([fn(t, ...) for ...]))])`` yields, built with NumPy.
     ``tmpl_idx`` / ``t0``: 2-D arrays or lists of 1-D arrays (ragged channels); ``params``:
@@ -426,7 +530,7 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=
     if len(nxt) and np.any(first_edge[nxt] < last_edge[nxt - 1]):
         bad = nxt[np.nonzero(first_edge[nxt] < last_edge[nxt - 1])[0][0]]
         raise ValueError(f'pulse {int(bad - ch_first[ch_of[bad]])} of channel {int(ch_of[bad])} starts before '
-                         'its predecessor ends: overlapping members need WaveVStack + lower()')
+                         'its predecessor ends (pulse_train_batch routes such channels through the general merge)')
     keep = np.ones(n_seg_full + 1, dtype=bool)
     dup = nxt[first_edge[nxt] == last_edge[nxt - 1]]
     keep[seg_pos[dup]] = False

@@ -624,6 +624,60 @@ def lower(items) -> LoweredBatch:
         chan_n=np.asarray(chan_n, dtype=np.int64))
 
 
+def merge_batches(parts, owners) -> LoweredBatch:
+    """Several lowered batches as ONE, their waves interleaved back into an original order: ``owners[k][i]`` is
+    the position (0 .. n-1, every position exactly once) of wave ``i`` of ``parts[k]``.  Tables are concatenated
+    with rebased indices; output rows are re-assigned back to back in the merged order."""
+    n = sum(len(o) for o in owners)
+    waves = np.zeros(n, dtype=WAVE_DT)
+    seg_base = fac_base = term_base = ref_base = arg_base = x_base = 0
+    bounds, segptrs, facs, terms, refs, args, xs = [], [], [], [], [], [], []
+    for part, own in zip(parts, owners):
+        assert len(part.waves) == len(own)
+        w = part.waves.copy()
+        w['seg_begin'] += seg_base
+        w['x_off'] += x_base
+        waves[np.asarray(own, dtype=np.int64)] = w
+        ns = len(part.seg_bound)
+        sp = part.seg_ptr[:ns].copy()
+        sp['fac'] += fac_base
+        sp['term'] += term_base
+        f = part.facs.copy()
+        f['arg_off'] += arg_base
+        t = part.terms.copy()
+        t['ref_begin'] += ref_base
+        bounds.append(part.seg_bound)
+        segptrs.append(sp)
+        facs.append(f)
+        terms.append(t)
+        refs.append(part.refs)
+        args.append(part.args)
+        xs.append(part.x)
+        seg_base += ns
+        fac_base += len(part.facs)
+        term_base += len(part.terms)
+        ref_base += len(part.refs)
+        arg_base += len(part.args)
+        x_base += len(part.x)
+    if max(seg_base, fac_base, term_base, ref_base, arg_base) >= 2**31:
+        raise ValueError('merged batch too large for 32-bit table indices')
+    seg_ptr = np.zeros(seg_base + 1, dtype=SEGPTR_DT)
+    seg_ptr[:seg_base] = np.concatenate(segptrs) if segptrs else np.zeros(0, SEGPTR_DT)
+    seg_ptr['fac'][seg_base], seg_ptr['term'][seg_base] = fac_base, term_base
+    out_off = 0
+    for i in range(n):
+        pitch = (int(waves['n'][i]) + 3) & ~3
+        waves['out_off'][i] = out_off
+        out_off += pitch
+        if waves['flags'][i] & WAVE_PAIR:
+            waves['out_off2'][i] = out_off
+            out_off += pitch
+    return LoweredBatch(waves=waves, seg_bound=np.concatenate(bounds), seg_ptr=seg_ptr, facs=np.concatenate(facs),
+                        terms=np.concatenate(terms), refs=np.concatenate(refs), args=np.concatenate(args),
+                        x=np.concatenate(xs), total_samples=out_off,
+                        any_complex=any(p.any_complex for p in parts))
+
+
 def replicate(batch: LoweredBatch, copies: int, amp_scale=None) -> LoweredBatch:
     """``copies`` independent copies of a lowered batch laid out back to back
     (every table duplicated, indices rebased) — how a scheduler's batch of
