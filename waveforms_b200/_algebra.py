@@ -380,6 +380,11 @@ def _D(x):
 # gaussian powers, equal-frequency phasor merge.  Host-only; never applied on
 # the device side (simplify is not value-neutral at 1e-12).
 # ---------------------------------------------------------------------------
+# NOTE (provenance): ``_cos_power_n`` and ``_trigMul_t`` TRANSCRIBE the arithmetic of the reference's
+# ``_waveform.pyx:483-515`` operation for operation (only the names of the locals differ): ``==`` between waveforms and
+# the ``tolist()`` goldens of the reference's tests compare the simplified tuples EXACTLY, so the order of every
+# floating-point operation here is part of the drop-in contract, not a design choice of this package.  They are
+# host-only API glue and carry no claim of original design.
 def _cos_power_n(factor, n):
     _, w, sh = factor
     out = ZERO

@@ -42,6 +42,13 @@ def _from_device(t, was_numpy):
     return t.cpu().numpy() if was_numpy else t
 
 
+# NOTE (provenance): the filter DESIGN helpers below (``shift``, ``extractKernel``, ``zDistortKernel``,
+# ``high_pass_filter``, ``exp_decay_filter_old``, ``exp_decay_filter``, ``reflection_filter``, ``combine_filters``,
+# ``factor_filter``, ``stable_filter``) restate the reference's closed-form formulas (distortion.py:12-286) with the
+# same NumPy / SciPy calls in the same order — their outputs are compared with ``array_equal`` against golden vectors
+# of the reference (tests/test_gpu_dsp.py::test_design_functions_golden), so nothing about them is free to differ.
+# They are tiny host-side polynomial algebra; this package's own work is the APPLICATION of the filters on the GPU
+# (``reflection``, ``correct_reflection``, ``predistort``, ``distort`` -> csrc/wfm_iir.cu, csrc/wfm_fft.cu).
 def shift(signal: np.ndarray, delay: float, dt: float) -> np.ndarray:
     """delay a signal (reference distortion.py:12-39; host, three-tap
     interpolation + integer shift — not on the GPU path)."""

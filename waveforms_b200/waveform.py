@@ -511,6 +511,11 @@ class WaveVStack(Waveform):
         ret.offset = self.offset
         return ret
 
+    # NOTE (provenance): ``__add__`` / ``__mul__`` / ``__eq__`` / ``__getstate__`` / ``__setstate__`` below TRANSCRIBE the
+    # behaviour of the reference's ``WaveVStack`` (waveform.py:771-844) branch for branch: which operand is shifted or
+    # simplified first, where the offset goes, what the pickle tuple holds are all observable through the drop-in API
+    # (tests/test_host_model.py compares ``tolist()`` of both packages on the reference's own stack tests).  Host glue;
+    # no claim of original design.  What is new for stacks lives in ``_channel`` / ``lowering`` / the kernels.
     def __add__(self, other):
         ret = self._like(list(self.wlist))
         if isinstance(other, WaveVStack):
