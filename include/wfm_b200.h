@@ -142,7 +142,13 @@ typedef struct WfmRef {
   int32_t kind;
 } WfmRef;
 
-/* host-side view of a lowered batch; all pointers are HOST pointers */
+/* WfmProgramDesc.flags */
+#define WFM_DESC_DEVICE_TABLES 0x1u /* facs / terms / refs / args are DEVICE pointers (written by wfm_expand_templates):
+                                       copied device -> device, their rows are not re-validated on the host; max_rows
+                                       must then give the largest number of value rows (factor rows that are not
+                                       WFM_NOP) of any segment */
+
+/* host-side view of a lowered batch; all pointers are HOST pointers (but see WFM_DESC_DEVICE_TABLES) */
 typedef struct WfmProgramDesc {
   int64_t n_waves;   const WfmWave*   waves;
   int64_t n_segs;    const double*    seg_bound; /* [n_segs] upper bounds        */
@@ -152,7 +158,38 @@ typedef struct WfmProgramDesc {
   int64_t n_refs;    const WfmRef*    refs;
   int64_t n_args;    const double*    args;      /* f64 argument / table pool    */
   int64_t n_x;       const double*    x;         /* explicit abscissae (may be NULL) */
+  uint32_t flags;    int32_t max_rows;           /* both 0 for plain host tables */
 } WfmProgramDesc;
+
+/* ---- pulse templates expanded on the device (see csrc/wfm_expand.cu) ------------------------------------------
+ * All pointers of WfmExpandDesc are DEVICE pointers. */
+enum { WFM_PATCH_SHIFT = 0, WFM_PATCH_A0 = 1, WFM_PATCH_A1 = 2, WFM_PATCH_ARG = 3, WFM_PATCH_AMP = 4, WFM_PATCH_VALUE = 5 };
+typedef struct WfmTemplateDesc {   /* ranges of ONE template in the concatenated template tables — 48 bytes */
+  int32_t fac0, n_fac, term0, n_term, ref0, n_ref, arg0, n_arg, patch0, n_patch, rot0, n_rot;
+} WfmTemplateDesc;
+typedef struct WfmPatch {          /* payload slot j of a pulse goes to entry `index` of table `kind` (template-local) */
+  int32_t kind, index;
+} WfmPatch;
+typedef struct WfmRotRow {         /* a WFM_COS_ROT row of the template: pool block at arg_off (template-local) */
+  int32_t fac_row, arg_off;
+  double  w, s_b;                  /* constants ... */
+  int32_t w_slot, sb_slot;         /* ... unless >= 0: payload slots holding the per-pulse values */
+} WfmRotRow;
+typedef struct WfmExpandDesc {
+  int64_t n_templates;  const WfmTemplateDesc* templates;
+  const WfmFactor* t_facs;  const WfmTerm* t_terms;  const WfmRef* t_refs;  const double* t_args;
+  const uint8_t* t_has_args;       /* per template factor row: owns a block of the argument pool */
+  const WfmPatch* patches;  const WfmRotRow* rots;
+  int64_t n_pulses;
+  const int32_t* pulse_tmpl;       /* [n_pulses] template of every pulse                         */
+  const int32_t* pulse_fac;        /* [n_pulses] first row of the pulse in the expanded tables   */
+  const int32_t* pulse_term;  const int32_t* pulse_ref;  const int32_t* pulse_arg;
+  int32_t payload_stride;  int32_t reserved;
+  const double* payload;           /* [n_pulses][payload_stride]: one double per patch of the pulse's template */
+} WfmExpandDesc;
+/* writes the rows of every pulse into the DEVICE tables facs / terms / refs / args (sized by the caller) */
+int  wfm_expand_templates(const WfmExpandDesc* d, WfmFactor* facs, WfmTerm* terms, WfmRef* refs, double* args,
+                          void* stream);
 
 typedef struct WfmProgram* wfm_program_t;
 

@@ -348,3 +348,159 @@ def test_overlapping_flux_channels_on_the_gpu(ns):
         w.start, w.stop, w.sample_rate = 0.0, t_end, rate
         want = X.cpu_sample(w)
         assert np.max(np.abs(res[c] - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+# -- compact batches: templates + per-pulse payload, rows written on the device (csrc/wfm_expand.cu) ----------------
+def replay_expansion(cb):
+    """What expand_kernel does, in numpy: the test-side statement of the compact format."""
+    from waveforms_b200.lowering import FACTOR_DT, REF_DT, TERM_DT
+    facs, terms = np.zeros(cb.n_facs, FACTOR_DT), np.zeros(cb.n_terms, TERM_DT)
+    refs, args = np.zeros(cb.n_refs, REF_DT), np.zeros(cb.n_args, np.float64)
+    for p, m in enumerate(cb.pulse_tmpl):
+        T = cb.t_desc[m]
+        f0, t0, r0, a0 = int(cb.pulse_fac[p]), int(cb.pulse_term[p]), int(cb.pulse_ref[p]), int(cb.pulse_arg[p])
+        f = cb.t_facs[T['fac0']:T['fac0'] + T['n_fac']].copy()
+        f['arg_off'] += np.where(cb.t_has_args[T['fac0']:T['fac0'] + T['n_fac']] != 0, a0, 0).astype(np.int32)
+        facs[f0:f0 + len(f)] = f
+        t = cb.t_terms[T['term0']:T['term0'] + T['n_term']].copy()
+        t['ref_begin'] += r0
+        terms[t0:t0 + len(t)] = t
+        refs[r0:r0 + T['n_ref']] = cb.t_refs[T['ref0']:T['ref0'] + T['n_ref']]
+        args[a0:a0 + T['n_arg']] = cb.t_args[T['arg0']:T['arg0'] + T['n_arg']]
+        pay = cb.payload[p]
+        for j, pt in enumerate(cb.t_patches[T['patch0']:T['patch0'] + T['n_patch']]):
+            k, i = int(pt['kind']), int(pt['index'])
+            if k == 0:
+                facs['shift'][f0 + i] = pay[j]
+            elif k == 1:
+                facs['a0'][f0 + i] = pay[j]
+            elif k == 2:
+                facs['a1'][f0 + i] = pay[j]
+            elif k == 3:
+                args[a0 + i] = pay[j]
+            elif k == 4:
+                terms['amp_re'][t0 + i] = pay[j]
+        for rr in cb.t_rots[T['rot0']:T['rot0'] + T['n_rot']]:
+            w = pay[rr['w_slot']] if rr['w_slot'] >= 0 else rr['w']
+            sb = pay[rr['sb_slot']] if rr['sb_slot'] >= 0 else rr['s_b']
+            dl = w * (sb - facs['shift'][f0 + rr['fac_row']])
+            o = a0 + int(rr['arg_off'])
+            args[o + 1:o + 5] = sb, dl, math.cos(dl), math.sin(dl)
+    return facs, terms, refs, args
+
+
+def assert_compact_equals_full(cb, full, trig_ulps=2):
+    for k in ('waves', 'seg_bound', 'seg_ptr'):
+        assert np.array_equal(getattr(cb, k), getattr(full, k)), k
+    assert (cb.n_facs, cb.n_terms, cb.n_refs, cb.n_args) == (len(full.facs), len(full.terms), len(full.refs), len(full.args))
+    facs, terms, refs, args = replay_expansion(cb)
+    assert np.array_equal(facs, full.facs) and np.array_equal(terms, full.terms) and np.array_equal(refs, full.refs)
+    # cos / sin of the rotation blocks: libm here, numpy in the full build
+    assert np.allclose(args, full.args, rtol=0, atol=trig_ulps * 2.3e-16)
+    assert np.array_equal(cb.chan_off, full.chan_off) and np.array_equal(cb.chan_n, full.chan_n)
+    assert cb.total_samples == full.total_samples
+
+
+def test_compact_batch_replays_to_the_full_tables(ns):
+    """pulse_train_batch(compact=True): per pulse only (template, 4 offsets, payload) — replayed, the full tables."""
+    fns = drag_fns(ns, 0)[:4] + [lambda t0: -0.25 * ns.square(60e-9, edge=2e-9) >> t0,
+                                 lambda t0: 0.3 * ns.gaussian(30e-9, plateau=20e-9) >> t0]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(23)
+    idx, t0 = [], []
+    for n in (40, 3, 0, 25):
+        idx.append(rng.integers(0, len(fns), n))
+        t0.append(200e-9 + 100e-9 * np.arange(n) + rng.uniform(0, 20e-9, n))
+    full = pulse_train_batch(templates, idx, t0, 0, 6e-6, 2e9)
+    cb = pulse_train_batch(templates, idx, t0, 0, 6e-6, 2e9, compact=True)
+    assert_compact_equals_full(cb, full)
+    assert cb.nbytes() < 0.45 * cb.expanded_nbytes() and cb.expanded_nbytes() == full.nbytes()
+    assert cb.max_rows >= 2
+
+
+def test_compact_batch_with_per_pulse_parameters(ns):
+    """amplitude / phase / frequency per pulse: AMP, A0/A1 and ARG patches, traced rotation frequencies."""
+    import warnings
+    from waveforms_b200 import multy_drag
+    fns = [
+        lambda t0, amp, phase: ns.mixing(amp * ns.cosPulse(20e-9) >> t0, freq=-60e6, phase=phase, DRAGScaling=4e-10)[0],
+        lambda t0, amp, phase: ns.mixing(amp * ns.gaussian(20e-9) >> t0, freq=145e6, phase=phase, DRAGScaling=7e-10)[1],
+        lambda t0, amp, phase: (amp * ns.square(50e-9, edge=2e-9) >> t0) * 0.5,
+    ]
+    templates = [PulseTemplate.trace(f, params=('t0', 'amp', 'phase')) for f in fns]
+    rng = np.random.default_rng(29)
+    idx, t0, amp, phase = [], [], [], []
+    for n in (30, 9):
+        idx.append(rng.integers(0, len(fns), n))
+        t0.append(150e-9 + 80e-9 * np.arange(n) + rng.uniform(0, 20e-9, n))
+        amp.append(rng.uniform(-1, 1, n))
+        phase.append(rng.uniform(0, 2 * np.pi, n))
+    params = {'amp': amp, 'phase': phase}
+    full = pulse_train_batch(templates, idx, t0, 0, 4e-6, 2e9, params=params)
+    cb = pulse_train_batch(templates, idx, t0, 0, 4e-6, 2e9, params=params, compact=True)
+    assert_compact_equals_full(cb, full)
+
+    def sweep(t0, amp, freq, phase):
+        return amp * multy_drag.drag_sin(freq, 30e-9, plateau=0, delta=1e6, block_freq=(-250e6, ), phase=phase, t0=t0)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        tp = PulseTemplate.trace(sweep, params=('t0', 'amp', 'freq', 'phase'), probe={'t0': 100e-9, 'amp': 0.61, 'freq': 87e6, 'phase': 0.3},
+                                 check={'t0': 140e-9, 'amp': 0.27, 'freq': 133e6, 'phase': 2.1})
+        n = 9
+        kw = dict(params={'amp': rng.uniform(0.1, 1, (n, 1)), 'freq': rng.uniform(50e6, 150e6, (n, 1)), 'phase': rng.uniform(0, 6, (n, 1))})
+        a = (np.zeros((n, 1), np.int64), np.full((n, 1), 100e-9), 0.0, 4e-6, 5e9)
+        assert_compact_equals_full(pulse_train_batch([tp], *a, compact=True, **kw), pulse_train_batch([tp], *a, **kw))
+
+
+def test_compact_batch_of_iq_pairs(ns):
+    """templates that return the (I, Q) tuple of mixing(): pair rows, plane flags and both offsets survive"""
+    fns = [lambda t0, a=a, ph=ph: ns.mixing(a * ns.cosPulse(20e-9) >> t0, freq=-60e6, phase=ph, DRAGScaling=4e-10)
+           for a in (0.5, 1.0) for ph in (0, np.pi / 2, np.pi)]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(37)
+    idx = rng.integers(0, len(fns), (5, 120))
+    t0 = np.tile(100e-9 + 20e-9 * np.arange(120) + 10e-9, (5, 1))
+    a = (templates, idx, t0, 0, 3e-6, 2e9)
+    full, cb = pulse_train_batch(*a), pulse_train_batch(*a, compact=True)
+    assert_compact_equals_full(cb, full)
+    assert cb.n_channels == 10 and cb.nbytes() < 0.2 * full.nbytes()
+
+
+def test_compact_refuses_what_it_cannot_carry(ns):
+    tp = PulseTemplate.trace(lambda t0: 0.3 * ns.gaussian(30e-9) >> t0)
+    with pytest.raises(ValueError, match='compact'):
+        pulse_train_batch([tp], [[0, 0]], [[100e-9, 110e-9]], 0, 1e-6, 2e9, compact=True)     # overlapping pulses
+    tc = PulseTemplate.trace(lambda t0: (0.5 + 0.25j) * ns.cosPulse(16e-9) >> t0)
+    cb = pulse_train_batch([tc], [[0]], [[100e-9]], 0, 1e-6, 2e9, compact=True)               # a stack stays real
+    assert not cb.any_complex
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_compact_batch_on_the_gpu(ns, dtype):
+    """The device expansion + WFM_DESC_DEVICE_TABLES program against the host-built tables: same samples (the
+    rotation blocks' cos/sin come from the device's sincos instead of numpy's: <= a few ulp of a term)."""
+    from waveforms_b200.engine import WFM_F32, WFM_F64, Program
+    code = WFM_F64 if dtype == np.float64 else WFM_F32
+    fns = drag_fns(ns, 0) + drag_fns(ns, 1)[:3] + [lambda t0: -0.25 * ns.square(60e-9, edge=2e-9) >> t0]
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(31)
+    n_ch, depth = 24, 150
+    idx = rng.integers(0, len(fns), (n_ch, depth))
+    t0 = np.tile(100e-9 + 70e-9 * np.arange(depth), (n_ch, 1)) + rng.uniform(0, 5e-9, (n_ch, depth))
+    stop = 100e-9 + 70e-9 * depth + 500e-9
+    full = pulse_train_batch(templates, idx, t0, 0, stop, 2e9)
+    cb = pulse_train_batch(templates, idx, t0, 0, stop, 2e9, compact=True)
+    a = Program(full).sample_device(dtype=code).cpu().numpy()
+    b = Program(cb).sample_device(dtype=code).cpu().numpy()
+    tol = 4e-15 if dtype == np.float64 else 1.2e-7
+    assert np.max(np.abs(a.astype(np.float64) - b)) <= tol * np.max(np.abs(a))
+    # per-pulse parameters through the same path
+    fns2 = [lambda t0, amp, phase: ns.mixing(amp * ns.cosPulse(20e-9) >> t0, freq=-60e6, phase=phase, DRAGScaling=4e-10)[0]]
+    tp2 = [PulseTemplate.trace(f, params=('t0', 'amp', 'phase')) for f in fns2]
+    params = {'amp': rng.uniform(-1, 1, (n_ch, depth)), 'phase': rng.uniform(0, 6, (n_ch, depth))}
+    z = np.zeros((n_ch, depth), np.int64)
+    a = Program(pulse_train_batch(tp2, z, t0, 0, stop, 2e9, params=params)).sample_device(dtype=code).cpu().numpy()
+    b = Program(pulse_train_batch(tp2, z, t0, 0, stop, 2e9, params=params, compact=True)).sample_device(dtype=code).cpu().numpy()
+    assert np.max(np.abs(a.astype(np.float64) - b)) <= tol * np.max(np.abs(a))

@@ -192,6 +192,7 @@ def config_lines(ns, torch, engine, peak, fp64, quick=False):
     t_b = time.perf_counter()
     fns = [fn(f8, a, p) for f8 in range(8) for a in range(2) for p in range(4)]
     templates = [PulseTemplate.trace(f) for f in fns]
+    trace_s = time.perf_counter() - t_b
     rng = np.random.default_rng(20260003)
     depth = 1000
     gate = rng.integers(0, 8, (n_ch, depth))
@@ -216,6 +217,31 @@ def config_lines(ns, torch, engine, peak, fp64, quick=False):
     line['cpu_baseline'] = {'value': int(batch.chan_n[0]) / per / 1e9, 'unit': 'GSa/s', 'cores': 1, 'kind': kind,
                             'sample': 'one depth-1000 I channel (42 000 samples), %d passes' % n}
     prog.close()
+    # the same batch as templates + per-pulse payloads, the rows written on the device (wfm_expand_templates)
+    t_c = time.perf_counter()
+    cb = pulse_train_batch(templates, idx, t0s, 0, stop, 2e9, compact=True)
+    compact_build_s = time.perf_counter() - t_c
+
+    def create_s(b):
+        ts = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            p = engine.Program(b, torch.cuda.current_device())
+            ts.append(time.perf_counter() - t)
+            p.close()
+        return float(min(ts[1:]))
+    full_create, compact_create = create_s(batch), create_s(cb)
+    pc = engine.Program(cb, torch.cuda.current_device())
+    out_c = pc.sample_device(dtype=engine.WFM_F64)
+    diff = float((out_c - out).abs().max().item() / out.abs().max().item())
+    pc.close()
+    line['compact'] = {'host_build_s': trace_s + compact_build_s, 'trace_s': trace_s, 'upload_bytes': int(cb.nbytes()), 'full_table_bytes': int(batch.nbytes()),
+                       'create_s': compact_create, 'full_create_s': full_create, 'max_rel_diff_vs_full_tables': diff,
+                       'ok': bool(diff <= 4e-15),
+                       'what': 'pulse_train_batch(compact=True): templates once + per pulse (template id, 4 offsets, payload); '
+                               'create_s = upload + wfm_expand_templates + wfm_program_create, pageable host memory both ways'}
+    del out_c
     del out
     res['cfg3'] = line
 

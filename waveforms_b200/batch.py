@@ -199,14 +199,16 @@ def sample_wire(records, kinds=None, **kw):
 
 
 def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
-                        dtype=np.float64, devices=None, params=None):
+                        dtype=np.float64, devices=None, params=None, compact='auto'):
     """Channels given as PARAMETER ARRAYS instead of objects: channel ``c`` is the
     stack of pulses ``templates[tmpl_idx[c][k]]`` started at ``t0[c][k]``
     (``builder.PulseTemplate.trace`` / ``builder.pulse_train_batch``), sampled on
     ``np.arange(start, stop, 1/sample_rate)``; ``params = {name: array like t0}``
     carries the templates' further per-pulse parameters (amplitude, phase ...).
     Same sharding and result type as ``sample_batch``; the tables are those the
-    object API would have produced."""
+    object API would have produced.  ``compact``: upload templates + per-pulse payloads and write the per-pulse rows
+    on the device (``builder.CompactBatch``, ``wfm_expand_templates``) — 'auto' = whenever the channels allow it
+    (time-ordered, non-overlapping pulses), True = insist, False = build the full tables on the host."""
     import torch
     from .builder import pulse_train_batch
     engine.require_gpu()
@@ -220,9 +222,17 @@ def sample_pulse_trains(templates, tmpl_idx, t0, start, stop, sample_rate,
 
     def run(shard):
         dev, lo, hi = shard
-        batch = pulse_train_batch(templates, tmpl_idx[lo:hi], t0[lo:hi], start, stop,
-                                  sample_rate,
-                                  params={k: v[lo:hi] for k, v in (params or {}).items()})
+        args = (templates, tmpl_idx[lo:hi], t0[lo:hi], start, stop, sample_rate)
+        kw = dict(params={k: v[lo:hi] for k, v in (params or {}).items()})
+        if compact == 'auto':
+            try:
+                batch = pulse_train_batch(*args, compact=True, **kw)
+            except ValueError as e:
+                if 'compact' not in str(e):
+                    raise
+                batch = pulse_train_batch(*args, **kw)
+        else:
+            batch = pulse_train_batch(*args, compact=bool(compact), **kw)
         with torch.cuda.device(dev):
             prog = engine.Program(batch, dev)
             out = prog.sample_device(dtype=code)

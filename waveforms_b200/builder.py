@@ -113,6 +113,30 @@ SymTime = Sym  # the start time was the first traced parameter
 _round_ufuncs = {}
 
 
+def _round_decimal(v, nd):
+    """Python's ``round(float, nd)`` over an array.  round() returns the double nearest to the decimal that is the
+    exact binary value rounded to ``nd`` places; for 0 <= nd <= 22 that is ``k / 10**nd`` with ``k`` the integer
+    nearest to ``v * 10**nd`` (10**nd and k exact in binary64, one correctly rounded division) — unless the product
+    is so close to a tie, or so large, that its own rounding could change ``k``: those elements (none in practice)
+    go through round() itself."""
+    v = np.asarray(v, dtype=np.float64)
+    uf = _round_ufuncs.get(nd)
+    if uf is None:
+        uf = _round_ufuncs[nd] = np.frompyfunc(lambda x, nd=nd: round(x, nd), 1, 1)
+    if not 0 <= nd <= 22 or v.ndim == 0:
+        return uf(v).astype(np.float64)
+    s = 10.0 ** nd
+    with np.errstate(invalid='ignore', over='ignore'):
+        y = v * s
+        k = np.rint(y)
+        safe = (np.abs(y - k) < 0.5 - np.abs(y) * 2.0 ** -50) & (np.abs(y) < 2.0 ** 51)
+        out = k / s
+    if not safe.all():
+        bad = ~safe
+        out[bad] = uf(v[bad]).astype(np.float64)
+    return out
+
+
 def _eval(expr, env):
     """Replay a recorded expression over float64 arrays ``env[name]`` (element-wise IEEE
     operations: identical to the Python float arithmetic of the trace)."""
@@ -124,11 +148,7 @@ def _eval(expr, env):
     if op == 'neg':
         return -_eval(expr[1], env)
     if op == 'round':
-        nd = expr[2]
-        uf = _round_ufuncs.get(nd)
-        if uf is None:  # Python's correctly rounded decimal round(), not np.round's scaling
-            uf = _round_ufuncs[nd] = np.frompyfunc(lambda v, nd=nd: round(v, nd), 1, 1)
-        return uf(np.asarray(_eval(expr[1], env), dtype=np.float64)).astype(np.float64)
+        return _round_decimal(_eval(expr[1], env), expr[2])  # Python's correctly rounded decimal round()
     a, b = _eval(expr[1], env), _eval(expr[2], env)
     if op == 'add':
         return a + b
@@ -342,6 +362,41 @@ class PulseTemplate:
             args[:, off + 4] = _sin_uf(delta).astype(np.float64)
         return bounds, facs, args, amps
 
+    # -- compact form: what wfm_expand_templates needs (include/wfm_b200.h, csrc/wfm_expand.cu) ------------------
+    PATCH_SHIFT, PATCH_A0, PATCH_A1, PATCH_ARG, PATCH_AMP, PATCH_VALUE = range(6)
+
+    def compact_spec(self):
+        """(patches, rots, max_rows): ``patches[j] = (kind, index, expr)`` — payload slot j of a pulse of this
+        template; ``rots[k] = (fac_row, arg_off, w, s_b, w_slot, sb_slot)``; ``max_rows`` = most value rows
+        (factor rows that are not placeholders) of any of its segments."""
+        if getattr(self, '_compact', None) is not None:
+            return self._compact
+        patches = [(self.PATCH_SHIFT, r, e) for r, e in self.sym_shift]
+        patches += [(self.PATCH_A0 if f == 'a0' else self.PATCH_A1, r, e) for r, f, e in self.sym_arg]
+        patches += [(self.PATCH_ARG, i, e) for i, e in self.sym_pool]
+        patches += [(self.PATCH_AMP, r, e) for r, e in self.sym_amp]
+        rots = []
+        for r, off, w_expr, base_expr in self.rot_rows:
+            slots = []
+            for e in (w_expr, base_expr):
+                if e[0] == 'const':
+                    slots.append((float(e[1]), -1))
+                else:
+                    slots.append((0.0, len(patches)))
+                    patches.append((self.PATCH_VALUE, 0, e))
+            rots.append((int(r), int(off), slots[0][0], slots[1][0], slots[0][1], slots[1][1]))
+        edges = list(self.seg_fac) + [len(self.facs)]
+        nop = 33
+        max_rows = max([int((self.facs['func'][a:b] != nop).sum()) for a, b in zip(edges[:-1], edges[1:])] or [0])
+        self._compact = (patches, rots, max_rows)
+        return self._compact
+
+    def eval_bounds(self, env, P):
+        bounds = np.empty((P, self.n_seg), dtype=np.float64)
+        for j, e in enumerate(self.bound_expr):
+            bounds[:, j] = _eval(e, env)
+        return bounds
+
     def materialize(self, **point):
         """(bounds, seq) — or (bounds, seq_I, seq_Q) of a pair template — of ONE pulse as plain tuples, exactly what
         the object API builds for these parameter values (no algebra is run: the traced values are substituted)."""
@@ -375,8 +430,68 @@ class PulseTemplate:
                                    'changes with the parameter value')
 
 
+class CompactBatch:
+    """A pulse-train batch whose per-pulse factor / term / reference / argument rows are NOT materialised on the
+    host: the templates' tables once, per pulse its template, four destination offsets and a short payload (one
+    double per traced entry).  ``engine.Program`` uploads this and lets ``wfm_expand_templates`` write the rows on
+    the device.  Same channel bookkeeping as ``LoweredBatch``."""
+
+    def __init__(self, waves, seg_bound, seg_ptr, templates, specs, pulse_tmpl, pulse_fac, pulse_term, pulse_ref,
+                 pulse_arg, payload, sizes, total_samples):
+        self.waves, self.seg_bound, self.seg_ptr = waves, seg_bound, seg_ptr
+        self.x = np.zeros(0, np.float64)
+        self.pulse_tmpl, self.pulse_fac, self.pulse_term = pulse_tmpl, pulse_fac, pulse_term
+        self.pulse_ref, self.pulse_arg, self.payload = pulse_ref, pulse_arg, np.ascontiguousarray(payload)
+        self.n_facs, self.n_terms, self.n_refs, self.n_args = sizes
+        self.total_samples, self.any_complex = total_samples, False
+        pair = (waves['flags'] & WAVE_PAIR) != 0
+        off = np.stack([waves['out_off'], waves['out_off2']], 1)
+        keep = np.stack([np.ones(len(pair), bool), pair], 1)
+        self.chan_off = off[keep]
+        self.chan_n = np.repeat(waves['n'], 1 + pair.astype(np.int64))
+        # the templates' tables back to back + their descriptors
+        TD = np.dtype([(k, '<i4') for k in ('fac0', 'n_fac', 'term0', 'n_term', 'ref0', 'n_ref', 'arg0', 'n_arg', 'patch0',
+                                            'n_patch', 'rot0', 'n_rot')])
+        PD = np.dtype([('kind', '<i4'), ('index', '<i4')])
+        RD = np.dtype([('fac_row', '<i4'), ('arg_off', '<i4'), ('w', '<f8'), ('s_b', '<f8'), ('w_slot', '<i4'), ('sb_slot', '<i4')])
+        desc = np.zeros(len(templates), dtype=TD)
+        facs, terms, refs, args, has, patches, rots = [], [], [], [], [], [], []
+        f0 = t0 = r0 = a0 = p0 = q0 = 0
+        self.max_rows = 0
+        for m, (tp, (pt, rt, mr)) in enumerate(zip(templates, specs)):
+            desc[m] = (f0, len(tp.facs), t0, len(tp.terms), r0, len(tp.refs), a0, len(tp.args), p0, len(pt), q0, len(rt))
+            facs.append(tp.facs); terms.append(tp.terms); refs.append(tp.refs); args.append(tp.args)
+            has.append(tp.has_args.astype(np.uint8))
+            patches.append(np.array([(k, i) for k, i, _ in pt], dtype=PD) if pt else np.zeros(0, PD))
+            rots.append(np.array(rt, dtype=RD) if rt else np.zeros(0, RD))
+            f0 += len(tp.facs); t0 += len(tp.terms); r0 += len(tp.refs); a0 += len(tp.args); p0 += len(pt); q0 += len(rt)
+            self.max_rows = max(self.max_rows, mr)
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+        self.t_desc, self.t_facs, self.t_terms = desc, cat(facs, FACTOR_DT), cat(terms, TERM_DT)
+        self.t_refs, self.t_args, self.t_has_args = cat(refs, REF_DT), cat(args, np.float64), cat(has, np.uint8)
+        self.t_patches, self.t_rots = cat(patches, PD), cat(rots, RD)
+
+    @property
+    def n_channels(self):
+        return len(self.chan_off)
+
+    _UPLOADS = ('waves', 'seg_bound', 'seg_ptr', 't_desc', 't_facs', 't_terms', 't_refs', 't_args', 't_has_args', 't_patches',
+                't_rots', 'pulse_tmpl', 'pulse_fac', 'pulse_term', 'pulse_ref', 'pulse_arg', 'payload')
+
+    def nbytes(self):
+        """bytes that cross the bus (the full tables would be ``expanded_nbytes()``)"""
+        return int(sum(getattr(self, k).nbytes for k in self._UPLOADS))
+
+    def expanded_nbytes(self):
+        return int(self.n_facs * FACTOR_DT.itemsize + self.n_terms * TERM_DT.itemsize + self.n_refs * REF_DT.itemsize +
+                   self.n_args * 8 + self.waves.nbytes + self.seg_bound.nbytes + self.seg_ptr.nbytes)
+
+    def pin(self):
+        return self
+
+
 def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=None,
-                      spot_check=4) -> LoweredBatch:
+                      spot_check=4, compact=False) -> LoweredBatch:
     """One channel per row: channel ``c`` is the stack of pulses ``templates[tmpl_idx[c][k]]`` started at
     ``t0[c][k]``.  Channels whose pulses are time-ordered and do not overlap — gate sequences — are assembled
     by NumPy scatter (``_pulse_train_disjoint``); a channel with OVERLAPPING (or unordered) pulses — flux
@@ -384,11 +499,15 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=
     segment (``lowering._merge_members`` / ``_plan_slots``, what the reference's ``WaveVStack.__call__`` does by
     accumulation, waveform.py:679-693): its pulses are MATERIALISED from the templates (the traced values
     substituted, no algebra) and lowered by ``lower()`` itself, so the tables are the object API's by
-    construction.  The two kinds are merged into one batch in channel order."""
+    construction.  The two kinds are merged into one batch in channel order.
+
+    ``compact=True`` (all channels disjoint): a ``CompactBatch`` — the templates' tables once plus a few
+    doubles per pulse; the per-pulse rows are written on the device (``wfm_expand_templates``), so the host
+    neither builds nor uploads them."""
     n_ch = len(t0)
     params = params or {}
     if n_ch == 0 or not templates:
-        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check)
+        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check, compact)
     # first / last edge of every pulse: the templates' outer bounds over the parameter arrays
     general = []
     for c in range(n_ch):
@@ -412,7 +531,10 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=
         if np.any(first[1:] < last[:-1]):
             general.append(c)
     if not general:
-        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check)
+        return _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params, spot_check, compact)
+    if compact:
+        raise ValueError('compact=True needs channels of time-ordered, non-overlapping pulses '
+                         f'(channel {general[0]} overlaps)')
     from .lowering import Channel, lower, merge_batches
     gset = set(general)
     plain = [c for c in range(n_ch) if c not in gset]
@@ -441,7 +563,7 @@ def pulse_train_batch(templates, tmpl_idx, t0, start, stop, sample_rate, params=
 
 
 def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, params=None,
-                          spot_check=4) -> LoweredBatch:
+                          spot_check=4, compact=False) -> LoweredBatch:
     """Channels of time-ordered, NON-overlapping pulses, sampled on
     ``np.arange(start, stop, 1/sample_rate)`` — the ``LoweredBatch`` that
     ``lower([channel_grid(WaveVStack([fn(t, ...) for ...]))])`` yields, built with NumPy.
@@ -487,10 +609,16 @@ def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, par
     seg_term = np.empty(n_seg_full + 1, dtype=np.int64)
     first_edge = np.empty(P, dtype=np.float64)
     last_edge = np.empty(P, dtype=np.float64)
-    facs = np.zeros(int(fac_off[-1]), dtype=FACTOR_DT)
-    terms = np.zeros(int(term_off[-1]), dtype=TERM_DT)
-    refs = np.zeros(int(ref_off[-1]), dtype=REF_DT)
-    args = np.zeros(int(arg_off[-1]), dtype=np.float64)
+    if compact:
+        specs = [tp.compact_spec() for tp in templates]
+        stride = max([len(sp[0]) for sp in specs] + [1])
+        payload = np.zeros((P, stride), dtype=np.float64)
+        facs = terms = refs = args = None
+    else:
+        facs = np.zeros(int(fac_off[-1]), dtype=FACTOR_DT)
+        terms = np.zeros(int(term_off[-1]), dtype=TERM_DT)
+        refs = np.zeros(int(ref_off[-1]), dtype=REF_DT)
+        args = np.zeros(int(arg_off[-1]), dtype=np.float64)
     for m, tp in enumerate(templates):
         idx = np.nonzero(M == m)[0]
         if not len(idx):
@@ -499,7 +627,14 @@ def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, par
         if missing:
             raise ValueError(f'template {m} needs the parameter array(s) {missing}')
         more = {n: flat[n][idx] for n in tp.params if n != 't0'}
-        b, f, a, amps = tp.instantiate(T[idx], **more)
+        if compact:
+            # bounds and the per-pulse payload only: one double per patch of the template
+            env = {'t0': T[idx], **more}
+            b = tp.eval_bounds(env, len(idx))
+            for j, (_, _, e) in enumerate(specs[m][0]):
+                payload[idx, j] = _eval(e, env)
+        else:
+            b, f, a, amps = tp.instantiate(T[idx], **more)
         for j in (np.random.default_rng(m).choice(len(idx), min(spot_check, len(idx)), replace=False) if spot_check else ()):
             tp._verify({'t0': float(T[idx[j]]), **{n: float(v[j]) for n, v in more.items()}})
         first_edge[idx], last_edge[idx] = b[:, 0], b[:, -1]
@@ -507,6 +642,8 @@ def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, par
         seg_bound[sp] = b
         seg_fac[sp] = fac_off[idx][:, None] + tp.seg_fac[None, :]
         seg_term[sp] = term_off[idx][:, None] + tp.seg_term[None, :]
+        if compact:
+            continue
         if len(tp.facs):
             f['arg_off'] += (arg_off[idx][:, None] * tp.has_args[None, :]).astype(np.int32)
             facs[fac_off[idx][:, None] + np.arange(len(tp.facs))[None, :]] = f
@@ -560,6 +697,15 @@ def _pulse_train_disjoint(templates, tmpl_idx, t0, start, stop, sample_rate, par
     if P:
         np.logical_or.at(ch_cplx, ch_of, cplx_t[M])
     waves['flags'] = np.where(ch_cplx, WAVE_COMPLEX, 0) | (WAVE_PAIR if pair else 0)
+    if compact:
+        if ch_cplx.any():
+            raise ValueError('compact=True: complex amplitudes need the full tables')
+        return CompactBatch(waves=waves, seg_bound=seg_bound, seg_ptr=seg_ptr, templates=list(templates), specs=specs,
+                            pulse_tmpl=M.astype(np.int32), pulse_fac=fac_off[:-1].astype(np.int32),
+                            pulse_term=term_off[:-1].astype(np.int32), pulse_ref=ref_off[:-1].astype(np.int32),
+                            pulse_arg=arg_off[:-1].astype(np.int32), payload=payload,
+                            sizes=(int(fac_off[-1]), int(term_off[-1]), int(ref_off[-1]), int(arg_off[-1])),
+                            total_samples=int(n_ch * rows * pitch))
     return LoweredBatch(waves=waves, seg_bound=seg_bound, seg_ptr=seg_ptr, facs=facs, terms=terms,
                         refs=refs, args=args, x=np.zeros(0, np.float64),
                         total_samples=int(n_ch * rows * pitch), any_complex=bool(ch_cplx.any()))

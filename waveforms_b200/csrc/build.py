@@ -11,7 +11,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / 'libwfmb200.so'
-SOURCES = ['wfm_api.cu', 'wfm_sample.cu', 'wfm_iir.cu', 'wfm_fft.cu', 'wfm_calib.cu']
+SOURCES = ['wfm_api.cu', 'wfm_sample.cu', 'wfm_iir.cu', 'wfm_fft.cu', 'wfm_calib.cu', 'wfm_expand.cu']
 HEADERS = ['wfm_internal.h', 'wfm_basis.cuh', 'wfm_math.cuh', 'wfm_multidrag.cuh', 'wfm_erf_table.h',
            '../../include/wfm_b200.h']
 NVCC_FLAGS = [

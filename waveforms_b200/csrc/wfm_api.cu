@@ -234,6 +234,7 @@ static int parallel_ranges(int64_t n, F fn) {
 
 static int validate(const WfmProgramDesc* d, int* max_rows_out) {
   if (!d) return fail(WFM_EINVAL, "null program descriptor");
+  const bool dev_tables = (d->flags & WFM_DESC_DEVICE_TABLES) != 0;
   if (d->n_waves < 0 || d->n_segs < 0 || d->n_facs < 0 || d->n_terms < 0 || d->n_refs < 0 || d->n_args < 0 || d->n_x < 0)
     return fail(WFM_EINVAL, "negative table size");
   if (d->n_segs > INT32_MAX - 1 || d->n_facs > INT32_MAX || d->n_terms > INT32_MAX || d->n_refs > INT32_MAX ||
@@ -248,7 +249,9 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
       return fail(WFM_EINVAL, "segment pointer table does not close (%d/%lld factors, %d/%lld terms)", e.fac,
                   (long long)d->n_facs, e.term, (long long)d->n_terms);
   }
-  int rc = parallel_ranges(d->n_facs, [&](int64_t lo, int64_t hi) {
+  // device-resident tables (wfm_expand_templates wrote them from validated templates): only the host-side tables
+  // — channels, segment bounds and pointers — are checked here
+  int rc = parallel_ranges(dev_tables ? 0 : d->n_facs, [&](int64_t lo, int64_t hi) {
     for (int64_t k = lo; k < hi; ++k) {
       const WfmFactor& f = d->facs[k];
       if (!known_func(f.func)) return fail(WFM_EUNSUPPORTED, "factor %lld: unknown basis id %d", (long long)k, f.func);
@@ -319,6 +322,7 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
       if (a.fac < 0 || a.term < 0 || b.fac < a.fac || b.term < a.term || b.fac > d->n_facs || b.term > d->n_terms)
         return fail(WFM_EINVAL, "segment %lld: pointer table not monotone", (long long)s);
       const int nf = b.fac - a.fac;
+      if (dev_tables) continue;
       int n_values = 0;  // value slots the segment needs: every row but the sine placeholders
       for (int k = 0; k < nf; ++k) {
         const WfmFactor& f = d->facs[a.fac + k];
@@ -368,7 +372,8 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
     return 0;
   });
   if (rc != WFM_OK) return rc;
-  *max_rows_out = max_rows.load();
+  *max_rows_out = dev_tables ? d->max_rows : max_rows.load();
+  if (dev_tables && (d->max_rows < 0 || d->max_rows > 4096)) return fail(WFM_EINVAL, "max_rows out of range");
   for (int64_t w = 0; w < d->n_waves; ++w) {
     const WfmWave& wv = d->waves[w];
     if (wv.n < 0 || wv.out_off < 0) return fail(WFM_EINVAL, "channel %lld: negative extent", (long long)w);
@@ -380,6 +385,8 @@ static int validate(const WfmProgramDesc* d, int* max_rows_out) {
     if ((wv.flags & WFM_WAVE_EXPLICIT_X) && (wv.x_off < 0 || wv.x_off + wv.n > d->n_x))
       return fail(WFM_EINVAL, "channel %lld: explicit abscissae out of range", (long long)w);
     if (wv.out_off % 4) return fail(WFM_EINVAL, "channel %lld: out_off must be a multiple of 4 (16-byte stores)", (long long)w);
+    if (dev_tables && (wv.flags & WFM_WAVE_COMPLEX))
+      return fail(WFM_EUNSUPPORTED, "channel %lld: complex amplitudes need host tables (the planar twin is built from them)", (long long)w);
     if (wv.flags & WFM_WAVE_PAIR) {
       if (wv.out_off2 < 0 || wv.out_off2 % 4) return fail(WFM_EINVAL, "channel %lld: out_off2 must be a non-negative multiple of 4", (long long)w);
       if (wv.flags & (WFM_WAVE_CLIP | WFM_WAVE_COMPLEX))
@@ -483,10 +490,21 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   up(o_waves, d->waves, sizeof(WfmWave) * d->n_waves);
   up(o_bound, d->seg_bound, sizeof(double) * d->n_segs);
   up(o_segptr, d->seg_ptr, d->n_segs ? sizeof(WfmSegPtr) * (d->n_segs + 1) : 0);
-  up(o_facs, d->facs, sizeof(WfmFactor) * d->n_facs);
-  up(o_terms, d->terms, sizeof(WfmTerm) * d->n_terms);
-  up(o_refs, d->refs, sizeof(WfmRef) * d->n_refs);
-  up(o_args, d->args, sizeof(double) * d->n_args);
+  if (d->flags & WFM_DESC_DEVICE_TABLES) {
+    // written on this device by wfm_expand_templates, on a stream the caller has ordered before this call
+    auto dd = [&](size_t off, const void* src, size_t bytes) {
+      if (e == cudaSuccess && bytes > 0) e = cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyDeviceToDevice, ST);
+    };
+    dd(o_facs, d->facs, sizeof(WfmFactor) * d->n_facs);
+    dd(o_terms, d->terms, sizeof(WfmTerm) * d->n_terms);
+    dd(o_refs, d->refs, sizeof(WfmRef) * d->n_refs);
+    dd(o_args, d->args, sizeof(double) * d->n_args);
+  } else {
+    up(o_facs, d->facs, sizeof(WfmFactor) * d->n_facs);
+    up(o_terms, d->terms, sizeof(WfmTerm) * d->n_terms);
+    up(o_refs, d->refs, sizeof(WfmRef) * d->n_refs);
+    up(o_args, d->args, sizeof(double) * d->n_args);
+  }
   up(o_x, d->x, sizeof(double) * d->n_x);
   p->dev.waves = (const WfmWave*)(base + o_waves);
   p->dev.seg_bound = (const double*)(base + o_bound);

@@ -43,7 +43,20 @@ class _ProgramDesc(C.Structure):
                 ('facs', C.c_void_p), ('n_terms', C.c_int64),
                 ('terms', C.c_void_p), ('n_refs', C.c_int64),
                 ('refs', C.c_void_p), ('n_args', C.c_int64),
-                ('args', C.c_void_p), ('n_x', C.c_int64), ('x', C.c_void_p)]
+                ('args', C.c_void_p), ('n_x', C.c_int64), ('x', C.c_void_p),
+                ('flags', C.c_uint32), ('max_rows', C.c_int32)]
+
+
+class _ExpandDesc(C.Structure):
+    _fields_ = [('n_templates', C.c_int64), ('templates', C.c_void_p), ('t_facs', C.c_void_p),
+                ('t_terms', C.c_void_p), ('t_refs', C.c_void_p), ('t_args', C.c_void_p),
+                ('t_has_args', C.c_void_p), ('patches', C.c_void_p), ('rots', C.c_void_p),
+                ('n_pulses', C.c_int64), ('pulse_tmpl', C.c_void_p), ('pulse_fac', C.c_void_p),
+                ('pulse_term', C.c_void_p), ('pulse_ref', C.c_void_p), ('pulse_arg', C.c_void_p),
+                ('payload_stride', C.c_int32), ('reserved', C.c_int32), ('payload', C.c_void_p)]
+
+
+WFM_DESC_DEVICE_TABLES = 1
 
 
 class _Launch(C.Structure):
@@ -59,7 +72,7 @@ EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_program_info', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
-    'wfm_lfilter', 'wfm_fft_filter', 'wfm_fft_response_create', 'wfm_fft_response_destroy',
+    'wfm_lfilter', 'wfm_expand_templates', 'wfm_fft_filter', 'wfm_fft_response_create', 'wfm_fft_response_destroy',
     'wfm_fft_filter_prepared', 'wfm_reflection_filter', 'wfm_fft_c2c', 'wfm_calibrate_fp64', 'wfm_calibrate_copy'
 ]
 
@@ -104,6 +117,8 @@ def load_library():
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
             C.c_void_p, C.c_void_p
         ]
+        lib.wfm_expand_templates.argtypes = [C.POINTER(_ExpandDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
         lib.wfm_fft_response_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
         lib.wfm_fft_response_destroy.argtypes = [C.c_void_p]
         lib.wfm_fft_filter_prepared.argtypes = [
@@ -224,11 +239,38 @@ class Program:
         d.n_waves, d.waves = len(batch.waves), ptr(batch.waves)
         d.n_segs, d.seg_bound = len(batch.seg_bound), ptr(batch.seg_bound)
         d.seg_ptr = ptr(batch.seg_ptr)
-        d.n_facs, d.facs = len(batch.facs), ptr(batch.facs)
-        d.n_terms, d.terms = len(batch.terms), ptr(batch.terms)
-        d.n_refs, d.refs = len(batch.refs), ptr(batch.refs)
-        d.n_args, d.args = len(batch.args), ptr(batch.args)
         d.n_x, d.x = len(batch.x), ptr(batch.x)
+        if hasattr(batch, 'pulse_tmpl'):
+            # a builder.CompactBatch: templates + per-pulse payload go up, the per-pulse rows are written on the device
+            dev = f'cuda:{self.device}'
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+            tabs = {k: up(getattr(batch, k)) for k in ('t_desc', 't_facs', 't_terms', 't_refs', 't_args', 't_has_args',
+                                                       't_patches', 't_rots', 'pulse_tmpl', 'pulse_fac', 'pulse_term',
+                                                       'pulse_ref', 'pulse_arg', 'payload')}
+            dp = lambda k: tabs[k].data_ptr() if tabs[k].numel() else None
+            out = {k: torch.empty(max(n * sz, 16), dtype=torch.uint8, device=dev)
+                   for k, n, sz in (('facs', batch.n_facs, FACTOR_DT.itemsize), ('terms', batch.n_terms, TERM_DT.itemsize),
+                                    ('refs', batch.n_refs, REF_DT.itemsize), ('args', batch.n_args, 8))}
+            x = _ExpandDesc(len(batch.t_desc), dp('t_desc'), dp('t_facs'), dp('t_terms'), dp('t_refs'), dp('t_args'),
+                            dp('t_has_args'), dp('t_patches'), dp('t_rots'), len(batch.pulse_tmpl), dp('pulse_tmpl'),
+                            dp('pulse_fac'), dp('pulse_term'), dp('pulse_ref'), dp('pulse_arg'),
+                            int(batch.payload.shape[1]), 0, dp('payload'))
+            with torch.cuda.device(self.device):
+                st = torch.cuda.current_stream(self.device)
+                _check(lib.wfm_expand_templates(C.byref(x), out['facs'].data_ptr(), out['terms'].data_ptr(),
+                                                out['refs'].data_ptr(), out['args'].data_ptr(), C.c_void_p(st.cuda_stream)))
+                st.synchronize()  # wfm_program_create copies the tables on its own stream
+            keep.append((tabs, out))
+            d.n_facs, d.facs = batch.n_facs, out['facs'].data_ptr()
+            d.n_terms, d.terms = batch.n_terms, out['terms'].data_ptr()
+            d.n_refs, d.refs = batch.n_refs, out['refs'].data_ptr()
+            d.n_args, d.args = batch.n_args, out['args'].data_ptr()
+            d.flags, d.max_rows = WFM_DESC_DEVICE_TABLES, int(batch.max_rows)
+        else:
+            d.n_facs, d.facs = len(batch.facs), ptr(batch.facs)
+            d.n_terms, d.terms = len(batch.terms), ptr(batch.terms)
+            d.n_refs, d.refs = len(batch.refs), ptr(batch.refs)
+            d.n_args, d.args = len(batch.args), ptr(batch.args)
         h = C.c_void_p()
         _check(lib.wfm_program_create(C.byref(d), self.device, C.byref(h)))
         self._h = h
