@@ -47,8 +47,9 @@ def build(force=False, verbose=False, defines=(), out=None):
     lib = LIB if out is None else Path(out)
     if out is None and not force and not stale():
         return LIB
-    objs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = HERE / (Path(src).stem + ('' if out is None else '.' + lib.stem) + '.o')
         cmd = [nvcc_path(), *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []),
                *[f'-D{d}' for d in defines], '-c', str(HERE / src), '-o', str(obj)]
@@ -57,7 +58,11 @@ def build(force=False, verbose=False, defines=(), out=None):
             cmd.insert(2, '-v')
             print(' '.join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
-        objs.append(str(obj))
+        return str(obj)
+
+    # the translation units are independent: one nvcc per source, side by side
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     cmd = [nvcc_path(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
            '-o', str(lib), *objs]
     subprocess.run(cmd, check=True)

@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -68,6 +70,7 @@ struct FftPlan {
   int n_stage;
   int radix[kMaxStages];
   uint32_t inv_ns[kMaxStages];  // ceil(2^32 / Ns) of every stage: j / Ns = umulhi(j, inv) for j < 2^16
+  int tstep[kMaxStages];        // L / (Ns * R) of every stage: the stride of its twiddles in the table
   const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)  (global memory)
   int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers
 };
@@ -257,10 +260,9 @@ __device__ __forceinline__ void load_twiddles(double2 (&w)[R], const double2* __
 }
 
 template <int R, class In, class Out>
-__device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, int Ns, uint32_t inv_ns,
+__device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, int Ns, uint32_t inv_ns, int tstep,
                                                const double2* __restrict__ tw, double sgn) {
-  const int nb = L / R;        // butterflies per transform
-  const int tstep = nb / Ns;   // L / (Ns*R): table stride of this stage
+  const int nb = L / R;        // butterflies per transform; tstep = L / (Ns*R): table stride of this stage (from the plan)
   const int cmask = (1 << logc) - 1;
   const int total = nb << logc;
   for (int jj = threadIdx.x; jj < total; jj += blockDim.x) {
@@ -286,26 +288,26 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
 }
 
 template <class In, class Out>
-__device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc, int Ns, uint32_t inv,
+__device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc, int Ns, uint32_t inv, int tstep,
                                           const double2* __restrict__ tw, double sgn) {
   switch (R) {
-    case 2: stockham_stage<2>(in, out, L, logc, Ns, inv, tw, sgn); break;
-    case 3: stockham_stage<3>(in, out, L, logc, Ns, inv, tw, sgn); break;
-    case 4: stockham_stage<4>(in, out, L, logc, Ns, inv, tw, sgn); break;
-    case 5: stockham_stage<5>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 2: stockham_stage<2>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 3: stockham_stage<3>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 4: stockham_stage<4>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 5: stockham_stage<5>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
 #if WFM_FFT_MAX_RADIX >= 8
-    case 8: stockham_stage<8>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 8: stockham_stage<8>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
 #endif
 #if WFM_FFT_MAX_RADIX >= 16
-    case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
 #endif
 #if WFM_FFT_BIG_RADIX
-    case 10: stockham_stage<10>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 10: stockham_stage<10>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
 #endif
 #if WFM_FFT_BIG_RADIX >= 2
-    case 25: stockham_stage<25>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    case 25: stockham_stage<25>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
 #endif
-    default: stockham_stage<7>(in, out, L, logc, Ns, inv, tw, sgn); break;
+    default: stockham_stage<7>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
   }
 }
 
@@ -314,8 +316,26 @@ __device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc
 // writes through `out` instead.  `in` may read buf1 (never buf0).  Ends with a block
 // barrier, so what `out` wrote to shared memory is visible.  All threads must call it.
 template <class In, class Out>
+__device__ __forceinline__ void smem_fft_rt(const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw, In in,
+                                            Out out, double2* buf0, double2* buf1);
+#ifndef WFM_FFT_CT_SGN
+#define WFM_FFT_CT_SGN 0  // 1: the direction is a compile-time constant inside the stages (two copies of the code)
+#endif
+template <class In, class Out>
 __device__ __forceinline__ void smem_fft(const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw, In in,
                                          Out out, double2* buf0, double2* buf1) {
+#if WFM_FFT_CT_SGN
+  if (sgn < 0.0)
+    smem_fft_rt(P, logc, -1.0, tw, in, out, buf0, buf1);
+  else
+    smem_fft_rt(P, logc, 1.0, tw, in, out, buf0, buf1);
+#else
+  smem_fft_rt(P, logc, sgn, tw, in, out, buf0, buf1);
+#endif
+}
+template <class In, class Out>
+__device__ __forceinline__ void smem_fft_rt(const FftPlan& P, int logc, double sgn, const double2* __restrict__ tw, In in,
+                                            Out out, double2* buf0, double2* buf1) {
   const int S = P.n_stage;
   if (S == 0) {  // L == 1: the transform is the identity
     for (int c = threadIdx.x; c < (1 << logc); c += blockDim.x) out(0, c, in(0, c));
@@ -323,21 +343,21 @@ __device__ __forceinline__ void smem_fft(const FftPlan& P, int logc, double sgn,
     return;
   }
   if (S == 1) {
-    stage_any(P.radix[0], in, out, P.L, logc, 1, P.inv_ns[0], tw, sgn);
+    stage_any(P.radix[0], in, out, P.L, logc, 1, P.inv_ns[0], P.tstep[0], tw, sgn);
     __syncthreads();
     return;
   }
-  stage_any(P.radix[0], in, SmemOut{buf0, logc}, P.L, logc, 1, P.inv_ns[0], tw, sgn);
+  stage_any(P.radix[0], in, SmemOut{buf0, logc}, P.L, logc, 1, P.inv_ns[0], P.tstep[0], tw, sgn);
   __syncthreads();
   int Ns = P.radix[0];
   double2 *src = buf0, *dst = buf1;
   for (int s = 1; s < S - 1; ++s) {
-    stage_any(P.radix[s], SmemIn{src, logc}, SmemOut{dst, logc}, P.L, logc, Ns, P.inv_ns[s], tw, sgn);
+    stage_any(P.radix[s], SmemIn{src, logc}, SmemOut{dst, logc}, P.L, logc, Ns, P.inv_ns[s], P.tstep[s], tw, sgn);
     __syncthreads();
     double2* t = src; src = dst; dst = t;
     Ns *= P.radix[s];
   }
-  stage_any(P.radix[S - 1], SmemIn{src, logc}, out, P.L, logc, Ns, P.inv_ns[S - 1], tw, sgn);
+  stage_any(P.radix[S - 1], SmemIn{src, logc}, out, P.L, logc, Ns, P.inv_ns[S - 1], P.tstep[S - 1], tw, sgn);
   __syncthreads();
 }
 // the buffer the last stage of smem_fft(.., buf0, buf1) may write through `out` (the one it
@@ -765,6 +785,7 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
   int64_t ns = 1;
   for (int s = 0; s < plan->n_stage; ++s) {
     plan->inv_ns[s] = (uint32_t)(((uint64_t(1) << 32) + ns - 1) / ns);  // exact quotient for j < 2^16
+    plan->tstep[s] = (int)(L / (ns * plan->radix[s]));
     ns *= plan->radix[s];
   }
   const size_t buffers = 2 * sizeof(double2) * padded_points((size_t)points);
@@ -1055,6 +1076,9 @@ static int run_filter(const double* x, double* y, int64_t n_sig, int64_t n, int6
     e = get_plan(N1, (int64_t)N1 << lc1, &P1, &smem1);
     if (e == cudaSuccess) e = get_plan(N2, (int64_t)N2 << lc2, &P2, &smem2);
     if (e == cudaSuccess) e = get_big_twiddle(n, &BT);
+    // (Measured and rejected: running the three passes group by group of signal pairs so that a group's scratch stays in
+    // the 126 MB L2 — 2.39 ms at 22 pairs per group .. 3.87 ms at 2 against 2.19 ms for one group: the passes are bound
+    // on the SM (L1TEX 63-76 %, issue 43-52 %), not by HBM, and smaller grids add tails.)
     if (e == cudaSuccess) e = cudaMallocAsync(&scratch, sizeof(double2) * (size_t)n * (size_t)n_pair, st);
     const int C1 = 1 << lc1, C2 = 1 << lc2;
     dim3 g1((unsigned)((N2 + C1 - 1) / C1), (unsigned)n_pair), g2((unsigned)((N1 + C2 - 1) / C2), (unsigned)n_pair);
