@@ -504,3 +504,30 @@ def test_compact_batch_on_the_gpu(ns, dtype):
     a = Program(pulse_train_batch(tp2, z, t0, 0, stop, 2e9, params=params)).sample_device(dtype=code).cpu().numpy()
     b = Program(pulse_train_batch(tp2, z, t0, 0, stop, 2e9, params=params, compact=True)).sample_device(dtype=code).cpu().numpy()
     assert np.max(np.abs(a.astype(np.float64) - b)) <= tol * np.max(np.abs(a))
+
+
+@pytest.mark.gpu
+def test_sample_pulse_trains_picks_the_compact_path_when_it_can(ns):
+    """compact='auto': gate-sequence channels go up compact, a batch with an overlapping channel falls back to the full
+    tables — same samples either way."""
+    from waveforms_b200.batch import sample_pulse_trains
+    fns = drag_fns(ns, 0)
+    templates = [PulseTemplate.trace(f) for f in fns]
+    rng = np.random.default_rng(41)
+    n_ch, depth = 6, 80
+    idx = rng.integers(0, len(fns), (n_ch, depth))
+    t0 = np.tile(100e-9 + 25e-9 * np.arange(depth), (n_ch, 1))
+    args = (templates, idx, t0, 0.0, 3e-6, 2e9)
+    a = sample_pulse_trains(*args, compact=False).numpy()
+    b = sample_pulse_trains(*args).numpy()
+    c = sample_pulse_trains(*args, compact=True).numpy()
+    for x, y, z in zip(a, b, c):
+        assert np.max(np.abs(x - y)) <= 4e-15 * np.max(np.abs(x)) and np.array_equal(y, z)
+    t1 = t0.copy()
+    t1[2, 5] = t1[2, 4] + 5e-9  # channel 2: pulses 4 and 5 overlap
+    a = sample_pulse_trains(templates, idx, t1, 0.0, 3e-6, 2e9, compact=False).numpy()
+    b = sample_pulse_trains(templates, idx, t1, 0.0, 3e-6, 2e9).numpy()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(ValueError, match='compact'):
+        sample_pulse_trains(templates, idx, t1, 0.0, 3e-6, 2e9, compact=True)

@@ -51,10 +51,13 @@ namespace wfm {
 #define WFM_FFT_THREADS 512
 #endif
 constexpr int kFftThreads = WFM_FFT_THREADS;
-// the row pass has the radix-10 stage: 320 threads x 2 CTAs leave it 102 registers (no spills) and match the 320
-// radix-8 / 256 radix-10 butterflies of a 640-point x 4 tile (measured 512 / 448 / 384 / 320: 2.27 / 2.21 / 2.20 / 2.19 ms)
+// the row pass has the radix-10 stage and reads contiguous rows, so its tile can be small: 2 rows per CTA, 160 threads
+// (the 160 radix-8 / 128 radix-10 butterflies of a 640-point x 2 tile), three CTAs per SM at up to 136 registers.  More,
+// smaller CTAs overlap the load / butterfly / store phases that block barriers serialise inside one CTA.  Measured on
+// cfg4 (fft_filter, ms): 4 rows x 320 threads x 2 CTAs 2.19 (512 / 448 / 384 threads: 2.27 / 2.21 / 2.20);
+// 2 rows x 160 x 3 CTAs 2.08; x 4 CTAs 2.13; x 2 CTAs 2.24; 2 rows x 128 x 3: 2.16; x 192 x 3: 2.12; 1 row x 96 x 6: 2.19
 #ifndef WFM_FFT_ROWS_THREADS
-#define WFM_FFT_ROWS_THREADS 320
+#define WFM_FFT_ROWS_THREADS 160
 #endif
 constexpr int kFftRowsThreads = WFM_FFT_ROWS_THREADS;
 #ifndef WFM_FFT_COLS_THREADS
@@ -560,10 +563,10 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
 // kFilter: FFT -> * Hp[k1*N2 + k2] -> IFFT, in place (spectrum stays transposed)
 // else   : FFT (sgn) and scatter to natural order out[k1 + N1*k2], scaled
 #ifndef WFM_FFT_ROWS_MINB
-#define WFM_FFT_ROWS_MINB 2
+#define WFM_FFT_ROWS_MINB 3
 #endif
 #ifndef WFM_FFT_ROWS_LOGC
-#define WFM_FFT_ROWS_LOGC 2
+#define WFM_FFT_ROWS_LOGC 1
 #endif
 struct RowsIn {
   WFM_NO_RUN_TWIDDLE
