@@ -377,3 +377,36 @@ def test_dynamic_deal_many_tiles_and_subranges(ns, monkeypatch):
     part = sample_batch(chans[5:19]).numpy()
     for a, b in zip(part, want[5:19]):
         assert np.array_equal(a, b)
+
+
+def test_fast_create_of_small_programs_falls_back_when_tiles_would_be_cold(ns, monkeypatch):
+    """Small programs are created on a fast path (arena staged and uploaded in one copy, tile size from the host
+    estimate, verified after the fact).  A program whose pulses crowd into a few tiles defeats the estimate: the fast
+    path must notice (statistics of the tile pass) and redo the measured sizing — same tile size and samples as the
+    slow path."""
+    from waveforms_b200 import engine
+    from waveforms_b200.batch import channel_grid
+    from waveforms_b200.lowering import lower
+    rng = np.random.default_rng(5)
+    w = ns.zero()
+    for k in range(120):  # 120 pulses inside the first 0.4 us of a 100 us channel
+        w = w + rng.uniform(0.1, 1) * (ns.gaussian(1.5e-9) >> (2e-9 + 3e-9 * k))
+    w.start, w.stop, w.sample_rate = 0.0, 100e-6, 4e9
+    even = ns.zero()
+    for k in range(40):   # the same kind of pulses spread evenly: the estimate holds, the fast path stays
+        even = even + rng.uniform(0.1, 1) * (ns.gaussian(1.5e-9) >> (1e-6 + 2.4e-6 * k))
+    even.start, even.stop, even.sample_rate = 0.0, 100e-6, 4e9
+    for wav in (w, even):
+        batch = lower([channel_grid(wav)])
+        res = {}
+        for mode in ('fast', 'slow'):
+            if mode == 'slow':
+                monkeypatch.setenv('WFM_NO_FAST_CREATE', '1')
+            else:
+                monkeypatch.delenv('WFM_NO_FAST_CREATE', raising=False)
+            prog = engine.Program(batch)
+            res[mode] = (prog.info(), prog.sample_host())
+            prog.close()
+        assert res['fast'][0]['tile_samples'] == res['slow'][0]['tile_samples']
+        assert np.array_equal(res['fast'][1], res['slow'][1])
+        assert rel_err(res['fast'][1], _oracle_sample(wav)) <= FP64_TOL

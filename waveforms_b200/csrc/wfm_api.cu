@@ -171,6 +171,20 @@ static cudaError_t read_words(void* dst_host, const void* src_dev, int n, cudaSt
   return e;
 }
 
+// Small programs (the README example: two channels, 20 000 samples) are bound by LATENCY: every cudaMemcpyAsync, memset
+// and host round trip of wfm_program_create costs microseconds.  Their arena is assembled in one pinned staging buffer
+// per host thread and goes up in ONE copy; the tile size comes from the host estimate and is verified after the fact.
+constexpr size_t kStageBytes = 256 << 10;
+static unsigned char* stage_buffer() {
+  static thread_local unsigned char* p = nullptr;
+  if (!p && cudaHostAlloc((void**)&p, kStageBytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+  }
+  return p;
+}
+static thread_local bool g_no_fast_create = false;  // set while a fast create is being redone the long way
+
 struct WfmProgram {
   int device = 0;
   wfm::DevProgram dev{};
@@ -483,9 +497,21 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                 arena_bytes, cudaGetErrorString(e));
   }
   char* base = (char*)p->arena.p;
+  const bool small_program = samples <= (int64_t)1 << 20;
+  const char* force_unit = std::getenv("WFM_K1_UNIT");
+  const bool unit_forced = force_unit && (force_unit[0] == '1' || force_unit[0] == '2' || force_unit[0] == '4');
+  // the fast path of small programs: the whole arena staged and sent in one copy, no sizing round trip
+  unsigned char* stg = (small_program && !g_no_fast_create && !(d->flags & WFM_DESC_DEVICE_TABLES) && !p->any_complex &&
+                        arena_bytes <= kStageBytes && d->n_waves > 0 && !std::getenv("WFM_NO_FAST_CREATE"))
+                           ? stage_buffer() : nullptr;
   auto up = [&](size_t off, const void* host, size_t bytes) {
+    if (bytes == 0) return;
+    if (stg) {
+      memcpy(stg + off, host, bytes);
+      return;
+    }
     // pinned host tables (cudaHostAlloc / torch pin_memory) copy at link speed; pageable ones are staged by the driver
-    if (e == cudaSuccess && bytes > 0) e = cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, ST);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, ST);
   };
   up(o_waves, d->waves, sizeof(WfmWave) * d->n_waves);
   up(o_bound, d->seg_bound, sizeof(double) * d->n_segs);
@@ -530,17 +556,52 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
                          nullptr, (const int64_t*)(base + o_prefix), nullptr};
   wfm::PrepareCounts pc{d->n_waves, d->n_segs, d->n_facs, d->n_terms, 0};
   p->dev.unit = 1;
+  uint32_t* d_stats = (uint32_t*)(base + o_stats);
+  auto cap_of = [&](int ts) {
+    const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots, p->dev.unit);
+    // (an I/Q pair program keeps one tile buffer per output row; the dense kernel keeps none)
+    if (p->dev.dense) return ((wfm::kDenseSliceBytes - fixed) / 2) & ~15;
+    return ((wfm::kWarpSliceBytes - fixed - ts * 8 * p->dev.planes) / 2) & ~15;
+  };
+  // the largest tile the average packet density allows (the device then measures every tile)
+  auto estimate_tile = [&]() {
+    int ts = wfm::kMaxTileSamples;
+    const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
+    const double ir = ((double)d->n_facs * 28.0 /* SRow, CRow, GRow: 32 bytes each; NOP rows vanish */ +
+                       (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
+    while (ts > wfm::kMinTileSamples && !(cap_of(ts) >= 256 && 64.0 + ir * ts <= cap_of(ts))) ts -= 128;
+    return ts;
+  };
+  int64_t n_tiles = 0;
+  auto set_tile = [&](int ts) {
+    p->dev.tile_samples = ts;
+    p->dev.pkt_cap = std::max(cap_of(ts), 64);
+    p->tile_prefix.resize(d->n_waves + 1);
+    n_tiles = 0;
+    for (int64_t w = 0; w < d->n_waves; ++w) {
+      p->tile_prefix[w] = n_tiles;
+      n_tiles += (d->waves[w].n + ts - 1) / ts;
+    }
+    p->tile_prefix[d->n_waves] = n_tiles;
+  };
+  if (stg) {
+    // everything the device needs is known on the host: unit, tile size, tile prefix; zeroed statistics ride along
+    if (unit_forced) p->dev.unit = force_unit[0] - '0';
+    p->dev.dense = p->dev.unit == wfm::kDenseUnit ? 1 : 0;
+    set_tile(estimate_tile());
+    up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
+    memset(stg + o_stats, 0, sizeof(uint64_t) * 2);
+    e = cudaMemcpyAsync(base, stg, arena_bytes, cudaMemcpyHostToDevice, ST);
+  }
   if (e == cudaSuccess) e = wfm::launch_prepare_segments(p->dev, pc, pb, ST);
 
   // Unit: samples per lane and evaluation.  Dense programs (more than two rounds of 32 active
   // samples in an average 1024-sample tile) evaluate two samples per lane, sparse ones one.
   // (Small programs skip the question and its round trip to the host: their figure of merit is latency — the README
   // example is 20 000 samples — and the unit size only tunes throughput.)
-  const bool small_program = samples <= (int64_t)1 << 20;
-  {
-    const char* force = std::getenv("WFM_K1_UNIT");
-    if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) {
-      p->dev.unit = force[0] - '0';
+  if (!stg) {
+    if (unit_forced) {
+      p->dev.unit = force_unit[0] - '0';
     } else if (small_program) {
       p->dev.unit = 1;
     } else {
@@ -560,32 +621,10 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   // for which every tile's packet fits its buffer, measured on the device: start from the
   // size the average packet density allows and step down while more than 1 tile in 4096 would
   // not fit (those take the kernel's cold path).
-  uint32_t* d_stats = (uint32_t*)(base + o_stats);
-  const int fixed = wfm::warp_fixed_bytes(p->dev.n_slots, p->dev.unit);
-  // (an I/Q pair program keeps one tile buffer per output row; the dense kernel keeps none)
-  auto cap_of = [&](int ts) {
-    if (p->dev.dense) return ((wfm::kDenseSliceBytes - fixed) / 2) & ~15;
-    return ((wfm::kWarpSliceBytes - fixed - ts * 8 * p->dev.planes) / 2) & ~15;
-  };
-  int ts = wfm::kMaxTileSamples;
-  {
-    const double per_sample = samples > 0 ? 1.0 / (double)samples : 0.0;
-    const double ir = ((double)d->n_facs * 28.0 /* SRow, CRow, GRow: 32 bytes each; NOP rows vanish */ +
-                       (double)d->n_terms * sizeof(wfm::CTerm) + (double)d->n_segs * sizeof(wfm::ARow)) * per_sample;
-    while (ts > wfm::kMinTileSamples && !(cap_of(ts) >= 256 && 64.0 + ir * ts <= cap_of(ts))) ts -= 128;
-  }
-  int64_t n_tiles = 0;
+  int ts = stg ? p->dev.tile_samples : estimate_tile();
   int sizing_passes = 0;
-  for (;; ts -= 128) {
-    p->dev.tile_samples = ts;
-    p->dev.pkt_cap = std::max(cap_of(ts), 64);
-    p->tile_prefix.resize(d->n_waves + 1);
-    n_tiles = 0;
-    for (int64_t w = 0; w < d->n_waves; ++w) {
-      p->tile_prefix[w] = n_tiles;
-      n_tiles += (d->waves[w].n + ts - 1) / ts;
-    }
-    p->tile_prefix[d->n_waves] = n_tiles;
+  for (; !stg; ts -= 128) {
+    set_tile(ts);
     if (n_tiles >= INT32_MAX) {
       delete p;
       return fail(WFM_EINVAL, "too many tiles (%lld)", (long long)n_tiles);
@@ -624,9 +663,10 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     pb.tiles = p->d_tiles;
     pb.pkt_size = (uint32_t*)(base2 + o_pktsize);
     pc.n_tiles = n_tiles;
-    up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
-    // pre-pass 1b: the tile rows with their packet sizes; then the packet offsets
-    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, nullptr, ST);
+    if (!stg) up(o_prefix, p->tile_prefix.data(), sizeof(int64_t) * (d->n_waves + 1));
+    // pre-pass 1b: the tile rows with their packet sizes (fast path: and the statistics the sizing pass would have
+    // taken); then the packet offsets
+    if (e == cudaSuccess) e = wfm::launch_prepare_tiles(p->dev, pc, pb, stg ? d_stats : nullptr, ST);
     if (e == cudaSuccess)
       e = wfm::launch_scan((uint32_t*)(base2 + o_pktsize), (uint32_t*)(base2 + o_pktoff), (uint32_t*)(base2 + o_scratch),
                            n_tiles, ST);
@@ -641,7 +681,21 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   if (e == cudaSuccess) e = pool::alloc(device, std::max<size_t>((size_t)total16 * 16, 16), &p->packets);
   p->dev.packets = (const unsigned char*)p->packets.p;
   if (e == cudaSuccess) e = wfm::launch_fill_packets(p->dev, p->d_tiles, n_tiles, (unsigned char*)p->packets.p, ST);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ST);
+  if (stg && n_tiles > 0 && ts > wfm::kMinTileSamples) {
+    // the one synchronisation of the fast path also brings the statistics: tiles whose packet does not fit their buffer
+    // (they would take the kernel's cold path) send the program through the measured sizing loop instead
+    uint32_t stats[2] = {0, 0};
+    if (e == cudaSuccess) e = read_words(stats, d_stats, 2, ST);
+    if (e == cudaSuccess && (int64_t)stats[1] * 4096 > n_tiles) {
+      delete p;
+      g_no_fast_create = true;
+      const int rc2 = wfm_program_create(d, device, out);
+      g_no_fast_create = false;
+      return rc2;
+    }
+  } else if (e == cudaSuccess) {
+    e = cudaStreamSynchronize(ST);
+  }
   tm.lap("device pre-pass 2");
   if (e != cudaSuccess) {
     delete p;
