@@ -36,6 +36,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 #include "wfm_internal.h"
 
@@ -46,6 +47,15 @@ namespace wfm {
 #endif
 #ifndef WFM_FFT_BIG_RADIX
 #define WFM_FFT_BIG_RADIX 1  // composite butterflies held in registers: 1 = 10 (2x5), 2 = also 25 (5x5)
+#endif
+#ifndef WFM_FFT_COMPUTED_TW
+#define WFM_FFT_COMPUTED_TW 0  // 1: inter-pass twiddles by sincospi instead of two table look-ups each (measured: L1TEX 63 -> 52 %, +11 % instructions, column passes 0.65 -> 0.68 ms: they are issue-bound, not L1TEX-bound)
+#endif
+#ifndef WFM_FFT_CT_GLOBAL_TW
+#define WFM_FFT_CT_GLOBAL_TW 1
+#endif
+#ifndef WFM_FFT_CT
+#define WFM_FFT_CT 1  // compile-time plans for the tile shapes of cfg4 (625 x 4 columns, 640 x 2 rows)
 #endif
 #ifndef WFM_FFT_THREADS
 #define WFM_FFT_THREADS 512
@@ -67,6 +77,7 @@ constexpr int kFftColsThreads = WFM_FFT_COLS_THREADS;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
 constexpr int kSmemBudget = 227 * 1024 - 1024;
+constexpr int kPlanSlackBytes = 256;  // behind the buffers and the twiddle table: per-column inter-pass twiddles of a tile
 
 struct FftPlan {
   int L;
@@ -383,6 +394,17 @@ struct BigTwiddle {
   const double2* hi;  // W_n^(1024 h)
   const double2* lo;  // W_n^l, l < 1024
 };
+// W_n^m = exp(sgn * 2 pi i m / n), 0 <= m < n, computed: the look-ups above cost two scattered 16-byte loads per value
+// (up to 32 cache lines per warp request) in passes that L1TEX bounds, while the FP64 pipe runs at a quarter of its rate.
+// 2m/n to the last bit (one Newton step on the rounded reciprocal), then sincospi.
+__device__ __forceinline__ double2 computed_twiddle(int64_t m, double nd, double inv_n, double sgn) {
+  const double m2 = (double)(2 * m);
+  double q = m2 * inv_n;
+  q = fma(fma(-q, nd, m2), inv_n, q);
+  double sn, cs;
+  sincospi(q, &sn, &cs);
+  return make_double2(cs, sgn * sn);
+}
 __device__ __forceinline__ double2 big_twiddle(const BigTwiddle& T, int64_t m, double sgn) {
   double2 w = cmul(__ldg(T.hi + (m >> 10)), __ldg(T.lo + (m & 1023)));
   w.y *= -sgn;  // tables hold exp(-i ..): forward (sgn = -1) keeps it, inverse conjugates
@@ -440,6 +462,139 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
   smem_fft(P, 0, +1.0, tw, SmemIn{z, 0}, PairOut{ys, two ? ys + y_stride : nullptr, 1.0 / (double)P.L, nv}, z == a ? b : a, z);
 }
 
+// ---- compile-time plans -------------------------------------------------------------------------------------------------
+// The generic stages take the transform length, the interleave, the radix sequence and the strides at run time: two
+// thirds of their instructions are index arithmetic (ncu: 88 M fp64 of 365 M warp instructions per column pass of cfg4).
+// For the tile shapes that matter the whole plan is a template argument: element indices become immediate offsets, the
+// butterfly count per thread is a constant, j / Ns is a multiply-shift by a constant.  CtIn / CtOut accessors get the
+// point, the column and the element index e = (point << LOGC) + column.
+template <int R, int L, int LOGC, int NS, int TOFF, bool kFwd, int T, bool kCompactTw, class In, class Out>
+__device__ __forceinline__ void stage_ct(In in, Out out, const double2* __restrict__ tw) {
+  constexpr double sgn = kFwd ? -1.0 : 1.0;
+  constexpr int nb = L / R, nbC = nb << LOGC, NsC = NS << LOGC, tstep = L / (NS * R);
+  constexpr int iters = (nbC + T - 1) / T;
+#pragma unroll
+  for (int it = 0; it < iters; ++it) {
+    const int jj = (int)threadIdx.x + it * T;
+    if (nbC % T != 0 && jj >= nbC) break;
+    const int c = jj & ((1 << LOGC) - 1), j = jj >> LOGC;
+    const int q = NS == 1 ? j : j / NS;
+    const int k = j - q * NS;
+    double2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in(j + r * nb, c, jj + r * nbC);
+    in.template twiddle_run<R>(v, j, nb, c);
+    if (!kCompactTw && NS > 1 && k > 0) {
+      // every W^(k r) from the full table (a length whose stage strides are odd multiples of 16 bytes — 625 — has no
+      // bank conflicts there, and the column passes are bound by instruction issue, not by shared memory)
+      const int kt = k * tstep;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        const double2 w = tw[r * kt];
+        v[r] = kFwd ? make_double2(fma(v[r].x, w.x, -v[r].y * w.y), fma(v[r].x, w.y, v[r].y * w.x))
+                    : make_double2(fma(v[r].x, w.x, v[r].y * w.y), fma(v[r].y, w.x, -v[r].x * w.y));
+      }
+    }
+    if (kCompactTw && NS > 1 && k > 0) {
+      // ONE look-up per butterfly, W^k from the stage's own compact table (consecutive k: consecutive addresses, no bank
+      // conflicts — in the full table a stage's twiddles are tstep * 16 bytes apart, a multiple of the 128-byte bank
+      // period for the early stages); W^(k r) by products of depth <= 3.  The shared-memory pipe, not the FP64 pipe, is
+      // what these passes saturate.
+      double2 w[R];
+      w[1] = tw[TOFF + k];
+#pragma unroll
+      for (int r = 2; r < R; ++r) w[r] = (r & 1) ? cmul(w[r - 1], w[1]) : cmul(w[r / 2], w[r / 2]);
+#pragma unroll
+      for (int r = 1; r < R; ++r)
+        v[r] = kFwd ? make_double2(fma(v[r].x, w[r].x, -v[r].y * w[r].y), fma(v[r].x, w[r].y, v[r].y * w[r].x))
+                    : make_double2(fma(v[r].x, w[r].x, v[r].y * w[r].y), fma(v[r].y, w[r].x, -v[r].x * w[r].y));
+    }
+    dft_small<R>(v, sgn);
+    const int j0 = j + q * (NS * (R - 1));
+    const int e0 = jj + q * (NsC * (R - 1));
+    out.template twiddle_run<R>(v, j0, NS, c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) out(j0 + r * NS, c, e0 + r * NsC, v[r]);
+  }
+}
+// the (point, column) accessors of the generic stages behind the compile-time interface
+template <class A>
+struct CtWrapIn {
+  A a;
+  __device__ __forceinline__ double2 operator()(int p, int c, int) const { return a(p, c); }
+  template <int R>
+  __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const { a.template twiddle_run<R>(v, r0, step, c); }
+};
+template <class A>
+struct CtWrapOut {
+  A a;
+  __device__ __forceinline__ void operator()(int p, int c, int, double2 v) const { a(p, c, v); }
+  template <int R>
+  __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const { a.template twiddle_run<R>(v, r0, step, c); }
+};
+struct CtSmemIn {
+  WFM_NO_RUN_TWIDDLE
+  const double2* a;
+  __device__ __forceinline__ double2 operator()(int, int, int e) const { return a[e]; }
+};
+struct CtSmemOut {
+  WFM_NO_RUN_TWIDDLE
+  double2* b;
+  __device__ __forceinline__ void operator()(int, int, int e, double2 v) const { b[e] = v; }
+};
+// stages 0 .. S-1 of the radix pack; stage s reads `in` (s = 0) or the buffer stage s-1 wrote, and writes `out`
+// (s = S-1) or buf[s & 1]
+template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int NS, int TOFF, class In, class Out, int R0, int... Rest>
+__device__ __forceinline__ void stages_ct_impl(int s, In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1,
+                                               std::integer_sequence<int, R0, Rest...>) {
+  double2* dst = (s & 1) ? buf1 : buf0;
+  if constexpr (sizeof...(Rest) == 0) {
+    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, out, tw);
+    __syncthreads();
+  } else {
+    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, CtSmemOut{dst}, tw);
+    __syncthreads();
+    stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, NS * R0, TOFF + NS>(s + 1, CtSmemIn{dst}, out, tw, buf0, buf1,
+                                                         std::integer_sequence<int, Rest...>{});
+  }
+}
+// same contract as smem_fft: `in` may read buf1, the last stage writes through `out` (last_stage_target is the buffer it
+// does not read)
+template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int... Rs, class In, class Out>
+__device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1) {
+  stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, 1, 0>(0, in, out, tw, buf0, buf1, std::integer_sequence<int, Rs...>{});
+}
+// the compact twiddle table of a plan: for stage s (stride Ns = product of the earlier radices) the Ns values
+// W_L^(k L / (Ns R_s)), k < Ns, back to back; gathered from the plan's full table.  Returns its length.
+__device__ __forceinline__ int stage_compact_twiddles(const FftPlan& P, double2* dst) {
+  int off = 0, ns = 1;
+  for (int s = 0; s < P.n_stage; ++s) {
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) dst[off + k] = P.tw[k * P.tstep[s]];
+    off += ns;
+    ns *= P.radix[s];
+  }
+  return off;
+}
+struct CtRowsTileIn {
+  WFM_NO_RUN_TWIDDLE
+  const double2* t;  // [c][p]
+  int N2;
+  __device__ __forceinline__ double2 operator()(int p, int c, int) const { return t[c * N2 + p]; }
+};
+struct CtRowsTileOut {
+  WFM_NO_RUN_TWIDDLE
+  double2* t;  // [c][p]
+  int N2;
+  __device__ __forceinline__ void operator()(int p, int c, int, double2 v) const { t[c * N2 + p] = v; }
+};
+struct CtRowsTileMulHOut {
+  WFM_NO_RUN_TWIDDLE
+  double2* z;        // interleaved
+  const double2* h;  // [c][p]
+  int N2;
+  __device__ __forceinline__ void operator()(int p, int c, int e, double2 v) const { z[e] = cmul(v, h[c * N2 + p]); }
+};
+
 // ---- four-step, kernel A / C: column transforms of length N1 -----------------------
 // element (r, n2) of the [N1][N2] view; C = 2^logc adjacent columns per CTA.  The inter-pass
 // twiddle W_n^(sgn * r * n2) (r * n2 < n: no reduction needed) is applied after the
@@ -463,6 +618,8 @@ struct ColsIn {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn;
+  const double2* wsc;  // shared memory: W^(step (c0 + c)) per column
+  double nd, inv_n;
   int64_t nv;  // real input: samples the signals hold (zeros beyond)
   __device__ __forceinline__ double2 operator()(int r, int c) const {
     double2 v = make_double2(0.0, 0.0);
@@ -484,8 +641,13 @@ struct ColsIn {
   template <int R>
   __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
     if (!kTwBefore || c >= cw) return;
+#if WFM_FFT_COMPUTED_TW
+    double2 w = computed_twiddle((int64_t)r0 * (c0 + c), nd, inv_n, sgn);
+    const double2 ws = wsc[c];  // W^(step col): one value per column of the tile, computed once per CTA
+#else
     double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
     const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
+#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       v[q] = cmul(v[q], w);
@@ -500,12 +662,19 @@ struct ColsOut {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn, scale;
+  const double2* wsc;
+  double nd, inv_n;
   int64_t nv;  // real output: samples kept (writes beyond are dropped)
   template <int R>
   __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
     if (!kTwAfter || c >= cw) return;
+#if WFM_FFT_COMPUTED_TW
+    double2 w = computed_twiddle((int64_t)r0 * (c0 + c), nd, inv_n, sgn);
+    const double2 ws = wsc[c];
+#else
     double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
     const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
+#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       v[q] = cmul(v[q], w);
@@ -532,7 +701,10 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + padded_points((size_t)N1 << logc);
-  const double2* tw = stage_twiddles(P, b + padded_points((size_t)N1 << logc));
+  const bool ct = WFM_FFT_CT && P.L == 625 && logc == 2 && (kTwAfter ? sgn < 0.0 : sgn > 0.0);
+  // (the compile-time path reads the 10 KB table through L1 instead of staging it per tile: one barrier-bounded phase
+  // less in a tile that lives for 8 us)
+  const double2* tw = (ct && WFM_FFT_CT_GLOBAL_TW) ? P.tw : stage_twiddles(P, b + padded_points((size_t)N1 << logc));
   const int c0 = blockIdx.x << logc;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
@@ -545,7 +717,18 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     src.pa = static_cast<const double2*>(in) + sig * in_stride;
     src.pb = nullptr;
   }
-  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn; src.nv = nv;
+  // the step twiddle of the tile's columns: rows j, j + step, ... of column col differ by W^(step col)
+  double2* wsc = const_cast<double2*>(reinterpret_cast<const double2*>(fft_smem_raw)) + 2 * padded_points((size_t)N1 << logc) +
+                 (P.tw_in_smem ? P.L : 0);
+  const double nd = (double)N1 * (double)N2, inv_n = 1.0 / nd;
+#if WFM_FFT_COMPUTED_TW
+  if ((int)threadIdx.x < cw) {
+    const int step = kTwAfter ? P.L / P.radix[P.n_stage - 1] : P.L / P.radix[0];
+    wsc[threadIdx.x] = computed_twiddle((int64_t)step * (c0 + (int)threadIdx.x), nd, inv_n, sgn);
+  }
+  __syncthreads();
+#endif
+  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn; src.nv = nv; src.wsc = wsc; src.nd = nd; src.inv_n = inv_n;
   ColsOut<kTwAfter, kRealOut> dst;
   if (kRealOut) {
     dst.pa = static_cast<double*>(out) + 2 * sig * out_stride;
@@ -554,7 +737,14 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     dst.pa = static_cast<double2*>(out) + sig * out_stride;
     dst.pb = nullptr;
   }
-  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv;
+  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n;
+  if (ct) {
+    // the filter's column passes on cfg4's grid: 625 = 5^4, four columns
+    const double2* tws = WFM_FFT_CT_GLOBAL_TW ? P.tw : (P.tw_in_smem ? b + padded_points((size_t)N1 << logc) : P.tw);
+    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, false, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+                                                                      CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b);
+    return;
+  }
   smem_fft(P, logc, sgn, tw, src, dst, a, b);
 }
 
@@ -622,6 +812,123 @@ __global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_k
     smem_fft(P, logc, +1.0, tw, SmemIn{z, logc}, RowsOut{rows, N2, rw}, z == a ? b : a, z);
   } else {
     smem_fft(P, logc, sgn, tw, RowsIn{rows, N2, rw}, NaturalOut{out + sig * out_stride + r0, N1, rw, scale}, a, b);
+  }
+}
+
+
+
+// ---- kernel B with TMA: the tile's rows are ONE contiguous span of the scratch ---------------------------------------
+// C adjacent rows of the [N1][N2] scratch are rw * N2 consecutive complex numbers, and so are the rows of the permuted
+// response that multiply them.  One elected thread moves both into shared memory with cp.async.bulk (two mbarriers) and
+// the filtered rows back with one bulk store: the row pass executes no LDG / STG at all — its L1TEX unit, at 76 % with
+// per-thread 16-byte accesses, is left to the shared-memory traffic of the stages.  The landing buffers keep the global
+// layout ([c][p]); the first stage reads it and the last one writes it through these accessors.
+__device__ __forceinline__ uint32_t fft_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fft_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fft_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fft_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fft_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fft_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(fft_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fft_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   fft_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(fft_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fft_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(fft_smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+constexpr int kRowPad = 4;  // elements (64 bytes) between the rows of a landing buffer
+struct RowsTileIn {
+  WFM_NO_RUN_TWIDDLE
+  const double2* t;  // [c][p]
+  int N2;
+  __device__ __forceinline__ double2 operator()(int p, int c) const { return t[c * N2 + p]; }
+};
+struct RowsTileOut {
+  WFM_NO_RUN_TWIDDLE
+  double2* t;  // [c][p]
+  int N2;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const { t[c * N2 + p] = v; }
+};
+struct RowsTileMulHOut {
+  WFM_NO_RUN_TWIDDLE
+  double2* z;          // interleaved [(p << logc) + c]
+  const double2* h;    // the response rows of the tile in shared memory, [c][p]
+  int N2, logc;
+  __device__ __forceinline__ void operator()(int p, int c, double2 v) const { z[spad((p << logc) + c)] = cmul(v, h[c * N2 + p]); }
+};
+__global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_tma_kernel(FftPlan P, int N1, int logc,
+                                                                                         double2* __restrict__ data, int64_t stride,
+                                                                                         const double2* __restrict__ Hp) {
+  const int N2 = P.L, C = 1 << logc;
+  // landing buffers keep the global layout, one row after the other, kRowPad elements apart: with N2 a multiple of 8
+  // the rows of a tile would start on the same bank group and the lanes of a butterfly pair (c = 0, 1) would collide
+  const int RS = N2 + kRowPad;
+  double2* a = reinterpret_cast<double2*>(fft_smem_raw);
+  double2* b = a + (size_t)C * RS;  // (>= pts: the buffers also serve as the interleaved work buffers of the stages)
+  double2* twp = b + (size_t)C * RS;
+  double2* h = twp + P.L;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(h + (size_t)C * RS);
+  const int r0 = blockIdx.x << logc;
+  const int rw = min(C, N1 - r0);
+  double2* rows = data + (int64_t)blockIdx.y * stride + (int64_t)r0 * N2;
+  const uint32_t row_bytes = (uint32_t)N2 * (uint32_t)sizeof(double2);
+  if (threadIdx.x == 0) {
+    fft_mbar_init(bar);
+    fft_mbar_init(bar + 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fft_mbar_expect_tx(bar, row_bytes * rw);
+    for (int c = 0; c < rw; ++c) fft_bulk_g2s(b + (size_t)c * RS, rows + (int64_t)c * N2, row_bytes, bar);
+    fft_mbar_expect_tx(bar + 1, row_bytes * rw);
+    for (int c = 0; c < rw; ++c) fft_bulk_g2s(h + (size_t)c * RS, Hp + (int64_t)(r0 + c) * N2, row_bytes, bar + 1);
+  }
+  const bool ct = WFM_FFT_CT && P.L == 640 && logc == 1;
+  const double2* tw = twp;
+  if (ct) stage_compact_twiddles(P, twp);
+  else tw = stage_twiddles(P, twp);
+  __syncthreads();  // the barriers are initialised (and the twiddles staged) for every thread
+  fft_mbar_wait(bar, 0);
+  fft_mbar_wait(bar + 1, 0);
+  // (a tile of fewer than C rows computes on whatever the missing rows' part of the buffers holds: columns are
+  // independent and only rw rows are stored)
+  double2* o = b;
+  if (ct) {
+    // 640 = 10 x 8 x 8, two rows: b -> a -> b -> (x H) a;  a -> b -> a -> b
+    smem_fft_ct<640, 1, true, kFftRowsThreads, true, 10, 8, 8>(CtRowsTileIn{b, 640 + kRowPad}, CtRowsTileMulHOut{a, h, 640 + kRowPad}, twp, a, b);
+    smem_fft_ct<640, 1, false, kFftRowsThreads, true, 10, 8, 8>(CtSmemIn{a}, CtRowsTileOut{b, 640 + kRowPad}, twp, b, a);
+  } else {
+    // (either buffer may end up holding the padded output rows: both have room for them)
+    double2* z = last_stage_target(P, a, b);
+    smem_fft(P, logc, -1.0, tw, RowsTileIn{b, RS}, RowsTileMulHOut{z, h, RS, logc}, a, b);
+    double2* w0 = z == a ? b : a;
+    double2* oo = last_stage_target(P, w0, z);
+    smem_fft(P, logc, +1.0, tw, SmemIn{z, logc}, RowsTileOut{oo, RS}, w0, z);
+    o = oo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's tile writes -> the async proxy
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < rw; ++c) fft_bulk_s2g(rows + (int64_t)c * N2, o + (size_t)c * RS, row_bytes);
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
 
@@ -791,7 +1098,7 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
     plan->tstep[s] = (int)(L / (ns * plan->radix[s]));
     ns *= plan->radix[s];
   }
-  const size_t buffers = 2 * sizeof(double2) * padded_points((size_t)points);
+  const size_t buffers = 2 * sizeof(double2) * padded_points((size_t)points) + kPlanSlackBytes;
   plan->tw_in_smem = buffers + sizeof(double2) * (size_t)L <= (size_t)kSmemBudget;
   *smem = buffers + (plan->tw_in_smem ? sizeof(double2) * (size_t)L : 0);
   int dev = 0;
@@ -1088,10 +1395,18 @@ static int run_filter(const double* x, double* y, int64_t n_sig, int64_t n, int6
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<true, true, false>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_cols_kernel<false, false, true>, smem1);
     if (e == cudaSuccess) e = set_smem(fft_rows_kernel<true>, smem2);
+    // the TMA row pass needs the response rows of the tile next to the two buffers and the twiddle table
+    const size_t smem2t = smem2 + sizeof(double2) * (((size_t)N2 << lc2) + 3 * ((size_t)kRowPad << lc2)) + 16;
+    static const bool no_tma = std::getenv("WFM_FFT_NO_TMA") != nullptr;
+    const bool rows_tma = !no_tma && P2.tw_in_smem && WFM_FFT_PAD == 0 && smem2t <= (size_t)kSmemBudget && P2.n_stage >= 1;
+    if (e == cudaSuccess && rows_tma) e = set_smem(fft_rows_tma_kernel, smem2t);
     if (e == cudaSuccess) {
       fft_cols_kernel<true, true, false><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, x, scratch, x_stride, n, -1.0, 1.0,
                                                                          n_sig, nv);
-      fft_rows_kernel<true><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, ready, -1.0, 1.0);
+      if (rows_tma)
+        fft_rows_tma_kernel<<<g2, kFftRowsThreads, smem2t, st>>>(P2, N1, lc2, scratch, n, ready);
+      else
+        fft_rows_kernel<true><<<g2, kFftRowsThreads, smem2, st>>>(P2, N1, lc2, scratch, nullptr, n, 0, ready, -1.0, 1.0);
       fft_cols_kernel<false, false, true><<<g1, kFftColsThreads, smem1, st>>>(P1, BT, N2, lc1, scratch, y, n, y_stride, +1.0,
                                                                           1.0 / (double)n, n_sig, nv);
       e = cudaGetLastError();
