@@ -54,6 +54,9 @@ namespace wfm {
 #ifndef WFM_FFT_CT_GLOBAL_TW
 #define WFM_FFT_CT_GLOBAL_TW 1
 #endif
+#ifndef WFM_FFT_CT_COLS_COMPACT
+#define WFM_FFT_CT_COLS_COMPACT 1  // column passes: one coalesced W^k look-up per butterfly (through L1) + powers in registers
+#endif
 #ifndef WFM_FFT_CT
 #define WFM_FFT_CT 1  // compile-time plans for the tile shapes of cfg4 (625 x 4 columns, 640 x 2 rows)
 #endif
@@ -86,6 +89,7 @@ struct FftPlan {
   uint32_t inv_ns[kMaxStages];  // ceil(2^32 / Ns) of every stage: j / Ns = umulhi(j, inv) for j < 2^16
   int tstep[kMaxStages];        // L / (Ns * R) of every stage: the stride of its twiddles in the table
   const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)  (global memory)
+  const double2* twc;  // compact per-stage table (global memory): for stage s the Ns values W_L^(k tstep[s]), k < Ns, back to back
   int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers
 };
 
@@ -567,13 +571,13 @@ __device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __res
 // the compact twiddle table of a plan: for stage s (stride Ns = product of the earlier radices) the Ns values
 // W_L^(k L / (Ns R_s)), k < Ns, back to back; gathered from the plan's full table.  Returns its length.
 __device__ __forceinline__ int stage_compact_twiddles(const FftPlan& P, double2* dst) {
-  int off = 0, ns = 1;
+  int len = 0, ns = 1;
   for (int s = 0; s < P.n_stage; ++s) {
-    for (int k = threadIdx.x; k < ns; k += blockDim.x) dst[off + k] = P.tw[k * P.tstep[s]];
-    off += ns;
+    len += ns;
     ns *= P.radix[s];
   }
-  return off;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) dst[k] = P.twc[k];
+  return len;
 }
 struct CtRowsTileIn {
   WFM_NO_RUN_TWIDDLE
@@ -626,12 +630,13 @@ struct ColsIn {
     if (c < cw) {
       const int64_t idx = (int64_t)r * N2 + c0 + c;
       if (kRealIn) {
+        // streaming loads (evict-first): the signal passes through once and must not push the twiddle tables out of L1
         if (idx < nv) {
-          v.x = static_cast<const double*>(pa)[idx];
-          if (pb) v.y = static_cast<const double*>(pb)[idx];
+          v.x = __ldcs(static_cast<const double*>(pa) + idx);
+          if (pb) v.y = __ldcs(static_cast<const double*>(pb) + idx);
         }
       } else {
-        v = static_cast<const double2*>(pa)[idx];
+        v = __ldcs(static_cast<const double2*>(pa) + idx);
       }
     }
     return v;
@@ -686,10 +691,10 @@ struct ColsOut {
     const int64_t idx = (int64_t)r * N2 + c0 + c;
     if (kRealOut) {
       if (idx >= nv) return;
-      static_cast<double*>(pa)[idx] = v.x * scale;
-      if (pb) static_cast<double*>(pb)[idx] = v.y * scale;
+      __stcs(static_cast<double*>(pa) + idx, v.x * scale);
+      if (pb) __stcs(static_cast<double*>(pb) + idx, v.y * scale);
     } else {
-      static_cast<double2*>(pa)[idx] = cscale(v, scale);
+      __stcs(static_cast<double2*>(pa) + idx, cscale(v, scale));
     }
   }
 };
@@ -740,8 +745,8 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n;
   if (ct) {
     // the filter's column passes on cfg4's grid: 625 = 5^4, four columns
-    const double2* tws = WFM_FFT_CT_GLOBAL_TW ? P.tw : (P.tw_in_smem ? b + padded_points((size_t)N1 << logc) : P.tw);
-    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, false, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+    const double2* tws = WFM_FFT_CT_COLS_COMPACT ? P.twc : (WFM_FFT_CT_GLOBAL_TW ? P.tw : (P.tw_in_smem ? b + padded_points((size_t)N1 << logc) : P.tw));
+    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, WFM_FFT_CT_COLS_COMPACT != 0, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
                                                                       CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b);
     return;
   }
@@ -1075,6 +1080,7 @@ static bool is_smooth(int64_t n) {
 
 static std::mutex g_tw_mutex;
 static std::map<std::pair<int, int>, double2*> g_tw_cache;              // (device, L) -> table
+static std::map<std::pair<int, int>, double2*> g_twc_cache;             // (device, L) -> compact per-stage table
 static std::map<std::pair<int, int64_t>, BigTwiddle> g_big_tw_cache;     // (device, n) -> inter-pass tables
 
 static cudaError_t upload_table(const std::vector<double2>& host, double2** out) {
@@ -1118,6 +1124,24 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
     it = g_tw_cache.emplace(std::make_pair(dev, L), d).first;
   }
   plan->tw = it->second;
+  auto ic = g_twc_cache.find({dev, L});
+  if (ic == g_twc_cache.end()) {
+    std::vector<double2> host;
+    const long double two_pi = 6.283185307179586476925286766559L;
+    int64_t nsc = 1;
+    for (int s = 0; s < plan->n_stage; ++s) {
+      for (int64_t k = 0; k < nsc; ++k) {
+        long double ang = two_pi * (long double)(k * plan->tstep[s]) / (long double)L;
+        host.push_back(make_double2((double)cosl(ang), (double)-sinl(ang)));
+      }
+      nsc *= plan->radix[s];
+    }
+    if (host.empty()) host.push_back(make_double2(1.0, 0.0));
+    double2* d = nullptr;
+    if ((e = upload_table(host, &d)) != cudaSuccess) return e;
+    ic = g_twc_cache.emplace(std::make_pair(dev, L), d).first;
+  }
+  plan->twc = ic->second;
   return cudaSuccess;
 }
 
