@@ -89,6 +89,7 @@ struct FftPlan {
   uint32_t inv_ns[kMaxStages];  // ceil(2^32 / Ns) of every stage: j / Ns = umulhi(j, inv) for j < 2^16
   int tstep[kMaxStages];        // L / (Ns * R) of every stage: the stride of its twiddles in the table
   const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)  (global memory)
+  int twc_len;         // entries of twc: sum of the stage strides Ns
   const double2* twc;  // compact per-stage table (global memory): for stage s the Ns values W_L^(k tstep[s]), k < Ns, back to back
   int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers
 };
@@ -260,27 +261,22 @@ struct SmemOut {
   __device__ __forceinline__ void operator()(int p, int c, double2 v) const { b[spad((p << logc) + c)] = v; }
 };
 
-// twiddles W^(k r), r = 1..R-1, of one butterfly: W^k, W^2k, W^4k (W^8k) come from the table,
-// the others are their products (one or two roundings more; keeps 3 of 7 table reads at R = 8)
+// twiddles W^(k r), r = 1..R-1, of one butterfly: ONE look-up, W^k from the stage's slice of the compact table
+// (FftPlan.twc: consecutive k at consecutive addresses — in a full W_L^p table a stage's twiddles sit tstep * 16 bytes
+// apart, a multiple of the bank period for the early stages of even lengths: up to 16-way conflicts), the powers by
+// products of depth <= log2 R (a few roundings more; the FP64 pipe idles in these kernels, the shared-memory pipe does not)
 template <int R>
-__device__ __forceinline__ void load_twiddles(double2 (&w)[R], const double2* __restrict__ tw, int t1, double sgn) {
+__device__ __forceinline__ void load_twiddles(double2 (&w)[R], const double2* __restrict__ tw_k, double sgn) {
+  w[1] = *tw_k;
+  w[1].y *= -sgn;  // table holds exp(-i..): forward (sgn=-1) keeps it, inverse conjugates
 #pragma unroll
-  for (int r = 1; r < R; r <<= 1) {
-    w[r] = tw[t1 * r];
-    w[r].y *= -sgn;  // table holds exp(-i..): forward (sgn=-1) keeps it, inverse conjugates
-  }
-#pragma unroll
-  for (int r = 3; r < R; ++r) {
-    if ((r & (r - 1)) == 0) continue;
-    const int hi = r >= 16 ? 16 : (r >= 8 ? 8 : (r >= 4 ? 4 : 2));
-    w[r] = cmul(w[hi], w[r - hi]);
-  }
+  for (int r = 2; r < R; ++r) w[r] = (r & 1) ? cmul(w[r - 1], w[1]) : cmul(w[r / 2], w[r / 2]);
 }
 
 template <int R, class In, class Out>
-__device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, int Ns, uint32_t inv_ns, int tstep,
+__device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, int Ns, uint32_t inv_ns, int toff,
                                                const double2* __restrict__ tw, double sgn) {
-  const int nb = L / R;        // butterflies per transform; tstep = L / (Ns*R): table stride of this stage (from the plan)
+  const int nb = L / R;        // butterflies per transform; toff: where the stage's Ns twiddles start in the compact table
   const int cmask = (1 << logc) - 1;
   const int total = nb << logc;
   for (int jj = threadIdx.x; jj < total; jj += blockDim.x) {
@@ -293,7 +289,7 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
     in.template twiddle_run<R>(v, j, nb, c);  // inter-pass twiddles of the run j, j+nb, ... (column passes)
     if (k > 0) {
       double2 w[R];
-      load_twiddles<R>(w, tw, k * tstep, sgn);
+      load_twiddles<R>(w, tw + toff + k, sgn);
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
     }
@@ -306,26 +302,26 @@ __device__ __forceinline__ void stockham_stage(In in, Out out, int L, int logc, 
 }
 
 template <class In, class Out>
-__device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc, int Ns, uint32_t inv, int tstep,
+__device__ __forceinline__ void stage_any(int R, In in, Out out, int L, int logc, int Ns, uint32_t inv, int toff,
                                           const double2* __restrict__ tw, double sgn) {
   switch (R) {
-    case 2: stockham_stage<2>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
-    case 3: stockham_stage<3>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
-    case 4: stockham_stage<4>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
-    case 5: stockham_stage<5>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 2: stockham_stage<2>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
+    case 3: stockham_stage<3>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
+    case 4: stockham_stage<4>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
+    case 5: stockham_stage<5>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
 #if WFM_FFT_MAX_RADIX >= 8
-    case 8: stockham_stage<8>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 8: stockham_stage<8>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
 #endif
 #if WFM_FFT_MAX_RADIX >= 16
-    case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 16: stockham_stage<16>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
 #endif
 #if WFM_FFT_BIG_RADIX
-    case 10: stockham_stage<10>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 10: stockham_stage<10>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
 #endif
 #if WFM_FFT_BIG_RADIX >= 2
-    case 25: stockham_stage<25>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    case 25: stockham_stage<25>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
 #endif
-    default: stockham_stage<7>(in, out, L, logc, Ns, inv, tstep, tw, sgn); break;
+    default: stockham_stage<7>(in, out, L, logc, Ns, inv, toff, tw, sgn); break;
   }
 }
 
@@ -361,21 +357,22 @@ __device__ __forceinline__ void smem_fft_rt(const FftPlan& P, int logc, double s
     return;
   }
   if (S == 1) {
-    stage_any(P.radix[0], in, out, P.L, logc, 1, P.inv_ns[0], P.tstep[0], tw, sgn);
+    stage_any(P.radix[0], in, out, P.L, logc, 1, P.inv_ns[0], 0, tw, sgn);
     __syncthreads();
     return;
   }
-  stage_any(P.radix[0], in, SmemOut{buf0, logc}, P.L, logc, 1, P.inv_ns[0], P.tstep[0], tw, sgn);
+  stage_any(P.radix[0], in, SmemOut{buf0, logc}, P.L, logc, 1, P.inv_ns[0], 0, tw, sgn);
   __syncthreads();
-  int Ns = P.radix[0];
+  int Ns = P.radix[0], toff = 1;
   double2 *src = buf0, *dst = buf1;
   for (int s = 1; s < S - 1; ++s) {
-    stage_any(P.radix[s], SmemIn{src, logc}, SmemOut{dst, logc}, P.L, logc, Ns, P.inv_ns[s], P.tstep[s], tw, sgn);
+    stage_any(P.radix[s], SmemIn{src, logc}, SmemOut{dst, logc}, P.L, logc, Ns, P.inv_ns[s], toff, tw, sgn);
     __syncthreads();
     double2* t = src; src = dst; dst = t;
+    toff += Ns;
     Ns *= P.radix[s];
   }
-  stage_any(P.radix[S - 1], SmemIn{src, logc}, out, P.L, logc, Ns, P.inv_ns[S - 1], P.tstep[S - 1], tw, sgn);
+  stage_any(P.radix[S - 1], SmemIn{src, logc}, out, P.L, logc, Ns, P.inv_ns[S - 1], toff, tw, sgn);
   __syncthreads();
 }
 // the buffer the last stage of smem_fft(.., buf0, buf1) may write through `out` (the one it
@@ -386,8 +383,8 @@ __device__ __forceinline__ double2* last_stage_target(const FftPlan& P, double2*
 
 // the plan's twiddle table: staged behind the two ping-pong buffers when it fits
 __device__ __forceinline__ const double2* stage_twiddles(const FftPlan& P, double2* smem_after_buffers) {
-  if (!P.tw_in_smem) return P.tw;
-  for (int p = threadIdx.x; p < P.L; p += blockDim.x) smem_after_buffers[p] = P.tw[p];
+  if (!P.tw_in_smem) return P.twc;
+  for (int p = threadIdx.x; p < P.twc_len; p += blockDim.x) smem_after_buffers[p] = P.twc[p];
   return smem_after_buffers;  // visible after the caller's next __syncthreads()
 }
 
@@ -567,17 +564,6 @@ __device__ __forceinline__ void stages_ct_impl(int s, In in, Out out, const doub
 template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int... Rs, class In, class Out>
 __device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1) {
   stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, 1, 0>(0, in, out, tw, buf0, buf1, std::integer_sequence<int, Rs...>{});
-}
-// the compact twiddle table of a plan: for stage s (stride Ns = product of the earlier radices) the Ns values
-// W_L^(k L / (Ns R_s)), k < Ns, back to back; gathered from the plan's full table.  Returns its length.
-__device__ __forceinline__ int stage_compact_twiddles(const FftPlan& P, double2* dst) {
-  int len = 0, ns = 1;
-  for (int s = 0; s < P.n_stage; ++s) {
-    len += ns;
-    ns *= P.radix[s];
-  }
-  for (int k = threadIdx.x; k < len; k += blockDim.x) dst[k] = P.twc[k];
-  return len;
 }
 struct CtRowsTileIn {
   WFM_NO_RUN_TWIDDLE
@@ -907,9 +893,7 @@ __global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_t
     for (int c = 0; c < rw; ++c) fft_bulk_g2s(h + (size_t)c * RS, Hp + (int64_t)(r0 + c) * N2, row_bytes, bar + 1);
   }
   const bool ct = WFM_FFT_CT && P.L == 640 && logc == 1;
-  const double2* tw = twp;
-  if (ct) stage_compact_twiddles(P, twp);
-  else tw = stage_twiddles(P, twp);
+  const double2* tw = stage_twiddles(P, twp);  // (the launch requires the table in shared memory)
   __syncthreads();  // the barriers are initialised (and the twiddles staged) for every thread
   fft_mbar_wait(bar, 0);
   fft_mbar_wait(bar + 1, 0);
@@ -1142,6 +1126,8 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
     ic = g_twc_cache.emplace(std::make_pair(dev, L), d).first;
   }
   plan->twc = ic->second;
+  plan->twc_len = 0;
+  for (int64_t s2 = 0, nsc = 1; s2 < plan->n_stage; nsc *= plan->radix[s2], ++s2) plan->twc_len += (int)nsc;
   return cudaSuccess;
 }
 
