@@ -80,7 +80,7 @@ constexpr int kFftColsThreads = WFM_FFT_COLS_THREADS;
 constexpr int kMaxPoints = 6144;  // complex points per shared-memory buffer (2 buffers = 192 KB)
 constexpr int kMaxStages = 20;
 constexpr int kSmemBudget = 227 * 1024 - 1024;
-constexpr int kPlanSlackBytes = 256;  // behind the buffers and the twiddle table: per-column inter-pass twiddles of a tile
+constexpr int kPlanSlackBytes = 1024;  // behind the buffers and the twiddle table: per-column inter-pass twiddles of a tile
 
 struct FftPlan {
   int L;
@@ -545,25 +545,33 @@ struct CtSmemOut {
 };
 // stages 0 .. S-1 of the radix pack; stage s reads `in` (s = 0) or the buffer stage s-1 wrote, and writes `out`
 // (s = S-1) or buf[s & 1]
-template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int NS, int TOFF, class In, class Out, int R0, int... Rest>
+struct CtNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `hook` runs once, after the first stage's butterflies and before its barrier: shared-memory stores placed there (tables
+// whose global loads were issued before the stage) are visible to every later stage at no extra barrier
+template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int NS, int TOFF, class In, class Out, class Hook, int R0, int... Rest>
 __device__ __forceinline__ void stages_ct_impl(int s, In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1,
-                                               std::integer_sequence<int, R0, Rest...>) {
+                                               Hook hook, std::integer_sequence<int, R0, Rest...>) {
   double2* dst = (s & 1) ? buf1 : buf0;
   if constexpr (sizeof...(Rest) == 0) {
     stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, out, tw);
+    hook();
     __syncthreads();
   } else {
     stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, CtSmemOut{dst}, tw);
+    hook();
     __syncthreads();
-    stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, NS * R0, TOFF + NS>(s + 1, CtSmemIn{dst}, out, tw, buf0, buf1,
+    stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, NS * R0, TOFF + NS>(s + 1, CtSmemIn{dst}, out, tw, buf0, buf1, CtNoHook{},
                                                          std::integer_sequence<int, Rest...>{});
   }
 }
 // same contract as smem_fft: `in` may read buf1, the last stage writes through `out` (last_stage_target is the buffer it
 // does not read)
-template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int... Rs, class In, class Out>
-__device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1) {
-  stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, 1, 0>(0, in, out, tw, buf0, buf1, std::integer_sequence<int, Rs...>{});
+template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int... Rs, class In, class Out, class Hook = CtNoHook>
+__device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1,
+                                            Hook hook = Hook{}) {
+  stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, 1, 0>(0, in, out, tw, buf0, buf1, hook, std::integer_sequence<int, Rs...>{});
 }
 struct CtRowsTileIn {
   WFM_NO_RUN_TWIDDLE
@@ -655,10 +663,21 @@ struct ColsOut {
   double sgn, scale;
   const double2* wsc;
   double nd, inv_n;
+  const double2* pre_w;  // compile-time path: this thread's run twiddle, fetched at kernel start (shared memory, [thread])
   int64_t nv;  // real output: samples kept (writes beyond are dropped)
   template <int R>
   __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
     if (!kTwAfter || c >= cw) return;
+    if (pre_w) {
+      double2 w = pre_w[threadIdx.x];
+      const double2 ws = pre_w[blockDim.x + c];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        v[q] = cmul(v[q], w);
+        if (q + 1 < R) w = cmul(w, ws);
+      }
+      return;
+    }
 #if WFM_FFT_COMPUTED_TW
     double2 w = computed_twiddle((int64_t)r0 * (c0 + c), nd, inv_n, sgn);
     const double2 ws = wsc[c];
@@ -692,7 +711,7 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + padded_points((size_t)N1 << logc);
-  const bool ct = WFM_FFT_CT && P.L == 625 && logc == 2 && (kTwAfter ? sgn < 0.0 : sgn > 0.0);
+  const bool ct = WFM_FFT_CT && P.L == 625 && logc == 2 && P.tw_in_smem && blockDim.x == 512 && (kTwAfter ? sgn < 0.0 : sgn > 0.0);
   // (the compile-time path reads the 10 KB table through L1 instead of staging it per tile: one barrier-bounded phase
   // less in a tile that lives for 8 us)
   const double2* tw = (ct && WFM_FFT_CT_GLOBAL_TW) ? P.tw : stage_twiddles(P, b + padded_points((size_t)N1 << logc));
@@ -728,12 +747,34 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     dst.pa = static_cast<double2*>(out) + sig * out_stride;
     dst.pb = nullptr;
   }
-  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n;
+  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n; dst.pre_w = nullptr;
   if (ct) {
-    // the filter's column passes on cfg4's grid: 625 = 5^4, four columns
-    const double2* tws = WFM_FFT_CT_COLS_COMPACT ? P.twc : (WFM_FFT_CT_GLOBAL_TW ? P.tw : (P.tw_in_smem ? b + padded_points((size_t)N1 << logc) : P.tw));
-    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, WFM_FFT_CT_COLS_COMPACT != 0, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
-                                                                      CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b);
+    // The filter's column passes on cfg4's grid: 625 = 5^4, four columns.  Every table value a thread will need is
+    // requested NOW, next to the first stage's own global loads, and parked in shared memory behind that stage's
+    // barrier: the compact stage twiddles (156 values) and, for the pass that applies the inter-pass twiddles at its
+    // END, this thread's W^(j col) with the four per-column steps W^(125 col).  (By source line 24 % of the stall
+    // samples of these passes were first uses of such look-ups, L1 misses behind the streaming signal.)
+    double2* tws = b + padded_points((size_t)N1 << logc);  // 156 compact twiddles, then blockDim + C run twiddles
+    double2* pre = tws + 160;
+    const int tid = (int)threadIdx.x;
+    double2 twv = make_double2(0.0, 0.0), wv = make_double2(0.0, 0.0);
+    if (tid < 156) twv = __ldg(P.twc + tid);
+    if (kTwAfter) {
+      // last stage (Ns = 125, radix 5): butterfly tid -> column tid & 3, first output row tid >> 2, step 125
+      const int c = tid & 3, j = tid >> 2;
+      if (tid < 500 && c < cw) wv = big_twiddle(T, (int64_t)j * (c0 + c), sgn);
+      else if (tid >= 508 && tid - 508 < cw) wv = big_twiddle(T, (int64_t)125 * (c0 + tid - 508), sgn);
+      dst.pre_w = pre;
+    }
+    auto park = [&]() {
+      if (tid < 156) tws[tid] = twv;
+      if (kTwAfter) {
+        if (tid < 500) pre[tid] = wv;
+        else if (tid >= 508) pre[kFftColsThreads + tid - 508] = wv;
+      }
+    };
+    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, true, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+                                                                     CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b, park);
     return;
   }
   smem_fft(P, logc, sgn, tw, src, dst, a, b);
