@@ -51,6 +51,9 @@ namespace wfm {
 #ifndef WFM_FFT_COMPUTED_TW
 #define WFM_FFT_COMPUTED_TW 0  // 1: inter-pass twiddles by sincospi instead of two table look-ups each (measured: L1TEX 63 -> 52 %, +11 % instructions, column passes 0.65 -> 0.68 ms: they are issue-bound, not L1TEX-bound)
 #endif
+#ifndef WFM_FFT_CT_COLS_640
+#define WFM_FFT_CT_COLS_640 1
+#endif
 #ifndef WFM_FFT_CT_GLOBAL_TW
 #define WFM_FFT_CT_GLOBAL_TW 1
 #endif
@@ -711,7 +714,8 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   const int N1 = P.L, C = 1 << logc;
   double2* a = reinterpret_cast<double2*>(fft_smem_raw);
   double2* b = a + padded_points((size_t)N1 << logc);
-  const bool ct = WFM_FFT_CT && P.L == 625 && logc == 2 && P.tw_in_smem && blockDim.x == 512 && (kTwAfter ? sgn < 0.0 : sgn > 0.0);
+  const bool ct = WFM_FFT_CT && (P.L == 625 || (WFM_FFT_CT_COLS_640 && P.L == 640)) && logc == 2 && P.tw_in_smem && blockDim.x == 512 &&
+                  (kTwAfter ? sgn < 0.0 : sgn > 0.0);
   // (the compile-time path reads the 10 KB table through L1 instead of staging it per tile: one barrier-bounded phase
   // less in a tile that lives for 8 us)
   const double2* tw = (ct && WFM_FFT_CT_GLOBAL_TW) ? P.tw : stage_twiddles(P, b + padded_points((size_t)N1 << logc));
@@ -749,31 +753,38 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   }
   dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n; dst.pre_w = nullptr;
   if (ct) {
-    // The filter's column passes on cfg4's grid: 625 = 5^4, four columns.  Every table value a thread will need is
-    // requested NOW, next to the first stage's own global loads, and parked in shared memory behind that stage's
-    // barrier: the compact stage twiddles (156 values) and, for the pass that applies the inter-pass twiddles at its
-    // END, this thread's W^(j col) with the four per-column steps W^(125 col).  (By source line 24 % of the stall
-    // samples of these passes were first uses of such look-ups, L1 misses behind the streaming signal.)
-    double2* tws = b + padded_points((size_t)N1 << logc);  // 156 compact twiddles, then blockDim + C run twiddles
+    // The filter's column passes on the grids of cfg4: 625 = 5^4 (reflection, n = 400 000) and 640 = 10 x 8 x 8 (the padded
+    // kernel convolution, n = 409 600), four columns.  Every table value a thread will need is requested NOW, next to
+    // the first stage's own global loads, and parked in shared memory behind that stage's barrier: the compact stage
+    // twiddles and, for the pass that applies the inter-pass twiddles at its END, this thread's W^(j col) with the four
+    // per-column steps W^(Ns col).  (By source line 24 % of the stall samples of these passes were first uses of such
+    // look-ups, L1 misses behind the streaming signal.)
+    double2* tws = b + padded_points((size_t)N1 << logc);  // compact twiddles (<= 160), then blockDim + C run twiddles
     double2* pre = tws + 160;
     const int tid = (int)threadIdx.x;
+    const bool l625 = P.L == 625;
+    const int n_tw = l625 ? 156 : 91, ns_last = l625 ? 125 : 80;  // last stage: radix 5 resp. 8, butterfly tid of ns_last * 4
     double2 twv = make_double2(0.0, 0.0), wv = make_double2(0.0, 0.0);
-    if (tid < 156) twv = __ldg(P.twc + tid);
+    if (tid < n_tw) twv = __ldg(P.twc + tid);
     if (kTwAfter) {
-      // last stage (Ns = 125, radix 5): butterfly tid -> column tid & 3, first output row tid >> 2, step 125
+      // last stage: butterfly tid -> column tid & 3, first output row tid >> 2 (< Ns), step Ns
       const int c = tid & 3, j = tid >> 2;
-      if (tid < 500 && c < cw) wv = big_twiddle(T, (int64_t)j * (c0 + c), sgn);
-      else if (tid >= 508 && tid - 508 < cw) wv = big_twiddle(T, (int64_t)125 * (c0 + tid - 508), sgn);
+      if (tid < 4 * ns_last && c < cw) wv = big_twiddle(T, (int64_t)j * (c0 + c), sgn);
+      else if (tid >= 508 && tid - 508 < cw) wv = big_twiddle(T, (int64_t)ns_last * (c0 + tid - 508), sgn);
       dst.pre_w = pre;
     }
     auto park = [&]() {
-      if (tid < 156) tws[tid] = twv;
+      if (tid < n_tw) tws[tid] = twv;
       if (kTwAfter) {
-        if (tid < 500) pre[tid] = wv;
+        if (tid < 4 * ns_last) pre[tid] = wv;
         else if (tid >= 508) pre[kFftColsThreads + tid - 508] = wv;
       }
     };
-    smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, true, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+    if (l625)
+      smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, true, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+                                                                       CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b, park);
+    else
+      smem_fft_ct<640, 2, kTwAfter, kFftColsThreads, true, 10, 8, 8>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
                                                                      CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b, park);
     return;
   }
