@@ -8,25 +8,29 @@
 // for ARBITRARY n (config 4: n = 400 000 = 2^7 * 5^5).
 //
 // Building block: `smem_fft` — C interleaved length-L transforms resident in
-// shared memory, mixed-radix Stockham autosort (radices 7,5,3,4,2), ping-pong
-// between two buffers, twiddles from a per-length table W_L^p computed on the
-// host in long double.
+// shared memory, mixed-radix Stockham autosort (radices 7,5,3,10,8,4,2), ping-pong
+// between two buffers.  Twiddles: ONE look-up per butterfly, W^k from a compact
+// per-stage table (host, long double), the powers W^(k r) formed in registers — the
+// row pass saturates the shared-memory pipe, not the FP64 pipe.  `smem_fft_ct` is the
+// same transform with the whole plan as template arguments (625 = 5^4 x 4 columns,
+// 640 = 10 x 8 x 8 x 2 rows / 4 columns: the tile shapes of cfg4).
 //
 //   n <= kMaxPoints, 7-smooth     one CTA per signal:
 //                                 load real -> FFT_n -> xH -> IFFT_n -> store real
 //   n = N1*N2 (both <= kMaxPoints, 7-smooth)   four-step, three kernels:
 //        A  column FFTs of length N1 (tiles of C columns), twiddle W_n^(n2 k1),
 //           real in -> complex scratch  [k1][n2]
-//        B  row FFT_N2 -> x H[k1 + N1 k2] -> row IFFT_N2, in place in scratch.
-//           The spectrum is never brought to natural order: H is permuted on
-//           the host instead, which saves two transposes.
+//        B  row FFT_N2 -> x H[k1 + N1 k2] -> row IFFT_N2, in place in scratch
+//           (fft_rows_tma_kernel: rows and response rows land by cp.async.bulk,
+//           leave by bulk stores).  The spectrum is never brought to natural order:
+//           H is permuted once instead, which saves two transposes.
 //        C  conj twiddle, column IFFT_N1, scale 1/n, real part -> output
 //   otherwise (a prime factor > 7)   Bluestein: chirp-z through 7-smooth
 //        transforms of length M >= 2n-1 (generic c2c path).
 //
-// HBM traffic of the fused path per sample: A 8+16, B 16+16, C 16+8 = 80 B
-// (two complex round trips of the scratch; SURVEY §8d counts 64 B for the
-// complex part).
+// Two real signals ride one complex transform (the response is made Hermitian), so
+// the HBM traffic of the fused path is 8+8 (A), 8+8 (B), 8+8 (C) = 48 B per real
+// sample (SURVEY 8d counts 16 B for an ideal single pass).
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -48,17 +52,8 @@ namespace wfm {
 #ifndef WFM_FFT_BIG_RADIX
 #define WFM_FFT_BIG_RADIX 1  // composite butterflies held in registers: 1 = 10 (2x5), 2 = also 25 (5x5)
 #endif
-#ifndef WFM_FFT_COMPUTED_TW
-#define WFM_FFT_COMPUTED_TW 0  // 1: inter-pass twiddles by sincospi instead of two table look-ups each (measured: L1TEX 63 -> 52 %, +11 % instructions, column passes 0.65 -> 0.68 ms: they are issue-bound, not L1TEX-bound)
-#endif
 #ifndef WFM_FFT_CT_COLS_640
 #define WFM_FFT_CT_COLS_640 1
-#endif
-#ifndef WFM_FFT_CT_GLOBAL_TW
-#define WFM_FFT_CT_GLOBAL_TW 1
-#endif
-#ifndef WFM_FFT_CT_COLS_COMPACT
-#define WFM_FFT_CT_COLS_COMPACT 1  // column passes: one coalesced W^k look-up per butterfly (through L1) + powers in registers
 #endif
 #ifndef WFM_FFT_CT
 #define WFM_FFT_CT 1  // compile-time plans for the tile shapes of cfg4 (625 x 4 columns, 640 x 2 rows)
@@ -90,11 +85,10 @@ struct FftPlan {
   int n_stage;
   int radix[kMaxStages];
   uint32_t inv_ns[kMaxStages];  // ceil(2^32 / Ns) of every stage: j / Ns = umulhi(j, inv) for j < 2^16
-  int tstep[kMaxStages];        // L / (Ns * R) of every stage: the stride of its twiddles in the table
-  const double2* tw;  // W_L^p = exp(-2 pi i p / L), p in [0, L)  (global memory)
   int twc_len;         // entries of twc: sum of the stage strides Ns
-  const double2* twc;  // compact per-stage table (global memory): for stage s the Ns values W_L^(k tstep[s]), k < Ns, back to back
-  int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers
+  const double2* twc;  // compact per-stage twiddle table (global memory): for stage s (stride Ns = product of the earlier
+                       // radices) the Ns values exp(-2 pi i k / (Ns R_s)), k < Ns, back to back; long double on the host
+  int tw_in_smem;     // the kernels stage the table in shared memory behind the two buffers (an area of L entries)
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -398,17 +392,6 @@ struct BigTwiddle {
   const double2* hi;  // W_n^(1024 h)
   const double2* lo;  // W_n^l, l < 1024
 };
-// W_n^m = exp(sgn * 2 pi i m / n), 0 <= m < n, computed: the look-ups above cost two scattered 16-byte loads per value
-// (up to 32 cache lines per warp request) in passes that L1TEX bounds, while the FP64 pipe runs at a quarter of its rate.
-// 2m/n to the last bit (one Newton step on the rounded reciprocal), then sincospi.
-__device__ __forceinline__ double2 computed_twiddle(int64_t m, double nd, double inv_n, double sgn) {
-  const double m2 = (double)(2 * m);
-  double q = m2 * inv_n;
-  q = fma(fma(-q, nd, m2), inv_n, q);
-  double sn, cs;
-  sincospi(q, &sn, &cs);
-  return make_double2(cs, sgn * sn);
-}
 __device__ __forceinline__ double2 big_twiddle(const BigTwiddle& T, int64_t m, double sgn) {
   double2 w = cmul(__ldg(T.hi + (m >> 10)), __ldg(T.lo + (m & 1023)));
   w.y *= -sgn;  // tables hold exp(-i ..): forward (sgn = -1) keeps it, inverse conjugates
@@ -472,10 +455,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_filter_single_kernel(FftPlan 
 // For the tile shapes that matter the whole plan is a template argument: element indices become immediate offsets, the
 // butterfly count per thread is a constant, j / Ns is a multiply-shift by a constant.  CtIn / CtOut accessors get the
 // point, the column and the element index e = (point << LOGC) + column.
-template <int R, int L, int LOGC, int NS, int TOFF, bool kFwd, int T, bool kCompactTw, class In, class Out>
+template <int R, int L, int LOGC, int NS, int TOFF, bool kFwd, int T, class In, class Out>
 __device__ __forceinline__ void stage_ct(In in, Out out, const double2* __restrict__ tw) {
   constexpr double sgn = kFwd ? -1.0 : 1.0;
-  constexpr int nb = L / R, nbC = nb << LOGC, NsC = NS << LOGC, tstep = L / (NS * R);
+  constexpr int nb = L / R, nbC = nb << LOGC, NsC = NS << LOGC;
   constexpr int iters = (nbC + T - 1) / T;
 #pragma unroll
   for (int it = 0; it < iters; ++it) {
@@ -488,18 +471,7 @@ __device__ __forceinline__ void stage_ct(In in, Out out, const double2* __restri
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = in(j + r * nb, c, jj + r * nbC);
     in.template twiddle_run<R>(v, j, nb, c);
-    if (!kCompactTw && NS > 1 && k > 0) {
-      // every W^(k r) from the full table (a length whose stage strides are odd multiples of 16 bytes — 625 — has no
-      // bank conflicts there, and the column passes are bound by instruction issue, not by shared memory)
-      const int kt = k * tstep;
-#pragma unroll
-      for (int r = 1; r < R; ++r) {
-        const double2 w = tw[r * kt];
-        v[r] = kFwd ? make_double2(fma(v[r].x, w.x, -v[r].y * w.y), fma(v[r].x, w.y, v[r].y * w.x))
-                    : make_double2(fma(v[r].x, w.x, v[r].y * w.y), fma(v[r].y, w.x, -v[r].x * w.y));
-      }
-    }
-    if (kCompactTw && NS > 1 && k > 0) {
+    if (NS > 1 && k > 0) {
       // ONE look-up per butterfly, W^k from the stage's own compact table (consecutive k: consecutive addresses, no bank
       // conflicts — in the full table a stage's twiddles are tstep * 16 bytes apart, a multiple of the 128-byte bank
       // period for the early stages); W^(k r) by products of depth <= 3.  The shared-memory pipe, not the FP64 pipe, is
@@ -553,28 +525,28 @@ struct CtNoHook {
 };
 // `hook` runs once, after the first stage's butterflies and before its barrier: shared-memory stores placed there (tables
 // whose global loads were issued before the stage) are visible to every later stage at no extra barrier
-template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int NS, int TOFF, class In, class Out, class Hook, int R0, int... Rest>
+template <int L, int LOGC, bool kFwd, int T, int NS, int TOFF, class In, class Out, class Hook, int R0, int... Rest>
 __device__ __forceinline__ void stages_ct_impl(int s, In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1,
                                                Hook hook, std::integer_sequence<int, R0, Rest...>) {
   double2* dst = (s & 1) ? buf1 : buf0;
   if constexpr (sizeof...(Rest) == 0) {
-    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, out, tw);
+    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T>(in, out, tw);
     hook();
     __syncthreads();
   } else {
-    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T, kCompactTw>(in, CtSmemOut{dst}, tw);
+    stage_ct<R0, L, LOGC, NS, TOFF, kFwd, T>(in, CtSmemOut{dst}, tw);
     hook();
     __syncthreads();
-    stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, NS * R0, TOFF + NS>(s + 1, CtSmemIn{dst}, out, tw, buf0, buf1, CtNoHook{},
+    stages_ct_impl<L, LOGC, kFwd, T, NS * R0, TOFF + NS>(s + 1, CtSmemIn{dst}, out, tw, buf0, buf1, CtNoHook{},
                                                          std::integer_sequence<int, Rest...>{});
   }
 }
 // same contract as smem_fft: `in` may read buf1, the last stage writes through `out` (last_stage_target is the buffer it
 // does not read)
-template <int L, int LOGC, bool kFwd, int T, bool kCompactTw, int... Rs, class In, class Out, class Hook = CtNoHook>
+template <int L, int LOGC, bool kFwd, int T, int... Rs, class In, class Out, class Hook = CtNoHook>
 __device__ __forceinline__ void smem_fft_ct(In in, Out out, const double2* __restrict__ tw, double2* buf0, double2* buf1,
                                             Hook hook = Hook{}) {
-  stages_ct_impl<L, LOGC, kFwd, T, kCompactTw, 1, 0>(0, in, out, tw, buf0, buf1, hook, std::integer_sequence<int, Rs...>{});
+  stages_ct_impl<L, LOGC, kFwd, T, 1, 0>(0, in, out, tw, buf0, buf1, hook, std::integer_sequence<int, Rs...>{});
 }
 struct CtRowsTileIn {
   WFM_NO_RUN_TWIDDLE
@@ -619,8 +591,6 @@ struct ColsIn {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn;
-  const double2* wsc;  // shared memory: W^(step (c0 + c)) per column
-  double nd, inv_n;
   int64_t nv;  // real input: samples the signals hold (zeros beyond)
   __device__ __forceinline__ double2 operator()(int r, int c) const {
     double2 v = make_double2(0.0, 0.0);
@@ -643,13 +613,10 @@ struct ColsIn {
   template <int R>
   __device__ __forceinline__ void twiddle_run(double2 (&v)[R], int r0, int step, int c) const {
     if (!kTwBefore || c >= cw) return;
-#if WFM_FFT_COMPUTED_TW
-    double2 w = computed_twiddle((int64_t)r0 * (c0 + c), nd, inv_n, sgn);
-    const double2 ws = wsc[c];  // W^(step col): one value per column of the tile, computed once per CTA
-#else
+    // (measured and rejected: sincospi instead of the two look-ups each — L1TEX 63 -> 52 %, but the longer dependent
+    // chain sits on the tile's critical path: 0.65 -> 0.68 ms per pass)
     double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
     const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
-#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       v[q] = cmul(v[q], w);
@@ -664,8 +631,6 @@ struct ColsOut {
   BigTwiddle T;
   int N2, c0, cw;
   double sgn, scale;
-  const double2* wsc;
-  double nd, inv_n;
   const double2* pre_w;  // compile-time path: this thread's run twiddle, fetched at kernel start (shared memory, [thread])
   int64_t nv;  // real output: samples kept (writes beyond are dropped)
   template <int R>
@@ -681,13 +646,8 @@ struct ColsOut {
       }
       return;
     }
-#if WFM_FFT_COMPUTED_TW
-    double2 w = computed_twiddle((int64_t)r0 * (c0 + c), nd, inv_n, sgn);
-    const double2 ws = wsc[c];
-#else
     double2 w = big_twiddle(T, (int64_t)r0 * (c0 + c), sgn);
     const double2 ws = big_twiddle(T, (int64_t)step * (c0 + c), sgn);
-#endif
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       v[q] = cmul(v[q], w);
@@ -716,9 +676,9 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
   double2* b = a + padded_points((size_t)N1 << logc);
   const bool ct = WFM_FFT_CT && (P.L == 625 || (WFM_FFT_CT_COLS_640 && P.L == 640)) && logc == 2 && P.tw_in_smem && blockDim.x == 512 &&
                   (kTwAfter ? sgn < 0.0 : sgn > 0.0);
-  // (the compile-time path reads the 10 KB table through L1 instead of staging it per tile: one barrier-bounded phase
-  // less in a tile that lives for 8 us)
-  const double2* tw = (ct && WFM_FFT_CT_GLOBAL_TW) ? P.tw : stage_twiddles(P, b + padded_points((size_t)N1 << logc));
+  // (the compile-time path parks its tables behind the first stage's barrier instead of staging them in a phase of
+  // their own: one barrier-bounded phase less in a tile that lives for 8 us)
+  const double2* tw = ct ? P.twc : stage_twiddles(P, b + padded_points((size_t)N1 << logc));
   const int c0 = blockIdx.x << logc;
   const int cw = min(C, N2 - c0);
   const int64_t sig = blockIdx.y;
@@ -731,18 +691,7 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     src.pa = static_cast<const double2*>(in) + sig * in_stride;
     src.pb = nullptr;
   }
-  // the step twiddle of the tile's columns: rows j, j + step, ... of column col differ by W^(step col)
-  double2* wsc = const_cast<double2*>(reinterpret_cast<const double2*>(fft_smem_raw)) + 2 * padded_points((size_t)N1 << logc) +
-                 (P.tw_in_smem ? P.L : 0);
-  const double nd = (double)N1 * (double)N2, inv_n = 1.0 / nd;
-#if WFM_FFT_COMPUTED_TW
-  if ((int)threadIdx.x < cw) {
-    const int step = kTwAfter ? P.L / P.radix[P.n_stage - 1] : P.L / P.radix[0];
-    wsc[threadIdx.x] = computed_twiddle((int64_t)step * (c0 + (int)threadIdx.x), nd, inv_n, sgn);
-  }
-  __syncthreads();
-#endif
-  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn; src.nv = nv; src.wsc = wsc; src.nd = nd; src.inv_n = inv_n;
+  src.T = T; src.N2 = N2; src.c0 = c0; src.cw = cw; src.sgn = sgn; src.nv = nv;
   ColsOut<kTwAfter, kRealOut> dst;
   if (kRealOut) {
     dst.pa = static_cast<double*>(out) + 2 * sig * out_stride;
@@ -751,7 +700,7 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
     dst.pa = static_cast<double2*>(out) + sig * out_stride;
     dst.pb = nullptr;
   }
-  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.wsc = wsc; dst.nd = nd; dst.inv_n = inv_n; dst.pre_w = nullptr;
+  dst.T = T; dst.N2 = N2; dst.c0 = c0; dst.cw = cw; dst.sgn = sgn; dst.scale = scale; dst.nv = nv; dst.pre_w = nullptr;
   if (ct) {
     // The filter's column passes on the grids of cfg4: 625 = 5^4 (reflection, n = 400 000) and 640 = 10 x 8 x 8 (the padded
     // kernel convolution, n = 409 600), four columns.  Every table value a thread will need is requested NOW, next to
@@ -781,10 +730,10 @@ __global__ void __launch_bounds__(kFftColsThreads, WFM_FFT_COLS_MINB) fft_cols_k
       }
     };
     if (l625)
-      smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, true, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+      smem_fft_ct<625, 2, kTwAfter, kFftColsThreads, 5, 5, 5, 5>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
                                                                        CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b, park);
     else
-      smem_fft_ct<640, 2, kTwAfter, kFftColsThreads, true, 10, 8, 8>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
+      smem_fft_ct<640, 2, kTwAfter, kFftColsThreads, 10, 8, 8>(CtWrapIn<ColsIn<!kTwAfter, kRealIn>>{src},
                                                                      CtWrapOut<ColsOut<kTwAfter, kRealOut>>{dst}, tws, a, b, park);
     return;
   }
@@ -954,8 +903,8 @@ __global__ void __launch_bounds__(kFftRowsThreads, WFM_FFT_ROWS_MINB) fft_rows_t
   double2* o = b;
   if (ct) {
     // 640 = 10 x 8 x 8, two rows: b -> a -> b -> (x H) a;  a -> b -> a -> b
-    smem_fft_ct<640, 1, true, kFftRowsThreads, true, 10, 8, 8>(CtRowsTileIn{b, 640 + kRowPad}, CtRowsTileMulHOut{a, h, 640 + kRowPad}, twp, a, b);
-    smem_fft_ct<640, 1, false, kFftRowsThreads, true, 10, 8, 8>(CtSmemIn{a}, CtRowsTileOut{b, 640 + kRowPad}, twp, b, a);
+    smem_fft_ct<640, 1, true, kFftRowsThreads, 10, 8, 8>(CtRowsTileIn{b, 640 + kRowPad}, CtRowsTileMulHOut{a, h, 640 + kRowPad}, twp, a, b);
+    smem_fft_ct<640, 1, false, kFftRowsThreads, 10, 8, 8>(CtSmemIn{a}, CtRowsTileOut{b, 640 + kRowPad}, twp, b, a);
   } else {
     // (either buffer may end up holding the padded output rows: both have room for them)
     double2* z = last_stage_target(P, a, b);
@@ -1115,7 +1064,6 @@ static bool is_smooth(int64_t n) {
 }
 
 static std::mutex g_tw_mutex;
-static std::map<std::pair<int, int>, double2*> g_tw_cache;              // (device, L) -> table
 static std::map<std::pair<int, int>, double2*> g_twc_cache;             // (device, L) -> compact per-stage table
 static std::map<std::pair<int, int64_t>, BigTwiddle> g_big_tw_cache;     // (device, n) -> inter-pass tables
 
@@ -1137,7 +1085,6 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
   int64_t ns = 1;
   for (int s = 0; s < plan->n_stage; ++s) {
     plan->inv_ns[s] = (uint32_t)(((uint64_t(1) << 32) + ns - 1) / ns);  // exact quotient for j < 2^16
-    plan->tstep[s] = (int)(L / (ns * plan->radix[s]));
     ns *= plan->radix[s];
   }
   const size_t buffers = 2 * sizeof(double2) * padded_points((size_t)points) + kPlanSlackBytes;
@@ -1147,19 +1094,6 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   std::lock_guard<std::mutex> lock(g_tw_mutex);
-  auto it = g_tw_cache.find({dev, L});
-  if (it == g_tw_cache.end()) {
-    std::vector<double2> host((size_t)L);
-    const long double two_pi = 6.283185307179586476925286766559L;
-    for (int p = 0; p < L; ++p) {
-      long double ang = two_pi * (long double)p / (long double)L;
-      host[p] = make_double2((double)cosl(ang), (double)-sinl(ang));
-    }
-    double2* d = nullptr;
-    if ((e = upload_table(host, &d)) != cudaSuccess) return e;
-    it = g_tw_cache.emplace(std::make_pair(dev, L), d).first;
-  }
-  plan->tw = it->second;
   auto ic = g_twc_cache.find({dev, L});
   if (ic == g_twc_cache.end()) {
     std::vector<double2> host;
@@ -1167,7 +1101,8 @@ static cudaError_t get_plan(int L, int64_t points, FftPlan* plan, size_t* smem) 
     int64_t nsc = 1;
     for (int s = 0; s < plan->n_stage; ++s) {
       for (int64_t k = 0; k < nsc; ++k) {
-        long double ang = two_pi * (long double)(k * plan->tstep[s]) / (long double)L;
+        // W_L^(k L / (Ns R_s)) = exp(-2 pi i k / (Ns R_s))
+        long double ang = two_pi * (long double)k / (long double)(nsc * plan->radix[s]);
         host.push_back(make_double2((double)cosl(ang), (double)-sinl(ang)));
       }
       nsc *= plan->radix[s];
