@@ -149,3 +149,26 @@ def test_roundtrips_keep_filters():
     assert np.array_equal(w2.filters[0], w.filters[0]) and w2.filters[1] == 0
     w3 = Waveform.fromtree(w.totree())
     assert w3.bounds == w.bounds and w3.seq == w.seq and w3.sample_rate == 1000
+
+
+def test_padded_fft_length_is_chosen_by_cost():
+    """distortion.dsp_next_fast_len: a 7-smooth length >= m within 5 % of the smallest one, the cheapest for the device's
+    plans (radix sequence and two-level split mirrored from csrc/wfm_fft.cu)."""
+    from waveforms_b200 import distortion as D
+
+    def smooth(v):
+        for r in (2, 3, 5, 7):
+            while v % r == 0:
+                v //= r
+        return v == 1
+    for m in (1, 2, 97, 1000, 4097, 6145, 20000, 123457, 401799, 1000003):
+        n = D.dsp_next_fast_len(m)
+        least = m
+        while not smooth(least):
+            least += 1
+        assert n >= m and smooth(n) and n <= least * 1.05 + 1
+        assert D._fft_cost(n) <= D._fft_cost(least)
+    # cfg4's kernel convolution: 400 000 samples + 1800 taps
+    assert D.dsp_next_fast_len(400000 + 1800 - 1) == 409600          # 640 x 640, not 403 200 = 630 x 640
+    assert D._fft_radices(640) == [10, 8, 8] and D._fft_radices(625) == [5, 5, 5, 5] and D._fft_radices(630) == [10, 7, 3, 3]
+    assert D._fft_radices(11) is None and D._fft_cost(2 ** 26) == float('inf')  # no split with both factors <= 6144
