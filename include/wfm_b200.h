@@ -269,6 +269,14 @@ int  wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na,
                  const double* x, double* y, int64_t n_sig, int64_t n,
                  int64_t stride, const double* zi, double* zf, void* stream);
 
+/* The same with a mode: WFM_IIR_EXACT = wfm_lfilter; WFM_IIR_SCAN = block-parallel (orders 1..4: the DF2T state is a
+ * linear system, carries by M x M matrix powers, the samples themselves by scipy's own recurrence from the carried-in
+ * state) — equal to the sequential result up to the filter's rounding-noise gain, at the cost of a read and a write
+ * (cfg4: 13.4 ms -> 0.3 ms).  Orders above 4 run the sequential kernel whatever the mode. */
+int  wfm_lfilter_mode(const double* b, int32_t nb, const double* a, int32_t na,
+                      const double* x, double* y, int64_t n_sig, int64_t n,
+                      int64_t stride, const double* zi, double* zf, int32_t mode, void* stream);
+
 /* y = real(ifft(fft(x) * H)) per signal, H given on the np.fft.fftfreq grid as
  * HOST interleaved complex [n]; arbitrary n.  x, y DEVICE f64 (may alias; signal s
  * of y starts at y + s*stride).  Only the Hermitian part of H contributes to the

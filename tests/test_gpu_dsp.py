@@ -205,3 +205,65 @@ def test_cfg4_pipeline_full_size_properties():
     xr = dx - (dx @ alt)[:, None] / n * alt
     back = D.correct_reflection(D.reflection(xr.clone(), 0.05, 13.3e-9, rate), 0.05, 13.3e-9, rate)
     assert float((back - xr).abs().max()) <= 1e-12 * float(xr.abs().max())
+
+
+# -- lfilter, block-parallel (wfm_lfilter_mode WFM_IIR_SCAN: predistort's combined filter) ---------------------------
+@pytest.mark.parametrize('order', [1, 2, 3, 4])
+@pytest.mark.parametrize('n', [1, 15, 16, 17, 4095, 4096, 4097, 12289, 50000])
+def test_lfilter_scan_well_conditioned(order, n):
+    """Butterworth polynomials (poles well inside the unit circle): the scan equals scipy.signal.lfilter to 1e-12,
+    with and without an initial state, final state included; ragged lengths put the signal's end anywhere in a
+    thread's chunk."""
+    from waveforms_b200.dsp import lfilter_device
+    rng = np.random.default_rng(100 * order + n)
+    b, a = butter(order, 0.2)
+    x = rng.standard_normal((3, n))
+    y, _ = lfilter_device(b, a, _dev(x), mode='scan')
+    assert rel_err(y.cpu().numpy(), lfilter(b, a, x, axis=-1)) <= FP64_TOL
+    zi = rng.standard_normal((3, order))
+    want = [lfilter(b, a, x[k], zi=zi[k]) for k in range(3)]
+    y, zf = lfilter_device(b, a, _dev(x), zi=zi, want_zf=True, mode='scan')
+    assert rel_err(y.cpu().numpy(), np.stack([w[0] for w in want])) <= FP64_TOL
+    assert np.max(np.abs(zf - np.stack([w[1] for w in want]))) <= 1e-12 * max(1.0, np.max(np.abs(zf)))
+
+
+def test_lfilter_scan_on_unaligned_rows_and_high_orders():
+    from waveforms_b200.dsp import lfilter_device
+    import torch
+    rng = np.random.default_rng(77)
+    b, a = butter(3, 0.3)
+    base = torch.from_numpy(rng.standard_normal(3 * 5001 + 1)).cuda()
+    x = base[1:].view(3, 5001)          # rows start on odd elements: the 8-byte access path
+    want = lfilter(b, a, x.cpu().numpy(), axis=-1)
+    y, _ = lfilter_device(b, a, x, mode='scan')
+    assert rel_err(y.cpu().numpy(), want) <= FP64_TOL
+    b6, a6 = butter(6, 0.25)             # order 6: no scan kernel, the sequential one answers (bit-identical)
+    x6 = rng.standard_normal((2, 3000))
+    y6, _ = lfilter_device(b6, a6, _dev(x6), mode='scan')
+    assert np.array_equal(y6.cpu().numpy(), lfilter(b6, a6, x6, axis=-1))
+
+
+def test_predistort_scan_is_as_accurate_as_scipy():
+    """predistort(filters=[two exponential decays]) on a 400 000-sample flux signal: the combined order-2 filter has its
+    poles at 0.995 / 0.998, SciPy's own float64 result sits ~1e-11 from the long-double truth (oracle/csrc/
+    ld_filters.c).  The scan must be no further from the truth than 1.5 x SciPy, the exact mode must BE SciPy."""
+    from oracle.build_c import lfilter_ld
+    from waveforms_b200 import distortion as D
+    rng = np.random.default_rng(13)
+    filters = [D.exp_decay_filter(-0.03, 0.1e-6, 2e9), D.exp_decay_filter(0.02, 0.3e-6, 2e9)]
+    b, a = D.combine_filters(filters)
+    for n in (60000, 400000):
+        x = np.zeros(n)
+        for _ in range(12):
+            lo, hi = sorted(rng.integers(0, n, 2))
+            x[lo:hi] += rng.uniform(-0.5, 0.5)
+        zi = lfiltic(b, a, np.full(len(a) - 1, 0.1), np.full(len(b) - 1, 0.1))
+        ref, ref_zf = lfilter(b, a, x, zi=zi)
+        truth = lfilter_ld(b, a, x, zi=zi)
+        got, zf = D.predistort(x, filters, initial=0.1, return_zf=True, iir_mode='scan')
+        err_scan, err_scipy = rel_err(got, truth), rel_err(ref, truth)
+        assert err_scan <= 1.5 * err_scipy + 1e-12, (err_scan, err_scipy)
+        assert rel_err(got, ref) <= 2.5 * err_scipy + 1e-12
+        assert np.max(np.abs(zf - ref_zf)) <= (2.5 * err_scipy + 1e-12) * max(1.0, np.max(np.abs(ref)))
+        exact, zfe = D.predistort(x, filters, initial=0.1, return_zf=True)
+        assert np.array_equal(exact, ref) and np.array_equal(zfe, ref_zf)

@@ -81,6 +81,9 @@ def main():
     w2 = work.clone()
     add('K2b lfilter exact (order %d)' % (max(len(a), len(b)) - 1), timed(lambda: dsp.lfilter_device(b, a, w2)), tot, 16,
         'bit-identical to scipy.signal.lfilter')
+    w3 = work.clone()
+    add('K2b lfilter scan (order %d)' % (max(len(a), len(b)) - 1), timed(lambda: dsp.lfilter_device(b, a, w3, mode='scan')), tot, 16,
+        "block-parallel: predistort(iir_mode='scan')")
     add('K3 fft_filter n=400000 (correct_reflection)', timed(lambda: dsp.fft_filter_device(work, Hinv, out=out)), tot, 16,
         'four-step Stockham, H applied between the passes')
     pad[:, :n] = work

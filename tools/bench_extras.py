@@ -353,6 +353,12 @@ def pipeline_cfg4(ns, torch, engine, peak, quick=False):
           'bit-identical to scipy.signal.sosfilt', 2)
     stage('K3 correct_reflection', lambda: D.correct_reflection(work, 0.05, 13.3e-9, rate, out=out_r), 16,
           'n = 400 000 = 625 x 640 four-step FFT; 16 B/sample is the SURVEY floor, the kernel moves 48')
+    pfilters = [D.exp_decay_filter(-0.03, 0.1e-6, rate), D.exp_decay_filter(0.02, 0.3e-6, rate)]
+    pwork = out_r.clone()
+    stage('K2b predistort(filters) scan', lambda: D.predistort(pwork, pfilters, iir_mode='scan'), 16,
+          "lfilter of the combined order-2 filter (distortion.py:300-321), block-parallel; predistort(iir_mode='scan')", 3)
+    stage('K2b predistort(filters) exact', lambda: D.predistort(pwork, pfilters), 16,
+          'the same, sequential kernel: bit-identical to scipy.signal.lfilter (the default)', 2)
     stage('K3 predistort(ker)', lambda: D.predistort(out_r, ker=ker), 16,
           'centred linear convolution with the %d-tap zDistortKernel through a padded 7-smooth FFT' % len(ker), 3)
 
@@ -397,11 +403,26 @@ def pipeline_cfg4(ns, torch, engine, peak, quick=False):
                            'the same DF2T recurrence in x87 long double (oracle/csrc/ld_filters.c).  SciPy\'s own float64 '
                            'result is this far from the exact filter output: 1e-12 against SciPy is not a meaningful bar for '
                            'this filter, the scan is held to "no further from the truth than SciPy"'}
+    # predistort's IIR on one full-size channel: exact mode = SciPy bit for bit, scan mode against the long-double truth
+    from oracle.build_c import lfilter_ld
+    from scipy.signal import lfilter, lfiltic
+    pb, pa = D.combine_filters(pfilters)
+    x0 = sig2[0].cpu().numpy()
+    pzi = lfiltic(pb, pa, np.zeros(len(pa) - 1), np.zeros(len(pb) - 1))
+    p_ref = lfilter(pb, pa, x0, zi=pzi)[0]
+    p_truth = lfilter_ld(pb, pa, x0, zi=pzi)
+    p_scan = D.predistort(sig2[0].clone(), pfilters, iir_mode='scan').cpu().numpy()
+    p_exact = D.predistort(sig2[0].clone(), pfilters).cpu().numpy()
+    iir['predistort_filters'] = {'err_scan_vs_long_double': rel_err(p_scan, p_truth), 'err_scipy_vs_long_double': rel_err(p_ref, p_truth),
+                                 'err_scan_vs_scipy': rel_err(p_scan, p_ref), 'exact_bits': bool(np.array_equal(p_exact, p_ref))}
+    worst['predistort_iir_exact_bits'] = iir['predistort_filters']['exact_bits']
     iir_tol = 1.5 * iir['err_scipy_vs_long_double'] + 1e-12
     tol = {'sample': FP64_TOL, 'correct_reflection_stage': FP64_TOL, 'predistort_ker_stage': FP64_TOL}
     res['parity'] = {'max_rel_err': worst, 'n_checked': 2, 'tol': dict(tol, sosfilt_scan_vs_long_double=iir_tol),
                      'ok': bool(all(worst[k] <= tol[k] for k in tol) and worst['sosfilt_exact_bits']
-                                and iir['err_scan_vs_long_double'] <= iir_tol),
+                                and iir['err_scan_vs_long_double'] <= iir_tol and worst['predistort_iir_exact_bits']
+                                and iir['predistort_filters']['err_scan_vs_long_double']
+                                <= 1.5 * iir['predistort_filters']['err_scipy_vs_long_double'] + 1e-12),
                      'note': 'sample / FFT stages: 1e-12 against the CPU stage on the same input; IIR: exact mode bit-identical to '
                              'scipy.signal.sosfilt, scan mode no further from the long-double truth than 1.5 x SciPy (iir_error)'}
     res['iir_error'] = iir

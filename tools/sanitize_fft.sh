@@ -8,7 +8,7 @@ mkdir -p $o
 for tool in memcheck racecheck synccheck; do
   echo "== compute-sanitizer --tool $tool" >> $o/${tag}_sanitizer_fft.txt
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_fft.py tests/test_gpu_dsp.py tests/test_builder.py tests/test_gpu_parity.py -m gpu -q -x \
-      -k "fft or reflection or predistort or kernel or compact or fast_create or four_step or two_level or padded" 2>&1 \
+      -k "fft or reflection or predistort or kernel or compact or fast_create or four_step or two_level or padded or lfilter" 2>&1 \
     | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Invalid|hazard|Error" | tail -12 >> $o/${tag}_sanitizer_fft.txt
 done
 cat $o/${tag}_sanitizer_fft.txt

@@ -665,6 +665,198 @@ __global__ void __launch_bounds__(32 * kExactWarps) lfilter_exact_kernel(const _
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// lfilter, block-parallel (orders 1..4): the DF2T recurrence above is a linear system on its M state words,
+// z' = A z + g x with A[i][0] = -a[i+1], A[i][i+1] = 1, so the machinery of the joint sosfilt scan applies unchanged:
+//   pass a: every thread runs its 16 samples from the zero state in the state-space form
+//           z_i' = -a_{i+1} z_0 + (z_{i+1} + c_{i+1} x), c_j = b_j - a_j b_0 (one FMA per step on the critical path);
+//   scan  : carries with M x M powers of A^16 (host, long double);
+//   pass c: scipy's own recurrence (lfilter_step: same operations, same association) from the carried-in state.
+// predistort() (distortion.py:289-337) filters every flux channel with ONE combined high-order (b, a): the sequential
+// kernel needs 13.4 ms for cfg4's 256 x 400 000 samples, this one the time of a read and a write.
+// ---------------------------------------------------------------------------
+struct LfScanParams {
+  double b[kMaxJoint + 1], a[kMaxJoint + 1], c[kMaxJoint + 1];  // normalised by a[0]; c[j] = b[j] - a[j] b[0]
+};
+template <int M>
+__device__ __forceinline__ double lfilter_step_scan(const LfScanParams& P, double xv, double (&z)[M]) {
+  const double yv = add(z[0], mul(P.b[0], xv));
+#pragma unroll
+  for (int k = 0; k < M - 1; ++k) z[k] = sub(add(z[k + 1], mul(xv, P.b[k + 1])), mul(yv, P.a[k + 1]));
+  z[M - 1] = sub(mul(xv, P.b[M]), mul(yv, P.a[M]));
+  return yv;
+}
+template <int M, bool kAligned>
+__global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) lfilter_scan_kernel(
+    const __grid_constant__ LfScanParams P, const __grid_constant__ IirJointTables TT, const double* __restrict__ x, double* y,
+    int64_t n, int64_t stride, const double* __restrict__ zi, double* __restrict__ zf) {
+  constexpr int D = M;
+  double* s_buf0 = reinterpret_cast<double*>(iir_smem);
+  double* s_buf1 = reinterpret_cast<double*>(iir_smem + kJointTileBytes);
+  __shared__ double s_lane[D * D][32];  // (A^16)^lane, entry-major: conflict-free
+  __shared__ double s_tot[kIirThreads / 32][D];
+  __shared__ double s_carry[D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t sig = blockIdx.x;
+  const double* __restrict__ xs = x + sig * stride;
+  double* ys = y + sig * stride;
+  for (int e = tid; e < D * D * 32; e += kIirThreads) s_lane[e / 32][e % 32] = TT.lane[e % 32][(e / 32) / D * kMaxJoint + (e / 32) % D];
+  if (tid < D) s_carry[tid] = zi ? zi[sig * D + tid] : 0.0;
+
+  auto load_tile = [&](double* buf, int64_t base) {
+    const int cnt = (int)min((int64_t)kIirTile, n - base);
+#pragma unroll
+    for (int j = 0; j < kIirT / 2; ++j) {
+      const int c = j * kIirThreads + tid;
+      double* dst = buf + (c >> 3) * kJointPitch + 2 * (c & 7);
+      if (kAligned) {
+        const int left = cnt - 2 * c;
+        cp_async16_zfill(dst, left > 0 ? xs + base + 2 * c : xs + base, left >= 2 ? 16 : (left == 1 ? 8 : 0));
+      } else {
+        dst[0] = 2 * c < cnt ? xs[base + 2 * c] : 0.0;
+        dst[1] = 2 * c + 1 < cnt ? xs[base + 2 * c + 1] : 0.0;
+      }
+    }
+  };
+  if (n > 0) load_tile(s_buf0, 0);
+  if (kAligned) cp_async_commit();
+  __syncthreads();
+
+  int it = 0;
+  for (int64_t base = 0; base < n; base += kIirTile, ++it) {
+    const int cnt = (int)min((int64_t)kIirTile, n - base);
+    double* buf = (it & 1) ? s_buf1 : s_buf0;
+    if (base + kIirTile < n) load_tile((it & 1) ? s_buf0 : s_buf1, base + kIirTile);
+    if (kAligned) {
+      cp_async_commit();
+      cp_async_wait<1>();
+    }
+    __syncthreads();
+    double v[kIirT];
+    {
+      const double2* row = reinterpret_cast<const double2*>(buf + tid * kJointPitch);
+#pragma unroll
+      for (int k = 0; k < kIirT / 2; ++k) {
+        const double2 d = row[k];
+        v[2 * k] = d.x;
+        v[2 * k + 1] = d.y;
+      }
+    }
+    const int valid = max(0, min(kIirT, cnt - tid * kIirT));
+    double carry[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) carry[i] = s_carry[i];
+    // ---- pass a: end state of my chunk from the zero state (thread 0: from the tile's carry-in)
+    double f[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) f[i] = tid == 0 ? carry[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < kIirT; ++k) {
+      const double in = v[k], z0 = f[0];
+#pragma unroll
+      for (int i = 0; i < D - 1; ++i) f[i] = fma(-P.a[i + 1], z0, fma(P.c[i + 1], in, f[i + 1]));
+      f[D - 1] = fma(-P.a[D], z0, P.c[D] * in);
+    }
+    // ---- scan over the threads
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      double p[D], r[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) p[i] = __shfl_up_sync(0xffffffffu, f[i], 1 << d);
+      if (lane >= (1 << d)) {
+        double m[D * D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) m[i * D + j] = TT.lvl[d][i * kMaxJoint + j];
+        matvec_d<D>(m, p, r);
+#pragma unroll
+        for (int i = 0; i < D; ++i) f[i] += r[i];
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_tot[warp][i] = f[i];
+    }
+    double e[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      e[i] = __shfl_up_sync(0xffffffffu, f[i], 1);
+      if (lane == 0) e[i] = 0.0;
+    }
+    __syncthreads();
+    if (warp > 0) {
+      double w[D], r[D], mq[D * D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) mq[i * D + j] = TT.warp[i * kMaxJoint + j];
+      for (int k = 0; k < warp; ++k) {
+        matvec_d<D>(mq, w, r);
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = r[i] + s_tot[k][i];
+      }
+      double ml[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) ml[i] = s_lane[i][lane];
+      matvec_d<D>(ml, w, r);
+#pragma unroll
+      for (int i = 0; i < D; ++i) e[i] += r[i];
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) e[i] = carry[i];
+    }
+    // ---- pass c: scipy's recurrence from the carried-in state
+    double z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = e[i];
+    const bool tail_here = valid < kIirT && tid * kIirT + valid == cnt;  // the signal ends inside my chunk
+    double fin[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) fin[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < kIirT; ++k) {
+      if (tail_here && k == valid) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) fin[i] = z[i];
+      }
+      v[k] = lfilter_step_scan<M>(P, v[k], z);
+    }
+    {
+      double2* row = reinterpret_cast<double2*>(buf + tid * kJointPitch);
+#pragma unroll
+      for (int k = 0; k < kIirT / 2; ++k) row[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    }
+    __syncthreads();
+    if (tail_here) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_carry[i] = fin[i];
+    }
+    if (cnt == kIirTile && tid == kIirThreads - 1) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) s_carry[i] = z[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kIirT / 2; ++j) {
+      const int c = j * kIirThreads + tid;
+      const double2 d = *reinterpret_cast<const double2*>(buf + (c >> 3) * kJointPitch + 2 * (c & 7));
+      if (kAligned && 2 * c + 1 < cnt) {
+        *reinterpret_cast<double2*>(ys + base + 2 * c) = d;
+      } else {
+        if (2 * c < cnt) ys[base + 2 * c] = d.x;
+        if (2 * c + 1 < cnt) ys[base + 2 * c + 1] = d.y;
+      }
+    }
+    __syncthreads();
+  }
+  if (kAligned) cp_async_wait<0>();
+  if (zf && tid < D) zf[sig * D + tid] = s_carry[tid];
+}
+
 // host: 2x2 matrix powers in long double
 struct M2 {
   long double a, b, c, d;
@@ -708,6 +900,22 @@ static void md_put(double* dst, const MD& a) {
   for (int i = 0; i < kMaxJoint; ++i)
     for (int j = 0; j < kMaxJoint; ++j) dst[i * kMaxJoint + j] = (double)a.m[i][j];
 }
+// (M^16)^l per lane, (M^16)^(2^d) per scan level, (M^16)^32 per warp
+static void power_tables(const MD& M, int D, IirJointTables* tab) {
+  MD MT = md_identity(D);
+  for (int i = 0; i < kIirT; ++i) MT = md_mul(MT, M, D);
+  MD pw = md_identity(D);
+  for (int l = 0; l < 32; ++l) {
+    md_put(tab->lane[l], pw);
+    pw = md_mul(pw, MT, D);
+  }
+  md_put(tab->warp, pw);
+  MD sq = MT;
+  for (int d = 0; d < 5; ++d) {
+    md_put(tab->lvl[d], sq);
+    sq = md_mul(sq, sq, D);
+  }
+}
 // homogeneous one-step matrix of the cascade: section k's input is y_{k-1} = z0_{k-1} + b0_{k-1} x_{k-1}
 static void joint_tables(const IirParams& P, IirJointTables* tab) {
   const int S = P.n_sections, D = 2 * S;
@@ -728,19 +936,16 @@ static void joint_tables(const IirParams& P, IirJointTables* tab) {
       gain *= P.sec[j].b0;
     }
   }
-  MD MT = md_identity(D);
-  for (int i = 0; i < kIirT; ++i) MT = md_mul(MT, M, D);
-  MD pw = md_identity(D);
-  for (int l = 0; l < 32; ++l) {
-    md_put(tab->lane[l], pw);
-    pw = md_mul(pw, MT, D);
+  power_tables(M, D, tab);
+}
+// one-step matrix of lfilter's DF2T state (order Mo): z_i' = -a_{i+1} z_0 + z_{i+1}
+static void lfilter_tables(const LfScanParams& P, int Mo, IirJointTables* tab) {
+  MD M{};
+  for (int i = 0; i < Mo; ++i) {
+    M.m[i][0] = -(long double)P.a[i + 1];
+    if (i + 1 < Mo) M.m[i][i + 1] = 1;
   }
-  md_put(tab->warp, pw);
-  MD sq = MT;
-  for (int d = 0; d < 5; ++d) {
-    md_put(tab->lvl[d], sq);
-    sq = md_mul(sq, sq, D);
-  }
+  power_tables(M, Mo, tab);
 }
 
 }  // namespace wfm
@@ -830,7 +1035,14 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
 
 extern "C" int wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t na, const double* x, double* y,
                            int64_t n_sig, int64_t n, int64_t stride, const double* zi, double* zf, void* stream) {
+  return wfm_lfilter_mode(b, nb, a, na, x, y, n_sig, n, stride, zi, zf, WFM_IIR_EXACT, stream);
+}
+
+extern "C" int wfm_lfilter_mode(const double* b, int32_t nb, const double* a, int32_t na, const double* x, double* y,
+                                int64_t n_sig, int64_t n, int64_t stride, const double* zi, double* zf, int32_t mode,
+                                void* stream) {
   using namespace wfm;
+  if (mode != WFM_IIR_EXACT && mode != WFM_IIR_SCAN) return WFM_EINVAL;
   if (!b || !a || nb < 1 || na < 1 || a[0] == 0.0 || n_sig < 0 || n < 0 || (n_sig > 1 && stride < n)) return WFM_EINVAL;
   const int M = std::max(nb, na) - 1;
   if (M > kMaxOrder) return WFM_EUNSUPPORTED;
@@ -851,7 +1063,31 @@ extern "C" int wfm_lfilter(const double* b, int32_t nb, const double* a, int32_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, sizeof(double) * M * n_sig, cudaMemcpyHostToDevice, st);
   }
   if (e == cudaSuccess && zf && M > 0) e = cudaMallocAsync(&d_zf, state_bytes, st);
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && mode == WFM_IIR_SCAN && M >= 1 && M <= kMaxJoint && n > 0) {
+    LfScanParams S{};
+    for (int k = 0; k <= M; ++k) {
+      S.b[k] = P.b[k];
+      S.a[k] = P.a[k];
+      S.c[k] = (double)((long double)P.b[k] - (long double)P.a[k] * (long double)P.b[0]);
+    }
+    static thread_local IirJointTables jt;
+    lfilter_tables(S, M, &jt);
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (stride % 2 == 0 || n_sig == 1);
+    const size_t smem = 2 * (size_t)kJointTileBytes;
+    auto launch = [&](auto kern) {
+      cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ee != cudaSuccess) return ee;
+      kern<<<(unsigned)n_sig, kIirThreads, smem, st>>>(S, jt, x, y, n, stride, d_zi, d_zf);
+      return cudaGetLastError();
+    };
+    switch (M) {
+      case 1: e = aligned ? launch(lfilter_scan_kernel<1, true>) : launch(lfilter_scan_kernel<1, false>); break;
+      case 2: e = aligned ? launch(lfilter_scan_kernel<2, true>) : launch(lfilter_scan_kernel<2, false>); break;
+      case 3: e = aligned ? launch(lfilter_scan_kernel<3, true>) : launch(lfilter_scan_kernel<3, false>); break;
+      default: e = aligned ? launch(lfilter_scan_kernel<4, true>) : launch(lfilter_scan_kernel<4, false>); break;
+    }
+  } else if (e == cudaSuccess) {
+    // (orders above 4, order 0 and empty signals: the sequential kernel, whatever the mode)
     lfilter_exact_kernel<<<(unsigned)((n_sig + kExactWarps - 1) / kExactWarps), 32 * kExactWarps, 0, st>>>(
         P, x, y, n_sig, n, stride, d_zi, d_zf);
     e = cudaGetLastError();

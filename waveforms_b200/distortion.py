@@ -292,9 +292,13 @@ def _kernel_response(ker, n, device):
 
 
 def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
-               initial_x=None, initial_y=None, zi=None, return_zf: bool = False):
+               initial_x=None, initial_y=None, zi=None, return_zf: bool = False, iir_mode='exact'):
     """IIR predistortion (lfilter with lfiltic initial state) followed by an
-    optional centred kernel convolution; reference :289-337."""
+    optional centred kernel convolution; reference :289-337.
+
+    ``iir_mode`` (not in the reference): 'exact' = the sequential kernel, bit-identical to scipy.signal.lfilter;
+    'scan' = block-parallel (combined filters up to order 4), 40 x faster on long batches, equal up to the filter's
+    rounding-noise gain; 'auto' = exact up to ``dsp.IIR_AUTO_EXACT_MAX`` samples per signal."""
     dev, was_np = _to_device(sig)
     zf = None
     if filters is not None:
@@ -312,7 +316,8 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
             else:
                 initial_y = np.asarray(initial_y)[:len(a) - 1]
             zi = lfiltic(b, a, initial_y, initial_x)
-        dev, zf = dsp.lfilter_device(b, a, dev, zi=zi, want_zf=True)
+        # (the final state costs a device->host copy and a synchronisation: only when it is asked for)
+        dev, zf = dsp.lfilter_device(b, a, dev, zi=zi, want_zf=return_zf, mode=iir_mode)
         if zf is not None and dev.dim() == 1:
             zf = zf[0]
     if ker is not None:

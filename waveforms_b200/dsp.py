@@ -136,9 +136,16 @@ def apply_channel_filters(out, batch, waveforms, mode=None):
                 sosfilt_device(sos, out[off:off + n], initial=initial, mode=mode)
 
 
-def lfilter_device(b, a, x, zi=None, want_zf=False):
+LFILTER_SCAN_MAX_ORDER = 4
+
+
+def lfilter_device(b, a, x, zi=None, want_zf=False, mode='exact'):
     """scipy.signal.lfilter(b, a, x, zi=zi) on a CUDA f64 tensor (n,) or
-    (n_sig, n), in place; bit-identical sequential kernel.  Returns (y, zf)."""
+    (n_sig, n), in place.  Returns (y, zf).
+
+    mode: 'exact' (sequential kernel, bit-identical to SciPy) | 'scan' (block-parallel, orders 1..4, equal up to the
+    filter's rounding-noise gain; higher orders run the sequential kernel) | 'auto' | None (= ``IIR_MODE``), as for
+    ``sosfilt_device``."""
     import torch
     lib = engine.require_gpu()
     b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1))
@@ -152,11 +159,11 @@ def lfilter_device(b, a, x, zi=None, want_zf=False):
         zi_arr = np.ascontiguousarray(
             np.broadcast_to(np.asarray(zi, dtype=np.float64), (n_sig, order)))
     zf = np.zeros((n_sig, max(order, 0))) if want_zf else None
-    rc = lib.wfm_lfilter(b.ctypes.data, len(b), a.ctypes.data, len(a),
-                         x2.data_ptr(), x2.data_ptr(), n_sig, n, x2.stride(0),
-                         zi_arr.ctypes.data if zi_arr is not None else None,
-                         zf.ctypes.data if zf is not None and order > 0 else None,
-                         _stream(torch, x.device))
+    rc = lib.wfm_lfilter_mode(b.ctypes.data, len(b), a.ctypes.data, len(a),
+                              x2.data_ptr(), x2.data_ptr(), n_sig, n, x2.stride(0),
+                              zi_arr.ctypes.data if zi_arr is not None else None,
+                              zf.ctypes.data if zf is not None and order > 0 else None,
+                              _IIR_MODES[resolve_iir_mode(n, mode)], _stream(torch, x.device))
     engine._check(rc)
     return x, zf
 

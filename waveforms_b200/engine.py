@@ -72,7 +72,7 @@ EXPORTS = [
     'wfm_abi_version', 'wfm_last_error', 'wfm_device_count', 'wfm_trim',
     'wfm_program_create', 'wfm_program_destroy', 'wfm_program_total_samples',
     'wfm_program_launch_count', 'wfm_program_info', 'wfm_sample', 'wfm_sample_host', 'wfm_sosfilt',
-    'wfm_lfilter', 'wfm_expand_templates', 'wfm_fft_filter', 'wfm_fft_response_create', 'wfm_fft_response_destroy',
+    'wfm_lfilter', 'wfm_lfilter_mode', 'wfm_expand_templates', 'wfm_fft_filter', 'wfm_fft_response_create', 'wfm_fft_response_destroy',
     'wfm_fft_filter_prepared', 'wfm_reflection_filter', 'wfm_fft_c2c', 'wfm_calibrate_fp64', 'wfm_calibrate_copy'
 ]
 
@@ -112,6 +112,11 @@ def load_library():
             C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
             C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
             C.c_void_p, C.c_void_p
+        ]
+        lib.wfm_lfilter_mode.argtypes = [
+            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+            C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+            C.c_void_p, C.c_int32, C.c_void_p
         ]
         lib.wfm_fft_filter.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
