@@ -176,6 +176,24 @@ def combine_filters(filters):
     return b.coeffs, a.coeffs
 
 
+_COMBINED = {}  # coefficient bytes of a filter list -> (b, a, all poles inside the unit circle)
+
+
+def _combined(filters):
+    """combine_filters + the stability test of predistort (reference :298-303), remembered per filter list: a calibration
+    applies the same filters to every batch, and the root finding costs more host time than the device filter takes."""
+    key = tuple((np.asarray(b_, dtype=np.float64).tobytes(), np.asarray(a_, dtype=np.float64).tobytes()) for b_, a_ in filters)
+    hit = _COMBINED.get(key)
+    if hit is None:
+        b, a = combine_filters(filters)
+        z, p, k = tf2zpk(b, a)
+        hit = (b, a, bool(np.all(np.abs(p) < 1)))
+        if len(_COMBINED) >= 64:
+            _COMBINED.pop(next(iter(_COMBINED)))
+        _COMBINED[key] = hit
+    return hit
+
+
 def factor_filter(b, a):
     """Split into first-order sections (reference :247-266)."""
     b, a = np.poly1d(b), np.poly1d(a)
@@ -302,9 +320,8 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
     dev, was_np = _to_device(sig)
     zf = None
     if filters is not None:
-        b, a = combine_filters(filters)
-        z, p, k = tf2zpk(b, a)
-        if not np.all(np.abs(p) < 1):
+        b, a, stable = _combined(filters)
+        if not stable:
             warnings.warn('Warning: filter is unstable')
         if zi is None:
             if initial_x is None:
