@@ -413,6 +413,8 @@ def main():
             except RuntimeError:  # no room for a second pinned buffer: single-buffered steps
                 pass
             n_thr = len(hosts)
+            if os.environ.get('WFM_BENCH_E2E_THREADS'):
+                n_thr = max(1, min(n_thr, int(os.environ['WFM_BENCH_E2E_THREADS'])))
             import concurrent.futures as cf
 
             def one_step(k):

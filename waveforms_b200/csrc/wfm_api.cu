@@ -175,6 +175,7 @@ static cudaError_t read_words(void* dst_host, const void* src_dev, int n, cudaSt
 // and host round trip of wfm_program_create costs microseconds.  Their arena is assembled in one pinned staging buffer
 // per host thread and goes up in ONE copy; the tile size comes from the host estimate and is verified after the fact.
 constexpr size_t kStageBytes = 256 << 10;
+constexpr size_t kBlockingWaitBytes = (size_t)64 << 20;  // wfm_sample_host: device->host copies from this size sleep on an event
 static unsigned char* stage_buffer() {
   static thread_local unsigned char* p = nullptr;
   if (!p && cudaHostAlloc((void**)&p, kStageBytes, cudaHostAllocPortable) != cudaSuccess) {
@@ -892,7 +893,22 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
   if (t1 > t0) prog->launches += 1;
   WFM_CUDA(cudaMemcpyAsync((char*)l->out + (size_t)lo * esz, (char*)prog->stage.p + (size_t)lo * esz,
                            (size_t)(need - lo) * esz, cudaMemcpyDeviceToHost, ST));
-  WFM_CUDA(cudaStreamSynchronize(ST));
+  // A long copy is waited for on a blocking-sync event: the host thread sleeps instead of spinning on the stream for
+  // hundreds of milliseconds (one process per GPU with two submitting threads each is more threads than an 8-GPU host
+  // has cores to spin on).  Short copies keep the spinning wait: its wake-up is tens of microseconds faster.
+  if ((size_t)(need - lo) * esz >= kBlockingWaitBytes) {
+    static thread_local cudaEvent_t ev[pool::kMaxDevices] = {};
+    const int dv = prog->device;
+    if (dv >= 0 && dv < pool::kMaxDevices) {
+      if (!ev[dv]) WFM_CUDA(cudaEventCreateWithFlags(&ev[dv], cudaEventBlockingSync | cudaEventDisableTiming));
+      WFM_CUDA(cudaEventRecord(ev[dv], ST));
+      WFM_CUDA(cudaEventSynchronize(ev[dv]));
+    } else {
+      WFM_CUDA(cudaStreamSynchronize(ST));
+    }
+  } else {
+    WFM_CUDA(cudaStreamSynchronize(ST));
+  }
   tm.lap("memset+kernel+D2H");
   return WFM_OK;
 }
