@@ -204,6 +204,7 @@ struct WfmProgram {
   int64_t total_samples = 0;  // extent of the output buffer in samples
   int64_t launches = 0;
   bool any_complex = false;
+  bool gapless = false;
   // complex128 output: a planar twin (channels [0, n) = real parts, [n, 2n) = imaginary parts,
   // both real-valued programs for the fast kernel) and the scratch the two planes are sampled into
   WfmProgram* planar = nullptr;
@@ -463,9 +464,10 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
   p->dev.planes = 1;
   p->dev.dense = 0;
 
-  int64_t samples = 0, total = 0;
+  int64_t samples = 0, total = 0, rows = 0;
   for (int64_t w = 0; w < d->n_waves; ++w) {
     samples += d->waves[w].n;
+    rows += d->waves[w].n * ((d->waves[w].flags & WFM_WAVE_PAIR) ? 2 : 1);
     total = std::max(total, d->waves[w].out_off + d->waves[w].n);
     if (d->waves[w].flags & WFM_WAVE_COMPLEX) p->any_complex = true;
     if (d->waves[w].flags & WFM_WAVE_PAIR) {
@@ -474,6 +476,7 @@ int wfm_program_create(const WfmProgramDesc* d, int device, wfm_program_t* out) 
     }
   }
   p->total_samples = total;
+  p->gapless = rows == total;  // the channels' rows tile the output: nothing between them that the kernel leaves unwritten
 
   // arena 1: every table that does not depend on the tile size (ABI tables + segment plans), 256-byte aligned slots
   size_t arena_bytes = 0;
@@ -883,8 +886,8 @@ int wfm_sample_host(wfm_program_t prog, const WfmLaunch* l) {
     if (ea != cudaSuccess) return fail(WFM_ENOMEM, "allocating the %zu-byte staging buffer failed: %s", bytes, cudaGetErrorString(ea));
   }
   tm.lap("stage alloc");
-  // padding between channels is never written by the kernel: keep it defined
-  WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, ST));
+  // padding between channels is never written by the kernel: keep it defined (nothing to do when the rows are gapless)
+  if (!(prog->gapless && first == 0 && count == (int64_t)prog->waves.size())) WFM_CUDA(cudaMemsetAsync((char*)prog->stage.p + (size_t)lo * esz, 0, (size_t)(need - lo) * esz, ST));
   const int64_t t0 = prog->tile_prefix[first], t1 = prog->tile_prefix[first + count];
   {
     const int rc2 = launch_request(prog, first, count, l->dtype, 0, prog->stage.p, ST);

@@ -233,6 +233,24 @@ class Program:
         self.device = int(device)
         self.batch = batch
         self._lib = lib
+        # the descriptor of host tables only holds pointers into the batch's own arrays: built once per batch (a scheduler
+        # re-submits a batch many times; for the README example the ctypes work was a sixth of the whole call)
+        cached = getattr(batch, '_desc_cache', None) if not hasattr(batch, 'pulse_tmpl') else None
+        if cached is not None:
+            d, keep = cached
+        else:
+            d, keep = self._describe(batch, lib)
+            if not hasattr(batch, 'pulse_tmpl'):
+                try:
+                    batch._desc_cache = (d, keep)
+                except AttributeError:
+                    pass
+        h = C.c_void_p()
+        _check(lib.wfm_program_create(C.byref(d), self.device, C.byref(h)))
+        self._h = h
+
+    def _describe(self, batch, lib):
+        torch = _torch()
         d = _ProgramDesc()
         keep = []
 
@@ -276,9 +294,7 @@ class Program:
             d.n_terms, d.terms = len(batch.terms), ptr(batch.terms)
             d.n_refs, d.refs = len(batch.refs), ptr(batch.refs)
             d.n_args, d.args = len(batch.args), ptr(batch.args)
-        h = C.c_void_p()
-        _check(lib.wfm_program_create(C.byref(d), self.device, C.byref(h)))
-        self._h = h
+        return d, keep
 
     def close(self):
         if getattr(self, '_h', None):
