@@ -18,11 +18,25 @@
  *   wfm_sample_host      – same, with HOST output buffers (device->host copy
  *                          inside the call): the end-to-end path.
  *   wfm_sosfilt          – scipy.signal.sosfilt call sites
- *                          waveforms/waveform.py:200-203, :249 and
- *                          scipy.signal.lfilter in distortion.py:321.
- *   wfm_fft_filter       – np.fft.fft / ifft in distortion.py:208-221
- *                          (reflection, correct_reflection) and
- *                          scipy.signal.fftconvolve in distortion.py:329-333.
+ *                          waveforms/waveform.py:200-203, :249.
+ *   wfm_lfilter,
+ *   wfm_lfilter_mode     – scipy.signal.lfilter in distortion.py:321 (predistort):
+ *                          sequential bit-identical kernel, or block-parallel
+ *                          scan for orders <= 4.
+ *   wfm_fft_filter,
+ *   wfm_reflection_filter,
+ *   wfm_fft_response_create / wfm_fft_filter_prepared
+ *                        – np.fft.fft / ifft in distortion.py:208-221
+ *                          (reflection, correct_reflection; the response built
+ *                          and cached on the device) and
+ *                          scipy.signal.fftconvolve in distortion.py:329-333
+ *                          (the kernel's response prepared once).
+ *   wfm_expand_templates – no reference counterpart (the reference builds one
+ *                          Python object per pulse, _waveform.pyx:68-88,
+ *                          :216-235): per-pulse IR rows written on the device
+ *                          from pulse templates + per-pulse payloads.
+ *   wfm_calibrate_fp64 / wfm_calibrate_copy
+ *                        – in-run FP64 and pinned-copy ceilings for bench.py.
  *
  * Conventions: plain C structs of pointers and counts; every function returns
  * 0 on success or a negative WFM_E* code (no exceptions cross the ABI), and
