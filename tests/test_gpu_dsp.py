@@ -267,3 +267,24 @@ def test_predistort_scan_is_as_accurate_as_scipy():
         assert np.max(np.abs(zf - ref_zf)) <= (2.5 * err_scipy + 1e-12) * max(1.0, np.max(np.abs(ref)))
         exact, zfe = D.predistort(x, filters, initial=0.1, return_zf=True)
         assert np.array_equal(exact, ref) and np.array_equal(zfe, ref_zf)
+
+
+@pytest.mark.parametrize('order', [5, 6, 8, 10, 16])
+def test_sosfilt_scan_long_cascades(order):
+    """Cascades of 3..8 sections run as a chain of two-section joint scans, each on its slice of the states: equal to
+    scipy.signal.sosfilt to 1e-12 (well-conditioned sections), initial state, final state and `initial` offset included."""
+    from scipy.signal import sosfilt_zi
+    from waveforms_b200.dsp import sosfilt_device
+    rng = np.random.default_rng(order)
+    sos = tf2sos(*butter(order, 0.3))
+    n = 30001
+    x = rng.standard_normal((3, n))
+    y, _ = sosfilt_device(sos, _dev(x), mode='scan')
+    assert rel_err(y.cpu().numpy(), sosfilt(sos, x, axis=-1)) <= FP64_TOL
+    zi = sosfilt_zi(sos)[None] * rng.standard_normal((3, 1, 1))          # (n_sig, n_sections, 2)
+    want = [sosfilt(sos, x[k], zi=zi[k]) for k in range(3)]
+    y, zf = sosfilt_device(sos, _dev(x), zi=zi, want_zf=True, mode='scan')
+    assert rel_err(y.cpu().numpy(), np.stack([w[0] for w in want])) <= FP64_TOL
+    assert np.max(np.abs(zf - np.stack([w[1] for w in want]))) <= 1e-11 * max(1.0, np.max(np.abs(zf)))
+    y, _ = sosfilt_device(sos, _dev(x + 0.7), initial=0.7, mode='scan')
+    assert rel_err(y.cpu().numpy(), sosfilt(sos, x, axis=-1) + 0.7) <= FP64_TOL

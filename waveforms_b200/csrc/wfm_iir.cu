@@ -65,6 +65,7 @@ struct Biquad {
 
 struct IirParams {
   int n_sections;
+  int shift_in, shift_out;  // joint scan only: subtract `initial` at the input / add it at the output of THIS launch
   double initial;
   Biquad sec[kMaxSections];
 };
@@ -366,7 +367,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int S, bool kAligned>
 __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_kernel(
     const __grid_constant__ IirParams P, const __grid_constant__ IirJointTables TT, const double* __restrict__ x, double* y,
-    int64_t n, int64_t stride, const double* __restrict__ zi, double* __restrict__ zf) {
+    int64_t n, int64_t stride, const double* __restrict__ zi, double* __restrict__ zf, int zs) {
+  // zs: state words between two signals in zi / zf (2 x the sections of the WHOLE cascade: a long cascade runs as a chain
+  // of launches over its sections two by two, each on its slice of the states)
   constexpr int D = 2 * S;
   double* s_buf0 = reinterpret_cast<double*>(iir_smem);
   double* s_buf1 = reinterpret_cast<double*>(iir_smem + kJointTileBytes);
@@ -377,9 +380,9 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_
   const int64_t sig = blockIdx.x;
   const double* __restrict__ xs = x + sig * stride;
   double* ys = y + sig * stride;
-  const bool shift = P.initial != 0.0;
+  const bool shift_in = P.initial != 0.0 && P.shift_in, shift_out = P.initial != 0.0 && P.shift_out;
   for (int e = tid; e < D * D * 32; e += kIirThreads) s_lane[e / 32][e % 32] = TT.lane[e % 32][(e / 32) / D * kMaxJoint + (e / 32) % D];
-  if (tid < D) s_carry[tid] = zi ? zi[sig * D + tid] : 0.0;  // zi[sig][section][2] is the joint state in order
+  if (tid < D) s_carry[tid] = zi ? zi[sig * zs + tid] : 0.0;  // zi[sig][section][2] is the joint state in order
   Biquad q[S];
   double c1[S], c2[S];
 #pragma unroll
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_
       }
     }
     const int valid = max(0, min(kIirT, cnt - tid * kIirT));  // my valid samples
-    if (shift) {
+    if (shift_in) {
 #pragma unroll
       for (int k = 0; k < kIirT; ++k) v[k] = k < valid ? sub(v[k], P.initial) : 0.0;
     }
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_
         o1_prev = o1;
       }
     }
-    if (shift) {
+    if (shift_out) {
 #pragma unroll
       for (int k = 0; k < kIirT; ++k) v[k] = add(v[k], P.initial);
     }
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_joint_
     __syncthreads();  // the buffer may be refilled (tile t + 2) and s_carry read (tile t + 1)
   }
   if (kAligned) cp_async_wait<0>();
-  if (zf && tid < D) zf[sig * D + tid] = s_carry[tid];
+  if (zf && tid < D) zf[sig * zs + tid] = s_carry[tid];
 }
 
 // ---------------------------------------------------------------------------
@@ -984,21 +987,31 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
       const unsigned blocks = (unsigned)((n_sig + kExactWarps - 1) / kExactWarps);
       sosfilt_exact_kernel<<<blocks, 32 * kExactWarps, 0, st>>>(P, x, y, n_sig, n, stride, d_zi, d_zf);
       e = cudaGetLastError();
-    } else if (n_sections <= 2 && !getenv("WFM_IIR_OLD_SCAN")) {
-      static thread_local IirJointTables jt;
-      joint_tables(P, &jt);
+    } else if (!getenv("WFM_IIR_OLD_SCAN")) {
+      // the joint kernel takes the sections two by two: a cascade of S sections is ceil(S / 2) launches, each a read and
+      // a write of the signal; `initial` is subtracted by the first launch and added back by the last one only
       const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (stride % 2 == 0 || n_sig == 1);
       const size_t smem = 2 * (size_t)kJointTileBytes;
-      auto launch = [&](auto kern) {
-        static thread_local bool attr_set[4] = {};
-        cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        (void)attr_set;
-        if (ee != cudaSuccess) return ee;
-        kern<<<(unsigned)n_sig, kIirThreads, smem, st>>>(P, jt, x, y, n, stride, d_zi, d_zf);
-        return cudaGetLastError();
-      };
-      if (n_sections == 1) e = aligned ? launch(sosfilt_scan_joint_kernel<1, true>) : launch(sosfilt_scan_joint_kernel<1, false>);
-      else e = aligned ? launch(sosfilt_scan_joint_kernel<2, true>) : launch(sosfilt_scan_joint_kernel<2, false>);
+      for (int k0 = 0; k0 < n_sections && e == cudaSuccess; k0 += 2) {
+        IirParams Pk{};
+        Pk.n_sections = std::min(2, n_sections - k0);
+        Pk.initial = P.initial;
+        Pk.shift_in = k0 == 0;
+        Pk.shift_out = k0 + 2 >= n_sections;
+        for (int k = 0; k < Pk.n_sections; ++k) Pk.sec[k] = P.sec[k0 + k];
+        static thread_local IirJointTables jt;
+        joint_tables(Pk, &jt);
+        const double* xin = k0 == 0 ? x : y;
+        auto launch = [&](auto kern) {
+          cudaError_t ee = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (ee != cudaSuccess) return ee;
+          kern<<<(unsigned)n_sig, kIirThreads, smem, st>>>(Pk, jt, xin, y, n, stride, d_zi ? d_zi + 2 * k0 : nullptr,
+                                                           d_zf ? d_zf + 2 * k0 : nullptr, 2 * n_sections);
+          return cudaGetLastError();
+        };
+        if (Pk.n_sections == 1) e = aligned ? launch(sosfilt_scan_joint_kernel<1, true>) : launch(sosfilt_scan_joint_kernel<1, false>);
+        else e = aligned ? launch(sosfilt_scan_joint_kernel<2, true>) : launch(sosfilt_scan_joint_kernel<2, false>);
+      }
     } else {
       static thread_local IirScanTables tab;
       for (int k = 0; k < n_sections; ++k) {
