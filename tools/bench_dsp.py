@@ -74,9 +74,9 @@ def main():
     tot = args.channels * n
     add('K1 sample (20 erf-edged squares / channel)', timed(lambda: prog.sample_device(dtype=engine.WFM_F64, out=sig)), tot, 8,
         'write-only')
-    add('K2 sosfilt exact (2 sections, 1 thread / signal)', timed(lambda: dsp.sosfilt_device(sos, work, out=out, mode='exact')),
+    add('K2 sosfilt exact (%d section(s), 1 warp / signal)' % len(sos), timed(lambda: dsp.sosfilt_device(sos, work, out=out, mode='exact')),
         tot, 16, 'bit-identical to scipy.signal.sosfilt')
-    add('K2 sosfilt scan (2 sections, 1 CTA / signal)', timed(lambda: dsp.sosfilt_device(sos, work, out=out, mode='scan')), tot,
+    add('K2 sosfilt scan (%d section(s), 1 CTA / signal)' % len(sos), timed(lambda: dsp.sosfilt_device(sos, work, out=out, mode='scan')), tot,
         16, 'block-parallel associative scan')
     w2 = work.clone()
     add('K2b lfilter exact (order %d)' % (max(len(a), len(b)) - 1), timed(lambda: dsp.lfilter_device(b, a, w2)), tot, 16,

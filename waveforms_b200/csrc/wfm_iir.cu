@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(kIirThreads, WFM_IIR_MINB) sosfilt_scan_kernel
 //   pass c: the FAITHFUL recurrence from E_i, the sections software-pipelined (section 1 of
 //           sample k+1 next to section 2 of sample k: two independent chains).
 // One scan and two passes per tile instead of two scans and four passes, and a shorter chain
-// in pass a: 0.63 -> ~0.3 ms on cfg4 (256 x 400 000 samples, 2 sections).
+// in pass a: 0.63 -> ~0.3 ms on cfg4 (256 x 400 000 samples; its two exponential decays make ONE biquad section; a
+// two-section cascade of the same size takes 0.50 ms).
 // ---------------------------------------------------------------------------
 constexpr int kMaxJoint = 4;  // D = 2 S, S <= 2
 struct IirJointTables {
