@@ -467,6 +467,23 @@ def test_compact_batch_of_iq_pairs(ns):
     assert cb.n_channels == 10 and cb.nbytes() < 0.2 * full.nbytes()
 
 
+def test_numpy_scalars_do_not_swallow_traced_amplitudes(ns):
+    """The derivative of an erf edge multiplies the amplitude by an np.float64 (2 / (s sqrt(pi))): ``np.float64 * Sym``
+    must stay traced (Sym.__array_ufunc__ = None), else an erf-edged DRAG pulse with a per-pulse amplitude is refused.
+    NumPy FUNCTIONS of a traced value are reported as untraceable."""
+    f = lambda t0, amp, phase: ns.mixing(amp * ns.square(40e-9, edge=4e-9) >> t0, freq=-150e6, phase=phase, DRAGScaling=3e-10)[0]
+    tp = PulseTemplate.trace(f, params=('t0', 'amp', 'phase'))
+    rng = np.random.default_rng(3)
+    n = 12
+    t0 = [200e-9 + 100e-9 * np.arange(n)]
+    amp, phase = [rng.uniform(-1, 1, n)], [rng.uniform(0, 6, n)]
+    got = pulse_train_batch([tp], [np.zeros(n, int)], t0, 0, 2e-6, 2e9, params={'amp': amp, 'phase': phase})
+    _, want = object_batch(ns, [f], [np.zeros(n, int)], t0, 0, 2e-6, 2e9, params={'amp': amp, 'phase': phase})
+    assert_same_tables(got, want)
+    with pytest.raises(UntraceablePulse, match='NumPy'):
+        PulseTemplate.trace(lambda t0, amp: (np.sqrt(amp) * ns.cosPulse(20e-9)) >> t0, params=('t0', 'amp'))
+
+
 def test_compact_refuses_what_it_cannot_carry(ns):
     tp = PulseTemplate.trace(lambda t0: 0.3 * ns.gaussian(30e-9) >> t0)
     with pytest.raises(ValueError, match='compact'):
@@ -585,3 +602,32 @@ def test_compact_replay_on_random_trains(ns, seed):
     assert_compact_equals_full(cb, full)
     assert cb.n_channels == (10 if pair else 5)
     assert cb.nbytes() < full.nbytes()
+
+
+@pytest.mark.gpu
+def test_non_strict_templates_sample_like_the_object_api(ns):
+    """strict=False: shapes whose TABLE structure depends on the value of a per-pulse parameter (slow carriers, erf
+    edges: the reference's algebra merges or keeps equal terms depending on the phase) are accepted when the traced
+    structure samples to the same values on the device; the batch then equals the object API to 1e-12."""
+    from waveforms_b200.batch import sample_pulse_trains
+    fns = [lambda t0, amp, phase: ns.mixing(amp * ns.cosPulse(20e-9) >> t0, freq=30e6, phase=phase, DRAGScaling=4e-10)[0],
+           lambda t0, amp, phase: ns.mixing(amp * ns.square(40e-9, edge=4e-9) >> t0, freq=30e6, phase=phase, DRAGScaling=3e-10)[0],
+           lambda t0, amp, phase: ns.mixing(amp * ns.gaussian(20e-9) >> t0, freq=-20e6, phase=phase, DRAGScaling=5e-10)[1]]
+    for f in fns:
+        with pytest.raises(UntraceablePulse):
+            PulseTemplate.trace(f, params=('t0', 'amp', 'phase'))
+    templates = [PulseTemplate.trace(f, params=('t0', 'amp', 'phase'), strict=False) for f in fns]
+    rng = np.random.default_rng(61)
+    n_ch, depth = 5, 30
+    idx = rng.integers(0, len(fns), (n_ch, depth))
+    t0 = np.tile(200e-9 + 120e-9 * np.arange(depth), (n_ch, 1)) + rng.uniform(0, 20e-9, (n_ch, depth))
+    amp = rng.uniform(0.1, 1, (n_ch, depth)) * rng.choice([-1, 1], (n_ch, depth))
+    phase = rng.uniform(0, 2 * np.pi, (n_ch, depth))
+    stop = 200e-9 + 120e-9 * depth + 300e-9
+    for compact in (False, True):
+        res = sample_pulse_trains(templates, idx, t0, 0.0, stop, 2e9, params={'amp': amp, 'phase': phase}, compact=compact).numpy()
+        for c in (0, n_ch - 1):
+            w = ns.WaveVStack([fns[int(i)](float(t), float(a), float(p)) for i, t, a, p in zip(idx[c], t0[c], amp[c], phase[c])])
+            w.start, w.stop, w.sample_rate = 0.0, stop, 2e9
+            want = w.sample()
+            assert np.max(np.abs(res[c] - want)) <= 1e-12 * np.max(np.abs(want))
