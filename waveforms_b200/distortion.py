@@ -345,13 +345,13 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
     return (out, zf) if return_zf else out
 
 
-def distort(points, params, sample_rate, initial=0.0):
-    """reference :340-346"""
+def distort(points, params, sample_rate, initial=0.0, iir_mode='exact'):
+    """reference :340-346 (``iir_mode``: see ``predistort``)"""
     filters = []
     for amp, tau in np.asarray(params).reshape(-1, 2):
         b, a = exp_decay_filter(amp, abs(tau), sample_rate)
         filters.append((b, a))
-    return predistort(points, filters, initial=initial)
+    return predistort(points, filters, initial=initial, iir_mode=iir_mode)
 
 
 def phase_curve(t, params, df_dphi, pulse_width, start, wav, sample_rate):
