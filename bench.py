@@ -460,6 +460,16 @@ def main():
                     'scheduler that rebuilds every frame through the object API spends this much host time per frame '
                     '(the reference spends the same: the algebra is its own); waveforms_b200.builder removes it for pulse '
                     'trains (configs.cfg3.host_build_s)'}
+        if args.dtype == 'f64' and not args.no_extras and rank == 0:
+            # ... and the same frame built from parameter arrays (waveforms_b200.builder): what the host cost becomes
+            try:
+                from tools import bench_extras as _bx
+                bld = _bx.cfg2_frame_from_arrays(ns, torch, engine, 20260002, CHANNELS, XY_PULSES, Z_PULSES, T_END, RATE, chans)
+                bld['GSa/s_if_every_frame_is_rebuilt'] = samples_per_step / (args.frames * bld['build_s_per_frame'] +
+                                                                              e2e['ms_per_step'] * 1e-3) / 1e9
+                e2e['with_host_build']['builder'] = bld
+            except Exception as ex:  # the builder leg is an extra: never lose the line over it
+                e2e['with_host_build']['builder'] = {'error': repr(ex)}
         if args.dtype == 'f64' and not args.no_extras:
             # fp32 output halves the bytes read back (north_star allows 1e-6): same steps, float32 buffers
             e32, _ = run_e2e(batch, engine.WFM_F32, torch.float32, 4, e_steps)

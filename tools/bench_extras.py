@@ -436,3 +436,78 @@ def pipeline_cfg4(ns, torch, engine, peak, quick=False):
                            'ms_per_channel': {'sample': t_smp * 1e3, 'sosfilt': t_iir * 1e3, 'correct_reflection': t_fft * 1e3}}
     prog.close()
     return res
+
+
+def cfg2_frame_from_arrays(ns, torch, engine, seed, channels, xy_pulses, z_pulses, t_end, rate, chans=None):
+    """The bench's cfg2 frame (bench.build_frame: cases.xy_channel / z_channel) built from PARAMETER ARRAYS with
+    waveforms_b200.builder instead of one Python object per pulse: the same random draws in the same order, one template
+    per (channel carrier, envelope) and one for the flux squares; templates are traced with strict=False (random carriers
+    between -200 and 200 MHz: the reference algebra's structure depends on the phase value for some of them), so the
+    batch equals the object API's to rounding instead of bit for bit.  Returns timings and the parity of the sampled
+    frame against the object-API frame's channels ``chans`` (sampled by the same kernels)."""
+    from waveforms_b200.builder import PulseTemplate, pulse_train_batch
+    rng = np.random.default_rng(seed)
+    half = channels // 2
+    freqs, T0, AMP, PH, DR = [], [], [], [], []
+    for q in range(half):
+        freqs.append(rng.uniform(-200e6, 200e6))
+        t0, amp, ph, dr = [], [], [], []
+        for k in range(xy_pulses):
+            t0.append(round((50e-9 + k * 400e-9 + rng.uniform(0, 100e-9)) * rate) / rate)
+            amp.append(rng.uniform(0.1, 1))
+            ph.append(rng.uniform(0, 2 * np.pi))
+            dr.append(rng.uniform(2e-10, 1e-9))
+        T0.append(t0); AMP.append(amp); PH.append(ph); DR.append(dr)
+    ZC, ZA, ZW = [], [], []
+    slot = t_end / z_pulses
+    for q in range(half):
+        c, a, wd = [], [], []
+        for k in range(z_pulses):
+            wd.append(rng.uniform(20e-9, 200e-9))
+            c.append(round((k + 0.5) * slot * rate) / rate)
+            a.append(rng.uniform(-0.5, 0.5))
+        ZC.append(c); ZA.append(a); ZW.append(wd)
+
+    t_tr = time.perf_counter()
+    templates = []
+    probe = {'t0': 1e-6, 'amp': 0.6, 'phase': 0.7, 'drag': 5e-10, 'width': 50e-9}
+    check = {'t0': 2.37e-6, 'amp': 0.4, 'phase': 2.5, 'drag': 8e-10, 'width': 120e-9}
+    names = ('t0', 'amp', 'phase', 'drag', 'width')  # one parameter set for every template (unused ones are ignored)
+    for q in range(half):
+        for env in (ns.cosPulse, ns.gaussian):
+            f = (lambda t0, amp, phase, drag, width, env=env, fr=freqs[q]:
+                 ns.mixing(amp * env(20e-9) >> t0, freq=fr, phase=phase, DRAGScaling=drag)[0])
+            templates.append(PulseTemplate.trace(f, params=names, probe=probe, check=check, strict=False))
+    templates.append(PulseTemplate.trace(lambda t0, amp, phase, drag, width: amp * (ns.square(width, edge=2e-9) >> t0),
+                                         params=names, probe=probe, check=check, strict=False))
+    trace_s = time.perf_counter() - t_tr
+
+    def build():
+        idx = [[2 * q + (k & 1) for k in range(xy_pulses)] for q in range(half)] + [[2 * half] * z_pulses for _ in range(half)]
+        t0 = T0 + ZC
+        one = lambda rows, n: [[1.0] * n for _ in range(rows)]
+        params = {'amp': AMP + ZA, 'phase': PH + one(half, z_pulses), 'drag': DR + one(half, z_pulses),
+                  'width': one(half, xy_pulses) + ZW}
+        return pulse_train_batch(templates, idx, t0, 0.0, t_end, rate, params=params, compact=True, spot_check=1)
+    build()
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter()
+        cb = build()
+        ts.append(time.perf_counter() - t)
+    prog = engine.Program(cb, torch.cuda.current_device())
+    out = prog.sample_device(dtype=engine.WFM_F64)
+    worst = None
+    if chans is not None:
+        worst = 0.0
+        for c in (0, half - 1, half, channels - 1):
+            want = chans[c].sample()
+            off, cnt = int(cb.chan_off[c]), int(cb.chan_n[c])
+            worst = max(worst, rel_err(out[off:off + cnt].cpu().numpy(), want))
+    prog.close()
+    return {'trace_s_once': trace_s, 'build_s_per_frame': float(min(ts)), 'templates': len(templates),
+            'pulses_per_frame': half * (xy_pulses + z_pulses), 'upload_bytes': int(cb.nbytes()),
+            'max_rel_err_vs_object_api_frame': worst, 'ok': bool(worst is None or worst <= FP64_TOL),
+            'what': 'the same frame from parameter arrays: PulseTemplate.trace(strict=False) per (carrier, envelope) once, then '
+                    'pulse_train_batch(compact=True, spot_check=1: one pulse per template re-checked against the object API) per frame; parity = 4 channels against the object-API channels sampled by the '
+                    'same library'}
