@@ -460,7 +460,7 @@ def main():
                     'scheduler that rebuilds every frame through the object API spends this much host time per frame '
                     '(the reference spends the same: the algebra is its own); waveforms_b200.builder removes it for pulse '
                     'trains (configs.cfg3.host_build_s)'}
-        if args.dtype == 'f64' and not args.no_extras and rank == 0:
+        if args.dtype == 'f64' and not args.no_extras and world == 1:
             # ... and the same frame built from parameter arrays (waveforms_b200.builder): what the host cost becomes
             try:
                 from tools import bench_extras as _bx
