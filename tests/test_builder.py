@@ -631,3 +631,24 @@ def test_non_strict_templates_sample_like_the_object_api(ns):
             w.start, w.stop, w.sample_rate = 0.0, stop, 2e9
             want = w.sample()
             assert np.max(np.abs(res[c] - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+def test_vectorised_decimal_round_equals_python_round():
+    """builder._round_decimal replays round(float, nd) — the reference rounds every shifted bound to 15 decimals
+    (waveform.py:508-511) — over arrays: k / 10**nd with k = rint(v * 10**nd), and Python's own round() for the elements
+    where the product's rounding could change k (near ties, huge values, non-finite)."""
+    from waveforms_b200.builder import _round_decimal
+    rng = np.random.default_rng(1)
+    for nd in (0, 3, 9, 12, 15, 18):
+        v = np.concatenate([rng.uniform(-1, 1, 20000) * 10.0 ** rng.integers(-12, 3, 20000),
+                            (rng.integers(-10 ** 6, 10 ** 6, 5000) + 0.5) / 10.0 ** nd,       # decimal ties
+                            rng.integers(-10 ** 6, 10 ** 6, 5000) / 10.0 ** nd,               # already rounded
+                            [0.0, -0.0, -1e-30, 1e300, -1e300, 2.5e-15, np.inf, -np.inf, np.nan]])
+        got = _round_decimal(v, nd)
+        want = np.array([round(float(x), nd) for x in v])
+        same = (got == want) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (nd, v[~same][:3])
+        fin = ~np.isnan(want)
+        assert np.array_equal(np.signbit(got[fin]), np.signbit(want[fin]))
+    assert _round_decimal(np.float64(1.23456), 2) == round(1.23456, 2)          # scalars and odd digit counts
+    assert np.array_equal(_round_decimal(np.array([1.25, 2.35]), 30), np.array([1.25, 2.35]))

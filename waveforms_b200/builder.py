@@ -129,7 +129,7 @@ def _round_decimal(v, nd):
     if uf is None:
         uf = _round_ufuncs[nd] = np.frompyfunc(lambda x, nd=nd: round(x, nd), 1, 1)
     if not 0 <= nd <= 22 or v.ndim == 0:
-        return uf(v).astype(np.float64)
+        return np.asarray(uf(v), dtype=np.float64)
     s = 10.0 ** nd
     with np.errstate(invalid='ignore', over='ignore'):
         y = v * s
