@@ -17,7 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:sample_kernel -s
     python bench.py --steps 2 --warmup 3 --frames 16 --no-cpu --no-e2e --no-extras > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sample_dense -s 2 -c 1 -o $o/${tag}_k1_cfg3 \
     python tools/bench_configs.py --only cfg3 --reps 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'fft_|sosfilt_scan' -s 4 -c 4 -o $o/${tag}_dsp \
+ncu --set full --clock-control none --import-source on -k regex:'fft_|sosfilt_scan|lfilter_scan' -s 4 -c 5 -o $o/${tag}_dsp \
     python tools/bench_dsp.py --reps 1 > /dev/null 2>&1
 # the reports stay on the box (gpurun returns at most 64 MiB): keep their text pages
 for r in k1_cfg2 k1_cfg3 dsp; do
