@@ -288,3 +288,22 @@ def test_sosfilt_scan_long_cascades(order):
     assert np.max(np.abs(zf - np.stack([w[1] for w in want]))) <= 1e-11 * max(1.0, np.max(np.abs(zf)))
     y, _ = sosfilt_device(sos, _dev(x + 0.7), initial=0.7, mode='scan')
     assert rel_err(y.cpu().numpy(), sosfilt(sos, x, axis=-1) + 0.7) <= FP64_TOL
+
+
+def test_lfilter_scan_degenerate_inputs():
+    """Empty signals and order-0 filters in scan mode fall back to the sequential kernel's behaviour: the state passes
+    through, a pure gain is a multiplication; 'auto' picks the mode by length."""
+    from waveforms_b200.dsp import lfilter_device, IIR_AUTO_EXACT_MAX
+    import torch
+    b, a = butter(2, 0.2)
+    zi = np.array([[0.3, -0.1]])
+    y, zf = lfilter_device(b, a, torch.zeros(1, 0, dtype=torch.float64, device='cuda'), zi=zi, want_zf=True, mode='scan')
+    assert y.shape == (1, 0) and np.array_equal(zf, zi)
+    x = np.linspace(-1, 1, 1000)
+    y, _ = lfilter_device([2.5], [1.0], _dev(x), mode='scan')
+    assert np.array_equal(y.cpu().numpy(), lfilter([2.5], [1.0], x))
+    for n in (IIR_AUTO_EXACT_MAX, IIR_AUTO_EXACT_MAX + 1):
+        x = np.random.default_rng(n).standard_normal(n)
+        y, _ = lfilter_device(b, a, _dev(x), mode='auto')
+        ref = lfilter(b, a, x)
+        assert np.array_equal(y.cpu().numpy(), ref) if n <= IIR_AUTO_EXACT_MAX else rel_err(y.cpu().numpy(), ref) <= FP64_TOL

@@ -962,7 +962,7 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
     return WFM_EINVAL;
   if (mode != WFM_IIR_EXACT && mode != WFM_IIR_SCAN) return WFM_EINVAL;
   if (n_sig == 0) return WFM_OK;
-  if (!x || !y) return WFM_EINVAL;
+  if ((!x || !y) && n > 0) return WFM_EINVAL;  // (an empty signal has no buffer to point at)
   cudaStream_t st = (cudaStream_t)stream;
   IirParams P{};
   P.n_sections = n_sections;
@@ -1061,7 +1061,7 @@ extern "C" int wfm_lfilter_mode(const double* b, int32_t nb, const double* a, in
   const int M = std::max(nb, na) - 1;
   if (M > kMaxOrder) return WFM_EUNSUPPORTED;
   if (n_sig == 0) return WFM_OK;
-  if (!x || !y) return WFM_EINVAL;
+  if ((!x || !y) && n > 0) return WFM_EINVAL;  // (an empty signal has no buffer to point at)
   cudaStream_t st = (cudaStream_t)stream;
   LfilterParams P{};
   P.order = M;
