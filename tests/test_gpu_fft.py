@@ -186,3 +186,23 @@ def test_prepared_response_convolution_without_padding_buffers(n, K):
     assert np.array_equal(dev.cpu().numpy(), sig)
     got1 = D.predistort(sig[1], ker=ker)  # NumPy in, NumPy out, one signal, cached response
     assert isinstance(got1, np.ndarray) and rel_err(got1, want[1]) <= FP64_TOL
+
+
+@pytest.mark.parametrize('n', [400000, 409600, 625 * 2 * 7, 640 * 3 * 5 * 7])
+@pytest.mark.parametrize('nsig', [1, 3])
+def test_compile_time_plans_with_odd_batches_and_strided_rows(n, nsig):
+    """The tile shapes with compile-time plans (625-point columns x 640-point rows = cfg4's 400 000; 640 x 640 = the padded
+    kernel convolution) and their neighbours (625 or 640 on one side only: the compile-time and the generic stages in
+    one filter), with an unpaired last signal, in place on a strided view (rows not 16-byte aligned for odd strides)."""
+    import torch
+    from waveforms_b200.dsp import fft_filter_device
+    rng = np.random.default_rng(n + nsig)
+    buf = rng.standard_normal((nsig, n + 3))
+    x = buf[:, :n]
+    H = np.fft.fft(rng.standard_normal(n) * np.exp(-np.arange(n) / 40.0))
+    want = np.fft.ifft(np.fft.fft(x, axis=-1) * H, axis=-1).real
+    dev = torch.from_numpy(buf).cuda()
+    view = dev[:, :n]
+    got = fft_filter_device(view, H, out=view).cpu().numpy()
+    assert rel_err(got, want) <= FP64_TOL
+    assert np.array_equal(dev[:, n:].cpu().numpy(), buf[:, n:])
