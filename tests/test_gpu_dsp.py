@@ -307,3 +307,25 @@ def test_lfilter_scan_degenerate_inputs():
         y, _ = lfilter_device(b, a, _dev(x), mode='auto')
         ref = lfilter(b, a, x)
         assert np.array_equal(y.cpu().numpy(), ref) if n <= IIR_AUTO_EXACT_MAX else rel_err(y.cpu().numpy(), ref) <= FP64_TOL
+
+
+def test_predistort_leaves_a_cuda_input_untouched():
+    """predistort / distort return NEW arrays (reference :289-337); a CUDA tensor input is read, never written and never
+    aliased by the result — without a defensive copy of the input."""
+    import torch
+    from waveforms_b200 import distortion as D
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((4, 5000))
+    filters = [D.exp_decay_filter(-0.03, 0.1e-6, 2e9), D.exp_decay_filter(0.02, 0.3e-6, 2e9)]
+    ker = D.zDistortKernel(1 / 2e9, [(0.1e-6, -0.03)])
+    b, a = D.combine_filters(filters)
+    for kw in (dict(filters=filters), dict(ker=ker), dict(filters=filters, ker=ker), dict(), dict(filters=filters, iir_mode='scan')):
+        dev = torch.from_numpy(x).cuda()
+        got = D.predistort(dev, **kw)
+        assert np.array_equal(dev.cpu().numpy(), x), kw
+        assert got.data_ptr() != dev.data_ptr() and got.shape == dev.shape
+        want = D.predistort(x.copy(), **kw)                      # the NumPy path of the same function
+        assert rel_err(got.cpu().numpy(), want) <= FP64_TOL
+    view = torch.from_numpy(np.ascontiguousarray(np.stack([x, x], axis=-1))).cuda()[..., 0]   # element stride 2: a copy is needed
+    got = D.predistort(view, filters=filters)
+    assert np.array_equal(got.cpu().numpy(), np.stack([lfilter(b, a, r, zi=lfiltic(b, a, np.zeros(len(a) - 1), np.zeros(len(b) - 1)))[0] for r in x]))

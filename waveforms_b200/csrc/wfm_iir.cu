@@ -952,6 +952,45 @@ static void lfilter_tables(const LfScanParams& P, int Mo, IirJointTables* tab) {
   power_tables(M, Mo, tab);
 }
 
+// Host -> device copy of a small table (the initial states) that does NOT stall the stream: cudaMemcpyAsync from
+// PAGEABLE memory synchronises the stream before it stages the data, which serialises the host with every filter call
+// (predistort in scan mode: 0.32 ms of kernel became 0.59 ms per call).  The bytes go through a small ring of pinned
+// buffers per host thread instead; a slot is reused only after the copy that read it has completed (one event each).
+static cudaError_t upload_small(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  constexpr int kSlots = 4;
+  constexpr size_t kSlotBytes = 64 << 10;
+  struct Ring {
+    unsigned char* host[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
+    int next = 0;
+  };
+  static thread_local Ring rings[64];  // per host thread AND device: an event belongs to the device it was created on
+  if (bytes == 0) return cudaSuccess;
+  int dev = -1;
+  if (bytes > kSlotBytes || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  Ring& ring = rings[dev];
+  const int i = ring.next;
+  cudaError_t e = cudaSuccess;
+  if (!ring.host[i]) {
+    e = cudaHostAlloc((void**)&ring.host[i], kSlotBytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ring.done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ring.host[i] = nullptr;
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    }
+  } else {
+    e = cudaEventSynchronize(ring.done[i]);
+    if (e != cudaSuccess) return e;
+  }
+  memcpy(ring.host[i], src, bytes);
+  e = cudaMemcpyAsync(dst, ring.host[i], bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventRecord(ring.done[i], st);
+  ring.next = (i + 1) % kSlots;
+  return e;
+}
+
 }  // namespace wfm
 
 extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial, const double* x, double* y,
@@ -980,7 +1019,7 @@ extern "C" int wfm_sosfilt(const double* sos, int32_t n_sections, double initial
   // before cudaMemcpyAsync returns, so no synchronisation is needed for them)
   if (zi) {
     e = cudaMallocAsync(&d_zi, state_bytes, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, state_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = upload_small(d_zi, zi, state_bytes, st);
   }
   if (e == cudaSuccess && zf) e = cudaMallocAsync(&d_zf, state_bytes, st);
   if (e == cudaSuccess && n > 0) {
@@ -1074,7 +1113,7 @@ extern "C" int wfm_lfilter_mode(const double* b, int32_t nb, const double* a, in
   cudaError_t e = cudaSuccess;
   if (zi && M > 0) {
     e = cudaMallocAsync(&d_zi, state_bytes, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_zi, zi, sizeof(double) * M * n_sig, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = upload_small(d_zi, zi, sizeof(double) * M * n_sig, st);
   }
   if (e == cudaSuccess && zf && M > 0) e = cudaMallocAsync(&d_zf, state_bytes, st);
   if (e == cudaSuccess && mode == WFM_IIR_SCAN && M >= 1 && M <= kMaxJoint && n > 0) {

@@ -187,7 +187,7 @@ def _combined(filters):
     if hit is None:
         b, a = combine_filters(filters)
         z, p, k = tf2zpk(b, a)
-        hit = (b, a, bool(np.all(np.abs(p) < 1)))
+        hit = (b, a, bool(np.all(np.abs(p) < 1)), {})  # the dict: lfiltic states per `initial` level
         if len(_COMBINED) >= 64:
             _COMBINED.pop(next(iter(_COMBINED)))
         _COMBINED[key] = hit
@@ -317,12 +317,31 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
     ``iir_mode`` (not in the reference): 'exact' = the sequential kernel, bit-identical to scipy.signal.lfilter;
     'scan' = block-parallel (combined filters up to order 4), 40 x faster on long batches, equal up to the filter's
     rounding-noise gain; 'auto' = exact up to ``dsp.IIR_AUTO_EXACT_MAX`` samples per signal."""
-    dev, was_np = _to_device(sig)
+    # the caller's tensor is only read: each stage writes a buffer of this call (the first one a fresh one), so a CUDA
+    # input costs no defensive copy (819 MB read + written for cfg4's 256 x 400 000 samples: as long as the IIR itself)
+    import torch
+    dev, was_np = _to_device(sig, copy=False)
+    owned = was_np or not isinstance(sig, torch.Tensor) or dev.data_ptr() != sig.data_ptr()
     zf = None
+
+    def target(cur):
+        if owned:
+            return cur
+        out = torch.empty_like(cur)
+        return out if out.stride() == cur.stride() else None
+
     if filters is not None:
-        b, a, stable = _combined(filters)
+        b, a, stable, zi_of = _combined(filters)
         if not stable:
             warnings.warn('Warning: filter is unstable')
+        if zi is None and initial_x is None and initial_y is None:
+            # the steady state for a constant level: remembered per filter list (scipy's lfiltic costs more host time
+            # than the block-parallel filter takes on the device)
+            zi = zi_of.get(float(initial))
+            if zi is None:
+                zi = lfiltic(b, a, np.full((len(a) - 1, ), initial), np.full((len(b) - 1, ), initial))
+                if len(zi_of) < 64:
+                    zi_of[float(initial)] = zi
         if zi is None:
             if initial_x is None:
                 initial_x = np.full((len(b) - 1, ), initial)
@@ -333,14 +352,26 @@ def predistort(sig, filters: list | None = None, ker=None, initial: float = 0.0,
             else:
                 initial_y = np.asarray(initial_y)[:len(a) - 1]
             zi = lfiltic(b, a, initial_y, initial_x)
+        out = target(dev)
+        if out is None:  # a view whose layout empty_like does not reproduce: filter a private copy in place
+            dev = dev.contiguous().clone()
+            out = dev
         # (the final state costs a device->host copy and a synchronisation: only when it is asked for)
-        dev, zf = dsp.lfilter_device(b, a, dev, zi=zi, want_zf=return_zf, mode=iir_mode)
+        dev, zf = dsp.lfilter_device(b, a, dev, zi=zi, want_zf=return_zf, mode=iir_mode, out=out)
+        owned = True
         if zf is not None and dev.dim() == 1:
             zf = zf[0]
     if ker is not None:
         ker = np.ascontiguousarray(np.asarray(ker, dtype=np.float64))
+        out = target(dev)
+        if out is None:
+            dev = dev.contiguous().clone()
+            out = dev
         # the zero padding of the linear convolution exists only inside the transform
-        dev = _kernel_response(ker, dev.shape[-1], dev.device.index).apply(dev, out=dev)
+        dev = _kernel_response(ker, dev.shape[-1], dev.device.index).apply(dev, out=out)
+        owned = True
+    if not owned:
+        dev = dev.clone()  # nothing ran: the reference still returns a new array
     out = _from_device(dev, was_np)
     return (out, zf) if return_zf else out
 

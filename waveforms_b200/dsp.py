@@ -139,9 +139,9 @@ def apply_channel_filters(out, batch, waveforms, mode=None):
 LFILTER_SCAN_MAX_ORDER = 4
 
 
-def lfilter_device(b, a, x, zi=None, want_zf=False, mode='exact'):
+def lfilter_device(b, a, x, zi=None, want_zf=False, mode='exact', out=None):
     """scipy.signal.lfilter(b, a, x, zi=zi) on a CUDA f64 tensor (n,) or
-    (n_sig, n), in place.  Returns (y, zf).
+    (n_sig, n), in place — or into ``out`` (same shape and row stride), which leaves ``x`` untouched.  Returns (y, zf).
 
     mode: 'exact' (sequential kernel, bit-identical to SciPy) | 'scan' (block-parallel, orders 1..4, equal up to the
     filter's rounding-noise gain; higher orders run the sequential kernel) | 'auto' | None (= ``IIR_MODE``), as for
@@ -159,13 +159,17 @@ def lfilter_device(b, a, x, zi=None, want_zf=False, mode='exact'):
         zi_arr = np.ascontiguousarray(
             np.broadcast_to(np.asarray(zi, dtype=np.float64), (n_sig, order)))
     zf = np.zeros((n_sig, max(order, 0))) if want_zf else None
+    y2 = x2
+    if out is not None:
+        y2 = out if out.dim() == 2 else out.unsqueeze(0)
+        assert y2.dtype == torch.float64 and y2.shape == x2.shape and y2.stride() == x2.stride()
     rc = lib.wfm_lfilter_mode(b.ctypes.data, len(b), a.ctypes.data, len(a),
-                              x2.data_ptr(), x2.data_ptr(), n_sig, n, x2.stride(0),
+                              x2.data_ptr(), y2.data_ptr(), n_sig, n, x2.stride(0),
                               zi_arr.ctypes.data if zi_arr is not None else None,
                               zf.ctypes.data if zf is not None and order > 0 else None,
                               _IIR_MODES[resolve_iir_mode(n, mode)], _stream(torch, x.device))
     engine._check(rc)
-    return x, zf
+    return (x if out is None else out), zf
 
 
 def fft_filter_device(x, H, out=None):
