@@ -206,3 +206,21 @@ def test_compile_time_plans_with_odd_batches_and_strided_rows(n, nsig):
     got = fft_filter_device(view, H, out=view).cpu().numpy()
     assert rel_err(got, want) <= FP64_TOL
     assert np.array_equal(dev[:, n:].cpu().numpy(), buf[:, n:])
+
+
+def test_reflection_functions_leave_a_cuda_input_untouched():
+    """reflection / correct_reflection without ``out``: a CUDA input is read, the result is a new tensor (no defensive
+    copy of the input first); with NumPy input and with ``out`` the results are the same."""
+    import torch
+    from waveforms_b200 import distortion as D
+    rng = np.random.default_rng(33)
+    x = rng.standard_normal((3, 4000))
+    for fn in (D.reflection, D.correct_reflection):
+        dev = torch.from_numpy(x).cuda()
+        got = fn(dev, 0.05, 13.3e-9, 2e9)
+        assert np.array_equal(dev.cpu().numpy(), x) and got.data_ptr() != dev.data_ptr()
+        want = fn(x.copy(), 0.05, 13.3e-9, 2e9)
+        assert np.array_equal(got.cpu().numpy(), want)
+        out = torch.empty_like(dev)
+        assert fn(dev, 0.05, 13.3e-9, 2e9, out=out).data_ptr() == out.data_ptr() and np.array_equal(out.cpu().numpy(), want)
+        assert np.array_equal(fn(dev, 0.05, 13.3e-9, 2e9, out=dev).cpu().numpy(), want)   # in place on request

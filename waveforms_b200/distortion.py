@@ -40,6 +40,15 @@ def _to_device(sig, copy=True):
     return torch.from_numpy(arr).cuda(), True
 
 
+def _fresh_out(sig, dev):
+    """Where a filter writes when the caller named no output: the uploaded copy of a NumPy input is ours to overwrite;
+    a CUDA input is only read and the result goes into a new tensor (no defensive copy of the input first)."""
+    import torch
+    if not isinstance(sig, torch.Tensor) or dev.data_ptr() != sig.data_ptr():
+        return dev
+    return torch.empty(dev.shape, dtype=dev.dtype, device=dev.device)
+
+
 def _from_device(t, was_numpy):
     return t.cpu().numpy() if was_numpy else t
 
@@ -148,8 +157,8 @@ def reflection_filter(f, A, tau):
 def reflection(sig, A, tau, sample_rate, out=None):
     """ifft(fft(sig) * H).real on the GPU (reference :208-210).  ``out``: CUDA tensor
     that receives the result when ``sig`` is a CUDA tensor (may be ``sig`` itself)."""
-    dev, was_np = _to_device(sig, copy=out is None)
-    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=False, out=dev if out is None else out)
+    dev, was_np = _to_device(sig, copy=False)
+    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=False, out=_fresh_out(sig, dev) if out is None else out)
     return _from_device(res, was_np)
 
 
@@ -162,8 +171,8 @@ def correct_reflection(sig, A, tau, sample_rate=None, out=None):
         return 1 / (1 - A) * sig - A / (1 - A) * (sig >> tau)
     if sample_rate is None:
         raise ValueError('sample_rate is not given')
-    dev, was_np = _to_device(sig, copy=out is None)
-    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=True, out=dev if out is None else out)
+    dev, was_np = _to_device(sig, copy=False)
+    res = dsp.reflection_device(dev, A, tau, sample_rate, inverse=True, out=_fresh_out(sig, dev) if out is None else out)
     return _from_device(res, was_np)
 
 
